@@ -1,0 +1,159 @@
+/* orion_gpu.h -- C ABI of liborion_gpu.so, the B200 (sm_100a) implementation of
+ * motroy/orion-kmer's k-mer hot path.
+ *
+ * The reference (a pure-Rust crate) has no FFI seam of its own; its hot path is the inner
+ * loop  normalize -> windows(k) -> seq_to_u64 -> canonical_u64 -> sink  repeated in five
+ * drivers.  This header is the batch-level boundary a Rust host would bind with
+ * `extern "C"` (see INTEGRATION.md for the binding) -- one group of calls per sink.  Every
+ * entry cites the reference code it replaces (paths relative to orion-kmer/ in the
+ * reference repository).
+ *
+ * Conventions
+ *   - every function returns an ok_status (0 = success); ok_last_error() gives the
+ *     thread-local message, worded like the reference's errors.rs where one exists.
+ *   - no C++ types, exceptions or panics cross the boundary.
+ *   - batch layout: one contiguous byte buffer of sequences + n_records+1 uint64 offsets
+ *     (offsets[0] == 0, record r = bases[offsets[r] .. offsets[r+1])).
+ *   - norm_mode OK_NORM_NORMALIZED = count/build/classify semantics: the host has already
+ *     removed whitespace (needletail normalize(false)); the device maps acgt/ACGT and u/U->T,
+ *     every other byte invalidates the windows that contain it.  OK_NORM_RAW = query
+ *     semantics (query.rs:66,81): bytes as they are, only acgtACGT valid.
+ *   - result arrays returned through `uint64_t**` are page-locked host memory owned by the
+ *     library; release them with ok_free().  Handles are opaque, owned by the caller, and
+ *     must not be used from two threads at once.
+ *   - one process drives one GPU (ok_init picks it); multi-GPU runs are one process per GPU
+ *     with the k-mer exchange between the *_route / *_add_kmers calls.
+ *   - there is no CPU fallback: without a usable CUDA device every compute call fails with
+ *     OK_ERR_NO_DEVICE.
+ */
+#ifndef ORION_GPU_H
+#define ORION_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ok_status {
+    OK_SUCCESS = 0,
+    OK_ERR_INVALID_KMER_SIZE = 1,   /* errors.rs:6-7   InvalidKmerSize(k)            */
+    OK_ERR_KMER_SIZE_MISMATCH = 2,  /* errors.rs:24-25 KmerSizeMismatch(k1,k2)       */
+    OK_ERR_INVALID_ARGUMENT = 3,
+    OK_ERR_OUT_OF_MEMORY = 4,
+    OK_ERR_CUDA = 5,
+    OK_ERR_NO_DEVICE = 6,
+    OK_ERR_INTERNAL = 7
+} ok_status;
+
+typedef enum ok_norm_mode { OK_NORM_NORMALIZED = 0, OK_NORM_RAW = 1 } ok_norm_mode;
+
+typedef struct ok_counter ok_counter; /* replaces DashMap<u64,AtomicUsize>  count.rs:48      */
+typedef struct ok_set ok_set;         /* replaces HashSet<u64> of one reference, db_types.rs:13 */
+
+/* ---- lifecycle (commands/mod.rs:10-33 dispatch_command) ------------------------------- */
+int ok_init(const int* device_ids, int n_devices); /* n_devices must be 1; NULL -> device 0 */
+int ok_shutdown(void);
+const char* ok_last_error(void);
+const char* ok_version(void);
+/* number of kernels this library has launched since ok_init (bench.py's gpu_launches) */
+uint64_t ok_launch_count(void);
+int ok_synchronize(void);
+
+/* page-locked host buffers for batches and results */
+int ok_host_alloc(void** out, uint64_t bytes);
+int ok_host_free(void* p);
+int ok_free(void* p); /* result arrays handed out by the library */
+
+/* ---- k-mer arithmetic on the host (src/kmer.rs, public API of the crate) --------------- */
+/* kmer.rs:37-57  returns 1 and writes *out for Some(v), 0 for None */
+int ok_seq_to_u64(const uint8_t* seq, uint64_t len, uint8_t k, uint64_t* out);
+/* kmer.rs:61-75  writes k bytes; OK_ERR_INVALID_KMER_SIZE where the reference panics */
+int ok_u64_to_seq(uint64_t kmer, uint8_t k, uint8_t* out);
+/* kmer.rs:79-94 */
+int ok_reverse_complement_u64(uint64_t kmer, uint8_t k, uint64_t* out);
+/* kmer.rs:99-106 */
+int ok_canonical_u64(uint64_t kmer, uint8_t k, uint64_t* out);
+
+/* ---- counter (count.rs:23-38,48,106-119 ; classify.rs:135-199) ------------------------- */
+/* k outside 1..=32 -> OK_ERR_INVALID_KMER_SIZE (count.rs:43-45).  capacity_hint = expected
+ * number of distinct canonical k-mers (0 = unknown; the table grows as needed). */
+int ok_counter_create(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_counter** out);
+/* process_sequence_chunk over every record of the batch; host buffers (pinned or pageable) */
+int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const uint64_t* rec_offsets,
+                         uint64_t n_records);
+/* same, buffers already resident in device memory (n_bases == rec_offsets[n_records]) */
+int ok_counter_add_batch_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                                const uint64_t* d_rec_offsets, uint64_t n_records);
+/* multi-GPU: add canonical k-mers received from peers (device pointer), +1 each */
+int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers, uint64_t n);
+/* multi-GPU: extract the batch's canonical k-mers and bucket them by owner rank
+ * (owner = key range, balanced by the canonical-k-mer prior).  d_out must hold n_bases
+ * entries; on return out_counts[r] (host, n_ranks entries) k-mers for rank r are stored
+ * contiguously, rank after rank.  The caller exchanges them (NCCL all-to-all) and feeds
+ * what it receives to ok_counter_add_kmers_device. */
+int ok_counter_route_batch_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                                  const uint64_t* d_rec_offsets, uint64_t n_records,
+                                  int n_ranks, uint64_t* d_out, uint64_t* out_counts);
+/* count.rs:106-119: entries with count >= min_count, ascending by k-mer value. */
+int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** kmers, uint64_t** counts,
+                      uint64_t* n);
+/* same, results left in device memory owned by the handle (valid until the next call on it) */
+int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t** d_kmers,
+                             const uint64_t** d_counts, uint64_t* n);
+/* forget all counts, keep the allocation (bench loops) */
+int ok_counter_clear(ok_counter* c);
+int ok_counter_destroy(ok_counter* c);
+
+typedef struct ok_counter_stats {
+    uint64_t n_slots;        /* table slots                                   */
+    uint64_t n_distinct;     /* occupied slots                                */
+    uint64_t n_windows;      /* valid windows added so far (sum of counts)    */
+    uint64_t n_bases;        /* bases seen so far                             */
+    uint64_t max_displacement;
+    uint64_t n_spilled;      /* inserts that overflowed the probe limit       */
+    uint64_t n_grows;        /* table rebuilds                                */
+    float ms_insert;         /* device time of the last add_batch kernels     */
+    float ms_readout;        /* device time of the last finish kernels        */
+    float ms_fill;           /* device time of the last table fill / rebuild  */
+} ok_counter_stats;
+int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out);
+
+/* ---- k-mer sets (build.rs:23-78,95-116 ; db_types.rs:38-58) ---------------------------- */
+int ok_set_create(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_set** out);
+int ok_set_add_batch(ok_set* s, const uint8_t* bases, const uint64_t* rec_offsets,
+                     uint64_t n_records);                  /* DashSet::insert build.rs:55 */
+/* a set from an existing sorted, duplicate-free host array (a reference loaded from a .db) */
+int ok_set_from_sorted(uint8_t k, const uint64_t* kmers, uint64_t n, ok_set** out);
+int ok_set_size(ok_set* s, uint64_t* n);                   /* HashSet::len                */
+int ok_set_k(ok_set* s, uint8_t* k);
+/* sorted ascending copy on the host (build_tests.rs compares decoded set contents) */
+int ok_set_export(ok_set* s, uint64_t** kmers, uint64_t* n);
+/* db_types.rs:43-48 get_all_kmers_unified ; all sets must share k */
+int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out);
+int ok_set_destroy(ok_set* s);
+
+/* ---- set algebra (compare.rs:51-66) ------------------------------------------------------ */
+/* |A n B| ; k mismatch -> OK_ERR_KMER_SIZE_MISMATCH (compare.rs:37-39) */
+int ok_set_intersection_size(ok_set* a, ok_set* b, uint64_t* out);
+/* sizes[n] and the full symmetric n*n matrix of intersection sizes (row-major) */
+int ok_sets_all_vs_all(ok_set* const* sets, uint64_t n, uint64_t* sizes, uint64_t* inter);
+
+/* ---- probes (query.rs:79-108 ; classify.rs:224-236) -------------------------------------- */
+/* hits_per_read[r] = number of windows of read r whose canonical k-mer is in the set */
+int ok_probe_reads(ok_set* s, int norm_mode, const uint8_t* bases, const uint64_t* rec_offsets,
+                   uint64_t n_records, uint32_t* hits_per_read);
+/* matched = |{i : kmers[i] in ref}| , depth_sum = sum of counts[i] over those */
+int ok_probe_counts(ok_set* ref, const uint64_t* kmers, const uint64_t* counts, uint64_t n,
+                    uint64_t* matched, uint64_t* depth_sum);
+
+/* ---- standalone 2-bit packing kernel (north-star subsystem 1) ---------------------------- */
+/* d_codes: one uint64 per 32 bases, first base in the top two bits; d_valid: one uint32 per
+ * 32 bases, first base in the top bit.  Both arrays hold ceil(n_bases/32) words. */
+int ok_pack_2bit_device(const uint8_t* d_bases, uint64_t n_bases, int norm_mode,
+                        uint64_t* d_codes, uint32_t* d_valid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORION_GPU_H */

@@ -1,0 +1,507 @@
+"""orion_kmer_b200 -- B200-native k-mer hot path of orion-kmer behind a C ABI.
+
+This module is the thin host mirror used by tests and bench.py: ctypes over
+include/orion_gpu.h (liborion_gpu.so, CUDA sm_100a) and over the host helpers
+(liborion_host.so: FASTA/FASTQ framing, TSV formatting, synthetic workloads), shaped like the
+reference's drivers (count.rs, build.rs, compare.rs, query.rs, classify.rs, db_types.rs).
+
+There is no CPU fallback: if liborion_gpu.so is missing or no CUDA device is present, compute
+calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+NORMALIZED, RAW = 0, 1
+
+OK_SUCCESS = 0
+OK_ERR_INVALID_KMER_SIZE = 1
+OK_ERR_KMER_SIZE_MISMATCH = 2
+OK_ERR_INVALID_ARGUMENT = 3
+OK_ERR_OUT_OF_MEMORY = 4
+OK_ERR_CUDA = 5
+OK_ERR_NO_DEVICE = 6
+OK_ERR_INTERNAL = 7
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+vp = C.c_void_p
+
+
+class OrionError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+class InvalidKmerSize(OrionError, ValueError):   # errors.rs:6-7
+    pass
+
+
+class KmerSizeMismatch(OrionError, ValueError):  # errors.rs:24-25
+    pass
+
+
+class FastxError(ValueError):
+    pass
+
+
+class CounterStats(C.Structure):
+    _fields_ = [("n_slots", C.c_uint64), ("n_distinct", C.c_uint64), ("n_windows", C.c_uint64),
+                ("n_bases", C.c_uint64), ("max_displacement", C.c_uint64), ("n_spilled", C.c_uint64),
+                ("n_grows", C.c_uint64), ("ms_insert", C.c_float), ("ms_readout", C.c_float),
+                ("ms_fill", C.c_float)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+# name -> (restype, argtypes); every symbol include/orion_gpu.h declares
+ABI = {
+    "ok_init": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "ok_shutdown": (C.c_int, []),
+    "ok_last_error": (C.c_char_p, []),
+    "ok_version": (C.c_char_p, []),
+    "ok_launch_count": (C.c_uint64, []),
+    "ok_synchronize": (C.c_int, []),
+    "ok_host_alloc": (C.c_int, [C.POINTER(vp), C.c_uint64]),
+    "ok_host_free": (C.c_int, [vp]),
+    "ok_free": (C.c_int, [vp]),
+    "ok_seq_to_u64": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint8, u64p]),
+    "ok_u64_to_seq": (C.c_int, [C.c_uint64, C.c_uint8, C.c_char_p]),
+    "ok_reverse_complement_u64": (C.c_int, [C.c_uint64, C.c_uint8, u64p]),
+    "ok_canonical_u64": (C.c_int, [C.c_uint64, C.c_uint8, u64p]),
+    "ok_counter_create": (C.c_int, [C.c_uint8, C.c_int, C.c_uint64, C.POINTER(vp)]),
+    "ok_counter_add_batch": (C.c_int, [vp, vp, vp, C.c_uint64]),
+    "ok_counter_add_batch_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64]),
+    "ok_counter_add_kmers_device": (C.c_int, [vp, vp, C.c_uint64]),
+    "ok_counter_route_batch_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp]),
+    "ok_counter_finish": (C.c_int, [vp, C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]),
+    "ok_counter_finish_device": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp), u64p]),
+    "ok_counter_clear": (C.c_int, [vp]),
+    "ok_counter_destroy": (C.c_int, [vp]),
+    "ok_counter_get_stats": (C.c_int, [vp, C.POINTER(CounterStats)]),
+    "ok_set_create": (C.c_int, [C.c_uint8, C.c_int, C.c_uint64, C.POINTER(vp)]),
+    "ok_set_add_batch": (C.c_int, [vp, vp, vp, C.c_uint64]),
+    "ok_set_from_sorted": (C.c_int, [C.c_uint8, vp, C.c_uint64, C.POINTER(vp)]),
+    "ok_set_size": (C.c_int, [vp, u64p]),
+    "ok_set_k": (C.c_int, [vp, u8p]),
+    "ok_set_export": (C.c_int, [vp, C.POINTER(u64p), u64p]),
+    "ok_set_union": (C.c_int, [C.POINTER(vp), C.c_uint64, C.POINTER(vp)]),
+    "ok_set_destroy": (C.c_int, [vp]),
+    "ok_set_intersection_size": (C.c_int, [vp, vp, u64p]),
+    "ok_sets_all_vs_all": (C.c_int, [C.POINTER(vp), C.c_uint64, vp, vp]),
+    "ok_probe_reads": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, vp]),
+    "ok_probe_counts": (C.c_int, [vp, vp, vp, C.c_uint64, u64p, u64p]),
+    "ok_pack_2bit_device": (C.c_int, [vp, C.c_uint64, C.c_int, vp, vp]),
+}
+# internal test hooks (not in include/)
+_HOOKS = {
+    "okx_emulate_extract": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64, C.c_uint, C.c_int, vp, C.c_uint64, u64p]),
+    "okx_emulate_table": (C.c_int, [vp, C.c_uint64, C.c_uint, C.c_int, C.c_uint64, C.c_uint, C.c_uint64, vp, vp, u64p, u64p]),
+    "okx_device_extract": (C.c_int, [vp, vp, C.c_uint64, C.c_uint, C.c_int, vp, C.c_uint64, u64p]),
+}
+
+_gpu = None
+_host = None
+
+
+def gpu_library_path():
+    return _build.SO
+
+
+def lib():
+    """liborion_gpu.so; raises when it is not built (no CPU fallback exists)."""
+    global _gpu
+    if _gpu is None:
+        if not os.path.exists(_build.SO):
+            raise OrionError(OK_ERR_NO_DEVICE,
+                             f"{_build.SO} is missing: build it with __graft_entry__.build() "
+                             "(there is no CPU fallback)")
+        L = C.CDLL(_build.SO)
+        for name, (res, args) in {**ABI, **_HOOKS}.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _gpu = L
+    return _gpu
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        so = os.path.join(_HERE, "liborion_host.so")
+        if not os.path.exists(so):
+            build_host()
+        L = C.CDLL(so)
+        L.okh_fastx_parse.restype = vp
+        L.okh_fastx_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_int)]
+        for n in ("okh_batch_n_records", "okh_batch_n_bases"):
+            getattr(L, n).restype = C.c_uint64
+            getattr(L, n).argtypes = [vp]
+        for n in ("okh_batch_bases", "okh_batch_offsets", "okh_batch_ids", "okh_batch_id_offsets"):
+            getattr(L, n).restype = vp
+            getattr(L, n).argtypes = [vp]
+        L.okh_batch_free.argtypes = [vp]
+        L.okh_format_counts.restype = C.c_uint64
+        L.okh_format_counts.argtypes = [vp, vp, C.c_uint64, C.c_uint, vp]
+        L.okh_synth_genome.argtypes = [C.c_uint64, C.c_uint64, vp]
+        L.okh_synth_reads.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
+                                      C.c_uint32, C.c_uint32, vp, C.c_int]
+        L.okh_synth_mutate.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, vp]
+        _host = L
+    return _host
+
+
+def build_host(force=False):
+    import subprocess
+    src = os.path.join(_HERE, "csrc", "host", "orion_host.cpp")
+    so = os.path.join(_HERE, "liborion_host.so")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-pthread",
+                               "-shared", "-o", so, src])
+    return so
+
+
+def _check(rc):
+    if rc == OK_SUCCESS:
+        return
+    msg = lib().ok_last_error().decode()
+    if rc == OK_ERR_INVALID_KMER_SIZE:
+        raise InvalidKmerSize(rc, msg)
+    if rc == OK_ERR_KMER_SIZE_MISMATCH:
+        raise KmerSizeMismatch(rc, msg)
+    raise OrionError(rc, msg)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(vp)
+
+
+def _copy_out(ptr, n, ctype, dtype):
+    """numpy copy of n elements at a C pointer (which may be NULL when n == 0)"""
+    n = int(n)
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).copy()
+
+
+def init(device=0):
+    dev = (C.c_int * 1)(device)
+    _check(lib().ok_init(dev, 1))
+
+
+def launch_count():
+    return int(lib().ok_launch_count())
+
+
+# ---- src/kmer.rs -----------------------------------------------------------------------------
+def seq_to_u64(seq: bytes, k: int):
+    out = C.c_uint64()
+    if not 0 <= k <= 255:
+        return None
+    return out.value if lib().ok_seq_to_u64(seq, len(seq), k, C.byref(out)) else None
+
+
+def u64_to_seq(v: int, k: int) -> bytes:
+    if not 0 <= k <= 255:
+        raise InvalidKmerSize(OK_ERR_INVALID_KMER_SIZE, f"Invalid k-mer length for decoding: {k}")
+    buf = C.create_string_buffer(33)
+    _check(lib().ok_u64_to_seq(v, k, buf))
+    return buf.raw[:k]
+
+
+def reverse_complement_u64(v: int, k: int) -> int:
+    out = C.c_uint64()
+    _check(lib().ok_reverse_complement_u64(v, k if 0 <= k <= 255 else 0, C.byref(out)))
+    return out.value
+
+
+def canonical_u64(v: int, k: int) -> int:
+    out = C.c_uint64()
+    _check(lib().ok_canonical_u64(v, k if 0 <= k <= 255 else 0, C.byref(out)))
+    return out.value
+
+
+# ---- needletail-shaped framing (host) -------------------------------------------------------------
+class Batch:
+    """C-ABI batch: concatenated bases + n+1 offsets (+ record ids)."""
+
+    def __init__(self, bases, offsets, ids=None):
+        self.bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.ids = ids
+
+    @property
+    def n_records(self):
+        return len(self.offsets) - 1
+
+
+def parse_fastx(content: bytes, norm_mode=NORMALIZED) -> Batch:
+    """parse_fastx_reader (+ whitespace removal of normalize(false) when NORMALIZED)."""
+    H = host_lib()
+    st = C.c_int()
+    h = H.okh_fastx_parse(content, len(content), 1 if norm_mode == NORMALIZED else 0, C.byref(st))
+    try:
+        if st.value:
+            raise FastxError({1: "empty file", 2: "invalid start byte", 3: "malformed FASTQ"}[st.value])
+        n, nb = H.okh_batch_n_records(h), H.okh_batch_n_bases(h)
+        bases = _copy_out(H.okh_batch_bases(h), nb, C.c_uint8, np.uint8)
+        off = _copy_out(H.okh_batch_offsets(h), n + 1, C.c_uint64, np.uint64)
+        ido = _copy_out(H.okh_batch_id_offsets(h), n + 1, C.c_uint64, np.uint64)
+        blob = bytes(_copy_out(H.okh_batch_ids(h), int(ido[-1]), C.c_uint8, np.uint8))
+        ids = [blob[int(ido[i]):int(ido[i + 1])] for i in range(n)]
+        return Batch(bases, off, ids)
+    finally:
+        H.okh_batch_free(h)
+
+
+def format_counts(kmers, counts, k) -> bytes:
+    """count.rs:127-135"""
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    buf = C.create_string_buffer(len(kmers) * (k + 22) + 1)
+    n = host_lib().okh_format_counts(_ptr(kmers), _ptr(counts), len(kmers), k, buf)
+    return buf.raw[:n]
+
+
+# ---- counter (count.rs) ------------------------------------------------------------------------------
+def _take(pk, pc, n):
+    n = int(n)
+    L = lib()
+    keys = _copy_out(pk, n, C.c_uint64, np.uint64)
+    counts = _copy_out(pc, n, C.c_uint64, np.uint64) if pc is not None else None
+    _check(L.ok_free(C.cast(pk, vp)))
+    if pc is not None:
+        _check(L.ok_free(C.cast(pc, vp)))
+    return keys, counts
+
+
+class KmerCounter:
+    """DashMap<u64, AtomicUsize> of run_count (count.rs:48) on the device."""
+
+    def __init__(self, k, norm_mode=NORMALIZED, capacity_hint=0):
+        h = vp()
+        if not 0 <= k <= 255:
+            raise InvalidKmerSize(OK_ERR_INVALID_KMER_SIZE, f"Invalid K-mer size: {k}. Must be between 1 and 32.")
+        _check(lib().ok_counter_create(k, norm_mode, capacity_hint, C.byref(h)))
+        self._h, self.k, self.norm_mode = h, k, norm_mode
+
+    def add_batch(self, bases, offsets):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _check(lib().ok_counter_add_batch(self._h, _ptr(bases), _ptr(offsets), len(offsets) - 1))
+
+    def add_batch_ptr(self, bases_ptr, offsets_ptr, n_records):
+        """raw host pointers (e.g. pinned torch tensors)"""
+        _check(lib().ok_counter_add_batch(self._h, bases_ptr, offsets_ptr, n_records))
+
+    def add_batch_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records):
+        _check(lib().ok_counter_add_batch_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records))
+
+    def add_kmers_device(self, d_kmers_ptr, n):
+        _check(lib().ok_counter_add_kmers_device(self._h, d_kmers_ptr, n))
+
+    def add_fastx(self, content: bytes):
+        b = parse_fastx(content, self.norm_mode)
+        self.add_batch(b.bases, b.offsets)
+
+    def finish(self, min_count=1):
+        pk, pc, n = u64p(), u64p(), C.c_uint64()
+        _check(lib().ok_counter_finish(self._h, min_count, C.byref(pk), C.byref(pc), C.byref(n)))
+        return _take(pk, pc, n.value)
+
+    def finish_raw(self, min_count=1):
+        """-> (kmers_ptr, counts_ptr, n): page-locked host arrays, release with free_result()"""
+        pk, pc, n = u64p(), u64p(), C.c_uint64()
+        _check(lib().ok_counter_finish(self._h, min_count, C.byref(pk), C.byref(pc), C.byref(n)))
+        return pk, pc, n.value
+
+    @staticmethod
+    def free_result(pk, pc):
+        _check(lib().ok_free(C.cast(pk, vp)))
+        _check(lib().ok_free(C.cast(pc, vp)))
+
+    def finish_device(self, min_count=1):
+        dk, dc, n = vp(), vp(), C.c_uint64()
+        _check(lib().ok_counter_finish_device(self._h, min_count, C.byref(dk), C.byref(dc), C.byref(n)))
+        return dk.value, dc.value, n.value
+
+    def clear(self):
+        _check(lib().ok_counter_clear(self._h))
+
+    def stats(self):
+        s = CounterStats()
+        _check(lib().ok_counter_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ok_counter_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def count_fastx(k, contents, min_count=1, capacity_hint=0):
+    """run_count (count.rs:40-141) over in-memory files -> (sorted kmers, counts)"""
+    c = KmerCounter(k, NORMALIZED, capacity_hint)
+    try:
+        for content in contents:
+            c.add_fastx(content)
+        return c.finish(min_count)
+    finally:
+        c.close()
+
+
+def run_count(k, contents, min_count=1) -> bytes:
+    """the TSV text run_count writes (count.rs:127-135)"""
+    kmers, counts = count_fastx(k, contents, min_count)
+    return format_counts(kmers, counts, k)
+
+
+# ---- sets (build.rs, db_types.rs, compare.rs, query.rs, classify.rs) ----------------------------------
+class KmerSet:
+    """HashSet<u64> of one reference (db_types.rs:13), device resident and sorted."""
+
+    def __init__(self, handle, k):
+        self._h, self.k = handle, k
+
+    @classmethod
+    def build(cls, k, norm_mode=NORMALIZED, capacity_hint=0):
+        h = vp()
+        if not 0 <= k <= 255:
+            raise InvalidKmerSize(OK_ERR_INVALID_KMER_SIZE, f"Invalid K-mer size: {k}. Must be between 1 and 32.")
+        _check(lib().ok_set_create(k, norm_mode, capacity_hint, C.byref(h)))
+        return cls(h, k)
+
+    @classmethod
+    def from_fastx(cls, k, content: bytes):
+        """process_sequences_for_file (build.rs:23-78)"""
+        s = cls.build(k)
+        b = parse_fastx(content, NORMALIZED)
+        s.add_batch(b.bases, b.offsets)
+        return s
+
+    @classmethod
+    def from_sorted(cls, k, kmers):
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        h = vp()
+        _check(lib().ok_set_from_sorted(k, _ptr(kmers), len(kmers), C.byref(h)))
+        return cls(h, k)
+
+    def add_batch(self, bases, offsets):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _check(lib().ok_set_add_batch(self._h, _ptr(bases), _ptr(offsets), len(offsets) - 1))
+
+    def __len__(self):
+        n = C.c_uint64()
+        _check(lib().ok_set_size(self._h, C.byref(n)))
+        return n.value
+
+    def to_array(self):
+        pk, n = u64p(), C.c_uint64()
+        _check(lib().ok_set_export(self._h, C.byref(pk), C.byref(n)))
+        return _take(pk, None, n.value)[0]
+
+    @staticmethod
+    def union(sets):
+        """get_all_kmers_unified (db_types.rs:43-48)"""
+        arr = (vp * len(sets))(*[s._h for s in sets])
+        h = vp()
+        _check(lib().ok_set_union(arr, len(sets), C.byref(h)))
+        return KmerSet(h, sets[0].k)
+
+    def intersection_size(self, other):
+        out = C.c_uint64()
+        _check(lib().ok_set_intersection_size(self._h, other._h, C.byref(out)))
+        return out.value
+
+    def probe_reads(self, bases, offsets, norm_mode=RAW):
+        """query.rs:79-108 per-read hit counts"""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        hits = np.zeros(len(offsets) - 1, dtype=np.uint32)
+        _check(lib().ok_probe_reads(self._h, norm_mode, _ptr(bases), _ptr(offsets), len(offsets) - 1, _ptr(hits)))
+        return hits
+
+    def probe_counts(self, kmers, counts):
+        """classify.rs:224-236 -> (matched, sum_depth)"""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        m, d = C.c_uint64(), C.c_uint64()
+        _check(lib().ok_probe_counts(self._h, _ptr(kmers), _ptr(counts), len(kmers), C.byref(m), C.byref(d)))
+        return m.value, d.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ok_set_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def all_vs_all(sets):
+    """sizes[n], intersection matrix[n,n] (compare.rs:51-60 for every pair)"""
+    n = len(sets)
+    arr = (vp * n)(*[s._h for s in sets])
+    sizes = np.zeros(n, dtype=np.uint64)
+    inter = np.zeros((n, n), dtype=np.uint64)
+    _check(lib().ok_sets_all_vs_all(arr, n, _ptr(sizes), _ptr(inter)))
+    return sizes, inter
+
+
+def compare(a: KmerSet, b: KmerSet):
+    """run_compare core (compare.rs:51-66); a and b are the unified sets of the two DBs"""
+    inter = a.intersection_size(b)
+    na, nb = len(a), len(b)
+    union = na + nb - inter
+    return dict(db1=na, db2=nb, intersection_size=inter, union_size=union,
+                jaccard_index=0.0 if union == 0 else inter / union)
+
+
+class KmerDbV2:
+    """db_types.rs:8-59"""
+
+    def __init__(self, k):
+        self.k = k
+        self.references = {}
+
+    def add_reference(self, name, kset):   # db_types.rs:38-40 (same name overwrites)
+        self.references[name] = kset
+
+    def get_all_kmers_unified(self):       # db_types.rs:43-48
+        if not self.references:
+            return KmerSet.from_sorted(self.k, np.zeros(0, np.uint64))
+        return KmerSet.union(list(self.references.values()))
+
+    def total_unique_kmers(self):          # db_types.rs:51-53
+        return len(self.get_all_kmers_unified())
+
+    def num_references(self):
+        return len(self.references)
+
+
+def run_build(k, files):
+    """run_build (build.rs:80-160) over {basename: content} -> KmerDbV2"""
+    if k == 0 or k > 32:
+        raise InvalidKmerSize(OK_ERR_INVALID_KMER_SIZE, f"Invalid K-mer size: {k}. Must be between 1 and 32.")
+    db = KmerDbV2(k)
+    for name, content in files.items():
+        db.add_reference(name, KmerSet.from_fastx(k, content))
+    return db
+
+
+def run_query(db: KmerDbV2, reads_content: bytes, min_hits=1):
+    """run_query (query.rs:24-134) -> (ids in input order, per-read hits)"""
+    unified = db.get_all_kmers_unified()
+    b = parse_fastx(reads_content, RAW)
+    hits = unified.probe_reads(b.bases, b.offsets, RAW)
+    return [i for i, h in zip(b.ids, hits) if h >= min_hits], hits

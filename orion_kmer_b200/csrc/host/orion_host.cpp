@@ -1,0 +1,217 @@
+// orion_host.cpp -- host-side pieces that sit ABOVE the C ABI (include/orion_gpu.h): what the
+// reference's Rust drivers do on the CPU before and after the device path.  Built with g++
+// into liborion_host.so; no CUDA here.
+//
+//   okh_fastx_to_batch    needletail parse_fastx_reader + the whitespace half of
+//                         normalize(false)  (count.rs:63-72, build.rs:42-48, query.rs:51-66)
+//                         -> the C-ABI batch layout (bases + offsets) and the record ids
+//   okh_format_counts     count.rs:127-135  "KMER\tcount\n"
+//   okh_synth_*           seeded synthetic workloads of SURVEY.md section 8(d) (SplitMix64)
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#define OKH_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+struct Batch {
+    std::vector<uint8_t> bases;
+    std::vector<uint64_t> offsets;
+    std::vector<uint8_t> ids;
+    std::vector<uint64_t> id_offsets;
+    Batch() : offsets(1, 0), id_offsets(1, 0) {}
+    void close_record() { offsets.push_back(bases.size()); }
+    void add_id(const uint8_t* p, size_t n) {
+        if (n && p[n - 1] == '\r') --n;
+        ids.insert(ids.end(), p, p + n);
+        id_offsets.push_back(ids.size());
+    }
+};
+
+enum { FX_OK = 0, FX_EMPTY = 1, FX_BAD_START = 2, FX_MALFORMED = 3 };
+
+inline bool is_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; }
+
+// one line = [p, e) without its '\n'; returns the start of the next line
+inline size_t next_line(const uint8_t* b, size_t len, size_t p, size_t* e) {
+    const uint8_t* nl = (const uint8_t*)memchr(b + p, '\n', len - p);
+    *e = nl ? (size_t)(nl - b) : len;
+    return nl ? *e + 1 : len;
+}
+
+void append_sequence(Batch& out, const uint8_t* p, size_t n, bool strip_ws) {
+    if (!strip_ws) { out.bases.insert(out.bases.end(), p, p + n); return; }
+    size_t old = out.bases.size();
+    out.bases.resize(old + n);
+    uint8_t* d = out.bases.data() + old;
+    size_t m = 0;
+    for (size_t i = 0; i < n; ++i) { uint8_t c = p[i]; d[m] = c; m += is_ws(c) ? 0 : 1; }
+    out.bases.resize(old + m);
+}
+
+int parse_fasta(const uint8_t* b, size_t len, bool strip_ws, Batch& out) {
+    size_t p = 0;
+    bool open = false;
+    size_t raw_begin = 0, raw_end = 0;  // raw mode: sequence region of the open record
+    auto close = [&]() {
+        if (!open) return;
+        if (!strip_ws) {  // raw bytes keep interior line breaks, lose the final end-of-line run
+            size_t e = raw_end;
+            while (e > raw_begin && (b[e - 1] == '\n' || b[e - 1] == '\r')) --e;
+            out.bases.insert(out.bases.end(), b + raw_begin, b + e);
+        }
+        out.close_record();
+        open = false;
+    };
+    while (p < len) {
+        size_t e, nx = next_line(b, len, p, &e);
+        if (b[p] == '>') {
+            close();
+            out.add_id(b + p + 1, e - p - 1);
+            open = true; raw_begin = raw_end = nx;
+        } else {
+            if (strip_ws) append_sequence(out, b + p, e - p, true);
+            raw_end = nx;
+        }
+        p = nx;
+    }
+    close();
+    return FX_OK;
+}
+
+int parse_fastq(const uint8_t* b, size_t len, bool strip_ws, Batch& out) {
+    size_t p = 0;
+    while (p < len) {
+        if (b[p] == '\n' || b[p] == '\r') { ++p; continue; }
+        if (b[p] != '@') return FX_MALFORMED;
+        size_t he, s0 = next_line(b, len, p, &he);
+        if (he >= len) return FX_MALFORMED;
+        size_t se, pl = next_line(b, len, s0, &se);
+        if (se >= len) return FX_MALFORMED;
+        size_t s1 = se; if (s1 > s0 && b[s1 - 1] == '\r') --s1;
+        if (pl >= len || b[pl] != '+') return FX_MALFORMED;
+        size_t pe, q0 = next_line(b, len, pl, &pe);
+        if (pe >= len) return FX_MALFORMED;
+        size_t qe, nx = next_line(b, len, q0, &qe);
+        size_t q1 = qe; if (q1 > q0 && b[q1 - 1] == '\r') --q1;
+        if (q1 - q0 != s1 - s0) return FX_MALFORMED;
+        out.add_id(b + p + 1, he - p - 1);
+        append_sequence(out, b + s0, s1 - s0, strip_ws);
+        out.close_record();
+        p = nx;
+    }
+    return FX_OK;
+}
+
+struct SplitMix64 {
+    uint64_t s;
+    explicit SplitMix64(uint64_t seed) : s(seed) {}
+    inline uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+};
+
+inline uint8_t comp(uint8_t c) {
+    switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return c; }
+}
+
+}  // namespace
+
+// ---- FASTA/FASTQ framing ------------------------------------------------------------------
+// strip_ws != 0: count/build/classify semantics (whitespace removed, as normalize(false) does;
+// the device handles case, U and invalid bytes).  strip_ws == 0: query semantics (raw bytes).
+OKH_EXPORT void* okh_fastx_parse(const uint8_t* buf, uint64_t len, int strip_ws, int* status) {
+    Batch* out = new Batch();
+    int st;
+    if (len == 0) st = FX_EMPTY;
+    else if (buf[0] == '>') st = parse_fasta(buf, (size_t)len, strip_ws != 0, *out);
+    else if (buf[0] == '@') st = parse_fastq(buf, (size_t)len, strip_ws != 0, *out);
+    else st = FX_BAD_START;
+    *status = st;
+    return out;
+}
+OKH_EXPORT uint64_t okh_batch_n_records(void* h) { return ((Batch*)h)->offsets.size() - 1; }
+OKH_EXPORT uint64_t okh_batch_n_bases(void* h) { return ((Batch*)h)->bases.size(); }
+OKH_EXPORT const uint8_t* okh_batch_bases(void* h) { return ((Batch*)h)->bases.data(); }
+OKH_EXPORT const uint64_t* okh_batch_offsets(void* h) { return ((Batch*)h)->offsets.data(); }
+OKH_EXPORT const uint8_t* okh_batch_ids(void* h) { return ((Batch*)h)->ids.data(); }
+OKH_EXPORT const uint64_t* okh_batch_id_offsets(void* h) { return ((Batch*)h)->id_offsets.data(); }
+OKH_EXPORT void okh_batch_free(void* h) { delete (Batch*)h; }
+
+// ---- count.rs:127-135 ------------------------------------------------------------------------
+OKH_EXPORT uint64_t okh_format_counts(const uint64_t* kmers, const uint64_t* counts, uint64_t n, unsigned k,
+                                      char* out) {
+    char* p = out;
+    for (uint64_t i = 0; i < n; ++i) {
+        for (unsigned j = 0; j < k; ++j) *p++ = "ACGT"[(kmers[i] >> (2 * (k - 1 - j))) & 3u];
+        *p++ = '\t';
+        char tmp[24]; int m = 0; uint64_t c = counts[i];
+        do { tmp[m++] = (char)('0' + c % 10); c /= 10; } while (c);
+        while (m) *p++ = tmp[--m];
+        *p++ = '\n';
+    }
+    return (uint64_t)(p - out);
+}
+
+// ---- synthetic workloads: SplitMix64, 2-bit fields low bits first -> ACGT ----
+OKH_EXPORT void okh_synth_genome(uint64_t seed, uint64_t n, uint8_t* out) {
+    SplitMix64 g(seed);
+    uint64_t i = 0;
+    while (i < n) {
+        uint64_t r = g.next();
+        for (int j = 0; j < 32 && i < n; ++j, ++i) out[i] = (uint8_t)"ACGT"[(r >> (2 * j)) & 3u];
+    }
+}
+
+// reads: start uniform, strand 50/50, substitution sub_ppm per million bases (uniform over the
+// other three), N n_ppm per million.  Each read has its own generator (seed, index), so the
+// output does not depend on the thread count.  out holds n_reads*read_len bytes, no separators.
+OKH_EXPORT void okh_synth_reads(const uint8_t* genome, uint64_t glen, uint64_t seed, uint64_t first_read,
+                                uint64_t n_reads, uint32_t read_len, uint32_t sub_ppm, uint32_t n_ppm,
+                                uint8_t* out, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t r = lo; r < hi; ++r) {
+            SplitMix64 g(seed ^ ((first_read + r + 1) * 0xD1B54A32D192ED03ull));
+            const uint64_t start = g.next() % (glen - read_len + 1);
+            const bool rev = g.next() & 1u;
+            uint8_t* o = out + r * (uint64_t)read_len;
+            for (uint32_t i = 0; i < read_len; ++i)
+                o[i] = rev ? comp(genome[start + read_len - 1 - i]) : genome[start + i];
+            for (uint32_t i = 0; i < read_len; ++i) {
+                const uint64_t x = g.next();
+                const uint32_t u = (uint32_t)(x % 1000000u);
+                if (u < n_ppm) o[i] = 'N';
+                else if (u < n_ppm + sub_ppm) {
+                    const char* alt = "ACGT";
+                    uint8_t c = o[i]; int pick = (int)((x >> 32) % 3u), seen = 0;
+                    for (int a = 0; a < 4; ++a) if ((uint8_t)alt[a] != c) { if (seen == pick) { o[i] = (uint8_t)alt[a]; break; } ++seen; }
+                }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, n_reads * t / n_threads, n_reads * (t + 1) / n_threads);
+    for (auto& t : th) t.join();
+}
+
+// descendant of a genome: every base substituted with probability sub_ppm per million
+OKH_EXPORT void okh_synth_mutate(const uint8_t* genome, uint64_t n, uint64_t seed, uint32_t sub_ppm, uint8_t* out) {
+    SplitMix64 g(seed);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t x = g.next();
+        uint8_t c = genome[i];
+        if ((uint32_t)(x % 1000000u) < sub_ppm) {
+            const char* alt = "ACGT"; int pick = (int)((x >> 32) % 3u), seen = 0;
+            for (int a = 0; a < 4; ++a) if ((uint8_t)alt[a] != c) { if (seen == pick) { c = (uint8_t)alt[a]; break; } ++seen; }
+        }
+        out[i] = c;
+    }
+}

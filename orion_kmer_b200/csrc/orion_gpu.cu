@@ -1,0 +1,924 @@
+// orion_gpu.cu -- C ABI (include/orion_gpu.h) over the sm_100a kernels in kernels.cuh.
+// Host-side runtime of the hot path: device buffers, streams, the copy/compute pipeline,
+// table sizing and growth.  No CPU fallback: every compute entry needs a CUDA device.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "orion_gpu.h"
+#include "kernels.cuh"
+
+#define OK_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+// ------------------------------------------------------------------ errors and globals --
+thread_local std::string g_err;
+int set_err(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return set_err(e_ == cudaErrorMemoryAllocation ? OK_ERR_OUT_OF_MEMORY : OK_ERR_CUDA, \
+                           "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                           cudaGetErrorString(e_));                                           \
+    } while (0)
+#define TRY(call) do { int r_ = (call); if (r_ != OK_SUCCESS) return r_; } while (0)
+
+int g_device = -1;
+int g_sms = 0;
+std::atomic<uint64_t> g_launches{0};
+std::mutex g_mu;
+
+#define LAUNCH(kern, grid, block, smem, stream, ...)                 \
+    do {                                                             \
+        kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+        g_launches.fetch_add(1, std::memory_order_relaxed);          \
+    } while (0)
+
+int ensure_init() {
+    if (g_device >= 0) return OK_SUCCESS;
+    return ok_init(nullptr, 0);
+}
+
+int invalid_k(unsigned k) {  // errors.rs:6-7
+    return set_err(OK_ERR_INVALID_KMER_SIZE, "Invalid K-mer size: %u. Must be between 1 and 32.", k);
+}
+
+inline unsigned grid_for(uint64_t n, unsigned per_block = 256, unsigned waves = 8) {
+    uint64_t need = (n + per_block - 1) / per_block;
+    uint64_t cap = (uint64_t)(g_sms > 0 ? g_sms : 148) * waves;
+    return (unsigned)std::max<uint64_t>(1, std::min(need, cap));
+}
+
+// --------------------------------------------------------------- pinned result buffers --
+struct PinnedBlock { void* p; size_t bytes; bool used; };
+std::vector<PinnedBlock> g_pool;
+
+int pool_alloc(void** out, size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    std::lock_guard<std::mutex> lk(g_mu);
+    PinnedBlock* best = nullptr;
+    for (auto& b : g_pool)
+        if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (!best || b.bytes < best->bytes)) best = &b;
+    if (best) { best->used = true; *out = best->p; return OK_SUCCESS; }
+    void* p = nullptr;
+    CU(cudaMallocHost(&p, bytes));
+    g_pool.push_back({p, bytes, true});
+    *out = p;
+    return OK_SUCCESS;
+}
+bool pool_release(void* p) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& b : g_pool) if (b.p == p) { b.used = false; return true; }
+    return false;
+}
+
+template <class T>
+int dev_reserve(T** p, uint64_t* cap, uint64_t need) {  // grow-only device buffer, contents dropped
+    if (*cap >= need && *p) return OK_SUCCESS;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    uint64_t n = std::max<uint64_t>(need, 1);
+    CU(cudaMalloc((void**)p, n * sizeof(T)));
+    *cap = n;
+    return OK_SUCCESS;
+}
+
+constexpr double LF_TARGET = 0.5;    // load factor a fresh table is sized for
+constexpr double LF_MAX = 0.7;       // occupancy at which the table is rebuilt larger
+constexpr unsigned MAX_PROBE = 2048; // displacement bound L (also the tail padding)
+constexpr uint64_t MIN_SLOTS = 1ull << 16;
+constexpr uint64_t SPILL_CAP = 1ull << 22;
+constexpr uint64_t COPY_CHUNK = 64ull << 20;  // bytes per H2D piece of the ingest pipeline
+
+}  // namespace
+
+// =============================================================================== counter ==
+struct ok_counter {
+    unsigned k = 0;
+    int norm_mode = 0;
+    uint64_t hint = 0;
+    cudaStream_t s_main = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    std::vector<cudaEvent_t> ev_chunks;
+    // table
+    OkTableView tv{};                 // tv.slots == nullptr until the first batch
+    OkDevStats* d_stats = nullptr;
+    OkDevStats* h_stats = nullptr;    // pinned mirror
+    OkSpill spill{};
+    uint64_t occupied = 0, windows = 0, bases_seen = 0, max_disp = 0, spilled_total = 0, grows = 0;
+    float ms_insert = 0, ms_readout = 0, ms_fill = 0;
+    // staging for host batches
+    uint8_t* d_bases = nullptr; uint64_t cap_bases = 0;
+    uint64_t* d_off = nullptr; uint64_t cap_off = 0;
+    // readout
+    unsigned long long* d_tiles = nullptr; uint64_t cap_tiles = 0;   // [n_tiles] + total
+    unsigned long long* d_out_keys = nullptr; uint64_t cap_out_keys = 0;
+    unsigned long long* d_out_counts = nullptr; uint64_t cap_out_counts = 0;
+};
+
+namespace {
+
+uint64_t keyspace_bound(unsigned k) { return k >= 31 ? ~0ull : (1ull << (2 * k)); }
+
+uint64_t slots_for(const ok_counter* c, uint64_t distinct) {
+    uint64_t ks = keyspace_bound(c->k);
+    if (distinct > ks) distinct = ks;
+    uint64_t n = (uint64_t)((double)distinct / LF_TARGET) + 1;
+    return std::max<uint64_t>(n, MIN_SLOTS);
+}
+
+int table_alloc(ok_counter* c, uint64_t n_home, OkTableView* out) {
+    OkTableView t{};
+    t.n_home = n_home;
+    t.n_total = n_home + MAX_PROBE;
+    t.key_shift = 64 - 2 * c->k;
+    t.map_mode = OK_MAP_CANON;
+    t.max_probe = MAX_PROBE;
+    cudaError_t e = cudaMalloc((void**)&t.slots, t.n_total * sizeof(OkSlot));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(OK_ERR_OUT_OF_MEMORY, "cannot allocate a %llu-slot k-mer table (%.1f GB): %s",
+                       (unsigned long long)t.n_total, t.n_total * 16.0 / 1e9, cudaGetErrorString(e));
+    }
+    LAUNCH(k_fill_slots, grid_for(t.n_total, 256, 16), 256, 0, c->s_main, t.slots, t.n_total);
+    *out = t;
+    return OK_SUCCESS;
+}
+
+int read_stats(ok_counter* c) {
+    CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(OkDevStats), cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    c->occupied = c->h_stats->occupied;
+    c->windows = c->h_stats->windows;
+    c->max_disp = std::max<uint64_t>(c->max_disp, c->h_stats->max_disp);
+    return OK_SUCCESS;
+}
+
+// Rebuild into a table of new_home slots, then re-add whatever the probe bound spilled.
+int table_rebuild(ok_counter* c, uint64_t new_home) {
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        cudaEvent_t e0 = c->ev_a, e1 = c->ev_b;
+        CU(cudaEventRecord(e0, c->s_main));
+        OkTableView nt{};
+        TRY(table_alloc(c, new_home, &nt));
+        const uint64_t n_spill = std::min<uint64_t>(c->h_stats->spill_n, c->spill.cap);
+        // reset the per-table statistics (windows is cumulative and kept)
+        CU(cudaMemsetAsync(&c->d_stats->occupied, 0, sizeof(unsigned long long), c->s_main));
+        CU(cudaMemsetAsync(&c->d_stats->max_disp, 0, sizeof(unsigned long long), c->s_main));
+        CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, sizeof(unsigned long long), c->s_main));
+        // spilled entries move to a scratch copy first (the rebuild may spill again)
+        uint64_t *sk = nullptr, *si = nullptr;
+        if (n_spill) {
+            CU(cudaMalloc((void**)&sk, n_spill * 8)); CU(cudaMalloc((void**)&si, n_spill * 8));
+            CU(cudaMemcpyAsync(sk, c->spill.keys, n_spill * 8, cudaMemcpyDeviceToDevice, c->s_main));
+            CU(cudaMemcpyAsync(si, c->spill.incs, n_spill * 8, cudaMemcpyDeviceToDevice, c->s_main));
+        }
+        if (c->tv.slots)
+            LAUNCH(k_rehash, grid_for(c->tv.n_total), 256, 0, c->s_main, nt, c->d_stats, c->spill,
+                   c->tv.slots, c->tv.n_total);
+        if (n_spill)
+            LAUNCH(k_add_kmers, grid_for(n_spill), 256, 0, c->s_main, nt, c->d_stats, c->spill,
+                   (const unsigned long long*)sk, (const unsigned long long*)si, n_spill, 0);
+        CU(cudaEventRecord(e1, c->s_main));
+        TRY(read_stats(c));
+        CU(cudaGetLastError());
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->ms_fill += ms;
+        if (sk) cudaFree(sk);
+        if (si) cudaFree(si);
+        if (c->tv.slots) cudaFree(c->tv.slots);
+        c->tv = nt;
+        c->max_disp = c->h_stats->max_disp;
+        ++c->grows;
+        if (c->h_stats->spill_n == 0) return OK_SUCCESS;
+        if (c->h_stats->spill_n > c->spill.cap)
+            return set_err(OK_ERR_INTERNAL, "spill list overflow while rebuilding the k-mer table");
+        c->spilled_total += c->h_stats->spill_n;
+        new_home *= 2;  // still too clustered for the displacement bound: spread further
+    }
+    return set_err(OK_ERR_INTERNAL,
+                   "k-mer keys are too clustered for the ordered table (displacement bound %u exceeded "
+                   "after repeated growth)", MAX_PROBE);
+}
+
+// Make room for up to `incoming` new distinct keys; returns how many may be added before the
+// next check.
+int ensure_headroom(ok_counter* c, uint64_t incoming, uint64_t* allowed) {
+    if (!c->tv.slots) {
+        uint64_t want = c->hint ? c->hint : incoming;
+        TRY(table_rebuild(c, slots_for(c, std::max<uint64_t>(want, 1))));
+        c->grows = 0;
+    }
+    const uint64_t ks = keyspace_bound(c->k);
+    for (;;) {
+        const uint64_t limit = (uint64_t)(LF_MAX * (double)c->tv.n_home);
+        // a table that already covers the whole key space at <= LF_TARGET can never overfill
+        if (ks != ~0ull && (double)ks <= LF_TARGET * (double)c->tv.n_home) { *allowed = ~0ull; return OK_SUCCESS; }
+        const uint64_t free_keys = limit > c->occupied ? limit - c->occupied : 0;
+        const uint64_t min_step = std::min<uint64_t>(incoming, 16ull << 20);
+        if (free_keys >= min_step) { *allowed = free_keys; return OK_SUCCESS; }
+        uint64_t want = std::max<uint64_t>(2 * c->tv.n_home, slots_for(c, c->occupied + min_step));
+        TRY(table_rebuild(c, want));
+    }
+}
+
+template <class Sink>
+void launch_extract(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off,
+                    uint64_t n_rec, uint64_t t0, uint64_t t1, cudaStream_t st, const Sink& sink, int norm_mode,
+                    unsigned k) {
+    (void)c;
+    const uint64_t n_tiles = t1 - t0;
+    const uint64_t max_warps = (uint64_t)(g_sms > 0 ? g_sms : 148) * 8 /*blocks per SM*/ * 8 /*warps*/;
+    const uint64_t tpw = std::max<uint64_t>(1, (n_tiles + max_warps - 1) / max_warps);
+    const uint64_t warps = (n_tiles + tpw - 1) / tpw;
+    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    auto kern = norm_mode == OK_NORM_NORMALIZED ? k_extract<true, Sink> : k_extract<false, Sink>;
+    LAUNCH(kern, blocks, 256, 0, st, d_bases, n_bases, d_off, n_rec, t0, t1, tpw, k, sink);
+}
+
+// count the windows of tiles [t0, t1) of a device-resident batch
+int counter_process_tiles(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off,
+                          uint64_t n_rec, uint64_t t0, uint64_t t1) {
+    while (t0 < t1) {
+        const uint64_t remaining = std::min<uint64_t>((t1 - t0) * OK_TILE_BASES, n_bases - t0 * OK_TILE_BASES);
+        uint64_t allowed = 0;
+        TRY(ensure_headroom(c, remaining, &allowed));
+        uint64_t nt = t1 - t0;
+        if (allowed != ~0ull) nt = std::min<uint64_t>(nt, std::max<uint64_t>(1, allowed / OK_TILE_BASES));
+        SinkCount sink{}; sink.t = c->tv; sink.st = c->d_stats; sink.sp = c->spill;
+        CU(cudaEventRecord(c->ev_a, c->s_main));
+        launch_extract(c, d_bases, n_bases, d_off, n_rec, t0, t0 + nt, c->s_main, sink, c->norm_mode, c->k);
+        CU(cudaEventRecord(c->ev_b, c->s_main));
+        TRY(read_stats(c));
+        CU(cudaGetLastError());
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->ms_insert += ms;
+        if (c->h_stats->spill_n) {
+            if (c->h_stats->spill_n > c->spill.cap)
+                return set_err(OK_ERR_INTERNAL, "spill list overflow (%llu entries): k-mer keys too clustered",
+                               (unsigned long long)c->h_stats->spill_n);
+            c->spilled_total += c->h_stats->spill_n;
+            TRY(table_rebuild(c, 2 * c->tv.n_home));
+        }
+        t0 += nt;
+    }
+    return OK_SUCCESS;
+}
+
+int counter_readout(ok_counter* c, uint64_t min_count, uint64_t* n_out) {
+    *n_out = 0;
+    if (!c->tv.slots || c->occupied == 0) return OK_SUCCESS;
+    if (min_count == 0) min_count = 1;
+    const uint64_t n_tiles = (c->tv.n_total + OK_RT_SLOTS - 1) / OK_RT_SLOTS;
+    TRY(dev_reserve(&c->d_tiles, &c->cap_tiles, n_tiles + 1));
+    CU(cudaEventRecord(c->ev_a, c->s_main));
+    LAUNCH(k_readout_count, (unsigned)n_tiles, 256, 0, c->s_main, c->tv.slots, c->tv.n_total, min_count, c->d_tiles);
+    LAUNCH(k_scan_tiles, 1, 1024, 0, c->s_main, c->d_tiles, n_tiles, c->d_tiles + n_tiles);
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, c->d_tiles + n_tiles, 8, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    if (total) {
+        TRY(dev_reserve(&c->d_out_keys, &c->cap_out_keys, total));
+        TRY(dev_reserve(&c->d_out_counts, &c->cap_out_counts, total));
+        if (min_count > 1)
+            LAUNCH(k_readout_write<true>, (unsigned)n_tiles, 256, 0, c->s_main, c->tv, min_count, c->d_tiles,
+                   c->d_out_keys, c->d_out_counts);
+        else
+            LAUNCH(k_readout_write<false>, (unsigned)n_tiles, 256, 0, c->s_main, c->tv, min_count, c->d_tiles,
+                   c->d_out_keys, c->d_out_counts);
+    }
+    CU(cudaEventRecord(c->ev_b, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&c->ms_readout, c->ev_a, c->ev_b);
+    *n_out = total;
+    return OK_SUCCESS;
+}
+
+}  // namespace
+
+// ============================================================================ lifecycle ==
+OK_EXPORT int ok_init(const int* device_ids, int n_devices) {
+    if (n_devices > 1)
+        return set_err(OK_ERR_INVALID_ARGUMENT, "one process drives one GPU: n_devices must be 1 (got %d)", n_devices);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_err(OK_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    int dev = (device_ids && n_devices == 1) ? device_ids[0] : 0;
+    if (dev < 0 || dev >= count) return set_err(OK_ERR_INVALID_ARGUMENT, "device id %d out of range (0..%d)", dev, count - 1);
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, dev));
+    g_sms = prop.multiProcessorCount;
+    g_device = dev;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& b : g_pool) cudaFreeHost(b.p);
+    g_pool.clear();
+    g_device = -1;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT const char* ok_last_error(void) { return g_err.c_str(); }
+OK_EXPORT const char* ok_version(void) { return "orion-kmer-b200 0.1 (sm_100a)"; }
+OK_EXPORT uint64_t ok_launch_count(void) { return g_launches.load(); }
+OK_EXPORT int ok_synchronize(void) { TRY(ensure_init()); CU(cudaDeviceSynchronize()); return OK_SUCCESS; }
+
+OK_EXPORT int ok_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_host_alloc: out is NULL");
+    TRY(ensure_init());
+    CU(cudaMallocHost(out, bytes ? bytes : 8));
+    return OK_SUCCESS;
+}
+OK_EXPORT int ok_host_free(void* p) { if (p) CU(cudaFreeHost(p)); return OK_SUCCESS; }
+OK_EXPORT int ok_free(void* p) {
+    if (!p) return OK_SUCCESS;
+    if (!pool_release(p)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_free: pointer was not handed out by this library");
+    return OK_SUCCESS;
+}
+
+// ==================================================================== host k-mer arithmetic ==
+OK_EXPORT int ok_seq_to_u64(const uint8_t* seq, uint64_t len, uint8_t k, uint64_t* out) {
+    if (k == 0 || k > 32 || len != k || !seq || !out) return 0;  // kmer.rs:38-43
+    uint64_t v = 0;
+    for (unsigned i = 0; i < k; ++i) {
+        uint32_t c8, v4;
+        ok_pack4<false>((uint32_t)seq[i], c8, v4);   // same table the kernels use
+        if (!(v4 & 8u)) return 0;
+        v = (v << 2) | (c8 >> 6);
+    }
+    *out = v;
+    return 1;
+}
+OK_EXPORT int ok_u64_to_seq(uint64_t kmer, uint8_t k, uint8_t* out) {
+    if (k == 0 || k > 32) return set_err(OK_ERR_INVALID_KMER_SIZE, "Invalid k-mer length for decoding: %u", (unsigned)k);
+    for (unsigned i = 0; i < k; ++i) out[i] = (uint8_t)"ACGT"[(kmer >> (2 * (k - 1 - i))) & 3u];
+    return OK_SUCCESS;
+}
+OK_EXPORT int ok_reverse_complement_u64(uint64_t kmer, uint8_t k, uint64_t* out) {
+    if (k == 0 || k > 32) return set_err(OK_ERR_INVALID_KMER_SIZE, "Invalid k-mer length for reverse complement: %u", (unsigned)k);
+    *out = ok_revcomp(kmer, k);
+    return OK_SUCCESS;
+}
+OK_EXPORT int ok_canonical_u64(uint64_t kmer, uint8_t k, uint64_t* out) {
+    if (k == 0 || k > 32) return set_err(OK_ERR_INVALID_KMER_SIZE, "Invalid k-mer length for reverse complement: %u", (unsigned)k);
+    *out = ok_canonical(kmer, k);
+    return OK_SUCCESS;
+}
+
+// ================================================================================ counter ==
+OK_EXPORT int ok_counter_create(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_counter** out) {
+    if (!out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_create: out is NULL");
+    *out = nullptr;
+    if (k == 0 || k > 32) return invalid_k(k);  // count.rs:43-45
+    if (norm_mode != OK_NORM_NORMALIZED && norm_mode != OK_NORM_RAW)
+        return set_err(OK_ERR_INVALID_ARGUMENT, "unknown norm_mode %d", norm_mode);
+    TRY(ensure_init());
+    ok_counter* c = new ok_counter();
+    c->k = k; c->norm_mode = norm_mode; c->hint = capacity_hint;
+    auto fail = [&](int code) { ok_counter_destroy(c); return code; };
+#define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(set_err(OK_ERR_CUDA, "CUDA error %s in ok_counter_create", cudaGetErrorName(e_))); } while (0)
+    CUF(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
+    CUF(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CUF(cudaEventCreate(&c->ev_a));
+    CUF(cudaEventCreate(&c->ev_b));
+    CUF(cudaMalloc((void**)&c->d_stats, sizeof(OkDevStats)));
+    CUF(cudaMemset(c->d_stats, 0, sizeof(OkDevStats)));
+    CUF(cudaMallocHost((void**)&c->h_stats, sizeof(OkDevStats)));
+    memset(c->h_stats, 0, sizeof(OkDevStats));
+    c->spill.cap = SPILL_CAP;
+    CUF(cudaMalloc((void**)&c->spill.keys, SPILL_CAP * 8));
+    CUF(cudaMalloc((void**)&c->spill.incs, SPILL_CAP * 8));
+#undef CUF
+    *out = c;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_counter_destroy(ok_counter* c) {
+    if (!c) return OK_SUCCESS;
+    if (c->s_main) cudaStreamSynchronize(c->s_main);
+    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    cudaFree(c->tv.slots); cudaFree(c->d_stats); cudaFreeHost(c->h_stats);
+    cudaFree(c->spill.keys); cudaFree(c->spill.incs);
+    cudaFree(c->d_bases); cudaFree(c->d_off); cudaFree(c->d_tiles);
+    cudaFree(c->d_out_keys); cudaFree(c->d_out_counts);
+    for (auto e : c->ev_chunks) cudaEventDestroy(e);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->s_main) cudaStreamDestroy(c->s_main);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    delete c;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_counter_clear(ok_counter* c) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_clear: NULL handle");
+    if (c->tv.slots) LAUNCH(k_fill_slots, grid_for(c->tv.n_total, 256, 16), 256, 0, c->s_main, c->tv.slots, c->tv.n_total);
+    CU(cudaMemsetAsync(c->d_stats, 0, sizeof(OkDevStats), c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    c->occupied = c->windows = c->bases_seen = c->max_disp = c->spilled_total = 0;
+    c->ms_insert = c->ms_readout = c->ms_fill = 0;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_counter_add_batch_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                                          const uint64_t* d_rec_offsets, uint64_t n_records) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_add_batch_device: NULL handle");
+    if (n_bases == 0 || n_records == 0) return OK_SUCCESS;
+    if (!d_bases || !d_rec_offsets) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL batch pointer");
+    if ((uintptr_t)d_bases & 15u) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
+    c->ms_insert = 0; c->ms_fill = 0;
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    TRY(counter_process_tiles(c, d_bases, n_bases, d_rec_offsets, n_records, 0, n_tiles));
+    c->bases_seen += n_bases;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const uint64_t* rec_offsets,
+                                   uint64_t n_records) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_add_batch: NULL handle");
+    if (n_records == 0) return OK_SUCCESS;
+    if (!rec_offsets) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL rec_offsets");
+    if (rec_offsets[0] != 0) return set_err(OK_ERR_INVALID_ARGUMENT, "rec_offsets[0] must be 0");
+    const uint64_t n_bases = rec_offsets[n_records];
+    if (n_bases == 0) return OK_SUCCESS;
+    if (!bases) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL bases");
+    c->ms_insert = 0; c->ms_fill = 0;
+    TRY(dev_reserve(&c->d_bases, &c->cap_bases, n_bases + 64));
+    TRY(dev_reserve(&c->d_off, &c->cap_off, n_records + 1));
+    // copy stream runs ahead piece by piece; the compute stream follows the events
+    const uint64_t n_pieces = (n_bases + COPY_CHUNK - 1) / COPY_CHUNK;
+    while (c->ev_chunks.size() < n_pieces + 1) {
+        cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_chunks.push_back(e);
+    }
+    CU(cudaMemcpyAsync(c->d_off, rec_offsets, (n_records + 1) * 8, cudaMemcpyHostToDevice, c->s_copy));
+    CU(cudaEventRecord(c->ev_chunks[n_pieces], c->s_copy));
+    for (uint64_t p = 0; p < n_pieces; ++p) {
+        const uint64_t b0 = p * COPY_CHUNK, b1 = std::min(n_bases, b0 + COPY_CHUNK);
+        CU(cudaMemcpyAsync(c->d_bases + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->s_copy));
+        CU(cudaEventRecord(c->ev_chunks[p], c->s_copy));
+    }
+    CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces], 0));
+    const uint64_t tiles_per_piece = COPY_CHUNK / OK_TILE_BASES;
+    for (uint64_t p = 0; p < n_pieces; ++p) {
+        CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[p], 0));
+        const uint64_t t0 = p * tiles_per_piece;
+        const uint64_t b1 = std::min(n_bases, (p + 1) * COPY_CHUNK);
+        // a tile is only complete once the piece holding its last base has landed
+        const uint64_t t1 = (p + 1 == n_pieces) ? (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES : b1 / OK_TILE_BASES;
+        // the kernel only reads bases below n_visible: pass the landed prefix as the batch length
+        TRY(counter_process_tiles(c, c->d_bases, (p + 1 == n_pieces) ? n_bases : b1, c->d_off, n_records, t0, t1));
+    }
+    c->bases_seen += n_bases;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers, uint64_t n) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_add_kmers_device: NULL handle");
+    if (n == 0) return OK_SUCCESS;
+    if (!d_kmers) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL d_kmers");
+    uint64_t done = 0;
+    while (done < n) {
+        uint64_t allowed = 0;
+        TRY(ensure_headroom(c, n - done, &allowed));
+        const uint64_t m = std::min<uint64_t>(n - done, allowed);
+        CU(cudaEventRecord(c->ev_a, c->s_main));
+        LAUNCH(k_add_kmers, grid_for(m), 256, 0, c->s_main, c->tv, c->d_stats, c->spill,
+               (const unsigned long long*)d_kmers + done, (const unsigned long long*)nullptr, m, 1);
+        CU(cudaEventRecord(c->ev_b, c->s_main));
+        TRY(read_stats(c));
+        CU(cudaGetLastError());
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->ms_insert += ms;
+        if (c->h_stats->spill_n) {
+            if (c->h_stats->spill_n > c->spill.cap) return set_err(OK_ERR_INTERNAL, "spill list overflow: k-mer keys too clustered");
+            c->spilled_total += c->h_stats->spill_n;
+            TRY(table_rebuild(c, 2 * c->tv.n_home));
+        }
+        done += m;
+    }
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_counter_route_batch_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                                            const uint64_t* d_rec_offsets, uint64_t n_records, int n_ranks,
+                                            uint64_t* d_out, uint64_t* out_counts) {
+    (void)c; (void)d_bases; (void)n_bases; (void)d_rec_offsets; (void)n_records; (void)n_ranks; (void)d_out; (void)out_counts;
+    return set_err(OK_ERR_INTERNAL, "ok_counter_route_batch_device: not built yet");
+}
+
+OK_EXPORT int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t** d_kmers,
+                                       const uint64_t** d_counts, uint64_t* n) {
+    if (!c || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_finish_device: NULL argument");
+    uint64_t total = 0;
+    TRY(counter_readout(c, min_count, &total));
+    if (d_kmers) *d_kmers = (const uint64_t*)c->d_out_keys;
+    if (d_counts) *d_counts = (const uint64_t*)c->d_out_counts;
+    *n = total;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** kmers, uint64_t** counts,
+                                uint64_t* n) {
+    if (!c || !kmers || !counts || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_finish: NULL argument");
+    uint64_t total = 0;
+    TRY(counter_readout(c, min_count, &total));
+    void *hk = nullptr, *hc = nullptr;
+    TRY(pool_alloc(&hk, total * 8));
+    TRY(pool_alloc(&hc, total * 8));
+    if (total) {
+        CU(cudaMemcpyAsync(hk, c->d_out_keys, total * 8, cudaMemcpyDeviceToHost, c->s_main));
+        CU(cudaMemcpyAsync(hc, c->d_out_counts, total * 8, cudaMemcpyDeviceToHost, c->s_copy));
+        CU(cudaStreamSynchronize(c->s_main));
+        CU(cudaStreamSynchronize(c->s_copy));
+    }
+    *kmers = (uint64_t*)hk; *counts = (uint64_t*)hc; *n = total;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out) {
+    if (!c || !out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_get_stats: NULL argument");
+    out->n_slots = c->tv.n_total; out->n_distinct = c->occupied; out->n_windows = c->windows;
+    out->n_bases = c->bases_seen; out->max_displacement = c->max_disp; out->n_spilled = c->spilled_total;
+    out->n_grows = c->grows; out->ms_insert = c->ms_insert; out->ms_readout = c->ms_readout; out->ms_fill = c->ms_fill;
+    return OK_SUCCESS;
+}
+
+// =================================================================================== sets ==
+struct ok_set {
+    unsigned k = 0;
+    int norm_mode = 0;
+    ok_counter* builder = nullptr;            // while batches are still being added
+    unsigned long long* d_keys = nullptr;     // sorted, duplicate-free, once sealed
+    uint64_t n = 0;
+    bool sealed = false;
+    int has_max = 0;                          // contains 0xFFFF...F (only possible for foreign k=32 sets)
+    unsigned long long* d_table = nullptr;    // hashed membership table, built on first probe
+    uint64_t n_table = 0;
+    cudaStream_t st = nullptr;
+};
+
+namespace {
+
+int set_seal(ok_set* s) {
+    if (s->sealed) return OK_SUCCESS;
+    if (!s->st) CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    uint64_t n = 0;
+    if (s->builder) {
+        const uint64_t *dk = nullptr, *dc = nullptr;
+        TRY(ok_counter_finish_device(s->builder, 1, &dk, &dc, &n));
+        const uint64_t total = n + (s->has_max ? 1 : 0);
+        if (total) {
+            CU(cudaMalloc((void**)&s->d_keys, total * 8));
+            if (n) CU(cudaMemcpy(s->d_keys, dk, n * 8, cudaMemcpyDeviceToDevice));
+            if (s->has_max) { unsigned long long m = OK_EMPTY_KEY; CU(cudaMemcpy(s->d_keys + n, &m, 8, cudaMemcpyHostToDevice)); }
+        }
+        n = total;
+        ok_counter_destroy(s->builder);
+        s->builder = nullptr;
+    }
+    s->n = n;
+    s->sealed = true;
+    return OK_SUCCESS;
+}
+
+int set_table(ok_set* s) {
+    TRY(set_seal(s));
+    if (s->d_table) return OK_SUCCESS;
+    s->n_table = std::max<uint64_t>(1024, 2 * s->n);
+    CU(cudaMalloc((void**)&s->d_table, s->n_table * 8));
+    LAUNCH(k_fill_u64, grid_for(s->n_table), 256, 0, s->st, s->d_table, s->n_table, OK_EMPTY_KEY);
+    if (s->n) LAUNCH(k_keytable_build, grid_for(s->n), 256, 0, s->st, s->d_table, s->n_table, s->d_keys, s->n);
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaGetLastError());
+    return OK_SUCCESS;
+}
+
+int kmer_size_mismatch(unsigned a, unsigned b) {  // errors.rs:24-25
+    return set_err(OK_ERR_KMER_SIZE_MISMATCH,
+                   "K-mer databases have incompatible k-mer sizes (overall comparison): %u vs %u", a, b);
+}
+
+}  // namespace
+
+OK_EXPORT int ok_set_create(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_set** out) {
+    if (!out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_create: out is NULL");
+    *out = nullptr;
+    ok_counter* b = nullptr;
+    TRY(ok_counter_create(k, norm_mode, capacity_hint, &b));  // build.rs:83-85 validates k the same way
+    ok_set* s = new ok_set();
+    s->k = k; s->norm_mode = norm_mode; s->builder = b;
+    *out = s;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_set_add_batch(ok_set* s, const uint8_t* bases, const uint64_t* rec_offsets, uint64_t n_records) {
+    if (!s) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_add_batch: NULL handle");
+    if (s->sealed || !s->builder) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_add_batch: the set is already sealed");
+    return ok_counter_add_batch(s->builder, bases, rec_offsets, n_records);
+}
+
+OK_EXPORT int ok_set_from_sorted(uint8_t k, const uint64_t* kmers, uint64_t n, ok_set** out) {
+    if (!out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_from_sorted: out is NULL");
+    *out = nullptr;
+    if (k == 0 || k > 32) return invalid_k(k);
+    if (n && !kmers) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL kmers");
+    for (uint64_t i = 1; i < n; ++i)
+        if (kmers[i] <= kmers[i - 1]) return set_err(OK_ERR_INVALID_ARGUMENT, "kmers must be strictly ascending (index %llu)", (unsigned long long)i);
+    TRY(ensure_init());
+    ok_set* s = new ok_set();
+    s->k = k; s->n = n; s->sealed = true;
+    s->has_max = (n && kmers[n - 1] == OK_EMPTY_KEY) ? 1 : 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess && n) e = cudaMalloc((void**)&s->d_keys, n * 8);
+    if (e == cudaSuccess && n) e = cudaMemcpy(s->d_keys, kmers, n * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { ok_set_destroy(s); return set_err(OK_ERR_CUDA, "CUDA error %s in ok_set_from_sorted", cudaGetErrorName(e)); }
+    *out = s;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_set_size(ok_set* s, uint64_t* n) {
+    if (!s || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_size: NULL argument");
+    TRY(set_seal(s));
+    *n = s->n;
+    return OK_SUCCESS;
+}
+OK_EXPORT int ok_set_k(ok_set* s, uint8_t* k) {
+    if (!s || !k) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_k: NULL argument");
+    *k = (uint8_t)s->k;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_set_export(ok_set* s, uint64_t** kmers, uint64_t* n) {
+    if (!s || !kmers || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_export: NULL argument");
+    TRY(set_seal(s));
+    void* h = nullptr;
+    TRY(pool_alloc(&h, s->n * 8));
+    if (s->n) CU(cudaMemcpy(h, s->d_keys, s->n * 8, cudaMemcpyDeviceToHost));
+    *kmers = (uint64_t*)h; *n = s->n;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
+    if (!out || (n_sets && !sets)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_union: NULL argument");
+    *out = nullptr;
+    if (n_sets == 0) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_union: no sets");
+    uint64_t sum = 0; int has_max = 0;
+    for (uint64_t i = 0; i < n_sets; ++i) {
+        if (!sets[i]) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_union: NULL set");
+        if (sets[i]->k != sets[0]->k) return kmer_size_mismatch(sets[0]->k, sets[i]->k);
+        TRY(set_seal(sets[i]));
+        sum += sets[i]->n; has_max |= sets[i]->has_max;
+    }
+    ok_set* u = nullptr;
+    TRY(ok_set_create((uint8_t)sets[0]->k, sets[0]->norm_mode, std::max<uint64_t>(sum, 1), &u));
+    u->has_max = has_max;
+    for (uint64_t i = 0; i < n_sets; ++i) {
+        const uint64_t m = sets[i]->n - (sets[i]->has_max ? 1 : 0);
+        int r = ok_counter_add_kmers_device(u->builder, (const uint64_t*)sets[i]->d_keys, m);
+        if (r != OK_SUCCESS) { ok_set_destroy(u); return r; }
+    }
+    *out = u;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_set_destroy(ok_set* s) {
+    if (!s) return OK_SUCCESS;
+    if (s->builder) ok_counter_destroy(s->builder);
+    cudaFree(s->d_keys); cudaFree(s->d_table);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_set_intersection_size(ok_set* a, ok_set* b, uint64_t* out) {
+    if (!a || !b || !out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_intersection_size: NULL argument");
+    if (a->k != b->k) return kmer_size_mismatch(a->k, b->k);  // compare.rs:37-39
+    TRY(set_seal(a)); TRY(set_seal(b));
+    if (a->n > b->n) std::swap(a, b);
+    *out = 0;
+    if (a->n == 0) return OK_SUCCESS;
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc((void**)&d, 8));
+    CU(cudaMemsetAsync(d, 0, 8, a->st));
+    LAUNCH(k_intersect_sorted, grid_for(a->n), 256, 0, a->st, a->d_keys, a->n, b->d_keys, b->n, d);
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, a->st));
+    CU(cudaStreamSynchronize(a->st));
+    cudaFree(d);
+    *out = h;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_sets_all_vs_all(ok_set* const* sets, uint64_t n, uint64_t* sizes, uint64_t* inter) {
+    if ((n && !sets) || !sizes || !inter) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_sets_all_vs_all: NULL argument");
+    if (n == 0) return OK_SUCCESS;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!sets[i]) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_sets_all_vs_all: NULL set");
+        if (sets[i]->k != sets[0]->k) return kmer_size_mismatch(sets[0]->k, sets[i]->k);
+        TRY(set_seal(sets[i]));
+        sizes[i] = sets[i]->n;
+    }
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc((void**)&d, n * n * 8));
+    cudaStream_t st = sets[0]->st;
+    CU(cudaMemsetAsync(d, 0, n * n * 8, st));
+    for (uint64_t i = 0; i < n; ++i)
+        for (uint64_t j = i + 1; j < n; ++j) {
+            ok_set *a = sets[i], *b = sets[j];
+            if (a->n > b->n) std::swap(a, b);
+            if (a->n == 0) continue;
+            LAUNCH(k_intersect_sorted, grid_for(a->n), 256, 0, st, a->d_keys, a->n, b->d_keys, b->n, d + i * n + j);
+        }
+    CU(cudaMemcpyAsync(inter, d, n * n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    cudaFree(d);
+    for (uint64_t i = 0; i < n; ++i) {
+        inter[i * n + i] = sizes[i];
+        for (uint64_t j = 0; j < i; ++j) inter[i * n + j] = inter[j * n + i];
+    }
+    return OK_SUCCESS;
+}
+
+// ================================================================================= probes ==
+OK_EXPORT int ok_probe_reads(ok_set* s, int norm_mode, const uint8_t* bases, const uint64_t* rec_offsets,
+                             uint64_t n_records, uint32_t* hits_per_read) {
+    if (!s || (n_records && (!rec_offsets || !hits_per_read)))
+        return set_err(OK_ERR_INVALID_ARGUMENT, "ok_probe_reads: NULL argument");
+    if (n_records == 0) return OK_SUCCESS;
+    if (rec_offsets[0] != 0) return set_err(OK_ERR_INVALID_ARGUMENT, "rec_offsets[0] must be 0");
+    TRY(set_table(s));
+    const uint64_t n_bases = rec_offsets[n_records];
+    memset(hits_per_read, 0, n_records * sizeof(uint32_t));
+    if (n_bases == 0) return OK_SUCCESS;
+    uint8_t* d_b = nullptr; uint64_t* d_o = nullptr; unsigned* d_h = nullptr;
+    CU(cudaMalloc((void**)&d_b, n_bases + 64));
+    CU(cudaMalloc((void**)&d_o, (n_records + 1) * 8));
+    CU(cudaMalloc((void**)&d_h, n_records * 4));
+    CU(cudaMemcpyAsync(d_b, bases, n_bases, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(d_o, rec_offsets, (n_records + 1) * 8, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemsetAsync(d_h, 0, n_records * 4, s->st));
+    SinkProbeReads sink{};
+    sink.t = OkKeyTableView{s->d_table, s->n_table, s->has_max};
+    sink.rec_off = d_o; sink.n_rec = n_records; sink.hits = d_h;
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    launch_extract(nullptr, d_b, n_bases, d_o, n_records, 0, n_tiles, s->st, sink, norm_mode, s->k);
+    CU(cudaMemcpyAsync(hits_per_read, d_h, n_records * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaGetLastError());
+    cudaFree(d_b); cudaFree(d_o); cudaFree(d_h);
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_probe_counts(ok_set* ref, const uint64_t* kmers, const uint64_t* counts, uint64_t n,
+                              uint64_t* matched, uint64_t* depth_sum) {
+    if (!ref || !matched || !depth_sum || (n && !kmers)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_probe_counts: NULL argument");
+    *matched = 0; *depth_sum = 0;
+    if (n == 0) return OK_SUCCESS;
+    TRY(set_table(ref));
+    unsigned long long *d_k = nullptr, *d_c = nullptr, *d_o = nullptr;
+    CU(cudaMalloc((void**)&d_k, n * 8));
+    if (counts) CU(cudaMalloc((void**)&d_c, n * 8));
+    CU(cudaMalloc((void**)&d_o, 16));
+    CU(cudaMemcpyAsync(d_k, kmers, n * 8, cudaMemcpyHostToDevice, ref->st));
+    if (counts) CU(cudaMemcpyAsync(d_c, counts, n * 8, cudaMemcpyHostToDevice, ref->st));
+    CU(cudaMemsetAsync(d_o, 0, 16, ref->st));
+    LAUNCH(k_probe_counts, grid_for(n), 256, 0, ref->st, (OkKeyTableView{ref->d_table, ref->n_table, ref->has_max}),
+           (const unsigned long long*)d_k, (const unsigned long long*)d_c, n, d_o);
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, d_o, 16, cudaMemcpyDeviceToHost, ref->st));
+    CU(cudaStreamSynchronize(ref->st));
+    CU(cudaGetLastError());
+    cudaFree(d_k); cudaFree(d_c); cudaFree(d_o);
+    *matched = h[0]; *depth_sum = h[1];
+    return OK_SUCCESS;
+}
+
+// =================================================================================== pack ==
+OK_EXPORT int ok_pack_2bit_device(const uint8_t* d_bases, uint64_t n_bases, int norm_mode, uint64_t* d_codes,
+                                  uint32_t* d_valid) {
+    TRY(ensure_init());
+    if (n_bases == 0) return OK_SUCCESS;
+    if (!d_bases || !d_codes || !d_valid) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_pack_2bit_device: NULL argument");
+    if ((uintptr_t)d_bases & 15u) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
+    const uint64_t n_groups = (n_bases + 31) / 32;
+    if (norm_mode == OK_NORM_NORMALIZED)
+        LAUNCH(k_pack_2bit<true>, grid_for(n_groups), 256, 0, 0, d_bases, n_bases, n_groups, (unsigned long long*)d_codes, d_valid);
+    else
+        LAUNCH(k_pack_2bit<false>, grid_for(n_groups), 256, 0, 0, d_bases, n_bases, n_groups, (unsigned long long*)d_codes, d_valid);
+    CU(cudaStreamSynchronize(0));
+    CU(cudaGetLastError());
+    return OK_SUCCESS;
+}
+
+// ============================================================================== test hooks ==
+// Not part of the public ABI (not declared in include/): host emulations of the exact
+// per-lane code the kernels run, so the arithmetic can be checked against the oracle on a
+// machine without a GPU, and a device hook that materialises the extracted k-mers.
+
+// Host walk of k_extract: same tiles, same lanes, same ok_pack32 / ok_window_mask /
+// ok_lane_windows.  Appends every canonical k-mer (in stream order) to out.
+OK_EXPORT int okx_emulate_extract(const uint8_t* bases, uint64_t n_bases, const uint64_t* rec_off, uint64_t n_rec,
+                                  unsigned k, int norm_mode, uint64_t* out, uint64_t cap, uint64_t* n_out) {
+    if (k == 0 || k > 32) return invalid_k(k);
+    uint64_t n = 0, r_next = 0;
+    uint64_t pc = 0; uint32_t pv = 0, ps = 0;
+    const uint64_t n_groups = (n_bases + 31) / 32;
+    for (uint64_t g = 0; g < n_groups; ++g) {
+        uint32_t w[8];
+        for (int i = 0; i < 8; ++i) {
+            uint32_t x = 0;
+            for (int b = 0; b < 4; ++b) { uint64_t p = g * 32 + 4 * i + b; if (p < n_bases) x |= (uint32_t)bases[p] << (8 * b); }
+            w[i] = x;
+        }
+        uint64_t cc; uint32_t cv, cs = 0;
+        if (norm_mode == OK_NORM_NORMALIZED) ok_pack32<true>(w, cc, cv); else ok_pack32<false>(w, cc, cv);
+        while (r_next < n_rec && rec_off[r_next] < (g + 1) * 32) { cs |= 0x80000000u >> (unsigned)(rec_off[r_next] - g * 32); ++r_next; }
+        const uint32_t okm = ok_window_mask(pv, cv, ps, cs, k);
+        ok_lane_windows(pc, cc, okm, k, [&](int, uint64_t key) { if (n < cap) out[n] = key; ++n; });
+        pc = cc; pv = cv; ps = cs;
+    }
+    *n_out = n;
+    return OK_SUCCESS;
+}
+
+// Host model of the ordered table: sequential inserts with the same home/probe rule, then the
+// same rank rule as k_readout_write.  out_* must hold n entries.
+OK_EXPORT int okx_emulate_table(const uint64_t* keys, uint64_t n, unsigned k, int map_mode, uint64_t n_home,
+                                unsigned max_probe, uint64_t min_count, uint64_t* out_keys, uint64_t* out_counts,
+                                uint64_t* n_out, uint64_t* n_spilled) {
+    const uint64_t n_total = n_home + max_probe;
+    std::vector<uint64_t> sk(n_total, OK_EMPTY_KEY), sc(n_total, 0);
+    uint64_t spilled = 0;
+    const unsigned shift = 64 - 2 * k;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t h = ok_home_slot(keys[i], shift, map_mode, n_home);
+        const uint64_t lim = std::min<uint64_t>(h + max_probe, n_total);
+        bool placed = false;
+        for (uint64_t q = h; q < lim; ++q) {
+            if (sk[q] == OK_EMPTY_KEY) sk[q] = keys[i];
+            if (sk[q] == keys[i]) { ++sc[q]; placed = true; break; }
+        }
+        if (!placed) ++spilled;
+    }
+    auto ld = [&](uint64_t q, uint64_t& kq, uint64_t& cq) { kq = sk[q]; cq = sc[q]; };
+    uint64_t before = 0, total = 0;
+    for (uint64_t s = 0; s < n_total; ++s) if (sk[s] != OK_EMPTY_KEY && sc[s] >= min_count) ++total;
+    for (uint64_t s = 0; s < n_total; ++s) {
+        if (sk[s] == OK_EMPTY_KEY || sc[s] < min_count) continue;
+        const uint64_t h = ok_home_slot(sk[s], shift, map_mode, n_home);
+        const long long adj = min_count > 1 ? ok_rank_adjust<true>(ld, s, sk[s], h, max_probe, n_total, min_count)
+                                            : ok_rank_adjust<false>(ld, s, sk[s], h, max_probe, n_total, min_count);
+        const uint64_t idx = before + adj;
+        if (idx >= total) return set_err(OK_ERR_INTERNAL, "rank out of range");
+        out_keys[idx] = sk[s]; out_counts[idx] = sc[s];
+        ++before;
+    }
+    *n_out = total; *n_spilled = spilled;
+    return OK_SUCCESS;
+}
+
+// Device: run k_extract with the materialising sink on host buffers (unordered output).
+OK_EXPORT int okx_device_extract(const uint8_t* bases, const uint64_t* rec_off, uint64_t n_rec, unsigned k,
+                                 int norm_mode, uint64_t* out, uint64_t cap, uint64_t* n_out) {
+    if (k == 0 || k > 32) return invalid_k(k);
+    TRY(ensure_init());
+    const uint64_t n_bases = rec_off[n_rec];
+    *n_out = 0;
+    if (n_bases == 0) return OK_SUCCESS;
+    uint8_t* d_b = nullptr; uint64_t* d_o = nullptr; unsigned long long *d_out = nullptr, *d_n = nullptr;
+    CU(cudaMalloc((void**)&d_b, n_bases + 64));
+    CU(cudaMalloc((void**)&d_o, (n_rec + 1) * 8));
+    CU(cudaMalloc((void**)&d_out, std::max<uint64_t>(cap, 1) * 8));
+    CU(cudaMalloc((void**)&d_n, 8));
+    CU(cudaMemcpy(d_b, bases, n_bases, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_o, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemset(d_n, 0, 8));
+    SinkEmit sink{d_out, d_n, cap};
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    launch_extract(nullptr, d_b, n_bases, d_o, n_rec, 0, n_tiles, 0, sink, norm_mode, k);
+    CU(cudaDeviceSynchronize());
+    CU(cudaGetLastError());
+    unsigned long long n = 0;
+    CU(cudaMemcpy(&n, d_n, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, d_out, std::min<uint64_t>(n, cap) * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_b); cudaFree(d_o); cudaFree(d_out); cudaFree(d_n);
+    *n_out = n;
+    return OK_SUCCESS;
+}

@@ -1,0 +1,349 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's golden
+vectors.  Needs a B200: run with `pytest -m gpu` under gpurun."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orion_kmer_b200 as ok
+from orion_kmer_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    ok.init(0)
+
+
+def enc(s):
+    return ok.seq_to_u64(s.encode(), len(s))
+
+
+def canon(s):
+    return ok.canonical_u64(enc(s), len(s))
+
+
+def as_dict(keys, counts, k):
+    return {ok.u64_to_seq(int(a), k).decode(): int(c) for a, c in zip(keys, counts)}
+
+
+ALPHABET = np.frombuffer(b"ACGTacgtNnUuRYKM-.*X", dtype=np.uint8)
+
+
+def random_batch(rng, n_bases, mean_len, p_junk=0.02):
+    p = np.full(len(ALPHABET), p_junk / (len(ALPHABET) - 4))
+    p[:4] = (1 - p_junk) / 4
+    bases = rng.choice(ALPHABET, size=n_bases, p=p)
+    cuts = np.unique(rng.integers(0, n_bases + 1, size=max(1, n_bases // mean_len)))
+    off = np.concatenate([[0], cuts, [n_bases]]).astype(np.uint64)
+    off = np.sort(np.concatenate([off, off[1:4]]))  # a few empty records
+    return bases, off
+
+
+# ---------------------------------------------------------------- extraction kernel alone --
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 16, 21, 31, 32])
+@pytest.mark.parametrize("norm", [ok.NORMALIZED, ok.RAW])
+def test_device_extract_matches_oracle(oracle, k, norm):
+    rng = np.random.default_rng(1000 + k)
+    for n_bases, mean_len in ((1, 1), (33, 5), (1500, 150), (70000, 37), (100000, 100000), (50000, 2)):
+        bases, off = random_batch(rng, n_bases, mean_len)
+        out = np.zeros(n_bases, dtype=np.uint64)
+        n = C.c_uint64()
+        rc = ok.lib().okx_device_extract(ok._ptr(bases), ok._ptr(off), len(off) - 1, k, norm, ok._ptr(out),
+                                         len(out), C.byref(n))
+        assert rc == 0, ok.lib().ok_last_error()
+        gk, gc = np.unique(out[:n.value], return_counts=True)
+        wk, wc = oracle.count_batch(k, bases, off, 1, norm == ok.NORMALIZED)
+        assert np.array_equal(gk, wk), (k, norm, n_bases)
+        assert np.array_equal(gc.astype(np.uint64), wc)
+
+
+def test_pack_kernel_matches_host_code(oracle):
+    import torch
+    rng = np.random.default_rng(3)
+    bases, _ = random_batch(rng, 100_001, 1000, p_junk=0.1)
+    d = torch.from_numpy(bases).cuda()
+    ng = (len(bases) + 31) // 32
+    codes = torch.zeros(ng, dtype=torch.int64, device="cuda")
+    valid = torch.zeros(ng, dtype=torch.int32, device="cuda")
+    for norm in (ok.NORMALIZED, ok.RAW):
+        ok._check(ok.lib().ok_pack_2bit_device(d.data_ptr(), len(bases), norm, codes.data_ptr(), valid.data_ptr()))
+        c = codes.cpu().numpy().view(np.uint64)
+        v = valid.cpu().numpy().view(np.uint32)
+        for g in rng.integers(0, ng, size=300):
+            chunk = bytes(bases[g * 32:(g + 1) * 32])
+            for i, b in enumerate(chunk):
+                code = oracle.seq_to_u64(bytes([b]), 1)
+                is_u = b in b"Uu" and norm == ok.NORMALIZED
+                want_valid = code is not None or is_u
+                assert bool((int(v[g]) >> (31 - i)) & 1) == want_valid
+                if want_valid:
+                    assert (int(c[g]) >> (62 - 2 * i)) & 3 == (3 if is_u else code)
+
+
+# ------------------------------------------------------- count: the reference's own vectors --
+def test_count_golden_cases(golden):
+    g = golden["count"]
+    for case in g["cases"]:
+        contents = [g["files"][n].encode() for n in case["inputs"]]
+        keys, counts = ok.count_fastx(case["k"], contents, case["min_count"])
+        assert as_dict(keys, counts, case["k"]) == case["expected"], case["name"]
+        text = ok.run_count(case["k"], contents, case["min_count"]).decode()
+        assert text == "".join(f"{s}\t{c}\n" for s, c in sorted(case["expected"].items()))
+
+
+def test_count_fixture_files(golden):
+    g = golden["derived_from_src"]
+    keys, counts = ok.count_fastx(7, [g["test_input1.fasta"].encode()])
+    assert as_dict(keys, counts, 7) == g["input1_k7"]
+    keys, counts = ok.count_fastx(6, [g["test_input2.fastq"].encode()])
+    assert as_dict(keys, counts, 6) == g["input2_k6"]
+
+
+def test_count_edge_cases(oracle):
+    c = ok.KmerCounter(5)
+    assert c.finish()[0].size == 0                               # nothing added
+    c.add_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64))  # empty batch
+    c.add_batch(np.frombuffer(b"ACG", np.uint8), np.array([0, 3], np.uint64))  # shorter than k
+    c.add_batch(np.frombuffer(b"NNNNNNNN", np.uint8), np.array([0, 8], np.uint64))
+    assert c.finish()[0].size == 0
+    c.add_batch(np.frombuffer(b"ACGTA", np.uint8), np.array([0, 5], np.uint64))
+    k, n = c.finish()
+    assert list(k) == [canon("ACGTA")] and list(n) == [1]
+    c.close()
+    # k = 32: all-T and all-A reads collapse on the key 0; u64::MAX is never canonical
+    c = ok.KmerCounter(32)
+    b = np.frombuffer(b"T" * 40 + b"A" * 40, np.uint8)
+    c.add_batch(b, np.array([0, 40, 80], np.uint64))
+    k, n = c.finish()
+    assert list(k) == [0] and list(n) == [18]
+    c.close()
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 11, 21, 31, 32])
+def test_count_random_batches_match_oracle(oracle, k):
+    rng = np.random.default_rng(k)
+    c = ok.KmerCounter(k)
+    o = oracle.Counter(k)
+    for n_bases, mean_len in ((300_000, 150), (200_000, 5000), (65_536, 64), (1, 1)):
+        bases, off = random_batch(rng, n_bases, mean_len)
+        c.add_batch(bases, off)
+        o.add_batch(bases, off, True)
+    for min_count in (1, 2, 5):
+        gk, gc = c.finish(min_count)
+        wk, wc = o.finish(min_count)
+        assert np.array_equal(gk, wk), (k, min_count)
+        assert np.array_equal(gc, wc), (k, min_count)
+    st = c.stats()
+    assert st["n_windows"] == int(o.finish(1)[1].sum())
+    c.close()
+
+
+def test_count_grows_without_hint_and_with_small_hint(oracle):
+    g = synth.genome(5, 3_000_000)
+    off = np.array([0, len(g)], np.uint64)
+    wk, wc = oracle.count_batch(25, g, off)
+    for hint in (0, 1000):
+        c = ok.KmerCounter(25, capacity_hint=hint)
+        third = len(g) // 3
+        # three batches that overlap by k-1 bases would double count: feed disjoint records instead
+        c.add_batch(g, off)
+        gk, gc = c.finish()
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+        c.add_batch(g[:third], np.array([0, third], np.uint64))   # a second batch on top
+        gk2, gc2 = c.finish()
+        o = oracle.Counter(25)
+        o.add_batch(g, off)
+        o.add_batch(g[:third], np.array([0, third], np.uint64))
+        wk2, wc2 = o.finish()
+        assert np.array_equal(gk2, wk2) and np.array_equal(gc2, wc2)
+        assert c.stats()["n_spilled"] == 0
+        c.close()
+
+
+def test_count_device_resident_input(oracle):
+    import torch
+    g = synth.genome(8, 400_000)
+    n_reads = 30_000
+    bases = synth.reads(g, 9, n_reads)
+    off = synth.read_offsets(n_reads)
+    d_b = torch.from_numpy(bases).cuda()
+    d_o = torch.from_numpy(off.view(np.int64)).cuda()
+    c = ok.KmerCounter(31, capacity_hint=4_000_000)
+    c.add_batch_device(d_b.data_ptr(), len(bases), d_o.data_ptr(), n_reads)
+    dk, dc, n = c.finish_device()
+    wk, wc = oracle.count_batch(31, bases, off)
+    assert n == len(wk)
+    assert dk and dc
+    h = c.finish()
+    assert np.array_equal(h[0], wk) and np.array_equal(h[1], wc)
+    c.clear()
+    assert c.finish()[0].size == 0
+    c.add_batch_device(d_b.data_ptr(), len(bases), d_o.data_ptr(), n_reads)
+    h = c.finish()
+    assert np.array_equal(h[0], wk) and np.array_equal(h[1], wc)
+    c.close()
+
+
+def test_count_config1_genome_exact(oracle):
+    """BASELINE.json configs[0]: canonical 21-mers of one 5 Mbp genome record (80-column FASTA)."""
+    g = synth.config1_genome()
+    text = synth.fasta_text(b"chr1", g)
+    keys, counts = ok.count_fastx(21, [text])
+    wk, wc = oracle.count_fastx(21, [text])
+    assert np.array_equal(keys, wk) and np.array_equal(counts, wc)
+    assert ok.format_counts(keys[:1000], counts[:1000], 21) == oracle.format_counts(wk[:1000], wc[:1000], 21)
+
+
+def test_count_config2_sample_exact(oracle):
+    """BASELINE.json configs[1] recipe on a 300k-read sample (the oracle finishes it in seconds)."""
+    g = synth.genome(3, 1_500_000)
+    n_reads = 300_000
+    bases = synth.reads(g, 3, n_reads)
+    off = synth.read_offsets(n_reads)
+    c = ok.KmerCounter(31)
+    c.add_batch(bases, off)
+    keys, counts = c.finish()
+    wk, wc = oracle.count_batch(31, bases, off)
+    assert np.array_equal(keys, wk) and np.array_equal(counts, wc)
+    c.close()
+
+
+def test_count_large_properties():
+    """size-independent properties at a size the oracle is not run on: total = number of
+    countable windows, strictly ascending keys, and both-strand invariance."""
+    g = synth.genome(21, 20_000_000)
+    n_reads = 2_000_000
+    bases = synth.reads(g, 22, n_reads)
+    off = synth.read_offsets(n_reads)
+    k = 31
+    c = ok.KmerCounter(k, capacity_hint=60_000_000)
+    c.add_batch(bases, off)
+    keys, counts = c.finish()
+    c.close()
+    assert np.all(keys[1:] > keys[:-1])
+    # countable windows = windows with no N: count them with a prefix sum of N flags
+    isn = (bases.reshape(n_reads, 150) == ord("N")).astype(np.int32)
+    cs = np.concatenate([np.zeros((n_reads, 1), np.int32), np.cumsum(isn, axis=1)], axis=1)
+    windows = int(((cs[:, k:] - cs[:, :-k]) == 0).sum())
+    assert int(counts.sum()) == windows
+    # reverse-complementing every read leaves the canonical count table unchanged
+    comp = np.zeros(256, np.uint8)
+    comp[:] = np.arange(256)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    rc = comp[bases.reshape(n_reads, 150)[:, ::-1]].reshape(-1).copy()
+    c = ok.KmerCounter(k, capacity_hint=60_000_000)
+    c.add_batch(rc, off)
+    k2, n2 = c.finish()
+    c.close()
+    assert np.array_equal(keys, k2) and np.array_equal(counts, n2)
+
+
+def test_invalid_k_messages(golden):
+    for k in golden["count"]["invalid_k"]:
+        with pytest.raises(ok.InvalidKmerSize) as e:
+            ok.KmerCounter(k)
+        assert str(e.value) == golden["count"]["invalid_k_message"].format(k=k)
+        with pytest.raises(ok.InvalidKmerSize):
+            ok.run_build(k, {"a.fa": b">a\nACGT"})
+
+
+# ----------------------------------------------------------------- build / sets / compare --
+def test_build_golden_cases(golden):
+    for case in golden["build"]["cases"]:
+        db = ok.run_build(case["k"], {n: c.encode() for n, c in case["files"].items()})
+        assert db.k == case["k"] and db.num_references() == len(case["files"])
+        for name, want in case["expected"].items():
+            assert list(db.references[name].to_array()) == sorted({canon(s) for s in want}), (case["name"], name)
+        assert db.total_unique_kmers() == case["total_unique"], case["name"]
+
+
+def test_compare_golden_cases(golden):
+    g = golden["compare"]
+    for case in g["cases"]:
+        a = ok.run_build(case["k"], {"db1.fa": case["db1"].encode()}).get_all_kmers_unified()
+        b = ok.run_build(case["k"], {"db2.fa": case["db2"].encode()}).get_all_kmers_unified()
+        r = ok.compare(a, b)
+        assert (r["db1"], r["db2"]) == (case["db1_size"], case["db2_size"]), case["name"]
+        assert r["intersection_size"] == case["intersection_size"]
+        assert r["union_size"] == case["union_size"]
+        assert abs(r["jaccard_index"] - case["jaccard"]) < g["jaccard_tolerance"]
+    a = ok.KmerSet.from_fastx(3, b">a\nACGTACGT")
+    b = ok.KmerSet.from_fastx(4, b">b\nACGTACGT")
+    with pytest.raises(ok.KmerSizeMismatch) as e:
+        a.intersection_size(b)
+    assert str(e.value) == g["mismatch_message"]
+    empty = ok.KmerSet.from_sorted(4, np.zeros(0, np.uint64))
+    assert ok.compare(empty, empty)["jaccard_index"] == 0.0   # compare.rs:62-63
+
+
+def test_sets_random_against_oracle(oracle):
+    rng = np.random.default_rng(77)
+    k = 21
+    base = synth.genome(31, 300_000)
+    gens = [base, synth.mutate(base, 1, 20_000), synth.mutate(base, 2, 50_000), synth.genome(32, 200_000),
+            base[:1000]]
+    sets = [ok.KmerSet.from_fastx(k, synth.fasta_text(b"g%d" % i, g)) for i, g in enumerate(gens)]
+    osets = [oracle.kmer_set_batch(k, g, np.array([0, len(g)], np.uint64)) for g in gens]
+    for s, o in zip(sets, osets):
+        assert len(s) == len(o) and np.array_equal(s.to_array(), o)
+    u = ok.KmerSet.union(sets)
+    assert np.array_equal(u.to_array(), oracle.set_union(osets))
+    sizes, inter = ok.all_vs_all(sets)
+    for i in range(len(sets)):
+        assert sizes[i] == len(osets[i])
+        for j in range(len(sets)):
+            want = oracle.compare(osets[i], osets[j])["intersection_size"]
+            assert inter[i, j] == want, (i, j)
+    # foreign (non-canonical) k=32 set holding u64::MAX
+    weird = np.array([0, 5, 2 ** 64 - 1], dtype=np.uint64)
+    w = ok.KmerSet.from_sorted(32, weird)
+    assert w.probe_counts(np.array([2 ** 64 - 1, 5, 6], np.uint64), np.array([7, 1, 1], np.uint64)) == (2, 8)
+    assert list(ok.KmerSet.union([w, ok.KmerSet.from_sorted(32, np.array([5, 9], np.uint64))]).to_array()) == [0, 5, 9, 2 ** 64 - 1]
+
+
+# ------------------------------------------------------------------------ query / classify --
+def test_query_golden(golden):
+    g = golden["query"]
+    db = ok.run_build(g["k"], {"db.fa": g["db"].encode()})
+    for mh, want in g["ids_by_min_hits"].items():
+        ids, hits = ok.run_query(db, g["reads"].encode(), int(mh))
+        assert list(hits) == g["hits"]
+        assert [i.decode() for i in ids] == want
+
+
+def test_query_random_against_oracle(oracle):
+    k = 31
+    g = synth.genome(50, 500_000)
+    other = synth.genome(51, 500_000)
+    kset = ok.KmerSet.from_fastx(k, synth.fasta_text(b"g", g))
+    oset = oracle.kmer_set_batch(k, g, np.array([0, len(g)], np.uint64))
+    n = 20_000
+    bases = np.concatenate([synth.reads(g, 52, n), synth.reads(other, 53, n)])
+    off = synth.read_offsets(2 * n)
+    hits = kset.probe_reads(bases, off, ok.RAW)
+    want = oracle.query_hits(oset, k, bases, off, 8)
+    assert np.array_equal(hits.astype(np.uint64), want)
+    # ragged reads incl. shorter than k and empty ones
+    rng = np.random.default_rng(4)
+    b2, o2 = random_batch(rng, 200_000, 40)
+    b2[:100_000] = g[:100_000]
+    assert np.array_equal(kset.probe_reads(b2, o2, ok.RAW).astype(np.uint64), oracle.query_hits(oset, k, b2, o2, 4))
+
+
+def test_classify_golden(golden):
+    for case in golden["classify"]["cases"]:
+        k = case["k"]
+        keys, counts = ok.count_fastx(k, [case["input"].encode()], case["min_kmer_frequency"])
+        assert len(keys) == case["total_unique_kmers_in_input"]
+        for dbspec in case["databases"]:
+            db = ok.run_build(k, {n: c.encode() for n, c in dbspec["refs"].items()})
+            union = db.get_all_kmers_unified()
+            assert len(union) == dbspec["total_unique_kmers_in_db"]
+            assert union.probe_counts(keys, counts) == (dbspec["overall_matched"], dbspec["overall_sum_depth"])
+            for name, want in dbspec["per_ref"].items():
+                ref = db.references[name]
+                assert len(ref) == want["total"]
+                assert ref.probe_counts(keys, counts) == (want["matched"], want["sum_depth"]), (case["name"], name)

@@ -1,0 +1,59 @@
+"""The product's host framing (liborion_host.so) against the oracle's needletail restatement."""
+import numpy as np
+import pytest
+
+import orion_kmer_b200 as ok
+
+CASES = [
+    b">seq1\nACGTACGTACGT\n>seq2\nTTTTCCCCGGGGAAAA\n>seq3\nAgCtAgCtNaCcGgTt",
+    b"@read1\nGATTACA\n+\n!!!!!!!\n@read2\nTACATACA\n+\n!!!!!!!!\n@read3\natatatNnN\n+\n!!!!!!!!!",
+    b">seq1\nACGTACGTACGT\n>seq2\nTGCATGCATGCANNNACGT\n>seq3\nGATTACA\nNNNNN\nGATTACA\n",
+    b"@read1\nCGTACGTACG\n+\nFFFFFFFFJJ\n@read3 NNN\nGATTACANNN\n+\nFFFFFFF###\n",
+    b">header1\n>header2\n",
+    b">h desc\r\nAC\r\nGT\r\n>x\r\n\r\nAC GT\tU\r\n\r\n",
+    b">only_header",
+    b"@r\r\nACGT\r\n+\r\n!!!!\r\n\r\n",
+]
+
+
+@pytest.mark.parametrize("content", CASES)
+def test_framing_matches_oracle(oracle, content):
+    recs = oracle.parse_fastx(content)
+    raw = ok.parse_fastx(content, ok.RAW)
+    assert raw.ids == [i for i, _ in recs]
+    assert [bytes(raw.bases[int(raw.offsets[i]):int(raw.offsets[i + 1])]) for i in range(raw.n_records)] == [s for _, s in recs]
+    norm = ok.parse_fastx(content, ok.NORMALIZED)
+    got = [bytes(norm.bases[int(norm.offsets[i]):int(norm.offsets[i + 1])]) for i in range(norm.n_records)]
+    # whitespace removed exactly where needletail's normalize(false) removes it
+    want = [bytes(c for c in s if c not in b" \t\r\n") for _, s in recs]
+    assert got == want
+    assert [len(oracle.normalize(s)) for _, s in recs] == [len(w) for w in want]
+
+
+@pytest.mark.parametrize("bad", [b"", b"This is not fasta content\nACGT", b"@r\nACGT\n+\n!!!\n", b"@r\nACGT\n"])
+def test_framing_errors(oracle, bad):
+    with pytest.raises(ok.FastxError):
+        ok.parse_fastx(bad)
+    with pytest.raises(oracle.FastxError):
+        oracle.parse_fastx(bad)
+
+
+def test_format_counts(oracle):
+    keys = np.array([0, 27, 255], dtype=np.uint64)
+    counts = np.array([1, 12345678901, 3], dtype=np.uint64)
+    assert ok.format_counts(keys, counts, 4) == oracle.format_counts(keys, counts, 4) == b"AAAA\t1\nACGT\t12345678901\nTTTT\t3\n"
+
+
+def test_synth_is_deterministic_and_thread_independent():
+    H = ok.host_lib()
+    g = np.zeros(5000, np.uint8)
+    H.okh_synth_genome(3, len(g), ok._ptr(g))
+    assert set(np.unique(g)) <= set(b"ACGT")
+    a = np.zeros(200 * 150, np.uint8)
+    b = np.zeros(200 * 150, np.uint8)
+    H.okh_synth_reads(ok._ptr(g), len(g), 7, 0, 200, 150, 5000, 1000, ok._ptr(a), 1)
+    H.okh_synth_reads(ok._ptr(g), len(g), 7, 0, 200, 150, 5000, 1000, ok._ptr(b), 4)
+    assert np.array_equal(a, b)
+    c = np.zeros(100 * 150, np.uint8)
+    H.okh_synth_reads(ok._ptr(g), len(g), 7, 100, 100, 150, 5000, 1000, ok._ptr(c), 2)
+    assert np.array_equal(a[100 * 150:], c)

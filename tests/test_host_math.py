@@ -1,0 +1,155 @@
+"""Host-side checks of the arithmetic the kernels run (shared __host__ __device__ code in
+orion_kmer_b200/csrc/kmer_math.cuh), against the reference's golden vectors and the oracle.
+CPU only -- the device runs of the same code are in test_gpu_parity.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orion_kmer_b200 as ok
+
+
+def emulate_extract(bases, offsets, k, norm_mode=ok.NORMALIZED):
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    cap = max(len(bases), 1)
+    out = np.zeros(cap, dtype=np.uint64)
+    n = C.c_uint64()
+    rc = ok.lib().okx_emulate_extract(ok._ptr(bases), len(bases), ok._ptr(offsets), len(offsets) - 1, k, norm_mode,
+                                      ok._ptr(out), cap, C.byref(n))
+    assert rc == 0
+    return out[:n.value]
+
+
+def emulate_table(keys, k, n_home, max_probe=2048, map_mode=1, min_count=1):
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    ok_ = np.zeros(max(len(keys), 1), dtype=np.uint64)
+    oc = np.zeros(max(len(keys), 1), dtype=np.uint64)
+    n, sp = C.c_uint64(), C.c_uint64()
+    rc = ok.lib().okx_emulate_table(ok._ptr(keys), len(keys), k, map_mode, n_home, max_probe, min_count,
+                                    ok._ptr(ok_), ok._ptr(oc), C.byref(n), C.byref(sp))
+    assert rc == 0, ok.lib().ok_last_error()
+    return ok_[:n.value], oc[:n.value], sp.value
+
+
+# ---- src/kmer.rs vectors through the C ABI's host functions -----------------------------------
+def test_kmer_golden_vectors(golden):
+    g = golden["kmer"]
+    for s, k, v in g["seq_to_u64_valid"]:
+        assert ok.seq_to_u64(s.encode(), k) == v
+    for s, k in g["seq_to_u64_none"]:
+        assert ok.seq_to_u64(s.encode(), k) is None
+    for v, k, s in g["u64_to_seq"]:
+        assert ok.u64_to_seq(v, k) == s.encode()
+    for k in g["panic_k"]:
+        with pytest.raises(ok.InvalidKmerSize):
+            ok.u64_to_seq(0, k)
+        with pytest.raises(ok.InvalidKmerSize):
+            ok.reverse_complement_u64(0, k)
+    for a, b in g["reverse_complement"]:
+        assert ok.reverse_complement_u64(ok.seq_to_u64(a.encode(), len(a)), len(a)) == ok.seq_to_u64(b.encode(), len(b))
+    for a, b in g["canonical"]:
+        assert ok.canonical_u64(ok.seq_to_u64(a.encode(), len(a)), len(a)) == ok.seq_to_u64(b.encode(), len(b))
+
+
+def test_every_byte_value_classified_like_the_reference(oracle):
+    """dna_base_to_u64 (kmer.rs:12-20) over all 256 byte values, k=1."""
+    for b in range(256):
+        s = bytes([b])
+        assert ok.seq_to_u64(s, 1) == oracle.seq_to_u64(s, 1), b
+
+
+def test_revcomp_canonical_random(oracle):
+    rng = np.random.default_rng(11)
+    for k in (1, 2, 3, 15, 16, 21, 31, 32):
+        for v in rng.integers(0, 2 ** 63, size=200, dtype=np.uint64):
+            v = int(v) * 2 + int(rng.integers(0, 2))
+            v &= (1 << (2 * k)) - 1
+            assert ok.reverse_complement_u64(v, k) == oracle.reverse_complement_u64(v, k)
+            assert ok.canonical_u64(v, k) == oracle.canonical_u64(v, k)
+
+
+# ---- the extraction walk (pack + window masks + rolling k-mers) ---------------------------------
+ALPHABET = np.frombuffer(b"ACGTacgtNnUuRYKM-.*X \n", dtype=np.uint8)
+
+
+def random_batch(rng, n_bases, mean_len, p_junk=0.02):
+    p = np.full(len(ALPHABET), p_junk / (len(ALPHABET) - 4))
+    p[:4] = (1 - p_junk) / 4
+    bases = rng.choice(ALPHABET, size=n_bases, p=p)
+    cuts = np.unique(rng.integers(0, n_bases + 1, size=max(1, n_bases // mean_len)))
+    off = np.concatenate([[0], cuts, [n_bases]]).astype(np.uint64)
+    # a few empty records
+    off = np.sort(np.concatenate([off, off[1:4]]))
+    return bases, off
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 15, 16, 17, 21, 31, 32])
+@pytest.mark.parametrize("norm", [ok.NORMALIZED, ok.RAW])
+def test_emulated_extract_matches_oracle(oracle, k, norm):
+    rng = np.random.default_rng(100 + k)
+    for n_bases, mean_len in ((0, 1), (1, 1), (31, 7), (32, 40), (33, 5), (1500, 150), (5000, 37), (4096, 4096), (3000, 2)):
+        if n_bases == 0:
+            bases, off = np.zeros(0, np.uint8), np.zeros(1, np.uint64)
+        else:
+            bases, off = random_batch(rng, n_bases, mean_len)
+        got = emulate_extract(bases, off, k, norm)
+        # oracle: NORMALIZED batches are whitespace-free by contract, so strip per record first
+        if norm == ok.NORMALIZED:
+            recs = [bytes(bases[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+            recs = [r.replace(b" ", b"").replace(b"\n", b"") for r in recs]
+            b2, o2 = oracle.batch_from_records(recs)
+            got = emulate_extract(b2, o2, k, norm)
+            want_k, want_c = oracle.count_batch(k, b2, o2, 1, True)
+        else:
+            want_k, want_c = oracle.count_batch(k, bases, off, 1, False)
+        gk, gc = np.unique(got, return_counts=True)
+        assert np.array_equal(gk, want_k), (k, norm, n_bases)
+        assert np.array_equal(gc.astype(np.uint64), want_c)
+
+
+def test_emulated_extract_long_record_with_n_runs(oracle):
+    rng = np.random.default_rng(5)
+    bases = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=20000)
+    for i in range(5):
+        bases[3000 * i + 500:3000 * i + 600] = ord("N")
+    bases[::97] |= 0x20  # lower case
+    off = np.array([0, 20000], dtype=np.uint64)
+    got = emulate_extract(bases, off, 21)
+    want_k, want_c = oracle.count_batch(21, bases, off)
+    gk, gc = np.unique(got, return_counts=True)
+    assert np.array_equal(gk, want_k) and np.array_equal(gc.astype(np.uint64), want_c)
+
+
+# ---- the ordered table (monotone home slot + rank rule of the readout) -------------------------------
+@pytest.mark.parametrize("k,n_home", [(3, 65536), (5, 64), (11, 4096), (21, 3000), (31, 2500), (32, 2500)])
+def test_emulated_table_is_sorted_and_exact(oracle, k, n_home):
+    rng = np.random.default_rng(k)
+    raw = rng.integers(0, 2 ** 63, size=1500, dtype=np.uint64)
+    keys = np.array([oracle.canonical_u64(int(v) & ((1 << (2 * k)) - 1), k) for v in raw], dtype=np.uint64)
+    keys = np.concatenate([keys, keys[:400], keys[:50]])  # duplicates
+    rng.shuffle(keys)
+    for min_count in (1, 2, 3):
+        gk, gc, spilled = emulate_table(keys, k, n_home, min_count=min_count)
+        assert spilled == 0
+        wk, wc = np.unique(keys, return_counts=True)
+        sel = wc >= min_count
+        assert np.array_equal(gk, wk[sel]) and np.array_equal(gc, wc[sel].astype(np.uint64))
+
+
+def test_emulated_table_clustered_keys_stay_sorted(oracle):
+    """keys sharing a long prefix land in one neighbourhood: long displacement runs"""
+    k = 31
+    rng = np.random.default_rng(9)
+    base = int(rng.integers(0, 2 ** 40)) << 20
+    keys = (base + rng.integers(0, 2 ** 20, size=600, dtype=np.uint64)).astype(np.uint64)
+    keys = np.concatenate([keys, rng.integers(0, 2 ** 60, size=600, dtype=np.uint64)])
+    rng.shuffle(keys)
+    gk, gc, spilled = emulate_table(keys, k, 4096, map_mode=0)
+    assert spilled == 0
+    wk, wc = np.unique(keys, return_counts=True)
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc.astype(np.uint64))
+    # with a tight displacement bound the overflow is reported, never silently dropped
+    gk2, gc2, spilled2 = emulate_table(keys, k, 4096, max_probe=64, map_mode=0)
+    assert spilled2 > 0 and int(gc2.sum()) + spilled2 == len(keys)
+    assert np.all(np.diff(gk2.astype(object)) > 0)
