@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- bases/sec counted (canonical k=31), BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R]
+
+A step = one whole count job over one batch of synthetic reads (BASELINE.json configs[1]:
+10M x 150 bp reads, k = 31): empty table -> extract + count every window -> sorted
+(k-mer, count) arrays.  `value` times it with the batch already resident in HBM and the result
+left in HBM; `e2e` times the same job through the C ABI with HOST buffers (page-locked input,
+host result arrays), copies inside the timed region.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+READ_LEN = 150
+GENOME_SEED, READ_SEED = 3, 3
+METRIC = "bases/sec counted (canonical k=31)"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned_array(ok, nbytes, dtype):
+    p = C.c_void_p()
+    ok._check(ok.lib().ok_host_alloc(C.byref(p), nbytes))
+    arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(dtype)
+    return arr, p
+
+
+def make_workload(ok, synth, n_reads, genome_len, first_read=0, pinned=True):
+    g = synth.genome(GENOME_SEED, genome_len)
+    if pinned:
+        bases, pb = pinned_array(ok, n_reads * READ_LEN, np.uint8)
+        off, po = pinned_array(ok, (n_reads + 1) * 8, np.uint64)
+    else:
+        bases, off = np.empty(n_reads * READ_LEN, np.uint8), np.empty(n_reads + 1, np.uint64)
+    synth.reads(g, READ_SEED, n_reads, first_read=first_read, out=bases)
+    synth.read_offsets(n_reads, out=off)
+    return g, bases, off
+
+
+# ------------------------------------------------------------------------------ reference arm --
+def cpu_baseline(n_reads_total, genome_len, sample_reads, all_cores=True):
+    """The CPU restatement of the reference (oracle/, kind 'port': the Rust crate cannot be built
+    here) on a bounded sample of the same workload: faithful single thread (count.rs:68-79 is a
+    sequential loop), plus the all-cores variant labelled as not reference behaviour."""
+    import oracle
+    import orion_kmer_b200 as ok
+    from orion_kmer_b200 import synth
+    oracle.build()
+    sample_reads = min(sample_reads, n_reads_total)
+    _, bases, off = make_workload(ok, synth, sample_reads, genome_len, pinned=False)
+    t0 = time.perf_counter()
+    keys, counts = oracle.count_batch(K, bases, off, 1, True)
+    dt = time.perf_counter() - t0
+    out = {"value": len(bases) / dt, "unit": "bases/s", "cores": 1, "kind": "port",
+           "sample": f"first {sample_reads} reads ({len(bases)} bases) of the workload, {dt:.2f} s, "
+                     f"{len(keys)} distinct",
+           "host_cores_available": os.cpu_count()}
+    if all_cores:
+        nt = min(os.cpu_count() or 1, 64)
+        t0 = time.perf_counter()
+        k2, c2 = oracle.count_batch_mt(K, bases, off, nt)
+        dt2 = time.perf_counter() - t0
+        assert np.array_equal(keys, k2) and np.array_equal(counts, c2)
+        out["all_cores"] = {"value": len(bases) / dt2, "cores": nt,
+                            "note": "NOT reference behaviour (its count loop is single-threaded)"}
+    return out, (bases, off, keys, counts)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_reads = args.reads
+    genome_len = args.genome or n_reads * 5
+    sample = args.sample_reads
+    vals = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, _ = cpu_baseline(n_reads, genome_len, sample, all_cores=False)
+        if i >= args.warmup:
+            vals.append(base["value"])
+    v = float(np.mean(vals))
+    sample_bases = min(sample, n_reads) * READ_LEN
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "bases/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample_bases / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": workload_config(n_reads, genome_len, args.gpus),
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n_reads, genome_len, n_gpus):
+    return {"workload": f"count canonical 31-mers from {n_reads}x150bp synthetic Illumina-like reads "
+                        f"per GPU (BASELINE.json configs[1]{' / configs[2] sharded' if n_gpus > 1 else ''})",
+            "k": K, "reads_per_gpu": n_reads, "read_len": READ_LEN, "genome_len": genome_len,
+            "substitution_rate": 0.005, "n_rate": 0.001, "seeds": [GENOME_SEED, READ_SEED], "min_count": 1,
+            "l2": "batch and table are both far larger than the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------ our arm --
+def run_ours(args):
+    import torch
+    import orion_kmer_b200 as ok
+    from orion_kmer_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    ok.init(local)
+
+    n_reads = args.reads
+    genome_len = args.genome or n_reads * 5
+    if world > 1:
+        from orion_kmer_b200 import multi
+        return multi.bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config,
+                           ClockSampler, measured_peak, METRIC)
+
+    g, bases, off = make_workload(ok, synth, n_reads, genome_len)
+    n_bases = len(bases)
+    d_bases = torch.from_numpy(bases).cuda()
+    d_off = torch.from_numpy(off.view(np.int64)).cuda()
+    hint = args.hint or int(n_bases * 0.17)       # ~error k-mers + genome; the table grows if short
+    counter = ok.KmerCounter(K, ok.NORMALIZED, hint)
+
+    def step_device():
+        counter.clear()
+        counter.add_batch_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads)
+        return counter.finish_device(1)
+
+    def step_host():
+        counter.clear()
+        counter.add_batch_ptr(bases.ctypes.data, off.ctypes.data, n_reads)
+        pk, pc, n = counter.finish_raw(1)
+        counter.free_result(pk, pc)
+        return n
+
+    # ---- value: batch resident in HBM ---------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ok.launch_count()
+    ins_ms, rd_ms, fill_ms, n_launch_insert = [], [], [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, n_distinct = step_device()
+        st = counter.stats()
+        ins_ms.append(st["ms_insert"]); rd_ms.append(st["ms_readout"]); fill_ms.append(st["ms_fill"])
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    launches = ok.launch_count() - launches0
+    clocks = sampler.stop()
+    st = counter.stats()
+    windows, distinct = st["n_windows"], st["n_distinct"]
+
+    # ---- e2e: host buffers through the C ABI ------------------------------------------------
+    for _ in range(max(1, args.warmup)):
+        step_host()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n_out = step_host()
+    torch.cuda.synchronize()
+    dt_e2e = (time.perf_counter() - t0) / args.steps
+
+    # ---- roofline of the dominant kernel (k_extract<SinkCount>: pack + extract + count) -----
+    peak, peak_src = measured_peak()
+    alg_insert = n_bases * 1.5 + windows * 16.0          # B(1+.25+.25) + 16 W
+    alg_step = alg_insert + distinct * 32.0              # + readout 32 D
+    ins = float(np.mean(ins_ms)) / 1e3
+    achieved = alg_insert / ins / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("k_extract_count_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    base, sample = cpu_baseline(n_reads, genome_len, args.sample_reads)
+    # parity spot check of the timed configuration: the sample's table through the same library
+    sb, so, wk, wc = sample
+    chk = ok.KmerCounter(K)
+    chk.add_batch(sb, so)
+    gk, gc = chk.finish(1)
+    chk.close()
+    parity_ok = bool(np.array_equal(gk, wk) and np.array_equal(gc, wc))
+
+    line = {
+        "metric": METRIC, "value": n_bases / dt, "unit": "bases/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(n_reads, genome_len, 1),
+        "e2e": {"value": n_bases / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3,
+                "h2d_bytes_per_step": int(n_bases + (n_reads + 1) * 8), "d2h_bytes_per_step": int(16 * n_out)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_extract<SinkCount> (fused pack+extract+count)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": traffic,
+                     "algorithmic_bytes_per_step": alg_insert, "kernel_ms_per_step": ins * 1e3,
+                     "step": {"algorithmic_bytes": alg_step, "achieved": alg_step / dt / 1e9,
+                              "frac": alg_step / dt / 1e9 / peak}},
+        "phases_ms": {"fill": float(np.mean(fill_ms)), "insert": float(np.mean(ins_ms)),
+                      "readout": float(np.mean(rd_ms))},
+        "table": {"windows": int(windows), "distinct": int(distinct), "slots": int(st["n_slots"]),
+                  "max_displacement": int(st["max_displacement"]), "spilled": int(st["n_spilled"]),
+                  "grows": int(st["n_grows"])},
+        "cpu_baseline": base,
+        "parity_sample_ok": parity_ok,
+    }
+    print(json.dumps(line))
+    counter.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")
+    ap.add_argument("--genome", type=int, default=0, help="genome length (default 5 x reads = 30x coverage)")
+    ap.add_argument("--hint", type=int, default=0, help="expected distinct k-mers per GPU")
+    ap.add_argument("--sample-reads", type=int, default=150_000, help="reads in the CPU baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
