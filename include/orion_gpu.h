@@ -85,6 +85,9 @@ int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const uint64_t* re
 /* same, buffers already resident in device memory (n_bases == rec_offsets[n_records]) */
 int ok_counter_add_batch_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
                                 const uint64_t* d_rec_offsets, uint64_t n_records);
+/* multi-GPU: declare this counter to be shard `rank` of `n_ranks` (1, 2, 4 or 8) key ranges.
+ * Must precede the first batch.  A sharded counter only accepts k-mers it owns. */
+int ok_counter_set_shard(ok_counter* c, int rank, int n_ranks);
 /* multi-GPU: add canonical k-mers received from peers (device pointer), +1 each */
 int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers, uint64_t n);
 /* multi-GPU: extract the batch's canonical k-mers and bucket them by owner rank
@@ -116,6 +119,7 @@ typedef struct ok_counter_stats {
     float ms_insert;         /* device time of the last add_batch kernels     */
     float ms_readout;        /* device time of the last finish kernels        */
     float ms_fill;           /* device time of the last table fill / rebuild  */
+    float ms_route;          /* device time of the last route_batch kernels   */
 } ok_counter_stats;
 int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out);
 

@@ -55,7 +55,7 @@ class CounterStats(C.Structure):
     _fields_ = [("n_slots", C.c_uint64), ("n_distinct", C.c_uint64), ("n_windows", C.c_uint64),
                 ("n_bases", C.c_uint64), ("max_displacement", C.c_uint64), ("n_spilled", C.c_uint64),
                 ("n_grows", C.c_uint64), ("ms_insert", C.c_float), ("ms_readout", C.c_float),
-                ("ms_fill", C.c_float)]
+                ("ms_fill", C.c_float), ("ms_route", C.c_float)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -79,6 +79,7 @@ ABI = {
     "ok_counter_create": (C.c_int, [C.c_uint8, C.c_int, C.c_uint64, C.POINTER(vp)]),
     "ok_counter_add_batch": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "ok_counter_add_batch_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64]),
+    "ok_counter_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
     "ok_counter_add_kmers_device": (C.c_int, [vp, vp, C.c_uint64]),
     "ok_counter_route_batch_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp]),
     "ok_counter_finish": (C.c_int, [vp, C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]),
@@ -105,6 +106,7 @@ _HOOKS = {
     "okx_emulate_extract": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64, C.c_uint, C.c_int, vp, C.c_uint64, u64p]),
     "okx_emulate_table": (C.c_int, [vp, C.c_uint64, C.c_uint, C.c_int, C.c_uint64, C.c_uint, C.c_uint64, vp, vp, u64p, u64p]),
     "okx_device_extract": (C.c_int, [vp, vp, C.c_uint64, C.c_uint, C.c_int, vp, C.c_uint64, u64p]),
+    "okx_owner_of": (C.c_int, [vp, C.c_uint64, C.c_uint, C.c_int, vp]),
 }
 
 _gpu = None
@@ -302,6 +304,16 @@ class KmerCounter:
 
     def add_batch_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records):
         _check(lib().ok_counter_add_batch_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records))
+
+    def set_shard(self, rank, n_ranks):
+        _check(lib().ok_counter_set_shard(self._h, rank, n_ranks))
+
+    def route_batch_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, n_ranks, d_out_ptr):
+        """-> per-rank k-mer counts; d_out holds the k-mers rank after rank"""
+        counts = np.zeros(n_ranks, dtype=np.uint64)
+        _check(lib().ok_counter_route_batch_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records,
+                                                   n_ranks, d_out_ptr, _ptr(counts)))
+        return counts
 
     def add_kmers_device(self, d_kmers_ptr, n):
         _check(lib().ok_counter_add_kmers_device(self._h, d_kmers_ptr, n))

@@ -20,8 +20,10 @@ struct OkSlot { unsigned long long key; unsigned long long count; };  // 16 B, o
 
 struct OkTableView {
     OkSlot* slots;
-    uint64_t n_home;      // home slots (the map's range)
+    uint64_t n_home;      // home slots held here
     uint64_t n_total;     // n_home + tail padding (probing never wraps)
+    uint64_t n_home_all;  // home slots of the whole (possibly sharded) table: the map's range
+    uint64_t home_base;   // first home slot of this shard within that range
     unsigned key_shift;   // 64 - 2k
     int map_mode;         // OK_MAP_*
     unsigned max_probe;   // displacement bound L; inserts beyond it are spilled, never lost
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) k_fill_u64(unsigned long long* p, uint64_
 // key could not be placed within max_probe slots of its home (caller spills it).
 __device__ __forceinline__ bool ok_table_add(const OkTableView& t, uint64_t key, uint64_t inc,
                                              unsigned& newkeys, unsigned& maxd) {
-    const uint64_t h = ok_home_slot(key, t.key_shift, t.map_mode, t.n_home);
+    const uint64_t h = ok_home_slot(key, t.key_shift, t.map_mode, t.n_home_all) - t.home_base;
     uint64_t lim = h + t.max_probe;
     if (lim > t.n_total) lim = t.n_total;
     for (uint64_t i = h; i < lim; ++i) {
@@ -229,20 +231,13 @@ __device__ __forceinline__ uint64_t ok_lower_bound(const uint64_t* __restrict__ 
     return lo;
 }
 
-template <bool MAP_U, class Sink>
-__global__ void __launch_bounds__(256)
-k_extract(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
-          uint64_t n_rec, uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp, unsigned k,
-          Sink sink_in) {
-    Sink sink = sink_in;
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-    uint64_t t0 = tile_begin + warp * tiles_per_warp;
-    if (t0 >= tile_end) return;
-    uint64_t t1 = t0 + tiles_per_warp;
-    if (t1 > tile_end) t1 = tile_end;
-
-    sink.begin();
+// The walk shared by every extraction kernel: per_group(pos, prev_codes, cur_codes, okmask) is
+// called by ALL 32 lanes once per tile (so it may use warp collectives); pos is the stream
+// position of the lane's first base, okmask the countable windows ending in its group.
+template <bool MAP_U, class PerGroup>
+__device__ __forceinline__ void ok_walk_tiles(const uint8_t* __restrict__ bases, uint64_t n_bases,
+                                              const uint64_t* __restrict__ rec_off, uint64_t n_rec,
+                                              uint64_t t0, uint64_t t1, unsigned k, int lane, PerGroup&& per_group) {
     uint64_t carry_codes = 0; uint32_t carry_valid = 0, carry_start = 0;
     uint64_t r_next = 0;
     if (t0 > 0) {  // warm-up on the tile before ours: its last group is our first halo
@@ -268,15 +263,100 @@ k_extract(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* _
         carry_codes = __shfl_sync(OK_FULL, cur_codes, 31);
         carry_valid = __shfl_sync(OK_FULL, cur_valid, 31);
         carry_start = __shfl_sync(OK_FULL, cur_start, 31);
-        const uint32_t okmask = ok_window_mask(prev_valid, cur_valid, prev_start, cur_start, k);
-        if (okmask) {
-            sink.group_begin(pos);
-            ok_lane_windows(prev_codes, cur_codes, okmask, k,
-                            [&](int j, uint64_t key) { sink(pos + j, key); });
-            sink.group_end();
+        per_group(pos, prev_codes, cur_codes, ok_window_mask(prev_valid, cur_valid, prev_start, cur_start, k));
+    }
+}
+
+// warp -> its run of tiles; false when the warp has nothing to do
+__device__ __forceinline__ bool ok_warp_tiles(uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp,
+                                              uint64_t& t0, uint64_t& t1) {
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    t0 = tile_begin + warp * tiles_per_warp;
+    if (t0 >= tile_end) return false;
+    t1 = t0 + tiles_per_warp;
+    if (t1 > tile_end) t1 = tile_end;
+    return true;
+}
+
+template <bool MAP_U, class Sink>
+__global__ void __launch_bounds__(256)
+k_extract(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
+          uint64_t n_rec, uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp, unsigned k,
+          Sink sink_in) {
+    Sink sink = sink_in;
+    uint64_t t0, t1;
+    if (!ok_warp_tiles(tile_begin, tile_end, tiles_per_warp, t0, t1)) return;
+    sink.begin();
+    ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t1, k, threadIdx.x & 31,
+        [&](uint64_t pos, uint64_t prev_codes, uint64_t cur_codes, uint32_t okmask) {
+            if (okmask) {
+                sink.group_begin(pos);
+                ok_lane_windows(prev_codes, cur_codes, okmask, k, [&](int j, uint64_t key) { sink(pos + j, key); });
+                sink.group_end();
+            }
+        });
+    sink.end();
+}
+
+// ---------------------------------------------------------------- multi-GPU routing kernels --
+// Owner of a canonical k-mer = its slice of the (prior-straightened) key space, so every rank
+// ends up with a contiguous key range: per-GPU tables are disjoint and the global sorted table
+// is the concatenation of the ranks' outputs.  PASS 0 counts k-mers per owner; PASS 1 writes
+// them, owner after owner, at the cursors the host derived from pass 0.
+template <bool MAP_U, int G, int PASS>
+__global__ void __launch_bounds__(256)
+k_route(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
+        uint64_t n_rec, uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp, unsigned k,
+        unsigned key_shift, int map_mode, unsigned long long* __restrict__ cursors /*[G]*/,
+        unsigned long long* __restrict__ out) {
+    uint64_t t0, t1;
+    if (!ok_warp_tiles(tile_begin, tile_end, tiles_per_warp, t0, t1)) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long tot[G];
+#pragma unroll
+    for (int r = 0; r < G; ++r) tot[r] = 0;
+    ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t1, k, lane,
+        [&](uint64_t, uint64_t prev_codes, uint64_t cur_codes, uint32_t okmask) {
+            unsigned cnt[G];
+#pragma unroll
+            for (int r = 0; r < G; ++r) cnt[r] = 0;
+            ok_lane_windows(prev_codes, cur_codes, okmask, k, [&](int, uint64_t key) {
+                const int o = (int)ok_home_slot(key, key_shift, map_mode, (uint64_t)G);
+#pragma unroll
+                for (int r = 0; r < G; ++r) cnt[r] += (o == r) ? 1u : 0u;
+            });
+            if (PASS == 0) {
+#pragma unroll
+                for (int r = 0; r < G; ++r) tot[r] += cnt[r];
+            } else {
+                unsigned long long wr[G];   // this lane's next write position per owner
+#pragma unroll
+                for (int r = 0; r < G; ++r) {
+                    unsigned inc = cnt[r];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
+                    const unsigned total = __shfl_sync(OK_FULL, inc, 31);
+                    unsigned long long base = 0;
+                    if (lane == 0 && total) base = atomicAdd(&cursors[r], (unsigned long long)total);
+                    base = __shfl_sync(OK_FULL, base, 0);
+                    wr[r] = base + inc - cnt[r];
+                }
+                ok_lane_windows(prev_codes, cur_codes, okmask, k, [&](int, uint64_t key) {
+                    const int o = (int)ok_home_slot(key, key_shift, map_mode, (uint64_t)G);
+                    unsigned long long p = 0;
+#pragma unroll
+                    for (int r = 0; r < G; ++r) if (o == r) { p = wr[r]; wr[r] = p + 1; }
+                    out[p] = key;
+                });
+            }
+        });
+    if (PASS == 0) {
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+            unsigned long long v = ok_warp_sum(tot[r]);
+            if (lane == 0 && v) atomicAdd(&cursors[r], v);
         }
     }
-    sink.end();
 }
 
 // standalone 2-bit packing kernel (subsystem 1 of the north star); one group per thread
@@ -424,7 +504,7 @@ k_readout_write(OkTableView t, uint64_t min_count, const unsigned long long* __r
         for (int i = 0; i < 8; ++i) { unsigned w = wsum[i]; woff += i < wid ? w : 0u; tot += w; }
         const unsigned long long before = running + woff + __popc(bal & ((1u << lane) - 1u));
         if (surv) {
-            const uint64_t h = ok_home_slot(key, t.key_shift, t.map_mode, t.n_home);
+            const uint64_t h = ok_home_slot(key, t.key_shift, t.map_mode, t.n_home_all) - t.home_base;
             const long long adj = ok_rank_adjust<FILTER>(
                 [&](uint64_t q, uint64_t& kq, uint64_t& cq) { ok_ld_slot(slots + q, kq, cq); },
                 s, key, h, t.max_probe, t.n_total, min_count);

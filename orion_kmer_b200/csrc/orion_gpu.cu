@@ -108,6 +108,7 @@ struct ok_counter {
     unsigned k = 0;
     int norm_mode = 0;
     uint64_t hint = 0;
+    int shard_rank = 0, n_shards = 1;   // multi-GPU: this table holds one key range of n_shards
     cudaStream_t s_main = nullptr, s_copy = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     std::vector<cudaEvent_t> ev_chunks;
@@ -117,7 +118,7 @@ struct ok_counter {
     OkDevStats* h_stats = nullptr;    // pinned mirror
     OkSpill spill{};
     uint64_t occupied = 0, windows = 0, bases_seen = 0, max_disp = 0, spilled_total = 0, grows = 0;
-    float ms_insert = 0, ms_readout = 0, ms_fill = 0;
+    float ms_insert = 0, ms_readout = 0, ms_fill = 0, ms_route = 0;
     // staging for host batches
     uint8_t* d_bases = nullptr; uint64_t cap_bases = 0;
     uint64_t* d_off = nullptr; uint64_t cap_off = 0;
@@ -142,6 +143,8 @@ int table_alloc(ok_counter* c, uint64_t n_home, OkTableView* out) {
     OkTableView t{};
     t.n_home = n_home;
     t.n_total = n_home + MAX_PROBE;
+    t.n_home_all = n_home * (uint64_t)c->n_shards;
+    t.home_base = n_home * (uint64_t)c->shard_rank;
     t.key_shift = 64 - 2 * c->k;
     t.map_mode = OK_MAP_CANON;
     t.max_probe = MAX_PROBE;
@@ -493,6 +496,7 @@ OK_EXPORT int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers
     if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_add_kmers_device: NULL handle");
     if (n == 0) return OK_SUCCESS;
     if (!d_kmers) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL d_kmers");
+    c->ms_insert = 0; c->ms_fill = 0;
     uint64_t done = 0;
     while (done < n) {
         uint64_t allowed = 0;
@@ -515,11 +519,67 @@ OK_EXPORT int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers
     return OK_SUCCESS;
 }
 
+OK_EXPORT int ok_counter_set_shard(ok_counter* c, int rank, int n_ranks) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_set_shard: NULL handle");
+    if (n_ranks != 1 && n_ranks != 2 && n_ranks != 4 && n_ranks != 8)
+        return set_err(OK_ERR_INVALID_ARGUMENT, "n_ranks must be 1, 2, 4 or 8 (got %d)", n_ranks);
+    if (rank < 0 || rank >= n_ranks) return set_err(OK_ERR_INVALID_ARGUMENT, "rank %d out of range", rank);
+    if (c->tv.slots) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_set_shard must precede the first batch");
+    c->shard_rank = rank; c->n_shards = n_ranks;
+    return OK_SUCCESS;
+}
+
+namespace {
+template <int G, int PASS>
+void launch_route(const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec, unsigned k,
+                  int norm_mode, unsigned long long* cursors, unsigned long long* out, cudaStream_t st) {
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    const uint64_t max_warps = (uint64_t)(g_sms > 0 ? g_sms : 148) * 8 * 8;
+    const uint64_t tpw = std::max<uint64_t>(1, (n_tiles + max_warps - 1) / max_warps);
+    const unsigned blocks = (unsigned)(((n_tiles + tpw - 1) / tpw + 7) / 8);
+    auto kern = norm_mode == OK_NORM_NORMALIZED ? k_route<true, G, PASS> : k_route<false, G, PASS>;
+    LAUNCH(kern, blocks, 256, 0, st, d_bases, n_bases, d_off, n_rec, (uint64_t)0, n_tiles, tpw, k, 64 - 2 * k,
+           (int)OK_MAP_CANON, cursors, out);
+}
+template <int PASS>
+void launch_route_g(int g, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec,
+                    unsigned k, int norm_mode, unsigned long long* cursors, unsigned long long* out, cudaStream_t st) {
+    switch (g) {
+        case 1: launch_route<1, PASS>(d_bases, n_bases, d_off, n_rec, k, norm_mode, cursors, out, st); break;
+        case 2: launch_route<2, PASS>(d_bases, n_bases, d_off, n_rec, k, norm_mode, cursors, out, st); break;
+        case 4: launch_route<4, PASS>(d_bases, n_bases, d_off, n_rec, k, norm_mode, cursors, out, st); break;
+        default: launch_route<8, PASS>(d_bases, n_bases, d_off, n_rec, k, norm_mode, cursors, out, st); break;
+    }
+}
+}  // namespace
+
 OK_EXPORT int ok_counter_route_batch_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
                                             const uint64_t* d_rec_offsets, uint64_t n_records, int n_ranks,
                                             uint64_t* d_out, uint64_t* out_counts) {
-    (void)c; (void)d_bases; (void)n_bases; (void)d_rec_offsets; (void)n_records; (void)n_ranks; (void)d_out; (void)out_counts;
-    return set_err(OK_ERR_INTERNAL, "ok_counter_route_batch_device: not built yet");
+    if (!c || !out_counts) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_route_batch_device: NULL argument");
+    if (n_ranks != 1 && n_ranks != 2 && n_ranks != 4 && n_ranks != 8)
+        return set_err(OK_ERR_INVALID_ARGUMENT, "n_ranks must be 1, 2, 4 or 8 (got %d)", n_ranks);
+    for (int r = 0; r < n_ranks; ++r) out_counts[r] = 0;
+    if (n_bases == 0 || n_records == 0) return OK_SUCCESS;
+    if (!d_bases || !d_rec_offsets || !d_out) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL batch pointer");
+    if ((uintptr_t)d_bases & 15u) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
+    unsigned long long* cur = c->d_stats->route_counts;
+    CU(cudaEventRecord(c->ev_a, c->s_main));
+    CU(cudaMemsetAsync(cur, 0, 8 * sizeof(unsigned long long), c->s_main));
+    launch_route_g<0>(n_ranks, d_bases, n_bases, d_rec_offsets, n_records, c->k, c->norm_mode, cur, nullptr, c->s_main);
+    unsigned long long h[8] = {0};
+    CU(cudaMemcpyAsync(h, cur, sizeof h, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    unsigned long long base[8] = {0}, run = 0;
+    for (int r = 0; r < n_ranks; ++r) { out_counts[r] = h[r]; base[r] = run; run += h[r]; }
+    CU(cudaMemcpyAsync(cur, base, sizeof base, cudaMemcpyHostToDevice, c->s_main));
+    launch_route_g<1>(n_ranks, d_bases, n_bases, d_rec_offsets, n_records, c->k, c->norm_mode, cur,
+                      (unsigned long long*)d_out, c->s_main);
+    CU(cudaEventRecord(c->ev_b, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&c->ms_route, c->ev_a, c->ev_b);
+    return OK_SUCCESS;
 }
 
 OK_EXPORT int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t** d_kmers,
@@ -555,7 +615,7 @@ OK_EXPORT int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out) {
     if (!c || !out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_get_stats: NULL argument");
     out->n_slots = c->tv.n_total; out->n_distinct = c->occupied; out->n_windows = c->windows;
     out->n_bases = c->bases_seen; out->max_displacement = c->max_disp; out->n_spilled = c->spilled_total;
-    out->n_grows = c->grows; out->ms_insert = c->ms_insert; out->ms_readout = c->ms_readout; out->ms_fill = c->ms_fill;
+    out->n_grows = c->grows; out->ms_insert = c->ms_insert; out->ms_readout = c->ms_readout; out->ms_fill = c->ms_fill; out->ms_route = c->ms_route;
     return OK_SUCCESS;
 }
 
@@ -920,5 +980,12 @@ OK_EXPORT int okx_device_extract(const uint8_t* bases, const uint64_t* rec_off, 
     CU(cudaMemcpy(out, d_out, std::min<uint64_t>(n, cap) * 8, cudaMemcpyDeviceToHost));
     cudaFree(d_b); cudaFree(d_o); cudaFree(d_out); cudaFree(d_n);
     *n_out = n;
+    return OK_SUCCESS;
+}
+
+// owner rank of each key under the routing rule of k_route (host evaluation of the same code)
+OK_EXPORT int okx_owner_of(const uint64_t* keys, uint64_t n, unsigned k, int n_ranks, int32_t* out) {
+    if (k == 0 || k > 32) return invalid_k(k);
+    for (uint64_t i = 0; i < n; ++i) out[i] = (int32_t)ok_home_slot(keys[i], 64 - 2 * k, OK_MAP_CANON, (uint64_t)n_ranks);
     return OK_SUCCESS;
 }
