@@ -104,6 +104,10 @@ int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** kmers, uint6
 /* same, results left in device memory owned by the handle (valid until the next call on it) */
 int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t** d_kmers,
                              const uint64_t** d_counts, uint64_t* n);
+/* which count path to use: 0 = automatic (large one-shot batches go through the partitioned
+ * shared-memory path, everything else through the device-wide table), 1 = table only,
+ * 2 = partitioned whenever the counter is still empty.  Results are identical. */
+int ok_counter_set_path(ok_counter* c, int mode);
 /* forget all counts, keep the allocation (bench loops) */
 int ok_counter_clear(ok_counter* c);
 int ok_counter_destroy(ok_counter* c);
@@ -120,6 +124,9 @@ typedef struct ok_counter_stats {
     float ms_readout;        /* device time of the last finish kernels        */
     float ms_fill;           /* device time of the last table fill / rebuild  */
     float ms_route;          /* device time of the last route_batch kernels   */
+    /* partitioned (one-shot) path: device time per phase of the last batch          */
+    float ms_sample, ms_scatter1, ms_scatter2, ms_count, ms_compact;
+    int partitioned;         /* 1 when the current result is a sorted run     */
 } ok_counter_stats;
 int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out);
 

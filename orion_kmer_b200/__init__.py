@@ -55,7 +55,9 @@ class CounterStats(C.Structure):
     _fields_ = [("n_slots", C.c_uint64), ("n_distinct", C.c_uint64), ("n_windows", C.c_uint64),
                 ("n_bases", C.c_uint64), ("max_displacement", C.c_uint64), ("n_spilled", C.c_uint64),
                 ("n_grows", C.c_uint64), ("ms_insert", C.c_float), ("ms_readout", C.c_float),
-                ("ms_fill", C.c_float), ("ms_route", C.c_float)]
+                ("ms_fill", C.c_float), ("ms_route", C.c_float), ("ms_sample", C.c_float),
+                ("ms_scatter1", C.c_float), ("ms_scatter2", C.c_float), ("ms_count", C.c_float),
+                ("ms_compact", C.c_float), ("partitioned", C.c_int)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -84,6 +86,7 @@ ABI = {
     "ok_counter_route_batch_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp]),
     "ok_counter_finish": (C.c_int, [vp, C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]),
     "ok_counter_finish_device": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp), u64p]),
+    "ok_counter_set_path": (C.c_int, [vp, C.c_int]),
     "ok_counter_clear": (C.c_int, [vp]),
     "ok_counter_destroy": (C.c_int, [vp]),
     "ok_counter_get_stats": (C.c_int, [vp, C.POINTER(CounterStats)]),
@@ -342,6 +345,10 @@ class KmerCounter:
         dk, dc, n = vp(), vp(), C.c_uint64()
         _check(lib().ok_counter_finish_device(self._h, min_count, C.byref(dk), C.byref(dc), C.byref(n)))
         return dk.value, dc.value, n.value
+
+    def set_path(self, mode):
+        """0 automatic, 1 table only, 2 partitioned whenever the counter is empty"""
+        _check(lib().ok_counter_set_path(self._h, mode))
 
     def clear(self):
         _check(lib().ok_counter_clear(self._h))

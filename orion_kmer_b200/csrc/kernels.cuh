@@ -237,10 +237,13 @@ __device__ __forceinline__ uint64_t ok_lower_bound(const uint64_t* __restrict__ 
 template <bool MAP_U, class PerGroup>
 __device__ __forceinline__ void ok_walk_tiles(const uint8_t* __restrict__ bases, uint64_t n_bases,
                                               const uint64_t* __restrict__ rec_off, uint64_t n_rec,
-                                              uint64_t t0, uint64_t t1, unsigned k, int lane, PerGroup&& per_group) {
+                                              uint64_t t0, uint64_t t1, uint64_t t_live, unsigned k, int lane,
+                                              PerGroup&& per_group) {
+    // tiles >= t_live do not exist: per_group is still called (okmask 0) so that kernels whose
+    // warps iterate in lock step keep their barriers aligned
     uint64_t carry_codes = 0; uint32_t carry_valid = 0, carry_start = 0;
     uint64_t r_next = 0;
-    if (t0 > 0) {  // warm-up on the tile before ours: its last group is our first halo
+    if (t0 > 0 && t0 < t_live) {  // warm-up on the tile before ours: its last group is our first halo
         const uint64_t ws = (t0 - 1) * OK_TILE_BASES;
         r_next = ok_lower_bound(rec_off, n_rec, ws);
         uint64_t c; uint32_t v;
@@ -253,6 +256,7 @@ __device__ __forceinline__ void ok_walk_tiles(const uint8_t* __restrict__ bases,
     for (uint64_t t = t0; t < t1; ++t) {
         const uint64_t ws = t * OK_TILE_BASES;
         const uint64_t pos = ws + 32u * lane;
+        if (t >= t_live) { per_group(pos, 0ull, 0ull, 0u); continue; }
         uint64_t cur_codes; uint32_t cur_valid;
         ok_load_group<MAP_U>(bases, n_bases, pos, cur_codes, cur_valid);
         uint32_t cur_start = ok_tile_starts(rec_off, n_rec, ws, r_next, lane);
@@ -287,7 +291,7 @@ k_extract(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* _
     uint64_t t0, t1;
     if (!ok_warp_tiles(tile_begin, tile_end, tiles_per_warp, t0, t1)) return;
     sink.begin();
-    ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t1, k, threadIdx.x & 31,
+    ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t1, t1, k, threadIdx.x & 31,
         [&](uint64_t pos, uint64_t prev_codes, uint64_t cur_codes, uint32_t okmask) {
             if (okmask) {
                 sink.group_begin(pos);
@@ -315,7 +319,7 @@ k_route(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __r
     unsigned long long tot[G];
 #pragma unroll
     for (int r = 0; r < G; ++r) tot[r] = 0;
-    ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t1, k, lane,
+    ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t1, t1, k, lane,
         [&](uint64_t, uint64_t prev_codes, uint64_t cur_codes, uint32_t okmask) {
             unsigned cnt[G];
 #pragma unroll

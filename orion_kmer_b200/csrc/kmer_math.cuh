@@ -141,6 +141,24 @@ OK_HD void ok_lane_windows(uint64_t prev_codes, uint64_t cur_codes, uint32_t okm
     }
 }
 
+// same walk, fully unrolled: j is a compile-time constant inside emit (register-array indexing)
+template <class Emit>
+OK_HD void ok_lane_windows_full(uint64_t prev_codes, uint64_t cur_codes, uint32_t okmask, unsigned k,
+                                Emit&& emit) {
+    if (okmask == 0) return;
+    const uint64_t mask = ok_mask_k(k);
+    const unsigned hs = 2 * (k - 1);
+    uint64_t fwd = prev_codes & mask;
+    uint64_t rc = ok_revcomp(fwd, k);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        uint64_t c = (cur_codes >> (62 - 2 * j)) & 3ull;
+        fwd = ((fwd << 2) | c) & mask;
+        rc = (rc >> 2) | ((3ull - c) << hs);
+        if (okmask & (0x80000000u >> j)) emit(j, fwd < rc ? fwd : rc);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Slot placement.  MONOTONE maps send a key to a home slot that never decreases with the key,
 // so linear probing leaves the table sorted up to short local displacements and the sorted

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -12,6 +13,7 @@
 
 #include "orion_gpu.h"
 #include "kernels.cuh"
+#include "partition.cuh"
 
 #define OK_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -126,6 +128,19 @@ struct ok_counter {
     unsigned long long* d_tiles = nullptr; uint64_t cap_tiles = 0;   // [n_tiles] + total
     unsigned long long* d_out_keys = nullptr; uint64_t cap_out_keys = 0;
     unsigned long long* d_out_counts = nullptr; uint64_t cap_out_counts = 0;
+    // partitioned (one-shot) path: its result is a sorted run instead of a table
+    int path_mode = 0;                 // 0 auto, 1 table only, 2 partitioned whenever the counter is empty
+    bool run_valid = false;
+    unsigned long long* d_run_keys = nullptr; uint64_t cap_run_keys = 0;
+    unsigned long long* d_run_counts = nullptr; uint64_t cap_run_counts = 0;
+    uint64_t n_run = 0;
+    unsigned long long* d_buf1 = nullptr; uint64_t cap_buf1 = 0;
+    unsigned long long* d_buf2 = nullptr; uint64_t cap_buf2 = 0;
+    unsigned long long* d_meta = nullptr; uint64_t cap_meta = 0;     // beg | cursor | cap_end | scan (per sub-partition) + level-1 arrays
+    unsigned* d_hist = nullptr; uint64_t cap_hist = 0;               // sample histogram / n_distinct
+    unsigned long long* d_items = nullptr; uint64_t cap_items = 0;   // level-2 work items
+    float ms_sample = 0, ms_scatter1 = 0, ms_scatter2 = 0, ms_count = 0, ms_compact = 0;
+    cudaEvent_t ev_p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -309,6 +324,297 @@ int counter_readout(ok_counter* c, uint64_t min_count, uint64_t* n_out) {
 
 }  // namespace
 
+// ===================================================================== partitioned path ==
+namespace {
+
+constexpr uint64_t PART_MIN_BASES = 1ull << 20;   // below this the table path is as fast
+constexpr unsigned PART_TARGET = 4096;            // keys per sub-partition if every key were distinct
+constexpr unsigned PART_MAX_BITS = 18;            // 8 bits at level 1 + up to 10 at level 2
+
+struct PartPlan {
+    OkPartCfg cfg{};
+    unsigned n_sub = 1, n_bin1 = 1;
+    uint64_t total_cap = 0;
+    // device arrays inside c->d_meta
+    unsigned long long *beg = nullptr, *cursor = nullptr, *cap_end = nullptr, *scan = nullptr;
+    unsigned long long *cursor1 = nullptr, *end1 = nullptr;
+    std::vector<unsigned long long> h_beg, h_end, h_beg1, h_end1;
+};
+
+bool part_eligible(const ok_counter* c, uint64_t n_units) {
+    if (c->path_mode == 1) return false;
+    if (c->run_valid || c->occupied) return false;
+    if (n_units >= (1ull << 32)) return false;
+    return c->path_mode == 2 || n_units >= PART_MIN_BASES;
+}
+
+// sizes every sub-partition from the sample histogram and lays the buffers out
+int part_plan(ok_counter* c, uint64_t n_units, uint64_t sample_stride, PartPlan& pl) {
+    const unsigned n_sub = pl.n_sub;
+    std::vector<unsigned> hist(n_sub);
+    CU(cudaMemcpyAsync(hist.data(), c->d_hist, n_sub * sizeof(unsigned), cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    pl.h_beg.resize(n_sub); pl.h_end.resize(n_sub);
+    uint64_t run = 0;
+    for (unsigned p = 0; p < n_sub; ++p) {
+        uint64_t est = (uint64_t)hist[p] * sample_stride;
+        uint64_t cap = est;
+        if (sample_stride > 1) cap += (uint64_t)(4.0 * std::sqrt((double)est * (double)sample_stride)) + 64;
+        if (cap > n_units) cap = n_units;
+        pl.h_beg[p] = run; run += cap; pl.h_end[p] = run;
+    }
+    pl.total_cap = run;
+    const unsigned b2n = 1u << pl.cfg.b2;
+    pl.h_beg1.resize(pl.n_bin1); pl.h_end1.resize(pl.n_bin1);
+    for (unsigned b = 0; b < pl.n_bin1; ++b) { pl.h_beg1[b] = pl.h_beg[(uint64_t)b * b2n]; pl.h_end1[b] = pl.h_end[(uint64_t)(b + 1) * b2n - 1]; }
+    // device copies: beg | cursor | cap_end | scan(n_sub+1) | cursor1 | end1
+    const uint64_t need = 4ull * n_sub + 1 + 2ull * pl.n_bin1;
+    TRY(dev_reserve(&c->d_meta, &c->cap_meta, need));
+    pl.beg = c->d_meta; pl.cursor = pl.beg + n_sub; pl.cap_end = pl.cursor + n_sub; pl.scan = pl.cap_end + n_sub;
+    pl.cursor1 = pl.scan + n_sub + 1; pl.end1 = pl.cursor1 + pl.n_bin1;
+    CU(cudaMemcpyAsync(pl.beg, pl.h_beg.data(), n_sub * 8, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(pl.cursor, pl.h_beg.data(), n_sub * 8, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(pl.cap_end, pl.h_end.data(), n_sub * 8, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(pl.cursor1, pl.h_beg1.data(), pl.n_bin1 * 8, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(pl.end1, pl.h_end1.data(), pl.n_bin1 * 8, cudaMemcpyHostToDevice, c->s_main));
+    TRY(dev_reserve(&c->d_buf2, &c->cap_buf2, pl.total_cap + 1));
+    TRY(dev_reserve(&c->d_buf1, &c->cap_buf1, pl.total_cap + 1));   // level-1 output, later the counts of the runs
+    return OK_SUCCESS;
+}
+
+void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl) {
+    uint64_t want = (n_units + PART_TARGET - 1) / PART_TARGET;
+    unsigned bits = 0;
+    while ((1ull << bits) < want && bits < PART_MAX_BITS) ++bits;
+    pl.cfg.key_shift = 64 - 2 * c->k;
+    pl.cfg.shard_log2 = 0;
+    for (int g = c->n_shards; g > 1; g >>= 1) ++pl.cfg.shard_log2;
+    pl.cfg.b1 = std::min(bits, 8u);
+    pl.cfg.b2 = bits - pl.cfg.b1;
+    pl.n_sub = 1u << bits;
+    pl.n_bin1 = 1u << pl.cfg.b1;
+}
+
+template <class K> int set_smem(K kern, size_t bytes) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return OK_SUCCESS;
+}
+
+// level 2 + count + compact, shared by the two entry points.  `lvl1` = keys already scattered
+// into level-1 bins in d_buf1 (b2 > 0) or straight into sub-partitions in d_buf2 (b2 == 0).
+int part_finish(ok_counter* c, PartPlan& pl) {
+    const OkPartSpill ps{c->spill, c->d_stats};
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    if (pl.cfg.b2 > 0) {
+        // level-1 fills -> work items of <= 8192 keys
+        std::vector<unsigned long long> cur1(pl.n_bin1);
+        CU(cudaMemcpyAsync(cur1.data(), pl.cursor1, pl.n_bin1 * 8, cudaMemcpyDeviceToHost, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        std::vector<unsigned long long> item_off; std::vector<unsigned> item_n, item_bin;
+        for (unsigned b = 0; b < pl.n_bin1; ++b) {
+            const uint64_t e = std::min<uint64_t>(cur1[b], pl.h_end1[b]);
+            for (uint64_t o = pl.h_beg1[b]; o < e; o += OK_PART_TILE) {
+                item_off.push_back(o); item_n.push_back((unsigned)std::min<uint64_t>(OK_PART_TILE, e - o)); item_bin.push_back(b);
+            }
+        }
+        const uint64_t ni = item_off.size();
+        if (ni) {
+            TRY(dev_reserve(&c->d_items, &c->cap_items, 2 * ni + 2));
+            unsigned* d_n = (unsigned*)(c->d_items + ni);
+            unsigned* d_b = d_n + ni;
+            CU(cudaMemcpyAsync(c->d_items, item_off.data(), ni * 8, cudaMemcpyHostToDevice, c->s_main));
+            CU(cudaMemcpyAsync(d_n, item_n.data(), ni * 4, cudaMemcpyHostToDevice, c->s_main));
+            CU(cudaMemcpyAsync(d_b, item_bin.data(), ni * 4, cudaMemcpyHostToDevice, c->s_main));
+            TRY(set_smem(k_part_scatter_keys<2>, sizeof(OkScatterSmem)));
+            const unsigned grid = (unsigned)std::min<uint64_t>(ni, (uint64_t)grid_sm * 2);
+            LAUNCH(k_part_scatter_keys<2>, grid, 256, sizeof(OkScatterSmem), c->s_main, c->d_buf1, c->d_items, d_n, d_b,
+                   (unsigned)ni, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps);
+            CU(cudaStreamSynchronize(c->s_main));   // the host vectors above must outlive the copies
+        }
+    }
+    CU(cudaEventRecord(c->ev_p[3], c->s_main));
+    // count every sub-partition in shared memory; sorted runs land in place
+    const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
+    TRY(set_smem(k_part_count, ct_smem));
+    unsigned* d_nd = c->d_hist;   // the sample histogram is no longer needed
+    LAUNCH(k_part_count, std::min<unsigned>(pl.n_sub, grid_sm * 2), OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg,
+           pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, ps);
+    CU(cudaEventRecord(c->ev_p[4], c->s_main));
+    LAUNCH(k_widen_u32, grid_for(pl.n_sub), 256, 0, c->s_main, d_nd, pl.scan, (uint64_t)pl.n_sub);
+    LAUNCH(k_scan_tiles, 1, 1024, 0, c->s_main, pl.scan, (uint64_t)pl.n_sub, pl.scan + pl.n_sub);
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, pl.scan + pl.n_sub, 8, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    TRY(dev_reserve(&c->d_run_keys, &c->cap_run_keys, total));
+    TRY(dev_reserve(&c->d_run_counts, &c->cap_run_counts, total));
+    if (total)
+        LAUNCH(k_part_compact, std::min<unsigned>(pl.n_sub, grid_sm * 8), 256, 0, c->s_main, c->d_buf2, c->d_buf1, pl.beg, d_nd,
+               pl.scan, pl.n_sub, c->d_run_keys, c->d_run_counts);
+    CU(cudaEventRecord(c->ev_p[5], c->s_main));
+    TRY(read_stats(c));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&c->ms_sample, c->ev_p[0], c->ev_p[1]);
+    cudaEventElapsedTime(&c->ms_scatter1, c->ev_p[1], c->ev_p[2]);
+    cudaEventElapsedTime(&c->ms_scatter2, c->ev_p[2], c->ev_p[3]);
+    cudaEventElapsedTime(&c->ms_count, c->ev_p[3], c->ev_p[4]);
+    cudaEventElapsedTime(&c->ms_compact, c->ev_p[4], c->ev_p[5]);
+    c->ms_insert = c->ms_sample + c->ms_scatter1 + c->ms_scatter2 + c->ms_count;
+    c->ms_readout = c->ms_compact;
+    c->n_run = total; c->run_valid = true;
+    c->occupied = total;
+    return OK_SUCCESS;
+}
+
+int run_to_table(ok_counter* c);
+
+// whatever the displacement / capacity bounds spilled is exact but unsorted: fold the run and
+// the spill list into the general table
+int part_absorb_spills(ok_counter* c) {
+    if (c->h_stats->spill_n == 0) return OK_SUCCESS;
+    if (c->h_stats->spill_n > c->spill.cap)
+        return set_err(OK_ERR_INTERNAL, "spill list overflow (%llu entries) in the partitioned path",
+                       (unsigned long long)c->h_stats->spill_n);
+    c->spilled_total += c->h_stats->spill_n;
+    return run_to_table(c);   // table_rebuild re-adds the spill list
+}
+
+int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec) {
+    PartPlan pl;
+    part_choose_bits(c, n_bases, pl);
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    const uint64_t stride = n_tiles > 4096 ? 16 : 1;
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    TRY(dev_reserve(&c->d_hist, &c->cap_hist, (uint64_t)pl.n_sub + 1));
+    CU(cudaEventRecord(c->ev_p[0], c->s_main));
+    CU(cudaMemsetAsync(c->d_hist, 0, pl.n_sub * sizeof(unsigned), c->s_main));
+    {
+        const uint64_t sampled = (n_tiles + stride - 1) / stride;
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((sampled + 7) / 8, (uint64_t)grid_sm * 8));
+        auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_sample<true> : k_part_sample<false>;
+        LAUNCH(kern, blocks, 256, 0, c->s_main, d_bases, n_bases, d_off, n_rec, n_tiles, stride, c->k, pl.cfg, c->d_hist);
+    }
+    TRY(part_plan(c, n_bases, stride, pl));
+    CU(cudaEventRecord(c->ev_p[1], c->s_main));
+    {
+        const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;   // 3 CTAs of 8 warps per SM (75 KB smem each)
+        const uint64_t tpw = std::max<uint64_t>(1, (n_tiles + max_warps - 1) / max_warps);
+        const unsigned blocks = (unsigned)((n_tiles + 8 * tpw - 1) / (8 * tpw));
+        const bool two = pl.cfg.b2 > 0;
+        auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true> : k_part_scatter_bases<false>;
+        TRY(set_smem(kern, sizeof(OkScatterSmem)));
+        LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_off, n_rec, n_tiles, tpw, c->k,
+               pl.cfg, two ? pl.cursor1 : pl.cursor, two ? pl.end1 : pl.cap_end, two ? c->d_buf1 : c->d_buf2,
+               (OkPartSpill{c->spill, c->d_stats}), &c->d_stats->windows);
+    }
+    CU(cudaEventRecord(c->ev_p[2], c->s_main));
+    TRY(part_finish(c, pl));
+    return part_absorb_spills(c);
+}
+
+int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
+    PartPlan pl;
+    part_choose_bits(c, n, pl);
+    const uint64_t n_chunks = (n + 255) / 256;
+    const uint64_t stride = n_chunks > 16384 ? 16 : 1;
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    TRY(dev_reserve(&c->d_hist, &c->cap_hist, (uint64_t)pl.n_sub + 1));
+    CU(cudaEventRecord(c->ev_p[0], c->s_main));
+    CU(cudaMemsetAsync(c->d_hist, 0, pl.n_sub * sizeof(unsigned), c->s_main));
+    LAUNCH(k_part_sample_keys, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + stride - 1) / stride, (uint64_t)grid_sm * 16)),
+           256, 0, c->s_main, (const unsigned long long*)d_keys, n, stride, pl.cfg, c->d_hist);
+    TRY(part_plan(c, n, stride, pl));
+    CU(cudaEventRecord(c->ev_p[1], c->s_main));
+    {
+        // one level-1 scatter over the whole key array, in items of 8192 keys
+        const uint64_t ni = (n + OK_PART_TILE - 1) / OK_PART_TILE;
+        std::vector<unsigned long long> item_off(ni); std::vector<unsigned> item_n(ni), item_bin(ni, 0);
+        for (uint64_t i = 0; i < ni; ++i) { item_off[i] = i * OK_PART_TILE; item_n[i] = (unsigned)std::min<uint64_t>(OK_PART_TILE, n - i * OK_PART_TILE); }
+        TRY(dev_reserve(&c->d_items, &c->cap_items, 2 * ni + 2));
+        unsigned* d_n = (unsigned*)(c->d_items + ni);
+        unsigned* d_b = d_n + ni;
+        CU(cudaMemcpyAsync(c->d_items, item_off.data(), ni * 8, cudaMemcpyHostToDevice, c->s_main));
+        CU(cudaMemcpyAsync(d_n, item_n.data(), ni * 4, cudaMemcpyHostToDevice, c->s_main));
+        CU(cudaMemcpyAsync(d_b, item_bin.data(), ni * 4, cudaMemcpyHostToDevice, c->s_main));
+        const bool two = pl.cfg.b2 > 0;
+        TRY(set_smem(k_part_scatter_keys<1>, sizeof(OkScatterSmem)));
+        LAUNCH(k_part_scatter_keys<1>, (unsigned)std::min<uint64_t>(ni, (uint64_t)grid_sm * 3), 256, sizeof(OkScatterSmem), c->s_main,
+               (const unsigned long long*)d_keys, c->d_items, d_n, d_b, (unsigned)ni, pl.cfg, two ? pl.cursor1 : pl.cursor,
+               two ? pl.end1 : pl.cap_end, two ? c->d_buf1 : c->d_buf2, (OkPartSpill{c->spill, c->d_stats}));
+        CU(cudaStreamSynchronize(c->s_main));
+        c->windows += n;
+        CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
+    }
+    CU(cudaEventRecord(c->ev_p[2], c->s_main));
+    TRY(part_finish(c, pl));
+    return part_absorb_spills(c);
+}
+
+// fold the sorted run into the general table (a later batch arrived, or the run spilled)
+int run_to_table(ok_counter* c) {
+    if (!c->run_valid) return OK_SUCCESS;
+    c->run_valid = false;
+    const uint64_t n = c->n_run;
+    c->occupied = 0;
+    c->hint = std::max<uint64_t>(c->hint, n + n / 4);
+    uint64_t done = 0;
+    if (n == 0 && c->h_stats->spill_n) TRY(table_rebuild(c, slots_for(c, std::max<uint64_t>(c->hint, 1))));
+    while (done < n) {
+        uint64_t allowed = 0;
+        TRY(ensure_headroom(c, n - done, &allowed));
+        const uint64_t m = std::min<uint64_t>(n - done, allowed);
+        LAUNCH(k_add_kmers, grid_for(m), 256, 0, c->s_main, c->tv, c->d_stats, c->spill, c->d_run_keys + done,
+               c->d_run_counts + done, m, 0);
+        TRY(read_stats(c));
+        CU(cudaGetLastError());
+        if (c->h_stats->spill_n) {
+            if (c->h_stats->spill_n > c->spill.cap) return set_err(OK_ERR_INTERNAL, "spill list overflow while folding a run");
+            TRY(table_rebuild(c, 2 * c->tv.n_home));
+        }
+        done += m;
+    }
+    c->n_run = 0;
+    return OK_SUCCESS;
+}
+
+// min_count filter of the run into the d_out arrays
+int run_filter(ok_counter* c, uint64_t min_count, uint64_t* n_out) {
+    const uint64_t n = c->n_run;
+    *n_out = 0;
+    if (n == 0) return OK_SUCCESS;
+    const uint64_t n_tiles = (n + 2047) / 2048;
+    TRY(dev_reserve(&c->d_tiles, &c->cap_tiles, n_tiles + 1));
+    LAUNCH(k_filter_count, (unsigned)n_tiles, 256, 0, c->s_main, c->d_run_counts, n, min_count, c->d_tiles);
+    LAUNCH(k_scan_tiles, 1, 1024, 0, c->s_main, c->d_tiles, n_tiles, c->d_tiles + n_tiles);
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, c->d_tiles + n_tiles, 8, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    if (total) {
+        TRY(dev_reserve(&c->d_out_keys, &c->cap_out_keys, total));
+        TRY(dev_reserve(&c->d_out_counts, &c->cap_out_counts, total));
+        LAUNCH(k_filter_write, (unsigned)n_tiles, 256, 0, c->s_main, c->d_run_keys, c->d_run_counts, n, min_count, c->d_tiles,
+               c->d_out_keys, c->d_out_counts);
+        CU(cudaStreamSynchronize(c->s_main));
+        CU(cudaGetLastError());
+    }
+    *n_out = total;
+    return OK_SUCCESS;
+}
+
+// result of the counter, wherever it lives: -> device pointers
+int counter_result(ok_counter* c, uint64_t min_count, const unsigned long long** dk, const unsigned long long** dc, uint64_t* n) {
+    if (c->run_valid) {
+        if (min_count <= 1) { *dk = c->d_run_keys; *dc = c->d_run_counts; *n = c->n_run; return OK_SUCCESS; }
+        TRY(run_filter(c, min_count, n));
+        *dk = c->d_out_keys; *dc = c->d_out_counts;
+        return OK_SUCCESS;
+    }
+    TRY(counter_readout(c, min_count, n));
+    *dk = c->d_out_keys; *dc = c->d_out_counts;
+    return OK_SUCCESS;
+}
+
+}  // namespace
+
 // ============================================================================ lifecycle ==
 OK_EXPORT int ok_init(const int* device_ids, int n_devices) {
     if (n_devices > 1)
@@ -401,6 +707,7 @@ OK_EXPORT int ok_counter_create(uint8_t k, int norm_mode, uint64_t capacity_hint
     CUF(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CUF(cudaEventCreate(&c->ev_a));
     CUF(cudaEventCreate(&c->ev_b));
+    for (auto& e : c->ev_p) CUF(cudaEventCreate(&e));
     CUF(cudaMalloc((void**)&c->d_stats, sizeof(OkDevStats)));
     CUF(cudaMemset(c->d_stats, 0, sizeof(OkDevStats)));
     CUF(cudaMallocHost((void**)&c->h_stats, sizeof(OkDevStats)));
@@ -421,6 +728,9 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
     cudaFree(c->spill.keys); cudaFree(c->spill.incs);
     cudaFree(c->d_bases); cudaFree(c->d_off); cudaFree(c->d_tiles);
     cudaFree(c->d_out_keys); cudaFree(c->d_out_counts);
+    cudaFree(c->d_run_keys); cudaFree(c->d_run_counts); cudaFree(c->d_buf1); cudaFree(c->d_buf2);
+    cudaFree(c->d_meta); cudaFree(c->d_hist); cudaFree(c->d_items);
+    for (auto e : c->ev_p) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_chunks) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -432,7 +742,9 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
 
 OK_EXPORT int ok_counter_clear(ok_counter* c) {
     if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_clear: NULL handle");
-    if (c->tv.slots) LAUNCH(k_fill_slots, grid_for(c->tv.n_total, 256, 16), 256, 0, c->s_main, c->tv.slots, c->tv.n_total);
+    if (c->tv.slots && c->occupied && !c->run_valid)
+        LAUNCH(k_fill_slots, grid_for(c->tv.n_total, 256, 16), 256, 0, c->s_main, c->tv.slots, c->tv.n_total);
+    c->run_valid = false; c->n_run = 0;
     CU(cudaMemsetAsync(c->d_stats, 0, sizeof(OkDevStats), c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
     c->occupied = c->windows = c->bases_seen = c->max_disp = c->spilled_total = 0;
@@ -447,6 +759,12 @@ OK_EXPORT int ok_counter_add_batch_device(ok_counter* c, const uint8_t* d_bases,
     if (!d_bases || !d_rec_offsets) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL batch pointer");
     if ((uintptr_t)d_bases & 15u) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
     c->ms_insert = 0; c->ms_fill = 0;
+    if (part_eligible(c, n_bases)) {
+        TRY(part_count_bases(c, d_bases, n_bases, d_rec_offsets, n_records));
+        c->bases_seen += n_bases;
+        return OK_SUCCESS;
+    }
+    TRY(run_to_table(c));
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
     TRY(counter_process_tiles(c, d_bases, n_bases, d_rec_offsets, n_records, 0, n_tiles));
     c->bases_seen += n_bases;
@@ -478,6 +796,13 @@ OK_EXPORT int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const ui
         CU(cudaEventRecord(c->ev_chunks[p], c->s_copy));
     }
     CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces], 0));
+    if (part_eligible(c, n_bases)) {   // one-shot partitioned path needs the whole batch resident
+        CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces - 1], 0));
+        TRY(part_count_bases(c, c->d_bases, n_bases, c->d_off, n_records));
+        c->bases_seen += n_bases;
+        return OK_SUCCESS;
+    }
+    TRY(run_to_table(c));
     const uint64_t tiles_per_piece = COPY_CHUNK / OK_TILE_BASES;
     for (uint64_t p = 0; p < n_pieces; ++p) {
         CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[p], 0));
@@ -497,6 +822,8 @@ OK_EXPORT int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers
     if (n == 0) return OK_SUCCESS;
     if (!d_kmers) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL d_kmers");
     c->ms_insert = 0; c->ms_fill = 0;
+    if (part_eligible(c, n)) return part_count_keys(c, d_kmers, n);
+    TRY(run_to_table(c));
     uint64_t done = 0;
     while (done < n) {
         uint64_t allowed = 0;
@@ -586,9 +913,10 @@ OK_EXPORT int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const 
                                        const uint64_t** d_counts, uint64_t* n) {
     if (!c || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_finish_device: NULL argument");
     uint64_t total = 0;
-    TRY(counter_readout(c, min_count, &total));
-    if (d_kmers) *d_kmers = (const uint64_t*)c->d_out_keys;
-    if (d_counts) *d_counts = (const uint64_t*)c->d_out_counts;
+    const unsigned long long *dk = nullptr, *dc = nullptr;
+    TRY(counter_result(c, min_count, &dk, &dc, &total));
+    if (d_kmers) *d_kmers = (const uint64_t*)dk;
+    if (d_counts) *d_counts = (const uint64_t*)dc;
     *n = total;
     return OK_SUCCESS;
 }
@@ -597,13 +925,14 @@ OK_EXPORT int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** km
                                 uint64_t* n) {
     if (!c || !kmers || !counts || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_finish: NULL argument");
     uint64_t total = 0;
-    TRY(counter_readout(c, min_count, &total));
+    const unsigned long long *dk = nullptr, *dc = nullptr;
+    TRY(counter_result(c, min_count, &dk, &dc, &total));
     void *hk = nullptr, *hc = nullptr;
     TRY(pool_alloc(&hk, total * 8));
     TRY(pool_alloc(&hc, total * 8));
     if (total) {
-        CU(cudaMemcpyAsync(hk, c->d_out_keys, total * 8, cudaMemcpyDeviceToHost, c->s_main));
-        CU(cudaMemcpyAsync(hc, c->d_out_counts, total * 8, cudaMemcpyDeviceToHost, c->s_copy));
+        CU(cudaMemcpyAsync(hk, dk, total * 8, cudaMemcpyDeviceToHost, c->s_main));
+        CU(cudaMemcpyAsync(hc, dc, total * 8, cudaMemcpyDeviceToHost, c->s_copy));
         CU(cudaStreamSynchronize(c->s_main));
         CU(cudaStreamSynchronize(c->s_copy));
     }
@@ -611,11 +940,19 @@ OK_EXPORT int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** km
     return OK_SUCCESS;
 }
 
+OK_EXPORT int ok_counter_set_path(ok_counter* c, int mode) {
+    if (!c || mode < 0 || mode > 2) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_set_path: bad argument");
+    c->path_mode = mode;
+    return OK_SUCCESS;
+}
+
 OK_EXPORT int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out) {
     if (!c || !out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_get_stats: NULL argument");
-    out->n_slots = c->tv.n_total; out->n_distinct = c->occupied; out->n_windows = c->windows;
+    out->n_slots = c->run_valid ? 0 : c->tv.n_total; out->n_distinct = c->occupied; out->n_windows = c->windows;
     out->n_bases = c->bases_seen; out->max_displacement = c->max_disp; out->n_spilled = c->spilled_total;
     out->n_grows = c->grows; out->ms_insert = c->ms_insert; out->ms_readout = c->ms_readout; out->ms_fill = c->ms_fill; out->ms_route = c->ms_route;
+    out->ms_sample = c->ms_sample; out->ms_scatter1 = c->ms_scatter1; out->ms_scatter2 = c->ms_scatter2;
+    out->ms_count = c->ms_count; out->ms_compact = c->ms_compact; out->partitioned = c->run_valid ? 1 : 0;
     return OK_SUCCESS;
 }
 

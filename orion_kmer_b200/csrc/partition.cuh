@@ -1,0 +1,369 @@
+// partition.cuh -- the partitioned count path (one-shot batches).
+//
+// Measured on B200 (tools/microbench.cu, profiles/): a DRAM-resident count table sustains only
+// ~17 G load+RED/s (random 32 B sector traffic, DRAM-activation bound) while shared-memory
+// atomics run at ~2.4 T/s.  So large batches are counted without a global table at all:
+//
+//   k_part_sample         1/16 of the tiles -> histogram of sub-partition ids (sizes the buffers)
+//   k_part_scatter_bases  ASCII -> pack -> rolling canonical k-mers -> level-1 partitions
+//   k_part_scatter_keys   level-1 partition -> level-2 sub-partitions
+//   k_part_count          one CTA per sub-partition: shared-memory table (CAS claim + add),
+//                         then an ordered sweep emits the sub-partition already sorted
+//   k_part_compact        sub-partition runs -> the final sorted (k-mer, count) arrays
+//
+// Partitions are ranges of the monotone position x(key) (kmer_math.cuh), so sub-partition
+// order == key order and the concatenation of the sorted sub-partitions is the sorted count
+// table of count.rs:106-119 -- no sort pass.  Both scatters are shared-memory multisplits:
+// rank by smem atomicAdd, stage the tile in shared memory in bin order, copy out in runs.
+#pragma once
+#include "kernels.cuh"
+
+#define OK_PART_TILE 8192u        // keys per CTA iteration of a scatter (8 warps x 1024)
+#define OK_PART_MAXBINS 1024u     // bins per scatter level
+#define OK_CT_SLOTS 8192u         // slots of the shared-memory count table
+#define OK_CT_PAD 512u            // tail padding = displacement bound of the smem table
+#define OK_CT_THREADS 512u
+
+struct OkPartCfg {
+    unsigned key_shift;    // 64 - 2k
+    unsigned shard_log2;   // multi-GPU: this rank holds 1/2^shard_log2 of the position space
+    unsigned b1, b2;       // bits of the level-1 / level-2 bin id
+};
+
+// position of a key inside this rank's slice of the (prior-straightened) key space, as a 64-bit
+// fraction; monotone in the key
+__device__ __forceinline__ uint64_t ok_part_pos(uint64_t key, const OkPartCfg& c) {
+    uint64_t w = ~(key << c.key_shift);
+    return (~ok_mulhi64(w, w)) << c.shard_log2;
+}
+__device__ __forceinline__ unsigned ok_part_bin1(uint64_t x, const OkPartCfg& c) { return c.b1 ? (unsigned)(x >> (64 - c.b1)) : 0u; }
+__device__ __forceinline__ unsigned ok_part_bin2(uint64_t x, const OkPartCfg& c) { return c.b2 ? (unsigned)((x << c.b1) >> (64 - c.b2)) : 0u; }
+__device__ __forceinline__ unsigned ok_part_sub(uint64_t x, const OkPartCfg& c) {
+    const unsigned b = c.b1 + c.b2;
+    return b ? (unsigned)(x >> (64 - b)) : 0u;
+}
+
+struct OkPartSpill { OkSpill sp; OkDevStats* st; };
+
+// ----------------------------------------------------------------------------- sampling --
+// every `stride`-th warp-tile; hist[sub] += 1 per k-mer (global RED; the sample is small)
+template <bool MAP_U>
+__global__ void __launch_bounds__(256)
+k_part_sample(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
+              uint64_t n_rec, uint64_t n_tiles, uint64_t stride, unsigned k, OkPartCfg cfg,
+              unsigned* __restrict__ hist) {
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t t = warp * stride; t < n_tiles; t += warps * stride)
+        ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t, t + 1, t + 1, k, lane,
+            [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {
+                ok_lane_windows(pc, cc, okmask, k, [&](int, uint64_t key) {
+                    atomicAdd(&hist[ok_part_sub(ok_part_pos(key, cfg), cfg)], 1u);
+                });
+            });
+}
+__global__ void __launch_bounds__(256)
+k_part_sample_keys(const unsigned long long* __restrict__ keys, uint64_t n, uint64_t stride, OkPartCfg cfg,
+                   unsigned* __restrict__ hist) {
+    // sample whole 256-key chunks so the loads stay coalesced
+    const uint64_t n_chunks = (n + 255) / 256;
+    for (uint64_t c = blockIdx.x * stride; c < n_chunks; c += (uint64_t)gridDim.x * stride) {
+        const uint64_t i = c * 256 + threadIdx.x;
+        if (i < n) atomicAdd(&hist[ok_part_sub(ok_part_pos(keys[i], cfg), cfg)], 1u);
+    }
+}
+
+// ------------------------------------------------------------- shared multisplit machinery --
+struct OkScatterSmem {
+    unsigned long long stage[OK_PART_TILE];   // keys of this iteration, in bin order
+    unsigned short sbin[OK_PART_TILE];        // bin of each staged key
+    unsigned hist[OK_PART_MAXBINS];           // per-bin count, then local exclusive offset
+    unsigned long long gdelta[OK_PART_MAXBINS];  // global index = gdelta[bin] + staged index
+    unsigned wsum[8];
+    unsigned total;
+};
+
+// after the histogram is complete: local offsets (exclusive scan over bins) and global bases
+// (one atomicAdd per non-empty bin on its cursor).  256 threads, n_bins <= 1024.
+__device__ __forceinline__ void ok_scatter_offsets(OkScatterSmem& sm, unsigned n_bins,
+                                                   unsigned long long* __restrict__ cursors) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned c[4], s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { unsigned b = threadIdx.x * 4 + q; c[q] = b < n_bins ? sm.hist[b] : 0u; s += c[q]; }
+    unsigned inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) sm.wsum[wid] = inc;
+    __syncthreads();
+    unsigned woff = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { unsigned w = sm.wsum[i]; woff += i < wid ? w : 0u; tot += w; }
+    unsigned off = woff + inc - s;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned b = threadIdx.x * 4 + q;
+        if (b < n_bins) {
+            sm.hist[b] = off;
+            unsigned long long g = c[q] ? atomicAdd(&cursors[b], (unsigned long long)c[q]) : 0ull;
+            sm.gdelta[b] = g - off;
+            off += c[q];
+        }
+    }
+    if (threadIdx.x == 0) sm.total = tot;
+    __syncthreads();
+}
+
+// staged keys -> global, run by run; entries past their bin's end are spilled, never lost
+__device__ __forceinline__ void ok_scatter_copy_out(OkScatterSmem& sm, const unsigned long long* __restrict__ bin_end,
+                                                    unsigned long long* __restrict__ out, const OkPartSpill& ps) {
+    const unsigned n = sm.total;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned b = sm.sbin[i];
+        const unsigned long long dst = sm.gdelta[b] + i;
+        const unsigned long long key = sm.stage[i];
+        if (dst < bin_end[b]) out[dst] = key;
+        else ok_spill(ps.sp, ps.st, key, 1);
+    }
+}
+
+// ------------------------------------------------------------------ level 1: from the bases --
+// The 8 warps of a CTA walk their own runs of tiles in lock step; each iteration the CTA holds
+// <= 8192 k-mers.  Pass A ranks them (smem atomicAdd), pass B re-rolls and stages them.
+template <bool MAP_U>
+__global__ void __launch_bounds__(256)
+k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
+                     uint64_t n_rec, uint64_t n_tiles, uint64_t tiles_per_warp, unsigned k, OkPartCfg cfg,
+                     unsigned long long* __restrict__ cursors, const unsigned long long* __restrict__ bin_end,
+                     unsigned long long* __restrict__ out, OkPartSpill ps, unsigned long long* __restrict__ n_keys) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
+    const unsigned n_bins = 1u << cfg.b1;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t t0 = warp * tiles_per_warp;
+    // whole CTA out of range? (warps of one CTA are consecutive)
+    if ((uint64_t)blockIdx.x * 8 * tiles_per_warp >= n_tiles) return;
+    unsigned long long my_keys = 0;
+    ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t0 + tiles_per_warp, n_tiles, k, lane,
+        [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {
+            for (unsigned i = threadIdx.x; i < n_bins; i += blockDim.x) sm.hist[i] = 0;
+            __syncthreads();
+            unsigned rk[16];                                    // 32 ranks, two per register
+#pragma unroll
+            for (int q = 0; q < 16; ++q) rk[q] = 0;
+            ok_lane_windows_full(pc, cc, okmask, k, [&](int j, uint64_t key) {
+                const unsigned b = ok_part_bin1(ok_part_pos(key, cfg), cfg);
+                const unsigned r = atomicAdd(&sm.hist[b], 1u);
+                rk[j >> 1] |= r << ((j & 1) * 16);
+                ++my_keys;
+            });
+            __syncthreads();
+            ok_scatter_offsets(sm, n_bins, cursors);
+            ok_lane_windows_full(pc, cc, okmask, k, [&](int j, uint64_t key) {
+                const unsigned b = ok_part_bin1(ok_part_pos(key, cfg), cfg);
+                const unsigned idx = sm.hist[b] + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+                sm.stage[idx] = key;
+                sm.sbin[idx] = (unsigned short)b;
+            });
+            __syncthreads();
+            ok_scatter_copy_out(sm, bin_end, out, ps);
+            __syncthreads();
+        });
+    my_keys = ok_warp_sum(my_keys);
+    if (lane == 0 && my_keys) atomicAdd(n_keys, my_keys);
+}
+
+// --------------------------------------------------------------------- level 2: from keys --
+// work item w: keys src[item_off[w] .. +item_n[w]) all of level-1 bin item_bin[w]
+template <int LEVEL>  // LEVEL 1: bin by bin1 (keys arriving from peers); LEVEL 2: bin by bin2 inside a bin1
+__global__ void __launch_bounds__(256)
+k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ item_off,
+                    const unsigned* __restrict__ item_n, const unsigned* __restrict__ item_bin, unsigned n_items,
+                    OkPartCfg cfg, unsigned long long* __restrict__ cursors,
+                    const unsigned long long* __restrict__ bin_end, unsigned long long* __restrict__ out,
+                    OkPartSpill ps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
+    const unsigned n_bins = 1u << (LEVEL == 1 ? cfg.b1 : cfg.b2);
+    for (unsigned w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const unsigned long long* __restrict__ keys = src + item_off[w];
+        const unsigned n = item_n[w];
+        const unsigned bin_base = LEVEL == 1 ? 0u : item_bin[w] << cfg.b2;
+        for (unsigned i = threadIdx.x; i < n_bins; i += blockDim.x) sm.hist[i] = 0;
+        __syncthreads();
+        unsigned rk[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) rk[q] = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const unsigned i = j * 256 + threadIdx.x;
+            if (i < n) {
+                const uint64_t x = ok_part_pos(keys[i], cfg);
+                const unsigned b = LEVEL == 1 ? ok_part_bin1(x, cfg) : ok_part_bin2(x, cfg);
+                rk[j >> 1] |= atomicAdd(&sm.hist[b], 1u) << ((j & 1) * 16);
+            }
+        }
+        __syncthreads();
+        ok_scatter_offsets(sm, n_bins, cursors + bin_base);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const unsigned i = j * 256 + threadIdx.x;
+            if (i < n) {
+                const unsigned long long key = keys[i];
+                const uint64_t x = ok_part_pos(key, cfg);
+                const unsigned b = LEVEL == 1 ? ok_part_bin1(x, cfg) : ok_part_bin2(x, cfg);
+                const unsigned idx = sm.hist[b] + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+                sm.stage[idx] = key;
+                sm.sbin[idx] = (unsigned short)b;
+            }
+        }
+        __syncthreads();
+        ok_scatter_copy_out(sm, bin_end + bin_base, out, ps);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------- count one sub-partition in smem --
+// sub-partition p holds keys src[beg[p] .. beg[p]+cnt[p]).  Its distinct keys come out sorted
+// in place (keys -> src[beg[p] ..], counts -> cnt_out[beg[p] ..]); n_distinct[p] says how many.
+__global__ void __launch_bounds__(OK_CT_THREADS)
+k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __restrict__ beg,
+             const unsigned long long* __restrict__ fill_end /* cursor after the scatter */,
+             const unsigned long long* __restrict__ cap_end, unsigned n_sub, OkPartCfg cfg,
+             unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct, OkPartSpill ps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem_raw);                 // [SLOTS+PAD]
+    unsigned* tcnt = reinterpret_cast<unsigned*>(tkey + OK_CT_SLOTS + OK_CT_PAD);               // [SLOTS+PAD]
+    __shared__ unsigned wsum[OK_CT_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned sub_bits = cfg.b1 + cfg.b2;
+    constexpr unsigned NT = OK_CT_SLOTS + OK_CT_PAD;
+    constexpr unsigned PER = NT / OK_CT_THREADS;   // 17 slots per thread in the sweep
+    for (unsigned p = blockIdx.x; p < n_sub; p += gridDim.x) {
+        const unsigned long long b0 = beg[p];
+        unsigned long long e0 = fill_end[p];
+        if (e0 > cap_end[p]) e0 = cap_end[p];          // the rest was spilled by the scatter
+        const unsigned n = (unsigned)(e0 - b0);
+        if (n == 0) { if (threadIdx.x == 0) n_distinct[p] = 0; continue; }
+        for (unsigned i = threadIdx.x; i < NT; i += OK_CT_THREADS) { tkey[i] = OK_EMPTY_KEY; tcnt[i] = 0; }
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < n; i += OK_CT_THREADS) {
+            const unsigned long long key = src[b0 + i];
+            const uint64_t f = sub_bits ? (ok_part_pos(key, cfg) << sub_bits) : ok_part_pos(key, cfg);
+            const unsigned h = (unsigned)(((f >> 32) * (uint64_t)OK_CT_SLOTS) >> 32);
+            bool placed = false;
+            for (unsigned s = h; s < h + OK_CT_PAD; ++s) {
+                unsigned long long cur = tkey[s];
+                if (cur == OK_EMPTY_KEY) {
+                    cur = atomicCAS(&tkey[s], OK_EMPTY_KEY, key);
+                    if (cur == OK_EMPTY_KEY) cur = key;
+                }
+                if (cur == key) { atomicAdd(&tcnt[s], 1u); placed = true; break; }
+            }
+            if (!placed) ok_spill(ps.sp, ps.st, key, 1);
+        }
+        __syncthreads();
+        // ordered sweep: thread t owns slots [t*PER, (t+1)*PER)
+        const unsigned s0 = threadIdx.x * PER;
+        unsigned mine = 0;
+#pragma unroll
+        for (unsigned q = 0; q < PER; ++q) mine += tkey[s0 + q] != OK_EMPTY_KEY ? 1u : 0u;
+        unsigned inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        unsigned woff = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < (int)(OK_CT_THREADS / 32); ++i) { unsigned w = wsum[i]; woff += i < wid ? w : 0u; tot += w; }
+        unsigned before = woff + inc - mine;
+        for (unsigned q = 0; q < PER; ++q) {
+            const unsigned s = s0 + q;
+            const unsigned long long key = tkey[s];
+            if (key == OK_EMPTY_KEY) continue;
+            const uint64_t f = sub_bits ? (ok_part_pos(key, cfg) << sub_bits) : ok_part_pos(key, cfg);
+            const unsigned h = (unsigned)(((f >> 32) * (uint64_t)OK_CT_SLOTS) >> 32);
+            int adj = 0;
+            for (unsigned t = h; t < s; ++t) adj -= tkey[t] > key ? 1 : 0;        // all occupied
+            for (unsigned t = s + 1; t < h + OK_CT_PAD && t < NT; ++t) {
+                const unsigned long long kt = tkey[t];
+                if (kt == OK_EMPTY_KEY) break;
+                adj += kt < key ? 1 : 0;
+            }
+            const unsigned idx = before + adj;
+            src[b0 + idx] = key;                       // idx < tot <= n: stays inside the region
+            cnt_out[b0 + idx] = tcnt[s];
+            ++before;
+        }
+        if (threadIdx.x == 0) n_distinct[p] = tot;
+        __syncthreads();
+    }
+}
+
+// sub-partition runs -> final arrays; base[p] = exclusive scan of n_distinct (as u64)
+__global__ void __launch_bounds__(256)
+k_part_compact(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ counts,
+               const unsigned long long* __restrict__ beg, const unsigned* __restrict__ n_distinct,
+               const unsigned long long* __restrict__ base, unsigned n_sub,
+               unsigned long long* __restrict__ out_keys, unsigned long long* __restrict__ out_counts) {
+    for (unsigned p = blockIdx.x; p < n_sub; p += gridDim.x) {
+        const unsigned n = n_distinct[p];
+        const unsigned long long b0 = beg[p], o0 = base[p];
+        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+            out_keys[o0 + i] = keys[b0 + i];
+            out_counts[o0 + i] = counts[b0 + i];
+        }
+    }
+}
+
+// n_distinct (u32) -> u64 copy for the scan kernel
+__global__ void __launch_bounds__(256) k_widen_u32(const unsigned* __restrict__ a, unsigned long long* __restrict__ b, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+
+// ---------------------------------------------------------------- min_count filter of a run --
+__global__ void __launch_bounds__(256)
+k_filter_count(const unsigned long long* __restrict__ counts, uint64_t n, uint64_t min_count,
+               unsigned long long* __restrict__ tile_counts) {
+    __shared__ unsigned wsum[8];
+    const uint64_t a = (uint64_t)blockIdx.x * 2048;
+    unsigned c = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) { uint64_t i = a + it * 256u + threadIdx.x; c += (i < n && counts[i] >= min_count) ? 1u : 0u; }
+    c = (unsigned)ok_warp_sum(c);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned t = 0; for (int i = 0; i < 8; ++i) t += wsum[i]; tile_counts[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(256)
+k_filter_write(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ counts, uint64_t n,
+               uint64_t min_count, const unsigned long long* __restrict__ tile_base,
+               unsigned long long* __restrict__ out_keys, unsigned long long* __restrict__ out_counts) {
+    __shared__ unsigned wsum[8];
+    __shared__ unsigned long long running;
+    const uint64_t a = (uint64_t)blockIdx.x * 2048;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = tile_base[blockIdx.x];
+    __syncthreads();
+    for (int it = 0; it < 8; ++it) {
+        const uint64_t i = a + it * 256u + threadIdx.x;
+        unsigned long long key = 0, cnt = 0;
+        if (i < n) { key = keys[i]; cnt = counts[i]; }
+        const bool keep = i < n && cnt >= min_count;
+        const unsigned bal = __ballot_sync(OK_FULL, keep);
+        if (lane == 0) wsum[wid] = __popc(bal);
+        __syncthreads();
+        unsigned woff = 0, tot = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { unsigned w = wsum[q]; woff += q < wid ? w : 0u; tot += w; }
+        if (keep) {
+            const unsigned long long idx = running + woff + __popc(bal & ((1u << lane) - 1u));
+            out_keys[idx] = key; out_counts[idx] = cnt;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) running += tot;
+        __syncthreads();
+    }
+}

@@ -347,3 +347,109 @@ def test_classify_golden(golden):
                 ref = db.references[name]
                 assert len(ref) == want["total"]
                 assert ref.probe_counts(keys, counts) == (want["matched"], want["sum_depth"]), (case["name"], name)
+
+
+# ----------------------------------------------- the two count paths give the same table --
+@pytest.mark.parametrize("k", [3, 11, 21, 31, 32])
+def test_partitioned_path_matches_oracle(oracle, k):
+    """path 2 = partition -> shared-memory tables -> sorted runs; path 1 = device-wide table"""
+    rng = np.random.default_rng(500 + k)
+    for n_bases, mean_len in ((1, 1), (40, 7), (70_000, 150), (3_000_000, 150), (2_500_000, 2_500_000)):
+        bases, off = random_batch(rng, n_bases, mean_len)
+        wk, wc = oracle.count_batch(k, bases, off)
+        for path in (1, 2):
+            c = ok.KmerCounter(k)
+            c.set_path(path)
+            c.add_batch(bases, off)
+            st = c.stats()
+            assert st["partitioned"] == (1 if path == 2 else 0)
+            for mc in (1, 2, 4):
+                gk, gc = c.finish(mc)
+                sel = wc >= mc
+                assert np.array_equal(gk, wk[sel]) and np.array_equal(gc, wc[sel]), (k, n_bases, path, mc)
+            assert st["n_windows"] == int(wc.sum())
+            c.close()
+
+
+def test_partitioned_run_then_more_batches(oracle):
+    """a second batch folds the sorted run into the table; results stay exact"""
+    g = synth.genome(61, 800_000)
+    n = 40_000
+    b1, b2 = synth.reads(g, 62, n), synth.reads(g, 63, n)
+    off = synth.read_offsets(n)
+    c = ok.KmerCounter(31)
+    c.set_path(2)
+    c.add_batch(b1, off)
+    assert c.stats()["partitioned"] == 1
+    c.add_batch(b2, off)
+    assert c.stats()["partitioned"] == 0
+    o = oracle.Counter(31)
+    o.add_batch(b1, off)
+    o.add_batch(b2, off)
+    for mc in (1, 3):
+        gk, gc = c.finish(mc)
+        wk, wc = o.finish(mc)
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+    c.clear()
+    c.add_batch(b2, off)
+    gk, gc = c.finish()
+    wk, wc = oracle.count_batch(31, b2, off)
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+    c.close()
+
+
+def test_partitioned_heavy_duplicates_and_low_complexity(oracle):
+    """poly-A / dinucleotide reads: millions of windows on a handful of keys"""
+    n = 20_000
+    reads = np.tile(np.frombuffer(b"A" * 150, np.uint8), n // 2)
+    reads2 = np.tile(np.frombuffer(b"AC" * 75, np.uint8), n // 2)
+    bases = np.concatenate([reads, reads2, synth.reads(synth.genome(1, 100_000), 2, 5000)])
+    off = synth.read_offsets(n + 5000)
+    wk, wc = oracle.count_batch(21, bases, off)
+    for path in (1, 2):
+        c = ok.KmerCounter(21)
+        c.set_path(path)
+        c.add_batch(bases, off)
+        gk, gc = c.finish()
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc), path
+        c.close()
+
+
+# ------------------------------------------------- multi-GPU route / shard logic on one GPU --
+@pytest.mark.parametrize("n_ranks", [2, 4, 8])
+def test_route_and_sharded_counters_concatenate_to_the_global_table(oracle, n_ranks):
+    import torch
+    k = 31
+    g = synth.genome(70, 1_000_000)
+    n = 60_000
+    bases = synth.reads(g, 71, n)
+    off = synth.read_offsets(n)
+    d_b = torch.from_numpy(bases).cuda()
+    d_o = torch.from_numpy(off.view(np.int64)).cuda()
+    d_out = torch.empty(len(bases), dtype=torch.int64, device="cuda")
+    router = ok.KmerCounter(k)
+    counts = router.route_batch_device(d_b.data_ptr(), len(bases), d_o.data_ptr(), n, n_ranks, d_out.data_ptr())
+    router.close()
+    wk, wc = oracle.count_batch(k, bases, off)
+    assert int(counts.sum()) == int(wc.sum())
+    routed = d_out[:int(counts.sum())].cpu().numpy().view(np.uint64)
+    owners = np.zeros(len(routed), np.int32)
+    ok._check(ok.lib().okx_owner_of(ok._ptr(routed), len(routed), k, n_ranks, ok._ptr(owners)))
+    bounds = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    pieces_k, pieces_c = [], []
+    for r in range(n_ranks):
+        assert np.all(owners[bounds[r]:bounds[r + 1]] == r)
+        for path in (1, 2):
+            c = ok.KmerCounter(k)
+            c.set_shard(r, n_ranks)
+            c.set_path(path)
+            c.add_kmers_device(d_out.data_ptr() + 8 * int(bounds[r]), int(counts[r]))
+            gk, gc = c.finish()
+            c.close()
+            if path == 1:
+                pieces_k.append(gk); pieces_c.append(gc)
+            else:
+                assert np.array_equal(gk, pieces_k[-1]) and np.array_equal(gc, pieces_c[-1]), (r, "paths differ")
+    # disjoint key ranges in rank order: plain concatenation is the sorted global table
+    assert np.array_equal(np.concatenate(pieces_k), wk)
+    assert np.array_equal(np.concatenate(pieces_c), wc)
