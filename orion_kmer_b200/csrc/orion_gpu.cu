@@ -359,7 +359,7 @@ int part_plan(ok_counter* c, uint64_t n_units, uint64_t sample_stride, PartPlan&
     for (unsigned p = 0; p < n_sub; ++p) {
         uint64_t est = (uint64_t)hist[p] * sample_stride;
         uint64_t cap = est;
-        if (sample_stride > 1) cap += (uint64_t)(4.0 * std::sqrt((double)est * (double)sample_stride)) + 64;
+        if (sample_stride > 1) cap += (uint64_t)(6.0 * std::sqrt((double)est * (double)sample_stride)) + 128;
         if (cap > n_units) cap = n_units;
         pl.h_beg[p] = run; run += cap; pl.h_end[p] = run;
     }
@@ -467,19 +467,28 @@ int part_finish(ok_counter* c, PartPlan& pl) {
 
 int run_to_table(ok_counter* c);
 
+constexpr int PART_RETRY = 100;   // internal: the one-shot path gave up, count the batch through the table instead
+
 // whatever the displacement / capacity bounds spilled is exact but unsorted: fold the run and
-// the spill list into the general table
-int part_absorb_spills(ok_counter* c) {
+// the spill list into the general table.  If even the spill list overflowed, nothing of this
+// batch is kept and the caller re-counts it through the table path.
+int part_absorb_spills(ok_counter* c, uint64_t windows_before) {
     if (c->h_stats->spill_n == 0) return OK_SUCCESS;
-    if (c->h_stats->spill_n > c->spill.cap)
-        return set_err(OK_ERR_INTERNAL, "spill list overflow (%llu entries) in the partitioned path",
-                       (unsigned long long)c->h_stats->spill_n);
+    if (c->h_stats->spill_n > c->spill.cap) {
+        c->run_valid = false; c->n_run = 0; c->occupied = 0; c->windows = windows_before;
+        CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
+        CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        c->h_stats->spill_n = 0;
+        return PART_RETRY;
+    }
     c->spilled_total += c->h_stats->spill_n;
-    return run_to_table(c);   // table_rebuild re-adds the spill list
+    return run_to_table(c);
 }
 
 int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec) {
     PartPlan pl;
+    const uint64_t windows_before = c->windows;
     part_choose_bits(c, n_bases, pl);
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
     const uint64_t stride = n_tiles > 4096 ? 16 : 1;
@@ -508,11 +517,12 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
     }
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
     TRY(part_finish(c, pl));
-    return part_absorb_spills(c);
+    return part_absorb_spills(c, windows_before);
 }
 
 int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
     PartPlan pl;
+    const uint64_t windows_before = c->windows;
     part_choose_bits(c, n, pl);
     const uint64_t n_chunks = (n + 255) / 256;
     const uint64_t stride = n_chunks > 16384 ? 16 : 1;
@@ -546,7 +556,7 @@ int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
     }
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
     TRY(part_finish(c, pl));
-    return part_absorb_spills(c);
+    return part_absorb_spills(c, windows_before);
 }
 
 // fold the sorted run into the general table (a later batch arrived, or the run spilled)
@@ -573,6 +583,7 @@ int run_to_table(ok_counter* c) {
         done += m;
     }
     c->n_run = 0;
+    if (c->h_stats->spill_n) TRY(table_rebuild(c, 2 * c->tv.n_home));   // also re-adds what the one-shot path spilled
     return OK_SUCCESS;
 }
 
@@ -760,9 +771,8 @@ OK_EXPORT int ok_counter_add_batch_device(ok_counter* c, const uint8_t* d_bases,
     if ((uintptr_t)d_bases & 15u) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
     c->ms_insert = 0; c->ms_fill = 0;
     if (part_eligible(c, n_bases)) {
-        TRY(part_count_bases(c, d_bases, n_bases, d_rec_offsets, n_records));
-        c->bases_seen += n_bases;
-        return OK_SUCCESS;
+        const int r = part_count_bases(c, d_bases, n_bases, d_rec_offsets, n_records);
+        if (r != PART_RETRY) { if (r == OK_SUCCESS) c->bases_seen += n_bases; return r; }
     }
     TRY(run_to_table(c));
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
@@ -798,9 +808,8 @@ OK_EXPORT int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const ui
     CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces], 0));
     if (part_eligible(c, n_bases)) {   // one-shot partitioned path needs the whole batch resident
         CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces - 1], 0));
-        TRY(part_count_bases(c, c->d_bases, n_bases, c->d_off, n_records));
-        c->bases_seen += n_bases;
-        return OK_SUCCESS;
+        const int r = part_count_bases(c, c->d_bases, n_bases, c->d_off, n_records);
+        if (r != PART_RETRY) { if (r == OK_SUCCESS) c->bases_seen += n_bases; return r; }
     }
     TRY(run_to_table(c));
     const uint64_t tiles_per_piece = COPY_CHUNK / OK_TILE_BASES;
@@ -822,7 +831,7 @@ OK_EXPORT int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers
     if (n == 0) return OK_SUCCESS;
     if (!d_kmers) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL d_kmers");
     c->ms_insert = 0; c->ms_fill = 0;
-    if (part_eligible(c, n)) return part_count_keys(c, d_kmers, n);
+    if (part_eligible(c, n)) { const int r = part_count_keys(c, d_kmers, n); if (r != PART_RETRY) return r; }
     TRY(run_to_table(c));
     uint64_t done = 0;
     while (done < n) {
