@@ -209,18 +209,21 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ok.launch_count()
-    ins_ms, rd_ms, fill_ms, n_launch_insert = [], [], [], 0
+    PH = ["ms_fill", "ms_insert", "ms_readout", "ms_sample", "ms_scatter1", "ms_scatter2", "ms_count", "ms_compact"]
+    acc = {p: [] for p in PH}
     t0 = time.perf_counter()
     for _ in range(args.steps):
         _, _, n_distinct = step_device()
         st = counter.stats()
-        ins_ms.append(st["ms_insert"]); rd_ms.append(st["ms_readout"]); fill_ms.append(st["ms_fill"])
+        for p in PH:
+            acc[p].append(st[p])
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / args.steps
     launches = ok.launch_count() - launches0
     clocks = sampler.stop()
     st = counter.stats()
     windows, distinct = st["n_windows"], st["n_distinct"]
+    phases = {p[3:]: float(np.mean(v)) for p, v in acc.items()}
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------
     for _ in range(max(1, args.warmup)):
@@ -232,17 +235,27 @@ def run_ours(args):
     torch.cuda.synchronize()
     dt_e2e = (time.perf_counter() - t0) / args.steps
 
-    # ---- roofline of the dominant kernel (k_extract<SinkCount>: pack + extract + count) -----
+    # ---- roofline of the dominant kernel ----------------------------------------------------
+    # Algorithmic bytes per SURVEY.md 8(d): count = B(1+.25+.25) + 16 W, readout = 32 D.  The path
+    # that ran decides which kernel dominates: the partitioned path spends its time in the two
+    # scatters and the shared-memory count kernel, the table path in k_extract<SinkCount>.
     peak, peak_src = measured_peak()
-    alg_insert = n_bases * 1.5 + windows * 16.0          # B(1+.25+.25) + 16 W
-    alg_step = alg_insert + distinct * 32.0              # + readout 32 D
-    ins = float(np.mean(ins_ms)) / 1e3
-    achieved = alg_insert / ins / 1e9
+    alg_count = n_bases * 1.5 + windows * 16.0
+    alg_step = alg_count + distinct * 32.0
+    if st["partitioned"]:
+        cand = {"k_part_scatter_bases (pack+extract+level-1 multisplit)": (phases["scatter1"], n_bases * 1.5 + windows * 8.0),
+                "k_part_scatter_keys<2> (level-2 multisplit)": (phases["scatter2"], windows * 16.0),
+                "k_part_count (shared-memory count tables + ordered emit)": (phases["count"], windows * 8.0 + distinct * 16.0)}
+    else:
+        cand = {"k_extract<SinkCount> (fused pack+extract+count)": (phases["insert"], alg_count)}
+    kname = max(cand, key=lambda n: cand[n][0])
+    k_ms, k_bytes = cand[kname]
+    achieved = k_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("k_extract_count_bytes_per_launch")
+            traffic = json.load(open(prof)).get(kname.split(" ")[0])
         except Exception:
             traffic = None
 
@@ -264,14 +277,13 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(n_bases + (n_reads + 1) * 8), "d2h_bytes_per_step": int(16 * n_out)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_extract<SinkCount> (fused pack+extract+count)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": traffic,
-                     "algorithmic_bytes_per_step": alg_insert, "kernel_ms_per_step": ins * 1e3,
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": k_bytes, "kernel_ms": k_ms,
                      "step": {"algorithmic_bytes": alg_step, "achieved": alg_step / dt / 1e9,
                               "frac": alg_step / dt / 1e9 / peak}},
-        "phases_ms": {"fill": float(np.mean(fill_ms)), "insert": float(np.mean(ins_ms)),
-                      "readout": float(np.mean(rd_ms))},
+        "phases_ms": phases,
+        "path": "partitioned" if st["partitioned"] else "table",
         "table": {"windows": int(windows), "distinct": int(distinct), "slots": int(st["n_slots"]),
                   "max_displacement": int(st["max_displacement"]), "spilled": int(st["n_spilled"]),
                   "grows": int(st["n_grows"])},

@@ -172,16 +172,45 @@ OK_HD uint64_t ok_mix64(uint64_t x) {  // murmur3 finaliser
     return x;
 }
 
-OK_HD uint64_t ok_home_slot(uint64_t key, unsigned key_shift, int map_mode, uint64_t n_home) {
-    uint64_t u;
-    if (map_mode == OK_MAP_HASH) {
-        u = ok_mix64(key);
-    } else {
-        u = key << key_shift;                 // key as a fraction of the key space
-        if (map_mode == OK_MAP_CANON) { uint64_t w = ~u; u = ~ok_mulhi64(w, w); }
-    }
-    return ok_mulhi64(u, n_home);
+// position of a key as a 64-bit fraction of the key space, straightened by the canonical
+// prior: x = 1 - (1-u)^2 evaluated on the top 32 bits of u (one 32x32->64 multiply).  Monotone
+// non-decreasing in the key; keys sharing their first 16 bases tie, which the probing and the
+// rank rule of the readout absorb.  Every placement decision (table home, partition bins,
+// multi-GPU owner) is a prefix of this one number, so they nest consistently.
+OK_HD uint64_t ok_canon_pos(uint64_t u) {
+    const uint64_t w = (~u) >> 32;
+    return ~(w * w);
 }
+
+OK_HD uint64_t ok_scale_pos(uint64_t x, uint64_t n) {   // floor(x * n / 2^64), cheap when n < 2^32
+    return n < (1ull << 32) ? ((x >> 32) * n) >> 32 : ok_mulhi64(x, n);
+}
+
+OK_HD uint64_t ok_home_slot(uint64_t key, unsigned key_shift, int map_mode, uint64_t n_home) {
+    uint64_t x;
+    if (map_mode == OK_MAP_HASH) x = ok_mix64(key);
+    else {
+        x = key << key_shift;                 // key as a fraction of the key space
+        if (map_mode == OK_MAP_CANON) x = ok_canon_pos(x);
+    }
+    return ok_scale_pos(x, n_home);
+}
+
+// resumable rolling canonical k-mer over one lane's 32 window ends (same arithmetic as
+// ok_lane_windows, but the caller drives the loop and may pause between steps)
+struct OkRoll {
+    uint64_t fwd, rc, cur, mask; unsigned hs;
+    OK_HD void init(uint64_t prev_codes, uint64_t cur_codes, unsigned k) {
+        mask = ok_mask_k(k); hs = 2 * (k - 1); cur = cur_codes;
+        fwd = prev_codes & mask; rc = ok_revcomp(fwd, k);
+    }
+    OK_HD uint64_t step(int j) {
+        const uint64_t c = (cur >> (62 - 2 * j)) & 3ull;
+        fwd = ((fwd << 2) | c) & mask;
+        rc = (rc >> 2) | ((3ull - c) << hs);
+        return fwd < rc ? fwd : rc;
+    }
+};
 
 // Ordered readout of a monotone table (see kernels.cuh k_readout_write): how far the entry
 // in slot s (key, home h) sits from its sorted position among the surviving entries.

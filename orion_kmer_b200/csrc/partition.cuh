@@ -11,14 +11,15 @@
 //                         then an ordered sweep emits the sub-partition already sorted
 //   k_part_compact        sub-partition runs -> the final sorted (k-mer, count) arrays
 //
-// Partitions are ranges of the monotone position x(key) (kmer_math.cuh), so sub-partition
-// order == key order and the concatenation of the sorted sub-partitions is the sorted count
-// table of count.rs:106-119 -- no sort pass.  Both scatters are shared-memory multisplits:
-// rank by smem atomicAdd, stage the tile in shared memory in bin order, copy out in runs.
+// Partitions are ranges of the monotone position x(key) (kmer_math.cuh ok_canon_pos), so
+// sub-partition order == key order and the concatenation of the sorted sub-partitions is the
+// sorted count table of count.rs:106-119 -- no sort pass.  Both scatters are shared-memory
+// multisplits: every thread holds 16 k-mers in registers, ranks them with one smem atomicAdd
+// each, the tile is staged in shared memory in bin order and copied out in runs.
 #pragma once
 #include "kernels.cuh"
 
-#define OK_PART_TILE 8192u        // keys per CTA iteration of a scatter (8 warps x 1024)
+#define OK_PART_TILE 4096u        // keys per CTA round of a scatter (256 threads x 16)
 #define OK_PART_MAXBINS 1024u     // bins per scatter level
 #define OK_CT_SLOTS 8192u         // slots of the shared-memory count table
 #define OK_CT_PAD 512u            // tail padding = displacement bound of the smem table
@@ -30,17 +31,20 @@ struct OkPartCfg {
     unsigned b1, b2;       // bits of the level-1 / level-2 bin id
 };
 
-// position of a key inside this rank's slice of the (prior-straightened) key space, as a 64-bit
-// fraction; monotone in the key
+// position of a key inside this rank's slice of the key space (64-bit fraction, monotone)
 __device__ __forceinline__ uint64_t ok_part_pos(uint64_t key, const OkPartCfg& c) {
-    uint64_t w = ~(key << c.key_shift);
-    return (~ok_mulhi64(w, w)) << c.shard_log2;
+    return ok_canon_pos(key << c.key_shift) << c.shard_log2;
 }
 __device__ __forceinline__ unsigned ok_part_bin1(uint64_t x, const OkPartCfg& c) { return c.b1 ? (unsigned)(x >> (64 - c.b1)) : 0u; }
 __device__ __forceinline__ unsigned ok_part_bin2(uint64_t x, const OkPartCfg& c) { return c.b2 ? (unsigned)((x << c.b1) >> (64 - c.b2)) : 0u; }
 __device__ __forceinline__ unsigned ok_part_sub(uint64_t x, const OkPartCfg& c) {
     const unsigned b = c.b1 + c.b2;
     return b ? (unsigned)(x >> (64 - b)) : 0u;
+}
+template <int LEVEL>
+__device__ __forceinline__ unsigned ok_part_bin(uint64_t key, const OkPartCfg& c) {
+    const uint64_t x = ok_part_pos(key, c);
+    return LEVEL == 1 ? ok_part_bin1(x, c) : ok_part_bin2(x, c);
 }
 
 struct OkPartSpill { OkSpill sp; OkDevStats* st; };
@@ -76,63 +80,85 @@ k_part_sample_keys(const unsigned long long* __restrict__ keys, uint64_t n, uint
 
 // ------------------------------------------------------------- shared multisplit machinery --
 struct OkScatterSmem {
-    unsigned long long stage[OK_PART_TILE];   // keys of this iteration, in bin order
-    unsigned short sbin[OK_PART_TILE];        // bin of each staged key
-    unsigned hist[OK_PART_MAXBINS];           // per-bin count, then local exclusive offset
-    unsigned long long gdelta[OK_PART_MAXBINS];  // global index = gdelta[bin] + staged index
+    unsigned long long stage[OK_PART_TILE];      // keys of this round, in bin order
+    ulonglong2 gd[OK_PART_MAXBINS];              // .x: global index = .x + staged index; .y: staged-index limit
+    unsigned hist[OK_PART_MAXBINS];              // per-bin count, then local exclusive offset
     unsigned wsum[8];
     unsigned total;
 };
 
-// after the histogram is complete: local offsets (exclusive scan over bins) and global bases
-// (one atomicAdd per non-empty bin on its cursor).  256 threads, n_bins <= 1024.
-__device__ __forceinline__ void ok_scatter_offsets(OkScatterSmem& sm, unsigned n_bins,
-                                                   unsigned long long* __restrict__ cursors) {
+// One multisplit round of the CTA (all 256 threads call it together): thread-held keys
+// key[0..15] (bit q of vmask says key[q] exists) -> out, grouped by bin.
+template <int LEVEL>
+__device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_t (&key)[16], unsigned vmask,
+                                                const OkPartCfg& cfg, unsigned n_bins,
+                                                unsigned long long* __restrict__ cursors,
+                                                const unsigned long long* __restrict__ bin_end,
+                                                unsigned long long* __restrict__ out, const OkPartSpill& ps) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned c[4], s = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { unsigned b = threadIdx.x * 4 + q; c[q] = b < n_bins ? sm.hist[b] : 0u; s += c[q]; }
-    unsigned inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
-    if (lane == 31) sm.wsum[wid] = inc;
+    for (unsigned i = threadIdx.x; i < n_bins; i += 256) sm.hist[i] = 0;
     __syncthreads();
-    unsigned woff = 0, tot = 0;
+    // pass A: rank of every key inside its bin (shared-memory atomicAdd)
+    unsigned rk[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { unsigned w = sm.wsum[i]; woff += i < wid ? w : 0u; tot += w; }
-    unsigned off = woff + inc - s;
+    for (int q = 0; q < 8; ++q) rk[q] = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        unsigned b = threadIdx.x * 4 + q;
-        if (b < n_bins) {
-            sm.hist[b] = off;
-            unsigned long long g = c[q] ? atomicAdd(&cursors[b], (unsigned long long)c[q]) : 0ull;
-            sm.gdelta[b] = g - off;
-            off += c[q];
+    for (int q = 0; q < 16; ++q)
+        if (vmask >> q & 1u) rk[q >> 1] |= atomicAdd(&sm.hist[ok_part_bin<LEVEL>(key[q], cfg)], 1u) << ((q & 1) * 16);
+    __syncthreads();
+    // local exclusive offsets + one global cursor bump per non-empty bin
+    {
+        unsigned c[4], s = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { unsigned b = threadIdx.x * 4 + q; c[q] = b < n_bins ? sm.hist[b] : 0u; s += c[q]; }
+        unsigned inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
+        if (lane == 31) sm.wsum[wid] = inc;
+        __syncthreads();
+        unsigned woff = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { unsigned w = sm.wsum[i]; woff += i < wid ? w : 0u; tot += w; }
+        unsigned off = woff + inc - s;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            unsigned b = threadIdx.x * 4 + q;
+            if (b < n_bins) {
+                sm.hist[b] = off;
+                if (c[q]) {
+                    const unsigned long long g = atomicAdd(&cursors[b], (unsigned long long)c[q]);
+                    const unsigned long long e = bin_end[b];
+                    // staged indices off .. off+c-1 go to g .. ; those reaching e are spilled
+                    sm.gd[b] = make_ulonglong2(g - off, g >= e ? 0ull : (e - g) + off);
+                }
+                off += c[q];
+            }
         }
+        if (threadIdx.x == 0) sm.total = tot;
+        __syncthreads();
     }
-    if (threadIdx.x == 0) sm.total = tot;
+    // pass B: stage in bin order
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+        if (vmask >> q & 1u)
+            sm.stage[sm.hist[ok_part_bin<LEVEL>(key[q], cfg)] + ((rk[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu)] = key[q];
     __syncthreads();
-}
-
-// staged keys -> global, run by run; entries past their bin's end are spilled, never lost
-__device__ __forceinline__ void ok_scatter_copy_out(OkScatterSmem& sm, const unsigned long long* __restrict__ bin_end,
-                                                    unsigned long long* __restrict__ out, const OkPartSpill& ps) {
+    // copy out: consecutive staged indices of one bin are consecutive in global memory
     const unsigned n = sm.total;
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned b = sm.sbin[i];
-        const unsigned long long dst = sm.gdelta[b] + i;
-        const unsigned long long key = sm.stage[i];
-        if (dst < bin_end[b]) out[dst] = key;
-        else ok_spill(ps.sp, ps.st, key, 1);
+    for (unsigned i = threadIdx.x; i < n; i += 256) {
+        const unsigned long long k = sm.stage[i];
+        const ulonglong2 g = sm.gd[ok_part_bin<LEVEL>(k, cfg)];
+        if (i < g.y) out[g.x + i] = k;
+        else ok_spill(ps.sp, ps.st, k, 1);
     }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------ level 1: from the bases --
-// The 8 warps of a CTA walk their own runs of tiles in lock step; each iteration the CTA holds
-// <= 8192 k-mers.  Pass A ranks them (smem atomicAdd), pass B re-rolls and stages them.
+// The 8 warps of a CTA walk their own runs of tiles in lock step; each warp-tile is split in
+// two rounds of 16 window ends per lane, so a round holds <= 4096 k-mers per CTA.
 template <bool MAP_U>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
                      uint64_t n_rec, uint64_t n_tiles, uint64_t tiles_per_warp, unsigned k, OkPartCfg cfg,
                      unsigned long long* __restrict__ cursors, const unsigned long long* __restrict__ bin_end,
@@ -143,42 +169,30 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t t0 = warp * tiles_per_warp;
-    // whole CTA out of range? (warps of one CTA are consecutive)
-    if ((uint64_t)blockIdx.x * 8 * tiles_per_warp >= n_tiles) return;
+    if ((uint64_t)blockIdx.x * 8 * tiles_per_warp >= n_tiles) return;   // whole CTA idle
     unsigned long long my_keys = 0;
     ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t0 + tiles_per_warp, n_tiles, k, lane,
         [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {
-            for (unsigned i = threadIdx.x; i < n_bins; i += blockDim.x) sm.hist[i] = 0;
-            __syncthreads();
-            unsigned rk[16];                                    // 32 ranks, two per register
+            OkRoll roll; roll.init(pc, cc, k);
+            my_keys += __popc(okmask);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) rk[q] = 0;
-            ok_lane_windows_full(pc, cc, okmask, k, [&](int j, uint64_t key) {
-                const unsigned b = ok_part_bin1(ok_part_pos(key, cfg), cfg);
-                const unsigned r = atomicAdd(&sm.hist[b], 1u);
-                rk[j >> 1] |= r << ((j & 1) * 16);
-                ++my_keys;
-            });
-            __syncthreads();
-            ok_scatter_offsets(sm, n_bins, cursors);
-            ok_lane_windows_full(pc, cc, okmask, k, [&](int j, uint64_t key) {
-                const unsigned b = ok_part_bin1(ok_part_pos(key, cfg), cfg);
-                const unsigned idx = sm.hist[b] + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
-                sm.stage[idx] = key;
-                sm.sbin[idx] = (unsigned short)b;
-            });
-            __syncthreads();
-            ok_scatter_copy_out(sm, bin_end, out, ps);
-            __syncthreads();
+            for (int half = 0; half < 2; ++half) {
+                uint64_t key[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) key[q] = roll.step(16 * half + q);
+                // window end j = 16*half + q lives in okmask bit 31-j; make bit q mean key[q]
+                const unsigned vm = __brev(okmask) >> (16 * half) & 0xFFFFu;
+                ok_multisplit16<1>(sm, key, vm, cfg, n_bins, cursors, bin_end, out, ps);
+            }
         });
     my_keys = ok_warp_sum(my_keys);
     if (lane == 0 && my_keys) atomicAdd(n_keys, my_keys);
 }
 
 // --------------------------------------------------------------------- level 2: from keys --
-// work item w: keys src[item_off[w] .. +item_n[w]) all of level-1 bin item_bin[w]
+// work item w: keys src[item_off[w] .. +item_n[w]) (<= 4096), all of level-1 bin item_bin[w]
 template <int LEVEL>  // LEVEL 1: bin by bin1 (keys arriving from peers); LEVEL 2: bin by bin2 inside a bin1
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ item_off,
                     const unsigned* __restrict__ item_n, const unsigned* __restrict__ item_bin, unsigned n_items,
                     OkPartCfg cfg, unsigned long long* __restrict__ cursors,
@@ -191,56 +205,39 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned l
         const unsigned long long* __restrict__ keys = src + item_off[w];
         const unsigned n = item_n[w];
         const unsigned bin_base = LEVEL == 1 ? 0u : item_bin[w] << cfg.b2;
-        for (unsigned i = threadIdx.x; i < n_bins; i += blockDim.x) sm.hist[i] = 0;
-        __syncthreads();
-        unsigned rk[16];
+        uint64_t key[16]; unsigned vm = 0;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) rk[q] = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const unsigned i = j * 256 + threadIdx.x;
-            if (i < n) {
-                const uint64_t x = ok_part_pos(keys[i], cfg);
-                const unsigned b = LEVEL == 1 ? ok_part_bin1(x, cfg) : ok_part_bin2(x, cfg);
-                rk[j >> 1] |= atomicAdd(&sm.hist[b], 1u) << ((j & 1) * 16);
-            }
+        for (int q = 0; q < 16; ++q) {
+            const unsigned i = q * 256 + threadIdx.x;
+            key[q] = 0;
+            if (i < n) { key[q] = __ldcs(keys + i); vm |= 1u << q; }
         }
-        __syncthreads();
-        ok_scatter_offsets(sm, n_bins, cursors + bin_base);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const unsigned i = j * 256 + threadIdx.x;
-            if (i < n) {
-                const unsigned long long key = keys[i];
-                const uint64_t x = ok_part_pos(key, cfg);
-                const unsigned b = LEVEL == 1 ? ok_part_bin1(x, cfg) : ok_part_bin2(x, cfg);
-                const unsigned idx = sm.hist[b] + ((rk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
-                sm.stage[idx] = key;
-                sm.sbin[idx] = (unsigned short)b;
-            }
-        }
-        __syncthreads();
-        ok_scatter_copy_out(sm, bin_end + bin_base, out, ps);
-        __syncthreads();
+        ok_multisplit16<LEVEL>(sm, key, vm, cfg, n_bins, cursors + bin_base, bin_end + bin_base, out, ps);
     }
 }
 
 // ------------------------------------------------------- count one sub-partition in smem --
-// sub-partition p holds keys src[beg[p] .. beg[p]+cnt[p]).  Its distinct keys come out sorted
-// in place (keys -> src[beg[p] ..], counts -> cnt_out[beg[p] ..]); n_distinct[p] says how many.
-__global__ void __launch_bounds__(OK_CT_THREADS)
+// sub-partition p holds keys src[beg[p] .. fill_end[p]).  Its distinct keys come out sorted in
+// place (keys -> src[beg[p] ..], counts -> cnt_out[beg[p] ..]); n_distinct[p] says how many.
+__device__ __forceinline__ unsigned ok_ct_home(uint64_t key, const OkPartCfg& cfg, unsigned sub_bits) {
+    const uint64_t f = ok_part_pos(key, cfg) << sub_bits;     // position inside the sub-partition
+    return (unsigned)(((f >> 32) * (uint64_t)OK_CT_SLOTS) >> 32);
+}
+
+__global__ void __launch_bounds__(OK_CT_THREADS, 2)
 k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __restrict__ beg,
              const unsigned long long* __restrict__ fill_end /* cursor after the scatter */,
              const unsigned long long* __restrict__ cap_end, unsigned n_sub, OkPartCfg cfg,
              unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct, OkPartSpill ps) {
+    constexpr unsigned NT = OK_CT_SLOTS + OK_CT_PAD;            // 8704
+    constexpr unsigned ROUNDS = NT / OK_CT_THREADS;             // 17 strided rounds in the sweep
+    constexpr unsigned NW = OK_CT_THREADS / 32;                 // 16 warps
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem_raw);                 // [SLOTS+PAD]
-    unsigned* tcnt = reinterpret_cast<unsigned*>(tkey + OK_CT_SLOTS + OK_CT_PAD);               // [SLOTS+PAD]
-    __shared__ unsigned wsum[OK_CT_THREADS / 32];
+    unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem_raw);   // [NT]
+    unsigned* tcnt = reinterpret_cast<unsigned*>(tkey + NT);                      // [NT]
+    __shared__ unsigned seg[ROUNDS * NW + 1];       // occupied slots per (round, warp), then exclusive scan
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned sub_bits = cfg.b1 + cfg.b2;
-    constexpr unsigned NT = OK_CT_SLOTS + OK_CT_PAD;
-    constexpr unsigned PER = NT / OK_CT_THREADS;   // 17 slots per thread in the sweep
     for (unsigned p = blockIdx.x; p < n_sub; p += gridDim.x) {
         const unsigned long long b0 = beg[p];
         unsigned long long e0 = fill_end[p];
@@ -249,53 +246,75 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __r
         if (n == 0) { if (threadIdx.x == 0) n_distinct[p] = 0; continue; }
         for (unsigned i = threadIdx.x; i < NT; i += OK_CT_THREADS) { tkey[i] = OK_EMPTY_KEY; tcnt[i] = 0; }
         __syncthreads();
-        for (unsigned i = threadIdx.x; i < n; i += OK_CT_THREADS) {
-            const unsigned long long key = src[b0 + i];
-            const uint64_t f = sub_bits ? (ok_part_pos(key, cfg) << sub_bits) : ok_part_pos(key, cfg);
-            const unsigned h = (unsigned)(((f >> 32) * (uint64_t)OK_CT_SLOTS) >> 32);
-            bool placed = false;
-            for (unsigned s = h; s < h + OK_CT_PAD; ++s) {
-                unsigned long long cur = tkey[s];
-                if (cur == OK_EMPTY_KEY) {
-                    cur = atomicCAS(&tkey[s], OK_EMPTY_KEY, key);
-                    if (cur == OK_EMPTY_KEY) cur = key;
-                }
-                if (cur == key) { atomicAdd(&tcnt[s], 1u); placed = true; break; }
+        // ---- insert: CAS claim + add, 4 keys in flight per thread
+        for (unsigned base = 0; base < n; base += 4 * OK_CT_THREADS) {
+            unsigned long long kk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned i = base + q * OK_CT_THREADS + threadIdx.x;
+                kk[q] = i < n ? __ldcs(src + b0 + i) : OK_EMPTY_KEY;
             }
-            if (!placed) ok_spill(ps.sp, ps.st, key, 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned long long key = kk[q];
+                if (key == OK_EMPTY_KEY) continue;      // canonical k-mers never equal the sentinel
+                const unsigned h = ok_ct_home(key, cfg, sub_bits);
+                bool placed = false;
+                for (unsigned s = h; s < h + OK_CT_PAD; ++s) {
+                    unsigned long long cur = tkey[s];
+                    if (cur == OK_EMPTY_KEY) {
+                        cur = atomicCAS(&tkey[s], OK_EMPTY_KEY, key);
+                        if (cur == OK_EMPTY_KEY) cur = key;
+                    }
+                    if (cur == key) { atomicAdd(&tcnt[s], 1u); placed = true; break; }
+                }
+                if (!placed) ok_spill(ps.sp, ps.st, key, 1);
+            }
         }
         __syncthreads();
-        // ordered sweep: thread t owns slots [t*PER, (t+1)*PER)
-        const unsigned s0 = threadIdx.x * PER;
-        unsigned mine = 0;
+        // ---- ordered sweep, round r covers slots [r*512, (r+1)*512), one per thread
+        unsigned occ = 0;                               // bit r: my slot of round r is occupied
 #pragma unroll
-        for (unsigned q = 0; q < PER; ++q) mine += tkey[s0 + q] != OK_EMPTY_KEY ? 1u : 0u;
-        unsigned inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
-        if (lane == 31) wsum[wid] = inc;
+        for (unsigned r = 0; r < ROUNDS; ++r) {
+            const bool o = tkey[r * OK_CT_THREADS + threadIdx.x] != OK_EMPTY_KEY;
+            const unsigned bal = __ballot_sync(OK_FULL, o);
+            occ |= (o ? 1u : 0u) << r;
+            if (lane == 0) seg[r * NW + wid] = __popc(bal);
+        }
         __syncthreads();
-        unsigned woff = 0, tot = 0;
+        if (wid == 0) {                                 // exclusive scan of the 272 segment counts
+            unsigned carry = 0;
+            for (unsigned i0 = 0; i0 < ROUNDS * NW; i0 += 32) {
+                const unsigned i = i0 + lane;
+                const unsigned v = i < ROUNDS * NW ? seg[i] : 0u;
+                unsigned inc = v;
 #pragma unroll
-        for (int i = 0; i < (int)(OK_CT_THREADS / 32); ++i) { unsigned w = wsum[i]; woff += i < wid ? w : 0u; tot += w; }
-        unsigned before = woff + inc - mine;
-        for (unsigned q = 0; q < PER; ++q) {
-            const unsigned s = s0 + q;
+                for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
+                if (i < ROUNDS * NW) seg[i] = carry + inc - v;
+                carry += __shfl_sync(OK_FULL, inc, 31);
+            }
+            if (lane == 0) seg[ROUNDS * NW] = carry;
+        }
+        __syncthreads();
+        const unsigned tot = seg[ROUNDS * NW];
+#pragma unroll 1
+        for (unsigned r = 0; r < ROUNDS; ++r) {
+            const bool o = occ >> r & 1u;
+            const unsigned bal = __ballot_sync(OK_FULL, o);
+            if (!o) continue;
+            const unsigned s = r * OK_CT_THREADS + threadIdx.x;
             const unsigned long long key = tkey[s];
-            if (key == OK_EMPTY_KEY) continue;
-            const uint64_t f = sub_bits ? (ok_part_pos(key, cfg) << sub_bits) : ok_part_pos(key, cfg);
-            const unsigned h = (unsigned)(((f >> 32) * (uint64_t)OK_CT_SLOTS) >> 32);
+            const unsigned h = ok_ct_home(key, cfg, sub_bits);
             int adj = 0;
-            for (unsigned t = h; t < s; ++t) adj -= tkey[t] > key ? 1 : 0;        // all occupied
-            for (unsigned t = s + 1; t < h + OK_CT_PAD && t < NT; ++t) {
+            for (unsigned t = h; t < s; ++t) adj -= tkey[t] > key ? 1 : 0;          // parked before us, larger
+            for (unsigned t = s + 1; t < h + OK_CT_PAD; ++t) {                       // pushed past us, smaller
                 const unsigned long long kt = tkey[t];
                 if (kt == OK_EMPTY_KEY) break;
                 adj += kt < key ? 1 : 0;
             }
-            const unsigned idx = before + adj;
+            const unsigned idx = seg[r * NW + wid] + __popc(bal & ((1u << lane) - 1u)) + adj;
             src[b0 + idx] = key;                       // idx < tot <= n: stays inside the region
             cnt_out[b0 + idx] = tcnt[s];
-            ++before;
         }
         if (threadIdx.x == 0) n_distinct[p] = tot;
         __syncthreads();
