@@ -79,77 +79,58 @@ k_part_sample_keys(const unsigned long long* __restrict__ keys, uint64_t n, uint
 }
 
 // ------------------------------------------------------------- shared multisplit machinery --
+// Slotted staging: the 8192 staging slots are split evenly among the bins of the level, a key's
+// rank inside its bin (one shared-memory atomicAdd) is its slot, so one pass stages the round.
+// A bin that outgrows its slots in a round sends the excess straight to global memory.
+#define OK_STAGE_SLOTS 8192u
 struct OkScatterSmem {
-    unsigned long long stage[OK_PART_TILE];      // keys of this round, in bin order
-    ulonglong2 gd[OK_PART_MAXBINS];              // .x: global index = .x + staged index; .y: staged-index limit
-    unsigned hist[OK_PART_MAXBINS];              // per-bin count, then local exclusive offset
-    unsigned wsum[8];
-    unsigned total;
+    unsigned long long stage[OK_STAGE_SLOTS];
+    unsigned hist[OK_PART_MAXBINS];              // zero between rounds
 };
 
+__device__ __forceinline__ void ok_part_put(unsigned long long key, unsigned long long dst, unsigned long long end,
+                                            unsigned long long* __restrict__ out, const OkPartSpill& ps) {
+    if (dst < end) out[dst] = key;
+    else ok_spill(ps.sp, ps.st, key, 1);     // past the sampled capacity of the bin: exact, slow path
+}
+
 // One multisplit round of the CTA (all 256 threads call it together): thread-held keys
-// key[0..15] (bit q of vmask says key[q] exists) -> out, grouped by bin.
+// key[0..15] (bit q of vmask says key[q] exists) -> out, grouped by bin.  sm.hist must be zero on
+// entry and is zero again on exit.
 template <int LEVEL>
 __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_t (&key)[16], unsigned vmask,
-                                                const OkPartCfg& cfg, unsigned n_bins,
+                                                const OkPartCfg& cfg, unsigned bins_log2,
                                                 unsigned long long* __restrict__ cursors,
                                                 const unsigned long long* __restrict__ bin_end,
                                                 unsigned long long* __restrict__ out, const OkPartSpill& ps) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (unsigned i = threadIdx.x; i < n_bins; i += 256) sm.hist[i] = 0;
-    __syncthreads();
-    // pass A: rank of every key inside its bin (shared-memory atomicAdd)
-    unsigned rk[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) rk[q] = 0;
+    const unsigned cap_log2 = 13u - bins_log2, cap = 1u << cap_log2, n_bins = 1u << bins_log2;
 #pragma unroll
     for (int q = 0; q < 16; ++q)
-        if (vmask >> q & 1u) rk[q >> 1] |= atomicAdd(&sm.hist[ok_part_bin<LEVEL>(key[q], cfg)], 1u) << ((q & 1) * 16);
-    __syncthreads();
-    // local exclusive offsets + one global cursor bump per non-empty bin
-    {
-        unsigned c[4], s = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { unsigned b = threadIdx.x * 4 + q; c[q] = b < n_bins ? sm.hist[b] : 0u; s += c[q]; }
-        unsigned inc = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
-        if (lane == 31) sm.wsum[wid] = inc;
-        __syncthreads();
-        unsigned woff = 0, tot = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { unsigned w = sm.wsum[i]; woff += i < wid ? w : 0u; tot += w; }
-        unsigned off = woff + inc - s;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            unsigned b = threadIdx.x * 4 + q;
-            if (b < n_bins) {
-                sm.hist[b] = off;
-                if (c[q]) {
-                    const unsigned long long g = atomicAdd(&cursors[b], (unsigned long long)c[q]);
-                    const unsigned long long e = bin_end[b];
-                    // staged indices off .. off+c-1 go to g .. ; those reaching e are spilled
-                    sm.gd[b] = make_ulonglong2(g - off, g >= e ? 0ull : (e - g) + off);
-                }
-                off += c[q];
-            }
+        if (vmask >> q & 1u) {
+            const unsigned b = ok_part_bin<LEVEL>(key[q], cfg);
+            const unsigned r = atomicAdd(&sm.hist[b], 1u);
+            if (r < cap) sm.stage[(b << cap_log2) + r] = key[q];
+            else ok_part_put(key[q], atomicAdd(&cursors[b], 1ull), bin_end[b], out, ps);
         }
-        if (threadIdx.x == 0) sm.total = tot;
-        __syncthreads();
-    }
-    // pass B: stage in bin order
-#pragma unroll
-    for (int q = 0; q < 16; ++q)
-        if (vmask >> q & 1u)
-            sm.stage[sm.hist[ok_part_bin<LEVEL>(key[q], cfg)] + ((rk[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu)] = key[q];
     __syncthreads();
-    // copy out: consecutive staged indices of one bin are consecutive in global memory
-    const unsigned n = sm.total;
-    for (unsigned i = threadIdx.x; i < n; i += 256) {
-        const unsigned long long k = sm.stage[i];
-        const ulonglong2 g = sm.gd[ok_part_bin<LEVEL>(k, cfg)];
-        if (i < g.y) out[g.x + i] = k;
-        else ok_spill(ps.sp, ps.st, k, 1);
+    // copy out: a warp takes 32 bins at a time, one global cursor bump per non-empty bin
+    for (unsigned b0 = wid * 32; b0 < n_bins; b0 += 256) {
+        const unsigned b = b0 + lane;
+        unsigned c = 0; unsigned long long g = 0, e = 0;
+        if (b < n_bins) {
+            c = sm.hist[b]; sm.hist[b] = 0;
+            if (c > cap) c = cap;
+            if (c) { g = atomicAdd(&cursors[b], (unsigned long long)c); e = bin_end[b]; }
+        }
+        unsigned live = __ballot_sync(OK_FULL, c != 0);
+        while (live) {
+            const int i = __ffs(live) - 1; live &= live - 1;
+            const unsigned cnt = __shfl_sync(OK_FULL, c, i);
+            const unsigned long long base = __shfl_sync(OK_FULL, g, i), end = __shfl_sync(OK_FULL, e, i);
+            const unsigned long long* st = sm.stage + ((b0 + i) << cap_log2);
+            for (unsigned j = lane; j < cnt; j += 32) ok_part_put(st[j], base + j, end, out, ps);
+        }
     }
     __syncthreads();
 }
@@ -165,11 +146,12 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
                      unsigned long long* __restrict__ out, OkPartSpill ps, unsigned long long* __restrict__ n_keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
-    const unsigned n_bins = 1u << cfg.b1;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t t0 = warp * tiles_per_warp;
     if ((uint64_t)blockIdx.x * 8 * tiles_per_warp >= n_tiles) return;   // whole CTA idle
+    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += 256) sm.hist[i] = 0;
+    __syncthreads();
     unsigned long long my_keys = 0;
     ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t0 + tiles_per_warp, n_tiles, k, lane,
         [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {
@@ -182,7 +164,7 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
                 for (int q = 0; q < 16; ++q) key[q] = roll.step(16 * half + q);
                 // window end j = 16*half + q lives in okmask bit 31-j; make bit q mean key[q]
                 const unsigned vm = __brev(okmask) >> (16 * half) & 0xFFFFu;
-                ok_multisplit16<1>(sm, key, vm, cfg, n_bins, cursors, bin_end, out, ps);
+                ok_multisplit16<1>(sm, key, vm, cfg, cfg.b1, cursors, bin_end, out, ps);
             }
         });
     my_keys = ok_warp_sum(my_keys);
@@ -200,7 +182,9 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned l
                     OkPartSpill ps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
-    const unsigned n_bins = 1u << (LEVEL == 1 ? cfg.b1 : cfg.b2);
+    const unsigned bins_log2 = LEVEL == 1 ? cfg.b1 : cfg.b2;
+    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += 256) sm.hist[i] = 0;
+    __syncthreads();
     for (unsigned w = blockIdx.x; w < n_items; w += gridDim.x) {
         const unsigned long long* __restrict__ keys = src + item_off[w];
         const unsigned n = item_n[w];
@@ -212,7 +196,7 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned l
             key[q] = 0;
             if (i < n) { key[q] = __ldcs(keys + i); vm |= 1u << q; }
         }
-        ok_multisplit16<LEVEL>(sm, key, vm, cfg, n_bins, cursors + bin_base, bin_end + bin_base, out, ps);
+        ok_multisplit16<LEVEL>(sm, key, vm, cfg, bins_log2, cursors + bin_base, bin_end + bin_base, out, ps);
     }
 }
 
@@ -244,7 +228,12 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __r
         if (e0 > cap_end[p]) e0 = cap_end[p];          // the rest was spilled by the scatter
         const unsigned n = (unsigned)(e0 - b0);
         if (n == 0) { if (threadIdx.x == 0) n_distinct[p] = 0; continue; }
-        for (unsigned i = threadIdx.x; i < NT; i += OK_CT_THREADS) { tkey[i] = OK_EMPTY_KEY; tcnt[i] = 0; }
+        {   // 128-bit stores: two keys / four counts at a time
+            ulonglong2* k2 = reinterpret_cast<ulonglong2*>(tkey);
+            uint4* c4 = reinterpret_cast<uint4*>(tcnt);
+            for (unsigned i = threadIdx.x; i < NT / 2; i += OK_CT_THREADS) k2[i] = make_ulonglong2(OK_EMPTY_KEY, OK_EMPTY_KEY);
+            for (unsigned i = threadIdx.x; i < NT / 4; i += OK_CT_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
         // ---- insert: CAS claim + add, 4 keys in flight per thread
         for (unsigned base = 0; base < n; base += 4 * OK_CT_THREADS) {
@@ -274,11 +263,14 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __r
         __syncthreads();
         // ---- ordered sweep, round r covers slots [r*512, (r+1)*512), one per thread
         unsigned occ = 0;                               // bit r: my slot of round r is occupied
+        unsigned long long pre_lo = 0, pre_hi = 0;      // 5 bits per round: occupied slots of my warp segment before mine
 #pragma unroll
         for (unsigned r = 0; r < ROUNDS; ++r) {
             const bool o = tkey[r * OK_CT_THREADS + threadIdx.x] != OK_EMPTY_KEY;
             const unsigned bal = __ballot_sync(OK_FULL, o);
             occ |= (o ? 1u : 0u) << r;
+            const unsigned long long before = __popc(bal & ((1u << lane) - 1u));
+            if (r < 12) pre_lo |= before << (5 * r); else pre_hi |= before << (5 * (r - 12));
             if (lane == 0) seg[r * NW + wid] = __popc(bal);
         }
         __syncthreads();
@@ -297,22 +289,24 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __r
         }
         __syncthreads();
         const unsigned tot = seg[ROUNDS * NW];
-#pragma unroll 1
-        for (unsigned r = 0; r < ROUNDS; ++r) {
-            const bool o = occ >> r & 1u;
-            const unsigned bal = __ballot_sync(OK_FULL, o);
-            if (!o) continue;
+        // second pass over MY occupied slots only (lanes pack their work, sparse tables cost little)
+        while (occ) {
+            const unsigned r = __ffs(occ) - 1; occ &= occ - 1;
             const unsigned s = r * OK_CT_THREADS + threadIdx.x;
             const unsigned long long key = tkey[s];
-            const unsigned h = ok_ct_home(key, cfg, sub_bits);
+            const unsigned before = (unsigned)((r < 12 ? pre_lo >> (5 * r) : pre_hi >> (5 * (r - 12))) & 31u);
             int adj = 0;
-            for (unsigned t = h; t < s; ++t) adj -= tkey[t] > key ? 1 : 0;          // parked before us, larger
-            for (unsigned t = s + 1; t < h + OK_CT_PAD; ++t) {                       // pushed past us, smaller
-                const unsigned long long kt = tkey[t];
-                if (kt == OK_EMPTY_KEY) break;
-                adj += kt < key ? 1 : 0;
+            const bool lone = (s == 0 || tkey[s - 1] == OK_EMPTY_KEY) && (s + 1 >= NT || tkey[s + 1] == OK_EMPTY_KEY);
+            if (!lone) {
+                const unsigned h = ok_ct_home(key, cfg, sub_bits);
+                for (unsigned t = h; t < s; ++t) adj -= tkey[t] > key ? 1 : 0;          // parked before us, larger
+                for (unsigned t = s + 1; t < h + OK_CT_PAD; ++t) {                       // pushed past us, smaller
+                    const unsigned long long kt = tkey[t];
+                    if (kt == OK_EMPTY_KEY) break;
+                    adj += kt < key ? 1 : 0;
+                }
             }
-            const unsigned idx = seg[r * NW + wid] + __popc(bal & ((1u << lane) - 1u)) + adj;
+            const unsigned idx = seg[r * NW + wid] + before + adj;
             src[b0 + idx] = key;                       // idx < tot <= n: stays inside the region
             cnt_out[b0 + idx] = tcnt[s];
         }
