@@ -344,7 +344,7 @@ struct PartPlan {
 bool part_eligible(const ok_counter* c, uint64_t n_units) {
     if (c->path_mode == 1) return false;
     if (c->run_valid || c->occupied) return false;
-    if (n_units >= (1ull << 32)) return false;
+    if (n_units >= (1ull << 31)) return false;   // scatter cursors are staged as 32-bit offsets
     return c->path_mode == 2 || n_units >= PART_MIN_BASES;
 }
 

@@ -85,7 +85,8 @@ k_part_sample_keys(const unsigned long long* __restrict__ keys, uint64_t n, uint
 #define OK_STAGE_SLOTS 8192u
 struct OkScatterSmem {
     unsigned long long stage[OK_STAGE_SLOTS];
-    unsigned hist[OK_PART_MAXBINS];              // zero between rounds
+    unsigned hist[OK_PART_MAXBINS];              // keys per bin this round; zero between rounds
+    unsigned gbase[OK_PART_MAXBINS];             // global index of the bin's first staged key (buffers < 2^32 keys)
 };
 
 __device__ __forceinline__ void ok_part_put(unsigned long long key, unsigned long long dst, unsigned long long end,
@@ -114,24 +115,36 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
             else ok_part_put(key[q], atomicAdd(&cursors[b], 1ull), bin_end[b], out, ps);
         }
     __syncthreads();
-    // copy out: a warp takes 32 bins at a time, one global cursor bump per non-empty bin
-    for (unsigned b0 = wid * 32; b0 < n_bins; b0 += 256) {
-        const unsigned b = b0 + lane;
-        unsigned c = 0; unsigned long long g = 0, e = 0;
-        if (b < n_bins) {
-            c = sm.hist[b]; sm.hist[b] = 0;
-            if (c > cap) c = cap;
-            if (c) { g = atomicAdd(&cursors[b], (unsigned long long)c); e = bin_end[b]; }
+    // copy out.  Warp w owns staging slots [w*1024, (w+1)*1024) = a contiguous range of bins.
+    // (1) one global cursor bump per non-empty bin; a bin whose region is full spills its tail here
+    const unsigned bins_per_warp = n_bins >= 8 ? n_bins >> 3 : 1u;
+    const unsigned wb0 = wid * bins_per_warp;
+    for (unsigned i = lane; i < bins_per_warp && wb0 + i < n_bins; i += 32) {
+        const unsigned b = wb0 + i;
+        unsigned c = sm.hist[b];
+        if (c > cap) c = cap;
+        if (c) {
+            const unsigned long long g = atomicAdd(&cursors[b], (unsigned long long)c), e = bin_end[b];
+            if (g + c > e) {
+                const unsigned keep = g < e ? (unsigned)(e - g) : 0u;
+                for (unsigned r = keep; r < c; ++r) ok_spill(ps.sp, ps.st, sm.stage[(b << cap_log2) + r], 1);
+                c = keep;
+            }
+            sm.gbase[b] = (unsigned)g;
         }
-        unsigned live = __ballot_sync(OK_FULL, c != 0);
-        while (live) {
-            const int i = __ffs(live) - 1; live &= live - 1;
-            const unsigned cnt = __shfl_sync(OK_FULL, c, i);
-            const unsigned long long base = __shfl_sync(OK_FULL, g, i), end = __shfl_sync(OK_FULL, e, i);
-            const unsigned long long* st = sm.stage + ((b0 + i) << cap_log2);
-            for (unsigned j = lane; j < cnt; j += 32) ok_part_put(st[j], base + j, end, out, ps);
+        sm.hist[b] = c;
+    }
+    __syncwarp();
+    // (2) dense walk over the warp's staging slots: consecutive lanes = consecutive slots of a bin
+    if (wb0 < n_bins) {
+        const unsigned t_end = (wb0 + bins_per_warp) << cap_log2;
+        for (unsigned t = (wb0 << cap_log2) + lane; t < t_end; t += 32) {
+            const unsigned b = t >> cap_log2, r = t & (cap - 1u);
+            if (r < sm.hist[b]) out[(unsigned long long)sm.gbase[b] + r] = sm.stage[t];
         }
     }
+    __syncwarp();
+    for (unsigned i = lane; i < bins_per_warp && wb0 + i < n_bins; i += 32) sm.hist[wb0 + i] = 0;
     __syncthreads();
 }
 
