@@ -389,7 +389,8 @@ void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl) {
     pl.cfg.key_shift = 64 - 2 * c->k;
     pl.cfg.shard_log2 = 0;
     for (int g = c->n_shards; g > 1; g >>= 1) ++pl.cfg.shard_log2;
-    pl.cfg.b1 = std::min(bits, 8u);
+    // one level up to 256 bins; two balanced levels beyond (staging runs stay >= 8 keys per bin)
+    pl.cfg.b1 = bits <= 8 ? bits : (bits + 1) / 2;
     pl.cfg.b2 = bits - pl.cfg.b1;
     pl.n_sub = 1u << bits;
     pl.n_bin1 = 1u << pl.cfg.b1;
