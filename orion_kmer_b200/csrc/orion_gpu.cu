@@ -138,6 +138,8 @@ struct ok_counter {
     unsigned long long* d_buf2 = nullptr; uint64_t cap_buf2 = 0;
     unsigned long long* d_meta = nullptr; uint64_t cap_meta = 0;     // beg | cursor | cap_end | scan (per sub-partition) + level-1 arrays
     unsigned* d_hist = nullptr; uint64_t cap_hist = 0;               // sample histogram / n_distinct
+    unsigned* d_hist2 = nullptr; uint64_t cap_hist2 = 0;             // retry list of the count kernel
+    uint64_t n_retry = 0;
     unsigned long long* d_items = nullptr; uint64_t cap_items = 0;   // level-2 work items
     float ms_sample = 0, ms_scatter1 = 0, ms_scatter2 = 0, ms_count = 0, ms_compact = 0;
     cudaEvent_t ev_p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -334,7 +336,7 @@ constexpr unsigned PART_MAX_BITS = 18;            // 8 bits at level 1 + up to 1
 struct PartPlan {
     OkPartCfg cfg{};
     unsigned n_sub = 1, n_bin1 = 1;
-    uint64_t total_cap = 0;
+    uint64_t total_cap = 0, est_keys = 0;
     // device arrays inside c->d_meta
     unsigned long long *beg = nullptr, *cursor = nullptr, *cap_end = nullptr, *scan = nullptr;
     unsigned long long *cursor1 = nullptr, *end1 = nullptr;
@@ -358,6 +360,7 @@ int part_plan(ok_counter* c, uint64_t n_units, uint64_t sample_stride, PartPlan&
     uint64_t run = 0;
     for (unsigned p = 0; p < n_sub; ++p) {
         uint64_t est = (uint64_t)hist[p] * sample_stride;
+        pl.est_keys += est;
         uint64_t cap = est;
         if (sample_stride > 1) cap += (uint64_t)(6.0 * std::sqrt((double)est * (double)sample_stride)) + 128;
         if (cap > n_units) cap = n_units;
@@ -435,11 +438,44 @@ int part_finish(ok_counter* c, PartPlan& pl) {
     }
     CU(cudaEventRecord(c->ev_p[3], c->s_main));
     // count every sub-partition in shared memory; sorted runs land in place
-    const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
-    TRY(set_smem(k_part_count, ct_smem));
-    unsigned* d_nd = c->d_hist;   // the sample histogram is no longer needed
-    LAUNCH(k_part_count, std::min<unsigned>(pl.n_sub, grid_sm * 2), OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg,
-           pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, ps);
+    unsigned* d_nd = c->d_hist;   // the sample histogram is no longer needed: [n_sub] n_distinct | [n_sub] fail list | n_fail
+    TRY(dev_reserve(&c->d_hist2, &c->cap_hist2, (uint64_t)pl.n_sub + 2));
+    unsigned* d_fail = c->d_hist2;
+    unsigned* d_nfail = d_fail + pl.n_sub;
+    CU(cudaMemsetAsync(d_nfail, 0, sizeof(unsigned), c->s_main));
+    // first launch: tables sized for a quarter of the average sub-partition (keys mostly repeat)
+    uint64_t avg_keys = pl.est_keys / pl.n_sub + 1;
+    unsigned slots1 = 512;
+    while (slots1 < avg_keys / 4 && slots1 < OK_CT_SLOTS) slots1 <<= 1;
+    auto ct_smem = [](unsigned slots, unsigned threads) {
+        const unsigned nt = slots + (slots >= 4096 ? OK_CT_PAD : slots / 4);
+        const unsigned cover = (nt + threads - 1) / threads * threads;
+        return (size_t)cover * 12;
+    };
+    if (slots1 <= 4096) {
+        const size_t sm1 = ct_smem(slots1, 256);
+        TRY(set_smem(k_part_count<256>, sm1));
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_part_count<256>, 256, sm1);
+        LAUNCH(k_part_count<256>, std::min<unsigned>(pl.n_sub, grid_sm * std::max(per_sm, 1)), 256, sm1, c->s_main, c->d_buf2,
+               pl.beg, pl.cursor, pl.cap_end, (const unsigned*)nullptr, pl.n_sub, slots1, pl.cfg, c->d_buf1, d_nd, d_fail, d_nfail, ps);
+        unsigned n_fail = 0;
+        CU(cudaMemcpyAsync(&n_fail, d_nfail, sizeof(unsigned), cudaMemcpyDeviceToHost, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        c->n_retry = n_fail;
+        if (n_fail) {
+            const size_t sm2 = ct_smem(OK_CT_SLOTS, 512);
+            TRY(set_smem(k_part_count<512>, sm2));
+            LAUNCH(k_part_count<512>, std::min<unsigned>(n_fail, grid_sm * 2), 512, sm2, c->s_main, c->d_buf2, pl.beg, pl.cursor,
+                   pl.cap_end, (const unsigned*)d_fail, n_fail, OK_CT_SLOTS, pl.cfg, c->d_buf1, d_nd, d_fail, d_nfail, ps);
+        }
+    } else {
+        const size_t sm2 = ct_smem(OK_CT_SLOTS, 512);
+        TRY(set_smem(k_part_count<512>, sm2));
+        LAUNCH(k_part_count<512>, std::min<unsigned>(pl.n_sub, grid_sm * 2), 512, sm2, c->s_main, c->d_buf2, pl.beg, pl.cursor,
+               pl.cap_end, (const unsigned*)nullptr, pl.n_sub, OK_CT_SLOTS, pl.cfg, c->d_buf1, d_nd, d_fail, d_nfail, ps);
+        c->n_retry = 0;
+    }
     CU(cudaEventRecord(c->ev_p[4], c->s_main));
     LAUNCH(k_widen_u32, grid_for(pl.n_sub), 256, 0, c->s_main, d_nd, pl.scan, (uint64_t)pl.n_sub);
     LAUNCH(k_scan_tiles, 1, 1024, 0, c->s_main, pl.scan, (uint64_t)pl.n_sub, pl.scan + pl.n_sub);
@@ -741,7 +777,7 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
     cudaFree(c->d_bases); cudaFree(c->d_off); cudaFree(c->d_tiles);
     cudaFree(c->d_out_keys); cudaFree(c->d_out_counts);
     cudaFree(c->d_run_keys); cudaFree(c->d_run_counts); cudaFree(c->d_buf1); cudaFree(c->d_buf2);
-    cudaFree(c->d_meta); cudaFree(c->d_hist); cudaFree(c->d_items);
+    cudaFree(c->d_meta); cudaFree(c->d_hist); cudaFree(c->d_hist2); cudaFree(c->d_items);
     for (auto e : c->ev_p) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_chunks) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
