@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -394,6 +395,10 @@ void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl) {
     for (int g = c->n_shards; g > 1; g >>= 1) ++pl.cfg.shard_log2;
     // one level up to 256 bins; two balanced levels beyond (staging runs stay >= 8 keys per bin)
     pl.cfg.b1 = bits <= 8 ? bits : (bits + 1) / 2;
+    if (const char* ev = getenv("ORION_B1")) {   // tuning knob: bits of the first scatter level
+        unsigned v = (unsigned)atoi(ev);
+        if (v >= 1 && v <= 10 && v <= bits && bits - v <= 10) pl.cfg.b1 = v;
+    }
     pl.cfg.b2 = bits - pl.cfg.b1;
     pl.n_sub = 1u << bits;
     pl.n_bin1 = 1u << pl.cfg.b1;
@@ -437,45 +442,13 @@ int part_finish(ok_counter* c, PartPlan& pl) {
         }
     }
     CU(cudaEventRecord(c->ev_p[3], c->s_main));
-    // count every sub-partition in shared memory; sorted runs land in place
-    unsigned* d_nd = c->d_hist;   // the sample histogram is no longer needed: [n_sub] n_distinct | [n_sub] fail list | n_fail
-    TRY(dev_reserve(&c->d_hist2, &c->cap_hist2, (uint64_t)pl.n_sub + 2));
-    unsigned* d_fail = c->d_hist2;
-    unsigned* d_nfail = d_fail + pl.n_sub;
-    CU(cudaMemsetAsync(d_nfail, 0, sizeof(unsigned), c->s_main));
-    // first launch: tables sized for a quarter of the average sub-partition (keys mostly repeat)
-    uint64_t avg_keys = pl.est_keys / pl.n_sub + 1;
-    unsigned slots1 = 512;
-    while (slots1 < avg_keys / 4 && slots1 < OK_CT_SLOTS) slots1 <<= 1;
-    auto ct_smem = [](unsigned slots, unsigned threads) {
-        const unsigned nt = slots + (slots >= 4096 ? OK_CT_PAD : slots / 4);
-        const unsigned cover = (nt + threads - 1) / threads * threads;
-        return (size_t)cover * 12;
-    };
-    if (slots1 <= 4096) {
-        const size_t sm1 = ct_smem(slots1, 256);
-        TRY(set_smem(k_part_count<256>, sm1));
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_part_count<256>, 256, sm1);
-        LAUNCH(k_part_count<256>, std::min<unsigned>(pl.n_sub, grid_sm * std::max(per_sm, 1)), 256, sm1, c->s_main, c->d_buf2,
-               pl.beg, pl.cursor, pl.cap_end, (const unsigned*)nullptr, pl.n_sub, slots1, pl.cfg, c->d_buf1, d_nd, d_fail, d_nfail, ps);
-        unsigned n_fail = 0;
-        CU(cudaMemcpyAsync(&n_fail, d_nfail, sizeof(unsigned), cudaMemcpyDeviceToHost, c->s_main));
-        CU(cudaStreamSynchronize(c->s_main));
-        c->n_retry = n_fail;
-        if (n_fail) {
-            const size_t sm2 = ct_smem(OK_CT_SLOTS, 512);
-            TRY(set_smem(k_part_count<512>, sm2));
-            LAUNCH(k_part_count<512>, std::min<unsigned>(n_fail, grid_sm * 2), 512, sm2, c->s_main, c->d_buf2, pl.beg, pl.cursor,
-                   pl.cap_end, (const unsigned*)d_fail, n_fail, OK_CT_SLOTS, pl.cfg, c->d_buf1, d_nd, d_fail, d_nfail, ps);
-        }
-    } else {
-        const size_t sm2 = ct_smem(OK_CT_SLOTS, 512);
-        TRY(set_smem(k_part_count<512>, sm2));
-        LAUNCH(k_part_count<512>, std::min<unsigned>(pl.n_sub, grid_sm * 2), 512, sm2, c->s_main, c->d_buf2, pl.beg, pl.cursor,
-               pl.cap_end, (const unsigned*)nullptr, pl.n_sub, OK_CT_SLOTS, pl.cfg, c->d_buf1, d_nd, d_fail, d_nfail, ps);
-        c->n_retry = 0;
-    }
+    // count every sub-partition in shared memory; sorted runs land in place.  (Launch-sized
+    // smaller tables with a retry launch were tried and measured slower -- see DESIGN.md.)
+    const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
+    TRY(set_smem(k_part_count, ct_smem));
+    unsigned* d_nd = c->d_hist;   // the sample histogram is no longer needed
+    LAUNCH(k_part_count, std::min<unsigned>(pl.n_sub, grid_sm * 2), OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg,
+           pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, ps);
     CU(cudaEventRecord(c->ev_p[4], c->s_main));
     LAUNCH(k_widen_u32, grid_for(pl.n_sub), 256, 0, c->s_main, d_nd, pl.scan, (uint64_t)pl.n_sub);
     LAUNCH(k_scan_tiles, 1, 1024, 0, c->s_main, pl.scan, (uint64_t)pl.n_sub, pl.scan + pl.n_sub);

@@ -216,41 +216,26 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned l
 // ------------------------------------------------------- count one sub-partition in smem --
 // sub-partition p holds keys src[beg[p] .. fill_end[p]).  Its distinct keys come out sorted in
 // place (keys -> src[beg[p] ..], counts -> cnt_out[beg[p] ..]); n_distinct[p] says how many.
-__device__ __forceinline__ unsigned ok_ct_home(uint64_t key, const OkPartCfg& cfg, unsigned sub_bits, unsigned slots) {
+__device__ __forceinline__ unsigned ok_ct_home(uint64_t key, const OkPartCfg& cfg, unsigned sub_bits) {
     const uint64_t f = ok_part_pos(key, cfg) << sub_bits;     // position inside the sub-partition
-    return (unsigned)(((f >> 32) * (uint64_t)slots) >> 32);
+    return (unsigned)(((f >> 32) * (uint64_t)OK_CT_SLOTS) >> 32);
 }
 
-// The launch fixes the table size (`slots`, a power of two <= 8192).  With sequencing coverage
-// most keys of a sub-partition repeat, so the first launch uses small tables (a quarter of the
-// average key count) and 256-thread CTAs -- many CTAs per SM, cheap init and sweep.  A
-// sub-partition whose table passes 70 % occupancy is appended to fail_list and redone by a
-// second launch with the full 8192-slot table (where overflow goes to the exact spill list).
-template <unsigned THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(OK_CT_THREADS, 2)
 k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __restrict__ beg,
              const unsigned long long* __restrict__ fill_end /* cursor after the scatter */,
-             const unsigned long long* __restrict__ cap_end, const unsigned* __restrict__ todo, unsigned n_work,
-             unsigned slots, OkPartCfg cfg, unsigned long long* __restrict__ cnt_out,
-             unsigned* __restrict__ n_distinct, unsigned* __restrict__ fail_list, unsigned* __restrict__ n_fail,
-             OkPartSpill ps) {
-    constexpr unsigned NW = THREADS / 32;
-    constexpr unsigned ROUNDS_MAX = (OK_CT_SLOTS + OK_CT_PAD) / 512 + 1;   // 18 rounds at most for either CTA size
+             const unsigned long long* __restrict__ cap_end, unsigned n_sub, OkPartCfg cfg,
+             unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct, OkPartSpill ps) {
+    constexpr unsigned NT = OK_CT_SLOTS + OK_CT_PAD;            // 8704
+    constexpr unsigned ROUNDS = NT / OK_CT_THREADS;             // 17 strided rounds in the sweep
+    constexpr unsigned NW = OK_CT_THREADS / 32;                 // 16 warps
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const bool full = slots == OK_CT_SLOTS;
-    const unsigned pad = slots >= 4096 ? OK_CT_PAD : slots / 4;
-    const unsigned nt = slots + pad;                                     // multiple of 128
-    const unsigned rounds = (nt + THREADS - 1) / THREADS;                // <= 18 (host guarantees)
-    const unsigned cover = rounds * THREADS;
-    const unsigned limit = full ? 0xFFFFFFFFu : (slots / 10) * 7;
-    unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem_raw);   // [cover]
-    unsigned* tcnt = reinterpret_cast<unsigned*>(tkey + cover);                   // [cover]
-    __shared__ unsigned seg[ROUNDS_MAX * NW + 1];   // occupied slots per (round, warp), then exclusive scan
-    __shared__ unsigned claimed;                    // distinct keys claimed (+ 0x10000 per failed probe)
+    unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem_raw);   // [NT]
+    unsigned* tcnt = reinterpret_cast<unsigned*>(tkey + NT);                      // [NT]
+    __shared__ unsigned seg[ROUNDS * NW + 1];       // occupied slots per (round, warp), then exclusive scan
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned sub_bits = cfg.b1 + cfg.b2;
-    for (unsigned w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const unsigned p = todo ? todo[w] : w;
+    for (unsigned p = blockIdx.x; p < n_sub; p += gridDim.x) {
         const unsigned long long b0 = beg[p];
         unsigned long long e0 = fill_end[p];
         if (e0 > cap_end[p]) e0 = cap_end[p];          // the rest was spilled by the scatter
@@ -259,53 +244,42 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __r
         {   // 128-bit stores: two keys / four counts at a time
             ulonglong2* k2 = reinterpret_cast<ulonglong2*>(tkey);
             uint4* c4 = reinterpret_cast<uint4*>(tcnt);
-            for (unsigned i = threadIdx.x; i < cover / 2; i += THREADS) k2[i] = make_ulonglong2(OK_EMPTY_KEY, OK_EMPTY_KEY);
-            for (unsigned i = threadIdx.x; i < cover / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (threadIdx.x == 0) claimed = 0;
+            for (unsigned i = threadIdx.x; i < NT / 2; i += OK_CT_THREADS) k2[i] = make_ulonglong2(OK_EMPTY_KEY, OK_EMPTY_KEY);
+            for (unsigned i = threadIdx.x; i < NT / 4; i += OK_CT_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();
         // ---- insert: CAS claim + add, 4 keys in flight per thread
-        for (unsigned base = 0; base < n; base += 4 * THREADS) {
-            if (*(volatile unsigned*)&claimed > limit) break;    // table too small: stop early
+        for (unsigned base = 0; base < n; base += 4 * OK_CT_THREADS) {
             unsigned long long kk[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const unsigned i = base + q * THREADS + threadIdx.x;
+                const unsigned i = base + q * OK_CT_THREADS + threadIdx.x;
                 kk[q] = i < n ? __ldcs(src + b0 + i) : OK_EMPTY_KEY;
             }
-            unsigned mine = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const unsigned long long key = kk[q];
                 if (key == OK_EMPTY_KEY) continue;      // canonical k-mers never equal the sentinel
-                const unsigned h = ok_ct_home(key, cfg, sub_bits, slots);
+                const unsigned h = ok_ct_home(key, cfg, sub_bits);
                 bool placed = false;
-                for (unsigned s = h; s < h + pad; ++s) {
+                for (unsigned s = h; s < h + OK_CT_PAD; ++s) {
                     unsigned long long cur = tkey[s];
                     if (cur == OK_EMPTY_KEY) {
                         cur = atomicCAS(&tkey[s], OK_EMPTY_KEY, key);
-                        if (cur == OK_EMPTY_KEY) { cur = key; ++mine; }
+                        if (cur == OK_EMPTY_KEY) cur = key;
                     }
                     if (cur == key) { atomicAdd(&tcnt[s], 1u); placed = true; break; }
                 }
-                if (!placed) {
-                    if (full) ok_spill(ps.sp, ps.st, key, 1);
-                    else mine += 0x10000u;              // hand the sub-partition to the full-table launch
-                }
+                if (!placed) ok_spill(ps.sp, ps.st, key, 1);
             }
-            if (!full && mine) atomicAdd(&claimed, mine);
         }
         __syncthreads();
-        if (claimed > limit) {                          // uniform: redo with the full table
-            if (threadIdx.x == 0) { fail_list[atomicAdd(n_fail, 1u)] = p; n_distinct[p] = 0; }
-            __syncthreads();
-            continue;
-        }
-        // ---- ordered sweep, round r covers slots [r*THREADS, (r+1)*THREADS), one per thread
+        // ---- ordered sweep, round r covers slots [r*512, (r+1)*512), one per thread
         unsigned occ = 0;                               // bit r: my slot of round r is occupied
         unsigned long long pre_lo = 0, pre_hi = 0;      // 5 bits per round: occupied slots of my warp segment before mine
-        for (unsigned r = 0; r < rounds; ++r) {
-            const bool o = tkey[r * THREADS + threadIdx.x] != OK_EMPTY_KEY;
+#pragma unroll
+        for (unsigned r = 0; r < ROUNDS; ++r) {
+            const bool o = tkey[r * OK_CT_THREADS + threadIdx.x] != OK_EMPTY_KEY;
             const unsigned bal = __ballot_sync(OK_FULL, o);
             occ |= (o ? 1u : 0u) << r;
             const unsigned long long before = __popc(bal & ((1u << lane) - 1u));
@@ -313,34 +287,33 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __r
             if (lane == 0) seg[r * NW + wid] = __popc(bal);
         }
         __syncthreads();
-        const unsigned n_seg = rounds * NW;
-        if (wid == 0) {                                 // exclusive scan of the segment counts
+        if (wid == 0) {                                 // exclusive scan of the 272 segment counts
             unsigned carry = 0;
-            for (unsigned i0 = 0; i0 < n_seg; i0 += 32) {
+            for (unsigned i0 = 0; i0 < ROUNDS * NW; i0 += 32) {
                 const unsigned i = i0 + lane;
-                const unsigned v = i < n_seg ? seg[i] : 0u;
+                const unsigned v = i < ROUNDS * NW ? seg[i] : 0u;
                 unsigned inc = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
-                if (i < n_seg) seg[i] = carry + inc - v;
+                if (i < ROUNDS * NW) seg[i] = carry + inc - v;
                 carry += __shfl_sync(OK_FULL, inc, 31);
             }
-            if (lane == 0) seg[ROUNDS_MAX * NW] = carry;
+            if (lane == 0) seg[ROUNDS * NW] = carry;
         }
         __syncthreads();
-        const unsigned tot = seg[ROUNDS_MAX * NW];
+        const unsigned tot = seg[ROUNDS * NW];
         // second pass over MY occupied slots only (lanes pack their work, sparse tables cost little)
         while (occ) {
             const unsigned r = __ffs(occ) - 1; occ &= occ - 1;
-            const unsigned s = r * THREADS + threadIdx.x;
+            const unsigned s = r * OK_CT_THREADS + threadIdx.x;
             const unsigned long long key = tkey[s];
             const unsigned before = (unsigned)((r < 12 ? pre_lo >> (5 * r) : pre_hi >> (5 * (r - 12))) & 31u);
             int adj = 0;
-            const bool lone = (s == 0 || tkey[s - 1] == OK_EMPTY_KEY) && (s + 1 >= nt || tkey[s + 1] == OK_EMPTY_KEY);
+            const bool lone = (s == 0 || tkey[s - 1] == OK_EMPTY_KEY) && (s + 1 >= NT || tkey[s + 1] == OK_EMPTY_KEY);
             if (!lone) {
-                const unsigned h = ok_ct_home(key, cfg, sub_bits, slots);
+                const unsigned h = ok_ct_home(key, cfg, sub_bits);
                 for (unsigned t = h; t < s; ++t) adj -= tkey[t] > key ? 1 : 0;          // parked before us, larger
-                for (unsigned t = s + 1; t < h + pad; ++t) {                             // pushed past us, smaller
+                for (unsigned t = s + 1; t < h + OK_CT_PAD; ++t) {                       // pushed past us, smaller
                     const unsigned long long kt = tkey[t];
                     if (kt == OK_EMPTY_KEY) break;
                     adj += kt < key ? 1 : 0;
