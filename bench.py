@@ -255,7 +255,7 @@ def run_ours(args):
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(kname.split(" ")[0])
+            traffic = json.load(open(prof)).get(kname.split(" ")[0].split("<")[0])
         except Exception:
             traffic = None
 

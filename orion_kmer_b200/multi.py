@@ -1,0 +1,156 @@
+"""Multi-GPU count: one process per GPU, k-mers exchanged by owner key range.
+
+Per step and rank:  route (extract + bucket by owner, on the device)  ->  all-to-all of the 8-byte
+k-mers over NCCL/NVLink  ->  count what arrived on the rank's own shard.  Owners are contiguous
+ranges of the monotone k-mer position, so rank r's sorted output is the r-th slice of the global
+sorted table and the ranks' outputs simply concatenate.
+
+torch.distributed is the plumbing (process group, all_to_all_single); every kernel is ours.
+`exchange` works on any backend (the CPU tests drive it over gloo).
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+
+def exchange(dist, torch, send, send_counts, group=None):
+    """send: 1-D int64 tensor holding the k-mers for rank 0, then rank 1, ... (send_counts each).
+    -> (recv tensor, recv_counts list)."""
+    world = dist.get_world_size(group)
+    sc = torch.as_tensor(np.asarray(send_counts, dtype=np.int64), device=send.device)
+    rc = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.cpu().tolist()]
+    recv = torch.empty(sum(recv_counts), dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(recv, send[:int(sum(send_counts))], output_split_sizes=recv_counts,
+                           input_split_sizes=[int(x) for x in send_counts], group=group)
+    return recv, recv_counts
+
+
+class ShardedCounter:
+    """KmerCounter sharded over the ranks of a process group."""
+
+    def __init__(self, ok, torch, dist, k, norm_mode=0):
+        self.ok, self.torch, self.dist = ok, torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.counter = ok.KmerCounter(k, norm_mode)
+        self.counter.set_shard(self.rank, self.world)
+        self.d_send = None
+        self.t = {}
+
+    def count_batch_device(self, d_bases, n_bases, d_off, n_reads):
+        torch = self.torch
+        if self.d_send is None or self.d_send.numel() < n_bases:
+            self.d_send = torch.empty(n_bases, dtype=torch.int64, device=d_bases.device)
+        t0 = time.perf_counter()
+        counts = self.counter.route_batch_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
+                                                 self.world, self.d_send.data_ptr())
+        t1 = time.perf_counter()
+        recv, _ = exchange(self.dist, torch, self.d_send, counts)
+        torch.cuda.current_stream().synchronize()
+        t2 = time.perf_counter()
+        self.counter.add_kmers_device(recv.data_ptr(), recv.numel())
+        t3 = time.perf_counter()
+        self.t = {"route_ms": (t1 - t0) * 1e3, "exchange_ms": (t2 - t1) * 1e3, "count_ms": (t3 - t2) * 1e3,
+                  "sent_kmers": int(counts.sum()), "sent_off_rank": int(counts.sum() - counts[self.rank]),
+                  "recv_kmers": int(recv.numel())}
+        del recv
+
+    def clear(self):
+        self.counter.clear()
+
+    def close(self):
+        self.counter.close()
+
+
+def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config, ClockSampler, measured_peak,
+          metric):
+    import torch.distributed as dist
+    K = 31
+    n_reads = args.reads
+    genome_len = (args.genome or n_reads * 5) * world         # coverage stays 30x as ranks are added
+    g, bases, off = make_workload(ok, synth, n_reads, genome_len, first_read=rank * n_reads)
+    n_bases = len(bases)
+    h_bases = torch.from_numpy(bases)          # page-locked (ok_host_alloc) host buffers
+    h_off = torch.from_numpy(off.view(np.int64))
+    d_bases = h_bases.cuda()
+    d_off = h_off.cuda()
+    sc = ShardedCounter(ok, torch, dist, K)
+
+    def step_device():
+        sc.clear()
+        sc.count_batch_device(d_bases, n_bases, d_off, n_reads)
+        return sc.counter.finish_device(1)
+
+    def step_host():
+        sc.clear()
+        d_bases.copy_(h_bases, non_blocking=True)
+        d_off.copy_(h_off, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        sc.count_batch_device(d_bases, n_bases, d_off, n_reads)
+        pk, pc, n = sc.counter.finish_raw(1)
+        sc.counter.free_result(pk, pc)
+        return n
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        acc = []
+        for _ in range(steps):
+            fn()
+            acc.append(dict(sc.t, **{k: v for k, v in sc.counter.stats().items() if k.startswith("ms_")}))
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item()), acc
+
+    sampler = ClockSampler(local)
+    launches0 = ok.launch_count()
+    sampler.start()
+    dt, acc = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop()
+    launches = ok.launch_count() - launches0
+    st = sc.counter.stats()
+    dt_e2e, _ = timed(step_host, args.steps, max(1, args.warmup))
+    n_out = sc.counter.finish_device(1)[2]
+
+    # whole-job totals
+    tot = torch.tensor([st["n_windows"], st["n_distinct"], n_bases], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tot)
+    windows, distinct, total_bases = (float(x) for x in tot.tolist())
+    mean = {k: float(np.mean([a[k] for a in acc])) for k in acc[0]}
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_step = total_bases * 1.5 + windows * 16.0 + distinct * 32.0 + windows * 32.0   # + multi-GPU 32 W (8d)
+        nvlink_bytes = mean["sent_off_rank"] * 8.0
+        line = {
+            "metric": metric, "value": total_bases / dt, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(n_reads, genome_len, world),
+            "e2e": {"value": total_bases / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3,
+                    "h2d_bytes_per_step": int((n_bases + (n_reads + 1) * 8) * world),
+                    "d2h_bytes_per_step": int(16 * distinct)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole step (route + all-to-all + sharded count), rank 0 phases below",
+                         "achieved": alg_step / dt / 1e9, "peak": peak * world, "unit": "GB/s",
+                         "frac": alg_step / dt / 1e9 / (peak * world), "peak_source": peak_src + " x n_gpus",
+                         "traffic": None,
+                         "nvlink": {"bytes_sent_per_rank": nvlink_bytes, "exchange_ms": mean["exchange_ms"],
+                                    "achieved_GBs_per_rank": nvlink_bytes / (mean["exchange_ms"] / 1e3) / 1e9,
+                                    "peak_GBs": 770.0, "peak_source": "B200_PROFILING.md peer copy per direction"}},
+            "phases_ms": mean,
+            "table": {"windows": int(windows), "distinct": int(distinct), "rank0_distinct": int(n_out),
+                      "spilled": int(st["n_spilled"])},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    sc.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,78 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the owner rule + exchange + concatenation.
+The k-mers come from the host emulation of the extraction kernel (same __host__ __device__ code),
+the owner of each k-mer from the same routine k_route uses; local counting is numpy.  What is
+checked: owners form contiguous key ranges, the exchange delivers every k-mer to its owner, and the
+ranks' sorted tables concatenate to the oracle's global table."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+K, READS = 21, 3000
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_reads(rank):
+    from orion_kmer_b200 import synth
+    g = synth.genome(7, 60_000)
+    return synth.reads(g, 8, READS, first_read=rank * READS, threads=1), synth.read_offsets(READS)
+
+
+def _worker(rank, world, port, ret):
+    import orion_kmer_b200 as ok
+    from orion_kmer_b200 import multi
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    try:
+        bases, off = _rank_reads(rank)
+        keys = np.zeros(len(bases), dtype=np.uint64)
+        n = C.c_uint64()
+        assert ok.lib().okx_emulate_extract(ok._ptr(bases), len(bases), ok._ptr(off), READS, K, ok.NORMALIZED,
+                                            ok._ptr(keys), len(keys), C.byref(n)) == 0
+        keys = keys[:n.value]
+        owners = np.zeros(len(keys), dtype=np.int32)
+        assert ok.lib().okx_owner_of(ok._ptr(keys), len(keys), K, world, ok._ptr(owners)) == 0
+        order = np.argsort(owners, kind="stable")
+        send = torch.from_numpy(keys[order].view(np.int64).copy())
+        counts = np.bincount(owners, minlength=world)
+        recv, recv_counts = multi.exchange(dist, torch, send, counts)
+        mine = recv.numpy().view(np.uint64)
+        chk = np.zeros(len(mine), dtype=np.int32)
+        assert ok.lib().okx_owner_of(ok._ptr(mine), len(mine), K, world, ok._ptr(chk)) == 0
+        assert np.all(chk == rank), "a k-mer reached a rank that does not own it"
+        uk, uc = np.unique(mine, return_counts=True)
+        out = [None] * world if rank == 0 else None
+        dist.gather_object((uk, uc.astype(np.uint64), int(len(keys)), int(sum(recv_counts))), out, dst=0)
+        if rank == 0:
+            ret["tables"] = out
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_exchange_concatenates_to_global_table(oracle):
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        tables = ret["tables"]
+    all_bases = np.concatenate([_rank_reads(r)[0] for r in range(world)])
+    all_off = np.arange(world * READS + 1, dtype=np.uint64) * np.uint64(150)
+    wk, wc = oracle.count_batch(K, all_bases, all_off)
+    gk = np.concatenate([t[0] for t in tables])
+    gc = np.concatenate([t[1] for t in tables])
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc)          # rank order == key order
+    assert sum(t[2] for t in tables) == sum(t[3] for t in tables) == int(wc.sum())
+    # both ranks hold a comparable share (owner ranges are balanced by the canonical prior)
+    shares = [len(t[0]) / len(wk) for t in tables]
+    assert all(0.4 < s < 0.6 for s in shares), shares
