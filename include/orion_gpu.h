@@ -98,6 +98,24 @@ int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers, uint64_t
 int ok_counter_route_batch_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
                                   const uint64_t* d_rec_offsets, uint64_t n_records,
                                   int n_ranks, uint64_t* d_out, uint64_t* out_counts);
+/* multi-GPU, fused form of the exchange: the routing kernel itself writes every owner's k-mers
+ * into that owner's receive buffer (peer memory over NVLink), so the transfer overlaps the
+ * extraction and no separate all-to-all runs.
+ *   ok_peer_buffer_*            a device buffer other ranks can map (CUDA IPC, 64-byte handle)
+ *   ok_counter_route_count_device    pass 0: k-mers of this batch per owner rank
+ *   ok_counter_route_scatter_device  pass 1: d_dst[r] = this sender's slice of rank r's buffer,
+ *                                    exactly counts[r] k-mers are written to it
+ * The receiver then calls ok_counter_add_kmers_device on its own buffer (after a barrier). */
+int ok_peer_buffer_create(uint64_t bytes, void** d_ptr, uint8_t handle[64]);
+int ok_peer_buffer_open(const uint8_t handle[64], void** d_ptr);
+int ok_peer_buffer_close(void* d_ptr);
+int ok_peer_buffer_destroy(void* d_ptr);
+int ok_counter_route_count_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                                  const uint64_t* d_rec_offsets, uint64_t n_records, int n_ranks,
+                                  uint64_t* out_counts);
+int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                                    const uint64_t* d_rec_offsets, uint64_t n_records, int n_ranks,
+                                    uint64_t* const* d_dst, const uint64_t* counts);
 /* count.rs:106-119: entries with count >= min_count, ascending by k-mer value. */
 int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** kmers, uint64_t** counts,
                       uint64_t* n);

@@ -84,6 +84,12 @@ ABI = {
     "ok_counter_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
     "ok_counter_add_kmers_device": (C.c_int, [vp, vp, C.c_uint64]),
     "ok_counter_route_batch_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp]),
+    "ok_peer_buffer_create": (C.c_int, [C.c_uint64, C.POINTER(vp), vp]),
+    "ok_peer_buffer_open": (C.c_int, [vp, C.POINTER(vp)]),
+    "ok_peer_buffer_close": (C.c_int, [vp]),
+    "ok_peer_buffer_destroy": (C.c_int, [vp]),
+    "ok_counter_route_count_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp]),
+    "ok_counter_route_scatter_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp]),
     "ok_counter_finish": (C.c_int, [vp, C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]),
     "ok_counter_finish_device": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp), u64p]),
     "ok_counter_set_path": (C.c_int, [vp, C.c_int]),
@@ -318,6 +324,19 @@ class KmerCounter:
                                                    n_ranks, d_out_ptr, _ptr(counts)))
         return counts
 
+    def route_count_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, n_ranks):
+        counts = np.zeros(n_ranks, dtype=np.uint64)
+        _check(lib().ok_counter_route_count_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records, n_ranks,
+                                                   _ptr(counts)))
+        return counts
+
+    def route_scatter_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, dst_ptrs, counts):
+        n_ranks = len(dst_ptrs)
+        arr = (vp * n_ranks)(*[int(p) for p in dst_ptrs])
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        _check(lib().ok_counter_route_scatter_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records, n_ranks,
+                                                     arr, _ptr(counts)))
+
     def add_kmers_device(self, d_kmers_ptr, n):
         _check(lib().ok_counter_add_kmers_device(self._h, d_kmers_ptr, n))
 
@@ -465,6 +484,35 @@ class KmerSet:
 
     def __del__(self):
         self.close()
+
+
+class PeerBuffer:
+    """device buffer that other ranks (processes) can map over NVLink"""
+
+    def __init__(self, nbytes):
+        p = vp()
+        self.handle = (C.c_uint8 * 64)()
+        _check(lib().ok_peer_buffer_create(nbytes, C.byref(p), self.handle))
+        self.ptr, self.nbytes, self._peers = p.value, nbytes, []
+
+    def handle_bytes(self):
+        return bytes(self.handle)
+
+    @staticmethod
+    def open(handle_bytes):
+        p = vp()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle_bytes)
+        _check(lib().ok_peer_buffer_open(buf, C.byref(p)))
+        return p.value
+
+    @staticmethod
+    def close_peer(ptr):
+        _check(lib().ok_peer_buffer_close(ptr))
+
+    def destroy(self):
+        if self.ptr:
+            lib().ok_peer_buffer_destroy(self.ptr)
+            self.ptr = None
 
 
 def all_vs_all(sets):

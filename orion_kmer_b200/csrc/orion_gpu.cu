@@ -523,7 +523,7 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
         TRY(set_smem(kern, sizeof(OkScatterSmem)));
         LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_off, n_rec, n_tiles, tpw, c->k,
                pl.cfg, two ? pl.cursor1 : pl.cursor, two ? pl.end1 : pl.cap_end, two ? c->d_buf1 : c->d_buf2,
-               (OkPartSpill{c->spill, c->d_stats}), &c->d_stats->windows);
+               (OkPartSpill{c->spill, c->d_stats}), &c->d_stats->windows, OkPeerOut{});
     }
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
     TRY(part_finish(c, pl));
@@ -925,6 +925,90 @@ OK_EXPORT int ok_counter_route_batch_device(ok_counter* c, const uint8_t* d_base
     CU(cudaStreamSynchronize(c->s_main));
     CU(cudaGetLastError());
     cudaEventElapsedTime(&c->ms_route, c->ev_a, c->ev_b);
+    return OK_SUCCESS;
+}
+
+// ---- fused multi-GPU routing: the owner multisplit writes straight into the owners' receive buffers ----
+OK_EXPORT int ok_peer_buffer_create(uint64_t bytes, void** d_ptr, uint8_t handle[64]) {
+    if (!d_ptr || !handle) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_peer_buffer_create: NULL argument");
+    TRY(ensure_init());
+    CU(cudaMalloc(d_ptr, bytes ? bytes : 8));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, *d_ptr));
+    memcpy(handle, &h, 64);
+    return OK_SUCCESS;
+}
+OK_EXPORT int ok_peer_buffer_open(const uint8_t handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_peer_buffer_open: NULL argument");
+    TRY(ensure_init());
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return OK_SUCCESS;
+}
+OK_EXPORT int ok_peer_buffer_close(void* d_ptr) { if (d_ptr) CU(cudaIpcCloseMemHandle(d_ptr)); return OK_SUCCESS; }
+OK_EXPORT int ok_peer_buffer_destroy(void* d_ptr) { if (d_ptr) CU(cudaFree(d_ptr)); return OK_SUCCESS; }
+
+// pass 0 of the routing: how many k-mers of this batch each rank owns (out_counts: n_ranks host entries)
+OK_EXPORT int ok_counter_route_count_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                                            const uint64_t* d_rec_offsets, uint64_t n_records, int n_ranks,
+                                            uint64_t* out_counts) {
+    if (!c || !out_counts) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_route_count_device: NULL argument");
+    if (n_ranks != 1 && n_ranks != 2 && n_ranks != 4 && n_ranks != 8)
+        return set_err(OK_ERR_INVALID_ARGUMENT, "n_ranks must be 1, 2, 4 or 8 (got %d)", n_ranks);
+    for (int r = 0; r < n_ranks; ++r) out_counts[r] = 0;
+    if (n_bases == 0 || n_records == 0) return OK_SUCCESS;
+    if ((uintptr_t)d_bases & 15u) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
+    unsigned long long* cur = c->d_stats->route_counts;
+    CU(cudaEventRecord(c->ev_a, c->s_main));
+    CU(cudaMemsetAsync(cur, 0, 8 * sizeof(unsigned long long), c->s_main));
+    launch_route_g<0>(n_ranks, d_bases, n_bases, d_rec_offsets, n_records, c->k, c->norm_mode, cur, nullptr, c->s_main);
+    unsigned long long h[8] = {0};
+    CU(cudaMemcpyAsync(h, cur, sizeof h, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaEventRecord(c->ev_b, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&c->ms_route, c->ev_a, c->ev_b);
+    for (int r = 0; r < n_ranks; ++r) out_counts[r] = h[r];
+    return OK_SUCCESS;
+}
+
+// pass 1: extract + multisplit by owner; rank r's k-mers are written, in runs, to d_dst[r][0 .. counts[r])
+// (d_dst[r] = the slice of rank r's receive buffer reserved for this sender: peer memory over NVLink)
+OK_EXPORT int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                                              const uint64_t* d_rec_offsets, uint64_t n_records, int n_ranks,
+                                              uint64_t* const* d_dst, const uint64_t* counts) {
+    if (!c || !d_dst || !counts) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_route_scatter_device: NULL argument");
+    if (n_ranks != 1 && n_ranks != 2 && n_ranks != 4 && n_ranks != 8)
+        return set_err(OK_ERR_INVALID_ARGUMENT, "n_ranks must be 1, 2, 4 or 8 (got %d)", n_ranks);
+    if (n_bases == 0 || n_records == 0) return OK_SUCCESS;
+    if ((uintptr_t)d_bases & 15u) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
+    OkPartCfg cfg{};
+    cfg.key_shift = 64 - 2 * c->k; cfg.shard_log2 = 0; cfg.b2 = 0; cfg.b1 = 0;
+    for (int g = n_ranks; g > 1; g >>= 1) ++cfg.b1;
+    OkPeerOut po{};
+    unsigned long long zero[8] = {0}, ends[8] = {0};
+    for (int r = 0; r < n_ranks; ++r) { po.p[r] = (unsigned long long*)d_dst[r]; ends[r] = counts[r]; }
+    TRY(dev_reserve(&c->d_meta, &c->cap_meta, 32));
+    unsigned long long *d_cur = c->d_meta, *d_end = c->d_meta + 8;
+    CU(cudaEventRecord(c->ev_a, c->s_main));
+    CU(cudaMemcpyAsync(d_cur, zero, sizeof zero, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(d_end, ends, sizeof ends, cudaMemcpyHostToDevice, c->s_main));
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;
+    const uint64_t tpw = std::max<uint64_t>(1, (n_tiles + max_warps - 1) / max_warps);
+    const unsigned blocks = (unsigned)((n_tiles + 8 * tpw - 1) / (8 * tpw));
+    auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true, true> : k_part_scatter_bases<false, true>;
+    TRY(set_smem(kern, sizeof(OkScatterSmem)));
+    LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, n_tiles, tpw, c->k,
+           cfg, d_cur, (const unsigned long long*)d_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
+           c->d_stats->route_counts, po);
+    CU(cudaEventRecord(c->ev_b, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->ms_route += ms;
     return OK_SUCCESS;
 }
 

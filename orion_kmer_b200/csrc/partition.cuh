@@ -49,6 +49,10 @@ __device__ __forceinline__ unsigned ok_part_bin(uint64_t key, const OkPartCfg& c
 
 struct OkPartSpill { OkSpill sp; OkDevStats* st; };
 
+// multi-GPU routing: bin b of the scatter is owner rank b and its keys go to that rank's
+// receive buffer -- peer memory mapped over NVLink (CUDA IPC), or local memory for b == self
+struct OkPeerOut { unsigned long long* p[8]; };
+
 // ----------------------------------------------------------------------------- sampling --
 // every `stride`-th warp-tile; hist[sub] += 1 per k-mer (global RED; the sample is small)
 template <bool MAP_U>
@@ -98,12 +102,13 @@ __device__ __forceinline__ void ok_part_put(unsigned long long key, unsigned lon
 // One multisplit round of the CTA (all 256 threads call it together): thread-held keys
 // key[0..15] (bit q of vmask says key[q] exists) -> out, grouped by bin.  sm.hist must be zero on
 // entry and is zero again on exit.
-template <int LEVEL>
+template <int LEVEL, bool PEER = false>
 __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_t (&key)[16], unsigned vmask,
                                                 const OkPartCfg& cfg, unsigned bins_log2,
                                                 unsigned long long* __restrict__ cursors,
                                                 const unsigned long long* __restrict__ bin_end,
-                                                unsigned long long* __restrict__ out, const OkPartSpill& ps) {
+                                                unsigned long long* __restrict__ out, const OkPartSpill& ps,
+                                                const OkPeerOut* peer = nullptr) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned cap_log2 = 13u - bins_log2, cap = 1u << cap_log2, n_bins = 1u << bins_log2;
 #pragma unroll
@@ -112,7 +117,7 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
             const unsigned b = ok_part_bin<LEVEL>(key[q], cfg);
             const unsigned r = atomicAdd(&sm.hist[b], 1u);
             if (r < cap) sm.stage[(b << cap_log2) + r] = key[q];
-            else ok_part_put(key[q], atomicAdd(&cursors[b], 1ull), bin_end[b], out, ps);
+            else ok_part_put(key[q], atomicAdd(&cursors[b], 1ull), bin_end[b], PEER ? peer->p[b] : out, ps);
         }
     __syncthreads();
     // copy out.  Warp w owns staging slots [w*1024, (w+1)*1024) = a contiguous range of bins.
@@ -140,7 +145,7 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
         const unsigned t_end = (wb0 + bins_per_warp) << cap_log2;
         for (unsigned t = (wb0 << cap_log2) + lane; t < t_end; t += 32) {
             const unsigned b = t >> cap_log2, r = t & (cap - 1u);
-            if (r < sm.hist[b]) out[(unsigned long long)sm.gbase[b] + r] = sm.stage[t];
+            if (r < sm.hist[b]) (PEER ? peer->p[b] : out)[(unsigned long long)sm.gbase[b] + r] = sm.stage[t];
         }
     }
     __syncwarp();
@@ -151,12 +156,13 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
 // ------------------------------------------------------------------ level 1: from the bases --
 // The 8 warps of a CTA walk their own runs of tiles in lock step; each warp-tile is split in
 // two rounds of 16 window ends per lane, so a round holds <= 4096 k-mers per CTA.
-template <bool MAP_U>
+template <bool MAP_U, bool PEER = false>
 __global__ void __launch_bounds__(256, 3)
 k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
                      uint64_t n_rec, uint64_t n_tiles, uint64_t tiles_per_warp, unsigned k, OkPartCfg cfg,
                      unsigned long long* __restrict__ cursors, const unsigned long long* __restrict__ bin_end,
-                     unsigned long long* __restrict__ out, OkPartSpill ps, unsigned long long* __restrict__ n_keys) {
+                     unsigned long long* __restrict__ out, OkPartSpill ps, unsigned long long* __restrict__ n_keys,
+                     const __grid_constant__ OkPeerOut peer_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -177,7 +183,7 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
                 for (int q = 0; q < 16; ++q) key[q] = roll.step(16 * half + q);
                 // window end j = 16*half + q lives in okmask bit 31-j; make bit q mean key[q]
                 const unsigned vm = __brev(okmask) >> (16 * half) & 0xFFFFu;
-                ok_multisplit16<1>(sm, key, vm, cfg, cfg.b1, cursors, bin_end, out, ps);
+                ok_multisplit16<1, PEER>(sm, key, vm, cfg, cfg.b1, cursors, bin_end, out, ps, &peer_out);
             }
         });
     my_keys = ok_warp_sum(my_keys);

@@ -30,17 +30,54 @@ def exchange(dist, torch, send, send_counts, group=None):
 
 
 class ShardedCounter:
-    """KmerCounter sharded over the ranks of a process group."""
+    """KmerCounter sharded over the ranks of a process group.
 
-    def __init__(self, ok, torch, dist, k, norm_mode=0):
+    fused=True (default): the routing kernel writes each owner's k-mers straight into that owner's
+    receive buffer (CUDA-IPC peer memory over NVLink); the only collectives left are a world x world
+    count matrix and a barrier.  fused=False: bucket locally, NCCL all_to_all_single, then count."""
+
+    def __init__(self, ok, torch, dist, k, norm_mode=0, fused=True):
         self.ok, self.torch, self.dist = ok, torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.counter = ok.KmerCounter(k, norm_mode)
         self.counter.set_shard(self.rank, self.world)
+        self.fused = fused
         self.d_send = None
+        self.recv, self.recv_cap, self.peer_ptrs = None, 0, None
         self.t = {}
 
+    # ---- receive buffer shared with the peers (collective) ----
+    def _ensure_recv(self, need_keys):
+        torch, dist = self.torch, self.dist
+        need = torch.tensor([need_keys], device="cuda", dtype=torch.int64)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX)
+        need = int(need.item())
+        if need <= self.recv_cap:
+            return
+        self._release_recv()
+        cap = int(need * 1.15) + 1024
+        self.recv = self.ok.PeerBuffer(cap * 8)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.recv.handle_bytes())
+        self.peer_ptrs = [self.recv.ptr if r == self.rank else self.ok.PeerBuffer.open(handles[r])
+                          for r in range(self.world)]
+        self.recv_cap = cap
+
+    def _release_recv(self):
+        if self.recv is None:
+            return
+        self.torch.cuda.synchronize()
+        self.dist.barrier()
+        for r, p in enumerate(self.peer_ptrs):
+            if r != self.rank:
+                self.ok.PeerBuffer.close_peer(p)
+        self.dist.barrier()
+        self.recv.destroy()
+        self.recv, self.recv_cap, self.peer_ptrs = None, 0, None
+
     def count_batch_device(self, d_bases, n_bases, d_off, n_reads):
+        if self.fused:
+            return self._count_fused(d_bases, n_bases, d_off, n_reads)
         torch = self.torch
         if self.d_send is None or self.d_send.numel() < n_bases:
             self.d_send = torch.empty(n_bases, dtype=torch.int64, device=d_bases.device)
@@ -58,10 +95,37 @@ class ShardedCounter:
                   "recv_kmers": int(recv.numel())}
         del recv
 
+    def _count_fused(self, d_bases, n_bases, d_off, n_reads):
+        torch, dist = self.torch, self.dist
+        t0 = time.perf_counter()
+        counts = self.counter.route_count_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads, self.world)
+        # world x world matrix M[src][dst]
+        mine = torch.from_numpy(counts.astype(np.int64)).cuda()
+        M = torch.empty(self.world * self.world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(M, mine)
+        M = M.cpu().numpy().reshape(self.world, self.world)
+        recv_total = M.sum(axis=0)
+        self._ensure_recv(int(recv_total[self.rank]))
+        t1 = time.perf_counter()
+        # my slice in rank d's buffer starts after the slices of the lower-ranked senders
+        offs = np.concatenate([np.zeros((1, self.world), np.int64), np.cumsum(M, axis=0)[:-1]])[self.rank]
+        dst = [self.peer_ptrs[d] + 8 * int(offs[d]) for d in range(self.world)]
+        self.counter.route_scatter_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads, dst, counts)
+        t2 = time.perf_counter()
+        dist.barrier()                       # every sender has finished writing into my buffer
+        t3 = time.perf_counter()
+        self.counter.add_kmers_device(self.recv.ptr, int(recv_total[self.rank]))
+        t4 = time.perf_counter()
+        self.t = {"route_ms": (t1 - t0) * 1e3 + (t2 - t1) * 1e3, "route_count_ms": (t1 - t0) * 1e3,
+                  "route_scatter_ms": (t2 - t1) * 1e3, "exchange_ms": (t3 - t2) * 1e3, "count_ms": (t4 - t3) * 1e3,
+                  "sent_kmers": int(counts.sum()), "sent_off_rank": int(counts.sum() - counts[self.rank]),
+                  "recv_kmers": int(recv_total[self.rank])}
+
     def clear(self):
         self.counter.clear()
 
     def close(self):
+        self._release_recv()
         self.counter.close()
 
 
@@ -77,7 +141,7 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
     h_off = torch.from_numpy(off.view(np.int64))
     d_bases = h_bases.cuda()
     d_off = h_off.cuda()
-    sc = ShardedCounter(ok, torch, dist, K)
+    sc = ShardedCounter(ok, torch, dist, K, fused=os.environ.get("ORION_FUSED", "1") != "0")
 
     def step_device():
         sc.clear()
@@ -142,9 +206,12 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
                          "achieved": alg_step / dt / 1e9, "peak": peak * world, "unit": "GB/s",
                          "frac": alg_step / dt / 1e9 / (peak * world), "peak_source": peak_src + " x n_gpus",
                          "traffic": None,
-                         "nvlink": {"bytes_sent_per_rank": nvlink_bytes, "exchange_ms": mean["exchange_ms"],
-                                    "achieved_GBs_per_rank": nvlink_bytes / (mean["exchange_ms"] / 1e3) / 1e9,
-                                    "peak_GBs": 770.0, "peak_source": "B200_PROFILING.md peer copy per direction"}},
+                         "nvlink": {"bytes_sent_per_rank": nvlink_bytes,
+                                    "transfer_ms": mean.get("route_scatter_ms", mean["exchange_ms"]),
+                                    "achieved_GBs_per_rank": nvlink_bytes / (mean.get("route_scatter_ms", mean["exchange_ms"]) / 1e3) / 1e9,
+                                    "peak_GBs": 770.0, "peak_source": "B200_PROFILING.md peer copy per direction",
+                                    "mode": "fused into k_part_scatter_bases<PEER> (writes into peer memory)" if sc.fused
+                                            else "NCCL all_to_all_single"}},
             "phases_ms": mean,
             "table": {"windows": int(windows), "distinct": int(distinct), "rank0_distinct": int(n_out),
                       "spilled": int(st["n_spilled"])},
