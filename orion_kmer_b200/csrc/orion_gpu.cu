@@ -102,11 +102,32 @@ constexpr double LF_MAX = 0.7;       // occupancy at which the table is rebuilt 
 constexpr unsigned MAX_PROBE = 2048; // displacement bound L (also the tail padding)
 constexpr uint64_t MIN_SLOTS = 1ull << 16;
 constexpr uint64_t SPILL_CAP = 1ull << 22;
-constexpr uint64_t COPY_CHUNK = 64ull << 20;  // bytes per H2D piece of the ingest pipeline
+constexpr uint64_t COPY_CHUNK = 128ull << 20;  // bytes per H2D piece of the ingest pipeline (a multiple of the tile size)
 
 }  // namespace
 
 // =============================================================================== counter ==
+enum { RUN_NONE = 0, RUN_SPARSE = 1, RUN_DENSE = 2 };
+
+// plan of one partitioned batch: bin widths and the per-batch device arrays (inside d_meta)
+struct PartPlan {
+    OkPartCfg cfg{};
+    unsigned n_sub = 1, n_bin1 = 1, stride = 1;
+    uint64_t cap_bound = 0, max_items = 0;
+    unsigned *hist = nullptr, *beg = nullptr, *cursor = nullptr, *cap_end = nullptr, *deferred = nullptr;
+    unsigned *beg1 = nullptr, *cursor1 = nullptr, *end1 = nullptr;
+    unsigned *item_off = nullptr, *item_n = nullptr, *item_bin = nullptr;
+    unsigned long long* scan = nullptr;      // exclusive scan of n_distinct, n_sub + 1 entries
+    OkPartScalars* scal = nullptr;
+    unsigned n_slices = 0, slice_step = 0;   // result slices: sub-partitions [i*step, (i+1)*step)
+};
+
+struct PartHost {                            // page-locked mirror of the batch's scalars
+    OkPartScalars scal;
+    unsigned long long total;
+    unsigned long long slice_base[64];       // output offset of every result slice, then the total
+};
+
 struct ok_counter {
     unsigned k = 0;
     int norm_mode = 0;
@@ -129,19 +150,18 @@ struct ok_counter {
     unsigned long long* d_tiles = nullptr; uint64_t cap_tiles = 0;   // [n_tiles] + total
     unsigned long long* d_out_keys = nullptr; uint64_t cap_out_keys = 0;
     unsigned long long* d_out_counts = nullptr; uint64_t cap_out_counts = 0;
-    // partitioned (one-shot) path: its result is a sorted run instead of a table
+    // partitioned (one-shot) path: its result is a sorted run instead of a table --
+    // RUN_SPARSE: sorted sub-partition runs in d_buf2 (keys) / d_buf1 (counts); RUN_DENSE: d_run_*
     int path_mode = 0;                 // 0 auto, 1 table only, 2 partitioned whenever the counter is empty
-    bool run_valid = false;
+    int run_state = RUN_NONE;
+    PartPlan pl;
+    PartHost* h_part = nullptr;
     unsigned long long* d_run_keys = nullptr; uint64_t cap_run_keys = 0;
     unsigned long long* d_run_counts = nullptr; uint64_t cap_run_counts = 0;
-    uint64_t n_run = 0;
+    uint64_t n_run = 0, n_deferred = 0;
     unsigned long long* d_buf1 = nullptr; uint64_t cap_buf1 = 0;
     unsigned long long* d_buf2 = nullptr; uint64_t cap_buf2 = 0;
-    unsigned long long* d_meta = nullptr; uint64_t cap_meta = 0;     // beg | cursor | cap_end | scan (per sub-partition) + level-1 arrays
-    unsigned* d_hist = nullptr; uint64_t cap_hist = 0;               // sample histogram / n_distinct
-    unsigned* d_hist2 = nullptr; uint64_t cap_hist2 = 0;             // retry list of the count kernel
-    uint64_t n_retry = 0;
-    unsigned long long* d_items = nullptr; uint64_t cap_items = 0;   // level-2 work items
+    unsigned* d_meta = nullptr; uint64_t cap_meta = 0;               // per-batch arrays of the plan (32-bit words)
     float ms_sample = 0, ms_scatter1 = 0, ms_scatter2 = 0, ms_count = 0, ms_compact = 0;
     cudaEvent_t ev_p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -332,58 +352,14 @@ namespace {
 
 constexpr uint64_t PART_MIN_BASES = 1ull << 20;   // below this the table path is as fast
 constexpr unsigned PART_TARGET = 4096;            // keys per sub-partition if every key were distinct
-constexpr unsigned PART_MAX_BITS = 18;            // 8 bits at level 1 + up to 10 at level 2
-
-struct PartPlan {
-    OkPartCfg cfg{};
-    unsigned n_sub = 1, n_bin1 = 1;
-    uint64_t total_cap = 0, est_keys = 0;
-    // device arrays inside c->d_meta
-    unsigned long long *beg = nullptr, *cursor = nullptr, *cap_end = nullptr, *scan = nullptr;
-    unsigned long long *cursor1 = nullptr, *end1 = nullptr;
-    std::vector<unsigned long long> h_beg, h_end, h_beg1, h_end1;
-};
+constexpr unsigned PART_MAX_BITS = 18;            // up to 9 bits at level 1 + up to 10 at level 2
+constexpr unsigned RESULT_SLICES = 16;            // the result pipeline compacts and ships the table in slices
 
 bool part_eligible(const ok_counter* c, uint64_t n_units) {
     if (c->path_mode == 1) return false;
-    if (c->run_valid || c->occupied) return false;
-    if (n_units >= (1ull << 31)) return false;   // scatter cursors are staged as 32-bit offsets
+    if (c->run_state != RUN_NONE || c->occupied) return false;
+    if (n_units >= (1ull << 31)) return false;   // buffers are indexed with 32-bit offsets
     return c->path_mode == 2 || n_units >= PART_MIN_BASES;
-}
-
-// sizes every sub-partition from the sample histogram and lays the buffers out
-int part_plan(ok_counter* c, uint64_t n_units, uint64_t sample_stride, PartPlan& pl) {
-    const unsigned n_sub = pl.n_sub;
-    std::vector<unsigned> hist(n_sub);
-    CU(cudaMemcpyAsync(hist.data(), c->d_hist, n_sub * sizeof(unsigned), cudaMemcpyDeviceToHost, c->s_main));
-    CU(cudaStreamSynchronize(c->s_main));
-    pl.h_beg.resize(n_sub); pl.h_end.resize(n_sub);
-    uint64_t run = 0;
-    for (unsigned p = 0; p < n_sub; ++p) {
-        uint64_t est = (uint64_t)hist[p] * sample_stride;
-        pl.est_keys += est;
-        uint64_t cap = est;
-        if (sample_stride > 1) cap += (uint64_t)(6.0 * std::sqrt((double)est * (double)sample_stride)) + 128;
-        if (cap > n_units) cap = n_units;
-        pl.h_beg[p] = run; run += cap; pl.h_end[p] = run;
-    }
-    pl.total_cap = run;
-    const unsigned b2n = 1u << pl.cfg.b2;
-    pl.h_beg1.resize(pl.n_bin1); pl.h_end1.resize(pl.n_bin1);
-    for (unsigned b = 0; b < pl.n_bin1; ++b) { pl.h_beg1[b] = pl.h_beg[(uint64_t)b * b2n]; pl.h_end1[b] = pl.h_end[(uint64_t)(b + 1) * b2n - 1]; }
-    // device copies: beg | cursor | cap_end | scan(n_sub+1) | cursor1 | end1
-    const uint64_t need = 4ull * n_sub + 1 + 2ull * pl.n_bin1;
-    TRY(dev_reserve(&c->d_meta, &c->cap_meta, need));
-    pl.beg = c->d_meta; pl.cursor = pl.beg + n_sub; pl.cap_end = pl.cursor + n_sub; pl.scan = pl.cap_end + n_sub;
-    pl.cursor1 = pl.scan + n_sub + 1; pl.end1 = pl.cursor1 + pl.n_bin1;
-    CU(cudaMemcpyAsync(pl.beg, pl.h_beg.data(), n_sub * 8, cudaMemcpyHostToDevice, c->s_main));
-    CU(cudaMemcpyAsync(pl.cursor, pl.h_beg.data(), n_sub * 8, cudaMemcpyHostToDevice, c->s_main));
-    CU(cudaMemcpyAsync(pl.cap_end, pl.h_end.data(), n_sub * 8, cudaMemcpyHostToDevice, c->s_main));
-    CU(cudaMemcpyAsync(pl.cursor1, pl.h_beg1.data(), pl.n_bin1 * 8, cudaMemcpyHostToDevice, c->s_main));
-    CU(cudaMemcpyAsync(pl.end1, pl.h_end1.data(), pl.n_bin1 * 8, cudaMemcpyHostToDevice, c->s_main));
-    TRY(dev_reserve(&c->d_buf2, &c->cap_buf2, pl.total_cap + 1));
-    TRY(dev_reserve(&c->d_buf1, &c->cap_buf1, pl.total_cap + 1));   // level-1 output, later the counts of the runs
-    return OK_SUCCESS;
 }
 
 void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl) {
@@ -409,75 +385,95 @@ template <class K> int set_smem(K kern, size_t bytes) {
     return OK_SUCCESS;
 }
 
-// level 2 + count + compact, shared by the two entry points.  `lvl1` = keys already scattered
-// into level-1 bins in d_buf1 (b2 > 0) or straight into sub-partitions in d_buf2 (b2 == 0).
-int part_finish(ok_counter* c, PartPlan& pl) {
-    const OkPartSpill ps{c->spill, c->d_stats};
-    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
-    if (pl.cfg.b2 > 0) {
-        // level-1 fills -> work items of <= 8192 keys
-        std::vector<unsigned long long> cur1(pl.n_bin1);
-        CU(cudaMemcpyAsync(cur1.data(), pl.cursor1, pl.n_bin1 * 8, cudaMemcpyDeviceToHost, c->s_main));
-        CU(cudaStreamSynchronize(c->s_main));
-        std::vector<unsigned long long> item_off; std::vector<unsigned> item_n, item_bin;
-        for (unsigned b = 0; b < pl.n_bin1; ++b) {
-            const uint64_t e = std::min<uint64_t>(cur1[b], pl.h_end1[b]);
-            for (uint64_t o = pl.h_beg1[b]; o < e; o += OK_PART_TILE) {
-                item_off.push_back(o); item_n.push_back((unsigned)std::min<uint64_t>(OK_PART_TILE, e - o)); item_bin.push_back(b);
-            }
-        }
-        const uint64_t ni = item_off.size();
-        if (ni) {
-            TRY(dev_reserve(&c->d_items, &c->cap_items, 2 * ni + 2));
-            unsigned* d_n = (unsigned*)(c->d_items + ni);
-            unsigned* d_b = d_n + ni;
-            CU(cudaMemcpyAsync(c->d_items, item_off.data(), ni * 8, cudaMemcpyHostToDevice, c->s_main));
-            CU(cudaMemcpyAsync(d_n, item_n.data(), ni * 4, cudaMemcpyHostToDevice, c->s_main));
-            CU(cudaMemcpyAsync(d_b, item_bin.data(), ni * 4, cudaMemcpyHostToDevice, c->s_main));
-            TRY(set_smem(k_part_scatter_keys<2>, sizeof(OkScatterSmem)));
-            const unsigned grid = (unsigned)std::min<uint64_t>(ni, (uint64_t)grid_sm * 2);
-            LAUNCH(k_part_scatter_keys<2>, grid, 256, sizeof(OkScatterSmem), c->s_main, c->d_buf1, c->d_items, d_n, d_b,
-                   (unsigned)ni, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps);
-            CU(cudaStreamSynchronize(c->s_main));   // the host vectors above must outlive the copies
-        }
-    }
-    CU(cudaEventRecord(c->ev_p[3], c->s_main));
-    // count every sub-partition in shared memory; sorted runs land in place.  (Launch-sized
-    // smaller tables with a retry launch were tried and measured slower -- see DESIGN.md.)
-    const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
-    TRY(set_smem(k_part_count, ct_smem));
-    unsigned* d_nd = c->d_hist;   // the sample histogram is no longer needed
-    LAUNCH(k_part_count, std::min<unsigned>(pl.n_sub, grid_sm * 2), OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg,
-           pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, ps);
-    CU(cudaEventRecord(c->ev_p[4], c->s_main));
-    LAUNCH(k_widen_u32, grid_for(pl.n_sub), 256, 0, c->s_main, d_nd, pl.scan, (uint64_t)pl.n_sub);
-    LAUNCH(k_scan_tiles, 1, 1024, 0, c->s_main, pl.scan, (uint64_t)pl.n_sub, pl.scan + pl.n_sub);
-    unsigned long long total = 0;
-    CU(cudaMemcpyAsync(&total, pl.scan + pl.n_sub, 8, cudaMemcpyDeviceToHost, c->s_main));
-    CU(cudaStreamSynchronize(c->s_main));
-    TRY(dev_reserve(&c->d_run_keys, &c->cap_run_keys, total));
-    TRY(dev_reserve(&c->d_run_counts, &c->cap_run_counts, total));
-    if (total)
-        LAUNCH(k_part_compact, std::min<unsigned>(pl.n_sub, grid_sm * 8), 256, 0, c->s_main, c->d_buf2, c->d_buf1, pl.beg, d_nd,
-               pl.scan, pl.n_sub, c->d_run_keys, c->d_run_counts);
-    CU(cudaEventRecord(c->ev_p[5], c->s_main));
-    TRY(read_stats(c));
-    CU(cudaGetLastError());
-    cudaEventElapsedTime(&c->ms_sample, c->ev_p[0], c->ev_p[1]);
-    cudaEventElapsedTime(&c->ms_scatter1, c->ev_p[1], c->ev_p[2]);
-    cudaEventElapsedTime(&c->ms_scatter2, c->ev_p[2], c->ev_p[3]);
-    cudaEventElapsedTime(&c->ms_count, c->ev_p[3], c->ev_p[4]);
-    cudaEventElapsedTime(&c->ms_compact, c->ev_p[4], c->ev_p[5]);
-    c->ms_insert = c->ms_sample + c->ms_scatter1 + c->ms_scatter2 + c->ms_count;
-    c->ms_readout = c->ms_compact;
-    c->n_run = total; c->run_valid = true;
-    c->occupied = total;
+// Upper bound of the sum of the sub-partition capacities k_part_plan will hand out, so that the
+// buffers can be allocated before the sample has been looked at (no host round trip):
+//   sum(est_p) <= S (every sampled unit stands for `stride` units),
+//   sum(6 sqrt(est_p stride)) <= 6 sqrt(stride) sqrt(n_sub S)   (Cauchy-Schwarz).
+uint64_t part_cap_bound(uint64_t n_units, unsigned n_sub, unsigned stride, uint64_t unit_chunk) {
+    const double S = (double)n_units + (double)unit_chunk * (stride + 1.0);
+    double b = S;
+    if (stride > 1) b += 6.0 * std::sqrt((double)stride) * std::sqrt((double)n_sub * S) + 129.0 * n_sub;
+    return (uint64_t)b + 2ull * n_sub + 64;
+}
+
+// carve the per-batch device arrays out of c->d_meta and make sure the key buffers are large enough
+int part_layout(ok_counter* c, uint64_t n_units, uint64_t unit_chunk, uint64_t flat_keys, PartPlan& pl) {
+    pl.cap_bound = part_cap_bound(n_units, pl.n_sub, pl.stride, unit_chunk);
+    if (pl.cap_bound >= (1ull << 32)) return set_err(OK_ERR_INTERNAL, "partitioned path: batch too large for 32-bit offsets");
+    pl.max_items = std::max<uint64_t>(pl.cap_bound / OK_PART_TILE + pl.n_bin1 + 1, flat_keys / OK_PART_TILE + 2);
+    const uint64_t n_sub = pl.n_sub;
+    uint64_t words = 0;                                   // 32-bit words
+    auto take = [&](uint64_t n) { uint64_t o = words; words += (n + 3) & ~3ull; return o; };
+    const uint64_t o_scan = take(2 * (n_sub + 2)), o_scal = take(sizeof(OkPartScalars) / 4), o_hist = take(n_sub), o_beg = take(n_sub),
+                   o_cur = take(n_sub), o_end = take(n_sub), o_def = take(n_sub), o_b1 = take(OK_PART_MAXBINS),
+                   o_c1 = take(OK_PART_MAXBINS), o_e1 = take(OK_PART_MAXBINS), o_io = take(pl.max_items),
+                   o_in = take(pl.max_items), o_ib = take(pl.max_items);
+    TRY(dev_reserve(&c->d_meta, &c->cap_meta, words));
+    unsigned* m = c->d_meta;
+    pl.scan = (unsigned long long*)(m + o_scan); pl.scal = (OkPartScalars*)(m + o_scal);
+    pl.hist = m + o_hist; pl.beg = m + o_beg; pl.cursor = m + o_cur; pl.cap_end = m + o_end; pl.deferred = m + o_def;
+    pl.beg1 = m + o_b1; pl.cursor1 = m + o_c1; pl.end1 = m + o_e1;
+    pl.item_off = m + o_io; pl.item_n = m + o_in; pl.item_bin = m + o_ib;
+    TRY(dev_reserve(&c->d_buf2, &c->cap_buf2, pl.cap_bound + 16));
+    TRY(dev_reserve(&c->d_buf1, &c->cap_buf1, pl.cap_bound + 16));   // level-1 output, later the counts of the runs
     return OK_SUCCESS;
 }
 
 int run_to_table(ok_counter* c);
+int run_make_dense(ok_counter* c);
 
 constexpr int PART_RETRY = 100;   // internal: the one-shot path gave up, count the batch through the table instead
+
+// level 2 + count + scan, shared by the two entry points.  The keys are already scattered into
+// level-1 bins in d_buf1 (b2 > 0) or straight into sub-partitions in d_buf2 (b2 == 0).  Leaves
+// the result as sorted sub-partition runs (RUN_SPARSE); compaction happens when it is asked for.
+int part_finish(ok_counter* c, PartPlan& pl) {
+    const OkPartSpill ps{c->spill, c->d_stats};
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    if (pl.cfg.b2 > 0) {
+        LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
+        TRY(set_smem(k_part_scatter_keys<2>, sizeof(OkScatterKeysSmem)));
+        LAUNCH(k_part_scatter_keys<2>, grid_sm * 2, 256, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
+               pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps);
+    }
+    CU(cudaEventRecord(c->ev_p[3], c->s_main));
+    // count every sub-partition in shared memory; sorted runs land in place, counts in d_buf1
+    TRY(set_smem(k_part_count, sizeof(OkCount2Smem)));
+    unsigned* d_nd = pl.hist;   // the sample histogram is no longer needed (k_part_plan zeroed it)
+    LAUNCH(k_part_count, std::min<unsigned>(pl.n_sub, grid_sm * 2), OK_C2_THREADS, sizeof(OkCount2Smem), c->s_main, c->d_buf2,
+           pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, pl.deferred, pl.scal);
+    const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
+    TRY(set_smem(k_part_count_generic, ct_smem));
+    LAUNCH(k_part_count_generic, grid_sm, OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg, pl.cursor, pl.cap_end,
+           pl.deferred, pl.scal, pl.cfg, c->d_buf1, d_nd, ps);
+    CU(cudaEventRecord(c->ev_p[4], c->s_main));
+    LAUNCH(k_widen_u32, grid_for(pl.n_sub), 256, 0, c->s_main, d_nd, pl.scan, (uint64_t)pl.n_sub);
+    LAUNCH(k_scan_tiles, 1, 1024, 0, c->s_main, pl.scan, (uint64_t)pl.n_sub, pl.scan + pl.n_sub);
+    CU(cudaEventRecord(c->ev_p[5], c->s_main));
+    // the one host round trip of the batch: totals, slice boundaries of the result, statistics
+    const unsigned step = std::max<unsigned>(1, pl.n_sub / RESULT_SLICES);
+    pl.n_slices = (pl.n_sub + step - 1) / step;
+    CU(cudaMemcpy2DAsync(c->h_part->slice_base, 8, pl.scan, (size_t)step * 8, 8, pl.n_slices, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaMemcpyAsync(&c->h_part->total, pl.scan + pl.n_sub, 8, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaMemcpyAsync(&c->h_part->scal, pl.scal, sizeof(OkPartScalars), cudaMemcpyDeviceToHost, c->s_main));
+    TRY(read_stats(c));   // synchronises the stream
+    CU(cudaGetLastError());
+    c->h_part->slice_base[pl.n_slices] = c->h_part->total;
+    pl.slice_step = step;
+    cudaEventElapsedTime(&c->ms_sample, c->ev_p[0], c->ev_p[1]);
+    cudaEventElapsedTime(&c->ms_scatter1, c->ev_p[1], c->ev_p[2]);
+    cudaEventElapsedTime(&c->ms_scatter2, c->ev_p[2], c->ev_p[3]);
+    cudaEventElapsedTime(&c->ms_count, c->ev_p[3], c->ev_p[4]);
+    float ms_scan = 0; cudaEventElapsedTime(&ms_scan, c->ev_p[4], c->ev_p[5]);
+    c->ms_count += ms_scan;
+    c->ms_compact = 0;
+    c->ms_insert = c->ms_sample + c->ms_scatter1 + c->ms_scatter2 + c->ms_count;
+    c->ms_readout = 0;
+    c->n_run = c->h_part->total; c->run_state = RUN_SPARSE;
+    c->n_deferred = c->h_part->scal.n_deferred;
+    c->occupied = c->n_run;
+    return OK_SUCCESS;
+}
 
 // whatever the displacement / capacity bounds spilled is exact but unsorted: fold the run and
 // the spill list into the general table.  If even the spill list overflowed, nothing of this
@@ -485,7 +481,7 @@ constexpr int PART_RETRY = 100;   // internal: the one-shot path gave up, count 
 int part_absorb_spills(ok_counter* c, uint64_t windows_before) {
     if (c->h_stats->spill_n == 0) return OK_SUCCESS;
     if (c->h_stats->spill_n > c->spill.cap) {
-        c->run_valid = false; c->n_run = 0; c->occupied = 0; c->windows = windows_before;
+        c->run_state = RUN_NONE; c->n_run = 0; c->occupied = 0; c->windows = windows_before;
         CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
         CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
         CU(cudaStreamSynchronize(c->s_main));
@@ -496,34 +492,53 @@ int part_absorb_spills(ok_counter* c, uint64_t windows_before) {
     return run_to_table(c);
 }
 
-int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec) {
-    PartPlan pl;
+// pieces of a batch that is still landing in device memory: piece i covers bases
+// [i*piece_bytes, (i+1)*piece_bytes) and is complete once ev[i] has fired on the copy stream
+struct PieceSchedule { uint64_t n_pieces, piece_bytes; const cudaEvent_t* ev; };
+
+// d_bases: the batch in device memory (possibly still landing, see `pieces`); sample_src: where the
+// sampling kernel reads the bases from -- d_bases itself, or the caller's page-locked host buffer
+// (zero-copy), so that the plan exists before the first piece has arrived.
+int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec,
+                     const uint8_t* sample_src, const PieceSchedule* pieces) {
+    PartPlan& pl = c->pl; pl = PartPlan{};
     const uint64_t windows_before = c->windows;
     part_choose_bits(c, n_bases, pl);
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
-    const uint64_t stride = n_tiles > 4096 ? 16 : 1;
+    pl.stride = n_tiles > 4096 ? 16 : 1;
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
-    TRY(dev_reserve(&c->d_hist, &c->cap_hist, (uint64_t)pl.n_sub + 1));
+    TRY(part_layout(c, n_bases, OK_TILE_BASES, 0, pl));
     CU(cudaEventRecord(c->ev_p[0], c->s_main));
-    CU(cudaMemsetAsync(c->d_hist, 0, pl.n_sub * sizeof(unsigned), c->s_main));
+    CU(cudaMemsetAsync(pl.hist, 0, pl.n_sub * sizeof(unsigned), c->s_main));
     {
-        const uint64_t sampled = (n_tiles + stride - 1) / stride;
+        const uint64_t sampled = (n_tiles + pl.stride - 1) / pl.stride;
         const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((sampled + 7) / 8, (uint64_t)grid_sm * 8));
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_sample<true> : k_part_sample<false>;
-        LAUNCH(kern, blocks, 256, 0, c->s_main, d_bases, n_bases, d_off, n_rec, n_tiles, stride, c->k, pl.cfg, c->d_hist);
+        LAUNCH(kern, blocks, 256, 0, c->s_main, sample_src, n_bases, d_off, n_rec, n_tiles, (uint64_t)pl.stride, c->k, pl.cfg, pl.hist);
     }
-    TRY(part_plan(c, n_bases, stride, pl));
+    LAUNCH(k_part_plan, 1, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.cfg.b2, pl.beg, pl.cursor,
+           pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     {
-        const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;   // 3 CTAs of 8 warps per SM (75 KB smem each)
-        const uint64_t tpw = std::max<uint64_t>(1, (n_tiles + max_warps - 1) / max_warps);
-        const unsigned blocks = (unsigned)((n_tiles + 8 * tpw - 1) / (8 * tpw));
         const bool two = pl.cfg.b2 > 0;
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true> : k_part_scatter_bases<false>;
         TRY(set_smem(kern, sizeof(OkScatterSmem)));
-        LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_off, n_rec, n_tiles, tpw, c->k,
-               pl.cfg, two ? pl.cursor1 : pl.cursor, two ? pl.end1 : pl.cap_end, two ? c->d_buf1 : c->d_buf2,
-               (OkPartSpill{c->spill, c->d_stats}), &c->d_stats->windows, OkPeerOut{});
+        const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;   // 3 CTAs of 8 warps per SM (72 KB smem each)
+        const uint64_t n_launch = pieces ? pieces->n_pieces : 1;
+        for (uint64_t p = 0; p < n_launch; ++p) {
+            uint64_t t0 = 0, t1 = n_tiles, visible = n_bases;
+            if (pieces) {
+                CU(cudaStreamWaitEvent(c->s_main, pieces->ev[p], 0));
+                t0 = p * (pieces->piece_bytes / OK_TILE_BASES);
+                if (p + 1 < n_launch) { visible = (p + 1) * pieces->piece_bytes; t1 = visible / OK_TILE_BASES; }
+            }
+            if (t1 <= t0) continue;
+            const uint64_t tpw = std::max<uint64_t>(1, (t1 - t0 + max_warps - 1) / max_warps);
+            const unsigned blocks = (unsigned)((t1 - t0 + 8 * tpw - 1) / (8 * tpw));
+            LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, visible, d_off, n_rec, t0, t1, tpw, c->k,
+                   pl.cfg, two ? pl.cursor1 : pl.cursor, (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2,
+                   (OkPartSpill{c->spill, c->d_stats}), &c->d_stats->windows, OkPeerOut{});
+        }
     }
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
     TRY(part_finish(c, pl));
@@ -531,36 +546,29 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
 }
 
 int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
-    PartPlan pl;
+    PartPlan& pl = c->pl; pl = PartPlan{};
     const uint64_t windows_before = c->windows;
     part_choose_bits(c, n, pl);
     const uint64_t n_chunks = (n + 255) / 256;
-    const uint64_t stride = n_chunks > 16384 ? 16 : 1;
+    pl.stride = n_chunks > 16384 ? 16 : 1;
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
-    TRY(dev_reserve(&c->d_hist, &c->cap_hist, (uint64_t)pl.n_sub + 1));
+    TRY(part_layout(c, n, 256, n, pl));
     CU(cudaEventRecord(c->ev_p[0], c->s_main));
-    CU(cudaMemsetAsync(c->d_hist, 0, pl.n_sub * sizeof(unsigned), c->s_main));
-    LAUNCH(k_part_sample_keys, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + stride - 1) / stride, (uint64_t)grid_sm * 16)),
-           256, 0, c->s_main, (const unsigned long long*)d_keys, n, stride, pl.cfg, c->d_hist);
-    TRY(part_plan(c, n, stride, pl));
+    CU(cudaMemsetAsync(pl.hist, 0, pl.n_sub * sizeof(unsigned), c->s_main));
+    LAUNCH(k_part_sample_keys, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + pl.stride - 1) / pl.stride, (uint64_t)grid_sm * 16)),
+           256, 0, c->s_main, (const unsigned long long*)d_keys, n, (uint64_t)pl.stride, pl.cfg, pl.hist);
+    LAUNCH(k_part_plan, 1, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n, pl.cfg.b2, pl.beg, pl.cursor,
+           pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     {
-        // one level-1 scatter over the whole key array, in items of 8192 keys
-        const uint64_t ni = (n + OK_PART_TILE - 1) / OK_PART_TILE;
-        std::vector<unsigned long long> item_off(ni); std::vector<unsigned> item_n(ni), item_bin(ni, 0);
-        for (uint64_t i = 0; i < ni; ++i) { item_off[i] = i * OK_PART_TILE; item_n[i] = (unsigned)std::min<uint64_t>(OK_PART_TILE, n - i * OK_PART_TILE); }
-        TRY(dev_reserve(&c->d_items, &c->cap_items, 2 * ni + 2));
-        unsigned* d_n = (unsigned*)(c->d_items + ni);
-        unsigned* d_b = d_n + ni;
-        CU(cudaMemcpyAsync(c->d_items, item_off.data(), ni * 8, cudaMemcpyHostToDevice, c->s_main));
-        CU(cudaMemcpyAsync(d_n, item_n.data(), ni * 4, cudaMemcpyHostToDevice, c->s_main));
-        CU(cudaMemcpyAsync(d_b, item_bin.data(), ni * 4, cudaMemcpyHostToDevice, c->s_main));
+        // one level-1 scatter over the whole key array, in items of 4096 keys
         const bool two = pl.cfg.b2 > 0;
-        TRY(set_smem(k_part_scatter_keys<1>, sizeof(OkScatterSmem)));
-        LAUNCH(k_part_scatter_keys<1>, (unsigned)std::min<uint64_t>(ni, (uint64_t)grid_sm * 3), 256, sizeof(OkScatterSmem), c->s_main,
-               (const unsigned long long*)d_keys, c->d_items, d_n, d_b, (unsigned)ni, pl.cfg, two ? pl.cursor1 : pl.cursor,
-               two ? pl.end1 : pl.cap_end, two ? c->d_buf1 : c->d_buf2, (OkPartSpill{c->spill, c->d_stats}));
-        CU(cudaStreamSynchronize(c->s_main));
+        LAUNCH(k_part_flat_items, 64, 1024, 0, c->s_main, (unsigned)n, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
+        auto kern = ((uintptr_t)d_keys & 15u) ? k_part_scatter_keys<1, false> : k_part_scatter_keys<1, true>;
+        TRY(set_smem(kern, sizeof(OkScatterKeysSmem)));
+        LAUNCH(kern, grid_sm * 2, 256, sizeof(OkScatterKeysSmem), c->s_main, (const unsigned long long*)d_keys,
+               pl.item_off, pl.item_n, pl.item_bin, pl.scal, pl.cfg, two ? pl.cursor1 : pl.cursor,
+               (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2, (OkPartSpill{c->spill, c->d_stats}));
         c->windows += n;
         CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
     }
@@ -569,10 +577,36 @@ int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
     return part_absorb_spills(c, windows_before);
 }
 
+// compact sub-partitions [p0, p1) of the sparse run into the dense arrays
+void launch_compact(ok_counter* c, unsigned p0, unsigned p1, unsigned long long* out_keys, unsigned long long* out_counts) {
+    const PartPlan& pl = c->pl;
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    LAUNCH(k_part_compact, std::min<unsigned>(p1 - p0, grid_sm * 8), 256, 0, c->s_main, c->d_buf2, c->d_buf1, pl.beg, pl.hist,
+           pl.scan, p0, p1, out_keys, out_counts);
+}
+
+// sorted sub-partition runs -> one dense sorted run in d_run_keys / d_run_counts
+int run_make_dense(ok_counter* c) {
+    if (c->run_state != RUN_SPARSE) return OK_SUCCESS;
+    const uint64_t total = c->n_run;
+    TRY(dev_reserve(&c->d_run_keys, &c->cap_run_keys, total));
+    TRY(dev_reserve(&c->d_run_counts, &c->cap_run_counts, total));
+    CU(cudaEventRecord(c->ev_a, c->s_main));
+    if (total) launch_compact(c, 0, c->pl.n_sub, c->d_run_keys, c->d_run_counts);
+    CU(cudaEventRecord(c->ev_b, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&c->ms_compact, c->ev_a, c->ev_b);
+    c->ms_readout = c->ms_compact;
+    c->run_state = RUN_DENSE;
+    return OK_SUCCESS;
+}
+
 // fold the sorted run into the general table (a later batch arrived, or the run spilled)
 int run_to_table(ok_counter* c) {
-    if (!c->run_valid) return OK_SUCCESS;
-    c->run_valid = false;
+    if (c->run_state == RUN_NONE) return OK_SUCCESS;
+    TRY(run_make_dense(c));
+    c->run_state = RUN_NONE;
     const uint64_t n = c->n_run;
     c->occupied = 0;
     c->hint = std::max<uint64_t>(c->hint, n + n / 4);
@@ -599,6 +633,7 @@ int run_to_table(ok_counter* c) {
 
 // min_count filter of the run into the d_out arrays
 int run_filter(ok_counter* c, uint64_t min_count, uint64_t* n_out) {
+    TRY(run_make_dense(c));
     const uint64_t n = c->n_run;
     *n_out = 0;
     if (n == 0) return OK_SUCCESS;
@@ -623,8 +658,12 @@ int run_filter(ok_counter* c, uint64_t min_count, uint64_t* n_out) {
 
 // result of the counter, wherever it lives: -> device pointers
 int counter_result(ok_counter* c, uint64_t min_count, const unsigned long long** dk, const unsigned long long** dc, uint64_t* n) {
-    if (c->run_valid) {
-        if (min_count <= 1) { *dk = c->d_run_keys; *dc = c->d_run_counts; *n = c->n_run; return OK_SUCCESS; }
+    if (c->run_state != RUN_NONE) {
+        if (min_count <= 1) {
+            TRY(run_make_dense(c));
+            *dk = c->d_run_keys; *dc = c->d_run_counts; *n = c->n_run;
+            return OK_SUCCESS;
+        }
         TRY(run_filter(c, min_count, n));
         *dk = c->d_out_keys; *dc = c->d_out_counts;
         return OK_SUCCESS;
@@ -733,6 +772,8 @@ OK_EXPORT int ok_counter_create(uint8_t k, int norm_mode, uint64_t capacity_hint
     CUF(cudaMemset(c->d_stats, 0, sizeof(OkDevStats)));
     CUF(cudaMallocHost((void**)&c->h_stats, sizeof(OkDevStats)));
     memset(c->h_stats, 0, sizeof(OkDevStats));
+    CUF(cudaMallocHost((void**)&c->h_part, sizeof(PartHost)));
+    memset(c->h_part, 0, sizeof(PartHost));
     c->spill.cap = SPILL_CAP;
     CUF(cudaMalloc((void**)&c->spill.keys, SPILL_CAP * 8));
     CUF(cudaMalloc((void**)&c->spill.incs, SPILL_CAP * 8));
@@ -750,7 +791,7 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
     cudaFree(c->d_bases); cudaFree(c->d_off); cudaFree(c->d_tiles);
     cudaFree(c->d_out_keys); cudaFree(c->d_out_counts);
     cudaFree(c->d_run_keys); cudaFree(c->d_run_counts); cudaFree(c->d_buf1); cudaFree(c->d_buf2);
-    cudaFree(c->d_meta); cudaFree(c->d_hist); cudaFree(c->d_hist2); cudaFree(c->d_items);
+    cudaFree(c->d_meta); cudaFreeHost(c->h_part);
     for (auto e : c->ev_p) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_chunks) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -763,9 +804,9 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
 
 OK_EXPORT int ok_counter_clear(ok_counter* c) {
     if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_clear: NULL handle");
-    if (c->tv.slots && c->occupied && !c->run_valid)
+    if (c->tv.slots && c->occupied && c->run_state == RUN_NONE)
         LAUNCH(k_fill_slots, grid_for(c->tv.n_total, 256, 16), 256, 0, c->s_main, c->tv.slots, c->tv.n_total);
-    c->run_valid = false; c->n_run = 0;
+    c->run_state = RUN_NONE; c->n_run = 0;
     CU(cudaMemsetAsync(c->d_stats, 0, sizeof(OkDevStats), c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
     c->occupied = c->windows = c->bases_seen = c->max_disp = c->spilled_total = 0;
@@ -781,7 +822,7 @@ OK_EXPORT int ok_counter_add_batch_device(ok_counter* c, const uint8_t* d_bases,
     if ((uintptr_t)d_bases & 15u) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
     c->ms_insert = 0; c->ms_fill = 0;
     if (part_eligible(c, n_bases)) {
-        const int r = part_count_bases(c, d_bases, n_bases, d_rec_offsets, n_records);
+        const int r = part_count_bases(c, d_bases, n_bases, d_rec_offsets, n_records, d_bases, nullptr);
         if (r != PART_RETRY) { if (r == OK_SUCCESS) c->bases_seen += n_bases; return r; }
     }
     TRY(run_to_table(c));
@@ -816,9 +857,19 @@ OK_EXPORT int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const ui
         CU(cudaEventRecord(c->ev_chunks[p], c->s_copy));
     }
     CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces], 0));
-    if (part_eligible(c, n_bases)) {   // one-shot partitioned path needs the whole batch resident
-        CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces - 1], 0));
-        const int r = part_count_bases(c, c->d_bases, n_bases, c->d_off, n_records);
+    if (part_eligible(c, n_bases)) {
+        // The level-1 scatter follows the pieces as they land.  The plan needs a sample of the WHOLE
+        // batch first: a page-locked caller buffer is sampled in place (zero-copy reads over PCIe,
+        // 1/16 of the tiles); a pageable one only after the last piece has landed.
+        const uint8_t* sample_src = c->d_bases;
+        cudaPointerAttributes attr{};
+        const bool mapped = cudaPointerGetAttributes(&attr, bases) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                            attr.devicePointer && ((uintptr_t)attr.devicePointer & 15u) == 0 && !getenv("ORION_NO_ZEROCOPY");
+        cudaGetLastError();
+        if (mapped) sample_src = (const uint8_t*)attr.devicePointer;
+        else CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces - 1], 0));
+        const PieceSchedule ps{n_pieces, COPY_CHUNK, c->ev_chunks.data()};
+        const int r = part_count_bases(c, c->d_bases, n_bases, c->d_off, n_records, sample_src, &ps);
         if (r != PART_RETRY) { if (r == OK_SUCCESS) c->bases_seen += n_bases; return r; }
     }
     TRY(run_to_table(c));
@@ -988,10 +1039,14 @@ OK_EXPORT int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_ba
     cfg.key_shift = 64 - 2 * c->k; cfg.shard_log2 = 0; cfg.b2 = 0; cfg.b1 = 0;
     for (int g = n_ranks; g > 1; g >>= 1) ++cfg.b1;
     OkPeerOut po{};
-    unsigned long long zero[8] = {0}, ends[8] = {0};
-    for (int r = 0; r < n_ranks; ++r) { po.p[r] = (unsigned long long*)d_dst[r]; ends[r] = counts[r]; }
-    TRY(dev_reserve(&c->d_meta, &c->cap_meta, 32));
-    unsigned long long *d_cur = c->d_meta, *d_end = c->d_meta + 8;
+    unsigned zero[8] = {0}, ends[8] = {0};
+    for (int r = 0; r < n_ranks; ++r) {
+        if (counts[r] >= (1ull << 32)) return set_err(OK_ERR_INVALID_ARGUMENT, "more than 2^32 k-mers for one rank in one batch");
+        po.p[r] = (unsigned long long*)d_dst[r]; ends[r] = (unsigned)counts[r];
+    }
+    if (c->run_state != RUN_NONE) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_route_scatter_device: the counter holds a result; clear it first");
+    TRY(dev_reserve(&c->d_meta, &c->cap_meta, 64));
+    unsigned *d_cur = c->d_meta, *d_end = c->d_meta + 8;
     CU(cudaEventRecord(c->ev_a, c->s_main));
     CU(cudaMemcpyAsync(d_cur, zero, sizeof zero, cudaMemcpyHostToDevice, c->s_main));
     CU(cudaMemcpyAsync(d_end, ends, sizeof ends, cudaMemcpyHostToDevice, c->s_main));
@@ -1002,8 +1057,8 @@ OK_EXPORT int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_ba
     const unsigned blocks = (unsigned)((n_tiles + 8 * tpw - 1) / (8 * tpw));
     auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true, true> : k_part_scatter_bases<false, true>;
     TRY(set_smem(kern, sizeof(OkScatterSmem)));
-    LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, n_tiles, tpw, c->k,
-           cfg, d_cur, (const unsigned long long*)d_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
+    LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, (uint64_t)0, n_tiles, tpw, c->k,
+           cfg, d_cur, (const unsigned*)d_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
            c->d_stats->route_counts, po);
     CU(cudaEventRecord(c->ev_b, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
@@ -1027,10 +1082,43 @@ OK_EXPORT int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const 
 OK_EXPORT int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** kmers, uint64_t** counts,
                                 uint64_t* n) {
     if (!c || !kmers || !counts || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_finish: NULL argument");
+    void *hk = nullptr, *hc = nullptr;
+    if (c->run_state == RUN_SPARSE && min_count <= 1 && c->n_run) {
+        // result pipeline: compact the sorted sub-partition runs slice by slice on the compute stream
+        // while the copy stream ships the slices already compacted to the host
+        const uint64_t total = c->n_run;
+        const PartPlan& pl = c->pl;
+        TRY(pool_alloc(&hk, total * 8));
+        TRY(pool_alloc(&hc, total * 8));
+        TRY(dev_reserve(&c->d_run_keys, &c->cap_run_keys, total));
+        TRY(dev_reserve(&c->d_run_counts, &c->cap_run_counts, total));
+        while (c->ev_chunks.size() < pl.n_slices) {
+            cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_chunks.push_back(e);
+        }
+        CU(cudaEventRecord(c->ev_a, c->s_main));
+        for (unsigned i = 0; i < pl.n_slices; ++i) {
+            const unsigned p0 = i * pl.slice_step, p1 = std::min(pl.n_sub, p0 + pl.slice_step);
+            const uint64_t o0 = c->h_part->slice_base[i], o1 = c->h_part->slice_base[i + 1];
+            if (o1 <= o0) continue;
+            launch_compact(c, p0, p1, c->d_run_keys, c->d_run_counts);
+            CU(cudaEventRecord(c->ev_chunks[i], c->s_main));
+            CU(cudaStreamWaitEvent(c->s_copy, c->ev_chunks[i], 0));
+            CU(cudaMemcpyAsync((uint64_t*)hk + o0, c->d_run_keys + o0, (o1 - o0) * 8, cudaMemcpyDeviceToHost, c->s_copy));
+            CU(cudaMemcpyAsync((uint64_t*)hc + o0, c->d_run_counts + o0, (o1 - o0) * 8, cudaMemcpyDeviceToHost, c->s_copy));
+        }
+        CU(cudaEventRecord(c->ev_b, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        CU(cudaStreamSynchronize(c->s_copy));
+        CU(cudaGetLastError());
+        cudaEventElapsedTime(&c->ms_compact, c->ev_a, c->ev_b);
+        c->ms_readout = c->ms_compact;
+        c->run_state = RUN_DENSE;
+        *kmers = (uint64_t*)hk; *counts = (uint64_t*)hc; *n = total;
+        return OK_SUCCESS;
+    }
     uint64_t total = 0;
     const unsigned long long *dk = nullptr, *dc = nullptr;
     TRY(counter_result(c, min_count, &dk, &dc, &total));
-    void *hk = nullptr, *hc = nullptr;
     TRY(pool_alloc(&hk, total * 8));
     TRY(pool_alloc(&hc, total * 8));
     if (total) {
@@ -1051,11 +1139,11 @@ OK_EXPORT int ok_counter_set_path(ok_counter* c, int mode) {
 
 OK_EXPORT int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out) {
     if (!c || !out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_get_stats: NULL argument");
-    out->n_slots = c->run_valid ? 0 : c->tv.n_total; out->n_distinct = c->occupied; out->n_windows = c->windows;
+    out->n_slots = c->run_state != RUN_NONE ? 0 : c->tv.n_total; out->n_distinct = c->occupied; out->n_windows = c->windows;
     out->n_bases = c->bases_seen; out->max_displacement = c->max_disp; out->n_spilled = c->spilled_total;
     out->n_grows = c->grows; out->ms_insert = c->ms_insert; out->ms_readout = c->ms_readout; out->ms_fill = c->ms_fill; out->ms_route = c->ms_route;
     out->ms_sample = c->ms_sample; out->ms_scatter1 = c->ms_scatter1; out->ms_scatter2 = c->ms_scatter2;
-    out->ms_count = c->ms_count; out->ms_compact = c->ms_compact; out->partitioned = c->run_valid ? 1 : 0;
+    out->ms_count = c->ms_count; out->ms_compact = c->ms_compact; out->partitioned = c->run_state != RUN_NONE ? 1 : 0;
     return OK_SUCCESS;
 }
 

@@ -4,11 +4,16 @@
 // ~17 G load+RED/s (random 32 B sector traffic, DRAM-activation bound) while shared-memory
 // atomics run at ~2.4 T/s.  So large batches are counted without a global table at all:
 //
-//   k_part_sample         1/16 of the tiles -> histogram of sub-partition ids (sizes the buffers)
+//   k_part_sample         1/16 of the tiles -> histogram of sub-partition ids
+//   k_part_plan           histogram -> capacity and start of every sub-partition (on the device:
+//                         no host round trip between the phases)
 //   k_part_scatter_bases  ASCII -> pack -> rolling canonical k-mers -> level-1 partitions
-//   k_part_scatter_keys   level-1 partition -> level-2 sub-partitions
-//   k_part_count          one CTA per sub-partition: shared-memory table (CAS claim + add),
-//                         then an ordered sweep emits the sub-partition already sorted
+//   k_part_items          level-1 fills -> 4096-key work items
+//   k_part_scatter_keys   level-1 partition -> level-2 sub-partitions (TMA bulk loads of the items)
+//   k_part_count          one CTA per sub-partition: hashed shared-memory table dedupes and counts
+//                         (CAS claim + add), then the distinct keys are bucketed by position and
+//                         emitted in key order
+//   k_part_count_generic  the few sub-partitions k_part_count defers (oversized / clustered)
 //   k_part_compact        sub-partition runs -> the final sorted (k-mer, count) arrays
 //
 // Partitions are ranges of the monotone position x(key) (kmer_math.cuh ok_canon_pos), so
@@ -21,9 +26,17 @@
 
 #define OK_PART_TILE 4096u        // keys per CTA round of a scatter (256 threads x 16)
 #define OK_PART_MAXBINS 1024u     // bins per scatter level
-#define OK_CT_SLOTS 8192u         // slots of the shared-memory count table
-#define OK_CT_PAD 512u            // tail padding = displacement bound of the smem table
+#define OK_STAGE_SLOTS 8192u      // staging slots of a scatter round
+// generic (fallback) count kernel: monotone shared-memory table
+#define OK_CT_SLOTS 8192u
+#define OK_CT_PAD 512u            // tail padding = displacement bound of the monotone table
 #define OK_CT_THREADS 512u
+// fast count kernel: hashed shared-memory table + position buckets
+#define OK_C2_SLOTS 8192u         // hashed table slots
+#define OK_C2_MAXKEYS 6144u       // largest sub-partition it takes (75 % load if all keys are distinct)
+#define OK_C2_BUCKETS 1024u       // position buckets that order the distinct keys (2 per thread)
+#define OK_C2_BUCKET_MAX 32u      // a fuller bucket defers the sub-partition to the generic kernel
+#define OK_C2_THREADS 512u
 
 struct OkPartCfg {
     unsigned key_shift;    // 64 - 2k
@@ -31,20 +44,26 @@ struct OkPartCfg {
     unsigned b1, b2;       // bits of the level-1 / level-2 bin id
 };
 
-// position of a key inside this rank's slice of the key space (64-bit fraction, monotone)
+// 64-bit position of a key inside this rank's slice of the key space (monotone)
 __device__ __forceinline__ uint64_t ok_part_pos(uint64_t key, const OkPartCfg& c) {
     return ok_canon_pos(key << c.key_shift) << c.shard_log2;
 }
-__device__ __forceinline__ unsigned ok_part_bin1(uint64_t x, const OkPartCfg& c) { return c.b1 ? (unsigned)(x >> (64 - c.b1)) : 0u; }
-__device__ __forceinline__ unsigned ok_part_bin2(uint64_t x, const OkPartCfg& c) { return c.b2 ? (unsigned)((x << c.b1) >> (64 - c.b2)) : 0u; }
-__device__ __forceinline__ unsigned ok_part_sub(uint64_t x, const OkPartCfg& c) {
+// its top 32 bits, which is all the bin arithmetic needs (shard + level-1 + level-2 + bucket bits
+// <= 3 + 18 + 10 <= 32 - shard_log2): three 32-bit instructions instead of 64-bit shifts
+__device__ __forceinline__ uint32_t ok_part_phi(uint64_t key, const OkPartCfg& c) {
+    const uint32_t w = ~(uint32_t)((key << c.key_shift) >> 32);
+    return (~__umulhi(w, w)) << c.shard_log2;
+}
+__device__ __forceinline__ unsigned ok_phi_bin1(uint32_t phi, const OkPartCfg& c) { return c.b1 ? phi >> (32 - c.b1) : 0u; }
+__device__ __forceinline__ unsigned ok_phi_bin2(uint32_t phi, const OkPartCfg& c) { return c.b2 ? (phi << c.b1) >> (32 - c.b2) : 0u; }
+__device__ __forceinline__ unsigned ok_phi_sub(uint32_t phi, const OkPartCfg& c) {
     const unsigned b = c.b1 + c.b2;
-    return b ? (unsigned)(x >> (64 - b)) : 0u;
+    return b ? phi >> (32 - b) : 0u;
 }
 template <int LEVEL>
 __device__ __forceinline__ unsigned ok_part_bin(uint64_t key, const OkPartCfg& c) {
-    const uint64_t x = ok_part_pos(key, c);
-    return LEVEL == 1 ? ok_part_bin1(x, c) : ok_part_bin2(x, c);
+    const uint32_t phi = ok_part_phi(key, c);
+    return LEVEL == 1 ? ok_phi_bin1(phi, c) : ok_phi_bin2(phi, c);
 }
 
 struct OkPartSpill { OkSpill sp; OkDevStats* st; };
@@ -52,6 +71,14 @@ struct OkPartSpill { OkSpill sp; OkDevStats* st; };
 // multi-GPU routing: bin b of the scatter is owner rank b and its keys go to that rank's
 // receive buffer -- peer memory mapped over NVLink (CUDA IPC), or local memory for b == self
 struct OkPeerOut { unsigned long long* p[8]; };
+
+// scalars of one batch, device resident (host reads them once, at the end)
+struct OkPartScalars {
+    unsigned n_items;        // level-2 work items
+    unsigned n_deferred;     // sub-partitions left to the generic count kernel
+    unsigned total_cap;      // sum of the sub-partition capacities
+    unsigned pad;
+};
 
 // ----------------------------------------------------------------------------- sampling --
 // every `stride`-th warp-tile; hist[sub] += 1 per k-mer (global RED; the sample is small)
@@ -67,7 +94,7 @@ k_part_sample(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_
         ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t, t + 1, t + 1, k, lane,
             [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {
                 ok_lane_windows(pc, cc, okmask, k, [&](int, uint64_t key) {
-                    atomicAdd(&hist[ok_part_sub(ok_part_pos(key, cfg), cfg)], 1u);
+                    atomicAdd(&hist[ok_phi_sub(ok_part_phi(key, cfg), cfg)], 1u);
                 });
             });
 }
@@ -78,101 +105,180 @@ k_part_sample_keys(const unsigned long long* __restrict__ keys, uint64_t n, uint
     const uint64_t n_chunks = (n + 255) / 256;
     for (uint64_t c = blockIdx.x * stride; c < n_chunks; c += (uint64_t)gridDim.x * stride) {
         const uint64_t i = c * 256 + threadIdx.x;
-        if (i < n) atomicAdd(&hist[ok_part_sub(ok_part_pos(keys[i], cfg), cfg)], 1u);
+        if (i < n) atomicAdd(&hist[ok_phi_sub(ok_part_phi(keys[i], cfg), cfg)], 1u);
     }
+}
+
+// ------------------------------------------------------------------------------ planning --
+// block-wide exclusive scan helper (1024 threads): returns the exclusive prefix of v, total in *tot
+__device__ __forceinline__ unsigned ok_block_excl_scan_1024(unsigned v, unsigned* wsum /*[33]*/, unsigned* tot) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
+    __syncthreads();                       // wsum may still be read from a previous call
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned w = wsum[lane];
+        unsigned winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, winc, o); if (lane >= o) winc += y; }
+        wsum[lane] = winc - w;
+        if (lane == 31) wsum[32] = winc;
+    }
+    __syncthreads();
+    *tot = wsum[32];
+    return wsum[wid] + inc - v;
+}
+
+// capacity of a sub-partition from its sampled count: estimate + 6 sigma of the sampling error
+// (+ slack), even so that every region starts 16-byte aligned (TMA bulk loads)
+__device__ __forceinline__ unsigned ok_part_capacity(unsigned sampled, unsigned stride, unsigned n_units) {
+    const unsigned long long est = (unsigned long long)sampled * stride;
+    unsigned long long cap = est;
+    if (stride > 1) cap += (unsigned long long)(6.0f * sqrtf((float)est * (float)stride)) + 128ull;
+    if (cap > n_units) cap = n_units;
+    return (unsigned)((cap + 1ull) & ~1ull);
+}
+
+// one CTA, 1024 threads: hist[n_sub] (sample counts) -> beg / cursor / cap_end per sub-partition,
+// beg1 / cursor1 / end1 per level-1 bin.  hist is zeroed again (it becomes n_distinct later).
+__global__ void __launch_bounds__(1024)
+k_part_plan(unsigned* __restrict__ hist, unsigned n_sub, unsigned stride, unsigned n_units, unsigned b2,
+            unsigned* __restrict__ beg, unsigned* __restrict__ cursor, unsigned* __restrict__ cap_end,
+            unsigned* __restrict__ beg1, unsigned* __restrict__ cursor1, unsigned* __restrict__ end1,
+            OkPartScalars* __restrict__ sc) {
+    __shared__ unsigned wsum[33];
+    const unsigned per = (n_sub + 1023u) / 1024u;
+    const unsigned p0 = threadIdx.x * per, p1 = min(p0 + per, n_sub);
+    unsigned local = 0;
+    for (unsigned p = p0; p < p1; ++p) local += ok_part_capacity(hist[p], stride, n_units);
+    unsigned total;
+    unsigned run = ok_block_excl_scan_1024(local, wsum, &total);
+    for (unsigned p = p0; p < p1; ++p) {
+        const unsigned cap = ok_part_capacity(hist[p], stride, n_units);
+        beg[p] = run; cursor[p] = run; run += cap; cap_end[p] = run;
+        hist[p] = 0;
+        if (b2 && (p & ((1u << b2) - 1u)) == 0) { beg1[p >> b2] = run - cap; cursor1[p >> b2] = run - cap; }
+        if (b2 && (p & ((1u << b2) - 1u)) == (1u << b2) - 1u) end1[p >> b2] = run;
+    }
+    if (threadIdx.x == 0) { sc->total_cap = total; sc->n_items = 0; sc->n_deferred = 0; }
+}
+
+// one CTA, 1024 threads: level-1 fills -> work items of <= OK_PART_TILE keys for the level-2 scatter
+__global__ void __launch_bounds__(1024)
+k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cursor1, const unsigned* __restrict__ end1,
+             unsigned n_bin1, unsigned* __restrict__ item_off, unsigned* __restrict__ item_n,
+             unsigned* __restrict__ item_bin, OkPartScalars* __restrict__ sc) {
+    __shared__ unsigned wsum[33];
+    const unsigned b = threadIdx.x;
+    unsigned fill = 0, b0 = 0;
+    if (b < n_bin1) { b0 = beg1[b]; const unsigned e = min(cursor1[b], end1[b]); fill = e > b0 ? e - b0 : 0u; }
+    const unsigned ni = (fill + OK_PART_TILE - 1u) / OK_PART_TILE;
+    unsigned total;
+    unsigned o = ok_block_excl_scan_1024(ni, wsum, &total);
+    for (unsigned i = 0; i < ni; ++i, ++o) {
+        item_off[o] = b0 + i * OK_PART_TILE;
+        item_n[o] = min(OK_PART_TILE, fill - i * OK_PART_TILE);
+        item_bin[o] = b;
+    }
+    if (threadIdx.x == 0) sc->n_items = total;
 }
 
 // ------------------------------------------------------------- shared multisplit machinery --
 // Slotted staging: the 8192 staging slots are split evenly among the bins of the level, a key's
 // rank inside its bin (one shared-memory atomicAdd) is its slot, so one pass stages the round.
 // A bin that outgrows its slots in a round sends the excess straight to global memory.
-#define OK_STAGE_SLOTS 8192u
 struct OkScatterSmem {
     unsigned long long stage[OK_STAGE_SLOTS];
-    unsigned hist[OK_PART_MAXBINS];              // keys per bin this round; zero between rounds
-    unsigned gbase[OK_PART_MAXBINS];             // global index of the bin's first staged key (buffers < 2^32 keys)
+    uint2 hg[OK_PART_MAXBINS];   // x: keys of the bin this round (zero between rounds), y: global index of its first staged key
 };
 
-__device__ __forceinline__ void ok_part_put(unsigned long long key, unsigned long long dst, unsigned long long end,
+__device__ __forceinline__ void ok_part_put(unsigned long long key, unsigned dst, unsigned end,
                                             unsigned long long* __restrict__ out, const OkPartSpill& ps) {
     if (dst < end) out[dst] = key;
     else ok_spill(ps.sp, ps.st, key, 1);     // past the sampled capacity of the bin: exact, slow path
 }
 
 // One multisplit round of the CTA (all 256 threads call it together): thread-held keys
-// key[0..15] (bit q of vmask says key[q] exists) -> out, grouped by bin.  sm.hist must be zero on
-// entry and is zero again on exit.
-template <int LEVEL, bool PEER = false>
+// key[0..15] (bit q of vmask says key[q] exists) -> out, grouped by bin.  sm.hg[].x must be zero
+// on entry and is zero again on exit.  after_stage() runs once the round's keys have left the
+// registers of every thread (the level-2 kernel issues its next TMA load there).
+template <int LEVEL, bool PEER, class AfterStage>
 __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_t (&key)[16], unsigned vmask,
                                                 const OkPartCfg& cfg, unsigned bins_log2,
-                                                unsigned long long* __restrict__ cursors,
-                                                const unsigned long long* __restrict__ bin_end,
+                                                unsigned* __restrict__ cursors, const unsigned* __restrict__ bin_end,
                                                 unsigned long long* __restrict__ out, const OkPartSpill& ps,
-                                                const OkPeerOut* peer = nullptr) {
+                                                const OkPeerOut* peer, AfterStage&& after_stage) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned cap_log2 = 13u - bins_log2, cap = 1u << cap_log2, n_bins = 1u << bins_log2;
 #pragma unroll
     for (int q = 0; q < 16; ++q)
         if (vmask >> q & 1u) {
             const unsigned b = ok_part_bin<LEVEL>(key[q], cfg);
-            const unsigned r = atomicAdd(&sm.hist[b], 1u);
+            const unsigned r = atomicAdd(&sm.hg[b].x, 1u);
             if (r < cap) sm.stage[(b << cap_log2) + r] = key[q];
-            else ok_part_put(key[q], atomicAdd(&cursors[b], 1ull), bin_end[b], PEER ? peer->p[b] : out, ps);
+            else ok_part_put(key[q], atomicAdd(&cursors[b], 1u), bin_end[b], PEER ? peer->p[b] : out, ps);
         }
     __syncthreads();
+    after_stage();
     // copy out.  Warp w owns staging slots [w*1024, (w+1)*1024) = a contiguous range of bins.
     // (1) one global cursor bump per non-empty bin; a bin whose region is full spills its tail here
     const unsigned bins_per_warp = n_bins >= 8 ? n_bins >> 3 : 1u;
     const unsigned wb0 = wid * bins_per_warp;
     for (unsigned i = lane; i < bins_per_warp && wb0 + i < n_bins; i += 32) {
         const unsigned b = wb0 + i;
-        unsigned c = sm.hist[b];
+        unsigned c = sm.hg[b].x, g = 0;
         if (c > cap) c = cap;
         if (c) {
-            const unsigned long long g = atomicAdd(&cursors[b], (unsigned long long)c), e = bin_end[b];
+            g = atomicAdd(&cursors[b], c);
+            const unsigned e = bin_end[b];
             if (g + c > e) {
-                const unsigned keep = g < e ? (unsigned)(e - g) : 0u;
+                const unsigned keep = g < e ? e - g : 0u;
                 for (unsigned r = keep; r < c; ++r) ok_spill(ps.sp, ps.st, sm.stage[(b << cap_log2) + r], 1);
                 c = keep;
             }
-            sm.gbase[b] = (unsigned)g;
         }
-        sm.hist[b] = c;
+        sm.hg[b] = make_uint2(c, g);
     }
     __syncwarp();
     // (2) dense walk over the warp's staging slots: consecutive lanes = consecutive slots of a bin
     if (wb0 < n_bins) {
         const unsigned t_end = (wb0 + bins_per_warp) << cap_log2;
+#pragma unroll 4
         for (unsigned t = (wb0 << cap_log2) + lane; t < t_end; t += 32) {
             const unsigned b = t >> cap_log2, r = t & (cap - 1u);
-            if (r < sm.hist[b]) (PEER ? peer->p[b] : out)[(unsigned long long)sm.gbase[b] + r] = sm.stage[t];
+            const uint2 h = sm.hg[b];
+            if (r < h.x) (PEER ? peer->p[b] : out)[h.y + r] = sm.stage[t];
         }
     }
     __syncwarp();
-    for (unsigned i = lane; i < bins_per_warp && wb0 + i < n_bins; i += 32) sm.hist[wb0 + i] = 0;
+    for (unsigned i = lane; i < bins_per_warp && wb0 + i < n_bins; i += 32) sm.hg[wb0 + i].x = 0;
     __syncthreads();
 }
 
 // ------------------------------------------------------------------ level 1: from the bases --
 // The 8 warps of a CTA walk their own runs of tiles in lock step; each warp-tile is split in
-// two rounds of 16 window ends per lane, so a round holds <= 4096 k-mers per CTA.
+// two rounds of 16 window ends per lane, so a round holds <= 4096 k-mers per CTA.  The launch
+// covers tiles [tile_begin, tile_end) -- the ingest pipeline launches it once per landed piece.
 template <bool MAP_U, bool PEER = false>
 __global__ void __launch_bounds__(256, 3)
 k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
-                     uint64_t n_rec, uint64_t n_tiles, uint64_t tiles_per_warp, unsigned k, OkPartCfg cfg,
-                     unsigned long long* __restrict__ cursors, const unsigned long long* __restrict__ bin_end,
+                     uint64_t n_rec, uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp, unsigned k,
+                     OkPartCfg cfg, unsigned* __restrict__ cursors, const unsigned* __restrict__ bin_end,
                      unsigned long long* __restrict__ out, OkPartSpill ps, unsigned long long* __restrict__ n_keys,
                      const __grid_constant__ OkPeerOut peer_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-    const uint64_t t0 = warp * tiles_per_warp;
-    if ((uint64_t)blockIdx.x * 8 * tiles_per_warp >= n_tiles) return;   // whole CTA idle
-    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += 256) sm.hist[i] = 0;
+    const uint64_t t0 = tile_begin + warp * tiles_per_warp;
+    if (tile_begin + (uint64_t)blockIdx.x * 8 * tiles_per_warp >= tile_end) return;   // whole CTA idle
+    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += 256) sm.hg[i] = make_uint2(0u, 0u);
     __syncthreads();
     unsigned long long my_keys = 0;
-    ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t0 + tiles_per_warp, n_tiles, k, lane,
+    ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t0 + tiles_per_warp, tile_end, k, lane,
         [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {
             OkRoll roll; roll.init(pc, cc, k);
             my_keys += __popc(okmask);
@@ -183,7 +289,7 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
                 for (int q = 0; q < 16; ++q) key[q] = roll.step(16 * half + q);
                 // window end j = 16*half + q lives in okmask bit 31-j; make bit q mean key[q]
                 const unsigned vm = __brev(okmask) >> (16 * half) & 0xFFFFu;
-                ok_multisplit16<1, PEER>(sm, key, vm, cfg, cfg.b1, cursors, bin_end, out, ps, &peer_out);
+                ok_multisplit16<1, PEER>(sm, key, vm, cfg, cfg.b1, cursors, bin_end, out, ps, &peer_out, [] {});
             }
         });
     my_keys = ok_warp_sum(my_keys);
@@ -191,47 +297,287 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
 }
 
 // --------------------------------------------------------------------- level 2: from keys --
-// work item w: keys src[item_off[w] .. +item_n[w]) (<= 4096), all of level-1 bin item_bin[w]
-template <int LEVEL>  // LEVEL 1: bin by bin1 (keys arriving from peers); LEVEL 2: bin by bin2 inside a bin1
-__global__ void __launch_bounds__(256, 3)
-k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ item_off,
-                    const unsigned* __restrict__ item_n, const unsigned* __restrict__ item_bin, unsigned n_items,
-                    OkPartCfg cfg, unsigned long long* __restrict__ cursors,
-                    const unsigned long long* __restrict__ bin_end, unsigned long long* __restrict__ out,
-                    OkPartSpill ps) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
+// TMA bulk copy global -> shared, completion on an mbarrier (one elected thread issues it)
+__device__ __forceinline__ uint32_t ok_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ok_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ok_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void ok_tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ok_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(ok_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(ok_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ok_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ok_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ok_mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OK_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OK_MBAR_DONE_%=;\n"
+        "bra OK_MBAR_WAIT_%=;\n"
+        "OK_MBAR_DONE_%=:\n"
+        "}\n" :: "r"(ok_smem_u32(bar)), "r"(phase) : "memory");
+}
+
+struct OkScatterKeysSmem {
+    OkScatterSmem sc;
+    unsigned long long in[OK_PART_TILE];     // landing buffer of the next work item (TMA)
+    unsigned long long bar;                  // mbarrier of the landing buffer
+};
+
+// work item w: keys src[item_off[w] .. +item_n[w]) (<= 4096), all of level-1 bin item_bin[w].
+// item_off is even (16-byte aligned regions) and the copy is rounded up to an even key count.
+// TMA = false: plain loads (a caller's key array that is not 16-byte aligned).
+template <int LEVEL, bool TMA = true>  // LEVEL 1: bin by bin1 (keys arriving from peers); LEVEL 2: bin by bin2 inside a bin1
+__global__ void __launch_bounds__(256, 2)
+k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* __restrict__ item_off,
+                    const unsigned* __restrict__ item_n, const unsigned* __restrict__ item_bin,
+                    const OkPartScalars* __restrict__ scal, OkPartCfg cfg, unsigned* __restrict__ cursors,
+                    const unsigned* __restrict__ bin_end, unsigned long long* __restrict__ out, OkPartSpill ps) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    OkScatterKeysSmem& sm = *reinterpret_cast<OkScatterKeysSmem*>(smem_raw);
     const unsigned bins_log2 = LEVEL == 1 ? cfg.b1 : cfg.b2;
-    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += 256) sm.hist[i] = 0;
+    const unsigned n_items = scal->n_items;
+    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += 256) sm.sc.hg[i] = make_uint2(0u, 0u);
+    // LEVEL 2 reads our own level-1 buffer (even capacities, slack at the end): an odd item is
+    // rounded UP to whole 16-byte units.  LEVEL 1 reads a caller's array: rounded DOWN, and the
+    // odd last key is fetched with a plain load.
+    auto load_item = [&](unsigned w) {
+        const unsigned n = item_n[w];
+        const unsigned bytes = (LEVEL == 2 ? (n + 1u) & ~1u : n & ~1u) * 8u;
+        if (bytes) ok_tma_load_1d(sm.in, src + item_off[w], bytes, &sm.bar);
+        else ok_mbar_arrive(&sm.bar);
+    };
+    if (TMA && threadIdx.x == 0) {
+        ok_mbar_init(&sm.bar, 1);
+        if (blockIdx.x < n_items) load_item(blockIdx.x);
+    }
     __syncthreads();
+    unsigned phase = 0;
     for (unsigned w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const unsigned long long* __restrict__ keys = src + item_off[w];
         const unsigned n = item_n[w];
         const unsigned bin_base = LEVEL == 1 ? 0u : item_bin[w] << cfg.b2;
         uint64_t key[16]; unsigned vm = 0;
+        if (TMA) {
+            ok_mbar_wait(&sm.bar, phase); phase ^= 1u;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const unsigned i = q * 256 + threadIdx.x;
-            key[q] = 0;
-            if (i < n) { key[q] = __ldcs(keys + i); vm |= 1u << q; }
+            for (int q = 0; q < 16; ++q) {
+                const unsigned i = q * 256 + threadIdx.x;
+                key[q] = sm.in[i];
+                if (LEVEL == 1 && i + 1 == n && (n & 1u)) key[q] = src[item_off[w] + i];
+                if (i < n) vm |= 1u << q;
+            }
+        } else {
+            const unsigned long long* __restrict__ keys = src + item_off[w];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const unsigned i = q * 256 + threadIdx.x;
+                key[q] = 0;
+                if (i < n) { key[q] = __ldcs(keys + i); vm |= 1u << q; }
+            }
         }
-        ok_multisplit16<LEVEL>(sm, key, vm, cfg, bins_log2, cursors + bin_base, bin_end + bin_base, out, ps);
+        const unsigned wn = w + gridDim.x;
+        ok_multisplit16<LEVEL, false>(sm.sc, key, vm, cfg, bins_log2, cursors + bin_base, bin_end + bin_base, out, ps, nullptr,
+            [&] {   // every thread holds its keys in registers: the landing buffer is free again
+                if (TMA && threadIdx.x == 0 && wn < n_items) load_item(wn);
+            });
     }
 }
 
-// ------------------------------------------------------- count one sub-partition in smem --
+// plain work items over a flat key array (keys received from peers): item w = keys [w*4096, ...)
+__global__ void __launch_bounds__(1024)
+k_part_flat_items(unsigned n_keys, unsigned* __restrict__ item_off, unsigned* __restrict__ item_n,
+                  unsigned* __restrict__ item_bin, OkPartScalars* __restrict__ sc) {
+    const unsigned ni = (n_keys + OK_PART_TILE - 1u) / OK_PART_TILE;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ni; i += gridDim.x * blockDim.x) {
+        item_off[i] = i * OK_PART_TILE;
+        item_n[i] = min(OK_PART_TILE, n_keys - i * OK_PART_TILE);
+        item_bin[i] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc->n_items = ni;
+}
+
+// ------------------------------------------------ count one sub-partition in shared memory --
 // sub-partition p holds keys src[beg[p] .. fill_end[p]).  Its distinct keys come out sorted in
 // place (keys -> src[beg[p] ..], counts -> cnt_out[beg[p] ..]); n_distinct[p] says how many.
+//
+// Fast kernel.  (1) dedupe + count in a HASHED table (CAS claim + add): duplicates -- ~80 % of the
+// windows at 30x coverage -- hit their key on the first probe, and a k-mer and its tail-error
+// variants no longer share a slot the way they must under an order-preserving placement.
+// (2) order the distinct keys only: bucket them by the next 10 position bits (two sweeps over the
+// table around one block scan), insertion-sort each bucket (~1 key per bucket), emit coalesced.
+struct OkCount2Smem {
+    unsigned long long tkey[OK_C2_SLOTS];          // 64 KB
+    unsigned tcnt[OK_C2_SLOTS / 2];                // two 16-bit counts per word (a count <= 6144)
+    unsigned short sidx[OK_C2_MAXKEYS];            // table slots of the distinct keys, in bucket order
+    unsigned boff[OK_C2_BUCKETS];                  // bucket histogram -> bucket end offsets
+    unsigned wsum[18];
+};
+
+__device__ __forceinline__ unsigned ok_c2_hash(uint64_t key) {
+    uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
+    x *= 0x85EBCA6Bu;
+    return x >> 19;      // 13 bits: OK_C2_SLOTS == 8192
+}
+__device__ __forceinline__ unsigned ok_c2_bucket(uint64_t key, const OkPartCfg& cfg, unsigned sub_bits) {
+    return (ok_part_phi(key, cfg) << sub_bits) >> 22;     // 10 bits: OK_C2_BUCKETS == 1024
+}
+__device__ __forceinline__ void ok_c2_add(OkCount2Smem& sm, unsigned s) {
+    atomicAdd(&sm.tcnt[s >> 1], 1u << ((s & 1u) << 4));
+}
+__device__ __forceinline__ void ok_c2_insert_slow(OkCount2Smem& sm, unsigned long long key, unsigned s) {
+    for (;;) {
+        unsigned long long cur = sm.tkey[s];
+        if (cur == OK_EMPTY_KEY) {
+            cur = atomicCAS(&sm.tkey[s], OK_EMPTY_KEY, key);
+            if (cur == OK_EMPTY_KEY) cur = key;
+        }
+        if (cur == key) { ok_c2_add(sm, s); return; }
+        s = (s + 1u) & (OK_C2_SLOTS - 1u);
+    }
+}
+
+__global__ void __launch_bounds__(OK_C2_THREADS, 2)
+k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ beg,
+             const unsigned* __restrict__ fill_end /* cursor after the scatter */,
+             const unsigned* __restrict__ cap_end, unsigned n_sub, OkPartCfg cfg,
+             unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct,
+             unsigned* __restrict__ deferred, OkPartScalars* __restrict__ scal) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OkCount2Smem& sm = *reinterpret_cast<OkCount2Smem*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned sub_bits = cfg.b1 + cfg.b2;
+    auto clear_table = [&] {
+        ulonglong2* k2 = reinterpret_cast<ulonglong2*>(sm.tkey);
+        uint4* c4 = reinterpret_cast<uint4*>(sm.tcnt);
+        for (unsigned i = threadIdx.x; i < OK_C2_SLOTS / 2; i += OK_C2_THREADS) k2[i] = make_ulonglong2(OK_EMPTY_KEY, OK_EMPTY_KEY);
+        for (unsigned i = threadIdx.x; i < OK_C2_SLOTS / 8; i += OK_C2_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    };
+    clear_table();
+    for (unsigned i = threadIdx.x; i < OK_C2_BUCKETS; i += OK_C2_THREADS) sm.boff[i] = 0;
+    __syncthreads();
+    for (unsigned p = blockIdx.x; p < n_sub; p += gridDim.x) {
+        // invariant here: table empty, counts zero, boff zero
+        const unsigned b0 = beg[p];
+        const unsigned e0 = min(fill_end[p], cap_end[p]);          // the rest was spilled by the scatter
+        const unsigned n = e0 > b0 ? e0 - b0 : 0u;
+        if (n == 0) { if (threadIdx.x == 0) n_distinct[p] = 0; continue; }
+        if (n > OK_C2_MAXKEYS) {                                     // too large for the hashed table
+            if (threadIdx.x == 0) deferred[atomicAdd(&scal->n_deferred, 1u)] = p;
+            continue;
+        }
+        const unsigned long long* __restrict__ keys = src + b0;
+        // ---- (1) insert: 4 keys in flight per thread, first probes issued together
+        for (unsigned base = 0; base < n; base += 4 * OK_C2_THREADS) {
+            unsigned long long kk[4], cur[4]; unsigned hs[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned i = base + q * OK_C2_THREADS + threadIdx.x;
+                kk[q] = i < n ? __ldcs(keys + i) : OK_EMPTY_KEY;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { hs[q] = ok_c2_hash(kk[q]); cur[q] = sm.tkey[hs[q]]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (kk[q] == OK_EMPTY_KEY) continue;                 // canonical k-mers never equal the sentinel
+                if (cur[q] == kk[q]) ok_c2_add(sm, hs[q]);           // duplicate of a key already placed: the common case
+                else ok_c2_insert_slow(sm, kk[q], hs[q]);
+            }
+        }
+        __syncthreads();
+        // ---- (2a) sweep 1: bucket histogram of the distinct keys
+#pragma unroll 4
+        for (unsigned s = threadIdx.x; s < OK_C2_SLOTS; s += OK_C2_THREADS) {
+            const unsigned long long key = sm.tkey[s];
+            if (key != OK_EMPTY_KEY) atomicAdd(&sm.boff[ok_c2_bucket(key, cfg, sub_bits)], 1u);
+        }
+        __syncthreads();
+        // ---- (2b) exclusive scan of the 1024 bucket counts, two per thread
+        const unsigned ha = sm.boff[2 * threadIdx.x], hb = sm.boff[2 * threadIdx.x + 1];
+        unsigned inc = ha + hb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
+        if (lane == 31) sm.wsum[wid] = inc;
+        const int crowded = __syncthreads_or(ha > OK_C2_BUCKET_MAX || hb > OK_C2_BUCKET_MAX);
+        if (wid == 0) {
+            const unsigned w = lane < 16 ? sm.wsum[lane] : 0u;
+            unsigned winc = w;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, winc, o); if (lane >= o) winc += y; }
+            if (lane < 16) sm.wsum[lane] = winc - w;
+            if (lane == 15) sm.wsum[16] = winc;
+        }
+        __syncthreads();
+        const unsigned tot = sm.wsum[16];
+        if (crowded) {      // keys too clustered for per-thread bucket sorts: leave it to the generic kernel
+            if (threadIdx.x == 0) deferred[atomicAdd(&scal->n_deferred, 1u)] = p;
+            clear_table();
+            sm.boff[2 * threadIdx.x] = 0; sm.boff[2 * threadIdx.x + 1] = 0;
+            __syncthreads();
+            continue;
+        }
+        const unsigned excl = sm.wsum[wid] + inc - (ha + hb);
+        sm.boff[2 * threadIdx.x] = excl; sm.boff[2 * threadIdx.x + 1] = excl + ha;
+        __syncthreads();
+        // ---- (2c) sweep 2: slot ids into bucket order (boff[b] ends up as the END of bucket b)
+#pragma unroll 4
+        for (unsigned s = threadIdx.x; s < OK_C2_SLOTS; s += OK_C2_THREADS) {
+            const unsigned long long key = sm.tkey[s];
+            if (key != OK_EMPTY_KEY) sm.sidx[atomicAdd(&sm.boff[ok_c2_bucket(key, cfg, sub_bits)], 1u)] = (unsigned short)s;
+        }
+        __syncthreads();
+        // ---- (2d) insertion sort inside my two buckets (by key; ~1 key per bucket)
+        {
+            unsigned lo = threadIdx.x ? sm.boff[2 * threadIdx.x - 1] : 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned hi = sm.boff[2 * threadIdx.x + h];
+                for (unsigned i = lo + 1; i < hi; ++i) {
+                    const unsigned short si = sm.sidx[i];
+                    const unsigned long long ki = sm.tkey[si];
+                    unsigned j = i;
+                    while (j > lo) {
+                        const unsigned short sj = sm.sidx[j - 1];
+                        if (sm.tkey[sj] <= ki) break;
+                        sm.sidx[j] = sj; --j;
+                    }
+                    sm.sidx[j] = si;
+                }
+                lo = hi;
+            }
+        }
+        __syncthreads();
+        // ---- (3) emit in order, coalesced; clean the used slots on the way
+        sm.boff[2 * threadIdx.x] = 0; sm.boff[2 * threadIdx.x + 1] = 0;
+        for (unsigned o = threadIdx.x; o < tot; o += OK_C2_THREADS) {
+            const unsigned s = sm.sidx[o];
+            src[b0 + o] = sm.tkey[s];
+            cnt_out[b0 + o] = reinterpret_cast<unsigned short*>(sm.tcnt)[s];
+            sm.tkey[s] = OK_EMPTY_KEY;
+            reinterpret_cast<unsigned short*>(sm.tcnt)[s] = 0;
+        }
+        if (threadIdx.x == 0) n_distinct[p] = tot;
+        __syncthreads();
+    }
+}
+
+// Generic kernel for the sub-partitions the fast kernel deferred: MONOTONE shared-memory table
+// (home slot = position inside the sub-partition, linear probing, displacement bound OK_CT_PAD
+// with an exact spill), ordered sweep + local rank fix.  Any sub-partition size.
 __device__ __forceinline__ unsigned ok_ct_home(uint64_t key, const OkPartCfg& cfg, unsigned sub_bits) {
     const uint64_t f = ok_part_pos(key, cfg) << sub_bits;     // position inside the sub-partition
     return (unsigned)(((f >> 32) * (uint64_t)OK_CT_SLOTS) >> 32);
 }
 
 __global__ void __launch_bounds__(OK_CT_THREADS, 2)
-k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __restrict__ beg,
-             const unsigned long long* __restrict__ fill_end /* cursor after the scatter */,
-             const unsigned long long* __restrict__ cap_end, unsigned n_sub, OkPartCfg cfg,
-             unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct, OkPartSpill ps) {
+k_part_count_generic(unsigned long long* __restrict__ src, const unsigned* __restrict__ beg,
+                     const unsigned* __restrict__ fill_end, const unsigned* __restrict__ cap_end,
+                     const unsigned* __restrict__ deferred, const OkPartScalars* __restrict__ scal, OkPartCfg cfg,
+                     unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct, OkPartSpill ps) {
     constexpr unsigned NT = OK_CT_SLOTS + OK_CT_PAD;            // 8704
     constexpr unsigned ROUNDS = NT / OK_CT_THREADS;             // 17 strided rounds in the sweep
     constexpr unsigned NW = OK_CT_THREADS / 32;                 // 16 warps
@@ -241,11 +587,12 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __r
     __shared__ unsigned seg[ROUNDS * NW + 1];       // occupied slots per (round, warp), then exclusive scan
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned sub_bits = cfg.b1 + cfg.b2;
-    for (unsigned p = blockIdx.x; p < n_sub; p += gridDim.x) {
-        const unsigned long long b0 = beg[p];
-        unsigned long long e0 = fill_end[p];
-        if (e0 > cap_end[p]) e0 = cap_end[p];          // the rest was spilled by the scatter
-        const unsigned n = (unsigned)(e0 - b0);
+    const unsigned n_def = scal->n_deferred;
+    for (unsigned d = blockIdx.x; d < n_def; d += gridDim.x) {
+        const unsigned p = deferred[d];
+        const unsigned b0 = beg[p];
+        const unsigned e0 = min(fill_end[p], cap_end[p]);
+        const unsigned n = e0 > b0 ? e0 - b0 : 0u;
         if (n == 0) { if (threadIdx.x == 0) n_distinct[p] = 0; continue; }
         {   // 128-bit stores: two keys / four counts at a time
             ulonglong2* k2 = reinterpret_cast<ulonglong2*>(tkey);
@@ -334,15 +681,17 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned long long* __r
     }
 }
 
-// sub-partition runs -> final arrays; base[p] = exclusive scan of n_distinct (as u64)
+// sub-partition runs -> final arrays; base[p] = exclusive scan of n_distinct (as u64).
+// Sub-partitions [p_begin, p_end): the result pipeline compacts and ships the table in slices.
 __global__ void __launch_bounds__(256)
 k_part_compact(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ counts,
-               const unsigned long long* __restrict__ beg, const unsigned* __restrict__ n_distinct,
-               const unsigned long long* __restrict__ base, unsigned n_sub,
+               const unsigned* __restrict__ beg, const unsigned* __restrict__ n_distinct,
+               const unsigned long long* __restrict__ base, unsigned p_begin, unsigned p_end,
                unsigned long long* __restrict__ out_keys, unsigned long long* __restrict__ out_counts) {
-    for (unsigned p = blockIdx.x; p < n_sub; p += gridDim.x) {
+    for (unsigned p = p_begin + blockIdx.x; p < p_end; p += gridDim.x) {
         const unsigned n = n_distinct[p];
-        const unsigned long long b0 = beg[p], o0 = base[p];
+        const unsigned b0 = beg[p];
+        const unsigned long long o0 = base[p];
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
             out_keys[o0 + i] = keys[b0 + i];
             out_counts[o0 + i] = counts[b0 + i];
