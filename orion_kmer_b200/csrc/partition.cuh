@@ -413,9 +413,11 @@ k_part_flat_items(unsigned n_keys, unsigned* __restrict__ item_off, unsigned* __
 struct OkCount2Smem {
     unsigned long long tkey[OK_C2_SLOTS];          // 64 KB
     unsigned tcnt[OK_C2_SLOTS / 2];                // two 16-bit counts per word (a count <= 6144)
-    unsigned short sidx[OK_C2_MAXKEYS];            // table slots of the distinct keys, in bucket order
+    unsigned short newl[OK_C2_MAXKEYS];            // table slots of the distinct keys, in claim order
+    unsigned short sidx[OK_C2_MAXKEYS];            // the same, grouped by bucket
     unsigned boff[OK_C2_BUCKETS];                  // bucket histogram -> bucket end offsets
     unsigned wsum[18];
+    unsigned n_new;
 };
 
 __device__ __forceinline__ unsigned ok_c2_hash(uint64_t key) {
@@ -429,15 +431,23 @@ __device__ __forceinline__ unsigned ok_c2_bucket(uint64_t key, const OkPartCfg& 
 __device__ __forceinline__ void ok_c2_add(OkCount2Smem& sm, unsigned s) {
     atomicAdd(&sm.tcnt[s >> 1], 1u << ((s & 1u) << 4));
 }
-__device__ __forceinline__ void ok_c2_insert_slow(OkCount2Smem& sm, unsigned long long key, unsigned s) {
+// key not found at its first probe (cur = what was read there): walk on, claim an empty slot.
+// The thread that claims a slot also files the new distinct key: claim list + bucket histogram.
+__device__ __forceinline__ void ok_c2_insert_slow(OkCount2Smem& sm, unsigned long long key, unsigned s,
+                                                  unsigned long long cur, const OkPartCfg& cfg, unsigned sub_bits) {
     for (;;) {
-        unsigned long long cur = sm.tkey[s];
         if (cur == OK_EMPTY_KEY) {
             cur = atomicCAS(&sm.tkey[s], OK_EMPTY_KEY, key);
-            if (cur == OK_EMPTY_KEY) cur = key;
+            if (cur == OK_EMPTY_KEY) {
+                ok_c2_add(sm, s);
+                sm.newl[atomicAdd(&sm.n_new, 1u)] = (unsigned short)s;
+                atomicAdd(&sm.boff[ok_c2_bucket(key, cfg, sub_bits)], 1u);
+                return;
+            }
         }
         if (cur == key) { ok_c2_add(sm, s); return; }
         s = (s + 1u) & (OK_C2_SLOTS - 1u);
+        cur = sm.tkey[s];
     }
 }
 
@@ -451,17 +461,17 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
     OkCount2Smem& sm = *reinterpret_cast<OkCount2Smem*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned sub_bits = cfg.b1 + cfg.b2;
-    auto clear_table = [&] {
+    {
         ulonglong2* k2 = reinterpret_cast<ulonglong2*>(sm.tkey);
         uint4* c4 = reinterpret_cast<uint4*>(sm.tcnt);
         for (unsigned i = threadIdx.x; i < OK_C2_SLOTS / 2; i += OK_C2_THREADS) k2[i] = make_ulonglong2(OK_EMPTY_KEY, OK_EMPTY_KEY);
         for (unsigned i = threadIdx.x; i < OK_C2_SLOTS / 8; i += OK_C2_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
-    };
-    clear_table();
-    for (unsigned i = threadIdx.x; i < OK_C2_BUCKETS; i += OK_C2_THREADS) sm.boff[i] = 0;
+        for (unsigned i = threadIdx.x; i < OK_C2_BUCKETS; i += OK_C2_THREADS) sm.boff[i] = 0;
+        if (threadIdx.x == 0) sm.n_new = 0;
+    }
     __syncthreads();
     for (unsigned p = blockIdx.x; p < n_sub; p += gridDim.x) {
-        // invariant here: table empty, counts zero, boff zero
+        // invariant here: table empty, counts zero, boff zero, n_new zero
         const unsigned b0 = beg[p];
         const unsigned e0 = min(fill_end[p], cap_end[p]);          // the rest was spilled by the scatter
         const unsigned n = e0 > b0 ? e0 - b0 : 0u;
@@ -471,13 +481,20 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             continue;
         }
         const unsigned long long* __restrict__ keys = src + b0;
-        // ---- (1) insert: 4 keys in flight per thread, first probes issued together
+        // ---- (1) insert: 4 keys in flight per thread, the next 4 already loading
+        unsigned long long nx[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned i = q * OK_C2_THREADS + threadIdx.x;
+            nx[q] = i < n ? __ldcs(keys + i) : OK_EMPTY_KEY;
+        }
         for (unsigned base = 0; base < n; base += 4 * OK_C2_THREADS) {
             unsigned long long kk[4], cur[4]; unsigned hs[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const unsigned i = base + q * OK_C2_THREADS + threadIdx.x;
-                kk[q] = i < n ? __ldcs(keys + i) : OK_EMPTY_KEY;
+                kk[q] = nx[q];
+                const unsigned i = base + (4 + q) * OK_C2_THREADS + threadIdx.x;
+                nx[q] = i < n ? __ldcs(keys + i) : OK_EMPTY_KEY;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) { hs[q] = ok_c2_hash(kk[q]); cur[q] = sm.tkey[hs[q]]; }
@@ -485,18 +502,12 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             for (int q = 0; q < 4; ++q) {
                 if (kk[q] == OK_EMPTY_KEY) continue;                 // canonical k-mers never equal the sentinel
                 if (cur[q] == kk[q]) ok_c2_add(sm, hs[q]);           // duplicate of a key already placed: the common case
-                else ok_c2_insert_slow(sm, kk[q], hs[q]);
+                else ok_c2_insert_slow(sm, kk[q], hs[q], cur[q], cfg, sub_bits);
             }
         }
         __syncthreads();
-        // ---- (2a) sweep 1: bucket histogram of the distinct keys
-#pragma unroll 4
-        for (unsigned s = threadIdx.x; s < OK_C2_SLOTS; s += OK_C2_THREADS) {
-            const unsigned long long key = sm.tkey[s];
-            if (key != OK_EMPTY_KEY) atomicAdd(&sm.boff[ok_c2_bucket(key, cfg, sub_bits)], 1u);
-        }
-        __syncthreads();
-        // ---- (2b) exclusive scan of the 1024 bucket counts, two per thread
+        // ---- (2) exclusive scan of the 1024 bucket counts, two per thread
+        const unsigned tot = sm.n_new;
         const unsigned ha = sm.boff[2 * threadIdx.x], hb = sm.boff[2 * threadIdx.x + 1];
         unsigned inc = ha + hb;
 #pragma unroll
@@ -509,58 +520,41 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, winc, o); if (lane >= o) winc += y; }
             if (lane < 16) sm.wsum[lane] = winc - w;
-            if (lane == 15) sm.wsum[16] = winc;
         }
         __syncthreads();
-        const unsigned tot = sm.wsum[16];
-        if (crowded) {      // keys too clustered for per-thread bucket sorts: leave it to the generic kernel
-            if (threadIdx.x == 0) deferred[atomicAdd(&scal->n_deferred, 1u)] = p;
-            clear_table();
-            sm.boff[2 * threadIdx.x] = 0; sm.boff[2 * threadIdx.x + 1] = 0;
+        if (!crowded) {
+            const unsigned excl = sm.wsum[wid] + inc - (ha + hb);
+            sm.boff[2 * threadIdx.x] = excl; sm.boff[2 * threadIdx.x + 1] = excl + ha;
             __syncthreads();
-            continue;
-        }
-        const unsigned excl = sm.wsum[wid] + inc - (ha + hb);
-        sm.boff[2 * threadIdx.x] = excl; sm.boff[2 * threadIdx.x + 1] = excl + ha;
-        __syncthreads();
-        // ---- (2c) sweep 2: slot ids into bucket order (boff[b] ends up as the END of bucket b)
-#pragma unroll 4
-        for (unsigned s = threadIdx.x; s < OK_C2_SLOTS; s += OK_C2_THREADS) {
-            const unsigned long long key = sm.tkey[s];
-            if (key != OK_EMPTY_KEY) sm.sidx[atomicAdd(&sm.boff[ok_c2_bucket(key, cfg, sub_bits)], 1u)] = (unsigned short)s;
-        }
-        __syncthreads();
-        // ---- (2d) insertion sort inside my two buckets (by key; ~1 key per bucket)
-        {
-            unsigned lo = threadIdx.x ? sm.boff[2 * threadIdx.x - 1] : 0u;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const unsigned hi = sm.boff[2 * threadIdx.x + h];
-                for (unsigned i = lo + 1; i < hi; ++i) {
-                    const unsigned short si = sm.sidx[i];
-                    const unsigned long long ki = sm.tkey[si];
-                    unsigned j = i;
-                    while (j > lo) {
-                        const unsigned short sj = sm.sidx[j - 1];
-                        if (sm.tkey[sj] <= ki) break;
-                        sm.sidx[j] = sj; --j;
-                    }
-                    sm.sidx[j] = si;
-                }
-                lo = hi;
+            // ---- (3) the distinct keys into bucket order (boff[b] ends up as the END of bucket b)
+            for (unsigned i = threadIdx.x; i < tot; i += OK_C2_THREADS) {
+                const unsigned s = sm.newl[i];
+                sm.sidx[atomicAdd(&sm.boff[ok_c2_bucket(sm.tkey[s], cfg, sub_bits)], 1u)] = (unsigned short)s;
             }
+            __syncthreads();
+            // ---- (4) rank inside the bucket (~1 key per bucket) = final position; emit
+            for (unsigned i = threadIdx.x; i < tot; i += OK_C2_THREADS) {
+                const unsigned s = sm.sidx[i];
+                const unsigned long long key = sm.tkey[s];
+                const unsigned b = ok_c2_bucket(key, cfg, sub_bits);
+                const unsigned lo = b ? sm.boff[b - 1] : 0u, hi = sm.boff[b];
+                unsigned pos = lo;
+                for (unsigned j = lo; j < hi; ++j) pos += sm.tkey[sm.sidx[j]] < key ? 1u : 0u;
+                src[b0 + pos] = key;
+                cnt_out[b0 + pos] = reinterpret_cast<unsigned short*>(sm.tcnt)[s];
+            }
+        } else if (threadIdx.x == 0) {   // keys too clustered for per-bucket ranking: leave it to the generic kernel
+            deferred[atomicAdd(&scal->n_deferred, 1u)] = p;
         }
         __syncthreads();
-        // ---- (3) emit in order, coalesced; clean the used slots on the way
-        sm.boff[2 * threadIdx.x] = 0; sm.boff[2 * threadIdx.x + 1] = 0;
-        for (unsigned o = threadIdx.x; o < tot; o += OK_C2_THREADS) {
-            const unsigned s = sm.sidx[o];
-            src[b0 + o] = sm.tkey[s];
-            cnt_out[b0 + o] = reinterpret_cast<unsigned short*>(sm.tcnt)[s];
+        // ---- (5) clean what this sub-partition used
+        for (unsigned i = threadIdx.x; i < tot; i += OK_C2_THREADS) {
+            const unsigned s = sm.newl[i];
             sm.tkey[s] = OK_EMPTY_KEY;
             reinterpret_cast<unsigned short*>(sm.tcnt)[s] = 0;
         }
-        if (threadIdx.x == 0) n_distinct[p] = tot;
+        sm.boff[2 * threadIdx.x] = 0; sm.boff[2 * threadIdx.x + 1] = 0;
+        if (threadIdx.x == 0) { sm.n_new = 0; if (!crowded) n_distinct[p] = tot; }
         __syncthreads();
     }
 }
