@@ -118,6 +118,7 @@ struct PartPlan {
     unsigned *beg1 = nullptr, *cursor1 = nullptr, *end1 = nullptr;
     unsigned *item_off = nullptr, *item_n = nullptr, *item_bin = nullptr;
     unsigned long long* scan = nullptr;      // exclusive scan of n_distinct, n_sub + 1 entries
+    unsigned long long* chunk_sum = nullptr; // per-1024-chunk totals of the two-launch scans
     OkPartScalars* scal = nullptr;
     unsigned n_slices = 0, slice_step = 0;   // result slices: sub-partitions [i*step, (i+1)*step)
 };
@@ -404,13 +405,13 @@ int part_layout(ok_counter* c, uint64_t n_units, uint64_t unit_chunk, uint64_t f
     const uint64_t n_sub = pl.n_sub;
     uint64_t words = 0;                                   // 32-bit words
     auto take = [&](uint64_t n) { uint64_t o = words; words += (n + 3) & ~3ull; return o; };
-    const uint64_t o_scan = take(2 * (n_sub + 2)), o_scal = take(sizeof(OkPartScalars) / 4), o_hist = take(n_sub), o_beg = take(n_sub),
+    const uint64_t o_scan = take(2 * (n_sub + 2)), o_chunk = take(2 * (n_sub / 1024 + 2)), o_scal = take(sizeof(OkPartScalars) / 4), o_hist = take(n_sub), o_beg = take(n_sub),
                    o_cur = take(n_sub), o_end = take(n_sub), o_def = take(n_sub), o_b1 = take(OK_PART_MAXBINS),
                    o_c1 = take(OK_PART_MAXBINS), o_e1 = take(OK_PART_MAXBINS), o_io = take(pl.max_items),
                    o_in = take(pl.max_items), o_ib = take(pl.max_items);
     TRY(dev_reserve(&c->d_meta, &c->cap_meta, words));
     unsigned* m = c->d_meta;
-    pl.scan = (unsigned long long*)(m + o_scan); pl.scal = (OkPartScalars*)(m + o_scal);
+    pl.scan = (unsigned long long*)(m + o_scan); pl.chunk_sum = (unsigned long long*)(m + o_chunk); pl.scal = (OkPartScalars*)(m + o_scal);
     pl.hist = m + o_hist; pl.beg = m + o_beg; pl.cursor = m + o_cur; pl.cap_end = m + o_end; pl.deferred = m + o_def;
     pl.beg1 = m + o_b1; pl.cursor1 = m + o_c1; pl.end1 = m + o_e1;
     pl.item_off = m + o_io; pl.item_n = m + o_in; pl.item_bin = m + o_ib;
@@ -447,8 +448,8 @@ int part_finish(ok_counter* c, PartPlan& pl) {
     LAUNCH(k_part_count_generic, grid_sm, OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg, pl.cursor, pl.cap_end,
            pl.deferred, pl.scal, pl.cfg, c->d_buf1, d_nd, ps);
     CU(cudaEventRecord(c->ev_p[4], c->s_main));
-    LAUNCH(k_widen_u32, grid_for(pl.n_sub), 256, 0, c->s_main, d_nd, pl.scan, (uint64_t)pl.n_sub);
-    LAUNCH(k_scan_tiles, 1, 1024, 0, c->s_main, pl.scan, (uint64_t)pl.n_sub, pl.scan + pl.n_sub);
+    LAUNCH(k_part_scan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, d_nd, pl.n_sub, pl.chunk_sum);
+    LAUNCH(k_part_scan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, d_nd, pl.n_sub, pl.chunk_sum, pl.scan);
     CU(cudaEventRecord(c->ev_p[5], c->s_main));
     // the one host round trip of the batch: totals, slice boundaries of the result, statistics
     const unsigned step = std::max<unsigned>(1, pl.n_sub / RESULT_SLICES);
@@ -516,8 +517,9 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_sample<true> : k_part_sample<false>;
         LAUNCH(kern, blocks, 256, 0, c->s_main, sample_src, n_bases, d_off, n_rec, n_tiles, (uint64_t)pl.stride, c->k, pl.cfg, pl.hist);
     }
-    LAUNCH(k_part_plan, 1, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.cfg.b2, pl.beg, pl.cursor,
-           pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
+    LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.chunk_sum);
+    LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.cfg.b2,
+           pl.chunk_sum, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     {
         const bool two = pl.cfg.b2 > 0;
@@ -557,8 +559,9 @@ int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
     CU(cudaMemsetAsync(pl.hist, 0, pl.n_sub * sizeof(unsigned), c->s_main));
     LAUNCH(k_part_sample_keys, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + pl.stride - 1) / pl.stride, (uint64_t)grid_sm * 16)),
            256, 0, c->s_main, (const unsigned long long*)d_keys, n, (uint64_t)pl.stride, pl.cfg, pl.hist);
-    LAUNCH(k_part_plan, 1, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n, pl.cfg.b2, pl.beg, pl.cursor,
-           pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
+    LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n, pl.chunk_sum);
+    LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n, pl.cfg.b2,
+           pl.chunk_sum, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     {
         // one level-1 scatter over the whole key array, in items of 4096 keys

@@ -142,28 +142,71 @@ __device__ __forceinline__ unsigned ok_part_capacity(unsigned sampled, unsigned 
     return (unsigned)((cap + 1ull) & ~1ull);
 }
 
-// one CTA, 1024 threads: hist[n_sub] (sample counts) -> beg / cursor / cap_end per sub-partition,
-// beg1 / cursor1 / end1 per level-1 bin.  hist is zeroed again (it becomes n_distinct later).
+// block-wide sum (1024 threads), result valid in every thread
+__device__ __forceinline__ unsigned long long ok_block_sum_1024(unsigned long long v, unsigned long long* wsum /*[33]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = ok_warp_sum(v);
+    __syncthreads();
+    if (lane == 0) wsum[wid] = v;
+    __syncthreads();
+    if (wid == 0) { unsigned long long w = ok_warp_sum(wsum[lane]); if (lane == 0) wsum[32] = w; }
+    __syncthreads();
+    return wsum[32];
+}
+
+// Two launches over chunks of 1024 sub-partitions (coalesced; no serial pass over all of them):
+// k_part_plan_sums: capacity total of every chunk.   k_part_plan: hist[n_sub] (sample counts) ->
+// beg / cursor / cap_end per sub-partition, beg1 / cursor1 / end1 per level-1 bin.  hist is zeroed
+// again (it becomes n_distinct later).
+__global__ void __launch_bounds__(1024)
+k_part_plan_sums(const unsigned* __restrict__ hist, unsigned n_sub, unsigned stride, unsigned n_units,
+                 unsigned long long* __restrict__ chunk_sum) {
+    __shared__ unsigned long long wsum[33];
+    const unsigned p = blockIdx.x * 1024u + threadIdx.x;
+    const unsigned long long t = ok_block_sum_1024(p < n_sub ? ok_part_capacity(hist[p], stride, n_units) : 0u, wsum);
+    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = t;
+}
 __global__ void __launch_bounds__(1024)
 k_part_plan(unsigned* __restrict__ hist, unsigned n_sub, unsigned stride, unsigned n_units, unsigned b2,
+            const unsigned long long* __restrict__ chunk_sum,
             unsigned* __restrict__ beg, unsigned* __restrict__ cursor, unsigned* __restrict__ cap_end,
             unsigned* __restrict__ beg1, unsigned* __restrict__ cursor1, unsigned* __restrict__ end1,
             OkPartScalars* __restrict__ sc) {
     __shared__ unsigned wsum[33];
-    const unsigned per = (n_sub + 1023u) / 1024u;
-    const unsigned p0 = threadIdx.x * per, p1 = min(p0 + per, n_sub);
-    unsigned local = 0;
-    for (unsigned p = p0; p < p1; ++p) local += ok_part_capacity(hist[p], stride, n_units);
+    __shared__ unsigned long long wsum64[33];
+    const unsigned long long before = ok_block_sum_1024(threadIdx.x < blockIdx.x ? chunk_sum[threadIdx.x] : 0ull, wsum64);
+    const unsigned p = blockIdx.x * 1024u + threadIdx.x;
+    const unsigned cap = p < n_sub ? ok_part_capacity(hist[p], stride, n_units) : 0u;
     unsigned total;
-    unsigned run = ok_block_excl_scan_1024(local, wsum, &total);
-    for (unsigned p = p0; p < p1; ++p) {
-        const unsigned cap = ok_part_capacity(hist[p], stride, n_units);
-        beg[p] = run; cursor[p] = run; run += cap; cap_end[p] = run;
+    const unsigned run = (unsigned)before + ok_block_excl_scan_1024(cap, wsum, &total);
+    if (p < n_sub) {
+        beg[p] = run; cursor[p] = run; cap_end[p] = run + cap;
         hist[p] = 0;
-        if (b2 && (p & ((1u << b2) - 1u)) == 0) { beg1[p >> b2] = run - cap; cursor1[p >> b2] = run - cap; }
-        if (b2 && (p & ((1u << b2) - 1u)) == (1u << b2) - 1u) end1[p >> b2] = run;
+        if (b2 && (p & ((1u << b2) - 1u)) == 0) { beg1[p >> b2] = run; cursor1[p >> b2] = run; }
+        if (b2 && (p & ((1u << b2) - 1u)) == (1u << b2) - 1u) end1[p >> b2] = run + cap;
     }
-    if (threadIdx.x == 0) { sc->total_cap = total; sc->n_items = 0; sc->n_deferred = 0; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { sc->total_cap = (unsigned)before + total; sc->n_items = 0; sc->n_deferred = 0; }
+}
+
+// exclusive scan of n_distinct[n_sub] -> base[n_sub + 1] (u64), same two-launch shape
+__global__ void __launch_bounds__(1024)
+k_part_scan_sums(const unsigned* __restrict__ v, unsigned n, unsigned long long* __restrict__ chunk_sum) {
+    __shared__ unsigned long long wsum[33];
+    const unsigned i = blockIdx.x * 1024u + threadIdx.x;
+    const unsigned long long t = ok_block_sum_1024(i < n ? v[i] : 0u, wsum);
+    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(1024)
+k_part_scan(const unsigned* __restrict__ v, unsigned n, const unsigned long long* __restrict__ chunk_sum,
+            unsigned long long* __restrict__ base) {
+    __shared__ unsigned wsum[33];
+    __shared__ unsigned long long wsum64[33];
+    const unsigned long long before = ok_block_sum_1024(threadIdx.x < blockIdx.x ? chunk_sum[threadIdx.x] : 0ull, wsum64);
+    const unsigned i = blockIdx.x * 1024u + threadIdx.x;
+    unsigned total;
+    const unsigned ex = ok_block_excl_scan_1024(i < n ? v[i] : 0u, wsum, &total);
+    if (i < n) base[i] = before + ex;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) base[n] = before + total;
 }
 
 // one CTA, 1024 threads: level-1 fills -> work items of <= OK_PART_TILE keys for the level-2 scatter
@@ -172,16 +215,23 @@ k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cur
              unsigned n_bin1, unsigned* __restrict__ item_off, unsigned* __restrict__ item_n,
              unsigned* __restrict__ item_bin, OkPartScalars* __restrict__ sc) {
     __shared__ unsigned wsum[33];
+    __shared__ unsigned s_first[OK_PART_MAXBINS + 1], s_b0[OK_PART_MAXBINS], s_fill[OK_PART_MAXBINS];
     const unsigned b = threadIdx.x;
     unsigned fill = 0, b0 = 0;
     if (b < n_bin1) { b0 = beg1[b]; const unsigned e = min(cursor1[b], end1[b]); fill = e > b0 ? e - b0 : 0u; }
     const unsigned ni = (fill + OK_PART_TILE - 1u) / OK_PART_TILE;
     unsigned total;
-    unsigned o = ok_block_excl_scan_1024(ni, wsum, &total);
-    for (unsigned i = 0; i < ni; ++i, ++o) {
-        item_off[o] = b0 + i * OK_PART_TILE;
-        item_n[o] = min(OK_PART_TILE, fill - i * OK_PART_TILE);
-        item_bin[o] = b;
+    const unsigned first = ok_block_excl_scan_1024(ni, wsum, &total);
+    s_first[b] = first; s_b0[b] = b0; s_fill[b] = fill;
+    if (b == 0) s_first[OK_PART_MAXBINS] = total;
+    __syncthreads();
+    for (unsigned o = threadIdx.x; o < total; o += 1024u) {     // item o belongs to the last bin whose first item is <= o
+        unsigned lo = 0, hi = OK_PART_MAXBINS - 1u;
+        while (lo < hi) { const unsigned mid = (lo + hi + 1u) >> 1; if (s_first[mid] <= o) lo = mid; else hi = mid - 1u; }
+        const unsigned i = o - s_first[lo];
+        item_off[o] = s_b0[lo] + i * OK_PART_TILE;
+        item_n[o] = min(OK_PART_TILE, s_fill[lo] - i * OK_PART_TILE);
+        item_bin[o] = lo;
     }
     if (threadIdx.x == 0) sc->n_items = total;
 }
