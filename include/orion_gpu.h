@@ -116,6 +116,33 @@ int ok_counter_route_count_device(ok_counter* c, const uint8_t* d_bases, uint64_
 int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
                                     const uint64_t* d_rec_offsets, uint64_t n_records, int n_ranks,
                                     uint64_t* const* d_dst, const uint64_t* counts);
+/* multi-GPU, fused exchange without a counting pass ("sharded scatter").  Every rank samples its
+ * batch; the ranks exchange the (small) histograms; then each sender's extraction kernel multisplits
+ * by (owner rank, level-1 bin) and writes straight into the owners' level-1 regions over NVLink, each
+ * region sized from that sender's sample -- so what arrives is already level-1 partitioned and the
+ * owner continues with its level-2 scatter.  Collectives stay with the caller (NCCL):
+ *   ok_shard_geometry        agree the geometry for batches of up to n_bases_max bases per rank;
+ *                            returns the histogram sizes and the size every peer buffer must have
+ *   ok_shard_set_buffers     the ok_peer_buffer_* level-1 buffers of all ranks as mapped here
+ *   ok_shard_sample_device   -> d_hist_fine[n_ranks << sub_bits], d_hist_l1[n_ranks << l1_bits]
+ *        caller: reduce-scatter(sum) d_hist_fine -> d_hist_mine[1 << sub_bits];
+ *                all-gather d_hist_l1 -> d_hist_l1_all[n_ranks][n_ranks << l1_bits]
+ *   ok_shard_scatter_device  plan + scatter; -> d_cursors_out[n_ranks << l1_bits]
+ *        caller: all-gather d_cursors_out -> d_cursors_all (this collective is also the barrier)
+ *   ok_shard_count_device    level-2 scatter + count of what the peers wrote
+ * A region that overflows its sampled capacity makes ok_shard_scatter_device fail on that rank; all
+ * ranks then clear and count the batch through the two-pass ok_counter_route_* calls. */
+int ok_shard_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* sub_bits, uint32_t* l1_bits,
+                      uint64_t* buffer_keys);
+int ok_shard_set_buffers(ok_counter* c, void* const* d_peer_buffers, uint64_t cap_keys);
+int ok_shard_sample_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                           const uint64_t* d_rec_offsets, uint64_t n_records, uint32_t* d_hist_fine,
+                           uint32_t* d_hist_l1);
+int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
+                            const uint64_t* d_rec_offsets, uint64_t n_records,
+                            const uint32_t* d_hist_mine, const uint32_t* d_hist_l1_all,
+                            uint32_t* d_cursors_out);
+int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all);
 /* count.rs:106-119: entries with count >= min_count, ascending by k-mer value. */
 int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** kmers, uint64_t** counts,
                       uint64_t* n);

@@ -90,6 +90,11 @@ ABI = {
     "ok_peer_buffer_destroy": (C.c_int, [vp]),
     "ok_counter_route_count_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp]),
     "ok_counter_route_scatter_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp]),
+    "ok_shard_geometry": (C.c_int, [vp, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), u64p]),
+    "ok_shard_set_buffers": (C.c_int, [vp, vp, C.c_uint64]),
+    "ok_shard_sample_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
+    "ok_shard_scatter_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, vp]),
+    "ok_shard_count_device": (C.c_int, [vp, vp]),
     "ok_counter_finish": (C.c_int, [vp, C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]),
     "ok_counter_finish_device": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp), u64p]),
     "ok_counter_set_path": (C.c_int, [vp, C.c_int]),
@@ -336,6 +341,26 @@ class KmerCounter:
         counts = np.ascontiguousarray(counts, dtype=np.uint64)
         _check(lib().ok_counter_route_scatter_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records, n_ranks,
                                                      arr, _ptr(counts)))
+
+    # ---- fused multi-GPU exchange (sharded scatter); collectives stay with the caller ----
+    def shard_geometry(self, n_bases_max):
+        sb, lb, cap = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        _check(lib().ok_shard_geometry(self._h, n_bases_max, C.byref(sb), C.byref(lb), C.byref(cap)))
+        return sb.value, lb.value, cap.value
+
+    def shard_set_buffers(self, peer_ptrs, cap_keys):
+        arr = (vp * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        _check(lib().ok_shard_set_buffers(self._h, arr, cap_keys))
+
+    def shard_sample_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_fine_ptr, d_hist_l1_ptr):
+        _check(lib().ok_shard_sample_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_fine_ptr, d_hist_l1_ptr))
+
+    def shard_scatter_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_mine_ptr, d_hist_l1_all_ptr, d_cursors_ptr):
+        _check(lib().ok_shard_scatter_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_mine_ptr,
+                                             d_hist_l1_all_ptr, d_cursors_ptr))
+
+    def shard_count_device(self, d_cursors_all_ptr):
+        _check(lib().ok_shard_count_device(self._h, d_cursors_all_ptr))
 
     def add_kmers_device(self, d_kmers_ptr, n):
         _check(lib().ok_counter_add_kmers_device(self._h, d_kmers_ptr, n))

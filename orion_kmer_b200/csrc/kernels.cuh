@@ -238,12 +238,14 @@ template <bool MAP_U, class PerGroup>
 __device__ __forceinline__ void ok_walk_tiles(const uint8_t* __restrict__ bases, uint64_t n_bases,
                                               const uint64_t* __restrict__ rec_off, uint64_t n_rec,
                                               uint64_t t0, uint64_t t1, uint64_t t_live, unsigned k, int lane,
-                                              PerGroup&& per_group) {
+                                              PerGroup&& per_group, bool halo = true) {
     // tiles >= t_live do not exist: per_group is still called (okmask 0) so that kernels whose
     // warps iterate in lock step keep their barriers aligned
     uint64_t carry_codes = 0; uint32_t carry_valid = 0, carry_start = 0;
     uint64_t r_next = 0;
-    if (t0 > 0 && t0 < t_live) {  // warm-up on the tile before ours: its last group is our first halo
+    if (!halo) {                  // sampling: windows reaching back into the previous tile are simply not seen
+        if (t0 > 0 && t0 < t_live) r_next = ok_lower_bound(rec_off, n_rec, t0 * OK_TILE_BASES);
+    } else if (t0 > 0 && t0 < t_live) {  // warm-up on the tile before ours: its last group is our first halo
         const uint64_t ws = (t0 - 1) * OK_TILE_BASES;
         r_next = ok_lower_bound(rec_off, n_rec, ws);
         uint64_t c; uint32_t v;

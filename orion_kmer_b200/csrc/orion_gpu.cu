@@ -113,6 +113,8 @@ enum { RUN_NONE = 0, RUN_SPARSE = 1, RUN_DENSE = 2 };
 struct PartPlan {
     OkPartCfg cfg{};
     unsigned n_sub = 1, n_bin1 = 1, stride = 1;
+    bool sharded = false;                    // keys arrived through the fused multi-GPU scatter (level-1 regions per sender)
+    bool big_count = false;                  // sub-partitions may average > 5800 keys: the 16384-slot count kernel
     uint64_t cap_bound = 0, max_items = 0;
     unsigned *hist = nullptr, *beg = nullptr, *cursor = nullptr, *cap_end = nullptr, *deferred = nullptr;
     unsigned *beg1 = nullptr, *cursor1 = nullptr, *end1 = nullptr;
@@ -123,10 +125,22 @@ struct PartPlan {
     unsigned n_slices = 0, slice_step = 0;   // result slices: sub-partitions [i*step, (i+1)*step)
 };
 
+// fused multi-GPU exchange (ok_shard_*): geometry agreed by all ranks + the peer-mapped level-1 buffers
+struct ShardState {
+    bool ready = false, buffers = false;
+    unsigned g = 0, sub_bits = 0, b1 = 0, b2 = 0, stride = 16;
+    uint64_t n_bases_max = 0, cap_keys = 0;
+    unsigned long long* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned* d_state = nullptr;             // reg_beg | reg_end | reg_fill | send_cur | send_end (1024 entries each)
+    unsigned *reg_beg = nullptr, *reg_end = nullptr, *reg_fill = nullptr, *send_cur = nullptr, *send_end = nullptr;
+    unsigned long long* d_received = nullptr;
+};
+
 struct PartHost {                            // page-locked mirror of the batch's scalars
     OkPartScalars scal;
     unsigned long long total;
     unsigned long long slice_base[64];       // output offset of every result slice, then the total
+    unsigned long long received;             // sharded path: k-mers the peers wrote into this rank's buffer
 };
 
 struct ok_counter {
@@ -157,6 +171,8 @@ struct ok_counter {
     int run_state = RUN_NONE;
     PartPlan pl;
     PartHost* h_part = nullptr;
+    ShardState shard;
+    bool buf1_external = false;        // d_buf1 is the caller's peer-mapped buffer (never reallocated or freed here)
     unsigned long long* d_run_keys = nullptr; uint64_t cap_run_keys = 0;
     unsigned long long* d_run_counts = nullptr; uint64_t cap_run_counts = 0;
     uint64_t n_run = 0, n_deferred = 0;
@@ -379,6 +395,7 @@ void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl) {
     pl.cfg.b2 = bits - pl.cfg.b1;
     pl.n_sub = 1u << bits;
     pl.n_bin1 = 1u << pl.cfg.b1;
+    pl.big_count = n_units / pl.n_sub > 5800;   // units bound the keys: a 6144-key table would defer too often
 }
 
 template <class K> int set_smem(K kern, size_t bytes) {
@@ -401,7 +418,7 @@ uint64_t part_cap_bound(uint64_t n_units, unsigned n_sub, unsigned stride, uint6
 int part_layout(ok_counter* c, uint64_t n_units, uint64_t unit_chunk, uint64_t flat_keys, PartPlan& pl) {
     pl.cap_bound = part_cap_bound(n_units, pl.n_sub, pl.stride, unit_chunk);
     if (pl.cap_bound >= (1ull << 32)) return set_err(OK_ERR_INTERNAL, "partitioned path: batch too large for 32-bit offsets");
-    pl.max_items = std::max<uint64_t>(pl.cap_bound / OK_PART_TILE + pl.n_bin1 + 1, flat_keys / OK_PART_TILE + 2);
+    pl.max_items = std::max<uint64_t>(pl.cap_bound / OK_PART_TILE + OK_PART_MAXBINS + 1, flat_keys / OK_PART_TILE + 2);   // one partial item per bin / region
     const uint64_t n_sub = pl.n_sub;
     uint64_t words = 0;                                   // 32-bit words
     auto take = [&](uint64_t n) { uint64_t o = words; words += (n + 3) & ~3ull; return o; };
@@ -416,7 +433,12 @@ int part_layout(ok_counter* c, uint64_t n_units, uint64_t unit_chunk, uint64_t f
     pl.beg1 = m + o_b1; pl.cursor1 = m + o_c1; pl.end1 = m + o_e1;
     pl.item_off = m + o_io; pl.item_n = m + o_in; pl.item_bin = m + o_ib;
     TRY(dev_reserve(&c->d_buf2, &c->cap_buf2, pl.cap_bound + 16));
-    TRY(dev_reserve(&c->d_buf1, &c->cap_buf1, pl.cap_bound + 16));   // level-1 output, later the counts of the runs
+    if (c->buf1_external) {
+        if (c->cap_buf1 < pl.cap_bound + 16) return set_err(OK_ERR_INVALID_ARGUMENT, "the peer buffer is too small for this batch (%llu < %llu keys)",
+                                                            (unsigned long long)c->cap_buf1, (unsigned long long)pl.cap_bound + 16);
+    } else {
+        TRY(dev_reserve(&c->d_buf1, &c->cap_buf1, pl.cap_bound + 16));   // level-1 output, later the counts of the runs
+    }
     return OK_SUCCESS;
 }
 
@@ -432,17 +454,27 @@ int part_finish(ok_counter* c, PartPlan& pl) {
     const OkPartSpill ps{c->spill, c->d_stats};
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
     if (pl.cfg.b2 > 0) {
-        LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
+        if (pl.sharded)   // (bin, sender) regions filled by the peers
+            LAUNCH(k_part_items, 1, 1024, 0, c->s_main, c->shard.reg_beg, c->shard.reg_fill, c->shard.reg_end, pl.n_bin1 << c->shard.g,
+                   c->shard.g, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
+        else
+            LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, 0u, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
         TRY(set_smem(k_part_scatter_keys<2>, sizeof(OkScatterKeysSmem)));
         LAUNCH(k_part_scatter_keys<2>, grid_sm * 2, 256, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
                pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps);
     }
     CU(cudaEventRecord(c->ev_p[3], c->s_main));
     // count every sub-partition in shared memory; sorted runs land in place, counts in d_buf1
-    TRY(set_smem(k_part_count, sizeof(OkCount2Smem)));
     unsigned* d_nd = pl.hist;   // the sample histogram is no longer needed (k_part_plan zeroed it)
-    LAUNCH(k_part_count, std::min<unsigned>(pl.n_sub, grid_sm * 2), OK_C2_THREADS, sizeof(OkCount2Smem), c->s_main, c->d_buf2,
-           pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, pl.deferred, pl.scal);
+    if (pl.big_count) {
+        TRY(set_smem(k_part_count<14>, sizeof(OkCount2Smem<14>)));
+        LAUNCH(k_part_count<14>, std::min<unsigned>(pl.n_sub, grid_sm), OkCount2Cfg<14>::THREADS, sizeof(OkCount2Smem<14>), c->s_main,
+               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, pl.deferred, pl.scal);
+    } else {
+        TRY(set_smem(k_part_count<13>, sizeof(OkCount2Smem<13>)));
+        LAUNCH(k_part_count<13>, std::min<unsigned>(pl.n_sub, grid_sm * 2), OkCount2Cfg<13>::THREADS, sizeof(OkCount2Smem<13>), c->s_main,
+               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, pl.deferred, pl.scal);
+    }
     const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
     TRY(set_smem(k_part_count_generic, ct_smem));
     LAUNCH(k_part_count_generic, grid_sm, OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg, pl.cursor, pl.cap_end,
@@ -519,7 +551,7 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
     }
     LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.chunk_sum);
     LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.cfg.b2,
-           pl.chunk_sum, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
+           pl.chunk_sum, (unsigned)pl.cap_bound, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     {
         const bool two = pl.cfg.b2 > 0;
@@ -561,7 +593,7 @@ int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
            256, 0, c->s_main, (const unsigned long long*)d_keys, n, (uint64_t)pl.stride, pl.cfg, pl.hist);
     LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n, pl.chunk_sum);
     LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n, pl.cfg.b2,
-           pl.chunk_sum, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
+           pl.chunk_sum, (unsigned)pl.cap_bound, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     {
         // one level-1 scatter over the whole key array, in items of 4096 keys
@@ -793,7 +825,8 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
     cudaFree(c->spill.keys); cudaFree(c->spill.incs);
     cudaFree(c->d_bases); cudaFree(c->d_off); cudaFree(c->d_tiles);
     cudaFree(c->d_out_keys); cudaFree(c->d_out_counts);
-    cudaFree(c->d_run_keys); cudaFree(c->d_run_counts); cudaFree(c->d_buf1); cudaFree(c->d_buf2);
+    cudaFree(c->d_run_keys); cudaFree(c->d_run_counts); if (!c->buf1_external) cudaFree(c->d_buf1); cudaFree(c->d_buf2);
+    cudaFree(c->shard.d_state); cudaFree(c->shard.d_received);
     cudaFree(c->d_meta); cudaFreeHost(c->h_part);
     for (auto e : c->ev_p) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_chunks) cudaEventDestroy(e);
@@ -1041,7 +1074,7 @@ OK_EXPORT int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_ba
     OkPartCfg cfg{};
     cfg.key_shift = 64 - 2 * c->k; cfg.shard_log2 = 0; cfg.b2 = 0; cfg.b1 = 0;
     for (int g = n_ranks; g > 1; g >>= 1) ++cfg.b1;
-    OkPeerOut po{};
+    OkPeerOut po{}; po.shift = 0;
     unsigned zero[8] = {0}, ends[8] = {0};
     for (int r = 0; r < n_ranks; ++r) {
         if (counts[r] >= (1ull << 32)) return set_err(OK_ERR_INVALID_ARGUMENT, "more than 2^32 k-mers for one rank in one batch");
@@ -1068,6 +1101,170 @@ OK_EXPORT int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_ba
     CU(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->ms_route += ms;
     return OK_SUCCESS;
+}
+
+// ---- fused multi-GPU exchange, second form: no counting pass, and the level-1 scatter of the owner happens on the sender ----
+// Per batch and rank:  ok_shard_sample_device -> [reduce-scatter of the fine histogram, all-gather of the
+// level-1 histograms] -> ok_shard_scatter_device (extract + multisplit by (owner, level-1 bin) straight
+// into the owners' level-1 regions over NVLink) -> [all-gather of the cursors = the barrier] ->
+// ok_shard_count_device (level-2 scatter + count of what arrived).
+OK_EXPORT int ok_shard_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* sub_bits, uint32_t* l1_bits, uint64_t* buffer_keys) {
+    if (!c || !sub_bits || !l1_bits || !buffer_keys) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_geometry: NULL argument");
+    if (c->n_shards < 2) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_geometry: call ok_counter_set_shard first (n_ranks >= 2)");
+    if (n_bases_max == 0 || n_bases_max >= (1ull << 31)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_geometry: batch size out of range");
+    ShardState& sh = c->shard;
+    sh.g = 0; for (int g = c->n_shards; g > 1; g >>= 1) ++sh.g;
+    // what a rank receives is balanced by the canonical prior: plan for 1.25 x the largest batch
+    const uint64_t n_units = n_bases_max + n_bases_max / 4;
+    PartPlan pl;
+    part_choose_bits(c, n_bases_max, pl);
+    unsigned bits = pl.cfg.b1 + pl.cfg.b2;
+    sh.b1 = std::min(pl.cfg.b1, 10u - sh.g);                 // sender bins = owners x level-1 bins <= 1024
+    if (const char* ev = getenv("ORION_SHARD_B1")) { unsigned v = (unsigned)atoi(ev); if (v >= 1 && v + sh.g <= 10 && v <= bits) sh.b1 = v; }
+    if (bits - sh.b1 > 10) bits = sh.b1 + 10;                // level 2 has at most 1024 bins: larger sub-partitions instead
+    sh.b2 = bits - sh.b1; sh.sub_bits = bits;
+    sh.stride = 16; sh.n_bases_max = n_bases_max;
+    sh.cap_keys = part_cap_bound(n_units, 1u << bits, sh.stride, OK_TILE_BASES) + 16;
+    if (sh.cap_keys >= (1ull << 32)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_geometry: batch too large for 32-bit offsets");
+    if (!sh.d_state) {
+        CU(cudaMalloc((void**)&sh.d_state, 5 * 1024 * sizeof(unsigned)));
+        CU(cudaMalloc((void**)&sh.d_received, 8));
+        sh.reg_beg = sh.d_state; sh.reg_end = sh.d_state + 1024; sh.reg_fill = sh.d_state + 2048;
+        sh.send_cur = sh.d_state + 3072; sh.send_end = sh.d_state + 4096;
+    }
+    sh.ready = true; sh.buffers = false;
+    *sub_bits = sh.sub_bits; *l1_bits = sh.b1; *buffer_keys = sh.cap_keys;
+    return OK_SUCCESS;
+}
+
+// d_peer_buffers[r] = rank r's level-1 buffer as mapped in THIS process (own buffer included), cap_keys each
+OK_EXPORT int ok_shard_set_buffers(ok_counter* c, void* const* d_peer_buffers, uint64_t cap_keys) {
+    if (!c || !d_peer_buffers) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_set_buffers: NULL argument");
+    ShardState& sh = c->shard;
+    if (!sh.ready) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_set_buffers: call ok_shard_geometry first");
+    if (cap_keys < sh.cap_keys) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_set_buffers: buffers hold %llu keys, %llu needed",
+                                               (unsigned long long)cap_keys, (unsigned long long)sh.cap_keys);
+    for (int r = 0; r < c->n_shards; ++r) {
+        if (!d_peer_buffers[r] || ((uintptr_t)d_peer_buffers[r] & 15u)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_set_buffers: bad buffer of rank %d", r);
+        sh.peer[r] = (unsigned long long*)d_peer_buffers[r];
+    }
+    if (!c->buf1_external && c->d_buf1) { cudaFree(c->d_buf1); }
+    c->d_buf1 = sh.peer[c->shard_rank]; c->cap_buf1 = cap_keys; c->buf1_external = true;
+    sh.buffers = true;
+    return OK_SUCCESS;
+}
+
+namespace {
+int shard_check(ok_counter* c, const char* who, uint64_t n_bases) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "%s: NULL handle", who);
+    if (!c->shard.ready || !c->shard.buffers) return set_err(OK_ERR_INVALID_ARGUMENT, "%s: ok_shard_geometry / ok_shard_set_buffers first", who);
+    if (n_bases > c->shard.n_bases_max) return set_err(OK_ERR_INVALID_ARGUMENT, "%s: batch larger than the agreed maximum", who);
+    if (c->run_state != RUN_NONE || c->occupied) return set_err(OK_ERR_INVALID_ARGUMENT, "%s: the counter holds a result; clear it first", who);
+    return OK_SUCCESS;
+}
+OkPartCfg shard_global_cfg(const ok_counter* c, unsigned bits) {   // bins over the WHOLE key space: (owner, ...) ids
+    OkPartCfg cfg{}; cfg.key_shift = 64 - 2 * c->k; cfg.shard_log2 = 0; cfg.b1 = c->shard.g + bits; cfg.b2 = 0;
+    return cfg;
+}
+}  // namespace
+
+// d_hist_fine[n_ranks << sub_bits] += sampled k-mers per (owner, sub-partition); d_hist_l1[n_ranks << l1_bits] = per (owner, level-1 bin)
+OK_EXPORT int ok_shard_sample_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                                     uint64_t n_records, uint32_t* d_hist_fine, uint32_t* d_hist_l1) {
+    TRY(shard_check(c, "ok_shard_sample_device", n_bases));
+    if (!d_hist_fine || !d_hist_l1) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_sample_device: NULL histogram");
+    if (n_bases && ((uintptr_t)d_bases & 15u)) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
+    const ShardState& sh = c->shard;
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    CU(cudaEventRecord(c->ev_a, c->s_main));
+    CU(cudaMemsetAsync(d_hist_fine, 0, ((size_t)c->n_shards << sh.sub_bits) * sizeof(unsigned), c->s_main));
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    if (n_tiles && n_records) {
+        const uint64_t sampled = (n_tiles + sh.stride - 1) / sh.stride;
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((sampled + 7) / 8, (uint64_t)grid_sm * 8));
+        auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_sample<true> : k_part_sample<false>;
+        LAUNCH(kern, blocks, 256, 0, c->s_main, d_bases, n_bases, d_rec_offsets, n_records, n_tiles, (uint64_t)sh.stride, c->k,
+               shard_global_cfg(c, sh.sub_bits), d_hist_fine);
+    }
+    LAUNCH(k_shard_l1_hist, (unsigned)(c->n_shards << sh.b1), 128, 0, c->s_main, d_hist_fine, sh.b2, d_hist_l1);
+    CU(cudaEventRecord(c->ev_b, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&c->ms_route, c->ev_a, c->ev_b);
+    return OK_SUCCESS;
+}
+
+// d_hist_mine[1 << sub_bits]: the fine histogram summed over the ranks, this rank's slice (reduce-scatter);
+// d_hist_l1_all[n_ranks][n_ranks << l1_bits]: every rank's level-1 histogram (all-gather);
+// d_cursors_out[n_ranks << l1_bits]: where this sender stopped in each of its regions (to be all-gathered).
+OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                                      uint64_t n_records, const uint32_t* d_hist_mine, const uint32_t* d_hist_l1_all,
+                                      uint32_t* d_cursors_out) {
+    TRY(shard_check(c, "ok_shard_scatter_device", n_bases));
+    if (!d_hist_mine || !d_hist_l1_all || !d_cursors_out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_scatter_device: NULL argument");
+    ShardState& sh = c->shard;
+    PartPlan& pl = c->pl; pl = PartPlan{};
+    pl.cfg.key_shift = 64 - 2 * c->k; pl.cfg.shard_log2 = sh.g; pl.cfg.b1 = sh.b1; pl.cfg.b2 = sh.b2;
+    pl.n_sub = 1u << sh.sub_bits; pl.n_bin1 = 1u << sh.b1; pl.stride = sh.stride; pl.sharded = true;
+    const uint64_t n_units = sh.n_bases_max + sh.n_bases_max / 4;
+    pl.big_count = n_units / pl.n_sub > 5800;
+    TRY(part_layout(c, n_units, OK_TILE_BASES, 0, pl));
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    CU(cudaEventRecord(c->ev_p[0], c->s_main));
+    // my sub-partitions (as the receiver) from the summed sample; my regions and my cursors in every owner's buffer
+    CU(cudaMemcpyAsync(pl.hist, d_hist_mine, pl.n_sub * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->s_main));
+    LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)sh.cap_keys, pl.chunk_sum);
+    LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)sh.cap_keys, pl.cfg.b2,
+           pl.chunk_sum, (unsigned)pl.cap_bound, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
+    LAUNCH(k_shard_plan, 1, 1024, 0, c->s_main, d_hist_l1_all, sh.g, (unsigned)c->shard_rank, sh.b1, sh.stride,
+           (unsigned)(std::min<uint64_t>(c->cap_buf1, 0xFFFFFFF0ull) & ~1ull), sh.reg_beg, sh.reg_end, sh.send_cur, sh.send_end);
+    CU(cudaEventRecord(c->ev_p[1], c->s_main));
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    if (n_tiles && n_records) {
+        OkPeerOut po{}; po.shift = sh.b1;
+        for (int r = 0; r < c->n_shards; ++r) po.p[r] = sh.peer[r];
+        const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;
+        const uint64_t tpw = std::max<uint64_t>(1, (n_tiles + max_warps - 1) / max_warps);
+        const unsigned blocks = (unsigned)((n_tiles + 8 * tpw - 1) / (8 * tpw));
+        auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true, true> : k_part_scatter_bases<false, true>;
+        TRY(set_smem(kern, sizeof(OkScatterSmem)));
+        OkPartCfg cfg = shard_global_cfg(c, sh.b1);      // level-1 bin id = (owner, bin)
+        LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, (uint64_t)0, n_tiles, tpw, c->k,
+               cfg, sh.send_cur, (const unsigned*)sh.send_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
+               c->d_stats->route_counts, po);
+    }
+    CU(cudaMemcpyAsync(d_cursors_out, sh.send_cur, ((size_t)c->n_shards << sh.b1) * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->s_main));
+    CU(cudaEventRecord(c->ev_p[2], c->s_main));
+    TRY(read_stats(c));
+    CU(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_p[0], c->ev_p[2]); c->ms_route += ms;
+    if (c->h_stats->spill_n) {
+        // a region overflowed: the spilled k-mers belong to OTHER ranks, this rank cannot count them
+        CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        c->h_stats->spill_n = 0;
+        return set_err(OK_ERR_INTERNAL, "sharded scatter overflowed a sampled region; count this batch through the two-pass route instead");
+    }
+    return OK_SUCCESS;
+}
+
+// d_cursors_all[n_ranks][n_ranks << l1_bits]: the all-gathered d_cursors_out of every rank
+OK_EXPORT int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all) {
+    if (!c || !d_cursors_all) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_count_device: NULL argument");
+    if (!c->pl.sharded || c->run_state != RUN_NONE) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_count_device: no scattered batch pending");
+    ShardState& sh = c->shard;
+    PartPlan& pl = c->pl;
+    const uint64_t windows_before = c->windows;
+    LAUNCH(k_shard_fills, 1, 1024, 0, c->s_main, d_cursors_all, sh.g, (unsigned)c->shard_rank, sh.b1, sh.reg_beg, sh.reg_end,
+           sh.reg_fill, sh.d_received);
+    CU(cudaMemcpyAsync(&c->h_part->received, sh.d_received, 8, cudaMemcpyDeviceToHost, c->s_main));
+    if (pl.cfg.b2 == 0) return set_err(OK_ERR_INTERNAL, "sharded path needs two scatter levels");
+    TRY(part_finish(c, pl));
+    c->windows = windows_before + c->h_part->received;
+    CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    const int r = part_absorb_spills(c, windows_before);
+    return r == PART_RETRY ? set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list") : r;
 }
 
 OK_EXPORT int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t** d_kmers,

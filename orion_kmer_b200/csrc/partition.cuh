@@ -31,12 +31,8 @@
 #define OK_CT_SLOTS 8192u
 #define OK_CT_PAD 512u            // tail padding = displacement bound of the monotone table
 #define OK_CT_THREADS 512u
-// fast count kernel: hashed shared-memory table + position buckets
-#define OK_C2_SLOTS 8192u         // hashed table slots
-#define OK_C2_MAXKEYS 6144u       // largest sub-partition it takes (75 % load if all keys are distinct)
-#define OK_C2_BUCKETS 1024u       // position buckets that order the distinct keys (2 per thread)
+// fast count kernel: hashed shared-memory table + position buckets (sizes: OkCount2Cfg)
 #define OK_C2_BUCKET_MAX 32u      // a fuller bucket defers the sub-partition to the generic kernel
-#define OK_C2_THREADS 512u
 
 struct OkPartCfg {
     unsigned key_shift;    // 64 - 2k
@@ -70,7 +66,7 @@ struct OkPartSpill { OkSpill sp; OkDevStats* st; };
 
 // multi-GPU routing: bin b of the scatter is owner rank b and its keys go to that rank's
 // receive buffer -- peer memory mapped over NVLink (CUDA IPC), or local memory for b == self
-struct OkPeerOut { unsigned long long* p[8]; };
+struct OkPeerOut { unsigned long long* p[8]; unsigned shift; };   // owner of scatter bin b = b >> shift
 
 // scalars of one batch, device resident (host reads them once, at the end)
 struct OkPartScalars {
@@ -96,7 +92,8 @@ k_part_sample(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_
                 ok_lane_windows(pc, cc, okmask, k, [&](int, uint64_t key) {
                     atomicAdd(&hist[ok_phi_sub(ok_part_phi(key, cfg), cfg)], 1u);
                 });
-            });
+            }, /*halo=*/stride == 1);   // a sampled tile stands alone (half the reads when the source is host memory);
+                                        // stride 1 is an exact count, so there the halo windows must be seen
 }
 __global__ void __launch_bounds__(256)
 k_part_sample_keys(const unsigned long long* __restrict__ keys, uint64_t n, uint64_t stride, OkPartCfg cfg,
@@ -168,7 +165,7 @@ k_part_plan_sums(const unsigned* __restrict__ hist, unsigned n_sub, unsigned str
 }
 __global__ void __launch_bounds__(1024)
 k_part_plan(unsigned* __restrict__ hist, unsigned n_sub, unsigned stride, unsigned n_units, unsigned b2,
-            const unsigned long long* __restrict__ chunk_sum,
+            const unsigned long long* __restrict__ chunk_sum, unsigned cap_limit,
             unsigned* __restrict__ beg, unsigned* __restrict__ cursor, unsigned* __restrict__ cap_end,
             unsigned* __restrict__ beg1, unsigned* __restrict__ cursor1, unsigned* __restrict__ end1,
             OkPartScalars* __restrict__ sc) {
@@ -178,12 +175,16 @@ k_part_plan(unsigned* __restrict__ hist, unsigned n_sub, unsigned stride, unsign
     const unsigned p = blockIdx.x * 1024u + threadIdx.x;
     const unsigned cap = p < n_sub ? ok_part_capacity(hist[p], stride, n_units) : 0u;
     unsigned total;
-    const unsigned run = (unsigned)before + ok_block_excl_scan_1024(cap, wsum, &total);
+    const unsigned long long run64 = before + ok_block_excl_scan_1024(cap, wsum, &total);
     if (p < n_sub) {
-        beg[p] = run; cursor[p] = run; cap_end[p] = run + cap;
+        // the host sized the buffers from a bound on the sum; regions past it (never, unless the
+        // caller's estimate of a sharded batch was off) get no room and spill instead
+        const unsigned run = (unsigned)min(run64, (unsigned long long)cap_limit);
+        const unsigned end = (unsigned)min(run64 + cap, (unsigned long long)cap_limit);
+        beg[p] = run; cursor[p] = run; cap_end[p] = end;
         hist[p] = 0;
         if (b2 && (p & ((1u << b2) - 1u)) == 0) { beg1[p >> b2] = run; cursor1[p >> b2] = run; }
-        if (b2 && (p & ((1u << b2) - 1u)) == (1u << b2) - 1u) end1[p >> b2] = run + cap;
+        if (b2 && (p & ((1u << b2) - 1u)) == (1u << b2) - 1u) end1[p >> b2] = end;
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { sc->total_cap = (unsigned)before + total; sc->n_items = 0; sc->n_deferred = 0; }
 }
@@ -212,8 +213,9 @@ k_part_scan(const unsigned* __restrict__ v, unsigned n, const unsigned long long
 // one CTA, 1024 threads: level-1 fills -> work items of <= OK_PART_TILE keys for the level-2 scatter
 __global__ void __launch_bounds__(1024)
 k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cursor1, const unsigned* __restrict__ end1,
-             unsigned n_bin1, unsigned* __restrict__ item_off, unsigned* __restrict__ item_n,
+             unsigned n_bin1, unsigned bin_shift, unsigned* __restrict__ item_off, unsigned* __restrict__ item_n,
              unsigned* __restrict__ item_bin, OkPartScalars* __restrict__ sc) {
+    // the sharded path hands in (bin, sender) regions: region r belongs to level-1 bin r >> bin_shift
     __shared__ unsigned wsum[33];
     __shared__ unsigned s_first[OK_PART_MAXBINS + 1], s_b0[OK_PART_MAXBINS], s_fill[OK_PART_MAXBINS];
     const unsigned b = threadIdx.x;
@@ -231,9 +233,64 @@ k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cur
         const unsigned i = o - s_first[lo];
         item_off[o] = s_b0[lo] + i * OK_PART_TILE;
         item_n[o] = min(OK_PART_TILE, s_fill[lo] - i * OK_PART_TILE);
-        item_bin[o] = lo;
+        item_bin[o] = lo >> bin_shift;
     }
     if (threadIdx.x == 0) sc->n_items = total;
+}
+
+// ------------------------------------------------------- sharded (multi-GPU) planning kernels --
+// Fused exchange: a sender scatters straight into the owners' level-1 regions (peer memory).  Every
+// level-1 bin of an owner is cut into one region per sender, sized from THAT sender's sample, so a
+// sender reserves space with local atomics only.  All ranks derive the same layout from the
+// all-gathered level-1 histograms l1_all[sender][owner][bin].
+__global__ void __launch_bounds__(128)
+k_shard_l1_hist(const unsigned* __restrict__ hist_fine, unsigned b2, unsigned* __restrict__ l1) {
+    __shared__ unsigned wsum[4];
+    unsigned v = 0;
+    for (unsigned j = threadIdx.x; j < (1u << b2); j += 128u) v += hist_fine[((size_t)blockIdx.x << b2) + j];
+    v = (unsigned)ok_warp_sum(v);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) l1[blockIdx.x] = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+}
+
+// one CTA, 1024 threads.  Region r = bin * G + sender of owner o starts where the capacities before it end.
+__global__ void __launch_bounds__(1024)
+k_shard_plan(const unsigned* __restrict__ l1_all, unsigned g_log2, unsigned me, unsigned b1, unsigned stride,
+             unsigned buf_cap, unsigned* __restrict__ reg_beg, unsigned* __restrict__ reg_end,
+             unsigned* __restrict__ send_cur, unsigned* __restrict__ send_end) {
+    __shared__ unsigned wsum[33];
+    const unsigned G = 1u << g_log2, n_bin1 = 1u << b1, n_reg = n_bin1 << g_log2;
+    const unsigned r = threadIdx.x, b = r >> g_log2, s = r & (G - 1u);
+    for (unsigned o = 0; o < G; ++o) {
+        const unsigned cap = r < n_reg ? ok_part_capacity(l1_all[((size_t)s * G + o) * n_bin1 + b], stride, buf_cap) : 0u;
+        unsigned total;
+        const unsigned start = ok_block_excl_scan_1024(cap, wsum, &total);
+        if (r < n_reg) {
+            const unsigned lo = min(start, buf_cap), hi = (unsigned)min((unsigned long long)start + cap, (unsigned long long)buf_cap);
+            if (s == me) { send_cur[o * n_bin1 + b] = lo; send_end[o * n_bin1 + b] = hi; }
+            if (o == me) { reg_beg[r] = lo; reg_end[r] = hi; }
+        }
+    }
+}
+
+// cursors of every sender after the scatter (all-gathered) -> fill of each of my regions; their sum
+// is the number of k-mers this rank received
+__global__ void __launch_bounds__(1024)
+k_shard_fills(const unsigned* __restrict__ cur_all, unsigned g_log2, unsigned me, unsigned b1,
+              const unsigned* __restrict__ reg_beg, const unsigned* __restrict__ reg_end,
+              unsigned* __restrict__ reg_fill, unsigned long long* __restrict__ n_received) {
+    __shared__ unsigned long long wsum[33];
+    const unsigned G = 1u << g_log2, n_bin1 = 1u << b1, n_reg = n_bin1 << g_log2;
+    const unsigned r = threadIdx.x, b = r >> g_log2, s = r & (G - 1u);
+    unsigned long long got = 0;
+    if (r < n_reg) {
+        const unsigned e = min(cur_all[((size_t)s * G + me) * n_bin1 + b], reg_end[r]);
+        reg_fill[r] = e;
+        got = e > reg_beg[r] ? e - reg_beg[r] : 0u;
+    }
+    got = ok_block_sum_1024(got, wsum);
+    if (threadIdx.x == 0) *n_received = got;
 }
 
 // ------------------------------------------------------------- shared multisplit machinery --
@@ -269,7 +326,7 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
             const unsigned b = ok_part_bin<LEVEL>(key[q], cfg);
             const unsigned r = atomicAdd(&sm.hg[b].x, 1u);
             if (r < cap) sm.stage[(b << cap_log2) + r] = key[q];
-            else ok_part_put(key[q], atomicAdd(&cursors[b], 1u), bin_end[b], PEER ? peer->p[b] : out, ps);
+            else ok_part_put(key[q], atomicAdd(&cursors[b], 1u), bin_end[b], PEER ? peer->p[b >> peer->shift] : out, ps);
         }
     __syncthreads();
     after_stage();
@@ -300,7 +357,7 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
         for (unsigned t = (wb0 << cap_log2) + lane; t < t_end; t += 32) {
             const unsigned b = t >> cap_log2, r = t & (cap - 1u);
             const uint2 h = sm.hg[b];
-            if (r < h.x) (PEER ? peer->p[b] : out)[h.y + r] = sm.stage[t];
+            if (r < h.x) (PEER ? peer->p[b >> peer->shift] : out)[h.y + r] = sm.stage[t];
         }
     }
     __syncwarp();
@@ -460,30 +517,39 @@ k_part_flat_items(unsigned n_keys, unsigned* __restrict__ item_off, unsigned* __
 // variants no longer share a slot the way they must under an order-preserving placement.
 // (2) order the distinct keys only: bucket them by the next 10 position bits (two sweeps over the
 // table around one block scan), insertion-sort each bucket (~1 key per bucket), emit coalesced.
-struct OkCount2Smem {
-    unsigned long long tkey[OK_C2_SLOTS];          // 64 KB
-    unsigned tcnt[OK_C2_SLOTS / 2];                // two 16-bit counts per word (a count <= 6144)
-    unsigned short newl[OK_C2_MAXKEYS];            // table slots of the distinct keys, in claim order
-    unsigned short sidx[OK_C2_MAXKEYS];            // the same, grouped by bucket
-    unsigned boff[OK_C2_BUCKETS];                  // bucket histogram -> bucket end offsets
-    unsigned wsum[18];
+// Two sizes: <13> = 8192 slots, sub-partitions up to 6144 keys, 512 threads, 2 CTAs per SM (the
+// normal case); <14> = 16384 slots, up to 12288 keys, 1024 threads, 1 CTA per SM (batches whose
+// sub-partitions cannot be made smaller: 8-GPU routing, > 1.2 G keys per batch).
+template <int LOG2> struct OkCount2Cfg {
+    static constexpr unsigned SLOTS = 1u << LOG2, MAXKEYS = 3u << (LOG2 - 2), THREADS = 1u << (LOG2 - 4),
+                              BUCKETS = 1u << (LOG2 - 3), WARPS = THREADS / 32u;
+};
+template <int LOG2> struct OkCount2Smem {
+    using C = OkCount2Cfg<LOG2>;
+    unsigned long long tkey[C::SLOTS];             // 64 KB / 128 KB
+    unsigned tcnt[C::SLOTS / 2];                   // two 16-bit counts per word (a count <= MAXKEYS < 65536)
+    unsigned short newl[C::MAXKEYS];               // table slots of the distinct keys, in claim order
+    unsigned short sidx[C::MAXKEYS];               // the same, grouped by bucket
+    unsigned boff[C::BUCKETS];                     // bucket histogram -> bucket end offsets
+    unsigned wsum[34];
     unsigned n_new;
 };
 
-__device__ __forceinline__ unsigned ok_c2_hash(uint64_t key) {
+template <int LOG2> __device__ __forceinline__ unsigned ok_c2_hash(uint64_t key) {
     uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
     x *= 0x85EBCA6Bu;
-    return x >> 19;      // 13 bits: OK_C2_SLOTS == 8192
+    return x >> (32 - LOG2);
 }
-__device__ __forceinline__ unsigned ok_c2_bucket(uint64_t key, const OkPartCfg& cfg, unsigned sub_bits) {
-    return (ok_part_phi(key, cfg) << sub_bits) >> 22;     // 10 bits: OK_C2_BUCKETS == 1024
+template <int LOG2> __device__ __forceinline__ unsigned ok_c2_bucket(uint64_t key, const OkPartCfg& cfg, unsigned sub_bits) {
+    return (ok_part_phi(key, cfg) << sub_bits) >> (32 - (LOG2 - 3));     // the next LOG2-3 position bits
 }
-__device__ __forceinline__ void ok_c2_add(OkCount2Smem& sm, unsigned s) {
+template <int LOG2> __device__ __forceinline__ void ok_c2_add(OkCount2Smem<LOG2>& sm, unsigned s) {
     atomicAdd(&sm.tcnt[s >> 1], 1u << ((s & 1u) << 4));
 }
 // key not found at its first probe (cur = what was read there): walk on, claim an empty slot.
 // The thread that claims a slot also files the new distinct key: claim list + bucket histogram.
-__device__ __forceinline__ void ok_c2_insert_slow(OkCount2Smem& sm, unsigned long long key, unsigned s,
+template <int LOG2>
+__device__ __forceinline__ void ok_c2_insert_slow(OkCount2Smem<LOG2>& sm, unsigned long long key, unsigned s,
                                                   unsigned long long cur, const OkPartCfg& cfg, unsigned sub_bits) {
     for (;;) {
         if (cur == OK_EMPTY_KEY) {
@@ -491,24 +557,27 @@ __device__ __forceinline__ void ok_c2_insert_slow(OkCount2Smem& sm, unsigned lon
             if (cur == OK_EMPTY_KEY) {
                 ok_c2_add(sm, s);
                 sm.newl[atomicAdd(&sm.n_new, 1u)] = (unsigned short)s;
-                atomicAdd(&sm.boff[ok_c2_bucket(key, cfg, sub_bits)], 1u);
+                atomicAdd(&sm.boff[ok_c2_bucket<LOG2>(key, cfg, sub_bits)], 1u);
                 return;
             }
         }
         if (cur == key) { ok_c2_add(sm, s); return; }
-        s = (s + 1u) & (OK_C2_SLOTS - 1u);
+        s = (s + 1u) & (OkCount2Cfg<LOG2>::SLOTS - 1u);
         cur = sm.tkey[s];
     }
 }
 
-__global__ void __launch_bounds__(OK_C2_THREADS, 2)
+template <int LOG2>
+__global__ void __launch_bounds__(OkCount2Cfg<LOG2>::THREADS, LOG2 == 13 ? 2 : 1)
 k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ beg,
              const unsigned* __restrict__ fill_end /* cursor after the scatter */,
              const unsigned* __restrict__ cap_end, unsigned n_sub, OkPartCfg cfg,
              unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct,
              unsigned* __restrict__ deferred, OkPartScalars* __restrict__ scal) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OkCount2Smem& sm = *reinterpret_cast<OkCount2Smem*>(smem_raw);
+    using C = OkCount2Cfg<LOG2>;
+    constexpr unsigned OK_C2_SLOTS = C::SLOTS, OK_C2_MAXKEYS = C::MAXKEYS, OK_C2_THREADS = C::THREADS, OK_C2_BUCKETS = C::BUCKETS;
+    OkCount2Smem<LOG2>& sm = *reinterpret_cast<OkCount2Smem<LOG2>*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned sub_bits = cfg.b1 + cfg.b2;
     {
@@ -547,7 +616,7 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
                 nx[q] = i < n ? __ldcs(keys + i) : OK_EMPTY_KEY;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { hs[q] = ok_c2_hash(kk[q]); cur[q] = sm.tkey[hs[q]]; }
+            for (int q = 0; q < 4; ++q) { hs[q] = ok_c2_hash<LOG2>(kk[q]); cur[q] = sm.tkey[hs[q]]; }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (kk[q] == OK_EMPTY_KEY) continue;                 // canonical k-mers never equal the sentinel
@@ -565,11 +634,11 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
         if (lane == 31) sm.wsum[wid] = inc;
         const int crowded = __syncthreads_or(ha > OK_C2_BUCKET_MAX || hb > OK_C2_BUCKET_MAX);
         if (wid == 0) {
-            const unsigned w = lane < 16 ? sm.wsum[lane] : 0u;
+            const unsigned w = lane < (int)C::WARPS ? sm.wsum[lane] : 0u;
             unsigned winc = w;
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, winc, o); if (lane >= o) winc += y; }
-            if (lane < 16) sm.wsum[lane] = winc - w;
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, winc, o); if (lane >= o) winc += y; }
+            if (lane < (int)C::WARPS) sm.wsum[lane] = winc - w;
         }
         __syncthreads();
         if (!crowded) {
@@ -579,14 +648,14 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             // ---- (3) the distinct keys into bucket order (boff[b] ends up as the END of bucket b)
             for (unsigned i = threadIdx.x; i < tot; i += OK_C2_THREADS) {
                 const unsigned s = sm.newl[i];
-                sm.sidx[atomicAdd(&sm.boff[ok_c2_bucket(sm.tkey[s], cfg, sub_bits)], 1u)] = (unsigned short)s;
+                sm.sidx[atomicAdd(&sm.boff[ok_c2_bucket<LOG2>(sm.tkey[s], cfg, sub_bits)], 1u)] = (unsigned short)s;
             }
             __syncthreads();
             // ---- (4) rank inside the bucket (~1 key per bucket) = final position; emit
             for (unsigned i = threadIdx.x; i < tot; i += OK_C2_THREADS) {
                 const unsigned s = sm.sidx[i];
                 const unsigned long long key = sm.tkey[s];
-                const unsigned b = ok_c2_bucket(key, cfg, sub_bits);
+                const unsigned b = ok_c2_bucket<LOG2>(key, cfg, sub_bits);
                 const unsigned lo = b ? sm.boff[b - 1] : 0u, hi = sm.boff[b];
                 unsigned pos = lo;
                 for (unsigned j = lo; j < hi; ++j) pos += sm.tkey[sm.sidx[j]] < key ? 1u : 0u;

@@ -36,14 +36,17 @@ class ShardedCounter:
     receive buffer (CUDA-IPC peer memory over NVLink); the only collectives left are a world x world
     count matrix and a barrier.  fused=False: bucket locally, NCCL all_to_all_single, then count."""
 
-    def __init__(self, ok, torch, dist, k, norm_mode=0, fused=True):
+    def __init__(self, ok, torch, dist, k, norm_mode=0, fused=2):
         self.ok, self.torch, self.dist = ok, torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.counter = ok.KmerCounter(k, norm_mode)
         self.counter.set_shard(self.rank, self.world)
-        self.fused = fused
+        # 2: sharded scatter (sample, then ONE extraction pass that writes level-1 partitioned k-mers into
+        #    the owners' buffers); 1: two-pass fused route (count, then scatter by owner); 0: NCCL all-to-all
+        self.fused = int(fused)
         self.d_send = None
         self.recv, self.recv_cap, self.peer_ptrs = None, 0, None
+        self.geom = None
         self.t = {}
 
     # ---- receive buffer shared with the peers (collective) ----
@@ -76,8 +79,60 @@ class ShardedCounter:
         self.recv, self.recv_cap, self.peer_ptrs = None, 0, None
 
     def count_batch_device(self, d_bases, n_bases, d_off, n_reads):
-        if self.fused:
+        if self.fused == 2:
+            return self._count_sharded(d_bases, n_bases, d_off, n_reads)
+        if self.fused == 1:
             return self._count_fused(d_bases, n_bases, d_off, n_reads)
+        return self._count_unfused(d_bases, n_bases, d_off, n_reads)
+
+    def _count_sharded(self, d_bases, n_bases, d_off, n_reads):
+        """sample -> [reduce-scatter + all-gather of the histograms] -> scatter into the owners' level-1
+        regions over NVLink -> [all-gather of the cursors: also the barrier] -> level 2 + count."""
+        torch, dist, W = self.torch, self.dist, self.world
+        t0 = time.perf_counter()
+        nmax = torch.tensor([n_bases], device="cuda", dtype=torch.int64)
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+        nmax = int(nmax.item())
+        if self.geom is None or nmax > self.geom["nmax"]:
+            sub_bits, l1_bits, cap = self.counter.shard_geometry(nmax)
+            self._ensure_recv(cap)
+            self.counter.shard_set_buffers(self.peer_ptrs, self.recv_cap)
+            i32 = dict(dtype=torch.int32, device="cuda")
+            self.geom = {"nmax": nmax, "sub_bits": sub_bits, "l1_bits": l1_bits,
+                         "hist_fine": torch.empty(W << sub_bits, **i32), "hist_l1": torch.empty(W << l1_bits, **i32),
+                         "hist_mine": torch.empty(1 << sub_bits, **i32), "l1_all": torch.empty(W * (W << l1_bits), **i32),
+                         "cursors": torch.empty(W << l1_bits, **i32), "cur_all": torch.empty(W * (W << l1_bits), **i32),
+                         "flag": torch.empty(1, **i32)}
+        g = self.geom
+        self.counter.shard_sample_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
+                                         g["hist_fine"].data_ptr(), g["hist_l1"].data_ptr())
+        dist.reduce_scatter_tensor(g["hist_mine"], g["hist_fine"])
+        dist.all_gather_into_tensor(g["l1_all"], g["hist_l1"])
+        torch.cuda.current_stream().synchronize()
+        t1 = time.perf_counter()
+        ok_flag = 1
+        try:
+            self.counter.shard_scatter_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
+                                              g["hist_mine"].data_ptr(), g["l1_all"].data_ptr(), g["cursors"].data_ptr())
+        except self.ok.OrionError:
+            ok_flag = 0
+        t2 = time.perf_counter()
+        g["flag"].fill_(ok_flag)
+        dist.all_reduce(g["flag"], op=dist.ReduceOp.MIN)
+        dist.all_gather_into_tensor(g["cur_all"], g["cursors"])      # every sender has finished writing into my buffer
+        all_ok = int(g["flag"].item())
+        t3 = time.perf_counter()
+        if not all_ok:          # a sampled region overflowed somewhere: every rank recounts through the exact route
+            self.counter.clear()
+            return self._count_unfused(d_bases, n_bases, d_off, n_reads)
+        self.counter.shard_count_device(g["cur_all"].data_ptr())
+        t4 = time.perf_counter()
+        st = self.counter.stats()
+        self.t = {"route_ms": (t2 - t0) * 1e3, "route_count_ms": (t1 - t0) * 1e3, "route_scatter_ms": (t2 - t1) * 1e3,
+                  "exchange_ms": (t3 - t2) * 1e3, "count_ms": (t4 - t3) * 1e3,
+                  "sent_kmers": float("nan"), "sent_off_rank": float("nan"), "recv_kmers": int(st["n_windows"])}
+
+    def _count_unfused(self, d_bases, n_bases, d_off, n_reads):
         torch = self.torch
         if self.d_send is None or self.d_send.numel() < n_bases:
             self.d_send = torch.empty(n_bases, dtype=torch.int64, device=d_bases.device)
@@ -141,7 +196,7 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
     h_off = torch.from_numpy(off.view(np.int64))
     d_bases = h_bases.cuda()
     d_off = h_off.cuda()
-    sc = ShardedCounter(ok, torch, dist, K, fused=os.environ.get("ORION_FUSED", "1") != "0")
+    sc = ShardedCounter(ok, torch, dist, K, fused=int(os.environ.get("ORION_FUSED", "2")))
 
     def step_device():
         sc.clear()
@@ -192,7 +247,12 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
     if rank == 0:
         peak, peak_src = measured_peak()
         alg_step = total_bases * 1.5 + windows * 16.0 + distinct * 32.0 + windows * 32.0   # + multi-GPU 32 W (8d)
-        nvlink_bytes = mean["sent_off_rank"] * 8.0
+        off_rank = mean["sent_off_rank"]
+        if not np.isfinite(off_rank):       # the sharded scatter does not count per owner: the prior balances the owners
+            off_rank = windows / world * (world - 1) / world
+            mean["sent_off_rank"] = off_rank
+            mean["sent_kmers"] = windows / world
+        nvlink_bytes = off_rank * 8.0
         line = {
             "metric": metric, "value": total_bases / dt, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -210,8 +270,9 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
                                     "transfer_ms": mean.get("route_scatter_ms", mean["exchange_ms"]),
                                     "achieved_GBs_per_rank": nvlink_bytes / (mean.get("route_scatter_ms", mean["exchange_ms"]) / 1e3) / 1e9,
                                     "peak_GBs": 770.0, "peak_source": "B200_PROFILING.md peer copy per direction",
-                                    "mode": "fused into k_part_scatter_bases<PEER> (writes into peer memory)" if sc.fused
-                                            else "NCCL all_to_all_single"}},
+                                    "mode": {2: "sharded scatter: k_part_scatter_bases<PEER> writes level-1 partitioned k-mers into the owners' buffers",
+                                             1: "two-pass route fused into k_part_scatter_bases<PEER> (writes into peer memory)",
+                                             0: "NCCL all_to_all_single"}[sc.fused]}},
             "phases_ms": mean,
             "table": {"windows": int(windows), "distinct": int(distinct), "rank0_distinct": int(n_out),
                       "spilled": int(st["n_spilled"])},
