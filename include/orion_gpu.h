@@ -172,6 +172,8 @@ typedef struct ok_counter_stats {
     /* partitioned (one-shot) path: device time per phase of the last batch          */
     float ms_sample, ms_scatter1, ms_scatter2, ms_count, ms_compact;
     int partitioned;         /* 1 when the current result is a sorted run     */
+    float ms_push;           /* sharded scatter: bulk copies into the peers' buffers (NVLink) */
+    uint64_t n_deferred;     /* sub-partitions the fast count kernel left to the generic one  */
 } ok_counter_stats;
 int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out);
 

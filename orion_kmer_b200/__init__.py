@@ -57,7 +57,7 @@ class CounterStats(C.Structure):
                 ("n_grows", C.c_uint64), ("ms_insert", C.c_float), ("ms_readout", C.c_float),
                 ("ms_fill", C.c_float), ("ms_route", C.c_float), ("ms_sample", C.c_float),
                 ("ms_scatter1", C.c_float), ("ms_scatter2", C.c_float), ("ms_count", C.c_float),
-                ("ms_compact", C.c_float), ("partitioned", C.c_int)]
+                ("ms_compact", C.c_float), ("partitioned", C.c_int), ("ms_push", C.c_float), ("n_deferred", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -131,7 +131,10 @@ struct ShardState {
     unsigned g = 0, sub_bits = 0, b1 = 0, b2 = 0, stride = 16;
     uint64_t n_bases_max = 0, cap_keys = 0;
     unsigned long long* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    unsigned* d_state = nullptr;             // reg_beg | reg_end | reg_fill | send_cur | send_end (1024 entries each)
+    unsigned* d_state = nullptr;             // reg_beg | reg_end | reg_fill | send_cur | send_end (1024 entries each) | OkShardBlocks
+    OkShardBlocks* d_blk = nullptr;
+    unsigned* d_snap = nullptr;              // cursor snapshots between the chunks of a sharded scatter, 9 x 1024
+    OkShardBlocks* h_blk = nullptr;          // page-locked mirror
     unsigned *reg_beg = nullptr, *reg_end = nullptr, *reg_fill = nullptr, *send_cur = nullptr, *send_end = nullptr;
     unsigned long long* d_received = nullptr;
 };
@@ -157,7 +160,7 @@ struct ok_counter {
     OkDevStats* h_stats = nullptr;    // pinned mirror
     OkSpill spill{};
     uint64_t occupied = 0, windows = 0, bases_seen = 0, max_disp = 0, spilled_total = 0, grows = 0;
-    float ms_insert = 0, ms_readout = 0, ms_fill = 0, ms_route = 0;
+    float ms_insert = 0, ms_readout = 0, ms_fill = 0, ms_route = 0, ms_push = 0;
     // staging for host batches
     uint8_t* d_bases = nullptr; uint64_t cap_bases = 0;
     uint64_t* d_off = nullptr; uint64_t cap_off = 0;
@@ -178,6 +181,7 @@ struct ok_counter {
     uint64_t n_run = 0, n_deferred = 0;
     unsigned long long* d_buf1 = nullptr; uint64_t cap_buf1 = 0;
     unsigned long long* d_buf2 = nullptr; uint64_t cap_buf2 = 0;
+    unsigned long long* d_cnt = nullptr; uint64_t cap_cnt = 0;       // counts of the runs when d_buf1 is peer-mapped memory (measured: 25 % slower to write)
     unsigned* d_meta = nullptr; uint64_t cap_meta = 0;               // per-batch arrays of the plan (32-bit words)
     float ms_sample = 0, ms_scatter1 = 0, ms_scatter2 = 0, ms_count = 0, ms_compact = 0;
     cudaEvent_t ev_p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -436,6 +440,7 @@ int part_layout(ok_counter* c, uint64_t n_units, uint64_t unit_chunk, uint64_t f
     if (c->buf1_external) {
         if (c->cap_buf1 < pl.cap_bound + 16) return set_err(OK_ERR_INVALID_ARGUMENT, "the peer buffer is too small for this batch (%llu < %llu keys)",
                                                             (unsigned long long)c->cap_buf1, (unsigned long long)pl.cap_bound + 16);
+        TRY(dev_reserve(&c->d_cnt, &c->cap_cnt, pl.cap_bound + 16));
     } else {
         TRY(dev_reserve(&c->d_buf1, &c->cap_buf1, pl.cap_bound + 16));   // level-1 output, later the counts of the runs
     }
@@ -456,9 +461,9 @@ int part_finish(ok_counter* c, PartPlan& pl) {
     if (pl.cfg.b2 > 0) {
         if (pl.sharded)   // (bin, sender) regions filled by the peers
             LAUNCH(k_part_items, 1, 1024, 0, c->s_main, c->shard.reg_beg, c->shard.reg_fill, c->shard.reg_end, pl.n_bin1 << c->shard.g,
-                   c->shard.g, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
+                   pl.n_bin1 - 1u, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
         else
-            LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, 0u, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
+            LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, 0xFFFFFFFFu, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
         TRY(set_smem(k_part_scatter_keys<2>, sizeof(OkScatterKeysSmem)));
         LAUNCH(k_part_scatter_keys<2>, grid_sm * 2, 256, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
                pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps);
@@ -466,19 +471,20 @@ int part_finish(ok_counter* c, PartPlan& pl) {
     CU(cudaEventRecord(c->ev_p[3], c->s_main));
     // count every sub-partition in shared memory; sorted runs land in place, counts in d_buf1
     unsigned* d_nd = pl.hist;   // the sample histogram is no longer needed (k_part_plan zeroed it)
+    unsigned long long* cnt_out = c->buf1_external ? c->d_cnt : c->d_buf1;
     if (pl.big_count) {
         TRY(set_smem(k_part_count<14>, sizeof(OkCount2Smem<14>)));
         LAUNCH(k_part_count<14>, std::min<unsigned>(pl.n_sub, grid_sm), OkCount2Cfg<14>::THREADS, sizeof(OkCount2Smem<14>), c->s_main,
-               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, pl.deferred, pl.scal);
+               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal);
     } else {
         TRY(set_smem(k_part_count<13>, sizeof(OkCount2Smem<13>)));
         LAUNCH(k_part_count<13>, std::min<unsigned>(pl.n_sub, grid_sm * 2), OkCount2Cfg<13>::THREADS, sizeof(OkCount2Smem<13>), c->s_main,
-               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, c->d_buf1, d_nd, pl.deferred, pl.scal);
+               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal);
     }
     const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
     TRY(set_smem(k_part_count_generic, ct_smem));
     LAUNCH(k_part_count_generic, grid_sm, OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg, pl.cursor, pl.cap_end,
-           pl.deferred, pl.scal, pl.cfg, c->d_buf1, d_nd, ps);
+           pl.deferred, pl.scal, pl.cfg, cnt_out, d_nd, ps);
     CU(cudaEventRecord(c->ev_p[4], c->s_main));
     LAUNCH(k_part_scan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, d_nd, pl.n_sub, pl.chunk_sum);
     LAUNCH(k_part_scan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, d_nd, pl.n_sub, pl.chunk_sum, pl.scan);
@@ -547,7 +553,8 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
         const uint64_t sampled = (n_tiles + pl.stride - 1) / pl.stride;
         const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((sampled + 7) / 8, (uint64_t)grid_sm * 8));
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_sample<true> : k_part_sample<false>;
-        LAUNCH(kern, blocks, 256, 0, c->s_main, sample_src, n_bases, d_off, n_rec, n_tiles, (uint64_t)pl.stride, c->k, pl.cfg, pl.hist);
+        LAUNCH(kern, blocks, 256, 0, c->s_main, sample_src, n_bases, d_off, n_rec, n_tiles, (uint64_t)pl.stride, c->k, pl.cfg, pl.hist,
+               /*halo=*/sample_src == d_bases);
     }
     LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.chunk_sum);
     LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.cfg.b2,
@@ -571,7 +578,7 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
             const unsigned blocks = (unsigned)((t1 - t0 + 8 * tpw - 1) / (8 * tpw));
             LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, visible, d_off, n_rec, t0, t1, tpw, c->k,
                    pl.cfg, two ? pl.cursor1 : pl.cursor, (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2,
-                   (OkPartSpill{c->spill, c->d_stats}), &c->d_stats->windows, OkPeerOut{});
+                   (OkPartSpill{c->spill, c->d_stats}), &c->d_stats->windows, OkPeerOut{}, OkPushDesc{});
         }
     }
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
@@ -616,7 +623,7 @@ int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
 void launch_compact(ok_counter* c, unsigned p0, unsigned p1, unsigned long long* out_keys, unsigned long long* out_counts) {
     const PartPlan& pl = c->pl;
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
-    LAUNCH(k_part_compact, std::min<unsigned>(p1 - p0, grid_sm * 8), 256, 0, c->s_main, c->d_buf2, c->d_buf1, pl.beg, pl.hist,
+    LAUNCH(k_part_compact, std::min<unsigned>(p1 - p0, grid_sm * 8), 256, 0, c->s_main, c->d_buf2, c->buf1_external ? c->d_cnt : c->d_buf1, pl.beg, pl.hist,
            pl.scan, p0, p1, out_keys, out_counts);
 }
 
@@ -825,8 +832,8 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
     cudaFree(c->spill.keys); cudaFree(c->spill.incs);
     cudaFree(c->d_bases); cudaFree(c->d_off); cudaFree(c->d_tiles);
     cudaFree(c->d_out_keys); cudaFree(c->d_out_counts);
-    cudaFree(c->d_run_keys); cudaFree(c->d_run_counts); if (!c->buf1_external) cudaFree(c->d_buf1); cudaFree(c->d_buf2);
-    cudaFree(c->shard.d_state); cudaFree(c->shard.d_received);
+    cudaFree(c->d_run_keys); cudaFree(c->d_run_counts); if (!c->buf1_external) cudaFree(c->d_buf1); cudaFree(c->d_buf2); cudaFree(c->d_cnt);
+    cudaFree(c->shard.d_state); cudaFree(c->shard.d_received); cudaFree(c->shard.d_snap); cudaFreeHost(c->shard.h_blk);
     cudaFree(c->d_meta); cudaFreeHost(c->h_part);
     for (auto e : c->ev_p) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_chunks) cudaEventDestroy(e);
@@ -1095,7 +1102,7 @@ OK_EXPORT int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_ba
     TRY(set_smem(kern, sizeof(OkScatterSmem)));
     LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, (uint64_t)0, n_tiles, tpw, c->k,
            cfg, d_cur, (const unsigned*)d_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
-           c->d_stats->route_counts, po);
+           c->d_stats->route_counts, po, OkPushDesc{});
     CU(cudaEventRecord(c->ev_b, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
     CU(cudaGetLastError());
@@ -1127,10 +1134,12 @@ OK_EXPORT int ok_shard_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* s
     sh.cap_keys = part_cap_bound(n_units, 1u << bits, sh.stride, OK_TILE_BASES) + 16;
     if (sh.cap_keys >= (1ull << 32)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_geometry: batch too large for 32-bit offsets");
     if (!sh.d_state) {
-        CU(cudaMalloc((void**)&sh.d_state, 5 * 1024 * sizeof(unsigned)));
+        CU(cudaMalloc((void**)&sh.d_state, 5 * 1024 * sizeof(unsigned) + sizeof(OkShardBlocks)));
+        CU(cudaMallocHost((void**)&sh.h_blk, sizeof(OkShardBlocks)));
+        CU(cudaMalloc((void**)&sh.d_snap, 9 * 1024 * sizeof(unsigned)));
         CU(cudaMalloc((void**)&sh.d_received, 8));
         sh.reg_beg = sh.d_state; sh.reg_end = sh.d_state + 1024; sh.reg_fill = sh.d_state + 2048;
-        sh.send_cur = sh.d_state + 3072; sh.send_end = sh.d_state + 4096;
+        sh.send_cur = sh.d_state + 3072; sh.send_end = sh.d_state + 4096; sh.d_blk = (OkShardBlocks*)(sh.d_state + 5120);
     }
     sh.ready = true; sh.buffers = false;
     *sub_bits = sh.sub_bits; *l1_bits = sh.b1; *buffer_keys = sh.cap_keys;
@@ -1184,7 +1193,7 @@ OK_EXPORT int ok_shard_sample_device(ok_counter* c, const uint8_t* d_bases, uint
         const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((sampled + 7) / 8, (uint64_t)grid_sm * 8));
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_sample<true> : k_part_sample<false>;
         LAUNCH(kern, blocks, 256, 0, c->s_main, d_bases, n_bases, d_rec_offsets, n_records, n_tiles, (uint64_t)sh.stride, c->k,
-               shard_global_cfg(c, sh.sub_bits), d_hist_fine);
+               shard_global_cfg(c, sh.sub_bits), d_hist_fine, /*halo=*/true);
     }
     LAUNCH(k_shard_l1_hist, (unsigned)(c->n_shards << sh.b1), 128, 0, c->s_main, d_hist_fine, sh.b2, d_hist_l1);
     CU(cudaEventRecord(c->ev_b, c->s_main));
@@ -1207,7 +1216,7 @@ OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uin
     pl.cfg.key_shift = 64 - 2 * c->k; pl.cfg.shard_log2 = sh.g; pl.cfg.b1 = sh.b1; pl.cfg.b2 = sh.b2;
     pl.n_sub = 1u << sh.sub_bits; pl.n_bin1 = 1u << sh.b1; pl.stride = sh.stride; pl.sharded = true;
     const uint64_t n_units = sh.n_bases_max + sh.n_bases_max / 4;
-    pl.big_count = n_units / pl.n_sub > 5800;
+    pl.big_count = sh.n_bases_max / pl.n_sub > 5800;     // what arrives is balanced: about one batch worth of k-mers
     TRY(part_layout(c, n_units, OK_TILE_BASES, 0, pl));
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
     CU(cudaEventRecord(c->ev_p[0], c->s_main));
@@ -1217,26 +1226,56 @@ OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uin
     LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)sh.cap_keys, pl.cfg.b2,
            pl.chunk_sum, (unsigned)pl.cap_bound, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
     LAUNCH(k_shard_plan, 1, 1024, 0, c->s_main, d_hist_l1_all, sh.g, (unsigned)c->shard_rank, sh.b1, sh.stride,
-           (unsigned)(std::min<uint64_t>(c->cap_buf1, 0xFFFFFFF0ull) & ~1ull), sh.reg_beg, sh.reg_end, sh.send_cur, sh.send_end);
+           (unsigned)(std::min<uint64_t>(c->cap_buf1, 0xFFFFFFF0ull) & ~1ull), sh.reg_beg, sh.reg_end, sh.send_cur, sh.send_end, sh.d_blk);
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    const unsigned n_regs = (unsigned)c->n_shards << sh.b1;
+    // bins = (owner, level-1 bin).  Own keys land in the own level-1 buffer; the other owners' blocks are built
+    // in the level-2 buffer (idle until the count) and pushed over NVLink by the pusher CTAs of the NEXT chunk's
+    // launch, so the transfer of chunk i overlaps the extraction of chunk i+1.
+    OkPushDesc pd{};
+    pd.end = sh.send_end; pd.blk = sh.d_blk; pd.local = c->d_buf2; pd.n_regs = n_regs; pd.b1 = sh.b1; pd.me = (unsigned)c->shard_rank;
+    for (int r = 0; r < c->n_shards; ++r) pd.peer[r] = sh.peer[r];
+    unsigned n_chunks = 8;
+    if (const char* ev = getenv("ORION_SHARD_CHUNKS")) n_chunks = (unsigned)std::max(1, atoi(ev));
+    if (n_tiles < 64 * (uint64_t)n_chunks) n_chunks = 1;
+    n_chunks = std::min(n_chunks, 8u);
+    unsigned* snap = sh.d_snap;                                   // cursor snapshots: [0] = before chunk 0, [i+1] = after chunk i
+    CU(cudaMemcpyAsync(snap, sh.send_cur, n_regs * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->s_main));
     if (n_tiles && n_records) {
         OkPeerOut po{}; po.shift = sh.b1;
-        for (int r = 0; r < c->n_shards; ++r) po.p[r] = sh.peer[r];
-        const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;
-        const uint64_t tpw = std::max<uint64_t>(1, (n_tiles + max_warps - 1) / max_warps);
-        const unsigned blocks = (unsigned)((n_tiles + 8 * tpw - 1) / (8 * tpw));
+        for (int r = 0; r < c->n_shards; ++r) po.p[r] = r == c->shard_rank ? c->d_buf1 : c->d_buf2;
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true, true> : k_part_scatter_bases<false, true>;
         TRY(set_smem(kern, sizeof(OkScatterSmem)));
-        OkPartCfg cfg = shard_global_cfg(c, sh.b1);      // level-1 bin id = (owner, bin)
-        LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, (uint64_t)0, n_tiles, tpw, c->k,
-               cfg, sh.send_cur, (const unsigned*)sh.send_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
-               c->d_stats->route_counts, po);
+        const OkPartCfg cfg = shard_global_cfg(c, sh.b1);      // level-1 bin id = (owner, bin)
+        const uint64_t per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
+        for (unsigned ch = 0; ch < n_chunks; ++ch) {
+            const uint64_t t0 = ch * per_chunk, t1 = std::min<uint64_t>(n_tiles, t0 + per_chunk);
+            if (t1 <= t0) { CU(cudaMemcpyAsync(snap + (size_t)(ch + 1) * 1024, sh.send_cur, n_regs * 4, cudaMemcpyDeviceToDevice, c->s_main)); continue; }
+            pd.enabled = ch ? 1u : 0u;
+            pd.prev = snap + (size_t)(ch ? ch - 1 : 0) * 1024; pd.cur = snap + (size_t)ch * 1024;
+            const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;
+            const uint64_t tpw = std::max<uint64_t>(1, (t1 - t0 + max_warps - 1) / max_warps);
+            const unsigned blocks = (unsigned)((t1 - t0 + 8 * tpw - 1) / (8 * tpw));
+            LAUNCH(kern, blocks, 288, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, t0, t1, tpw, c->k,
+                   cfg, sh.send_cur, (const unsigned*)sh.send_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
+                   c->d_stats->route_counts, po, pd);
+            CU(cudaMemcpyAsync(snap + (size_t)(ch + 1) * 1024, sh.send_cur, n_regs * 4, cudaMemcpyDeviceToDevice, c->s_main));
+        }
+    } else {
+        for (unsigned ch = 0; ch < n_chunks; ++ch)
+            CU(cudaMemcpyAsync(snap + (size_t)(ch + 1) * 1024, sh.send_cur, n_regs * 4, cudaMemcpyDeviceToDevice, c->s_main));
     }
-    CU(cudaMemcpyAsync(d_cursors_out, sh.send_cur, ((size_t)c->n_shards << sh.b1) * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->s_main));
+    CU(cudaEventRecord(c->ev_a, c->s_main));
+    // the last chunk's push is the only exposed one
+    pd.enabled = 1u; pd.prev = snap + (size_t)(n_chunks - 1) * 1024; pd.cur = snap + (size_t)n_chunks * 1024;
+    LAUNCH(k_shard_push, grid_sm * 4, 256, 0, c->s_main, pd);
+    LAUNCH(k_shard_export, 1, 1024, 0, c->s_main, sh.send_cur, sh.g, (unsigned)c->shard_rank, sh.b1, sh.d_blk, d_cursors_out);
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
     TRY(read_stats(c));
     CU(cudaGetLastError());
+    cudaEventElapsedTime(&c->ms_scatter1, c->ev_p[1], c->ev_p[2]);
+    cudaEventElapsedTime(&c->ms_push, c->ev_a, c->ev_p[2]);
     float ms = 0; cudaEventElapsedTime(&ms, c->ev_p[0], c->ev_p[2]); c->ms_route += ms;
     if (c->h_stats->spill_n) {
         // a region overflowed: the spilled k-mers belong to OTHER ranks, this rank cannot count them
@@ -1344,6 +1383,7 @@ OK_EXPORT int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out) {
     out->n_grows = c->grows; out->ms_insert = c->ms_insert; out->ms_readout = c->ms_readout; out->ms_fill = c->ms_fill; out->ms_route = c->ms_route;
     out->ms_sample = c->ms_sample; out->ms_scatter1 = c->ms_scatter1; out->ms_scatter2 = c->ms_scatter2;
     out->ms_count = c->ms_count; out->ms_compact = c->ms_compact; out->partitioned = c->run_state != RUN_NONE ? 1 : 0;
+    out->ms_push = c->ms_push; out->n_deferred = c->n_deferred;
     return OK_SUCCESS;
 }
 

@@ -82,7 +82,10 @@ template <bool MAP_U>
 __global__ void __launch_bounds__(256)
 k_part_sample(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
               uint64_t n_rec, uint64_t n_tiles, uint64_t stride, unsigned k, OkPartCfg cfg,
-              unsigned* __restrict__ hist) {
+              unsigned* __restrict__ hist, bool halo) {
+    // halo = false: a sampled tile stands alone (no read of the tile before it: half the PCIe traffic when
+    // the source is the caller's host buffer); the k-1 windows reaching back are not seen, a ~3 % low
+    // bias that only the generously padded single-GPU plan tolerates.  Exact counts need the halo.
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -92,8 +95,7 @@ k_part_sample(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_
                 ok_lane_windows(pc, cc, okmask, k, [&](int, uint64_t key) {
                     atomicAdd(&hist[ok_phi_sub(ok_part_phi(key, cfg), cfg)], 1u);
                 });
-            }, /*halo=*/stride == 1);   // a sampled tile stands alone (half the reads when the source is host memory);
-                                        // stride 1 is an exact count, so there the halo windows must be seen
+            }, halo || stride == 1);
 }
 __global__ void __launch_bounds__(256)
 k_part_sample_keys(const unsigned long long* __restrict__ keys, uint64_t n, uint64_t stride, OkPartCfg cfg,
@@ -213,9 +215,9 @@ k_part_scan(const unsigned* __restrict__ v, unsigned n, const unsigned long long
 // one CTA, 1024 threads: level-1 fills -> work items of <= OK_PART_TILE keys for the level-2 scatter
 __global__ void __launch_bounds__(1024)
 k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cursor1, const unsigned* __restrict__ end1,
-             unsigned n_bin1, unsigned bin_shift, unsigned* __restrict__ item_off, unsigned* __restrict__ item_n,
+             unsigned n_bin1, unsigned bin_mask, unsigned* __restrict__ item_off, unsigned* __restrict__ item_n,
              unsigned* __restrict__ item_bin, OkPartScalars* __restrict__ sc) {
-    // the sharded path hands in (bin, sender) regions: region r belongs to level-1 bin r >> bin_shift
+    // the sharded path hands in (sender, bin) regions: region r belongs to level-1 bin r & bin_mask
     __shared__ unsigned wsum[33];
     __shared__ unsigned s_first[OK_PART_MAXBINS + 1], s_b0[OK_PART_MAXBINS], s_fill[OK_PART_MAXBINS];
     const unsigned b = threadIdx.x;
@@ -233,16 +235,20 @@ k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cur
         const unsigned i = o - s_first[lo];
         item_off[o] = s_b0[lo] + i * OK_PART_TILE;
         item_n[o] = min(OK_PART_TILE, s_fill[lo] - i * OK_PART_TILE);
-        item_bin[o] = lo >> bin_shift;
+        item_bin[o] = lo & bin_mask;
     }
     if (threadIdx.x == 0) sc->n_items = total;
 }
 
 // ------------------------------------------------------- sharded (multi-GPU) planning kernels --
-// Fused exchange: a sender scatters straight into the owners' level-1 regions (peer memory).  Every
-// level-1 bin of an owner is cut into one region per sender, sized from THAT sender's sample, so a
-// sender reserves space with local atomics only.  All ranks derive the same layout from the
-// all-gathered level-1 histograms l1_all[sender][owner][bin].
+// Fused exchange without a counting pass.  An owner's level-1 buffer is cut into one BLOCK per sender
+// and each block into one region per level-1 bin, sized from THAT sender's sample -- so a sender
+// reserves space with local atomics only, and what it produces for one owner is one contiguous
+// block.  The sender's extraction kernel multisplits by (owner, bin): its own keys go straight into
+// its own buffer, the other owners' blocks are built in local memory (the level-2 buffer, idle at
+// that point) and pushed over NVLink as one bulk copy per peer -- measured 4x faster than scattering
+// 24-byte runs into peer memory directly.  All ranks derive the same layout from the all-gathered
+// level-1 histograms l1_all[sender][owner][bin].
 __global__ void __launch_bounds__(128)
 k_shard_l1_hist(const unsigned* __restrict__ hist_fine, unsigned b2, unsigned* __restrict__ l1) {
     __shared__ unsigned wsum[4];
@@ -254,24 +260,61 @@ k_shard_l1_hist(const unsigned* __restrict__ hist_fine, unsigned b2, unsigned* _
     if (threadIdx.x == 0) l1[blockIdx.x] = wsum[0] + wsum[1] + wsum[2] + wsum[3];
 }
 
-// one CTA, 1024 threads.  Region r = bin * G + sender of owner o starts where the capacities before it end.
+struct OkShardBlocks {              // per owner o: the block this sender fills
+    unsigned remote_start[8];       // where it starts in owner o's buffer
+    unsigned local_base[8];         // where it is built locally (index into the send buffer; unused for o == me)
+    unsigned cap[8];                // its capacity in keys
+};
+
+// one CTA, 1024 threads.  Region r = sender * n_bin1 + bin of owner o starts where the capacities before it end.
+// send_cur / send_end are in the coordinates the scatter kernel writes with: the own buffer for o == me,
+// the local send buffer otherwise.
 __global__ void __launch_bounds__(1024)
 k_shard_plan(const unsigned* __restrict__ l1_all, unsigned g_log2, unsigned me, unsigned b1, unsigned stride,
              unsigned buf_cap, unsigned* __restrict__ reg_beg, unsigned* __restrict__ reg_end,
-             unsigned* __restrict__ send_cur, unsigned* __restrict__ send_end) {
+             unsigned* __restrict__ send_cur, unsigned* __restrict__ send_end, OkShardBlocks* __restrict__ blk) {
     __shared__ unsigned wsum[33];
+    __shared__ OkShardBlocks sb;
     const unsigned G = 1u << g_log2, n_bin1 = 1u << b1, n_reg = n_bin1 << g_log2;
-    const unsigned r = threadIdx.x, b = r >> g_log2, s = r & (G - 1u);
+    const unsigned r = threadIdx.x, s = r >> b1, b = r & (n_bin1 - 1u);
     for (unsigned o = 0; o < G; ++o) {
         const unsigned cap = r < n_reg ? ok_part_capacity(l1_all[((size_t)s * G + o) * n_bin1 + b], stride, buf_cap) : 0u;
         unsigned total;
         const unsigned start = ok_block_excl_scan_1024(cap, wsum, &total);
         if (r < n_reg) {
             const unsigned lo = min(start, buf_cap), hi = (unsigned)min((unsigned long long)start + cap, (unsigned long long)buf_cap);
-            if (s == me) { send_cur[o * n_bin1 + b] = lo; send_end[o * n_bin1 + b] = hi; }
+            if (s == me) {
+                send_cur[o * n_bin1 + b] = lo; send_end[o * n_bin1 + b] = hi;
+                if (b == 0) sb.remote_start[o] = lo;
+                if (b == n_bin1 - 1u) sb.cap[o] = hi;      // block end for now
+            }
             if (o == me) { reg_beg[r] = lo; reg_end[r] = hi; }
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (unsigned o = 0; o < G; ++o) {
+            sb.cap[o] -= sb.remote_start[o];
+            sb.local_base[o] = run;
+            if (o != me) run += sb.cap[o];
+        }
+        *blk = sb;
+    }
+    __syncthreads();
+    const unsigned i = threadIdx.x, o = i >> b1;
+    if (i < n_reg && o != me) {      // other owners' regions: remote coordinates -> the local send buffer
+        const unsigned shift = sb.local_base[o] - sb.remote_start[o];
+        send_cur[i] += shift; send_end[i] += shift;
+    }
+}
+
+// this sender's cursors after the scatter, back in the owners' coordinates (to be all-gathered)
+__global__ void __launch_bounds__(1024)
+k_shard_export(const unsigned* __restrict__ send_cur, unsigned g_log2, unsigned me, unsigned b1,
+               const OkShardBlocks* __restrict__ blk, unsigned* __restrict__ out) {
+    const unsigned i = threadIdx.x, o = i >> b1;
+    if (i < ((1u << b1) << g_log2)) out[i] = o == me ? send_cur[i] : send_cur[i] - blk->local_base[o] + blk->remote_start[o];
 }
 
 // cursors of every sender after the scatter (all-gathered) -> fill of each of my regions; their sum
@@ -282,7 +325,7 @@ k_shard_fills(const unsigned* __restrict__ cur_all, unsigned g_log2, unsigned me
               unsigned* __restrict__ reg_fill, unsigned long long* __restrict__ n_received) {
     __shared__ unsigned long long wsum[33];
     const unsigned G = 1u << g_log2, n_bin1 = 1u << b1, n_reg = n_bin1 << g_log2;
-    const unsigned r = threadIdx.x, b = r >> g_log2, s = r & (G - 1u);
+    const unsigned r = threadIdx.x, s = r >> b1, b = r & (n_bin1 - 1u);
     unsigned long long got = 0;
     if (r < n_reg) {
         const unsigned e = min(cur_all[((size_t)s * G + me) * n_bin1 + b], reg_end[r]);
@@ -297,6 +340,13 @@ k_shard_fills(const unsigned* __restrict__ cur_all, unsigned g_log2, unsigned me
 // Slotted staging: the 8192 staging slots are split evenly among the bins of the level, a key's
 // rank inside its bin (one shared-memory atomicAdd) is its slot, so one pass stages the round.
 // A bin that outgrows its slots in a round sends the excess straight to global memory.
+// CTA barrier of the 256 scatter threads.  The sharded (PEER) scatter carries a ninth warp that only
+// copies to the peers and never joins these barriers, hence a named barrier with an explicit count.
+template <bool PEER> __device__ __forceinline__ void ok_scatter_sync() {
+    if (PEER) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __syncthreads();
+}
+
 struct OkScatterSmem {
     unsigned long long stage[OK_STAGE_SLOTS];
     uint2 hg[OK_PART_MAXBINS];   // x: keys of the bin this round (zero between rounds), y: global index of its first staged key
@@ -328,7 +378,7 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
             if (r < cap) sm.stage[(b << cap_log2) + r] = key[q];
             else ok_part_put(key[q], atomicAdd(&cursors[b], 1u), bin_end[b], PEER ? peer->p[b >> peer->shift] : out, ps);
         }
-    __syncthreads();
+    ok_scatter_sync<PEER>();
     after_stage();
     // copy out.  Warp w owns staging slots [w*1024, (w+1)*1024) = a contiguous range of bins.
     // (1) one global cursor bump per non-empty bin; a bin whose region is full spills its tail here
@@ -362,7 +412,66 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
     }
     __syncwarp();
     for (unsigned i = lane; i < bins_per_warp && wb0 + i < n_bins; i += 32) sm.hg[wb0 + i].x = 0;
-    __syncthreads();
+    ok_scatter_sync<PEER>();
+}
+
+// ------------------------------------------------- sharded scatter: push fused into the scatter --
+// The batch is scattered in a few chunks (launches).  Every CTA of a launch carries a ninth warp that
+// does no scattering: it copies what the PREVIOUS chunk appended to the other owners' blocks (cursor
+// deltas prev -> cur per region, contiguous runs) from the local send buffer into the owners' buffers
+// over NVLink while the other eight warps extract and scatter the next chunk.  One kernel computes and
+// communicates; only the last chunk's push is exposed.  (Measured: an SM sustains only ~4 GB/s of
+// remote stores -- outstanding-request bound -- so the copy has to be spread over ALL SMs; dedicated
+// pusher CTAs on a few SMs reached 300 GB/s, direct 24-byte scatter runs into peer memory 175 GB/s.)
+struct OkPushDesc {
+    const unsigned* prev;                 // cursors before the chunk being pushed (local coordinates)
+    const unsigned* cur;                  // ... and after it
+    const unsigned* end;                  // region ends (a cursor past it means the rest was spilled)
+    const OkShardBlocks* blk;
+    const unsigned long long* local;      // the local send buffer
+    unsigned long long* peer[8];          // the owners' level-1 buffers
+    unsigned n_regs, b1, me, enabled;     // enabled == 0: nothing to push
+};
+
+// the calling group of `nthreads` threads (rank `tid` in it) is worker `worker` of `n_workers`: the regions are
+// cut into 8192-key pieces and dealt round robin, so the workers stay balanced whatever the region sizes are
+__device__ __forceinline__ void ok_shard_push(const OkPushDesc& d, unsigned worker, unsigned n_workers, unsigned tid, unsigned nthreads) {
+    constexpr unsigned PIECE = 8192u;
+    unsigned turn = worker;               // pieces until my next one
+    for (unsigned reg = 0; reg < d.n_regs; ++reg) {
+        const unsigned o = reg >> d.b1;
+        if (o == d.me) continue;
+        const unsigned lo0 = d.prev[reg], hi0 = min(d.cur[reg], d.end[reg]);
+        if (hi0 <= lo0) continue;
+        const unsigned n_pieces = (hi0 - lo0 + PIECE - 1u) / PIECE;
+        if (turn >= n_pieces) { turn -= n_pieces; continue; }
+        const unsigned long long* __restrict__ src = d.local;
+        // block starts are even in both coordinate systems, so index parity == 16-byte alignment on both sides
+        unsigned long long* __restrict__ dst = d.peer[o] + (long long)d.blk->remote_start[o] - (long long)d.blk->local_base[o];
+        for (; turn < n_pieces; turn += n_workers) {
+            unsigned lo = lo0 + turn * PIECE;
+            const unsigned hi = min(lo + PIECE, hi0);
+            if (lo & 1u) { if (tid == 0) dst[lo] = src[lo]; ++lo; }
+            const unsigned n2 = (hi - lo) >> 1;                         // 16-byte units
+            const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src + lo);
+            uint4* __restrict__ d4 = reinterpret_cast<uint4*>(dst + lo);
+            unsigned i = tid;
+            for (; i + 7u * nthreads < n2; i += 8u * nthreads) {       // 128 bytes in flight per thread: NVLink latency is ~2 us
+                uint4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = ok_ld_stream16(s4 + i + q * nthreads);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d4[i + q * nthreads] = v[q];
+            }
+            for (; i < n2; i += nthreads) d4[i] = ok_ld_stream16(s4 + i);
+            if (((hi - lo) & 1u) && tid == 0) dst[hi - 1] = src[hi - 1];
+        }
+        turn -= n_pieces;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_shard_push(const __grid_constant__ OkPushDesc d) {
+    ok_shard_push(d, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------------ level 1: from the bases --
@@ -370,20 +479,24 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
 // two rounds of 16 window ends per lane, so a round holds <= 4096 k-mers per CTA.  The launch
 // covers tiles [tile_begin, tile_end) -- the ingest pipeline launches it once per landed piece.
 template <bool MAP_U, bool PEER = false>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(PEER ? 288 : 256, 3)
 k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
                      uint64_t n_rec, uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp, unsigned k,
                      OkPartCfg cfg, unsigned* __restrict__ cursors, const unsigned* __restrict__ bin_end,
                      unsigned long long* __restrict__ out, OkPartSpill ps, unsigned long long* __restrict__ n_keys,
-                     const __grid_constant__ OkPeerOut peer_out) {
+                     const __grid_constant__ OkPeerOut peer_out, const __grid_constant__ OkPushDesc push) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
     const int lane = threadIdx.x & 31;
-    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (PEER && threadIdx.x >= 256) {      // the copy warp of a sharded scatter (launched with 288 threads)
+        if (push.enabled) ok_shard_push(push, blockIdx.x, gridDim.x, threadIdx.x - 256u, 32u);
+        return;
+    }
+    const uint64_t warp = blockIdx.x * 8ull + (threadIdx.x >> 5);
     const uint64_t t0 = tile_begin + warp * tiles_per_warp;
     if (tile_begin + (uint64_t)blockIdx.x * 8 * tiles_per_warp >= tile_end) return;   // whole CTA idle
     for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += 256) sm.hg[i] = make_uint2(0u, 0u);
-    __syncthreads();
+    ok_scatter_sync<PEER>();
     unsigned long long my_keys = 0;
     ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t0 + tiles_per_warp, tile_end, k, lane,
         [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {

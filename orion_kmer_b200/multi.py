@@ -114,8 +114,11 @@ class ShardedCounter:
         try:
             self.counter.shard_scatter_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
                                               g["hist_mine"].data_ptr(), g["l1_all"].data_ptr(), g["cursors"].data_ptr())
-        except self.ok.OrionError:
+        except self.ok.OrionError as e:
             ok_flag = 0
+            self.fallbacks = getattr(self, "fallbacks", 0) + 1
+            if os.environ.get("ORION_VERBOSE"):
+                print(f"[rank {self.rank}] sharded scatter failed, falling back: {e}", flush=True)
         t2 = time.perf_counter()
         g["flag"].fill_(ok_flag)
         dist.all_reduce(g["flag"], op=dist.ReduceOp.MIN)
@@ -275,7 +278,7 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
                                              0: "NCCL all_to_all_single"}[sc.fused]}},
             "phases_ms": mean,
             "table": {"windows": int(windows), "distinct": int(distinct), "rank0_distinct": int(n_out),
-                      "spilled": int(st["n_spilled"])},
+                      "spilled": int(st["n_spilled"]), "rank0_fallbacks_to_nccl_all_to_all": int(getattr(sc, "fallbacks", 0))},
             "cpu_baseline": None,
         }
         print(json.dumps(line))

@@ -1,4 +1,4 @@
-"""2-GPU parity of the sharded count (both exchange modes) against the oracle.  Needs >= 2 B200s:
+"""2-GPU parity of the sharded count (all three exchange modes: sharded scatter, two-pass fused route, NCCL all-to-all) against the oracle.  Needs >= 2 B200s:
 run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`; skipped otherwise."""
 import os
 import socket
@@ -37,7 +37,7 @@ def _worker(rank, world, port, ret):
     d_b = torch.from_numpy(bases).cuda()
     d_o = torch.from_numpy(off.view(np.int64)).cuda()
     out = {}
-    for fused in (True, False):
+    for fused in (2, 1, 0):
         sc = multi.ShardedCounter(ok, torch, dist, K, fused=fused)
         for _ in range(2):                      # twice: buffers are reused across steps
             sc.clear()
@@ -65,7 +65,7 @@ def test_two_gpu_sharded_count_matches_oracle(oracle):
     all_bases = np.concatenate([_reads(r)[0] for r in range(world)])
     all_off = np.arange(world * READS + 1, dtype=np.uint64) * np.uint64(150)
     wk, wc = oracle.count_batch(K, all_bases, all_off)
-    for fused in (True, False):
+    for fused in (2, 1, 0):
         gk = np.concatenate([t[fused][0] for t in tables])
         gc = np.concatenate([t[fused][1] for t in tables])
         assert np.array_equal(gk, wk) and np.array_equal(gc, wc), f"fused={fused}"
