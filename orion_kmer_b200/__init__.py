@@ -169,18 +169,104 @@ def host_lib():
         L.okh_synth_reads.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                       C.c_uint32, C.c_uint32, vp, C.c_int]
         L.okh_synth_mutate.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, vp]
+        # orion_io.cpp: codecs + .db
+        L.okh_io_last_error.restype = C.c_char_p
+        L.okh_read_file.restype = vp; L.okh_read_file.argtypes = [C.c_char_p, C.c_int]
+        L.okh_file_data.restype = vp; L.okh_file_data.argtypes = [vp]
+        L.okh_file_size.restype = C.c_uint64; L.okh_file_size.argtypes = [vp]
+        L.okh_file_free.argtypes = [vp]
+        L.okh_write_file.restype = C.c_int; L.okh_write_file.argtypes = [C.c_char_p, vp, C.c_uint64, C.c_int]
+        L.okh_db_new.restype = vp; L.okh_db_new.argtypes = [C.c_uint8]
+        L.okh_db_add_reference.argtypes = [vp, C.c_char_p, vp, C.c_uint64]
+        L.okh_db_k.restype = C.c_uint8; L.okh_db_k.argtypes = [vp]
+        L.okh_db_n_references.restype = C.c_uint64; L.okh_db_n_references.argtypes = [vp]
+        L.okh_db_name.restype = C.c_char_p; L.okh_db_name.argtypes = [vp, C.c_uint64]
+        L.okh_db_n_kmers.restype = C.c_uint64; L.okh_db_n_kmers.argtypes = [vp, C.c_uint64]
+        L.okh_db_kmers.restype = vp; L.okh_db_kmers.argtypes = [vp, C.c_uint64]
+        L.okh_db_free.argtypes = [vp]
+        L.okh_db_write.restype = C.c_int; L.okh_db_write.argtypes = [vp, C.c_char_p]
+        L.okh_db_read.restype = vp; L.okh_db_read.argtypes = [C.c_char_p]
         _host = L
     return _host
 
 
 def build_host(force=False):
+    """g++: liborion_host.so (framing, TSV, codecs, .db format, synthetic data) and the CLI binary
+    orion-kmer-b200 (the reference's command line over liborion_gpu.so)."""
     import subprocess
-    src = os.path.join(_HERE, "csrc", "host", "orion_host.cpp")
+    hd = os.path.join(_HERE, "csrc", "host")
+    srcs = [os.path.join(hd, "orion_host.cpp"), os.path.join(hd, "orion_io.cpp")]
     so = os.path.join(_HERE, "liborion_host.so")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["g++", "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-pthread",
-                               "-shared", "-o", so, src])
+                               "-shared", "-o", so] + srcs + ["-lz", "-ldl"])
+    cli_src = os.path.join(hd, "orion_cli.cpp")
+    exe = cli_path()
+    gpu_so = os.path.join(_HERE, "liborion_gpu.so")
+    if os.path.exists(gpu_so) and (force or not os.path.exists(exe) or
+                                   os.path.getmtime(exe) < max(os.path.getmtime(cli_src), os.path.getmtime(so))):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(os.path.dirname(_HERE), "include"),
+                               "-o", exe, cli_src, "-L", _HERE, "-lorion_gpu", "-lorion_host",
+                               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + _HERE])
     return so
+
+
+def cli_path():
+    return os.path.join(_HERE, "orion-kmer-b200")
+
+
+class IoError(OSError):
+    pass
+
+
+def read_file(path, by_magic=False):
+    """utils.rs:125-152 (codec by extension) or, by_magic, the raw read + needletail sniff of build/classify"""
+    H = host_lib()
+    h = H.okh_read_file(os.fsencode(path), 1 if by_magic else 0)
+    if not h:
+        raise IoError(H.okh_io_last_error().decode())
+    try:
+        n = H.okh_file_size(h)
+        return C.string_at(H.okh_file_data(h), n) if n else b""
+    finally:
+        H.okh_file_free(h)
+
+
+def write_file(path, data, by_extension=True):
+    """utils.rs:167-199 get_output_writer"""
+    H = host_lib()
+    buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data if data else b"\0")
+    if H.okh_write_file(os.fsencode(path), buf, len(data), 1 if by_extension else 0):
+        raise IoError(H.okh_io_last_error().decode())
+
+
+def write_kmer_db(path, k, references):
+    """db_types.rs:8-14 KmerDbV2 as bincode 1.3.3 (build.rs:141).  references: {name: uint64 array}"""
+    H = host_lib()
+    h = H.okh_db_new(k)
+    try:
+        for name, kmers in references.items():
+            a = np.ascontiguousarray(kmers, dtype=np.uint64)
+            H.okh_db_add_reference(h, name.encode(), _ptr(a), len(a))
+        if H.okh_db_write(h, os.fsencode(path)):
+            raise IoError(H.okh_io_last_error().decode())
+    finally:
+        H.okh_db_free(h)
+
+
+def read_kmer_db(path):
+    """utils.rs:37-55 load_kmer_db_v2 -> (k, {name: uint64 array in file order})"""
+    H = host_lib()
+    h = H.okh_db_read(os.fsencode(path))
+    if not h:
+        raise IoError(H.okh_io_last_error().decode())
+    try:
+        refs = {}
+        for i in range(H.okh_db_n_references(h)):
+            refs[H.okh_db_name(h, i).decode()] = _copy_out(H.okh_db_kmers(h, i), H.okh_db_n_kmers(h, i), C.c_uint64, np.uint64)
+        return H.okh_db_k(h), refs
+    finally:
+        H.okh_db_free(h)
 
 
 def _check(rc):
