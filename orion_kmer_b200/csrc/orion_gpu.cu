@@ -465,7 +465,7 @@ int part_finish(ok_counter* c, PartPlan& pl) {
         else
             LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, 0xFFFFFFFFu, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
         TRY(set_smem(k_part_scatter_keys<2>, sizeof(OkScatterKeysSmem)));
-        LAUNCH(k_part_scatter_keys<2>, grid_sm * 2, 256, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
+        LAUNCH(k_part_scatter_keys<2>, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
                pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps);
     }
     CU(cudaEventRecord(c->ev_p[3], c->s_main));
@@ -564,7 +564,7 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
         const bool two = pl.cfg.b2 > 0;
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true> : k_part_scatter_bases<false>;
         TRY(set_smem(kern, sizeof(OkScatterSmem)));
-        const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;   // 3 CTAs of 8 warps per SM (72 KB smem each)
+        const uint64_t max_warps = (uint64_t)grid_sm * (OK_SB_KPT == 16 ? 3 : 2) * OK_SB_WARPS;   // resident warps (72 KB smem per CTA)
         const uint64_t n_launch = pieces ? pieces->n_pieces : 1;
         for (uint64_t p = 0; p < n_launch; ++p) {
             uint64_t t0 = 0, t1 = n_tiles, visible = n_bases;
@@ -575,8 +575,8 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
             }
             if (t1 <= t0) continue;
             const uint64_t tpw = std::max<uint64_t>(1, (t1 - t0 + max_warps - 1) / max_warps);
-            const unsigned blocks = (unsigned)((t1 - t0 + 8 * tpw - 1) / (8 * tpw));
-            LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, visible, d_off, n_rec, t0, t1, tpw, c->k,
+            const unsigned blocks = (unsigned)((t1 - t0 + OK_SB_WARPS * tpw - 1) / (OK_SB_WARPS * tpw));
+            LAUNCH(kern, blocks, OK_SB_THREADS, sizeof(OkScatterSmem), c->s_main, d_bases, visible, d_off, n_rec, t0, t1, tpw, c->k,
                    pl.cfg, two ? pl.cursor1 : pl.cursor, (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2,
                    (OkPartSpill{c->spill, c->d_stats}), &c->d_stats->windows, OkPeerOut{}, OkPushDesc{});
         }
@@ -608,7 +608,7 @@ int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
         LAUNCH(k_part_flat_items, 64, 1024, 0, c->s_main, (unsigned)n, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
         auto kern = ((uintptr_t)d_keys & 15u) ? k_part_scatter_keys<1, false> : k_part_scatter_keys<1, true>;
         TRY(set_smem(kern, sizeof(OkScatterKeysSmem)));
-        LAUNCH(kern, grid_sm * 2, 256, sizeof(OkScatterKeysSmem), c->s_main, (const unsigned long long*)d_keys,
+        LAUNCH(kern, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, (const unsigned long long*)d_keys,
                pl.item_off, pl.item_n, pl.item_bin, pl.scal, pl.cfg, two ? pl.cursor1 : pl.cursor,
                (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2, (OkPartSpill{c->spill, c->d_stats}));
         c->windows += n;
@@ -1095,12 +1095,12 @@ OK_EXPORT int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_ba
     CU(cudaMemcpyAsync(d_end, ends, sizeof ends, cudaMemcpyHostToDevice, c->s_main));
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
-    const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;
+    const uint64_t max_warps = (uint64_t)grid_sm * (OK_SB_KPT == 16 ? 3 : 2) * OK_SB_WARPS;
     const uint64_t tpw = std::max<uint64_t>(1, (n_tiles + max_warps - 1) / max_warps);
-    const unsigned blocks = (unsigned)((n_tiles + 8 * tpw - 1) / (8 * tpw));
+    const unsigned blocks = (unsigned)((n_tiles + OK_SB_WARPS * tpw - 1) / (OK_SB_WARPS * tpw));
     auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true, true> : k_part_scatter_bases<false, true>;
     TRY(set_smem(kern, sizeof(OkScatterSmem)));
-    LAUNCH(kern, blocks, 256, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, (uint64_t)0, n_tiles, tpw, c->k,
+    LAUNCH(kern, blocks, OK_SB_THREADS, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, (uint64_t)0, n_tiles, tpw, c->k,
            cfg, d_cur, (const unsigned*)d_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
            c->d_stats->route_counts, po, OkPushDesc{});
     CU(cudaEventRecord(c->ev_b, c->s_main));
@@ -1254,10 +1254,10 @@ OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uin
             if (t1 <= t0) { CU(cudaMemcpyAsync(snap + (size_t)(ch + 1) * 1024, sh.send_cur, n_regs * 4, cudaMemcpyDeviceToDevice, c->s_main)); continue; }
             pd.enabled = ch ? 1u : 0u;
             pd.prev = snap + (size_t)(ch ? ch - 1 : 0) * 1024; pd.cur = snap + (size_t)ch * 1024;
-            const uint64_t max_warps = (uint64_t)grid_sm * 3 * 8;
+            const uint64_t max_warps = (uint64_t)grid_sm * (OK_SB_KPT == 16 ? 3 : 2) * OK_SB_WARPS;
             const uint64_t tpw = std::max<uint64_t>(1, (t1 - t0 + max_warps - 1) / max_warps);
-            const unsigned blocks = (unsigned)((t1 - t0 + 8 * tpw - 1) / (8 * tpw));
-            LAUNCH(kern, blocks, 288, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, t0, t1, tpw, c->k,
+            const unsigned blocks = (unsigned)((t1 - t0 + OK_SB_WARPS * tpw - 1) / (OK_SB_WARPS * tpw));
+            LAUNCH(kern, blocks, OK_SB_THREADS + 32, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, t0, t1, tpw, c->k,
                    cfg, sh.send_cur, (const unsigned*)sh.send_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
                    c->d_stats->route_counts, po, pd);
             CU(cudaMemcpyAsync(snap + (size_t)(ch + 1) * 1024, sh.send_cur, n_regs * 4, cudaMemcpyDeviceToDevice, c->s_main));

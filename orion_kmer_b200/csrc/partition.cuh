@@ -340,10 +340,15 @@ k_shard_fills(const unsigned* __restrict__ cur_all, unsigned g_log2, unsigned me
 // Slotted staging: the 8192 staging slots are split evenly among the bins of the level, a key's
 // rank inside its bin (one shared-memory atomicAdd) is its slot, so one pass stages the round.
 // A bin that outgrows its slots in a round sends the excess straight to global memory.
-// CTA barrier of the 256 scatter threads.  The sharded (PEER) scatter carries a ninth warp that only
+// CTA barrier of the scatter threads.  The sharded (PEER) scatter carries one extra warp that only
 // copies to the peers and never joins these barriers, hence a named barrier with an explicit count.
+#ifndef OK_SB_KPT
+#define OK_SB_KPT 8                                   // keys per thread and round in the level-1 scatter
+#endif
+#define OK_SB_THREADS (OK_PART_TILE / OK_SB_KPT)      // scatter threads per CTA (512 at 8 keys per thread)
+#define OK_SB_WARPS (OK_SB_THREADS / 32)
 template <bool PEER> __device__ __forceinline__ void ok_scatter_sync() {
-    if (PEER) asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (PEER) asm volatile("bar.sync 1, %0;" :: "n"((int)OK_SB_THREADS) : "memory");
     else __syncthreads();
 }
 
@@ -358,12 +363,12 @@ __device__ __forceinline__ void ok_part_put(unsigned long long key, unsigned dst
     else ok_spill(ps.sp, ps.st, key, 1);     // past the sampled capacity of the bin: exact, slow path
 }
 
-// One multisplit round of the CTA (all 256 threads call it together): thread-held keys
-// key[0..15] (bit q of vmask says key[q] exists) -> out, grouped by bin.  sm.hg[].x must be zero
+// One multisplit round of the CTA (all 4096/KPT threads call it together): thread-held keys
+// key[0..KPT) (bit q of vmask says key[q] exists) -> out, grouped by bin.  sm.hg[].x must be zero
 // on entry and is zero again on exit.  after_stage() runs once the round's keys have left the
 // registers of every thread (the level-2 kernel issues its next TMA load there).
-template <int LEVEL, bool PEER, class AfterStage>
-__device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_t (&key)[16], unsigned vmask,
+template <int LEVEL, bool PEER, int KPT, class AfterStage>
+__device__ __forceinline__ void ok_multisplit(OkScatterSmem& sm, const uint64_t (&key)[KPT], unsigned vmask,
                                                 const OkPartCfg& cfg, unsigned bins_log2,
                                                 unsigned* __restrict__ cursors, const unsigned* __restrict__ bin_end,
                                                 unsigned long long* __restrict__ out, const OkPartSpill& ps,
@@ -371,7 +376,7 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned cap_log2 = 13u - bins_log2, cap = 1u << cap_log2, n_bins = 1u << bins_log2;
 #pragma unroll
-    for (int q = 0; q < 16; ++q)
+    for (int q = 0; q < KPT; ++q)
         if (vmask >> q & 1u) {
             const unsigned b = ok_part_bin<LEVEL>(key[q], cfg);
             const unsigned r = atomicAdd(&sm.hg[b].x, 1u);
@@ -380,9 +385,10 @@ __device__ __forceinline__ void ok_multisplit16(OkScatterSmem& sm, const uint64_
         }
     ok_scatter_sync<PEER>();
     after_stage();
-    // copy out.  Warp w owns staging slots [w*1024, (w+1)*1024) = a contiguous range of bins.
+    // copy out.  Warp w owns an equal share of the staging slots = a contiguous range of bins.
     // (1) one global cursor bump per non-empty bin; a bin whose region is full spills its tail here
-    const unsigned bins_per_warp = n_bins >= 8 ? n_bins >> 3 : 1u;
+    constexpr unsigned NW = OK_PART_TILE / KPT / 32u;      // warps of the CTA: 8 (16 keys per thread) or 16 (8 keys per thread)
+    const unsigned bins_per_warp = n_bins >= NW ? n_bins / NW : 1u;
     const unsigned wb0 = wid * bins_per_warp;
     for (unsigned i = lane; i < bins_per_warp && wb0 + i < n_bins; i += 32) {
         const unsigned b = wb0 + i;
@@ -475,11 +481,11 @@ __global__ void __launch_bounds__(256) k_shard_push(const __grid_constant__ OkPu
 }
 
 // ------------------------------------------------------------------ level 1: from the bases --
-// The 8 warps of a CTA walk their own runs of tiles in lock step; each warp-tile is split in
-// two rounds of 16 window ends per lane, so a round holds <= 4096 k-mers per CTA.  The launch
-// covers tiles [tile_begin, tile_end) -- the ingest pipeline launches it once per landed piece.
+// The warps of a CTA walk their own runs of tiles in lock step; each warp-tile (32 window ends per
+// lane) is split in rounds of OK_SB_KPT window ends per lane, so a round holds <= 4096 k-mers per CTA.
+// The launch covers tiles [tile_begin, tile_end) -- the ingest pipeline launches it once per landed piece.
 template <bool MAP_U, bool PEER = false>
-__global__ void __launch_bounds__(PEER ? 288 : 256, 3)
+__global__ void __launch_bounds__(PEER ? OK_SB_THREADS + 32 : OK_SB_THREADS, OK_SB_KPT == 16 ? 3 : 2)
 k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
                      uint64_t n_rec, uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp, unsigned k,
                      OkPartCfg cfg, unsigned* __restrict__ cursors, const unsigned* __restrict__ bin_end,
@@ -488,28 +494,28 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
     const int lane = threadIdx.x & 31;
-    if (PEER && threadIdx.x >= 256) {      // the copy warp of a sharded scatter (launched with 288 threads)
-        if (push.enabled) ok_shard_push(push, blockIdx.x, gridDim.x, threadIdx.x - 256u, 32u);
+    if (PEER && threadIdx.x >= OK_SB_THREADS) {      // the copy warp of a sharded scatter (launched with 32 more threads)
+        if (push.enabled) ok_shard_push(push, blockIdx.x, gridDim.x, threadIdx.x - OK_SB_THREADS, 32u);
         return;
     }
-    const uint64_t warp = blockIdx.x * 8ull + (threadIdx.x >> 5);
+    const uint64_t warp = blockIdx.x * (uint64_t)OK_SB_WARPS + (threadIdx.x >> 5);
     const uint64_t t0 = tile_begin + warp * tiles_per_warp;
-    if (tile_begin + (uint64_t)blockIdx.x * 8 * tiles_per_warp >= tile_end) return;   // whole CTA idle
-    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += 256) sm.hg[i] = make_uint2(0u, 0u);
+    if (tile_begin + (uint64_t)blockIdx.x * OK_SB_WARPS * tiles_per_warp >= tile_end) return;   // whole CTA idle
+    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += OK_SB_THREADS) sm.hg[i] = make_uint2(0u, 0u);
     ok_scatter_sync<PEER>();
     unsigned long long my_keys = 0;
     ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t0, t0 + tiles_per_warp, tile_end, k, lane,
         [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {
             OkRoll roll; roll.init(pc, cc, k);
             my_keys += __popc(okmask);
+            const unsigned rev = __brev(okmask);      // window end j lives in okmask bit 31-j: bit j of rev
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint64_t key[16];
+            for (int part = 0; part < 32 / OK_SB_KPT; ++part) {
+                uint64_t key[OK_SB_KPT];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) key[q] = roll.step(16 * half + q);
-                // window end j = 16*half + q lives in okmask bit 31-j; make bit q mean key[q]
-                const unsigned vm = __brev(okmask) >> (16 * half) & 0xFFFFu;
-                ok_multisplit16<1, PEER>(sm, key, vm, cfg, cfg.b1, cursors, bin_end, out, ps, &peer_out, [] {});
+                for (int q = 0; q < OK_SB_KPT; ++q) key[q] = roll.step(OK_SB_KPT * part + q);
+                const unsigned vm = rev >> (OK_SB_KPT * part) & ((1u << OK_SB_KPT) - 1u);   // bit q <=> key[q]
+                ok_multisplit<1, PEER, OK_SB_KPT>(sm, key, vm, cfg, cfg.b1, cursors, bin_end, out, ps, &peer_out, [] {});
             }
         });
     my_keys = ok_warp_sum(my_keys);
@@ -552,8 +558,12 @@ struct OkScatterKeysSmem {
 // work item w: keys src[item_off[w] .. +item_n[w]) (<= 4096), all of level-1 bin item_bin[w].
 // item_off is even (16-byte aligned regions) and the copy is rounded up to an even key count.
 // TMA = false: plain loads (a caller's key array that is not 16-byte aligned).
+// 512 threads x 8 keys: with two CTAs per SM that is 32 resident warps to cover the shared-memory atomics
+// and the global cursor bumps of a round (the kernel is latency-, not issue-bound).
+#define OK_SK_KPT 8
+#define OK_SK_THREADS (OK_PART_TILE / OK_SK_KPT)
 template <int LEVEL, bool TMA = true>  // LEVEL 1: bin by bin1 (keys arriving from peers); LEVEL 2: bin by bin2 inside a bin1
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(OK_SK_THREADS, 2)
 k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* __restrict__ item_off,
                     const unsigned* __restrict__ item_n, const unsigned* __restrict__ item_bin,
                     const OkPartScalars* __restrict__ scal, OkPartCfg cfg, unsigned* __restrict__ cursors,
@@ -562,7 +572,7 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* 
     OkScatterKeysSmem& sm = *reinterpret_cast<OkScatterKeysSmem*>(smem_raw);
     const unsigned bins_log2 = LEVEL == 1 ? cfg.b1 : cfg.b2;
     const unsigned n_items = scal->n_items;
-    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += 256) sm.sc.hg[i] = make_uint2(0u, 0u);
+    for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += OK_SK_THREADS) sm.sc.hg[i] = make_uint2(0u, 0u);
     // LEVEL 2 reads our own level-1 buffer (even capacities, slack at the end): an odd item is
     // rounded UP to whole 16-byte units.  LEVEL 1 reads a caller's array: rounded DOWN, and the
     // odd last key is fetched with a plain load.
@@ -581,12 +591,12 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* 
     for (unsigned w = blockIdx.x; w < n_items; w += gridDim.x) {
         const unsigned n = item_n[w];
         const unsigned bin_base = LEVEL == 1 ? 0u : item_bin[w] << cfg.b2;
-        uint64_t key[16]; unsigned vm = 0;
+        uint64_t key[OK_SK_KPT]; unsigned vm = 0;
         if (TMA) {
             ok_mbar_wait(&sm.bar, phase); phase ^= 1u;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const unsigned i = q * 256 + threadIdx.x;
+            for (int q = 0; q < OK_SK_KPT; ++q) {
+                const unsigned i = q * OK_SK_THREADS + threadIdx.x;
                 key[q] = sm.in[i];
                 if (LEVEL == 1 && i + 1 == n && (n & 1u)) key[q] = src[item_off[w] + i];
                 if (i < n) vm |= 1u << q;
@@ -594,14 +604,14 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* 
         } else {
             const unsigned long long* __restrict__ keys = src + item_off[w];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const unsigned i = q * 256 + threadIdx.x;
+            for (int q = 0; q < OK_SK_KPT; ++q) {
+                const unsigned i = q * OK_SK_THREADS + threadIdx.x;
                 key[q] = 0;
                 if (i < n) { key[q] = __ldcs(keys + i); vm |= 1u << q; }
             }
         }
         const unsigned wn = w + gridDim.x;
-        ok_multisplit16<LEVEL, false>(sm.sc, key, vm, cfg, bins_log2, cursors + bin_base, bin_end + bin_base, out, ps, nullptr,
+        ok_multisplit<LEVEL, false, OK_SK_KPT>(sm.sc, key, vm, cfg, bins_log2, cursors + bin_base, bin_end + bin_base, out, ps, nullptr,
             [&] {   // every thread holds its keys in registers: the landing buffer is free again
                 if (TMA && threadIdx.x == 0 && wn < n_items) load_item(wn);
             });
