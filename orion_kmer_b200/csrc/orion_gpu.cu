@@ -400,6 +400,7 @@ void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl) {
     pl.n_sub = 1u << bits;
     pl.n_bin1 = 1u << pl.cfg.b1;
     pl.big_count = n_units / pl.n_sub > 5800;   // units bound the keys: a 6144-key table would defer too often
+    if (const char* ev = getenv("ORION_BIG_COUNT")) pl.big_count = atoi(ev) != 0;   // test hook: force the 16384-slot count kernel
 }
 
 template <class K> int set_smem(K kern, size_t bytes) {
@@ -1217,6 +1218,7 @@ OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uin
     pl.n_sub = 1u << sh.sub_bits; pl.n_bin1 = 1u << sh.b1; pl.stride = sh.stride; pl.sharded = true;
     const uint64_t n_units = sh.n_bases_max + sh.n_bases_max / 4;
     pl.big_count = sh.n_bases_max / pl.n_sub > 5800;     // what arrives is balanced: about one batch worth of k-mers
+    if (const char* ev = getenv("ORION_BIG_COUNT")) pl.big_count = atoi(ev) != 0;
     TRY(part_layout(c, n_units, OK_TILE_BASES, 0, pl));
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
     CU(cudaEventRecord(c->ev_p[0], c->s_main));

@@ -506,3 +506,21 @@ def test_sharded_scatter_matches_oracle(oracle, n_ranks):
     wk, wc = oracle.count_batch(k, all_bases, all_off)
     assert np.array_equal(np.concatenate(keys), wk)
     assert np.array_equal(np.concatenate(counts), wc)
+
+
+def test_large_table_count_kernel_variant(oracle, monkeypatch):
+    """k_part_count<14> (16384 slots, sub-partitions up to 12288 keys, one CTA per SM) is what 8-GPU routing and
+    batches beyond ~1.5 G bases use; force it on a batch the oracle can check."""
+    monkeypatch.setenv("ORION_BIG_COUNT", "1")
+    g = synth.genome(95, 300_000)
+    n = 40_000
+    bases, off = synth.reads(g, 96, n), synth.read_offsets(n)
+    wk, wc = oracle.count_batch(31, bases, off)
+    c = ok.KmerCounter(31)
+    c.set_path(2)
+    c.add_batch(bases, off)
+    st = c.stats()
+    gk, gc = c.finish()
+    c.close()
+    assert st["partitioned"] == 1 and st["n_spilled"] == 0
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
