@@ -403,6 +403,9 @@ void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl) {
     if (const char* ev = getenv("ORION_BIG_COUNT")) pl.big_count = atoi(ev) != 0;   // test hook: force the 16384-slot count kernel
 }
 
+// kernels specialised on k: 31 and 21 (BASELINE.json's configurations) get compile-time shifts, any other k the generic code
+#define OK_BY_K(k, KERN, ...) ((k) == 31 ? KERN<__VA_ARGS__, 31> : (k) == 21 ? KERN<__VA_ARGS__, 21> : KERN<__VA_ARGS__, 0>)
+
 template <class K> int set_smem(K kern, size_t bytes) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return OK_SUCCESS;
@@ -465,8 +468,9 @@ int part_finish(ok_counter* c, PartPlan& pl) {
                    pl.n_bin1 - 1u, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
         else
             LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, 0xFFFFFFFFu, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
-        TRY(set_smem(k_part_scatter_keys<2>, sizeof(OkScatterKeysSmem)));
-        LAUNCH(k_part_scatter_keys<2>, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
+        auto k_l2 = OK_BY_K(c->k, k_part_scatter_keys, 2, true);
+        TRY(set_smem(k_l2, sizeof(OkScatterKeysSmem)));
+        LAUNCH(k_l2, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
                pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps);
     }
     CU(cudaEventRecord(c->ev_p[3], c->s_main));
@@ -474,12 +478,14 @@ int part_finish(ok_counter* c, PartPlan& pl) {
     unsigned* d_nd = pl.hist;   // the sample histogram is no longer needed (k_part_plan zeroed it)
     unsigned long long* cnt_out = c->buf1_external ? c->d_cnt : c->d_buf1;
     if (pl.big_count) {
-        TRY(set_smem(k_part_count<14>, sizeof(OkCount2Smem<14>)));
-        LAUNCH(k_part_count<14>, std::min<unsigned>(pl.n_sub, grid_sm), OkCount2Cfg<14>::THREADS, sizeof(OkCount2Smem<14>), c->s_main,
+        auto k_cnt = OK_BY_K(c->k, k_part_count, 14);
+        TRY(set_smem(k_cnt, sizeof(OkCount2Smem<14>)));
+        LAUNCH(k_cnt, std::min<unsigned>(pl.n_sub, grid_sm), OkCount2Cfg<14>::THREADS, sizeof(OkCount2Smem<14>), c->s_main,
                c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal);
     } else {
-        TRY(set_smem(k_part_count<13>, sizeof(OkCount2Smem<13>)));
-        LAUNCH(k_part_count<13>, std::min<unsigned>(pl.n_sub, grid_sm * 2), OkCount2Cfg<13>::THREADS, sizeof(OkCount2Smem<13>), c->s_main,
+        auto k_cnt = OK_BY_K(c->k, k_part_count, 13);
+        TRY(set_smem(k_cnt, sizeof(OkCount2Smem<13>)));
+        LAUNCH(k_cnt, std::min<unsigned>(pl.n_sub, grid_sm * 2), OkCount2Cfg<13>::THREADS, sizeof(OkCount2Smem<13>), c->s_main,
                c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal);
     }
     const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
@@ -563,7 +569,7 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     {
         const bool two = pl.cfg.b2 > 0;
-        auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true> : k_part_scatter_bases<false>;
+        auto kern = c->norm_mode == OK_NORM_NORMALIZED ? OK_BY_K(c->k, k_part_scatter_bases, true, false) : OK_BY_K(c->k, k_part_scatter_bases, false, false);
         TRY(set_smem(kern, sizeof(OkScatterSmem)));
         const uint64_t max_warps = (uint64_t)grid_sm * (OK_SB_KPT == 16 ? 3 : 2) * OK_SB_WARPS;   // resident warps (72 KB smem per CTA)
         const uint64_t n_launch = pieces ? pieces->n_pieces : 1;
@@ -1247,7 +1253,7 @@ OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uin
     if (n_tiles && n_records) {
         OkPeerOut po{}; po.shift = sh.b1;
         for (int r = 0; r < c->n_shards; ++r) po.p[r] = r == c->shard_rank ? c->d_buf1 : c->d_buf2;
-        auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_scatter_bases<true, true> : k_part_scatter_bases<false, true>;
+        auto kern = c->norm_mode == OK_NORM_NORMALIZED ? OK_BY_K(c->k, k_part_scatter_bases, true, true) : OK_BY_K(c->k, k_part_scatter_bases, false, true);
         TRY(set_smem(kern, sizeof(OkScatterSmem)));
         const OkPartCfg cfg = shard_global_cfg(c, sh.b1);      // level-1 bin id = (owner, bin)
         const uint64_t per_chunk = (n_tiles + n_chunks - 1) / n_chunks;

@@ -484,16 +484,21 @@ __global__ void __launch_bounds__(256) k_shard_push(const __grid_constant__ OkPu
 // The warps of a CTA walk their own runs of tiles in lock step; each warp-tile (32 window ends per
 // lane) is split in rounds of OK_SB_KPT window ends per lane, so a round holds <= 4096 k-mers per CTA.
 // The launch covers tiles [tile_begin, tile_end) -- the ingest pipeline launches it once per landed piece.
-template <bool MAP_U, bool PEER = false>
+// KC: k as a compile-time constant (31 and 21, the configurations of BASELINE.json; 0 = any k at run time).
+// With k fixed the 64-bit shifts of the rolling update and of the position become immediate-operand funnel shifts.
+template <bool MAP_U, bool PEER = false, int KC = 0>
 __global__ void __launch_bounds__(PEER ? OK_SB_THREADS + 32 : OK_SB_THREADS, OK_SB_KPT == 16 ? 3 : 2)
 k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
-                     uint64_t n_rec, uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp, unsigned k,
-                     OkPartCfg cfg, unsigned* __restrict__ cursors, const unsigned* __restrict__ bin_end,
+                     uint64_t n_rec, uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp, unsigned k_in,
+                     OkPartCfg cfg_in, unsigned* __restrict__ cursors, const unsigned* __restrict__ bin_end,
                      unsigned long long* __restrict__ out, OkPartSpill ps, unsigned long long* __restrict__ n_keys,
                      const __grid_constant__ OkPeerOut peer_out, const __grid_constant__ OkPushDesc push) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OkScatterSmem& sm = *reinterpret_cast<OkScatterSmem*>(smem_raw);
     const int lane = threadIdx.x & 31;
+    const unsigned k = KC ? (unsigned)KC : k_in;
+    OkPartCfg cfg = cfg_in;
+    if (KC) cfg.key_shift = 64u - 2u * KC;
     if (PEER && threadIdx.x >= OK_SB_THREADS) {      // the copy warp of a sharded scatter (launched with 32 more threads)
         if (push.enabled) ok_shard_push(push, blockIdx.x, gridDim.x, threadIdx.x - OK_SB_THREADS, 32u);
         return;
@@ -562,14 +567,16 @@ struct OkScatterKeysSmem {
 // and the global cursor bumps of a round (the kernel is latency-, not issue-bound).
 #define OK_SK_KPT 8
 #define OK_SK_THREADS (OK_PART_TILE / OK_SK_KPT)
-template <int LEVEL, bool TMA = true>  // LEVEL 1: bin by bin1 (keys arriving from peers); LEVEL 2: bin by bin2 inside a bin1
+template <int LEVEL, bool TMA = true, int KC = 0>  // LEVEL 1: bin by bin1 (keys arriving from peers); LEVEL 2: bin by bin2 inside a bin1
 __global__ void __launch_bounds__(OK_SK_THREADS, 2)
 k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* __restrict__ item_off,
                     const unsigned* __restrict__ item_n, const unsigned* __restrict__ item_bin,
-                    const OkPartScalars* __restrict__ scal, OkPartCfg cfg, unsigned* __restrict__ cursors,
+                    const OkPartScalars* __restrict__ scal, OkPartCfg cfg_in, unsigned* __restrict__ cursors,
                     const unsigned* __restrict__ bin_end, unsigned long long* __restrict__ out, OkPartSpill ps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     OkScatterKeysSmem& sm = *reinterpret_cast<OkScatterKeysSmem*>(smem_raw);
+    OkPartCfg cfg = cfg_in;
+    if (KC) cfg.key_shift = 64u - 2u * KC;
     const unsigned bins_log2 = LEVEL == 1 ? cfg.b1 : cfg.b2;
     const unsigned n_items = scal->n_items;
     for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += OK_SK_THREADS) sm.sc.hg[i] = make_uint2(0u, 0u);
@@ -645,7 +652,8 @@ k_part_flat_items(unsigned n_keys, unsigned* __restrict__ item_off, unsigned* __
 // sub-partitions cannot be made smaller: 8-GPU routing, > 1.2 G keys per batch).
 template <int LOG2> struct OkCount2Cfg {
     static constexpr unsigned SLOTS = 1u << LOG2, MAXKEYS = 3u << (LOG2 - 2), THREADS = 1u << (LOG2 - 4),
-                              BUCKETS = 1u << (LOG2 - 3), WARPS = THREADS / 32u;
+                              BUCKETS = 1u << (LOG2 - 3), WARPS = THREADS / 32u,
+                              WQ = MAXKEYS * 2u / 8u / WARPS;      // pending-key queue entries per warp (carved from sidx): 96
 };
 template <int LOG2> struct OkCount2Smem {
     using C = OkCount2Cfg<LOG2>;
@@ -690,11 +698,11 @@ __device__ __forceinline__ void ok_c2_insert_slow(OkCount2Smem<LOG2>& sm, unsign
     }
 }
 
-template <int LOG2>
+template <int LOG2, int KC = 0>
 __global__ void __launch_bounds__(OkCount2Cfg<LOG2>::THREADS, LOG2 == 13 ? 2 : 1)
 k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ beg,
              const unsigned* __restrict__ fill_end /* cursor after the scatter */,
-             const unsigned* __restrict__ cap_end, unsigned n_sub, OkPartCfg cfg,
+             const unsigned* __restrict__ cap_end, unsigned n_sub, OkPartCfg cfg_in,
              unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct,
              unsigned* __restrict__ deferred, OkPartScalars* __restrict__ scal) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -702,6 +710,8 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
     constexpr unsigned OK_C2_SLOTS = C::SLOTS, OK_C2_MAXKEYS = C::MAXKEYS, OK_C2_THREADS = C::THREADS, OK_C2_BUCKETS = C::BUCKETS;
     OkCount2Smem<LOG2>& sm = *reinterpret_cast<OkCount2Smem<LOG2>*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    OkPartCfg cfg = cfg_in;
+    if (KC) cfg.key_shift = 64u - 2u * KC;
     const unsigned sub_bits = cfg.b1 + cfg.b2;
     {
         ulonglong2* k2 = reinterpret_cast<ulonglong2*>(sm.tkey);
@@ -723,7 +733,23 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             continue;
         }
         const unsigned long long* __restrict__ keys = src + b0;
-        // ---- (1) insert: 4 keys in flight per thread, the next 4 already loading
+        // ---- (1) insert: 4 keys in flight per thread, the next 4 already loading.  A key found at its first
+        // probe (a duplicate: ~80 % of the windows at 30x coverage) is counted on the spot by all lanes alike.
+        // The rest -- new keys and collisions -- are compacted into a per-warp queue (ballot ranks, shared
+        // memory borrowed from sidx, unused until pass 3) and drained with all lanes busy, instead of running
+        // the divergent claim loop once per key slot with a quarter of the lanes.
+        unsigned long long* wq = reinterpret_cast<unsigned long long*>(sm.sidx) + wid * C::WQ;
+        unsigned qn = 0;
+        auto drain = [&] {
+            __syncwarp();
+            for (unsigned i = lane; i < qn; i += 32) {
+                const unsigned long long key = wq[i];
+                const unsigned h = ok_c2_hash<LOG2>(key);
+                ok_c2_insert_slow(sm, key, h, sm.tkey[h], cfg, sub_bits);
+            }
+            __syncwarp();
+            qn = 0;
+        };
         unsigned long long nx[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -742,10 +768,18 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             for (int q = 0; q < 4; ++q) { hs[q] = ok_c2_hash<LOG2>(kk[q]); cur[q] = sm.tkey[hs[q]]; }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (kk[q] == OK_EMPTY_KEY) continue;                 // canonical k-mers never equal the sentinel
-                if (cur[q] == kk[q]) ok_c2_add(sm, hs[q]);           // duplicate of a key already placed: the common case
-                else ok_c2_insert_slow(sm, kk[q], hs[q], cur[q], cfg, sub_bits);
+                const bool live = kk[q] != OK_EMPTY_KEY;             // canonical k-mers never equal the sentinel
+                if (live && cur[q] == kk[q]) ok_c2_add(sm, hs[q]);   // duplicate of a key already placed: the common case
+                const bool pending = live && cur[q] != kk[q];
+                const unsigned bal = __ballot_sync(OK_FULL, pending);
+                if (bal) {
+                    const unsigned cnt = __popc(bal);
+                    if (qn + cnt > C::WQ) drain();                   // warp-uniform
+                    if (pending) wq[qn + __popc(bal & ((1u << lane) - 1u))] = kk[q];
+                    qn += cnt;
+                }
             }
+            drain();
         }
         __syncthreads();
         // ---- (2) exclusive scan of the 1024 bucket counts, two per thread
