@@ -380,7 +380,9 @@ __device__ __forceinline__ void ok_multisplit(OkScatterSmem& sm, const uint64_t 
         if (vmask >> q & 1u) {
             const unsigned b = ok_part_bin<LEVEL>(key[q], cfg);
             const unsigned r = atomicAdd(&sm.hg[b].x, 1u);
-            if (r < cap) sm.stage[(b << cap_log2) + r] = key[q];
+            // rank r of bin b sits in slot (r + b) mod cap of the bin: without the rotation the bank of a staged
+            // key depends on r alone and most ranks are 0..3, an 8-way conflict on every store (548 M per pass, ncu)
+            if (r < cap) sm.stage[(b << cap_log2) + ((r + b) & (cap - 1u))] = key[q];
             else ok_part_put(key[q], atomicAdd(&cursors[b], 1u), bin_end[b], PEER ? peer->p[b >> peer->shift] : out, ps);
         }
     ok_scatter_sync<PEER>();
@@ -399,7 +401,7 @@ __device__ __forceinline__ void ok_multisplit(OkScatterSmem& sm, const uint64_t 
             const unsigned e = bin_end[b];
             if (g + c > e) {
                 const unsigned keep = g < e ? e - g : 0u;
-                for (unsigned r = keep; r < c; ++r) ok_spill(ps.sp, ps.st, sm.stage[(b << cap_log2) + r], 1);
+                for (unsigned r = keep; r < c; ++r) ok_spill(ps.sp, ps.st, sm.stage[(b << cap_log2) + ((r + b) & (cap - 1u))], 1);
                 c = keep;
             }
         }
@@ -411,7 +413,7 @@ __device__ __forceinline__ void ok_multisplit(OkScatterSmem& sm, const uint64_t 
         const unsigned t_end = (wb0 + bins_per_warp) << cap_log2;
 #pragma unroll 4
         for (unsigned t = (wb0 << cap_log2) + lane; t < t_end; t += 32) {
-            const unsigned b = t >> cap_log2, r = t & (cap - 1u);
+            const unsigned b = t >> cap_log2, r = (t - b) & (cap - 1u);      // undo the rotation: slot -> rank
             const uint2 h = sm.hg[b];
             if (r < h.x) (PEER ? peer->p[b >> peer->shift] : out)[h.y + r] = sm.stage[t];
         }
