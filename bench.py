@@ -116,6 +116,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
+def bind_to_gpu_numa_node(gpu):
+    """Run this rank (and first-touch its page-locked buffers) on the CPUs next to its GPU: with 8 ranks
+    on a two-socket host, buffers on the wrong node cross the socket link on every H2D / D2H copy."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def pinned_array(ok, nbytes, dtype):
     p = C.c_void_p()
     ok._check(ok.lib().ok_host_alloc(C.byref(p), nbytes))
@@ -212,6 +238,7 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local)
     ok.init(local)
 
     n_reads = args.reads
@@ -219,7 +246,7 @@ def run_ours(args):
     if world > 1:
         from orion_kmer_b200 import multi
         return multi.bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config,
-                           ClockSampler, measured_peak, METRIC)
+                           ClockSampler, measured_peak, METRIC, numa_node)
 
     g, bases, off = make_workload(ok, synth, n_reads, genome_len)
     n_bases = len(bases)
@@ -321,8 +348,9 @@ def run_ours(args):
         "e2e": {"value": n_bases / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3,
                 "h2d_bytes_per_step": int(n_bases + (n_reads + 1) * 8), "d2h_bytes_per_step": int(16 * n_out),
                 "add_batch_ms": float(np.mean(e2e_t["add_batch_ms"])), "finish_ms": float(np.mean(e2e_t["finish_ms"])),
-                "note": "add_batch = H2D pieces overlapped with the level-1 scatter, then level 2 + count; "
-                        "finish = compaction slices overlapped with the D2H of the sorted table"},
+                "numa_node": numa_node,
+                "note": "add_batch = H2D pieces overlapped with the level-1 scatter; finish = level 2 + count + "
+                        "compaction in 16 key-range slices under the D2H of the slices already finished"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",

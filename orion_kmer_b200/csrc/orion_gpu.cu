@@ -40,6 +40,7 @@ int set_err(int code, const char* fmt, ...) {
 
 int g_device = -1;
 int g_sms = 0;
+int g_count_seed = 1;      // ORION_COUNT_SEED: 1 = seed round in the count kernel (measured 8.66 -> 7.86 ms), 0 = none, 2 = first round unqueued
 std::atomic<uint64_t> g_launches{0};
 std::mutex g_mu;
 
@@ -107,13 +108,16 @@ constexpr uint64_t COPY_CHUNK = 128ull << 20;  // bytes per H2D piece of the ing
 }  // namespace
 
 // =============================================================================== counter ==
-enum { RUN_NONE = 0, RUN_SPARSE = 1, RUN_DENSE = 2 };
+// RUN_LEVEL1: a host batch has been scattered into level-1 bins and everything after that (level 2, count,
+// compaction) is deferred, so that ok_counter_finish can run it slice by slice under the result's D2H copy
+enum { RUN_NONE = 0, RUN_SPARSE = 1, RUN_DENSE = 2, RUN_LEVEL1 = 3 };
 
 // plan of one partitioned batch: bin widths and the per-batch device arrays (inside d_meta)
 struct PartPlan {
     OkPartCfg cfg{};
     unsigned n_sub = 1, n_bin1 = 1, stride = 1;
     bool sharded = false;                    // keys arrived through the fused multi-GPU scatter (level-1 regions per sender)
+    bool hinted = false;                     // sub-partitions sized from the caller's capacity hint (distinct keys), not from the windows
     bool big_count = false;                  // sub-partitions may average > 5800 keys: the 16384-slot count kernel
     uint64_t cap_bound = 0, max_items = 0;
     unsigned *hist = nullptr, *beg = nullptr, *cursor = nullptr, *cap_end = nullptr, *deferred = nullptr;
@@ -122,6 +126,7 @@ struct PartPlan {
     unsigned long long* scan = nullptr;      // exclusive scan of n_distinct, n_sub + 1 entries
     unsigned long long* chunk_sum = nullptr; // per-1024-chunk totals of the two-launch scans
     OkPartScalars* scal = nullptr;
+    unsigned* bin_first = nullptr;           // first level-2 work item of every level-1 bin (+ the total)
     unsigned n_slices = 0, slice_step = 0;   // result slices: sub-partitions [i*step, (i+1)*step)
 };
 
@@ -144,14 +149,17 @@ struct PartHost {                            // page-locked mirror of the batch'
     unsigned long long total;
     unsigned long long slice_base[64];       // output offset of every result slice, then the total
     unsigned long long received;             // sharded path: k-mers the peers wrote into this rank's buffer
+    unsigned long long slice0_windows;       // sliced result pipeline: windows held by the first slice
+    unsigned long long windows_now;          //   ... and by the whole batch
 };
 
 struct ok_counter {
     unsigned k = 0;
     int norm_mode = 0;
-    uint64_t hint = 0;
+    uint64_t hint = 0, user_hint = 0;   // user_hint: ok_counter_create's capacity_hint as given (hint follows the table)
+    bool distrust_hint = false;         // the hint made shared-memory tables overflow once: sub-partitions are sized from the windows again
     int shard_rank = 0, n_shards = 1;   // multi-GPU: this table holds one key range of n_shards
-    cudaStream_t s_main = nullptr, s_copy = nullptr;
+    cudaStream_t s_main = nullptr, s_copy = nullptr, s_aux = nullptr;   // s_aux: compaction of the sliced result pipeline
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     std::vector<cudaEvent_t> ev_chunks;
     // table
@@ -174,6 +182,8 @@ struct ok_counter {
     int run_state = RUN_NONE;
     PartPlan pl;
     PartHost* h_part = nullptr;
+    PartHost* h_part_dev = nullptr;    // the same page-locked block as the kernels address it (zero-copy stores)
+    uint64_t pend_bases = 0, pend_rec = 0, pend_windows_before = 0;   // RUN_LEVEL1: the batch still sitting in d_bases / d_off
     ShardState shard;
     bool buf1_external = false;        // d_buf1 is the caller's peer-mapped buffer (never reallocated or freed here)
     unsigned long long* d_run_keys = nullptr; uint64_t cap_run_keys = 0;
@@ -373,8 +383,10 @@ namespace {
 
 constexpr uint64_t PART_MIN_BASES = 1ull << 20;   // below this the table path is as fast
 constexpr unsigned PART_TARGET = 4096;            // keys per sub-partition if every key were distinct
+constexpr unsigned PART_DISTINCT_TARGET = 4096;   // ... expected distinct keys per sub-partition when the caller gave a capacity hint
+constexpr unsigned PART_WINDOWS_MAX = 24576;      // ... and windows per sub-partition at most (16-bit counts: < 61440 even when unbalanced)
 constexpr unsigned PART_MAX_BITS = 18;            // up to 9 bits at level 1 + up to 10 at level 2
-constexpr unsigned RESULT_SLICES = 16;            // the result pipeline compacts and ships the table in slices
+unsigned RESULT_SLICES = 16;            // the result pipeline compacts and ships the table in slices
 
 bool part_eligible(const ok_counter* c, uint64_t n_units) {
     if (c->path_mode == 1) return false;
@@ -383,10 +395,26 @@ bool part_eligible(const ok_counter* c, uint64_t n_units) {
     return c->path_mode == 2 || n_units >= PART_MIN_BASES;
 }
 
-void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl) {
-    uint64_t want = (n_units + PART_TARGET - 1) / PART_TARGET;
+void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl, bool use_hint = false) {
+    uint64_t want = (n_units + PART_TARGET - 1) / PART_TARGET;       // safe when every key is distinct
+    uint64_t exp_distinct = n_units;
+    if (use_hint && c->user_hint && !c->distrust_hint && !getenv("ORION_NO_HINT_BITS")) {
+        // The count kernel's table holds a sub-partition's DISTINCT keys.  With the caller's capacity hint
+        // (expected distinct k-mers) sub-partitions can hold several windows per slot: fewer, larger ones mean
+        // fewer bins per scatter level and less per-sub-partition overhead.  A hint that is too low costs
+        // speed only: what outgrows a table is deferred to the generic kernel.
+        exp_distinct = std::min<uint64_t>(c->user_hint, n_units);
+        const uint64_t by_distinct = (exp_distinct + PART_DISTINCT_TARGET - 1) / PART_DISTINCT_TARGET;
+        const uint64_t by_windows = (n_units + PART_WINDOWS_MAX - 1) / PART_WINDOWS_MAX;
+        const uint64_t hinted_want = std::max(by_distinct, by_windows);
+        if (hinted_want < want) { want = hinted_want; pl.hinted = true; }
+    }
     unsigned bits = 0;
     while ((1ull << bits) < want && bits < PART_MAX_BITS) ++bits;
+    if (const char* ev = getenv("ORION_SUB_BITS")) {   // tuning knob: total bits of the two scatter levels
+        const unsigned v = (unsigned)atoi(ev);
+        if (v >= 1 && v <= PART_MAX_BITS) bits = v;
+    }
     pl.cfg.key_shift = 64 - 2 * c->k;
     pl.cfg.shard_log2 = 0;
     for (int g = c->n_shards; g > 1; g >>= 1) ++pl.cfg.shard_log2;
@@ -399,7 +427,7 @@ void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl) {
     pl.cfg.b2 = bits - pl.cfg.b1;
     pl.n_sub = 1u << bits;
     pl.n_bin1 = 1u << pl.cfg.b1;
-    pl.big_count = n_units / pl.n_sub > 5800;   // units bound the keys: a 6144-key table would defer too often
+    pl.big_count = exp_distinct / pl.n_sub > (pl.hinted ? 4600u : 5800u);   // units bound the keys: a 6144-key table would defer too often
     if (const char* ev = getenv("ORION_BIG_COUNT")) pl.big_count = atoi(ev) != 0;   // test hook: force the 16384-slot count kernel
 }
 
@@ -433,13 +461,13 @@ int part_layout(ok_counter* c, uint64_t n_units, uint64_t unit_chunk, uint64_t f
     const uint64_t o_scan = take(2 * (n_sub + 2)), o_chunk = take(2 * (n_sub / 1024 + 2)), o_scal = take(sizeof(OkPartScalars) / 4), o_hist = take(n_sub), o_beg = take(n_sub),
                    o_cur = take(n_sub), o_end = take(n_sub), o_def = take(n_sub), o_b1 = take(OK_PART_MAXBINS),
                    o_c1 = take(OK_PART_MAXBINS), o_e1 = take(OK_PART_MAXBINS), o_io = take(pl.max_items),
-                   o_in = take(pl.max_items), o_ib = take(pl.max_items);
+                   o_in = take(pl.max_items), o_ib = take(pl.max_items), o_bf = take(OK_PART_MAXBINS + 1);
     TRY(dev_reserve(&c->d_meta, &c->cap_meta, words));
     unsigned* m = c->d_meta;
     pl.scan = (unsigned long long*)(m + o_scan); pl.chunk_sum = (unsigned long long*)(m + o_chunk); pl.scal = (OkPartScalars*)(m + o_scal);
     pl.hist = m + o_hist; pl.beg = m + o_beg; pl.cursor = m + o_cur; pl.cap_end = m + o_end; pl.deferred = m + o_def;
     pl.beg1 = m + o_b1; pl.cursor1 = m + o_c1; pl.end1 = m + o_e1;
-    pl.item_off = m + o_io; pl.item_n = m + o_in; pl.item_bin = m + o_ib;
+    pl.item_off = m + o_io; pl.item_n = m + o_in; pl.item_bin = m + o_ib; pl.bin_first = m + o_bf;
     TRY(dev_reserve(&c->d_buf2, &c->cap_buf2, pl.cap_bound + 16));
     if (c->buf1_external) {
         if (c->cap_buf1 < pl.cap_bound + 16) return set_err(OK_ERR_INVALID_ARGUMENT, "the peer buffer is too small for this batch (%llu < %llu keys)",
@@ -456,45 +484,70 @@ int run_make_dense(ok_counter* c);
 
 constexpr int PART_RETRY = 100;   // internal: the one-shot path gave up, count the batch through the table instead
 
-// level 2 + count + scan, shared by the two entry points.  The keys are already scattered into
-// level-1 bins in d_buf1 (b2 > 0) or straight into sub-partitions in d_buf2 (b2 == 0).  Leaves
-// the result as sorted sub-partition runs (RUN_SPARSE); compaction happens when it is asked for.
-int part_finish(ok_counter* c, PartPlan& pl) {
+// work items of the level-2 scatter, from the level-1 fills (one small launch per batch)
+void part_launch_items(ok_counter* c, PartPlan& pl) {
+    if (pl.cfg.b2 == 0) return;
+    if (pl.sharded)   // (bin, sender) regions filled by the peers
+        LAUNCH(k_part_items, 1, 1024, 0, c->s_main, c->shard.reg_beg, c->shard.reg_fill, c->shard.reg_end, pl.n_bin1 << c->shard.g,
+               pl.n_bin1 - 1u, pl.item_off, pl.item_n, pl.item_bin, pl.scal, (unsigned*)nullptr);
+    else
+        LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, 0xFFFFFFFFu, pl.item_off, pl.item_n, pl.item_bin,
+               pl.scal, pl.bin_first);
+}
+
+// Level 2 + count + scan of sub-partitions [p0, p1) on the compute stream.  The whole batch is one
+// such range; the sliced result pipeline issues one per slice (p0, p1: multiples of 1024 and of
+// the sub-partitions per level-1 bin).  Sorted runs land in place (keys in d_buf2, counts in
+// d_buf1); pl.scan[p] = output offset of sub-partition p; host_total (page-locked, optional)
+// receives the running total of distinct k-mers after this range.
+int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, bool whole, unsigned long long* host_total) {
     const OkPartSpill ps{c->spill, c->d_stats};
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
     if (pl.cfg.b2 > 0) {
-        if (pl.sharded)   // (bin, sender) regions filled by the peers
-            LAUNCH(k_part_items, 1, 1024, 0, c->s_main, c->shard.reg_beg, c->shard.reg_fill, c->shard.reg_end, pl.n_bin1 << c->shard.g,
-                   pl.n_bin1 - 1u, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
-        else
-            LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, 0xFFFFFFFFu, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
         auto k_l2 = OK_BY_K(c->k, k_part_scatter_keys, 2, true);
         TRY(set_smem(k_l2, sizeof(OkScatterKeysSmem)));
-        LAUNCH(k_l2, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
-               pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps);
+        if (whole)
+            LAUNCH(k_l2, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
+                   pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps, (const unsigned*)nullptr, 0u, 0u);
+        else
+            LAUNCH(k_l2, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
+                   pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps, (const unsigned*)pl.bin_first,
+                   p0 >> pl.cfg.b2, p1 >> pl.cfg.b2);
     }
-    CU(cudaEventRecord(c->ev_p[3], c->s_main));
+    if (whole) CU(cudaEventRecord(c->ev_p[3], c->s_main));
     // count every sub-partition in shared memory; sorted runs land in place, counts in d_buf1
     unsigned* d_nd = pl.hist;   // the sample histogram is no longer needed (k_part_plan zeroed it)
     unsigned long long* cnt_out = c->buf1_external ? c->d_cnt : c->d_buf1;
     if (pl.big_count) {
         auto k_cnt = OK_BY_K(c->k, k_part_count, 14);
         TRY(set_smem(k_cnt, sizeof(OkCount2Smem<14>)));
-        LAUNCH(k_cnt, std::min<unsigned>(pl.n_sub, grid_sm), OkCount2Cfg<14>::THREADS, sizeof(OkCount2Smem<14>), c->s_main,
-               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal);
+        LAUNCH(k_cnt, std::min<unsigned>(p1 - p0, grid_sm), OkCount2Cfg<14>::THREADS, sizeof(OkCount2Smem<14>), c->s_main,
+               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, p0, p1, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal,
+               g_count_seed == 1 ? OkCount2Cfg<14>::THREADS : 0u, g_count_seed == 2);
     } else {
         auto k_cnt = OK_BY_K(c->k, k_part_count, 13);
         TRY(set_smem(k_cnt, sizeof(OkCount2Smem<13>)));
-        LAUNCH(k_cnt, std::min<unsigned>(pl.n_sub, grid_sm * 2), OkCount2Cfg<13>::THREADS, sizeof(OkCount2Smem<13>), c->s_main,
-               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, pl.n_sub, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal);
+        LAUNCH(k_cnt, std::min<unsigned>(p1 - p0, grid_sm * 2), OkCount2Cfg<13>::THREADS, sizeof(OkCount2Smem<13>), c->s_main,
+               c->d_buf2, pl.beg, pl.cursor, pl.cap_end, p0, p1, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal,
+               g_count_seed == 1 ? OkCount2Cfg<13>::THREADS : 0u, g_count_seed == 2);
     }
     const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
     TRY(set_smem(k_part_count_generic, ct_smem));
     LAUNCH(k_part_count_generic, grid_sm, OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg, pl.cursor, pl.cap_end,
            pl.deferred, pl.scal, pl.cfg, cnt_out, d_nd, ps);
-    CU(cudaEventRecord(c->ev_p[4], c->s_main));
-    LAUNCH(k_part_scan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, d_nd, pl.n_sub, pl.chunk_sum);
-    LAUNCH(k_part_scan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, d_nd, pl.n_sub, pl.chunk_sum, pl.scan);
+    if (whole) CU(cudaEventRecord(c->ev_p[4], c->s_main));
+    const unsigned chunk0 = p0 / 1024u, n_chunks = (p1 - p0 + 1023u) / 1024u;
+    LAUNCH(k_part_scan_sums, n_chunks, 1024, 0, c->s_main, d_nd, pl.n_sub, pl.chunk_sum, chunk0);
+    LAUNCH(k_part_scan, n_chunks, 1024, 0, c->s_main, d_nd, pl.n_sub, pl.chunk_sum, pl.scan, chunk0, host_total, pl.scal);
+    return OK_SUCCESS;
+}
+
+// level 2 + count + scan, shared by the two entry points.  The keys are already scattered into
+// level-1 bins in d_buf1 (b2 > 0) or straight into sub-partitions in d_buf2 (b2 == 0).  Leaves
+// the result as sorted sub-partition runs (RUN_SPARSE); compaction happens when it is asked for.
+int part_finish(ok_counter* c, PartPlan& pl) {
+    part_launch_items(c, pl);
+    TRY(part_launch_range(c, pl, 0, pl.n_sub, true, nullptr));
     CU(cudaEventRecord(c->ev_p[5], c->s_main));
     // the one host round trip of the batch: totals, slice boundaries of the result, statistics
     const unsigned step = std::max<unsigned>(1, pl.n_sub / RESULT_SLICES);
@@ -524,14 +577,27 @@ int part_finish(ok_counter* c, PartPlan& pl) {
 // whatever the displacement / capacity bounds spilled is exact but unsorted: fold the run and
 // the spill list into the general table.  If even the spill list overflowed, nothing of this
 // batch is kept and the caller re-counts it through the table path.
+// forget everything the one-shot path did with the current batch
+int part_discard(ok_counter* c, uint64_t windows_before) {
+    c->run_state = RUN_NONE; c->n_run = 0; c->occupied = 0; c->windows = windows_before; c->n_deferred = 0;
+    CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
+    CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    c->h_stats->spill_n = 0;
+    return OK_SUCCESS;
+}
+
+// A capacity hint far below the truth makes the shared-memory tables of the count kernel overflow; the
+// deferred sub-partitions would crawl through the generic kernel and its spill list.  Cheaper and
+// cleaner: drop the attempt and count the batch again with sub-partitions sized from the windows.
+bool part_hint_misled(const ok_counter* c, const PartPlan& pl) {
+    return pl.hinted && c->n_deferred > pl.n_sub / 256u + 4u;
+}
+
 int part_absorb_spills(ok_counter* c, uint64_t windows_before) {
     if (c->h_stats->spill_n == 0) return OK_SUCCESS;
     if (c->h_stats->spill_n > c->spill.cap) {
-        c->run_state = RUN_NONE; c->n_run = 0; c->occupied = 0; c->windows = windows_before;
-        CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
-        CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
-        CU(cudaStreamSynchronize(c->s_main));
-        c->h_stats->spill_n = 0;
+        TRY(part_discard(c, windows_before));
         return PART_RETRY;
     }
     c->spilled_total += c->h_stats->spill_n;
@@ -545,11 +611,14 @@ struct PieceSchedule { uint64_t n_pieces, piece_bytes; const cudaEvent_t* ev; };
 // d_bases: the batch in device memory (possibly still landing, see `pieces`); sample_src: where the
 // sampling kernel reads the bases from -- d_bases itself, or the caller's page-locked host buffer
 // (zero-copy), so that the plan exists before the first piece has arrived.
+// defer: stop after the level-1 scatter when the plan can be finished slice by slice (RUN_LEVEL1);
+// part_settle or the sliced ok_counter_finish does the rest.
+bool part_sliceable(const PartPlan& pl);
 int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec,
-                     const uint8_t* sample_src, const PieceSchedule* pieces) {
+                     const uint8_t* sample_src, const PieceSchedule* pieces, bool defer = false) {
     PartPlan& pl = c->pl; pl = PartPlan{};
     const uint64_t windows_before = c->windows;
-    part_choose_bits(c, n_bases, pl);
+    part_choose_bits(c, n_bases, pl, /*use_hint=*/true);
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
     pl.stride = n_tiles > 4096 ? 16 : 1;
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
@@ -589,7 +658,17 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
         }
     }
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
+    if (defer && part_sliceable(pl)) {
+        c->run_state = RUN_LEVEL1;
+        c->pend_bases = n_bases; c->pend_rec = n_rec; c->pend_windows_before = windows_before;
+        return OK_SUCCESS;
+    }
     TRY(part_finish(c, pl));
+    if (part_hint_misled(c, pl)) {
+        TRY(part_discard(c, windows_before));
+        c->distrust_hint = true;
+        return part_count_bases(c, d_bases, n_bases, d_off, n_rec, d_bases, pieces, false);
+    }
     return part_absorb_spills(c, windows_before);
 }
 
@@ -617,7 +696,8 @@ int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
         TRY(set_smem(kern, sizeof(OkScatterKeysSmem)));
         LAUNCH(kern, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, (const unsigned long long*)d_keys,
                pl.item_off, pl.item_n, pl.item_bin, pl.scal, pl.cfg, two ? pl.cursor1 : pl.cursor,
-               (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2, (OkPartSpill{c->spill, c->d_stats}));
+               (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2, (OkPartSpill{c->spill, c->d_stats}),
+               (const unsigned*)nullptr, 0u, 0u);
         c->windows += n;
         CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
     }
@@ -627,10 +707,11 @@ int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
 }
 
 // compact sub-partitions [p0, p1) of the sparse run into the dense arrays
-void launch_compact(ok_counter* c, unsigned p0, unsigned p1, unsigned long long* out_keys, unsigned long long* out_counts) {
+void launch_compact(ok_counter* c, unsigned p0, unsigned p1, unsigned long long* out_keys, unsigned long long* out_counts,
+                    cudaStream_t stream = nullptr) {
     const PartPlan& pl = c->pl;
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
-    LAUNCH(k_part_compact, std::min<unsigned>(p1 - p0, grid_sm * 8), 256, 0, c->s_main, c->d_buf2, c->buf1_external ? c->d_cnt : c->d_buf1, pl.beg, pl.hist,
+    LAUNCH(k_part_compact, std::min<unsigned>(p1 - p0, grid_sm * 8), 256, 0, stream ? stream : c->s_main, c->d_buf2, c->buf1_external ? c->d_cnt : c->d_buf1, pl.beg, pl.hist,
            pl.scan, p0, p1, out_keys, out_counts);
 }
 
@@ -705,6 +786,153 @@ int run_filter(ok_counter* c, uint64_t min_count, uint64_t* n_out) {
     return OK_SUCCESS;
 }
 
+// ---- deferred batches (RUN_LEVEL1) ------------------------------------------------------------
+// result slices of the sliced pipeline: whole level-1 bins and whole 1024-sub-partition scan chunks
+unsigned part_slice_step(const PartPlan& pl) {
+    const unsigned align = std::max(1024u, 1u << pl.cfg.b2);
+    const unsigned step = std::max(align, pl.n_sub / RESULT_SLICES);
+    return (step + align - 1) / align * align;
+}
+bool part_sliceable(const PartPlan& pl) {
+    if (getenv("ORION_NO_DEFER")) return false;
+    if (pl.cfg.b2 == 0 || pl.sharded) return false;
+    const unsigned step = part_slice_step(pl);
+    return pl.n_sub % step == 0 && pl.n_sub / step >= 4 && pl.n_sub / step <= 60;
+}
+
+// the batch of a RUN_LEVEL1 counter, re-counted through the general table (the one-shot path gave up)
+int part_recount_pending(ok_counter* c) {
+    TRY(run_to_table(c));
+    const uint64_t n_tiles = (c->pend_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    return counter_process_tiles(c, c->d_bases, c->pend_bases, c->d_off, c->pend_rec, 0, n_tiles);
+}
+
+// finish a deferred batch in one go: whatever needs the counted result calls this first
+int part_settle(ok_counter* c) {
+    if (c->run_state != RUN_LEVEL1) return OK_SUCCESS;
+    c->run_state = RUN_NONE;
+    TRY(part_finish(c, c->pl));
+    int r;
+    if (part_hint_misled(c, c->pl)) {
+        TRY(part_discard(c, c->pend_windows_before));
+        c->distrust_hint = true;
+        r = part_count_bases(c, c->d_bases, c->pend_bases, c->d_off, c->pend_rec, c->d_bases, nullptr, false);
+    } else {
+        r = part_absorb_spills(c, c->pend_windows_before);
+    }
+    return r == PART_RETRY ? part_recount_pending(c) : r;
+}
+
+// Sliced result pipeline of a deferred batch (min_count <= 1): for every slice of the key space
+//   compute stream: level-2 scatter -> count -> scan        (~1 ms per slice)
+//   aux stream    : compaction into the dense arrays          (as soon as the slice's offsets exist)
+//   copy stream   : D2H of the slice                          (~4 ms per slice: the bottleneck)
+// so all compute after the level-1 scatter hides under the copy of the result.  The result buffers are
+// sized after the first slice (distinct per window and per key range, + 4 %); if a later slice does
+// not fit, the remaining slices are only counted and the caller falls back to the exact-size path.
+// *shipped = false: counted, but the result has not (completely) reached the host: the state is RUN_SPARSE (or the
+// table, after a spill) and the caller goes on with the exact-size path
+int part_finish_sliced(ok_counter* c, uint64_t** kmers, uint64_t** counts, uint64_t* n, bool* shipped) {
+    *shipped = false;
+    PartPlan& pl = c->pl;
+    const unsigned step = part_slice_step(pl), n_slices = pl.n_sub / step;
+    PartHost* h = c->h_part;
+    PartHost* hd = c->h_part_dev;
+    c->run_state = RUN_NONE;
+    if (!c->s_aux) CU(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+    while (c->ev_chunks.size() < 2 * (size_t)n_slices) {
+        cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_chunks.push_back(e);
+    }
+    cudaEvent_t* ev_scan = c->ev_chunks.data();
+    cudaEvent_t* ev_comp = c->ev_chunks.data() + n_slices;
+    part_launch_items(c, pl);
+    auto issue = [&](unsigned i) -> int {
+        const unsigned p0 = i * step, p1 = p0 + step;
+        TRY(part_launch_range(c, pl, p0, p1, false, &hd->slice_base[i + 1]));
+        if (i == 0) LAUNCH(k_part_slice_fill, 1, 1024, 0, c->s_main, pl.beg, pl.cursor, pl.cap_end, 0u, p1, &hd->slice0_windows);
+        CU(cudaEventRecord(ev_scan[i], c->s_main));
+        return OK_SUCCESS;
+    };
+    h->slice_base[0] = 0;
+    CU(cudaMemcpyAsync(&h->windows_now, &c->d_stats->windows, 8, cudaMemcpyDeviceToHost, c->s_main));   // the copy engines are idle here
+    TRY(issue(0));
+    if (n_slices > 1) TRY(issue(1));
+    void *hk = nullptr, *hc = nullptr;
+    uint64_t cap = 0;
+    bool shipping = true;
+    for (unsigned i = 0; i < n_slices; ++i) {
+        CU(cudaEventSynchronize(ev_scan[i]));
+        const volatile unsigned long long* sb = h->slice_base;
+        const uint64_t o0 = sb[i], o1 = sb[i + 1];
+        if (i == 0) {
+            // distinct k-mers of the batch, estimated from the first slice two ways: per key range (the
+            // position map balances the slices) and per window (slice_fill = windows the slice holds)
+            const double d0 = (double)o1;
+            const double w0 = (double)*(volatile unsigned long long*)&h->slice0_windows;
+            const double w_all = (double)*(volatile unsigned long long*)&h->windows_now - (double)c->pend_windows_before;
+            double est = d0 * (double)n_slices;
+            if (w0 > 0) est = std::max(est, d0 * (w_all / w0));
+            est = std::min(est * 1.04 + 262144.0, std::max(w_all, d0) + 16.0);   // distinct <= windows
+            cap = (uint64_t)est;
+            TRY(pool_alloc(&hk, cap * 8));
+            TRY(pool_alloc(&hc, cap * 8));
+            TRY(dev_reserve(&c->d_run_keys, &c->cap_run_keys, cap));
+            TRY(dev_reserve(&c->d_run_counts, &c->cap_run_counts, cap));
+        }
+        if (shipping && o1 > cap) shipping = false;
+        if (shipping && o1 > o0) {
+            CU(cudaStreamWaitEvent(c->s_aux, ev_scan[i], 0));
+            launch_compact(c, i * step, (i + 1) * step, c->d_run_keys, c->d_run_counts, c->s_aux);
+            CU(cudaEventRecord(ev_comp[i], c->s_aux));
+            CU(cudaStreamWaitEvent(c->s_copy, ev_comp[i], 0));
+            CU(cudaMemcpyAsync((uint64_t*)hk + o0, c->d_run_keys + o0, (o1 - o0) * 8, cudaMemcpyDeviceToHost, c->s_copy));
+            CU(cudaMemcpyAsync((uint64_t*)hc + o0, c->d_run_counts + o0, (o1 - o0) * 8, cudaMemcpyDeviceToHost, c->s_copy));
+        }
+        if (i + 2 < n_slices) TRY(issue(i + 2));
+    }
+    CU(cudaMemcpyAsync(&h->scal, pl.scal, sizeof(OkPartScalars), cudaMemcpyDeviceToHost, c->s_main));
+    TRY(read_stats(c));   // synchronises the compute stream
+    CU(cudaStreamSynchronize(c->s_aux));
+    CU(cudaStreamSynchronize(c->s_copy));
+    CU(cudaGetLastError());
+    const uint64_t total = h->slice_base[n_slices];
+    h->total = total;
+    c->ms_sample = c->ms_scatter1 = c->ms_scatter2 = c->ms_count = c->ms_compact = 0;
+    c->ms_insert = c->ms_readout = 0;
+    c->n_run = total; c->occupied = total;
+    c->n_deferred = h->scal.n_deferred;
+    c->run_state = RUN_SPARSE;
+    const bool spilled = c->h_stats->spill_n != 0;
+    if (part_hint_misled(c, pl)) {       // see part_hint_misled: count the batch again, sized from its windows
+        if (hk) pool_release(hk);
+        if (hc) pool_release(hc);
+        TRY(part_discard(c, c->pend_windows_before));
+        c->distrust_hint = true;
+        const int r = part_count_bases(c, c->d_bases, c->pend_bases, c->d_off, c->pend_rec, c->d_bases, nullptr, false);
+        return r == PART_RETRY ? part_recount_pending(c) : r;
+    }
+    if (shipping && !spilled) {
+        c->run_state = RUN_DENSE;
+        *kmers = (uint64_t*)hk; *counts = (uint64_t*)hc; *n = total;
+        *shipped = true;
+        return OK_SUCCESS;
+    }
+    if (hk) pool_release(hk);
+    if (hc) pool_release(hc);
+    {   // slice boundaries for the exact-size result path of ok_counter_finish
+        const unsigned fstep = std::max<unsigned>(1, pl.n_sub / RESULT_SLICES);
+        pl.n_slices = (pl.n_sub + fstep - 1) / fstep; pl.slice_step = fstep;
+        CU(cudaMemcpy2DAsync(h->slice_base, 8, pl.scan, (size_t)fstep * 8, 8, pl.n_slices, cudaMemcpyDeviceToHost, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        h->slice_base[pl.n_slices] = total;
+    }
+    if (spilled) {
+        const int r = part_absorb_spills(c, c->pend_windows_before);
+        if (r == PART_RETRY) TRY(part_recount_pending(c)); else if (r != OK_SUCCESS) return r;
+    }
+    return OK_SUCCESS;
+}
+
 // result of the counter, wherever it lives: -> device pointers
 int counter_result(ok_counter* c, uint64_t min_count, const unsigned long long** dk, const unsigned long long** dc, uint64_t* n) {
     if (c->run_state != RUN_NONE) {
@@ -742,6 +970,8 @@ OK_EXPORT int ok_init(const int* device_ids, int n_devices) {
     CU(cudaGetDeviceProperties(&prop, dev));
     g_sms = prop.multiProcessorCount;
     g_device = dev;
+    if (const char* ev = getenv("ORION_COUNT_SEED")) g_count_seed = atoi(ev);
+    if (const char* ev = getenv("ORION_SLICES")) { const int v = atoi(ev); if (v >= 4 && v <= 60) RESULT_SLICES = (unsigned)v; }
     return OK_SUCCESS;
 }
 
@@ -809,7 +1039,7 @@ OK_EXPORT int ok_counter_create(uint8_t k, int norm_mode, uint64_t capacity_hint
         return set_err(OK_ERR_INVALID_ARGUMENT, "unknown norm_mode %d", norm_mode);
     TRY(ensure_init());
     ok_counter* c = new ok_counter();
-    c->k = k; c->norm_mode = norm_mode; c->hint = capacity_hint;
+    c->k = k; c->norm_mode = norm_mode; c->hint = capacity_hint; c->user_hint = capacity_hint;
     auto fail = [&](int code) { ok_counter_destroy(c); return code; };
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(set_err(OK_ERR_CUDA, "CUDA error %s in ok_counter_create", cudaGetErrorName(e_))); } while (0)
     CUF(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
@@ -823,6 +1053,7 @@ OK_EXPORT int ok_counter_create(uint8_t k, int norm_mode, uint64_t capacity_hint
     memset(c->h_stats, 0, sizeof(OkDevStats));
     CUF(cudaMallocHost((void**)&c->h_part, sizeof(PartHost)));
     memset(c->h_part, 0, sizeof(PartHost));
+    CUF(cudaHostGetDevicePointer((void**)&c->h_part_dev, c->h_part, 0));
     c->spill.cap = SPILL_CAP;
     CUF(cudaMalloc((void**)&c->spill.keys, SPILL_CAP * 8));
     CUF(cudaMalloc((void**)&c->spill.incs, SPILL_CAP * 8));
@@ -835,6 +1066,7 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
     if (!c) return OK_SUCCESS;
     if (c->s_main) cudaStreamSynchronize(c->s_main);
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    if (c->s_aux) { cudaStreamSynchronize(c->s_aux); cudaStreamDestroy(c->s_aux); }
     cudaFree(c->tv.slots); cudaFree(c->d_stats); cudaFreeHost(c->h_stats);
     cudaFree(c->spill.keys); cudaFree(c->spill.incs);
     cudaFree(c->d_bases); cudaFree(c->d_off); cudaFree(c->d_tiles);
@@ -854,6 +1086,7 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
 
 OK_EXPORT int ok_counter_clear(ok_counter* c) {
     if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_clear: NULL handle");
+    if (c->run_state == RUN_LEVEL1) { CU(cudaStreamSynchronize(c->s_main)); c->run_state = RUN_NONE; }   // a deferred batch is simply dropped
     if (c->tv.slots && c->occupied && c->run_state == RUN_NONE)
         LAUNCH(k_fill_slots, grid_for(c->tv.n_total, 256, 16), 256, 0, c->s_main, c->tv.slots, c->tv.n_total);
     c->run_state = RUN_NONE; c->n_run = 0;
@@ -870,6 +1103,7 @@ OK_EXPORT int ok_counter_add_batch_device(ok_counter* c, const uint8_t* d_bases,
     if (n_bases == 0 || n_records == 0) return OK_SUCCESS;
     if (!d_bases || !d_rec_offsets) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL batch pointer");
     if ((uintptr_t)d_bases & 15u) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
+    TRY(part_settle(c));
     c->ms_insert = 0; c->ms_fill = 0;
     if (part_eligible(c, n_bases)) {
         const int r = part_count_bases(c, d_bases, n_bases, d_rec_offsets, n_records, d_bases, nullptr);
@@ -891,6 +1125,7 @@ OK_EXPORT int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const ui
     const uint64_t n_bases = rec_offsets[n_records];
     if (n_bases == 0) return OK_SUCCESS;
     if (!bases) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL bases");
+    TRY(part_settle(c));               // a deferred batch still lives in d_bases
     c->ms_insert = 0; c->ms_fill = 0;
     TRY(dev_reserve(&c->d_bases, &c->cap_bases, n_bases + 64));
     TRY(dev_reserve(&c->d_off, &c->cap_off, n_records + 1));
@@ -919,7 +1154,10 @@ OK_EXPORT int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const ui
         if (mapped) sample_src = (const uint8_t*)attr.devicePointer;
         else CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces - 1], 0));
         const PieceSchedule ps{n_pieces, COPY_CHUNK, c->ev_chunks.data()};
-        const int r = part_count_bases(c, c->d_bases, n_bases, c->d_off, n_records, sample_src, &ps);
+        // Deferred: level 2, count and compaction run in ok_counter_finish, slice by slice under the D2H copy
+        // of the result (or in part_settle, if anything else is asked of the counter first).
+        const int r = part_count_bases(c, c->d_bases, n_bases, c->d_off, n_records, sample_src, &ps, /*defer=*/true);
+        if (r == OK_SUCCESS && c->run_state == RUN_LEVEL1) CU(cudaStreamSynchronize(c->s_copy));   // the caller's buffers are free again
         if (r != PART_RETRY) { if (r == OK_SUCCESS) c->bases_seen += n_bases; return r; }
     }
     TRY(run_to_table(c));
@@ -941,6 +1179,7 @@ OK_EXPORT int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers
     if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_add_kmers_device: NULL handle");
     if (n == 0) return OK_SUCCESS;
     if (!d_kmers) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL d_kmers");
+    TRY(part_settle(c));
     c->ms_insert = 0; c->ms_fill = 0;
     if (part_eligible(c, n)) { const int r = part_count_keys(c, d_kmers, n); if (r != PART_RETRY) return r; }
     TRY(run_to_table(c));
@@ -1317,6 +1556,7 @@ OK_EXPORT int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all
 OK_EXPORT int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t** d_kmers,
                                        const uint64_t** d_counts, uint64_t* n) {
     if (!c || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_finish_device: NULL argument");
+    TRY(part_settle(c));
     uint64_t total = 0;
     const unsigned long long *dk = nullptr, *dc = nullptr;
     TRY(counter_result(c, min_count, &dk, &dc, &total));
@@ -1330,6 +1570,15 @@ OK_EXPORT int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** km
                                 uint64_t* n) {
     if (!c || !kmers || !counts || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_finish: NULL argument");
     void *hk = nullptr, *hc = nullptr;
+    if (c->run_state == RUN_LEVEL1) {
+        if (min_count <= 1) {
+            bool shipped = false;
+            TRY(part_finish_sliced(c, kmers, counts, n, &shipped));
+            if (shipped) return OK_SUCCESS;      // otherwise: counted, result not shipped -> the paths below
+        } else {
+            TRY(part_settle(c));
+        }
+    }
     if (c->run_state == RUN_SPARSE && min_count <= 1 && c->n_run) {
         // result pipeline: compact the sorted sub-partition runs slice by slice on the compute stream
         // while the copy stream ships the slices already compacted to the host
@@ -1385,6 +1634,7 @@ OK_EXPORT int ok_counter_set_path(ok_counter* c, int mode) {
 }
 
 OK_EXPORT int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out) {
+    if (c && out) TRY(part_settle(c));
     if (!c || !out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_get_stats: NULL argument");
     out->n_slots = c->run_state != RUN_NONE ? 0 : c->tv.n_total; out->n_distinct = c->occupied; out->n_windows = c->windows;
     out->n_bases = c->bases_seen; out->max_displacement = c->max_disp; out->n_spilled = c->spilled_total;

@@ -73,7 +73,7 @@ struct OkPartScalars {
     unsigned n_items;        // level-2 work items
     unsigned n_deferred;     // sub-partitions left to the generic count kernel
     unsigned total_cap;      // sum of the sub-partition capacities
-    unsigned pad;
+    unsigned def_done;       // deferred sub-partitions the generic kernel has already counted (sliced runs)
 };
 
 // ----------------------------------------------------------------------------- sampling --
@@ -188,35 +188,58 @@ k_part_plan(unsigned* __restrict__ hist, unsigned n_sub, unsigned stride, unsign
         if (b2 && (p & ((1u << b2) - 1u)) == 0) { beg1[p >> b2] = run; cursor1[p >> b2] = run; }
         if (b2 && (p & ((1u << b2) - 1u)) == (1u << b2) - 1u) end1[p >> b2] = end;
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { sc->total_cap = (unsigned)before + total; sc->n_items = 0; sc->n_deferred = 0; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { sc->total_cap = (unsigned)before + total; sc->n_items = 0; sc->n_deferred = 0; sc->def_done = 0; }
 }
 
 // exclusive scan of n_distinct[n_sub] -> base[n_sub + 1] (u64), same two-launch shape
+// A sliced run scans chunks [chunk0, chunk0 + gridDim.x) only: the chunk sums of the earlier slices are
+// already in chunk_sum, so `before` carries the running total across slices.
 __global__ void __launch_bounds__(1024)
-k_part_scan_sums(const unsigned* __restrict__ v, unsigned n, unsigned long long* __restrict__ chunk_sum) {
+k_part_scan_sums(const unsigned* __restrict__ v, unsigned n, unsigned long long* __restrict__ chunk_sum, unsigned chunk0) {
     __shared__ unsigned long long wsum[33];
-    const unsigned i = blockIdx.x * 1024u + threadIdx.x;
+    const unsigned cb = blockIdx.x + chunk0;
+    const unsigned i = cb * 1024u + threadIdx.x;
     const unsigned long long t = ok_block_sum_1024(i < n ? v[i] : 0u, wsum);
-    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = t;
+    if (threadIdx.x == 0) chunk_sum[cb] = t;
 }
 __global__ void __launch_bounds__(1024)
 k_part_scan(const unsigned* __restrict__ v, unsigned n, const unsigned long long* __restrict__ chunk_sum,
-            unsigned long long* __restrict__ base) {
+            unsigned long long* __restrict__ base, unsigned chunk0, unsigned long long* __restrict__ host_total,
+            OkPartScalars* __restrict__ sc) {
     __shared__ unsigned wsum[33];
     __shared__ unsigned long long wsum64[33];
-    const unsigned long long before = ok_block_sum_1024(threadIdx.x < blockIdx.x ? chunk_sum[threadIdx.x] : 0ull, wsum64);
-    const unsigned i = blockIdx.x * 1024u + threadIdx.x;
+    const unsigned cb = blockIdx.x + chunk0;
+    const unsigned long long before = ok_block_sum_1024(threadIdx.x < cb ? chunk_sum[threadIdx.x] : 0ull, wsum64);
+    const unsigned i = cb * 1024u + threadIdx.x;
     unsigned total;
     const unsigned ex = ok_block_excl_scan_1024(i < n ? v[i] : 0u, wsum, &total);
     if (i < n) base[i] = before + ex;
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) base[n] = before + total;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        base[min(n, (cb + 1u) * 1024u)] = before + total;   // running total: the next slice rewrites it with the same value
+        if (host_total) *host_total = before + total;        // page-locked host word (zero-copy store): no D2H copy to queue
+        if (sc) sc->def_done = sc->n_deferred;               // what the generic kernel has counted so far
+    }
+}
+// windows held by sub-partitions [p0, p1) after the scatters (one CTA): the sliced result pipeline
+// sizes the result buffers from the first slice's distinct / windows ratio
+__global__ void __launch_bounds__(1024)
+k_part_slice_fill(const unsigned* __restrict__ beg, const unsigned* __restrict__ fill_end, const unsigned* __restrict__ cap_end,
+                  unsigned p0, unsigned p1, unsigned long long* __restrict__ host_out) {
+    __shared__ unsigned long long wsum[33];
+    unsigned long long t = 0;
+    for (unsigned p = p0 + threadIdx.x; p < p1; p += 1024u) {
+        const unsigned b0 = beg[p], e0 = min(fill_end[p], cap_end[p]);
+        t += e0 > b0 ? e0 - b0 : 0u;
+    }
+    t = ok_block_sum_1024(t, wsum);
+    if (threadIdx.x == 0) *host_out = t;
 }
 
 // one CTA, 1024 threads: level-1 fills -> work items of <= OK_PART_TILE keys for the level-2 scatter
 __global__ void __launch_bounds__(1024)
 k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cursor1, const unsigned* __restrict__ end1,
              unsigned n_bin1, unsigned bin_mask, unsigned* __restrict__ item_off, unsigned* __restrict__ item_n,
-             unsigned* __restrict__ item_bin, OkPartScalars* __restrict__ sc) {
+             unsigned* __restrict__ item_bin, OkPartScalars* __restrict__ sc, unsigned* __restrict__ bin_first /* [MAXBINS + 1] or null */) {
     // the sharded path hands in (sender, bin) regions: region r belongs to level-1 bin r & bin_mask
     __shared__ unsigned wsum[33];
     __shared__ unsigned s_first[OK_PART_MAXBINS + 1], s_b0[OK_PART_MAXBINS], s_fill[OK_PART_MAXBINS];
@@ -228,6 +251,7 @@ k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cur
     const unsigned first = ok_block_excl_scan_1024(ni, wsum, &total);
     s_first[b] = first; s_b0[b] = b0; s_fill[b] = fill;
     if (b == 0) s_first[OK_PART_MAXBINS] = total;
+    if (bin_first) { bin_first[b] = first; if (b == 0) bin_first[OK_PART_MAXBINS] = total; }   // bins past n_bin1 hold no items: first == total
     __syncthreads();
     for (unsigned o = threadIdx.x; o < total; o += 1024u) {     // item o belongs to the last bin whose first item is <= o
         unsigned lo = 0, hi = OK_PART_MAXBINS - 1u;
@@ -574,13 +598,16 @@ __global__ void __launch_bounds__(OK_SK_THREADS, 2)
 k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* __restrict__ item_off,
                     const unsigned* __restrict__ item_n, const unsigned* __restrict__ item_bin,
                     const OkPartScalars* __restrict__ scal, OkPartCfg cfg_in, unsigned* __restrict__ cursors,
-                    const unsigned* __restrict__ bin_end, unsigned long long* __restrict__ out, OkPartSpill ps) {
+                    const unsigned* __restrict__ bin_end, unsigned long long* __restrict__ out, OkPartSpill ps,
+                    const unsigned* __restrict__ bin_first = nullptr, unsigned bin_lo = 0, unsigned bin_hi = 0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     OkScatterKeysSmem& sm = *reinterpret_cast<OkScatterKeysSmem*>(smem_raw);
     OkPartCfg cfg = cfg_in;
     if (KC) cfg.key_shift = 64u - 2u * KC;
     const unsigned bins_log2 = LEVEL == 1 ? cfg.b1 : cfg.b2;
-    const unsigned n_items = scal->n_items;
+    // a sliced run handles the items of level-1 bins [bin_lo, bin_hi) only
+    const unsigned w_begin = bin_first ? bin_first[bin_lo] : 0u;
+    const unsigned n_items = bin_first ? bin_first[bin_hi] : scal->n_items;
     for (unsigned i = threadIdx.x; i < OK_PART_MAXBINS; i += OK_SK_THREADS) sm.sc.hg[i] = make_uint2(0u, 0u);
     // LEVEL 2 reads our own level-1 buffer (even capacities, slack at the end): an odd item is
     // rounded UP to whole 16-byte units.  LEVEL 1 reads a caller's array: rounded DOWN, and the
@@ -593,11 +620,11 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* 
     };
     if (TMA && threadIdx.x == 0) {
         ok_mbar_init(&sm.bar, 1);
-        if (blockIdx.x < n_items) load_item(blockIdx.x);
+        if (w_begin + blockIdx.x < n_items) load_item(w_begin + blockIdx.x);
     }
     __syncthreads();
     unsigned phase = 0;
-    for (unsigned w = blockIdx.x; w < n_items; w += gridDim.x) {
+    for (unsigned w = w_begin + blockIdx.x; w < n_items; w += gridDim.x) {
         const unsigned n = item_n[w];
         const unsigned bin_base = LEVEL == 1 ? 0u : item_bin[w] << cfg.b2;
         uint64_t key[OK_SK_KPT]; unsigned vm = 0;
@@ -654,8 +681,12 @@ k_part_flat_items(unsigned n_keys, unsigned* __restrict__ item_off, unsigned* __
 // sub-partitions cannot be made smaller: 8-GPU routing, > 1.2 G keys per batch).
 template <int LOG2> struct OkCount2Cfg {
     static constexpr unsigned SLOTS = 1u << LOG2, MAXKEYS = 3u << (LOG2 - 2), THREADS = 1u << (LOG2 - 4),
-                              BUCKETS = 1u << (LOG2 - 3), WARPS = THREADS / 32u,
-                              WQ = MAXKEYS * 2u / 8u / WARPS;      // pending-key queue entries per warp (carved from sidx): 96
+                              BUCKET_BITS = LOG2 - 2, BUCKETS = 1u << BUCKET_BITS, BPT = BUCKETS / THREADS /* buckets per thread in the scan: 4 */,
+                              WARPS = THREADS / 32u,
+                              WQ = MAXKEYS * 2u / 8u / WARPS,      // pending-key queue entries per warp (carved from sidx): 96
+                              MAXN = 61440u,                       // windows per sub-partition: counts are 16-bit
+                              LIMIT = MAXKEYS - 64u;               // distinct keys after which no new round is started: the rounds
+                                                                   // in flight then claim < 4 * THREADS more, so an EMPTY slot always remains
 };
 template <int LOG2> struct OkCount2Smem {
     using C = OkCount2Cfg<LOG2>;
@@ -674,29 +705,43 @@ template <int LOG2> __device__ __forceinline__ unsigned ok_c2_hash(uint64_t key)
     return x >> (32 - LOG2);
 }
 template <int LOG2> __device__ __forceinline__ unsigned ok_c2_bucket(uint64_t key, const OkPartCfg& cfg, unsigned sub_bits) {
-    return (ok_part_phi(key, cfg) << sub_bits) >> (32 - (LOG2 - 3));     // the next LOG2-3 position bits
+    return (ok_part_phi(key, cfg) << sub_bits) >> (32 - OkCount2Cfg<LOG2>::BUCKET_BITS);     // the next position bits
 }
 template <int LOG2> __device__ __forceinline__ void ok_c2_add(OkCount2Smem<LOG2>& sm, unsigned s) {
     atomicAdd(&sm.tcnt[s >> 1], 1u << ((s & 1u) << 4));
 }
 // key not found at its first probe (cur = what was read there): walk on, claim an empty slot.
 // The thread that claims a slot also files the new distinct key: claim list + bucket histogram.
+// The walk only decides WHERE the key lives; the count and the filing happen after the lanes have
+// reconverged, once per call instead of once per divergent exit of the loop, and the claim-list
+// cursor is bumped once per warp (ballot) instead of once per claiming lane on one shared word.
 template <int LOG2>
 __device__ __forceinline__ void ok_c2_insert_slow(OkCount2Smem<LOG2>& sm, unsigned long long key, unsigned s,
                                                   unsigned long long cur, const OkPartCfg& cfg, unsigned sub_bits) {
+    bool claimed = false;
     for (;;) {
         if (cur == OK_EMPTY_KEY) {
             cur = atomicCAS(&sm.tkey[s], OK_EMPTY_KEY, key);
-            if (cur == OK_EMPTY_KEY) {
-                ok_c2_add(sm, s);
-                sm.newl[atomicAdd(&sm.n_new, 1u)] = (unsigned short)s;
-                atomicAdd(&sm.boff[ok_c2_bucket<LOG2>(key, cfg, sub_bits)], 1u);
-                return;
-            }
+            claimed = cur == OK_EMPTY_KEY;
         }
-        if (cur == key) { ok_c2_add(sm, s); return; }
+        if (claimed || cur == key) break;
         s = (s + 1u) & (OkCount2Cfg<LOG2>::SLOTS - 1u);
         cur = sm.tkey[s];
+    }
+    ok_c2_add(sm, s);
+    const unsigned act = __activemask();
+    const unsigned bal = __ballot_sync(act, claimed);
+    if (bal) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(bal) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&sm.n_new, __popc(bal));
+        base = __shfl_sync(act, base, leader);
+        if (claimed) {
+            const unsigned at = base + __popc(bal & ((1u << lane) - 1u));
+            if (at < OkCount2Cfg<LOG2>::MAXKEYS) sm.newl[at] = (unsigned short)s;     // past it the sub-partition is given up anyway
+            atomicAdd(&sm.boff[ok_c2_bucket<LOG2>(key, cfg, sub_bits)], 1u);
+        }
     }
 }
 
@@ -704,9 +749,10 @@ template <int LOG2, int KC = 0>
 __global__ void __launch_bounds__(OkCount2Cfg<LOG2>::THREADS, LOG2 == 13 ? 2 : 1)
 k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ beg,
              const unsigned* __restrict__ fill_end /* cursor after the scatter */,
-             const unsigned* __restrict__ cap_end, unsigned n_sub, OkPartCfg cfg_in,
+             const unsigned* __restrict__ cap_end, unsigned p_begin, unsigned p_end, OkPartCfg cfg_in,
              unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct,
-             unsigned* __restrict__ deferred, OkPartScalars* __restrict__ scal) {
+             unsigned* __restrict__ deferred, OkPartScalars* __restrict__ scal, unsigned seed_keys /* 0 or THREADS */,
+             bool direct_first) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using C = OkCount2Cfg<LOG2>;
     constexpr unsigned OK_C2_SLOTS = C::SLOTS, OK_C2_MAXKEYS = C::MAXKEYS, OK_C2_THREADS = C::THREADS, OK_C2_BUCKETS = C::BUCKETS;
@@ -724,16 +770,20 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
         if (threadIdx.x == 0) sm.n_new = 0;
     }
     __syncthreads();
-    for (unsigned p = blockIdx.x; p < n_sub; p += gridDim.x) {
+    for (unsigned p = p_begin + blockIdx.x; p < p_end; p += gridDim.x) {
         // invariant here: table empty, counts zero, boff zero, n_new zero
         const unsigned b0 = beg[p];
         const unsigned e0 = min(fill_end[p], cap_end[p]);          // the rest was spilled by the scatter
         const unsigned n = e0 > b0 ? e0 - b0 : 0u;
         if (n == 0) { if (threadIdx.x == 0) n_distinct[p] = 0; continue; }
-        if (n > OK_C2_MAXKEYS) {                                     // too large for the hashed table
+        // The table has to hold the DISTINCT keys only: a sub-partition may bring many more windows than slots
+        // (the host sizes sub-partitions from the caller's capacity hint).  If the distinct keys do outgrow the
+        // table the insert phase stops early and the sub-partition goes to the generic kernel.
+        if (n > C::MAXN) {
             if (threadIdx.x == 0) deferred[atomicAdd(&scal->n_deferred, 1u)] = p;
             continue;
         }
+        const bool may_overflow = n > OK_C2_MAXKEYS;
         const unsigned long long* __restrict__ keys = src + b0;
         // ---- (1) insert: 4 keys in flight per thread, the next 4 already loading.  A key found at its first
         // probe (a duplicate: ~80 % of the windows at 30x coverage) is counted on the spot by all lanes alike.
@@ -752,13 +802,27 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             __syncwarp();
             qn = 0;
         };
+        // Round 0: one key per thread goes straight through the claim loop.  The table is empty, so a first
+        // probe cannot hit; with 4 keys per thread the whole first round (half of a typical sub-partition)
+        // used to miss, queue up and take the slow path even though most of those keys are duplicates of
+        // one another.  Seeding the table with 1/8 of the keys first (at 30x coverage ~95 % of the repeated
+        // k-mers are among them) lets the rounds that follow hit on their first probe.
         unsigned long long nx[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const unsigned i = q * OK_C2_THREADS + threadIdx.x;
+            const unsigned i = seed_keys + q * OK_C2_THREADS + threadIdx.x;
             nx[q] = i < n ? __ldcs(keys + i) : OK_EMPTY_KEY;
         }
-        for (unsigned base = 0; base < n; base += 4 * OK_C2_THREADS) {
+        if (seed_keys) {
+            if (threadIdx.x < n) {
+                const unsigned long long key = __ldcs(keys + threadIdx.x);
+                const unsigned h = ok_c2_hash<LOG2>(key);
+                ok_c2_insert_slow(sm, key, h, sm.tkey[h], cfg, sub_bits);
+            }
+            __syncthreads();
+        }
+        for (unsigned base = seed_keys; base < n; base += 4 * OK_C2_THREADS) {
+            if (may_overflow && *(volatile unsigned*)&sm.n_new > C::LIMIT) break;   // warp-uniform (one shared word)
             unsigned long long kk[4], cur[4]; unsigned hs[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -768,6 +832,12 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) { hs[q] = ok_c2_hash<LOG2>(kk[q]); cur[q] = sm.tkey[hs[q]]; }
+            if (direct_first && base == 0) {     // empty table: no first probe can hit, skip the queue
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (kk[q] != OK_EMPTY_KEY) ok_c2_insert_slow(sm, kk[q], hs[q], sm.tkey[hs[q]], cfg, sub_bits);
+                continue;
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const bool live = kk[q] != OK_EMPTY_KEY;             // canonical k-mers never equal the sentinel
@@ -784,14 +854,27 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             drain();
         }
         __syncthreads();
-        // ---- (2) exclusive scan of the 1024 bucket counts, two per thread
+        if (may_overflow && sm.n_new > C::LIMIT) {       // block-uniform: too many distinct keys, start over clean
+            __syncthreads();
+            ulonglong2* k2 = reinterpret_cast<ulonglong2*>(sm.tkey);
+            uint4* c4 = reinterpret_cast<uint4*>(sm.tcnt);
+            for (unsigned i = threadIdx.x; i < OK_C2_SLOTS / 2; i += OK_C2_THREADS) k2[i] = make_ulonglong2(OK_EMPTY_KEY, OK_EMPTY_KEY);
+            for (unsigned i = threadIdx.x; i < OK_C2_SLOTS / 8; i += OK_C2_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (unsigned i = threadIdx.x; i < OK_C2_BUCKETS; i += OK_C2_THREADS) sm.boff[i] = 0;
+            if (threadIdx.x == 0) { sm.n_new = 0; deferred[atomicAdd(&scal->n_deferred, 1u)] = p; }
+            __syncthreads();
+            continue;
+        }
+        // ---- (2) exclusive scan of the bucket counts, BPT per thread
         const unsigned tot = sm.n_new;
-        const unsigned ha = sm.boff[2 * threadIdx.x], hb = sm.boff[2 * threadIdx.x + 1];
-        unsigned inc = ha + hb;
+        unsigned hh[C::BPT], hsum = 0, hmax = 0;
+#pragma unroll
+        for (unsigned q = 0; q < C::BPT; ++q) { hh[q] = sm.boff[C::BPT * threadIdx.x + q]; hsum += hh[q]; hmax = max(hmax, hh[q]); }
+        unsigned inc = hsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
         if (lane == 31) sm.wsum[wid] = inc;
-        const int crowded = __syncthreads_or(ha > OK_C2_BUCKET_MAX || hb > OK_C2_BUCKET_MAX);
+        const int crowded = __syncthreads_or(hmax > OK_C2_BUCKET_MAX);
         if (wid == 0) {
             const unsigned w = lane < (int)C::WARPS ? sm.wsum[lane] : 0u;
             unsigned winc = w;
@@ -801,8 +884,9 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
         }
         __syncthreads();
         if (!crowded) {
-            const unsigned excl = sm.wsum[wid] + inc - (ha + hb);
-            sm.boff[2 * threadIdx.x] = excl; sm.boff[2 * threadIdx.x + 1] = excl + ha;
+            unsigned excl = sm.wsum[wid] + inc - hsum;
+#pragma unroll
+            for (unsigned q = 0; q < C::BPT; ++q) { sm.boff[C::BPT * threadIdx.x + q] = excl; excl += hh[q]; }
             __syncthreads();
             // ---- (3) the distinct keys into bucket order (boff[b] ends up as the END of bucket b)
             for (unsigned i = threadIdx.x; i < tot; i += OK_C2_THREADS) {
@@ -831,7 +915,8 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             sm.tkey[s] = OK_EMPTY_KEY;
             reinterpret_cast<unsigned short*>(sm.tcnt)[s] = 0;
         }
-        sm.boff[2 * threadIdx.x] = 0; sm.boff[2 * threadIdx.x + 1] = 0;
+#pragma unroll
+        for (unsigned q = 0; q < C::BPT; ++q) sm.boff[C::BPT * threadIdx.x + q] = 0;
         if (threadIdx.x == 0) { sm.n_new = 0; if (!crowded) n_distinct[p] = tot; }
         __syncthreads();
     }
@@ -860,7 +945,7 @@ k_part_count_generic(unsigned long long* __restrict__ src, const unsigned* __res
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned sub_bits = cfg.b1 + cfg.b2;
     const unsigned n_def = scal->n_deferred;
-    for (unsigned d = blockIdx.x; d < n_def; d += gridDim.x) {
+    for (unsigned d = scal->def_done + blockIdx.x; d < n_def; d += gridDim.x) {
         const unsigned p = deferred[d];
         const unsigned b0 = beg[p];
         const unsigned e0 = min(fill_end[p], cap_end[p]);

@@ -188,7 +188,7 @@ class ShardedCounter:
 
 
 def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config, ClockSampler, measured_peak,
-          metric):
+          metric, numa_node=None):
     import torch.distributed as dist
     K = 31
     n_reads = args.reads
@@ -263,7 +263,7 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
             "config": workload_config(n_reads, genome_len, world),
             "e2e": {"value": total_bases / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3,
                     "h2d_bytes_per_step": int((n_bases + (n_reads + 1) * 8) * world),
-                    "d2h_bytes_per_step": int(16 * distinct)},
+                    "d2h_bytes_per_step": int(16 * distinct), "rank0_numa_node": numa_node},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole step (route + all-to-all + sharded count), rank 0 phases below",
                          "achieved": alg_step / dt / 1e9, "peak": peak * world, "unit": "GB/s",

@@ -415,6 +415,117 @@ def test_partitioned_heavy_duplicates_and_low_complexity(oracle):
         c.close()
 
 
+def test_capacity_hint_sizes_sub_partitions_and_a_wrong_hint_stays_exact(oracle):
+    """With a capacity hint the sub-partitions are sized for their expected DISTINCT keys (several windows per
+    table slot).  A hint far below the truth makes every shared-memory table overflow: the sub-partitions are
+    deferred / spilled / recounted, slower but with the same table."""
+    rng = np.random.default_rng(81)
+    bases, off = random_batch(rng, 6_000_000, 150)            # random bases: nearly every window is distinct
+    wk, wc = oracle.count_batch(31, bases, off)
+    for hint in (50_000, 3_000_000, 10_000_000):
+        c = ok.KmerCounter(31, capacity_hint=hint)
+        c.set_path(2)
+        c.add_batch(bases, off)
+        gk, gc = c.finish()
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc), hint
+        c.close()
+    # 40x coverage with a good hint: ~10 windows per distinct key, large sub-partitions, nothing deferred
+    g = synth.genome(82, 300_000)
+    n_reads = 80_000
+    b2, o2 = synth.reads(g, 83, n_reads), synth.read_offsets(n_reads)
+    wk, wc = oracle.count_batch(31, b2, o2)
+    c = ok.KmerCounter(31, capacity_hint=int(len(wk) * 1.1))
+    c.set_path(2)
+    c.add_batch(b2, o2)
+    gk, gc = c.finish()
+    st = c.stats()
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+    assert st["partitioned"] == 1 and st["n_deferred"] == 0
+    c.close()
+
+
+# ------------------------------------------- deferred host batches: the sliced result pipeline --
+def _sliced_workload():
+    g = synth.genome(71, 4_000_000)
+    n_reads = 160_000                      # 24 M bases: 8192 sub-partitions, 8 result slices
+    return synth.reads(g, 72, n_reads), synth.read_offsets(n_reads)
+
+
+def test_sliced_result_pipeline_matches_oracle(oracle, monkeypatch):
+    """ok_counter_add_batch defers level 2 + count of a large host batch; ok_counter_finish runs them slice
+    by slice under the D2H copy.  Every way out of the deferred state gives the oracle's table."""
+    bases, off = _sliced_workload()
+    wk, wc = oracle.count_batch(31, bases, off)
+    windows = int(wc.sum())
+    # (a) straight through the pipeline
+    c = ok.KmerCounter(31)
+    c.add_batch(bases, off)
+    gk, gc = c.finish()
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+    st = c.stats()
+    assert st["partitioned"] == 1 and st["n_windows"] == windows and st["n_distinct"] == len(wk)
+    # the counter still answers afterwards: device result, filtered result
+    _, _, n = c.finish_device(1)
+    assert n == len(wk)
+    gk, gc = c.finish(3)
+    assert np.array_equal(gk, wk[wc >= 3]) and np.array_equal(gc, wc[wc >= 3])
+    # (b) clear and reuse: stats first (settles the deferred batch), then finish
+    c.clear()
+    c.add_batch(bases, off)
+    assert c.stats()["n_windows"] == windows
+    gk, gc = c.finish()
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+    # (c) min_count > 1 straight from the deferred state
+    c.clear()
+    c.add_batch(bases, off)
+    gk, gc = c.finish(2)
+    assert np.array_equal(gk, wk[wc >= 2]) and np.array_equal(gc, wc[wc >= 2])
+    # (d) a deferred batch that is dropped
+    c.clear()
+    c.add_batch(bases, off)
+    c.clear()
+    assert c.finish()[0].size == 0
+    # (e) a second batch arrives while the first is deferred: both are counted
+    c.add_batch(bases, off)
+    c.add_batch(bases[:150 * 1000], off[:1001])
+    gk, gc = c.finish()
+    o = oracle.Counter(31)
+    o.add_batch(bases, off)
+    o.add_batch(bases[:150 * 1000], off[:1001])
+    ek, ec = o.finish(1)
+    assert np.array_equal(gk, ek) and np.array_equal(gc, ec)
+    c.close()
+    # (f) the undeferred path (what add_batch did before) agrees
+    monkeypatch.setenv("ORION_NO_DEFER", "1")
+    c = ok.KmerCounter(31)
+    c.add_batch(bases, off)
+    gk, gc = c.finish()
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+    c.close()
+
+
+def test_sliced_result_pipeline_misjudged_size_falls_back(oracle):
+    """The result buffers are sized from the first key-range slice.  A batch with (almost) nothing in that
+    slice -- no AA / TT dinucleotides, so no canonical k-mer starts with AA -- overflows the estimate; the
+    pipeline must notice and ship the exact-size result instead."""
+    rng = np.random.default_rng(73)
+    n = 24_000_000
+    seq = rng.integers(0, 4, n).astype(np.uint8)
+    for _ in range(40):                       # break up AA (0,0) and TT (3,3) pairs
+        bad = np.flatnonzero((seq[1:] == seq[:-1]) & ((seq[1:] == 0) | (seq[1:] == 3))) + 1
+        if bad.size == 0:
+            break
+        seq[bad] = rng.integers(1, 3, bad.size)
+    bases = np.frombuffer(b"ACGT", np.uint8)[seq]
+    off = np.arange(0, n + 1, 150, dtype=np.uint64)
+    wk, wc = oracle.count_batch(31, bases, off)
+    c = ok.KmerCounter(31)
+    c.add_batch(bases, off)
+    gk, gc = c.finish()
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+    c.close()
+
+
 # ------------------------------------------------- multi-GPU route / shard logic on one GPU --
 @pytest.mark.parametrize("n_ranks", [2, 4, 8])
 def test_route_and_sharded_counters_concatenate_to_the_global_table(oracle, n_ranks):
