@@ -77,9 +77,19 @@ int ok_canonical_u64(uint64_t kmer, uint8_t k, uint64_t* out);
 
 /* ---- counter (count.rs:23-38,48,106-119 ; classify.rs:135-199) ------------------------- */
 /* k outside 1..=32 -> OK_ERR_INVALID_KMER_SIZE (count.rs:43-45).  capacity_hint = expected
- * number of distinct canonical k-mers (0 = unknown; the table grows as needed). */
+ * number of distinct canonical k-mers (0 = unknown; the table grows as needed).  The hint is a
+ * speed knob only (the reference's DashMap::new() at count.rs:48 takes none): large one-shot
+ * batches are cut into sub-partitions sized for their expected DISTINCT k-mers when a hint is
+ * given (several windows per shared-memory table slot), for their windows otherwise.  A hint
+ * that proves too low costs one recount of the batch and is ignored from then on. */
 int ok_counter_create(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_counter** out);
-/* process_sequence_chunk over every record of the batch; host buffers (pinned or pageable) */
+/* replace the capacity hint (0 = none); for a sharded counter: expected distinct k-mers of its shard */
+int ok_counter_set_capacity_hint(ok_counter* c, uint64_t capacity_hint);
+/* process_sequence_chunk over every record of the batch; host buffers (pinned or pageable).
+ * The buffers are free again when the call returns.  For a large batch into an empty counter
+ * the call returns once the batch has landed and been scattered by key range; the rest of the
+ * count runs inside ok_counter_finish, slice by slice under the device-to-host copy of the
+ * result (or at the next call on the handle that needs the counts). */
 int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const uint64_t* rec_offsets,
                          uint64_t n_records);
 /* same, buffers already resident in device memory (n_bases == rec_offsets[n_records]) */

@@ -98,6 +98,7 @@ ABI = {
     "ok_counter_finish": (C.c_int, [vp, C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]),
     "ok_counter_finish_device": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp), u64p]),
     "ok_counter_set_path": (C.c_int, [vp, C.c_int]),
+    "ok_counter_set_capacity_hint": (C.c_int, [vp, C.c_uint64]),
     "ok_counter_clear": (C.c_int, [vp]),
     "ok_counter_destroy": (C.c_int, [vp]),
     "ok_counter_get_stats": (C.c_int, [vp, C.POINTER(CounterStats)]),
@@ -475,6 +476,10 @@ class KmerCounter:
         dk, dc, n = vp(), vp(), C.c_uint64()
         _check(lib().ok_counter_finish_device(self._h, min_count, C.byref(dk), C.byref(dc), C.byref(n)))
         return dk.value, dc.value, n.value
+
+    def set_capacity_hint(self, capacity_hint):
+        """expected distinct k-mers (0 = none): a speed knob, see include/orion_gpu.h"""
+        _check(lib().ok_counter_set_capacity_hint(self._h, capacity_hint))
 
     def set_path(self, mode):
         """0 automatic, 1 table only, 2 partitioned whenever the counter is empty"""

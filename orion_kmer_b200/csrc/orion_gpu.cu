@@ -133,6 +133,7 @@ struct PartPlan {
 // fused multi-GPU exchange (ok_shard_*): geometry agreed by all ranks + the peer-mapped level-1 buffers
 struct ShardState {
     bool ready = false, buffers = false;
+    bool hinted = false;                     // sub-partitions sized from the capacity hint (expected distinct k-mers of THIS rank's shard)
     unsigned g = 0, sub_bits = 0, b1 = 0, b2 = 0, stride = 16;
     uint64_t n_bases_max = 0, cap_keys = 0;
     unsigned long long* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -488,10 +489,10 @@ constexpr int PART_RETRY = 100;   // internal: the one-shot path gave up, count 
 void part_launch_items(ok_counter* c, PartPlan& pl) {
     if (pl.cfg.b2 == 0) return;
     if (pl.sharded)   // (bin, sender) regions filled by the peers
-        LAUNCH(k_part_items, 1, 1024, 0, c->s_main, c->shard.reg_beg, c->shard.reg_fill, c->shard.reg_end, pl.n_bin1 << c->shard.g,
+        LAUNCH(k_part_items, 32, 1024, 0, c->s_main, c->shard.reg_beg, c->shard.reg_fill, c->shard.reg_end, pl.n_bin1 << c->shard.g,
                pl.n_bin1 - 1u, pl.item_off, pl.item_n, pl.item_bin, pl.scal, (unsigned*)nullptr);
     else
-        LAUNCH(k_part_items, 1, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, 0xFFFFFFFFu, pl.item_off, pl.item_n, pl.item_bin,
+        LAUNCH(k_part_items, 32, 1024, 0, c->s_main, pl.beg1, pl.cursor1, pl.end1, pl.n_bin1, 0xFFFFFFFFu, pl.item_off, pl.item_n, pl.item_bin,
                pl.scal, pl.bin_first);
 }
 
@@ -620,7 +621,8 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
     const uint64_t windows_before = c->windows;
     part_choose_bits(c, n_bases, pl, /*use_hint=*/true);
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
-    pl.stride = n_tiles > 4096 ? 16 : 1;
+    // every `stride`-th tile is sampled; large sub-partitions (sized from a capacity hint) still see > 500 samples each at 1/32
+    pl.stride = n_tiles > 4096 ? (n_bases / pl.n_sub >= 12288 ? 32 : 16) : 1;
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
     TRY(part_layout(c, n_bases, OK_TILE_BASES, 0, pl));
     CU(cudaEventRecord(c->ev_p[0], c->s_main));
@@ -1370,9 +1372,11 @@ OK_EXPORT int ok_shard_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* s
     // what a rank receives is balanced by the canonical prior: plan for 1.25 x the largest batch
     const uint64_t n_units = n_bases_max + n_bases_max / 4;
     PartPlan pl;
-    part_choose_bits(c, n_bases_max, pl);
+    part_choose_bits(c, n_bases_max, pl, /*use_hint=*/true);
+    sh.hinted = pl.hinted;
     unsigned bits = pl.cfg.b1 + pl.cfg.b2;
     sh.b1 = std::min(pl.cfg.b1, 10u - sh.g);                 // sender bins = owners x level-1 bins <= 1024
+    if (sh.b1 >= bits && bits >= 2) sh.b1 = bits / 2;          // the sharded count always runs a second level
     if (const char* ev = getenv("ORION_SHARD_B1")) { unsigned v = (unsigned)atoi(ev); if (v >= 1 && v + sh.g <= 10 && v <= bits) sh.b1 = v; }
     if (bits - sh.b1 > 10) bits = sh.b1 + 10;                // level 2 has at most 1024 bins: larger sub-partitions instead
     sh.b2 = bits - sh.b1; sh.sub_bits = bits;
@@ -1462,7 +1466,9 @@ OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uin
     pl.cfg.key_shift = 64 - 2 * c->k; pl.cfg.shard_log2 = sh.g; pl.cfg.b1 = sh.b1; pl.cfg.b2 = sh.b2;
     pl.n_sub = 1u << sh.sub_bits; pl.n_bin1 = 1u << sh.b1; pl.stride = sh.stride; pl.sharded = true;
     const uint64_t n_units = sh.n_bases_max + sh.n_bases_max / 4;
-    pl.big_count = sh.n_bases_max / pl.n_sub > 5800;     // what arrives is balanced: about one batch worth of k-mers
+    pl.hinted = sh.hinted;
+    pl.big_count = sh.hinted ? std::min<uint64_t>(c->user_hint, sh.n_bases_max) / pl.n_sub > 4600     // expected distinct keys per sub-partition
+                             : sh.n_bases_max / pl.n_sub > 5800;     // what arrives is balanced: about one batch worth of k-mers
     if (const char* ev = getenv("ORION_BIG_COUNT")) pl.big_count = atoi(ev) != 0;
     TRY(part_layout(c, n_units, OK_TILE_BASES, 0, pl));
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
@@ -1549,6 +1555,14 @@ OK_EXPORT int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all
     c->windows = windows_before + c->h_part->received;
     CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
+    if (part_hint_misled(c, pl)) {
+        // the keys came from the peers and are gone: this rank cannot recount alone.  The caller clears the
+        // counter and routes the batch again (multi.py: every rank agrees through one all-reduce).
+        TRY(part_discard(c, windows_before));
+        c->distrust_hint = true; sh.ready = false;
+        return set_err(OK_ERR_INTERNAL, "capacity hint too low for the sharded count (%llu sub-partitions outgrew their tables); "
+                                        "recount the batch: the hint is ignored from now on", (unsigned long long)c->h_part->scal.n_deferred);
+    }
     const int r = part_absorb_spills(c, windows_before);
     return r == PART_RETRY ? set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list") : r;
 }
@@ -1624,6 +1638,14 @@ OK_EXPORT int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** km
         CU(cudaStreamSynchronize(c->s_copy));
     }
     *kmers = (uint64_t*)hk; *counts = (uint64_t*)hc; *n = total;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_counter_set_capacity_hint(ok_counter* c, uint64_t capacity_hint) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_set_capacity_hint: NULL handle");
+    c->user_hint = capacity_hint; c->distrust_hint = false;
+    if (capacity_hint > c->hint) c->hint = capacity_hint;
+    c->shard.ready = false;            // a sharded geometry derived from the old hint is void
     return OK_SUCCESS;
 }
 

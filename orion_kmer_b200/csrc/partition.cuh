@@ -235,7 +235,8 @@ k_part_slice_fill(const unsigned* __restrict__ beg, const unsigned* __restrict__
     if (threadIdx.x == 0) *host_out = t;
 }
 
-// one CTA, 1024 threads: level-1 fills -> work items of <= OK_PART_TILE keys for the level-2 scatter
+// CTAs of 1024 threads (each repeats the cheap scan over the bins, then builds its share of the items):
+// level-1 fills -> work items of <= OK_PART_TILE keys for the level-2 scatter
 __global__ void __launch_bounds__(1024)
 k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cursor1, const unsigned* __restrict__ end1,
              unsigned n_bin1, unsigned bin_mask, unsigned* __restrict__ item_off, unsigned* __restrict__ item_n,
@@ -251,9 +252,9 @@ k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cur
     const unsigned first = ok_block_excl_scan_1024(ni, wsum, &total);
     s_first[b] = first; s_b0[b] = b0; s_fill[b] = fill;
     if (b == 0) s_first[OK_PART_MAXBINS] = total;
-    if (bin_first) { bin_first[b] = first; if (b == 0) bin_first[OK_PART_MAXBINS] = total; }   // bins past n_bin1 hold no items: first == total
+    if (bin_first && blockIdx.x == 0) { bin_first[b] = first; if (b == 0) bin_first[OK_PART_MAXBINS] = total; }   // bins past n_bin1 hold no items: first == total
     __syncthreads();
-    for (unsigned o = threadIdx.x; o < total; o += 1024u) {     // item o belongs to the last bin whose first item is <= o
+    for (unsigned o = blockIdx.x * 1024u + threadIdx.x; o < total; o += gridDim.x * 1024u) {     // item o belongs to the last bin whose first item is <= o
         unsigned lo = 0, hi = OK_PART_MAXBINS - 1u;
         while (lo < hi) { const unsigned mid = (lo + hi + 1u) >> 1; if (s_first[mid] <= o) lo = mid; else hi = mid - 1u; }
         const unsigned i = o - s_first[lo];
@@ -261,7 +262,7 @@ k_part_items(const unsigned* __restrict__ beg1, const unsigned* __restrict__ cur
         item_n[o] = min(OK_PART_TILE, s_fill[lo] - i * OK_PART_TILE);
         item_bin[o] = lo & bin_mask;
     }
-    if (threadIdx.x == 0) sc->n_items = total;
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc->n_items = total;
 }
 
 // ------------------------------------------------------- sharded (multi-GPU) planning kernels --

@@ -36,10 +36,13 @@ class ShardedCounter:
     receive buffer (CUDA-IPC peer memory over NVLink); the only collectives left are a world x world
     count matrix and a barrier.  fused=False: bucket locally, NCCL all_to_all_single, then count."""
 
-    def __init__(self, ok, torch, dist, k, norm_mode=0, fused=2):
+    def __init__(self, ok, torch, dist, k, norm_mode=0, fused=2, capacity_hint=0):
         self.ok, self.torch, self.dist = ok, torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.counter = ok.KmerCounter(k, norm_mode)
+        # capacity_hint = expected distinct k-mers of THIS rank's shard (0: none): sizes the sub-partitions for their
+        # distinct keys (fewer bins per scatter level); a hint that proves too low costs one recount, then it is ignored
+        self.counter = ok.KmerCounter(k, norm_mode, capacity_hint)
+        self.hinted = capacity_hint > 0
         self.counter.set_shard(self.rank, self.world)
         # 2: sharded scatter (sample, then ONE extraction pass that writes level-1 partitioned k-mers into
         #    the owners' buffers); 1: two-pass fused route (count, then scatter by owner); 0: NCCL all-to-all
@@ -128,7 +131,22 @@ class ShardedCounter:
         if not all_ok:          # a sampled region overflowed somewhere: every rank recounts through the exact route
             self.counter.clear()
             return self._count_unfused(d_bases, n_bases, d_off, n_reads)
-        self.counter.shard_count_device(g["cur_all"].data_ptr())
+        count_ok = 1
+        try:
+            self.counter.shard_count_device(g["cur_all"].data_ptr())
+        except self.ok.OrionError:
+            if not self.hinted:
+                raise
+            count_ok = 0
+        if self.hinted:         # a capacity hint that is too low only shows once the shared-memory tables overflow
+            g["flag"].fill_(count_ok)
+            dist.all_reduce(g["flag"], op=dist.ReduceOp.MIN)
+            if not int(g["flag"].item()):
+                self.fallbacks = getattr(self, "fallbacks", 0) + 1
+                self.counter.clear()
+                self.counter.set_capacity_hint(0)      # every rank drops the hint: the geometry must stay collective
+                self.hinted, self.geom = False, None
+                return self._count_unfused(d_bases, n_bases, d_off, n_reads)
         t4 = time.perf_counter()
         st = self.counter.stats()
         self.t = {"route_ms": (t2 - t0) * 1e3, "route_count_ms": (t1 - t0) * 1e3, "route_scatter_ms": (t2 - t1) * 1e3,
@@ -199,7 +217,8 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
     h_off = torch.from_numpy(off.view(np.int64))
     d_bases = h_bases.cuda()
     d_off = h_off.cuda()
-    sc = ShardedCounter(ok, torch, dist, K, fused=int(os.environ.get("ORION_FUSED", "2")))
+    hint = args.hint or int(n_bases * 0.17)       # expected distinct k-mers per rank (30x coverage, 0.5 % errors)
+    sc = ShardedCounter(ok, torch, dist, K, fused=int(os.environ.get("ORION_FUSED", "2")), capacity_hint=hint)
 
     def step_device():
         sc.clear()

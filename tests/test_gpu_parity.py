@@ -567,56 +567,89 @@ def test_route_and_sharded_counters_concatenate_to_the_global_table(oracle, n_ra
 
 
 # --------------------------- fused multi-GPU exchange (sharded scatter), all ranks emulated on one GPU --
-@pytest.mark.parametrize("n_ranks", [2, 4, 8])
-def test_sharded_scatter_matches_oracle(oracle, n_ranks):
-    """ok_shard_*: every rank samples, the histograms are 'exchanged' (torch ops stand in for the
-    reduce-scatter / all-gathers), every sender scatters into the owners' level-1 regions, every owner
-    counts what arrived.  The ranks' outputs must concatenate to the oracle's table of all batches."""
+def _sharded_dance(counters, batches, n):
+    """one sharded count step of every emulated rank: sample, 'exchange' the histograms (torch ops stand in for
+    the reduce-scatter / all-gathers), scatter into the owners' level-1 regions, count what arrived"""
     import torch
-    k = 31
-    g = synth.genome(80, 400_000)
-    n = 12_000                                   # reads per rank: 1.8 M bases -> partitioned geometry
-    batches = [(synth.reads(g, 81, n, first_read=r * n), synth.read_offsets(n)) for r in range(n_ranks)]
+    n_ranks = len(counters)
     dev = [(torch.from_numpy(b).cuda(), torch.from_numpy(o.view(np.int64)).cuda()) for b, o in batches]
-    counters = [ok.KmerCounter(k) for _ in range(n_ranks)]
-    for r, c in enumerate(counters):
-        c.set_shard(r, n_ranks)
     nmax = max(len(b) for b, _ in batches)
     geoms = [c.shard_geometry(nmax) for c in counters]
     assert len(set(geoms)) == 1
     sub_bits, l1_bits, cap = geoms[0]
     bufs = [ok.PeerBuffer(cap * 8) for _ in range(n_ranks)]
-    for c in counters:
-        c.shard_set_buffers([b.ptr for b in bufs], cap)
-    i32 = dict(dtype=torch.int32, device="cuda")
-    hist_fine = [torch.empty(n_ranks << sub_bits, **i32) for _ in range(n_ranks)]
-    hist_l1 = [torch.empty(n_ranks << l1_bits, **i32) for _ in range(n_ranks)]
+    try:
+        for c in counters:
+            c.shard_set_buffers([b.ptr for b in bufs], cap)
+        i32 = dict(dtype=torch.int32, device="cuda")
+        hist_fine = [torch.empty(n_ranks << sub_bits, **i32) for _ in range(n_ranks)]
+        hist_l1 = [torch.empty(n_ranks << l1_bits, **i32) for _ in range(n_ranks)]
+        for r, c in enumerate(counters):
+            c.shard_sample_device(dev[r][0].data_ptr(), len(batches[r][0]), dev[r][1].data_ptr(), n,
+                                  hist_fine[r].data_ptr(), hist_l1[r].data_ptr())
+        hist_sum = torch.stack(hist_fine).sum(0, dtype=torch.int32)
+        l1_all = torch.cat(hist_l1).contiguous()
+        cursors = [torch.empty(n_ranks << l1_bits, **i32) for _ in range(n_ranks)]
+        for r, c in enumerate(counters):
+            mine = hist_sum[r << sub_bits:(r + 1) << sub_bits].contiguous()
+            c.shard_scatter_device(dev[r][0].data_ptr(), len(batches[r][0]), dev[r][1].data_ptr(), n,
+                                   mine.data_ptr(), l1_all.data_ptr(), cursors[r].data_ptr())
+        cur_all = torch.cat(cursors).contiguous()
+        keys, counts = [], []
+        for r, c in enumerate(counters):
+            c.shard_count_device(cur_all.data_ptr())
+            gk, gc = c.finish()
+            assert c.stats()["n_spilled"] == 0
+            keys.append(gk); counts.append(gc)
+        return np.concatenate(keys), np.concatenate(counts), sub_bits
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            b.destroy()
+
+
+@pytest.mark.parametrize("n_ranks", [2, 4, 8])
+@pytest.mark.parametrize("hint", [0, 600_000])
+def test_sharded_scatter_matches_oracle(oracle, n_ranks, hint):
+    """ok_shard_*: every rank samples, the histograms are exchanged, every sender scatters into the owners'
+    level-1 regions, every owner counts what arrived.  The ranks' outputs must concatenate to the oracle's
+    table of all batches.  hint: sub-partitions sized for their expected distinct keys."""
+    k = 31
+    g = synth.genome(80, 400_000)
+    n = 12_000                                   # reads per rank: 1.8 M bases -> partitioned geometry
+    batches = [(synth.reads(g, 81, n, first_read=r * n), synth.read_offsets(n)) for r in range(n_ranks)]
+    counters = [ok.KmerCounter(k, capacity_hint=hint) for _ in range(n_ranks)]
     for r, c in enumerate(counters):
-        c.shard_sample_device(dev[r][0].data_ptr(), len(batches[r][0]), dev[r][1].data_ptr(), n,
-                              hist_fine[r].data_ptr(), hist_l1[r].data_ptr())
-    hist_sum = torch.stack(hist_fine).sum(0, dtype=torch.int32)
-    l1_all = torch.cat(hist_l1).contiguous()
-    cursors = [torch.empty(n_ranks << l1_bits, **i32) for _ in range(n_ranks)]
-    for r, c in enumerate(counters):
-        mine = hist_sum[r << sub_bits:(r + 1) << sub_bits].contiguous()
-        c.shard_scatter_device(dev[r][0].data_ptr(), len(batches[r][0]), dev[r][1].data_ptr(), n,
-                               mine.data_ptr(), l1_all.data_ptr(), cursors[r].data_ptr())
-    cur_all = torch.cat(cursors).contiguous()
-    keys, counts = [], []
-    for r, c in enumerate(counters):
-        c.shard_count_device(cur_all.data_ptr())
-        gk, gc = c.finish()
-        assert c.stats()["n_spilled"] == 0
-        keys.append(gk); counts.append(gc)
+        c.set_shard(r, n_ranks)
+    gk, gc, _ = _sharded_dance(counters, batches, n)
     for c in counters:
         c.close()
-    for b in bufs:
-        b.destroy()
     all_bases = np.concatenate([b for b, _ in batches])
     all_off = synth.read_offsets(n * n_ranks)
     wk, wc = oracle.count_batch(k, all_bases, all_off)
-    assert np.array_equal(np.concatenate(keys), wk)
-    assert np.array_equal(np.concatenate(counts), wc)
+    assert np.array_equal(gk, wk)
+    assert np.array_equal(gc, wc)
+
+
+def test_sharded_count_with_a_hint_far_too_low_asks_for_a_recount(oracle):
+    """the shared-memory tables overflow, the keys came from the peers: the rank reports it, the caller clears,
+    drops the hint on every rank and counts the batch again"""
+    k, n_ranks, n = 31, 2, 12_000
+    rng = np.random.default_rng(84)           # random bases: every window distinct, ~14 K keys per sub-partition
+    batches = [(np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n * 150)], synth.read_offsets(n)) for r in range(n_ranks)]
+    counters = [ok.KmerCounter(k, capacity_hint=2_000) for _ in range(n_ranks)]
+    for r, c in enumerate(counters):
+        c.set_shard(r, n_ranks)
+    with pytest.raises(ok.OrionError, match="capacity hint too low"):
+        _sharded_dance(counters, batches, n)
+    for c in counters:
+        c.clear()
+        c.set_capacity_hint(0)
+    gk, gc, _ = _sharded_dance(counters, batches, n)
+    for c in counters:
+        c.close()
+    wk, wc = oracle.count_batch(k, np.concatenate([b for b, _ in batches]), synth.read_offsets(n * n_ranks))
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
 
 
 def test_large_table_count_kernel_variant(oracle, monkeypatch):
