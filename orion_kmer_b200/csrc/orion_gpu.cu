@@ -40,7 +40,8 @@ int set_err(int code, const char* fmt, ...) {
 
 int g_device = -1;
 int g_sms = 0;
-int g_count_seed = 1;      // ORION_COUNT_SEED: 1 = seed round in the count kernel (measured 8.66 -> 7.86 ms), 0 = none, 2 = first round unqueued
+int g_scatter_p3 = 1;       // ORION_SCATTER_P3: 3 rounds per warp-tile in the level-1 scatter when it has <= 256 bins
+int g_count_seed = 2;      // ORION_COUNT_SEED bits: 1 = seed round of one key per thread, 2 = first round unqueued (measured: 0 8.66, 1 7.42, 2 7.21 ms)
 std::atomic<uint64_t> g_launches{0};
 std::mutex g_mu;
 
@@ -434,6 +435,7 @@ void part_choose_bits(ok_counter* c, uint64_t n_units, PartPlan& pl, bool use_hi
 
 // kernels specialised on k: 31 and 21 (BASELINE.json's configurations) get compile-time shifts, any other k the generic code
 #define OK_BY_K(k, KERN, ...) ((k) == 31 ? KERN<__VA_ARGS__, 31> : (k) == 21 ? KERN<__VA_ARGS__, 21> : KERN<__VA_ARGS__, 0>)
+#define OK_BY_K3(k, KERN, ...) ((k) == 31 ? KERN<__VA_ARGS__, 31, true> : (k) == 21 ? KERN<__VA_ARGS__, 21, true> : KERN<__VA_ARGS__, 0, true>)
 
 template <class K> int set_smem(K kern, size_t bytes) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -518,19 +520,19 @@ int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, boo
     if (whole) CU(cudaEventRecord(c->ev_p[3], c->s_main));
     // count every sub-partition in shared memory; sorted runs land in place, counts in d_buf1
     unsigned* d_nd = pl.hist;   // the sample histogram is no longer needed (k_part_plan zeroed it)
-    unsigned long long* cnt_out = c->buf1_external ? c->d_cnt : c->d_buf1;
+    unsigned* cnt_out = reinterpret_cast<unsigned*>(c->buf1_external ? c->d_cnt : c->d_buf1);   // 32-bit counts, same indices as the keys
     if (pl.big_count) {
         auto k_cnt = OK_BY_K(c->k, k_part_count, 14);
         TRY(set_smem(k_cnt, sizeof(OkCount2Smem<14>)));
         LAUNCH(k_cnt, std::min<unsigned>(p1 - p0, grid_sm), OkCount2Cfg<14>::THREADS, sizeof(OkCount2Smem<14>), c->s_main,
                c->d_buf2, pl.beg, pl.cursor, pl.cap_end, p0, p1, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal,
-               g_count_seed == 1 ? OkCount2Cfg<14>::THREADS : 0u, g_count_seed == 2);
+               (g_count_seed & 1) ? OkCount2Cfg<14>::THREADS : 0u, (g_count_seed & 2) != 0);
     } else {
         auto k_cnt = OK_BY_K(c->k, k_part_count, 13);
         TRY(set_smem(k_cnt, sizeof(OkCount2Smem<13>)));
         LAUNCH(k_cnt, std::min<unsigned>(p1 - p0, grid_sm * 2), OkCount2Cfg<13>::THREADS, sizeof(OkCount2Smem<13>), c->s_main,
                c->d_buf2, pl.beg, pl.cursor, pl.cap_end, p0, p1, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal,
-               g_count_seed == 1 ? OkCount2Cfg<13>::THREADS : 0u, g_count_seed == 2);
+               (g_count_seed & 1) ? OkCount2Cfg<13>::THREADS : 0u, (g_count_seed & 2) != 0);
     }
     const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
     TRY(set_smem(k_part_count_generic, ct_smem));
@@ -641,6 +643,9 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
     {
         const bool two = pl.cfg.b2 > 0;
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? OK_BY_K(c->k, k_part_scatter_bases, true, false) : OK_BY_K(c->k, k_part_scatter_bases, false, false);
+        const unsigned bins1 = 1u << (two ? pl.cfg.b1 : pl.cfg.b1 + pl.cfg.b2);
+        if (bins1 <= 256 && g_scatter_p3)      // 32 staging slots per bin: three fuller rounds per warp-tile instead of four
+            kern = c->norm_mode == OK_NORM_NORMALIZED ? OK_BY_K3(c->k, k_part_scatter_bases, true, false) : OK_BY_K3(c->k, k_part_scatter_bases, false, false);
         TRY(set_smem(kern, sizeof(OkScatterSmem)));
         const uint64_t max_warps = (uint64_t)grid_sm * (OK_SB_KPT == 16 ? 3 : 2) * OK_SB_WARPS;   // resident warps (72 KB smem per CTA)
         const uint64_t n_launch = pieces ? pieces->n_pieces : 1;
@@ -713,7 +718,7 @@ void launch_compact(ok_counter* c, unsigned p0, unsigned p1, unsigned long long*
                     cudaStream_t stream = nullptr) {
     const PartPlan& pl = c->pl;
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
-    LAUNCH(k_part_compact, std::min<unsigned>(p1 - p0, grid_sm * 8), 256, 0, stream ? stream : c->s_main, c->d_buf2, c->buf1_external ? c->d_cnt : c->d_buf1, pl.beg, pl.hist,
+    LAUNCH(k_part_compact, std::min<unsigned>(p1 - p0, grid_sm * 8), 256, 0, stream ? stream : c->s_main, c->d_buf2, reinterpret_cast<const unsigned*>(c->buf1_external ? c->d_cnt : c->d_buf1), pl.beg, pl.hist,
            pl.scan, p0, p1, out_keys, out_counts);
 }
 
@@ -973,6 +978,7 @@ OK_EXPORT int ok_init(const int* device_ids, int n_devices) {
     g_sms = prop.multiProcessorCount;
     g_device = dev;
     if (const char* ev = getenv("ORION_COUNT_SEED")) g_count_seed = atoi(ev);
+    if (const char* ev = getenv("ORION_SCATTER_P3")) g_scatter_p3 = atoi(ev);
     if (const char* ev = getenv("ORION_SLICES")) { const int v = atoi(ev); if (v >= 4 && v <= 60) RESULT_SLICES = (unsigned)v; }
     return OK_SUCCESS;
 }

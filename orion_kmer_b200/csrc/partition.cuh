@@ -22,6 +22,7 @@
 // multisplits: every thread holds 16 k-mers in registers, ranks them with one smem atomicAdd
 // each, the tile is staged in shared memory in bin order and copied out in runs.
 #pragma once
+#include <type_traits>
 #include "kernels.cuh"
 
 #define OK_PART_TILE 4096u        // keys per CTA round of a scatter (256 threads x 16)
@@ -392,7 +393,7 @@ __device__ __forceinline__ void ok_part_put(unsigned long long key, unsigned dst
 // key[0..KPT) (bit q of vmask says key[q] exists) -> out, grouped by bin.  sm.hg[].x must be zero
 // on entry and is zero again on exit.  after_stage() runs once the round's keys have left the
 // registers of every thread (the level-2 kernel issues its next TMA load there).
-template <int LEVEL, bool PEER, int KPT, class AfterStage>
+template <int LEVEL, bool PEER, int KPT, class AfterStage, unsigned NW = OK_PART_TILE / KPT / 32u /* warps of the CTA */>
 __device__ __forceinline__ void ok_multisplit(OkScatterSmem& sm, const uint64_t (&key)[KPT], unsigned vmask,
                                                 const OkPartCfg& cfg, unsigned bins_log2,
                                                 unsigned* __restrict__ cursors, const unsigned* __restrict__ bin_end,
@@ -414,7 +415,6 @@ __device__ __forceinline__ void ok_multisplit(OkScatterSmem& sm, const uint64_t 
     after_stage();
     // copy out.  Warp w owns an equal share of the staging slots = a contiguous range of bins.
     // (1) one global cursor bump per non-empty bin; a bin whose region is full spills its tail here
-    constexpr unsigned NW = OK_PART_TILE / KPT / 32u;      // warps of the CTA: 8 (16 keys per thread) or 16 (8 keys per thread)
     const unsigned bins_per_warp = n_bins >= NW ? n_bins / NW : 1u;
     const unsigned wb0 = wid * bins_per_warp;
     for (unsigned i = lane; i < bins_per_warp && wb0 + i < n_bins; i += 32) {
@@ -434,7 +434,28 @@ __device__ __forceinline__ void ok_multisplit(OkScatterSmem& sm, const uint64_t 
     }
     __syncwarp();
     // (2) dense walk over the warp's staging slots: consecutive lanes = consecutive slots of a bin
-    if (wb0 < n_bins) {
+    if (NW == 16u && cap_log2 >= 3u && cap_log2 <= 5u) {
+        // 256 / 512 / 1024 bins with 16 warps: every warp owns 512 staging slots = 16 passes of 32 lanes, a pass covers
+        // 1 / 2 / 4 whole bins.  Unrolled with the slots-per-bin as a constant, the staging and header addresses become
+        // immediates and the slot -> rank rotation one subtraction per pass: ~9 instructions per pass instead of 17
+        // in the generic walk below (the copy-out was 28 % of the level-1 scatter's instructions).
+        auto walk = [&](auto cl2) {
+            constexpr unsigned C = decltype(cl2)::value, BPP = 32u >> C /* bins per pass */, M = (1u << C) - 1u;
+            const unsigned sub = lane >> C;
+            const unsigned long long* __restrict__ st = sm.stage + (wb0 << C) + lane;
+            const uint2* __restrict__ hg = sm.hg + wb0 + sub;
+            unsigned r = ((lane & M) - wb0 - sub) & M;
+#pragma unroll 8
+            for (int it = 0; it < 16; ++it) {
+                const uint2 h = hg[it * BPP];
+                if (r < h.x) (PEER ? peer->p[(wb0 + sub + it * BPP) >> peer->shift] : out)[h.y + r] = st[it * 32];
+                r = (r - BPP) & M;
+            }
+        };
+        if (cap_log2 == 5u) walk(std::integral_constant<unsigned, 5>{});
+        else if (cap_log2 == 4u) walk(std::integral_constant<unsigned, 4>{});
+        else walk(std::integral_constant<unsigned, 3>{});
+    } else if (wb0 < n_bins) {
         const unsigned t_end = (wb0 + bins_per_warp) << cap_log2;
 #pragma unroll 4
         for (unsigned t = (wb0 << cap_log2) + lane; t < t_end; t += 32) {
@@ -513,7 +534,10 @@ __global__ void __launch_bounds__(256) k_shard_push(const __grid_constant__ OkPu
 // The launch covers tiles [tile_begin, tile_end) -- the ingest pipeline launches it once per landed piece.
 // KC: k as a compile-time constant (31 and 21, the configurations of BASELINE.json; 0 = any k at run time).
 // With k fixed the 64-bit shifts of the rolling update and of the position become immediate-operand funnel shifts.
-template <bool MAP_U, bool PEER = false, int KC = 0>
+// P3: a warp-tile (32 window ends per lane) is split in 3 rounds of 11/11/10 instead of 4 rounds of 8: the 8192 staging
+// slots are filled to ~2/3 instead of 1/2 per round (fewer empty slots walked by the copy-out, fewer barriers and cursor
+// bumps per key).  Only for <= 256 bins (32 slots per bin: a bin overflows its slots in < 2 % of the rounds).
+template <bool MAP_U, bool PEER = false, int KC = 0, bool P3 = false>
 __global__ void __launch_bounds__(PEER ? OK_SB_THREADS + 32 : OK_SB_THREADS, OK_SB_KPT == 16 ? 3 : 2)
 k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
                      uint64_t n_rec, uint64_t tile_begin, uint64_t tile_end, uint64_t tiles_per_warp, unsigned k_in,
@@ -541,13 +565,15 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
             OkRoll roll; roll.init(pc, cc, k);
             my_keys += __popc(okmask);
             const unsigned rev = __brev(okmask);      // window end j lives in okmask bit 31-j: bit j of rev
+            constexpr int KP = P3 ? 11 : OK_SB_KPT, NP = P3 ? 3 : 32 / OK_SB_KPT;
 #pragma unroll
-            for (int part = 0; part < 32 / OK_SB_KPT; ++part) {
-                uint64_t key[OK_SB_KPT];
+            for (int part = 0; part < NP; ++part) {
+                uint64_t key[KP];
 #pragma unroll
-                for (int q = 0; q < OK_SB_KPT; ++q) key[q] = roll.step(OK_SB_KPT * part + q);
-                const unsigned vm = rev >> (OK_SB_KPT * part) & ((1u << OK_SB_KPT) - 1u);   // bit q <=> key[q]
-                ok_multisplit<1, PEER, OK_SB_KPT>(sm, key, vm, cfg, cfg.b1, cursors, bin_end, out, ps, &peer_out, [] {});
+                for (int q = 0; q < KP; ++q) key[q] = KP * part + q < 32 ? roll.step(KP * part + q) : 0ull;
+                const unsigned vm = rev >> (KP * part) & ((1u << KP) - 1u);   // bit q <=> key[q]; window ends past 31 do not exist
+                auto nop = [] {};
+                ok_multisplit<1, PEER, KP, decltype(nop)&, OK_SB_WARPS>(sm, key, vm, cfg, cfg.b1, cursors, bin_end, out, ps, &peer_out, nop);
             }
         });
     my_keys = ok_warp_sum(my_keys);
@@ -751,7 +777,7 @@ __global__ void __launch_bounds__(OkCount2Cfg<LOG2>::THREADS, LOG2 == 13 ? 2 : 1
 k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ beg,
              const unsigned* __restrict__ fill_end /* cursor after the scatter */,
              const unsigned* __restrict__ cap_end, unsigned p_begin, unsigned p_end, OkPartCfg cfg_in,
-             unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct,
+             unsigned* __restrict__ cnt_out /* 32-bit counts of the runs, same indices as src */, unsigned* __restrict__ n_distinct,
              unsigned* __restrict__ deferred, OkPartScalars* __restrict__ scal, unsigned seed_keys /* 0 or THREADS */,
              bool direct_first) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -808,6 +834,7 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
         // used to miss, queue up and take the slow path even though most of those keys are duplicates of
         // one another.  Seeding the table with 1/8 of the keys first (at 30x coverage ~95 % of the repeated
         // k-mers are among them) lets the rounds that follow hit on their first probe.
+        // (16-byte loads of key pairs were measured SLOWER here: 8.0 vs 7.4 ms; the four 8-byte loads stay)
         unsigned long long nx[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -833,7 +860,7 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) { hs[q] = ok_c2_hash<LOG2>(kk[q]); cur[q] = sm.tkey[hs[q]]; }
-            if (direct_first && base == 0) {     // empty table: no first probe can hit, skip the queue
+            if (direct_first && base == seed_keys) {     // empty table: no first probe can hit, skip the queue
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if (kk[q] != OK_EMPTY_KEY) ok_c2_insert_slow(sm, kk[q], hs[q], sm.tkey[hs[q]], cfg, sub_bits);
@@ -935,7 +962,7 @@ __global__ void __launch_bounds__(OK_CT_THREADS, 2)
 k_part_count_generic(unsigned long long* __restrict__ src, const unsigned* __restrict__ beg,
                      const unsigned* __restrict__ fill_end, const unsigned* __restrict__ cap_end,
                      const unsigned* __restrict__ deferred, const OkPartScalars* __restrict__ scal, OkPartCfg cfg,
-                     unsigned long long* __restrict__ cnt_out, unsigned* __restrict__ n_distinct, OkPartSpill ps) {
+                     unsigned* __restrict__ cnt_out, unsigned* __restrict__ n_distinct, OkPartSpill ps) {
     constexpr unsigned NT = OK_CT_SLOTS + OK_CT_PAD;            // 8704
     constexpr unsigned ROUNDS = NT / OK_CT_THREADS;             // 17 strided rounds in the sweep
     constexpr unsigned NW = OK_CT_THREADS / 32;                 // 16 warps
@@ -1042,7 +1069,7 @@ k_part_count_generic(unsigned long long* __restrict__ src, const unsigned* __res
 // sub-partition runs -> final arrays; base[p] = exclusive scan of n_distinct (as u64).
 // Sub-partitions [p_begin, p_end): the result pipeline compacts and ships the table in slices.
 __global__ void __launch_bounds__(256)
-k_part_compact(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ counts,
+k_part_compact(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ counts /* 32-bit, widened here */,
                const unsigned* __restrict__ beg, const unsigned* __restrict__ n_distinct,
                const unsigned long long* __restrict__ base, unsigned p_begin, unsigned p_end,
                unsigned long long* __restrict__ out_keys, unsigned long long* __restrict__ out_counts) {
