@@ -635,6 +635,7 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_sample<true> : k_part_sample<false>;
         LAUNCH(kern, blocks, 256, 0, c->s_main, sample_src, n_bases, d_off, n_rec, n_tiles, (uint64_t)pl.stride, c->k, pl.cfg, pl.hist,
                /*halo=*/sample_src == d_bases);
+        CU(cudaEventRecord(c->ev_b, c->s_main));   // the last reader of sample_src (possibly the caller's own buffer, zero-copy)
     }
     LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.chunk_sum);
     LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.cfg.b2,
@@ -865,6 +866,10 @@ int part_finish_sliced(ok_counter* c, uint64_t** kmers, uint64_t** counts, uint6
     TRY(issue(0));
     if (n_slices > 1) TRY(issue(1));
     void *hk = nullptr, *hc = nullptr;
+    struct Blocks {                      // page-locked result blocks go back to the pool unless they are handed to the caller
+        void *&k, *&c; bool keep = false;
+        ~Blocks() { if (!keep) { if (k) pool_release(k); if (c) pool_release(c); } }
+    } blocks{hk, hc};
     uint64_t cap = 0;
     bool shipping = true;
     for (unsigned i = 0; i < n_slices; ++i) {
@@ -911,8 +916,6 @@ int part_finish_sliced(ok_counter* c, uint64_t** kmers, uint64_t** counts, uint6
     c->run_state = RUN_SPARSE;
     const bool spilled = c->h_stats->spill_n != 0;
     if (part_hint_misled(c, pl)) {       // see part_hint_misled: count the batch again, sized from its windows
-        if (hk) pool_release(hk);
-        if (hc) pool_release(hc);
         TRY(part_discard(c, c->pend_windows_before));
         c->distrust_hint = true;
         const int r = part_count_bases(c, c->d_bases, c->pend_bases, c->d_off, c->pend_rec, c->d_bases, nullptr, false);
@@ -921,11 +924,9 @@ int part_finish_sliced(ok_counter* c, uint64_t** kmers, uint64_t** counts, uint6
     if (shipping && !spilled) {
         c->run_state = RUN_DENSE;
         *kmers = (uint64_t*)hk; *counts = (uint64_t*)hc; *n = total;
-        *shipped = true;
+        *shipped = true; blocks.keep = true;
         return OK_SUCCESS;
     }
-    if (hk) pool_release(hk);
-    if (hc) pool_release(hc);
     {   // slice boundaries for the exact-size result path of ok_counter_finish
         const unsigned fstep = std::max<unsigned>(1, pl.n_sub / RESULT_SLICES);
         pl.n_slices = (pl.n_sub + fstep - 1) / fstep; pl.slice_step = fstep;
@@ -1165,7 +1166,10 @@ OK_EXPORT int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const ui
         // Deferred: level 2, count and compaction run in ok_counter_finish, slice by slice under the D2H copy
         // of the result (or in part_settle, if anything else is asked of the counter first).
         const int r = part_count_bases(c, c->d_bases, n_bases, c->d_off, n_records, sample_src, &ps, /*defer=*/true);
-        if (r == OK_SUCCESS && c->run_state == RUN_LEVEL1) CU(cudaStreamSynchronize(c->s_copy));   // the caller's buffers are free again
+        if (r == OK_SUCCESS && c->run_state == RUN_LEVEL1) {     // deferred: return as soon as the caller's buffers are free again
+            CU(cudaStreamSynchronize(c->s_copy));               //   every piece has landed
+            CU(cudaEventSynchronize(c->ev_b));                  //   and the sampling kernel (zero-copy reads of `bases`) is done
+        }
         if (r != PART_RETRY) { if (r == OK_SUCCESS) c->bases_seen += n_bases; return r; }
     }
     TRY(run_to_table(c));
