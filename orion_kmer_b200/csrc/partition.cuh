@@ -368,9 +368,6 @@ k_shard_fills(const unsigned* __restrict__ cur_all, unsigned g_log2, unsigned me
 // A bin that outgrows its slots in a round sends the excess straight to global memory.
 // CTA barrier of the scatter threads.  The sharded (PEER) scatter carries one extra warp that only
 // copies to the peers and never joins these barriers, hence a named barrier with an explicit count.
-#ifndef OK_MS_GROUP
-#define OK_MS_GROUP 4                                 // keys ranked together before their staging stores (see ok_multisplit)
-#endif
 #ifndef OK_SB_KPT
 #define OK_SB_KPT 8                                   // keys per thread and round in the level-1 scatter
 #endif
@@ -404,36 +401,18 @@ __device__ __forceinline__ void ok_multisplit(OkScatterSmem& sm, const uint64_t 
                                                 const OkPeerOut* peer, AfterStage&& after_stage) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned cap_log2 = 13u - bins_log2, cap = 1u << cap_log2, n_bins = 1u << bins_log2;
-    // Rank first, store after: the shared-memory atomics of a group of keys are issued back to back and their
-    // latencies overlap.  (Ranked and stored key by key, every store waited for its own atomic's return and the
-    // next atomic -- possibly aliasing the store as far as the compiler knows -- waited for the store: 8 or 11
-    // serialised round trips per thread and round, the top stall of both scatters in the ncu source view.)
-    constexpr int GROUP = OK_MS_GROUP;
-    constexpr unsigned NO_KEY = 0xFFFFFFFFu, OVERFLOW = 0xFFFFFFFEu;
+    // (Ranking a group of keys first and storing them afterwards, so that the shared-memory atomics overlap, was
+    // measured SLOWER: level 1 5.8 -> 6.4 ms, level 2 3.8 -> 4.1 ms.  Key by key it stays.)
 #pragma unroll
-    for (int g0 = 0; g0 < KPT; g0 += GROUP) {
-        unsigned slot[GROUP];
-#pragma unroll
-        for (int q = g0; q < g0 + GROUP && q < KPT; ++q) {
-            slot[q - g0] = NO_KEY;
-            if (vmask >> q & 1u) {
-                const unsigned b = ok_part_bin<LEVEL>(key[q], cfg);
-                const unsigned r = atomicAdd(&sm.hg[b].x, 1u);
-                // rank r of bin b sits in slot (r + b) mod cap of the bin: without the rotation the bank of a staged
-                // key depends on r alone and most ranks are 0..3, an 8-way conflict on every store (548 M per pass, ncu)
-                slot[q - g0] = r < cap ? (b << cap_log2) + ((r + b) & (cap - 1u)) : OVERFLOW;
-            }
+    for (int q = 0; q < KPT; ++q)
+        if (vmask >> q & 1u) {
+            const unsigned b = ok_part_bin<LEVEL>(key[q], cfg);
+            const unsigned r = atomicAdd(&sm.hg[b].x, 1u);
+            // rank r of bin b sits in slot (r + b) mod cap of the bin: without the rotation the bank of a staged
+            // key depends on r alone and most ranks are 0..3, an 8-way conflict on every store (548 M per pass, ncu)
+            if (r < cap) sm.stage[(b << cap_log2) + ((r + b) & (cap - 1u))] = key[q];
+            else ok_part_put(key[q], atomicAdd(&cursors[b], 1u), bin_end[b], PEER ? peer->p[b >> peer->shift] : out, ps);
         }
-#pragma unroll
-        for (int q = g0; q < g0 + GROUP && q < KPT; ++q) {
-            const unsigned sl = slot[q - g0];
-            if (sl < OK_STAGE_SLOTS) sm.stage[sl] = key[q];
-            else if (sl == OVERFLOW) {         // the bin outgrew its slots this round: straight to global memory
-                const unsigned b = ok_part_bin<LEVEL>(key[q], cfg);
-                ok_part_put(key[q], atomicAdd(&cursors[b], 1u), bin_end[b], PEER ? peer->p[b >> peer->shift] : out, ps);
-            }
-        }
-    }
     ok_scatter_sync<PEER>();
     after_stage();
     // copy out.  Warp w owns an equal share of the staging slots = a contiguous range of bins.
@@ -700,10 +679,11 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* 
                 if (i < n) { key[q] = __ldcs(keys + i); vm |= 1u << q; }
             }
         }
-        ok_multisplit<LEVEL, false, OK_SK_KPT>(sm.sc, key, vm, cfg, bins_log2, cursors + bin_base, bin_end + bin_base, out, ps, nullptr,
-            [&] {   // every thread holds its keys in registers: the landing buffer is free again
-                if (TMA && threadIdx.x == 0 && wn < n_items) load_item(wn, n_next);
-            });
+        auto next_load = [&] {   // every thread holds its keys in registers: the landing buffer is free again
+            if (TMA && threadIdx.x == 0 && wn < n_items) load_item(wn, n_next);
+        };
+        ok_multisplit<LEVEL, false, OK_SK_KPT, decltype(next_load)&, OK_SK_THREADS / 32u>(
+            sm.sc, key, vm, cfg, bins_log2, cursors + bin_base, bin_end + bin_base, out, ps, nullptr, next_load);
         n = n_next; bin = bin_next;
     }
 }
