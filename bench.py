@@ -412,8 +412,8 @@ def main():
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")
     ap.add_argument("--genome", type=int, default=0, help="genome length (default 5 x reads = 30x coverage)")
     ap.add_argument("--hint", type=int, default=0, help="expected distinct k-mers per GPU")
-    ap.add_argument("--sample-reads", type=int, default=400_000,
-                    help="reads in the CPU baseline sample (400k = 60 M bases: ~15 s of single-thread CPU work)")
+    ap.add_argument("--sample-reads", type=int, default=250_000,
+                    help="reads in the CPU baseline sample (250k = 37.5 M bases: ~10-20 s of single-thread CPU work)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

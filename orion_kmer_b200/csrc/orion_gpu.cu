@@ -40,6 +40,7 @@ int set_err(int code, const char* fmt, ...) {
 
 int g_device = -1;
 int g_sms = 0;
+int g_push_tma = 0;         // ORION_PUSH_TMA=1: the sharded scatter's copy warp pushes with TMA bulk copies (measured slower at N=2: 11.4 vs 9.0 ms)
 int g_scatter_p3 = 1;       // ORION_SCATTER_P3: 3 rounds per warp-tile in the level-1 scatter when it has <= 256 bins
 int g_count_seed = 2;      // ORION_COUNT_SEED bits: 1 = seed round of one key per thread, 2 = first round unqueued (measured: 0 8.66, 1 7.42, 2 7.21 ms)
 std::atomic<uint64_t> g_launches{0};
@@ -980,6 +981,7 @@ OK_EXPORT int ok_init(const int* device_ids, int n_devices) {
     g_device = dev;
     if (const char* ev = getenv("ORION_COUNT_SEED")) g_count_seed = atoi(ev);
     if (const char* ev = getenv("ORION_SCATTER_P3")) g_scatter_p3 = atoi(ev);
+    if (const char* ev = getenv("ORION_PUSH_TMA")) g_push_tma = atoi(ev);
     if (const char* ev = getenv("ORION_SLICES")) { const int v = atoi(ev); if (v >= 4 && v <= 60) RESULT_SLICES = (unsigned)v; }
     return OK_SUCCESS;
 }
@@ -1509,7 +1511,9 @@ OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uin
         OkPeerOut po{}; po.shift = sh.b1;
         for (int r = 0; r < c->n_shards; ++r) po.p[r] = r == c->shard_rank ? c->d_buf1 : c->d_buf2;
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? OK_BY_K(c->k, k_part_scatter_bases, true, true) : OK_BY_K(c->k, k_part_scatter_bases, false, true);
-        TRY(set_smem(kern, sizeof(OkScatterSmem)));
+        const size_t smem_push = sizeof(OkScatterSmem) + sizeof(OkPushSmem);      // staging buffers of the copy warp (TMA push)
+        TRY(set_smem(kern, smem_push));
+        { const char* ev = getenv("ORION_PUSH_TMA"); pd.tma = (ev ? atoi(ev) : g_push_tma) ? 1u : 0u; }   // read per batch: A/B runs
         const OkPartCfg cfg = shard_global_cfg(c, sh.b1);      // level-1 bin id = (owner, bin)
         const uint64_t per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
         for (unsigned ch = 0; ch < n_chunks; ++ch) {
@@ -1520,7 +1524,7 @@ OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uin
             const uint64_t max_warps = (uint64_t)grid_sm * (OK_SB_KPT == 16 ? 3 : 2) * OK_SB_WARPS;
             const uint64_t tpw = std::max<uint64_t>(1, (t1 - t0 + max_warps - 1) / max_warps);
             const unsigned blocks = (unsigned)((t1 - t0 + OK_SB_WARPS * tpw - 1) / (OK_SB_WARPS * tpw));
-            LAUNCH(kern, blocks, OK_SB_THREADS + 32, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, t0, t1, tpw, c->k,
+            LAUNCH(kern, blocks, OK_SB_THREADS + 32, smem_push, c->s_main, d_bases, n_bases, d_rec_offsets, n_records, t0, t1, tpw, c->k,
                    cfg, sh.send_cur, (const unsigned*)sh.send_end, (unsigned long long*)nullptr, (OkPartSpill{c->spill, c->d_stats}),
                    c->d_stats->route_counts, po, pd);
             CU(cudaMemcpyAsync(snap + (size_t)(ch + 1) * 1024, sh.send_cur, n_regs * 4, cudaMemcpyDeviceToDevice, c->s_main));

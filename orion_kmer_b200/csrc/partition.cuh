@@ -471,6 +471,41 @@ __device__ __forceinline__ void ok_multisplit(OkScatterSmem& sm, const uint64_t 
     ok_scatter_sync<PEER>();
 }
 
+// TMA bulk copy global -> shared, completion on an mbarrier (one elected thread issues it)
+__device__ __forceinline__ uint32_t ok_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ok_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ok_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void ok_tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ok_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(ok_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(ok_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ok_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ok_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ok_mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OK_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OK_MBAR_DONE_%=;\n"
+        "bra OK_MBAR_WAIT_%=;\n"
+        "OK_MBAR_DONE_%=:\n"
+        "}\n" :: "r"(ok_smem_u32(bar)), "r"(phase) : "memory");
+}
+
+// TMA bulk store shared -> global (local or peer-mapped), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void ok_tma_store_1d(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst_gmem), "r"(ok_smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void ok_tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void ok_tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------- sharded scatter: push fused into the scatter --
 // The batch is scattered in a few chunks (launches).  Every CTA of a launch carries a ninth warp that
 // does no scattering: it copies what the PREVIOUS chunk appended to the other owners' blocks (cursor
@@ -487,6 +522,7 @@ struct OkPushDesc {
     const unsigned long long* local;      // the local send buffer
     unsigned long long* peer[8];          // the owners' level-1 buffers
     unsigned n_regs, b1, me, enabled;     // enabled == 0: nothing to push
+    unsigned tma;                         // 1: the copy warp moves the data with TMA bulk copies (ok_shard_push_tma)
 };
 
 // the calling group of `nthreads` threads (rank `tid` in it) is worker `worker` of `n_workers`: the regions are
@@ -526,6 +562,58 @@ __device__ __forceinline__ void ok_shard_push(const OkPushDesc& d, unsigned work
     }
 }
 
+// The same copy through the TMA unit: lanes 0..OK_PUSH_STAGES-1 of the copy warp each own one 4 KB staging buffer
+// and stream their share of a piece through it -- bulk load local -> shared (mbarrier), bulk store shared -> peer
+// (bulk async-group).  No registers hold data and a lane only waits until the engine has READ its buffer, not until
+// the remote write has landed, so the bytes in flight per SM are no longer bounded by what 32 threads can keep in
+// registers.  MEASURED AND NOT ADOPTED (ORION_PUSH_TMA=1 selects it): at 2 GPUs the fused scatter+push takes 11.4 ms
+// with it against 9.0 ms with the register copies, i.e. it tops out near 400 GB/s as well.  At 8 GPUs the register
+// copies (386 GB/s per GPU inside the scatter) and the stand-alone k_shard_push with 16x the bytes in flight
+// (435 GB/s) land at the same figure, so the all-to-all of SM stores, not the copy loop, is the bound there.
+#define OK_PUSH_STAGES 4u
+#define OK_PUSH_CHUNK 512u                 // keys per staging buffer (4 KB)
+struct OkPushSmem {
+    unsigned long long stage[OK_PUSH_STAGES][OK_PUSH_CHUNK];
+    unsigned long long bar[OK_PUSH_STAGES];
+};
+__device__ __forceinline__ void ok_shard_push_tma(const OkPushDesc& d, unsigned worker, unsigned n_workers, unsigned lane, OkPushSmem& ps) {
+    constexpr unsigned PIECE = 8192u;
+    if (lane < OK_PUSH_STAGES) ok_mbar_init(&ps.bar[lane], 1);
+    __syncwarp();
+    unsigned phase = 0;
+    unsigned turn = worker;               // pieces until my next one
+    for (unsigned reg = 0; reg < d.n_regs; ++reg) {
+        const unsigned o = reg >> d.b1;
+        if (o == d.me) continue;
+        const unsigned lo0 = d.prev[reg], hi0 = min(d.cur[reg], d.end[reg]);
+        if (hi0 <= lo0) continue;
+        const unsigned n_pieces = (hi0 - lo0 + PIECE - 1u) / PIECE;
+        if (turn >= n_pieces) { turn -= n_pieces; continue; }
+        const unsigned long long* __restrict__ src = d.local;
+        // block starts are even in both coordinate systems, so index parity == 16-byte alignment on both sides
+        unsigned long long* __restrict__ dst = d.peer[o] + (long long)d.blk->remote_start[o] - (long long)d.blk->local_base[o];
+        for (; turn < n_pieces; turn += n_workers) {
+            unsigned lo = lo0 + turn * PIECE;
+            unsigned hi = min(lo + PIECE, hi0);
+            if (lo & 1u) { if (lane == 0) dst[lo] = src[lo]; ++lo; }
+            if ((hi - lo) & 1u) { --hi; if (lane == 0) dst[hi] = src[hi]; }
+            if (lane < OK_PUSH_STAGES) {
+                for (unsigned c0 = lo + lane * OK_PUSH_CHUNK; c0 < hi; c0 += OK_PUSH_STAGES * OK_PUSH_CHUNK) {
+                    const unsigned bytes = (min(c0 + OK_PUSH_CHUNK, hi) - c0) * 8u;      // a multiple of 16
+                    ok_tma_store_wait_read();                                             // my buffer's previous store has read it
+                    ok_tma_load_1d(ps.stage[lane], src + c0, bytes, &ps.bar[lane]);
+                    ok_mbar_wait(&ps.bar[lane], phase); phase ^= 1u;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    ok_tma_store_1d(dst + c0, ps.stage[lane], bytes);
+                }
+            }
+        }
+        turn -= n_pieces;
+    }
+    if (lane < OK_PUSH_STAGES) ok_tma_store_wait_all();       // the remote writes are done before the kernel ends
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(256) k_shard_push(const __grid_constant__ OkPushDesc d) {
     ok_shard_push(d, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x);
 }
@@ -553,7 +641,10 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
     OkPartCfg cfg = cfg_in;
     if (KC) cfg.key_shift = 64u - 2u * KC;
     if (PEER && threadIdx.x >= OK_SB_THREADS) {      // the copy warp of a sharded scatter (launched with 32 more threads)
-        if (push.enabled) ok_shard_push(push, blockIdx.x, gridDim.x, threadIdx.x - OK_SB_THREADS, 32u);
+        if (push.enabled) {
+            if (push.tma) ok_shard_push_tma(push, blockIdx.x, gridDim.x, threadIdx.x - OK_SB_THREADS, *reinterpret_cast<OkPushSmem*>(smem_raw + sizeof(OkScatterSmem)));
+            else ok_shard_push(push, blockIdx.x, gridDim.x, threadIdx.x - OK_SB_THREADS, 32u);
+        }
         return;
     }
     const uint64_t warp = blockIdx.x * (uint64_t)OK_SB_WARPS + (threadIdx.x >> 5);
@@ -583,32 +674,6 @@ k_part_scatter_bases(const uint8_t* __restrict__ bases, uint64_t n_bases, const 
 }
 
 // --------------------------------------------------------------------- level 2: from keys --
-// TMA bulk copy global -> shared, completion on an mbarrier (one elected thread issues it)
-__device__ __forceinline__ uint32_t ok_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ok_mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ok_smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void ok_tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ok_smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(ok_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(ok_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void ok_mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ok_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void ok_mbar_wait(unsigned long long* bar, unsigned phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "OK_MBAR_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra OK_MBAR_DONE_%=;\n"
-        "bra OK_MBAR_WAIT_%=;\n"
-        "OK_MBAR_DONE_%=:\n"
-        "}\n" :: "r"(ok_smem_u32(bar)), "r"(phase) : "memory");
-}
-
 struct OkScatterKeysSmem {
     OkScatterSmem sc;
     unsigned long long in[OK_PART_TILE];     // landing buffer of the next work item (TMA)
