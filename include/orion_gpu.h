@@ -206,6 +206,12 @@ int ok_set_destroy(ok_set* s);
 int ok_set_intersection_size(ok_set* a, ok_set* b, uint64_t* out);
 /* sizes[n] and the full symmetric n*n matrix of intersection sizes (row-major) */
 int ok_sets_all_vs_all(ok_set* const* sets, uint64_t n, uint64_t* sizes, uint64_t* inter);
+/* multi-GPU all-vs-all (BASELINE.json configs[4]): the unordered pairs i < j, numbered row by row, are dealt
+ * round robin to n_parts ranks; this call computes the pairs of `part` only: sizes[n] and inter[i*n+j] for its
+ * pairs, every other entry 0.  Each rank holds all sets; one all-reduce(sum) of the matrix completes it (the
+ * diagonal is sizes[], the lower triangle the mirror image) -- the compare.rs:51-60 loop has no other exchange. */
+int ok_sets_all_vs_all_part(ok_set* const* sets, uint64_t n, uint64_t part, uint64_t n_parts, uint64_t* sizes,
+                            uint64_t* inter);
 
 /* ---- probes (query.rs:79-108 ; classify.rs:224-236) -------------------------------------- */
 /* hits_per_read[r] = number of windows of read r whose canonical k-mer is in the set */

@@ -112,6 +112,7 @@ ABI = {
     "ok_set_destroy": (C.c_int, [vp]),
     "ok_set_intersection_size": (C.c_int, [vp, vp, u64p]),
     "ok_sets_all_vs_all": (C.c_int, [C.POINTER(vp), C.c_uint64, vp, vp]),
+    "ok_sets_all_vs_all_part": (C.c_int, [C.POINTER(vp), C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]),
     "ok_probe_reads": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, vp]),
     "ok_probe_counts": (C.c_int, [vp, vp, vp, C.c_uint64, u64p, u64p]),
     "ok_pack_2bit_device": (C.c_int, [vp, C.c_uint64, C.c_int, vp, vp]),
@@ -639,6 +640,23 @@ def all_vs_all(sets):
     inter = np.zeros((n, n), dtype=np.uint64)
     _check(lib().ok_sets_all_vs_all(arr, n, _ptr(sizes), _ptr(inter)))
     return sizes, inter
+
+
+def all_vs_all_part(sets, part, n_parts):
+    """this part's share of the pairs (ok_sets_all_vs_all_part): sizes[n], upper-triangle entries of its pairs"""
+    n = len(sets)
+    arr = (vp * n)(*[s._h for s in sets])
+    sizes = np.zeros(n, dtype=np.uint64)
+    inter = np.zeros((n, n), dtype=np.uint64)
+    _check(lib().ok_sets_all_vs_all_part(arr, n, part, n_parts, _ptr(sizes), _ptr(inter)))
+    return sizes, inter
+
+
+def finish_all_vs_all(sizes, upper):
+    """summed upper-triangle matrix -> the full symmetric matrix with the set sizes on the diagonal"""
+    full = upper + upper.T
+    full[np.diag_indices(len(sizes))] = sizes
+    return full
 
 
 def compare(a: KmerSet, b: KmerSet):

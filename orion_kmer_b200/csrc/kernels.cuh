@@ -554,6 +554,60 @@ k_probe_counts(OkKeyTableView t, const unsigned long long* __restrict__ keys,
     if ((threadIdx.x & 31) == 0) { if (m) atomicAdd(&out[0], m); if (d) atomicAdd(&out[1], d); }
 }
 
+// compare.rs:58 |A n B| for two sorted duplicate-free arrays, tile by tile.  A is cut into tiles of OK_IS_TILE
+// keys; k_intersect_bounds finds, for every tile, where its first key would go in B (one binary search per
+// tile, all tiles at once), so tile t can only match B[lo[t], lo[t+1]).  k_intersect_tiled streams that range
+// through shared memory in chunks and lets every A key binary-search the chunk it falls into: each key of A and
+// of B is read from global memory once (the per-key search of k_intersect_sorted makes ~23 dependent global
+// loads per key of A: measured 13 s for the 32,640 pairs of config 5).
+#define OK_IS_TILE 2048u
+__global__ void __launch_bounds__(256)
+k_intersect_bounds(const unsigned long long* __restrict__ a, uint64_t na, const unsigned long long* __restrict__ b,
+                   uint64_t nb, unsigned long long* __restrict__ lo_out /* n_tiles + 1 */) {
+    const uint64_t n_tiles = (na + OK_IS_TILE - 1) / OK_IS_TILE;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t <= n_tiles; t += (uint64_t)gridDim.x * blockDim.x) {
+        if (t == n_tiles) { lo_out[t] = nb; continue; }
+        const unsigned long long key = a[t * OK_IS_TILE];
+        uint64_t lo = 0, hi = nb;
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (__ldg(&b[mid]) < key) lo = mid + 1; else hi = mid; }
+        lo_out[t] = lo;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_intersect_tiled(const unsigned long long* __restrict__ a, uint64_t na, const unsigned long long* __restrict__ b,
+                  const unsigned long long* __restrict__ tile_lo, unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long sb[OK_IS_TILE];
+    const uint64_t n_tiles = (na + OK_IS_TILE - 1) / OK_IS_TILE;
+    unsigned long long m = 0;
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint64_t i0 = t * OK_IS_TILE;
+        unsigned long long ka[OK_IS_TILE / 256];
+#pragma unroll
+        for (unsigned q = 0; q < OK_IS_TILE / 256; ++q) {
+            const uint64_t i = i0 + q * 256u + threadIdx.x;
+            ka[q] = i < na ? a[i] : OK_EMPTY_KEY;          // the sentinel is handled below: it may be a real key of a k = 32 set
+        }
+        const uint64_t lo = tile_lo[t], hi = tile_lo[t + 1];
+        for (uint64_t c = lo; c < hi; c += OK_IS_TILE) {
+            const unsigned cn = (unsigned)(hi - c < OK_IS_TILE ? hi - c : OK_IS_TILE);
+            __syncthreads();                               // the previous chunk is no longer being searched
+            for (unsigned j = threadIdx.x; j < cn; j += 256u) sb[j] = b[c + j];
+            __syncthreads();
+            const unsigned long long first = sb[0], last = sb[cn - 1];
+#pragma unroll
+            for (unsigned q = 0; q < OK_IS_TILE / 256; ++q) {
+                const unsigned long long key = ka[q];
+                if (i0 + q * 256u + threadIdx.x >= na || key < first || key > last) continue;
+                unsigned l = 0, h = cn;
+                while (l < h) { const unsigned mid = (l + h) >> 1; if (sb[mid] < key) l = mid + 1; else h = mid; }
+                m += (l < cn && sb[l] == key) ? 1u : 0u;
+            }
+        }
+    }
+    m = ok_warp_sum(m);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, m);
+}
+
 // compare.rs:58 |A n B| for two sorted duplicate-free arrays: every element of A binary-
 // searches B (A is the smaller one).
 __global__ void __launch_bounds__(256)

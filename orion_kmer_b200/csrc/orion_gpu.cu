@@ -1828,6 +1828,22 @@ OK_EXPORT int ok_set_destroy(ok_set* s) {
     return OK_SUCCESS;
 }
 
+namespace {
+// |A n B| into *d_out (device, zeroed by the caller) on stream st; A is the smaller set.  Small sets keep the plain
+// per-key search (one launch); larger ones the tiled two-launch form.  d_lo: scratch of >= |A| / OK_IS_TILE + 2 words.
+void launch_intersection(const ok_set* a, const ok_set* b, unsigned long long* d_lo, unsigned long long* d_out, cudaStream_t st) {
+    static const bool plain = getenv("ORION_INTERSECT_PLAIN") != nullptr;      // A/B knob: the per-key search for every size
+    if (a->n < 4 * OK_IS_TILE || !d_lo || plain) {
+        LAUNCH(k_intersect_sorted, grid_for(a->n), 256, 0, st, a->d_keys, a->n, b->d_keys, b->n, d_out);
+        return;
+    }
+    const uint64_t n_tiles = (a->n + OK_IS_TILE - 1) / OK_IS_TILE;
+    LAUNCH(k_intersect_bounds, grid_for(n_tiles + 1), 256, 0, st, a->d_keys, a->n, b->d_keys, b->n, d_lo);
+    LAUNCH(k_intersect_tiled, (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)(g_sms > 0 ? g_sms : 148) * 8), 256, 0, st,
+           a->d_keys, a->n, b->d_keys, d_lo, d_out);
+}
+}  // namespace
+
 OK_EXPORT int ok_set_intersection_size(ok_set* a, ok_set* b, uint64_t* out) {
     if (!a || !b || !out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_intersection_size: NULL argument");
     if (a->k != b->k) return kmer_size_mismatch(a->k, b->k);  // compare.rs:37-39
@@ -1836,9 +1852,10 @@ OK_EXPORT int ok_set_intersection_size(ok_set* a, ok_set* b, uint64_t* out) {
     *out = 0;
     if (a->n == 0) return OK_SUCCESS;
     unsigned long long* d = nullptr;
-    CU(cudaMalloc((void**)&d, 8));
+    const uint64_t n_lo = a->n / OK_IS_TILE + 2;
+    CU(cudaMalloc((void**)&d, (1 + n_lo) * 8));
     CU(cudaMemsetAsync(d, 0, 8, a->st));
-    LAUNCH(k_intersect_sorted, grid_for(a->n), 256, 0, a->st, a->d_keys, a->n, b->d_keys, b->n, d);
+    launch_intersection(a, b, d + 1, d, a->st);
     unsigned long long h = 0;
     CU(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, a->st));
     CU(cudaStreamSynchronize(a->st));
@@ -1847,8 +1864,14 @@ OK_EXPORT int ok_set_intersection_size(ok_set* a, ok_set* b, uint64_t* out) {
     return OK_SUCCESS;
 }
 
-OK_EXPORT int ok_sets_all_vs_all(ok_set* const* sets, uint64_t n, uint64_t* sizes, uint64_t* inter) {
+// pairs (i < j) in row-major order, pair p belongs to part p % n_parts: sizes[n] and the upper-triangle entries of
+// this part's pairs (everything else in inter[n*n] is zero).  Multi-GPU: every rank holds all sets, takes one
+// part, and one all-reduce(sum) of the matrix completes it.
+OK_EXPORT int ok_sets_all_vs_all_part(ok_set* const* sets, uint64_t n, uint64_t part, uint64_t n_parts, uint64_t* sizes,
+                                      uint64_t* inter) {
     if ((n && !sets) || !sizes || !inter) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_sets_all_vs_all: NULL argument");
+    if (n_parts == 0 || part >= n_parts) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_sets_all_vs_all_part: part %llu of %llu",
+                                                         (unsigned long long)part, (unsigned long long)n_parts);
     if (n == 0) return OK_SUCCESS;
     for (uint64_t i = 0; i < n; ++i) {
         if (!sets[i]) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_sets_all_vs_all: NULL set");
@@ -1857,20 +1880,30 @@ OK_EXPORT int ok_sets_all_vs_all(ok_set* const* sets, uint64_t n, uint64_t* size
         sizes[i] = sets[i]->n;
     }
     unsigned long long* d = nullptr;
-    CU(cudaMalloc((void**)&d, n * n * 8));
+    uint64_t n_lo = 2;
+    for (uint64_t i = 0; i < n; ++i) n_lo = std::max<uint64_t>(n_lo, sets[i]->n / OK_IS_TILE + 2);
+    CU(cudaMalloc((void**)&d, (n * n + n_lo) * 8));
+    unsigned long long* d_lo = d + n * n;                 // tile bounds of the pair in flight (the pairs run in stream order)
     cudaStream_t st = sets[0]->st;
     CU(cudaMemsetAsync(d, 0, n * n * 8, st));
+    uint64_t p = 0;
     for (uint64_t i = 0; i < n; ++i)
-        for (uint64_t j = i + 1; j < n; ++j) {
+        for (uint64_t j = i + 1; j < n; ++j, ++p) {
+            if (p % n_parts != part) continue;
             ok_set *a = sets[i], *b = sets[j];
             if (a->n > b->n) std::swap(a, b);
             if (a->n == 0) continue;
-            LAUNCH(k_intersect_sorted, grid_for(a->n), 256, 0, st, a->d_keys, a->n, b->d_keys, b->n, d + i * n + j);
+            launch_intersection(a, b, d_lo, d + i * n + j, st);
         }
     CU(cudaMemcpyAsync(inter, d, n * n * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     cudaFree(d);
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_sets_all_vs_all(ok_set* const* sets, uint64_t n, uint64_t* sizes, uint64_t* inter) {
+    TRY(ok_sets_all_vs_all_part(sets, n, 0, 1, sizes, inter));
     for (uint64_t i = 0; i < n; ++i) {
         inter[i * n + i] = sizes[i];
         for (uint64_t j = 0; j < i; ++j) inter[i * n + j] = inter[j * n + i];

@@ -205,6 +205,20 @@ class ShardedCounter:
         self.counter.close()
 
 
+def all_vs_all(ok, torch, dist, sets, device=None):
+    """All-vs-all intersection sizes over the ranks of a process group (BASELINE.json configs[4]).
+    Every rank holds all the sets (256 x 5 M keys = 10 GB); the pairs are dealt round robin to the ranks and ONE
+    all-reduce(sum) of the n x n matrix is the only exchange the path has.  `device`: where the matrix is reduced
+    ("cuda" under NCCL, "cpu" under gloo)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sizes, upper = ok.all_vs_all_part(sets, rank, world)
+    if device is None:
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    m = torch.from_numpy(upper.view(np.int64)).to(device)
+    dist.all_reduce(m, op=dist.ReduceOp.SUM)
+    return sizes, ok.finish_all_vs_all(sizes, m.cpu().numpy().view(np.uint64))
+
+
 def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config, ClockSampler, measured_peak,
           metric, numa_node=None):
     import torch.distributed as dist

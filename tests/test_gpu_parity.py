@@ -297,11 +297,48 @@ def test_sets_random_against_oracle(oracle):
         for j in range(len(sets)):
             want = oracle.compare(osets[i], osets[j])["intersection_size"]
             assert inter[i, j] == want, (i, j)
+    # the multi-GPU split of the same job: every part's pairs, summed (the all-reduce), give the same matrix
+    for n_parts in (2, 3, 8):
+        parts = [ok.all_vs_all_part(sets, r, n_parts) for r in range(n_parts)]
+        assert all(np.array_equal(p[0], sizes) for p in parts)
+        assert sum(int(np.count_nonzero(p[1])) for p in parts) <= len(sets) * (len(sets) - 1) // 2
+        assert np.array_equal(ok.finish_all_vs_all(sizes, sum(p[1] for p in parts)), inter)
     # foreign (non-canonical) k=32 set holding u64::MAX
     weird = np.array([0, 5, 2 ** 64 - 1], dtype=np.uint64)
     w = ok.KmerSet.from_sorted(32, weird)
     assert w.probe_counts(np.array([2 ** 64 - 1, 5, 6], np.uint64), np.array([7, 1, 1], np.uint64)) == (2, 8)
     assert list(ok.KmerSet.union([w, ok.KmerSet.from_sorted(32, np.array([5, 9], np.uint64))]).to_array()) == [0, 5, 9, 2 ** 64 - 1]
+
+
+def test_intersection_tiled_kernel_shapes():
+    """k_intersect_bounds + k_intersect_tiled against numpy on shapes that stress the tiling: equal sets, disjoint
+    ranges, a small set inside a large one (one tile of A against hundreds of chunks of B), interleaved keys, tile
+    and chunk boundaries, and a k = 32 set that holds the sentinel value u64::MAX."""
+    rng = np.random.default_rng(91)
+
+    def uniq(n, lo=0, hi=2 ** 62):
+        return np.unique(rng.integers(lo, hi, n, dtype=np.uint64))
+
+    big = uniq(3_000_000)
+    cases = [
+        (big, big),
+        (big[::2].copy(), big[1::2].copy()),                       # interleaved, nothing shared
+        (big[:100_000], big),                                       # A is a prefix of B
+        (np.sort(rng.choice(big, 20_000, replace=False)), big),     # small A scattered over a large B
+        (uniq(50_000, 0, 2 ** 40), uniq(50_000, 2 ** 41, 2 ** 42)),  # disjoint ranges
+        (big[:2048 * 5], big[2048 * 3:2048 * 9]),                   # overlaps that start and end on tile boundaries
+        (np.concatenate([big[:40_000], np.array([2 ** 64 - 1], np.uint64)]),
+         np.concatenate([big[20_000:90_000], np.array([2 ** 64 - 1], np.uint64)])),
+    ]
+    for a, b in cases:
+        k = 32 if (a[-1] == 2 ** 64 - 1 or b[-1] == 2 ** 64 - 1) else 31
+        sa, sb = ok.KmerSet.from_sorted(k, a), ok.KmerSet.from_sorted(k, b)
+        want = len(np.intersect1d(a, b, assume_unique=True))
+        assert sa.intersection_size(sb) == want
+        assert sb.intersection_size(sa) == want
+        sizes, inter = ok.all_vs_all([sa, sb])
+        assert list(sizes) == [len(a), len(b)] and inter[0, 1] == want and inter[1, 0] == want
+        sa.close(); sb.close()
 
 
 # ------------------------------------------------------------------------ query / classify --

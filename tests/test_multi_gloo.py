@@ -76,3 +76,58 @@ def test_two_rank_exchange_concatenates_to_global_table(oracle):
     # both ranks hold a comparable share (owner ranges are balanced by the canonical prior)
     shares = [len(t[0]) / len(wk) for t in tables]
     assert all(0.4 < s < 0.6 for s in shares), shares
+
+
+# ------------------------------------------------------- all-vs-all compare across ranks --
+class _HostSets:
+    """numpy stand-in for the device side of multi.all_vs_all: the same pair dealing as ok_sets_all_vs_all_part
+    (pairs i < j numbered row by row, pair p belongs to part p % n_parts), intersections by np.intersect1d"""
+
+    @staticmethod
+    def all_vs_all_part(sets, part, n_parts):
+        n = len(sets)
+        sizes = np.array([len(s) for s in sets], dtype=np.uint64)
+        inter = np.zeros((n, n), dtype=np.uint64)
+        p = 0
+        for i in range(n):
+            for j in range(i + 1, n):
+                if p % n_parts == part:
+                    inter[i, j] = len(np.intersect1d(sets[i], sets[j], assume_unique=True))
+                p += 1
+        return sizes, inter
+
+    @staticmethod
+    def finish_all_vs_all(sizes, upper):
+        import orion_kmer_b200 as ok
+        return ok.finish_all_vs_all(sizes, upper)
+
+
+def _sets():
+    rng = np.random.default_rng(12)
+    pool = np.unique(rng.integers(0, 2 ** 42, 40_000, dtype=np.uint64))
+    return [pool[rng.random(len(pool)) < f] for f in (0.5, 0.3, 0.7, 0.0, 0.5, 1.0, 0.1)]
+
+
+def _ava_worker(rank, world, port, ret):
+    from orion_kmer_b200 import multi
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    try:
+        sizes, full = multi.all_vs_all(_HostSets, torch, dist, _sets())
+        if rank == 0:
+            ret["sizes"], ret["full"] = sizes, full
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_all_vs_all_matches_single_process():
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_ava_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        sizes, full = ret["sizes"], ret["full"]
+    sets = _sets()
+    n = len(sets)
+    for i in range(n):
+        assert sizes[i] == len(sets[i]) == full[i, i]
+        for j in range(n):
+            assert full[i, j] == len(np.intersect1d(sets[i], sets[j], assume_unique=True)), (i, j)
