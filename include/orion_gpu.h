@@ -220,6 +220,10 @@ int ok_probe_reads(ok_set* s, int norm_mode, const uint8_t* bases, const uint64_
 /* matched = |{i : kmers[i] in ref}| , depth_sum = sum of counts[i] over those */
 int ok_probe_counts(ok_set* ref, const uint64_t* kmers, const uint64_t* counts, uint64_t n,
                     uint64_t* matched, uint64_t* depth_sum);
+/* the same input count map against n_refs references (the loop of classify.rs:224-277): the input is uploaded
+ * once; matched[r], depth_sum[r] for reference r */
+int ok_probe_counts_many(ok_set* const* refs, uint64_t n_refs, const uint64_t* kmers, const uint64_t* counts,
+                         uint64_t n, uint64_t* matched, uint64_t* depth_sum);
 
 /* ---- standalone 2-bit packing kernel (north-star subsystem 1) ---------------------------- */
 /* d_codes: one uint64 per 32 bases, first base in the top two bits; d_valid: one uint32 per

@@ -115,6 +115,7 @@ ABI = {
     "ok_sets_all_vs_all_part": (C.c_int, [C.POINTER(vp), C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]),
     "ok_probe_reads": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, vp]),
     "ok_probe_counts": (C.c_int, [vp, vp, vp, C.c_uint64, u64p, u64p]),
+    "ok_probe_counts_many": (C.c_int, [C.POINTER(vp), C.c_uint64, vp, vp, C.c_uint64, vp, vp]),
     "ok_pack_2bit_device": (C.c_int, [vp, C.c_uint64, C.c_int, vp, vp]),
 }
 # internal test hooks (not in include/)
@@ -640,6 +641,18 @@ def all_vs_all(sets):
     inter = np.zeros((n, n), dtype=np.uint64)
     _check(lib().ok_sets_all_vs_all(arr, n, _ptr(sizes), _ptr(inter)))
     return sizes, inter
+
+
+def probe_counts_many(refs, kmers, counts):
+    """classify.rs:224-277: one input count map against every reference -> (matched[n_refs], sum_depth[n_refs])"""
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    n = len(refs)
+    arr = (vp * n)(*[r._h for r in refs])
+    matched = np.zeros(n, dtype=np.uint64)
+    depth = np.zeros(n, dtype=np.uint64)
+    _check(lib().ok_probe_counts_many(arr, n, _ptr(kmers), _ptr(counts), len(kmers), _ptr(matched), _ptr(depth)))
+    return matched, depth
 
 
 def all_vs_all_part(sets, part, n_parts):

@@ -419,9 +419,13 @@ void run_classify(const Parsed& p) {
         j.kvf("proportion_input_kmers_in_db_overall", ratio(om, n_in));
         j.kvf("proportion_db_kmers_covered_overall", ratio(om, db_total));
         j.key("references"); j.begin('[');
+        // one upload of the input count map, every reference probed on the device (ok_probe_counts_many)
+        std::vector<ok_set*> ref_handles;
+        for (uint64_t i = 0; i < dbs[d].n_refs(); ++i) ref_handles.push_back(refs[i].s);
+        std::vector<uint64_t> ref_m(ref_handles.size(), 0), ref_dep(ref_handles.size(), 0);
+        gpu(ok_probe_counts_many(ref_handles.data(), ref_handles.size(), keys, counts, n_in, ref_m.data(), ref_dep.data()));
         for (uint64_t i = 0; i < dbs[d].n_refs(); ++i) {
-            uint64_t m = 0, dep = 0;
-            gpu(ok_probe_counts(refs[i].s, keys, counts, n_in, &m, &dep));
+            const uint64_t m = ref_m[i], dep = ref_dep[i];
             const uint64_t rn = refs[i].size();
             const double breadth = ratio(m, rn);
             if (!(breadth >= min_cov)) continue;                        // classify.rs:247

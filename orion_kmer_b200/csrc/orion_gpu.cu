@@ -45,6 +45,7 @@ int g_scatter_p3 = 1;       // ORION_SCATTER_P3: 3 rounds per warp-tile in the l
 int g_count_seed = 2;      // ORION_COUNT_SEED bits: 1 = seed round of one key per thread, 2 = first round unqueued (measured: 0 8.66, 1 7.42, 2 7.21 ms)
 std::atomic<uint64_t> g_launches{0};
 std::mutex g_mu;
+std::vector<ok_counter*> g_spare_builders;   // cleared set builders waiting for the next ok_set_create (guarded by g_mu)
 
 #define LAUNCH(kern, grid, block, smem, stream, ...)                 \
     do {                                                             \
@@ -987,6 +988,9 @@ OK_EXPORT int ok_init(const int* device_ids, int n_devices) {
 }
 
 OK_EXPORT int ok_shutdown(void) {
+    std::vector<ok_counter*> spare;
+    { std::lock_guard<std::mutex> lk(g_mu); spare.swap(g_spare_builders); }
+    for (ok_counter* c : spare) ok_counter_destroy(c);
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& b : g_pool) cudaFreeHost(b.p);
     g_pool.clear();
@@ -1682,6 +1686,37 @@ OK_EXPORT int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out) {
 }
 
 // =================================================================================== sets ==
+// Set builders are counters, and a counter owns streams, page-locked mirrors, a spill list and grow-only device
+// buffers: creating and destroying one per reference genome cost 130 ms per 5 Mbp genome, a hundred times the
+// count itself (tools/bench_build_query.py).  Sealed sets hand their (cleared) builder back to a small pool.
+namespace {
+constexpr size_t MAX_SPARE_BUILDERS = 4;
+
+int take_builder(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_counter** out) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_spare_builders.empty() && k >= 1 && k <= 32 && (norm_mode == OK_NORM_NORMALIZED || norm_mode == OK_NORM_RAW)) {
+            ok_counter* c = g_spare_builders.back();
+            g_spare_builders.pop_back();
+            c->k = k; c->norm_mode = norm_mode; c->hint = capacity_hint; c->user_hint = capacity_hint;
+            c->distrust_hint = false; c->path_mode = 0;
+            *out = c;
+            return OK_SUCCESS;
+        }
+    }
+    return ok_counter_create(k, norm_mode, capacity_hint, out);   // build.rs:83-85 validates k the same way
+}
+
+void give_builder(ok_counter* c) {
+    if (!c) return;
+    if (c->n_shards == 1 && !c->buf1_external && ok_counter_clear(c) == OK_SUCCESS) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_spare_builders.size() < MAX_SPARE_BUILDERS) { g_spare_builders.push_back(c); return; }
+    }
+    ok_counter_destroy(c);
+}
+}  // namespace
+
 struct ok_set {
     unsigned k = 0;
     int norm_mode = 0;
@@ -1711,7 +1746,7 @@ int set_seal(ok_set* s) {
             if (s->has_max) { unsigned long long m = OK_EMPTY_KEY; CU(cudaMemcpy(s->d_keys + n, &m, 8, cudaMemcpyHostToDevice)); }
         }
         n = total;
-        ok_counter_destroy(s->builder);
+        give_builder(s->builder);
         s->builder = nullptr;
     }
     s->n = n;
@@ -1742,7 +1777,7 @@ OK_EXPORT int ok_set_create(uint8_t k, int norm_mode, uint64_t capacity_hint, ok
     if (!out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_create: out is NULL");
     *out = nullptr;
     ok_counter* b = nullptr;
-    TRY(ok_counter_create(k, norm_mode, capacity_hint, &b));  // build.rs:83-85 validates k the same way
+    TRY(take_builder(k, norm_mode, capacity_hint, &b));
     ok_set* s = new ok_set();
     s->k = k; s->norm_mode = norm_mode; s->builder = b;
     *out = s;
@@ -1821,7 +1856,7 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
 
 OK_EXPORT int ok_set_destroy(ok_set* s) {
     if (!s) return OK_SUCCESS;
-    if (s->builder) ok_counter_destroy(s->builder);
+    if (s->builder) give_builder(s->builder);
     cudaFree(s->d_keys); cudaFree(s->d_table);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
@@ -1941,28 +1976,46 @@ OK_EXPORT int ok_probe_reads(ok_set* s, int norm_mode, const uint8_t* bases, con
     return OK_SUCCESS;
 }
 
+// classify.rs:224-277 probes the SAME input count map against every reference: the input is uploaded once and
+// every reference's hashed table is probed on the device (per reference a 5 M-key table is L2-resident; uploading
+// 1 GB of input per reference, as one ok_probe_counts call per reference does, took 150 ms each).
+OK_EXPORT int ok_probe_counts_many(ok_set* const* refs, uint64_t n_refs, const uint64_t* kmers, const uint64_t* counts,
+                                   uint64_t n, uint64_t* matched, uint64_t* depth_sum) {
+    if ((n_refs && (!refs || !matched || !depth_sum)) || (n && !kmers))
+        return set_err(OK_ERR_INVALID_ARGUMENT, "ok_probe_counts_many: NULL argument");
+    for (uint64_t r = 0; r < n_refs; ++r) {
+        if (!refs[r]) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_probe_counts_many: NULL set");
+        matched[r] = 0; depth_sum[r] = 0;
+    }
+    if (n == 0 || n_refs == 0) return OK_SUCCESS;
+    for (uint64_t r = 0; r < n_refs; ++r) TRY(set_table(refs[r]));
+    cudaStream_t st = refs[0]->st;
+    unsigned long long *d_k = nullptr, *d_c = nullptr, *d_o = nullptr;
+    auto release = [&] { cudaFree(d_k); cudaFree(d_c); cudaFree(d_o); };
+#define CUR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return set_err(OK_ERR_CUDA, "CUDA error %s in ok_probe_counts_many", cudaGetErrorName(e_)); } } while (0)
+    CUR(cudaMalloc((void**)&d_k, n * 8));
+    if (counts) CUR(cudaMalloc((void**)&d_c, n * 8));
+    CUR(cudaMalloc((void**)&d_o, n_refs * 16));
+    CUR(cudaMemcpyAsync(d_k, kmers, n * 8, cudaMemcpyHostToDevice, st));
+    if (counts) CUR(cudaMemcpyAsync(d_c, counts, n * 8, cudaMemcpyHostToDevice, st));
+    CUR(cudaMemsetAsync(d_o, 0, n_refs * 16, st));
+    for (uint64_t r = 0; r < n_refs; ++r)
+        LAUNCH(k_probe_counts, grid_for(n), 256, 0, st, (OkKeyTableView{refs[r]->d_table, refs[r]->n_table, refs[r]->has_max}),
+               (const unsigned long long*)d_k, (const unsigned long long*)d_c, n, d_o + 2 * r);
+    std::vector<unsigned long long> h(2 * n_refs, 0);
+    CUR(cudaMemcpyAsync(h.data(), d_o, n_refs * 16, cudaMemcpyDeviceToHost, st));
+    CUR(cudaStreamSynchronize(st));
+    CUR(cudaGetLastError());
+#undef CUR
+    release();
+    for (uint64_t r = 0; r < n_refs; ++r) { matched[r] = h[2 * r]; depth_sum[r] = h[2 * r + 1]; }
+    return OK_SUCCESS;
+}
+
 OK_EXPORT int ok_probe_counts(ok_set* ref, const uint64_t* kmers, const uint64_t* counts, uint64_t n,
                               uint64_t* matched, uint64_t* depth_sum) {
     if (!ref || !matched || !depth_sum || (n && !kmers)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_probe_counts: NULL argument");
-    *matched = 0; *depth_sum = 0;
-    if (n == 0) return OK_SUCCESS;
-    TRY(set_table(ref));
-    unsigned long long *d_k = nullptr, *d_c = nullptr, *d_o = nullptr;
-    CU(cudaMalloc((void**)&d_k, n * 8));
-    if (counts) CU(cudaMalloc((void**)&d_c, n * 8));
-    CU(cudaMalloc((void**)&d_o, 16));
-    CU(cudaMemcpyAsync(d_k, kmers, n * 8, cudaMemcpyHostToDevice, ref->st));
-    if (counts) CU(cudaMemcpyAsync(d_c, counts, n * 8, cudaMemcpyHostToDevice, ref->st));
-    CU(cudaMemsetAsync(d_o, 0, 16, ref->st));
-    LAUNCH(k_probe_counts, grid_for(n), 256, 0, ref->st, (OkKeyTableView{ref->d_table, ref->n_table, ref->has_max}),
-           (const unsigned long long*)d_k, (const unsigned long long*)d_c, n, d_o);
-    unsigned long long h[2] = {0, 0};
-    CU(cudaMemcpyAsync(h, d_o, 16, cudaMemcpyDeviceToHost, ref->st));
-    CU(cudaStreamSynchronize(ref->st));
-    CU(cudaGetLastError());
-    cudaFree(d_k); cudaFree(d_c); cudaFree(d_o);
-    *matched = h[0]; *depth_sum = h[1];
-    return OK_SUCCESS;
+    return ok_probe_counts_many(&ref, 1, kmers, counts, n, matched, depth_sum);
 }
 
 // =================================================================================== pack ==

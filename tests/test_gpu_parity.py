@@ -297,6 +297,14 @@ def test_sets_random_against_oracle(oracle):
         for j in range(len(sets)):
             want = oracle.compare(osets[i], osets[j])["intersection_size"]
             assert inter[i, j] == want, (i, j)
+    # classify's loop over references in one call: same numbers as one probe per reference
+    pk = np.concatenate([osets[0][::3], osets[3][::5], np.array([1, 2, 3], np.uint64)])
+    pc = (np.arange(len(pk), dtype=np.uint64) % np.uint64(7)) + np.uint64(1)
+    m_many, d_many = ok.probe_counts_many(sets, pk, pc)
+    for i, st in enumerate(sets):
+        assert st.probe_counts(pk, pc) == (int(m_many[i]), int(d_many[i]))
+        sel = np.isin(pk, osets[i])
+        assert int(m_many[i]) == int(sel.sum()) and int(d_many[i]) == int(pc[sel].sum())
     # the multi-GPU split of the same job: every part's pairs, summed (the all-reduce), give the same matrix
     for n_parts in (2, 3, 8):
         parts = [ok.all_vs_all_part(sets, r, n_parts) for r in range(n_parts)]
