@@ -1845,6 +1845,29 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
     ok_set* u = nullptr;
     TRY(ok_set_create((uint8_t)sets[0]->k, sets[0]->norm_mode, std::max<uint64_t>(sum, 1), &u));
     u->has_max = has_max;
+    // All keys in one array -> ONE pass of the partitioned path (scatter by key range, dedupe in shared memory): the
+    // union comes out sorted.  Set by set, the first set would take that path and every later one random-access
+    // inserts into a device-wide table sized for the sum (db_types.rs:43-48 re-hashes every key the same way).
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n_sets; ++i) total += sets[i]->n - (sets[i]->has_max ? 1 : 0);
+    if (n_sets > 1 && total >= PART_MIN_BASES && total < (1ull << 31) && !getenv("ORION_UNION_SETWISE")) {
+        unsigned long long* d_all = nullptr;
+        cudaStream_t st = u->builder->s_main;
+        cudaError_t e = cudaMalloc((void**)&d_all, total * 8);
+        uint64_t at = 0;
+        for (uint64_t i = 0; i < n_sets && e == cudaSuccess; ++i) {
+            const uint64_t m = sets[i]->n - (sets[i]->has_max ? 1 : 0);
+            if (m) e = cudaMemcpyAsync(d_all + at, sets[i]->d_keys, m * 8, cudaMemcpyDeviceToDevice, st);
+            at += m;
+        }
+        if (e != cudaSuccess) { cudaFree(d_all); ok_set_destroy(u); return set_err(OK_ERR_CUDA, "CUDA error %s in ok_set_union", cudaGetErrorName(e)); }
+        const int r = ok_counter_add_kmers_device(u->builder, (const uint64_t*)d_all, total);   // returns with the stream drained
+        cudaStreamSynchronize(st);
+        cudaFree(d_all);
+        if (r != OK_SUCCESS) { ok_set_destroy(u); return r; }
+        *out = u;
+        return OK_SUCCESS;
+    }
     for (uint64_t i = 0; i < n_sets; ++i) {
         const uint64_t m = sets[i]->n - (sets[i]->has_max ? 1 : 0);
         int r = ok_counter_add_kmers_device(u->builder, (const uint64_t*)sets[i]->d_keys, m);

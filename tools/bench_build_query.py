@@ -43,10 +43,13 @@ print(f"A9  build: {G} genomes x {L} bases, k={K}: {t_dev * 1e3:.0f} ms through 
       f"{t_dev / G * 1e3:.2f} ms per genome = {t_add / G * 1e3:.2f} create + add_batch, {t_seal / G * 1e3:.2f} seal; "
       f"with synthetic-genome generation {t_build:.1f} s), {total_keys} keys in all sets")
 
-t0 = time.perf_counter()
-union = ok.KmerSet.union(sets)
-n_union = len(union)
-t_union = time.perf_counter() - t0
+t_union = None
+for _ in range(3):                      # best of 3: the first call also pays for the device buffers
+    t0 = time.perf_counter()
+    union = ok.KmerSet.union(sets)
+    n_union = len(union)
+    dt = time.perf_counter() - t0
+    t_union = dt if t_union is None else min(t_union, dt)
 print(f"A10 union: {n_union} distinct of {total_keys} keys in {t_union * 1e3:.0f} ms ({total_keys * 8 / t_union / 1e9:.0f} GB/s of input keys)")
 
 # sample: reads from 10 of the genomes + 10 % from an unrelated genome (config-2 error recipe)
