@@ -124,6 +124,7 @@ _HOOKS = {
     "okx_emulate_table": (C.c_int, [vp, C.c_uint64, C.c_uint, C.c_int, C.c_uint64, C.c_uint, C.c_uint64, vp, vp, u64p, u64p]),
     "okx_device_extract": (C.c_int, [vp, vp, C.c_uint64, C.c_uint, C.c_int, vp, C.c_uint64, u64p]),
     "okx_owner_of": (C.c_int, [vp, C.c_uint64, C.c_uint, C.c_int, vp]),
+    "okx_plan_bits": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint, vp]),
 }
 
 _gpu = None

@@ -2160,3 +2160,18 @@ OK_EXPORT int okx_owner_of(const uint64_t* keys, uint64_t n, unsigned k, int n_r
     for (uint64_t i = 0; i < n; ++i) out[i] = (int32_t)ok_home_slot(keys[i], 64 - 2 * k, OK_MAP_CANON, (uint64_t)n_ranks);
     return OK_SUCCESS;
 }
+
+// the plan of a one-shot batch as part_choose_bits / part_slice_step derive it (host logic only, no device needed):
+// out[0] = total bits, [1] = level-1 bits, [2] = level-2 bits, [3] = sized from the capacity hint (0/1),
+// [4] = 16384-slot count kernel (0/1), [5] = result slices of the deferred pipeline (0: not sliceable)
+OK_EXPORT int okx_plan_bits(uint64_t n_units, uint64_t capacity_hint, unsigned k, uint32_t* out) {
+    if (k == 0 || k > 32) return invalid_k(k);
+    if (!out) return set_err(OK_ERR_INVALID_ARGUMENT, "okx_plan_bits: NULL out");
+    ok_counter c;
+    c.k = k; c.hint = c.user_hint = capacity_hint;
+    PartPlan pl;
+    part_choose_bits(&c, n_units, pl, /*use_hint=*/true);
+    out[0] = pl.cfg.b1 + pl.cfg.b2; out[1] = pl.cfg.b1; out[2] = pl.cfg.b2; out[3] = pl.hinted ? 1u : 0u; out[4] = pl.big_count ? 1u : 0u;
+    out[5] = part_sliceable(pl) ? pl.n_sub / part_slice_step(pl) : 0u;
+    return OK_SUCCESS;
+}

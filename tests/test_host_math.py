@@ -153,3 +153,44 @@ def test_emulated_table_clustered_keys_stay_sorted(oracle):
     gk2, gc2, spilled2 = emulate_table(keys, k, 4096, max_probe=64, map_mode=0)
     assert spilled2 > 0 and int(gc2.sum()) + spilled2 == len(keys)
     assert np.all(np.diff(gk2.astype(object)) > 0)
+
+
+# ------------------------------------------------ the plan of a one-shot batch (host logic) --
+def _plan(n_units, hint=0, k=31):
+    out = np.zeros(6, dtype=np.uint32)
+    assert ok.lib().okx_plan_bits(n_units, hint, k, ok._ptr(out)) == 0
+    return dict(bits=int(out[0]), b1=int(out[1]), b2=int(out[2]), hinted=bool(out[3]), big=bool(out[4]), slices=int(out[5]))
+
+
+def test_plan_without_hint_sizes_sub_partitions_for_their_windows():
+    """no capacity hint: <= 4096 windows per sub-partition (every key could be distinct), at most 18 bits in two
+    balanced levels, one level up to 256 bins"""
+    for n in (1 << 20, 3_000_000, 24_000_000, 300_000_000, 1_500_000_000):
+        p = _plan(n)
+        assert not p["hinted"]
+        assert p["bits"] == min(18, int(np.ceil(np.log2(n / 4096))))
+        assert p["b1"] + p["b2"] == p["bits"] and (p["b2"] == 0) == (p["bits"] <= 8)
+        assert abs(p["b1"] - p["b2"]) <= 1 or p["b2"] == 0
+    assert _plan(1_500_000_000)["big"] is False           # 5722 windows per sub-partition: the 8192-slot tables
+    assert _plan(2_000_000_000)["big"] is True            # 7629: the 16384-slot tables
+
+
+def test_plan_with_hint_sizes_sub_partitions_for_their_distinct_keys():
+    # BASELINE.json configs[1]: 1.5 G bases, 255 M expected distinct k-mers -> 2^16 sub-partitions of ~3.9 K distinct keys
+    p = _plan(1_500_000_000, 255_000_000)
+    assert p == dict(bits=16, b1=8, b2=8, hinted=True, big=False, slices=16)
+    # a hint can only make sub-partitions larger, never smaller than the window-sized plan, and never beyond 24576
+    # windows per sub-partition (16-bit counts in the shared-memory tables)
+    for n in (3_000_000, 24_000_000, 300_000_000, 1_500_000_000):
+        base = _plan(n)["bits"]
+        for hint in (1, 1000, n // 100, n // 6, n // 2, n, 10 * n):
+            p = _plan(n, hint)
+            assert p["bits"] <= base
+            assert n / (1 << p["bits"]) <= 24576 or p["bits"] == base
+            assert p["hinted"] == (p["bits"] < base) or p["bits"] == 18
+            if hint >= n:
+                assert p["bits"] == base and not p["hinted"]      # every key distinct: the safe plan
+    # the deferred (sliced) result pipeline needs >= 4 slices of whole level-1 bins and whole 1024-entry scan chunks
+    assert _plan(3_000_000)["slices"] == 0
+    assert _plan(24_000_000)["slices"] == 8
+    assert _plan(1_500_000_000)["slices"] == 16
