@@ -261,6 +261,7 @@ __device__ __forceinline__ void ok_walk_tiles(const uint8_t* __restrict__ bases,
         if (t >= t_live) { per_group(pos, 0ull, 0ull, 0u); continue; }
         uint64_t cur_codes; uint32_t cur_valid;
         ok_load_group<MAP_U>(bases, n_bases, pos, cur_codes, cur_valid);
+        // (an L2 prefetch of the warp's next tile here was measured: no effect, 5.78 vs 5.79 ms in the level-1 scatter)
         uint32_t cur_start = ok_tile_starts(rec_off, n_rec, ws, r_next, lane);
         uint64_t prev_codes = __shfl_up_sync(OK_FULL, cur_codes, 1);
         uint32_t prev_valid = __shfl_up_sync(OK_FULL, cur_valid, 1);
