@@ -337,10 +337,19 @@ def canonical_u64(v: int, k: int) -> int:
 class Batch:
     """C-ABI batch: concatenated bases + n+1 offsets (+ record ids)."""
 
-    def __init__(self, bases, offsets, ids=None):
+    def __init__(self, bases, offsets, ids=None, id_blob=None, id_offsets=None):
         self.bases = np.ascontiguousarray(bases, dtype=np.uint8)
         self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-        self.ids = ids
+        self._ids, self._id_blob, self._id_offsets = ids, id_blob, id_offsets
+
+    @property
+    def ids(self):
+        """record ids as a list of bytes; sliced out of the id blob on first use (count / build never look at them,
+        and a list of 10 M bytes objects costs more than parsing the file)"""
+        if self._ids is None and self._id_blob is not None:
+            o = self._id_offsets
+            self._ids = [self._id_blob[int(o[i]):int(o[i + 1])] for i in range(len(o) - 1)]
+        return self._ids
 
     @property
     def n_records(self):
@@ -360,8 +369,7 @@ def parse_fastx(content: bytes, norm_mode=NORMALIZED) -> Batch:
         off = _copy_out(H.okh_batch_offsets(h), n + 1, C.c_uint64, np.uint64)
         ido = _copy_out(H.okh_batch_id_offsets(h), n + 1, C.c_uint64, np.uint64)
         blob = bytes(_copy_out(H.okh_batch_ids(h), int(ido[-1]), C.c_uint8, np.uint8))
-        ids = [blob[int(ido[i]):int(ido[i + 1])] for i in range(n)]
-        return Batch(bases, off, ids)
+        return Batch(bases, off, id_blob=blob, id_offsets=ido)
     finally:
         H.okh_batch_free(h)
 

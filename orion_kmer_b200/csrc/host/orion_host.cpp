@@ -18,17 +18,30 @@
 
 namespace {
 
+// bases / ids live in raw buffers sized once for the whole input (a parsed batch is never larger than its text;
+// untouched pages of a large malloc cost nothing) and are filled through a cursor: no per-record vector growth and no
+// zero-fill of bytes that are about to be overwritten
 struct Batch {
-    std::vector<uint8_t> bases;
+    uint8_t* bases = nullptr;
+    uint8_t* ids = nullptr;
     std::vector<uint64_t> offsets;
-    std::vector<uint8_t> ids;
     std::vector<uint64_t> id_offsets;
+    size_t nb = 0, ni = 0;               // bytes used in bases / ids
     Batch() : offsets(1, 0), id_offsets(1, 0) {}
-    void close_record() { offsets.push_back(bases.size()); }
+    ~Batch() { free(bases); free(ids); }
+    Batch(const Batch&) = delete;
+    Batch& operator=(const Batch&) = delete;
+    bool begin(size_t text_len) {
+        bases = (uint8_t*)malloc(text_len + 1); ids = (uint8_t*)malloc(text_len + 1);
+        const size_t guess = text_len / 200 + 16;     // ~ one record per 300 bytes of FASTQ; grows if wrong
+        offsets.reserve(guess); id_offsets.reserve(guess);
+        return bases && ids;
+    }
+    void close_record() { offsets.push_back(nb); }
     void add_id(const uint8_t* p, size_t n) {
         if (n && p[n - 1] == '\r') --n;
-        ids.insert(ids.end(), p, p + n);
-        id_offsets.push_back(ids.size());
+        memcpy(ids + ni, p, n); ni += n;
+        id_offsets.push_back(ni);
     }
 };
 
@@ -43,14 +56,20 @@ inline size_t next_line(const uint8_t* b, size_t len, size_t p, size_t* e) {
     return nl ? *e + 1 : len;
 }
 
+// true if [p, p + n) holds a byte <= 0x20 (every whitespace byte normalize(false) removes is one); the loop has no
+// early exit so that the compiler vectorises it
+inline bool may_hold_ws(const uint8_t* p, size_t n) {
+    unsigned any = 0;
+    for (size_t i = 0; i < n; ++i) any |= (unsigned)(p[i] <= 0x20);
+    return any != 0;
+}
+
 void append_sequence(Batch& out, const uint8_t* p, size_t n, bool strip_ws) {
-    if (!strip_ws) { out.bases.insert(out.bases.end(), p, p + n); return; }
-    size_t old = out.bases.size();
-    out.bases.resize(old + n);
-    uint8_t* d = out.bases.data() + old;
+    uint8_t* d = out.bases + out.nb;
+    if (!strip_ws || !may_hold_ws(p, n)) { memcpy(d, p, n); out.nb += n; return; }    // the usual line: nothing to strip
     size_t m = 0;
     for (size_t i = 0; i < n; ++i) { uint8_t c = p[i]; d[m] = c; m += is_ws(c) ? 0 : 1; }
-    out.bases.resize(old + m);
+    out.nb += m;
 }
 
 int parse_fasta(const uint8_t* b, size_t len, bool strip_ws, Batch& out) {
@@ -62,7 +81,7 @@ int parse_fasta(const uint8_t* b, size_t len, bool strip_ws, Batch& out) {
         if (!strip_ws) {  // raw bytes keep interior line breaks, lose the final end-of-line run
             size_t e = raw_end;
             while (e > raw_begin && (b[e - 1] == '\n' || b[e - 1] == '\r')) --e;
-            out.bases.insert(out.bases.end(), b + raw_begin, b + e);
+            memcpy(out.bases + out.nb, b + raw_begin, e - raw_begin); out.nb += e - raw_begin;
         }
         out.close_record();
         open = false;
@@ -130,7 +149,8 @@ inline uint8_t comp(uint8_t c) {
 OKH_EXPORT void* okh_fastx_parse(const uint8_t* buf, uint64_t len, int strip_ws, int* status) {
     Batch* out = new Batch();
     int st;
-    if (len == 0) st = FX_EMPTY;
+    if (!out->begin((size_t)len)) st = FX_MALFORMED;      // out of host memory: reported as unparseable
+    else if (len == 0) st = FX_EMPTY;
     else if (buf[0] == '>') st = parse_fasta(buf, (size_t)len, strip_ws != 0, *out);
     else if (buf[0] == '@') st = parse_fastq(buf, (size_t)len, strip_ws != 0, *out);
     else st = FX_BAD_START;
@@ -138,10 +158,10 @@ OKH_EXPORT void* okh_fastx_parse(const uint8_t* buf, uint64_t len, int strip_ws,
     return out;
 }
 OKH_EXPORT uint64_t okh_batch_n_records(void* h) { return ((Batch*)h)->offsets.size() - 1; }
-OKH_EXPORT uint64_t okh_batch_n_bases(void* h) { return ((Batch*)h)->bases.size(); }
-OKH_EXPORT const uint8_t* okh_batch_bases(void* h) { return ((Batch*)h)->bases.data(); }
+OKH_EXPORT uint64_t okh_batch_n_bases(void* h) { return ((Batch*)h)->nb; }
+OKH_EXPORT const uint8_t* okh_batch_bases(void* h) { return ((Batch*)h)->bases; }
 OKH_EXPORT const uint64_t* okh_batch_offsets(void* h) { return ((Batch*)h)->offsets.data(); }
-OKH_EXPORT const uint8_t* okh_batch_ids(void* h) { return ((Batch*)h)->ids.data(); }
+OKH_EXPORT const uint8_t* okh_batch_ids(void* h) { return ((Batch*)h)->ids; }
 OKH_EXPORT const uint64_t* okh_batch_id_offsets(void* h) { return ((Batch*)h)->id_offsets.data(); }
 OKH_EXPORT void okh_batch_free(void* h) { delete (Batch*)h; }
 
