@@ -378,9 +378,9 @@ def format_counts(kmers, counts, k) -> bytes:
     """count.rs:127-135"""
     kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
     counts = np.ascontiguousarray(counts, dtype=np.uint64)
-    buf = C.create_string_buffer(len(kmers) * (k + 22) + 1)
-    n = host_lib().okh_format_counts(_ptr(kmers), _ptr(counts), len(kmers), k, buf)
-    return buf.raw[:n]
+    buf = np.empty(len(kmers) * (k + 22) + 1, dtype=np.uint8)        # k bases + tab + <= 20 digits + newline per line
+    n = host_lib().okh_format_counts(_ptr(kmers), _ptr(counts), len(kmers), k, _ptr(buf))
+    return buf[:n].tobytes()
 
 
 # ---- counter (count.rs) ------------------------------------------------------------------------------
