@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -32,6 +33,7 @@ const uint8_t* okh_batch_ids(void* h);
 const uint64_t* okh_batch_id_offsets(void* h);
 void okh_batch_free(void* h);
 uint64_t okh_format_counts(const uint64_t* kmers, const uint64_t* counts, uint64_t n, unsigned k, char* out);
+uint64_t okh_format_counts_size(const uint64_t* counts, uint64_t n, unsigned k);
 const char* okh_io_last_error();
 void* okh_read_file(const char* path, int by_magic);
 const uint8_t* okh_file_data(void* h);
@@ -259,11 +261,14 @@ void run_count(const Parsed& p) {
     }
     uint64_t *keys = nullptr, *counts = nullptr, n = 0;
     gpu(ok_counter_finish(c, min_count, &keys, &counts, &n));
-    std::string text((size_t)n * (k + 22), '\0');
-    text.resize(okh_format_counts(keys, counts, n, k, &text[0]));
+    // exact-size, uninitialised text buffer: config 2's table is 215 M lines = 7.5 GB of text
+    const uint64_t text_bytes = okh_format_counts_size(counts, n, k);
+    std::unique_ptr<char[]> text(new char[text_bytes + 1]);
+    okh_format_counts(keys, counts, n, k, text.get());
     ok_free(keys); ok_free(counts);
     ok_counter_destroy(c);
-    write_out(out_path, text, true, "Failed to get output writer for file: " + quoted(out_path));
+    if (okh_write_file(out_path.c_str(), (const uint8_t*)text.get(), text_bytes, 1))
+        fail("Failed to get output writer for file: " + quoted(out_path));
     info("Successfully wrote k-mer counts to " + quoted(out_path));
 }
 

@@ -188,6 +188,13 @@ inline char* format_line(uint64_t kmer, uint64_t count, unsigned k, char* p) {
 }
 }  // namespace
 
+// exact size of the text okh_format_counts will write (so that the caller need not allocate k + 22 bytes per line)
+OKH_EXPORT uint64_t okh_format_counts_size(const uint64_t* counts, uint64_t n, unsigned k) {
+    uint64_t bytes = 0;
+    for (uint64_t i = 0; i < n; ++i) bytes += k + 2 + dec_digits(counts[i]);
+    return bytes;
+}
+
 OKH_EXPORT uint64_t okh_format_counts(const uint64_t* kmers, const uint64_t* counts, uint64_t n, unsigned k,
                                       char* out) {
     unsigned nt = std::thread::hardware_concurrency();
