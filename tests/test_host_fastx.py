@@ -57,3 +57,30 @@ def test_synth_is_deterministic_and_thread_independent():
     c = np.zeros(100 * 150, np.uint8)
     H.okh_synth_reads(ok._ptr(g), len(g), 7, 100, 100, 150, 5000, 1000, ok._ptr(c), 2)
     assert np.array_equal(a[100 * 150:], c)
+
+
+def test_parser_fast_path_and_stripping_agree_on_large_inputs(oracle):
+    """the parser copies lines without whitespace with one memcpy and strips the others byte by byte: both paths, CRLF
+    line ends, wrapped FASTA and a FASTQ with 20,000 records give the oracle's batch"""
+    rng = np.random.default_rng(23)
+    seq = np.frombuffer(b"ACGTNacgtn", np.uint8)[rng.integers(0, 10, 300_000)]
+    from orion_kmer_b200 import synth
+    fasta = synth.fasta_text(b"chr1 some description", seq, width=61)
+    fasta_crlf = fasta.replace(b"\n", b"\r\n")
+    fasta_ws = fasta.replace(b"ACG", b"A C\tG", 2000)
+    n = 20_000
+    reads = seq[:n * 15].copy()
+    fastq = b"".join(b"@r%d extra\n%s\n+\n%s\n" % (i, bytes(reads[i * 15:(i + 1) * 15]), b"I" * 15) for i in range(n))
+    for text in (fasta, fasta_crlf, fasta_ws, fastq, fastq.replace(b"\n", b"\r\n")):
+        got = ok.parse_fastx(text)
+        want = oracle.parse_fastx(text)                 # [(id, raw sequence bytes)]: ids and record framing
+        assert got.n_records == (1 if text[:1] == b">" else n)
+        assert not np.isin(got.bases, np.frombuffer(b" \t\r\n", np.uint8)).any()
+        if text[:1] == b">":
+            assert np.array_equal(got.bases, seq) and got.ids == [b"chr1 some description"]
+        else:
+            assert np.array_equal(got.bases, reads) and got.ids[n - 1] == b"r%d extra" % (n - 1)
+            assert np.array_equal(got.offsets, np.arange(n + 1, dtype=np.uint64) * np.uint64(15))
+        assert len(want) == got.n_records and [w[0] for w in want[:50]] == got.ids[:50]
+        ws = bytes.maketrans(b"", b"")
+        assert bytes(got.bases[:int(got.offsets[1])]) == want[0][1].translate(ws, b" \t\r\n")

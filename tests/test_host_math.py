@@ -194,3 +194,18 @@ def test_plan_with_hint_sizes_sub_partitions_for_their_distinct_keys():
     assert _plan(3_000_000)["slices"] == 0
     assert _plan(24_000_000)["slices"] == 8
     assert _plan(1_500_000_000)["slices"] == 16
+
+
+def test_format_counts_threaded_chunks_match_the_oracle_byte_for_byte(oracle):
+    """count.rs:127-135 text: above 2^18 lines the formatter sizes chunks first and lets several threads write them at
+    their final offsets; k mod 4 != 0 exercises the per-base head before the four-bases-per-lookup body"""
+    rng = np.random.default_rng(17)
+    for k, n in ((31, 400_000), (21, 300_000), (32, 270_000), (5, 1000), (1, 4)):
+        hi = 2 ** (2 * k) if k < 32 else 2 ** 64
+        keys = np.unique(rng.integers(0, hi, n, dtype=np.uint64))
+        counts = rng.integers(1, 10 ** int(rng.integers(1, 12)), len(keys)).astype(np.uint64)
+        counts[:2] = [1, 2 ** 64 - 1]
+        text = ok.format_counts(keys, counts, k)
+        assert text == oracle.format_counts(keys, counts, k), k
+        assert text.count(b"\n") == len(keys)
+    assert ok.format_counts(np.zeros(0, np.uint64), np.zeros(0, np.uint64), 31) == b""
