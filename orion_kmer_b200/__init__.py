@@ -167,6 +167,8 @@ def host_lib():
             getattr(L, n).restype = vp
             getattr(L, n).argtypes = [vp]
         L.okh_batch_free.argtypes = [vp]
+        L.okh_fastx_parse_mt.restype = vp
+        L.okh_fastx_parse_mt.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.okh_format_counts.restype = C.c_uint64
         L.okh_format_counts.argtypes = [vp, vp, C.c_uint64, C.c_uint, vp]
         L.okh_synth_genome.argtypes = [C.c_uint64, C.c_uint64, vp]
@@ -356,11 +358,12 @@ class Batch:
         return len(self.offsets) - 1
 
 
-def parse_fastx(content: bytes, norm_mode=NORMALIZED) -> Batch:
-    """parse_fastx_reader (+ whitespace removal of normalize(false) when NORMALIZED)."""
+def parse_fastx(content: bytes, norm_mode=NORMALIZED, threads=-1) -> Batch:
+    """parse_fastx_reader (+ whitespace removal of normalize(false) when NORMALIZED).  threads: -1 = as many as the host
+    offers for large texts (the text is cut at record starts), 1 = the sequential parser, n = exactly n pieces"""
     H = host_lib()
     st = C.c_int()
-    h = H.okh_fastx_parse(content, len(content), 1 if norm_mode == NORMALIZED else 0, C.byref(st))
+    h = H.okh_fastx_parse_mt(content, len(content), 1 if norm_mode == NORMALIZED else 0, threads, C.byref(st))
     try:
         if st.value:
             raise FastxError({1: "empty file", 2: "invalid start byte", 3: "malformed FASTQ"}[st.value])

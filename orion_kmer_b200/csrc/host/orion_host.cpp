@@ -7,6 +7,7 @@
 //                         -> the C-ABI batch layout (bases + offsets) and the record ids
 //   okh_format_counts     count.rs:127-135  "KMER\tcount\n"
 //   okh_synth_*           seeded synthetic workloads of SURVEY.md section 8(d) (SplitMix64)
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -143,19 +144,106 @@ inline uint8_t comp(uint8_t c) {
 
 }  // namespace
 
+namespace {
+
+// ---- parallel framing -----------------------------------------------------------------------------
+// A large text is cut at record starts and the pieces are parsed by several threads into their own batches,
+// which are then concatenated (offsets shifted).  Record starts can be recognised from any byte offset:
+//   FASTA: a line that begins with '>';
+//   FASTQ (strictly 4 lines per record, as parse_fastq requires): a line that begins with '@' whose second
+//          successor begins with '+'.  A quality line may begin with '@' as well, but then the line two further
+//          on is a sequence line, which never begins with '+'.
+inline size_t line_start_after(const uint8_t* b, size_t len, size_t p) {
+    if (p == 0) return 0;
+    const uint8_t* nl = (const uint8_t*)memchr(b + p - 1, '\n', len - (p - 1));
+    return nl ? (size_t)(nl - b) + 1 : len;
+}
+
+size_t next_record_start(const uint8_t* b, size_t len, size_t from, bool fastq) {
+    size_t p = line_start_after(b, len, from);
+    while (p < len) {
+        size_t e, l1 = next_line(b, len, p, &e);
+        if (!fastq) { if (b[p] == '>') return p; }
+        else if (b[p] == '@' && l1 < len) {
+            size_t e1, l2 = next_line(b, len, l1, &e1);
+            if (l2 < len && b[l2] == '+') return p;
+        }
+        p = l1;
+    }
+    return len;
+}
+
+int parse_one(const uint8_t* b, size_t len, bool fastq, bool strip_ws, Batch& out) {
+    if (!out.begin(len)) return FX_MALFORMED;            // out of host memory: reported as unparseable
+    return fastq ? parse_fastq(b, len, strip_ws, out) : parse_fasta(b, len, strip_ws, out);
+}
+
+int parse_parallel(const uint8_t* b, size_t len, bool fastq, bool strip_ws, unsigned parts, Batch& out) {
+    std::vector<size_t> cut(1, 0);
+    for (unsigned i = 1; i < parts; ++i) {
+        const size_t c = next_record_start(b, len, len / parts * i, fastq);
+        if (c > cut.back() && c < len) cut.push_back(c);
+    }
+    cut.push_back(len);
+    const size_t n = cut.size() - 1;
+    if (n < 2) return parse_one(b, len, fastq, strip_ws, out);
+    std::vector<Batch> piece(n);
+    std::vector<int> st(n, FX_OK);
+    {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < n; ++i)
+            th.emplace_back([&, i] { st[i] = parse_one(b + cut[i], cut[i + 1] - cut[i], fastq, strip_ws, piece[i]); });
+        for (auto& t : th) t.join();
+    }
+    for (size_t i = 0; i < n; ++i) if (st[i] != FX_OK) return st[i];
+    std::vector<size_t> b0(n + 1, 0), i0(n + 1, 0), r0(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) {
+        b0[i + 1] = b0[i] + piece[i].nb; i0[i + 1] = i0[i] + piece[i].ni; r0[i + 1] = r0[i] + piece[i].offsets.size() - 1;
+    }
+    out.bases = (uint8_t*)malloc(b0[n] + 1); out.ids = (uint8_t*)malloc(i0[n] + 1);
+    if (!out.bases || !out.ids) return FX_MALFORMED;
+    out.nb = b0[n]; out.ni = i0[n];
+    out.offsets.resize(r0[n] + 1); out.id_offsets.resize(r0[n] + 1);
+    out.offsets[0] = 0; out.id_offsets[0] = 0;
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < n; ++i)
+        th.emplace_back([&, i] {
+            memcpy(out.bases + b0[i], piece[i].bases, piece[i].nb);
+            memcpy(out.ids + i0[i], piece[i].ids, piece[i].ni);
+            for (size_t r = 1; r < piece[i].offsets.size(); ++r) {
+                out.offsets[r0[i] + r] = piece[i].offsets[r] + b0[i];
+                out.id_offsets[r0[i] + r] = piece[i].id_offsets[r] + i0[i];
+            }
+        });
+    for (auto& t : th) t.join();
+    return FX_OK;
+}
+
+}  // namespace
+
+// threads < 0: as many as the host offers (at most 16, at least 8 MB of text per thread); 1: the sequential parser
+OKH_EXPORT void* okh_fastx_parse_mt(const uint8_t* buf, uint64_t len, int strip_ws, int threads, int* status) {
+    Batch* out = new Batch();
+    int st;
+    if (len == 0) { out->begin(0); st = FX_EMPTY; }
+    else if (buf[0] != '>' && buf[0] != '@') { out->begin(0); st = FX_BAD_START; }
+    else {
+        unsigned parts = threads < 0 ? std::thread::hardware_concurrency() : (unsigned)threads;
+        if (threads < 0) parts = (unsigned)std::min<uint64_t>(std::min<unsigned>(parts, 16u), len / (8u << 20));
+        if (threads < 0 && parts < 4) parts = 1;        // the merge copy makes 2-3 pieces slower than the sequential parser (measured)
+        if (parts < 1) parts = 1;
+        st = parts > 1 ? parse_parallel(buf, (size_t)len, buf[0] == '@', strip_ws != 0, parts, *out)
+                       : parse_one(buf, (size_t)len, buf[0] == '@', strip_ws != 0, *out);
+    }
+    *status = st;
+    return out;
+}
+
 // ---- FASTA/FASTQ framing ------------------------------------------------------------------
 // strip_ws != 0: count/build/classify semantics (whitespace removed, as normalize(false) does;
 // the device handles case, U and invalid bytes).  strip_ws == 0: query semantics (raw bytes).
 OKH_EXPORT void* okh_fastx_parse(const uint8_t* buf, uint64_t len, int strip_ws, int* status) {
-    Batch* out = new Batch();
-    int st;
-    if (!out->begin((size_t)len)) st = FX_MALFORMED;      // out of host memory: reported as unparseable
-    else if (len == 0) st = FX_EMPTY;
-    else if (buf[0] == '>') st = parse_fasta(buf, (size_t)len, strip_ws != 0, *out);
-    else if (buf[0] == '@') st = parse_fastq(buf, (size_t)len, strip_ws != 0, *out);
-    else st = FX_BAD_START;
-    *status = st;
-    return out;
+    return okh_fastx_parse_mt(buf, len, strip_ws, -1, status);
 }
 OKH_EXPORT uint64_t okh_batch_n_records(void* h) { return ((Batch*)h)->offsets.size() - 1; }
 OKH_EXPORT uint64_t okh_batch_n_bases(void* h) { return ((Batch*)h)->nb; }

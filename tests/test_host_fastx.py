@@ -84,3 +84,49 @@ def test_parser_fast_path_and_stripping_agree_on_large_inputs(oracle):
         assert len(want) == got.n_records and [w[0] for w in want[:50]] == got.ids[:50]
         ws = bytes.maketrans(b"", b"")
         assert bytes(got.bases[:int(got.offsets[1])]) == want[0][1].translate(ws, b" \t\r\n")
+
+
+def _same_batch(a, b):
+    return (np.array_equal(a.bases, b.bases) and np.array_equal(a.offsets, b.offsets) and a.ids == b.ids)
+
+
+def test_parallel_framing_equals_the_sequential_parser():
+    """the text is cut at record starts found from arbitrary byte offsets ('>' lines; '@' lines whose second successor
+    begins with '+') and the pieces are parsed by several threads: same batch as the sequential parser, for quality
+    lines that begin with '@' or '+', blank lines, CRLF, multi-line FASTA records, fewer records than threads"""
+    rng = np.random.default_rng(29)
+    alphabet = np.frombuffer(b"ACGTNacgt", np.uint8)
+    qual = np.frombuffer(b"@+I#5", np.uint8)
+
+    def fastq(n, nl=b"\n", blank_every=0):
+        out = []
+        for i in range(n):
+            m = int(rng.integers(1, 40))
+            seq = bytes(alphabet[rng.integers(0, len(alphabet), m)])
+            q = bytes(qual[rng.integers(0, len(qual), m)])             # '@' and '+' as first quality characters too
+            out.append(b"@r%d some text" % i + nl + seq + nl + b"+" + (b"r%d" % i if i % 3 == 0 else b"") + nl + q + nl)
+            if blank_every and i % blank_every == 0:
+                out.append(nl)
+        return b"".join(out)
+
+    def fasta(n, nl=b"\n"):
+        out = []
+        for i in range(n):
+            m = int(rng.integers(0, 400))
+            seq = bytes(alphabet[rng.integers(0, len(alphabet), m)])
+            out.append(b">g%d desc" % i + nl + nl.join(seq[j:j + 37] for j in range(0, m, 37)) + (nl if m else b""))
+        return b"".join(out)
+
+    texts = [fastq(2000), fastq(500, b"\r\n"), fastq(700, blank_every=5), fastq(3), fastq(1),
+             fasta(1500), fasta(300, b"\r\n"), fasta(1), fasta(2)]
+    for text in texts:
+        for mode in (ok.NORMALIZED, ok.RAW):
+            want = ok.parse_fastx(text, mode, threads=1)
+            for t in (2, 3, 7, 16):
+                assert _same_batch(ok.parse_fastx(text, mode, threads=t), want), (text[:20], mode, t)
+    # errors survive the split: a record cut short in the middle of the text
+    bad = fastq(400)
+    bad = bad[:len(bad) // 2] + b"@broken\nACGT\n" + bad[len(bad) // 2:]
+    for t in (1, 4):
+        with pytest.raises(ok.FastxError):
+            ok.parse_fastx(bad, threads=t)

@@ -15,15 +15,16 @@ g = synth.genome(3, 5_000_000)
 bases = synth.reads(g, 3, args.reads)
 texts = {"FASTQ (150 bp reads)": synth.fastq_text(bases, args.reads), "FASTA (one record, 80 columns)": synth.fasta_text(b"chr1", g)}
 for name, text in texts.items():
-    best = None
-    for _ in range(3):
-        st = C.c_int()
-        t0 = time.perf_counter()
-        h = H.okh_fastx_parse(text, len(text), 1, C.byref(st))
-        dt = time.perf_counter() - t0
-        H.okh_batch_free(h)
-        best = dt if best is None else min(best, dt)
-    print(f"okh_fastx_parse {name}: {len(text) / 1e6:.0f} MB in {best * 1e3:.0f} ms = {len(text) / best / 1e9:.2f} GB/s (1 thread)")
+    for threads, label in ((1, "sequential"), (-1, f"automatic: up to {min(os.cpu_count() or 1, 16)} pieces cut at record starts")):
+        best = None
+        for _ in range(3):
+            st = C.c_int()
+            t0 = time.perf_counter()
+            h = H.okh_fastx_parse_mt(text, len(text), 1, threads, C.byref(st))
+            dt = time.perf_counter() - t0
+            H.okh_batch_free(h)
+            best = dt if best is None else min(best, dt)
+        print(f"okh_fastx_parse {name}, {label}: {len(text) / 1e6:.0f} MB in {best * 1e3:.0f} ms = {len(text) / best / 1e9:.2f} GB/s")
 rng = np.random.default_rng(1)
 n = 4_000_000
 keys = np.sort(rng.integers(0, 2 ** 62, n, dtype=np.uint64))
