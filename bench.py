@@ -190,6 +190,14 @@ def cpu_baseline(n_reads_total, genome_len, sample_reads, all_cores=True):
     return out, (bases, off, keys, counts)
 
 
+def oracle_slice_checker():
+    """The checker multi.bench verifies one key slice of the sharded table with (the oracle is test infrastructure:
+    it is only ever the checker, never the thing measured)."""
+    import oracle
+    oracle.build()
+    return oracle.count_batch_slice_mt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -246,7 +254,7 @@ def run_ours(args):
     if world > 1:
         from orion_kmer_b200 import multi
         return multi.bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config,
-                           ClockSampler, measured_peak, METRIC, numa_node)
+                           ClockSampler, measured_peak, METRIC, numa_node, slice_checker=oracle_slice_checker())
 
     g, bases, off = make_workload(ok, synth, n_reads, genome_len)
     n_bases = len(bases)
@@ -418,6 +426,8 @@ def main():
     ap.add_argument("--hint", type=int, default=0, help="expected distinct k-mers per GPU")
     ap.add_argument("--sample-reads", type=int, default=250_000,
                     help="reads in the CPU baseline sample (250k = 37.5 M bases: ~10-20 s of single-thread CPU work)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the parity check of the sharded table")
+    ap.add_argument("--parity-seconds", type=float, default=60.0, help="N > 1: CPU budget of the key-slice check")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

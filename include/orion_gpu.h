@@ -153,6 +153,27 @@ int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_ba
                             const uint32_t* d_hist_mine, const uint32_t* d_hist_l1_all,
                             uint32_t* d_cursors_out);
 int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all);
+/* multi-GPU, chunked exchange over the copy engines (the default form).  Same sampling and the same key-range
+ * ownership as the sharded scatter above, but the SMs never touch NVLink: the batch is scattered in n_chunks
+ * chunks; chunk c of a sender writes what it extracts for owner o into its own contiguous sub-block (a header with
+ * the fills of its level-1 regions, then the regions), laid out identically in the sender's send buffer and in
+ * the owner's level-1 buffer, and ONE plain asynchronous peer copy per (owner, chunk) moves it while the next chunk
+ * is being extracted.  The layout is computed on the host from the all-gathered per-chunk histograms.
+ *   ok_xchg_geometry        like ok_shard_geometry, also fixes n_chunks; then ok_shard_set_buffers
+ *   ok_xchg_sample_device   -> d_hist_fine[n_ranks << sub_bits], d_hist_l1c[n_chunks][n_ranks << l1_bits]
+ *        caller: reduce-scatter(sum) d_hist_fine -> d_hist_mine; all-gather d_hist_l1c -> HOST array
+ *                h_l1c_all[n_ranks][n_chunks][n_ranks << l1_bits]
+ *   ok_xchg_scatter_device  plan + chunked scatter + peer copies; returns when this sender's copies have landed
+ *        caller: any collective (e.g. the all-reduce of the ranks' success flags) is the barrier
+ *   ok_xchg_count_device    fills from the headers, level-2 scatter chunk by chunk, count
+ * An overflowing region fails ok_xchg_scatter_device on that rank; all ranks then fall back as above. */
+int ok_xchg_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* sub_bits, uint32_t* l1_bits, uint32_t* n_chunks,
+                     uint64_t* buffer_keys);
+int ok_xchg_sample_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                          uint64_t n_records, uint32_t* d_hist_fine, uint32_t* d_hist_l1c);
+int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                           uint64_t n_records, const uint32_t* d_hist_mine, const uint32_t* h_l1c_all);
+int ok_xchg_count_device(ok_counter* c);
 /* count.rs:106-119: entries with count >= min_count, ascending by k-mer value. */
 int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** kmers, uint64_t** counts,
                       uint64_t* n);

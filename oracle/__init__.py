@@ -66,6 +66,10 @@ def lib():
                                        u64p, u64p]
         L.orc_count_batch_mt.argtypes = [C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int,
                                          C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]
+        L.orc_count_batch_slice_mt.argtypes = [C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                               C.c_int, C.POINTER(u64p), C.POINTER(u64p), u64p]
+        L.orc_count_batch_ranged_mt.argtypes = [C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int,
+                                                C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]
         _lib = L
     return _lib
 
@@ -220,6 +224,26 @@ def count_batch_mt(k, bases, offsets, n_threads, min_count=1):
     pk, pc, n = u64p(), u64p(), C.c_uint64()
     lib().orc_count_batch_mt(k, _ptr(bases), _ptr(offsets), len(offsets) - 1, n_threads, min_count,
                              C.byref(pk), C.byref(pc), C.byref(n))
+    return _take(pk, pc, n.value)
+
+
+def count_batch_slice_mt(k, bases, offsets, lo, hi, n_threads):
+    """Count table restricted to canonical k-mers in [lo, hi] (inclusive); raw bases (no normalize pass)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    pk, pc, n = u64p(), u64p(), C.c_uint64()
+    lib().orc_count_batch_slice_mt(k, _ptr(bases), _ptr(offsets), len(offsets) - 1, int(lo), int(hi), n_threads,
+                                   C.byref(pk), C.byref(pc), C.byref(n))
+    return _take(pk, pc, n.value)
+
+
+def count_batch_ranged_mt(k, bases, offsets, n_threads, min_count=1):
+    """Whole count table of a batch too large for per-thread maps (8 bytes per window of scratch memory)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    pk, pc, n = u64p(), u64p(), C.c_uint64()
+    lib().orc_count_batch_ranged_mt(k, _ptr(bases), _ptr(offsets), len(offsets) - 1, n_threads, min_count,
+                                    C.byref(pk), C.byref(pc), C.byref(n))
     return _take(pk, pc, n.value)
 
 

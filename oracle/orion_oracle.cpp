@@ -448,4 +448,111 @@ void orc_count_batch_mt(unsigned k, const uint8_t* bases, const uint64_t* off, u
     for (size_t i = 0; i < all.size(); ++i) { (*keys)[i] = all[i].first; (*counts)[i] = all[i].second; }
 }
 
+
+// ---- checkers for inputs too large for one hash map (also "not reference behaviour" in their ORGANISATION
+// only: every window still goes through seq_to_u64 + canonical_u64 above and an exact map) -------------------
+//
+// orc_count_batch_slice_mt: the count table restricted to canonical k-mers in [lo, hi] (inclusive bounds), reads
+// split over threads.  The multi-GPU bench verifies one narrow key slice of the global table with it: every rank
+// runs it over its own reads, the partial tables are summed.
+void orc_count_batch_slice_mt(unsigned k, const uint8_t* bases, const uint64_t* off, uint64_t n, uint64_t lo,
+                              uint64_t hi, int n_threads, uint64_t** keys, uint64_t** counts, uint64_t* n_out) {
+    if (n_threads < 1) n_threads = 1;
+    const int T = n_threads;
+    std::vector<CountMap> maps; maps.reserve(T);
+    for (int t = 0; t < T; ++t) maps.emplace_back(1 << 12);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t] {
+            CountMap& m = maps[t];
+            for (uint64_t r = n * t / T; r < n * (t + 1) / T; ++r) {
+                const uint8_t* seq = bases + off[r]; const size_t len = (size_t)(off[r + 1] - off[r]);
+                if (len < k) continue;
+                for (size_t i = 0; i + k <= len; ++i) {
+                    uint64_t v;
+                    if (!seq_to_u64(seq + i, k, k, &v)) continue;
+                    const uint64_t c = canonical_u64(v, k);
+                    if (c >= lo && c <= hi) m.add(c, 1);
+                }
+            }
+        });
+    for (auto& t : th) t.join();
+    CountMap all(1 << 12);
+    for (int t = 0; t < T; ++t)
+        for (size_t i = 0; i <= maps[t].mask; ++i) if (maps[t].used[i]) all.add(maps[t].keys[i], maps[t].vals[i]);
+    std::vector<std::pair<uint64_t, uint64_t>> v; v.reserve(all.n);
+    for (size_t i = 0; i <= all.mask; ++i) if (all.used[i]) v.emplace_back(all.keys[i], all.vals[i]);
+    std::sort(v.begin(), v.end());
+    *n_out = v.size();
+    *keys = (uint64_t*)malloc(sizeof(uint64_t) * (v.size() + 1));
+    *counts = (uint64_t*)malloc(sizeof(uint64_t) * (v.size() + 1));
+    for (size_t i = 0; i < v.size(); ++i) { (*keys)[i] = v[i].first; (*counts)[i] = v[i].second; }
+}
+
+// orc_count_batch_ranged_mt: the WHOLE count table of a batch whose distinct k-mers would not fit per-thread maps
+// (config 2: 1.16e9 windows, 2.15e8 distinct).  Pass 1 (threads over reads): canonical k-mer of every window,
+// filed by its top 8 key bits.  Pass 2 (threads over the 256 key ranges, ascending): exact map per range, sorted,
+// appended -- ranges are ordered, so the concatenation is the sorted table of count.rs:106-119.
+// Peak memory: 8 bytes per window + the maps of the ranges in flight.
+void orc_count_batch_ranged_mt(unsigned k, const uint8_t* bases, const uint64_t* off, uint64_t n, int n_threads,
+                               uint64_t min_count, uint64_t** keys, uint64_t** counts, uint64_t* n_out) {
+    if (n_threads < 1) n_threads = 1;
+    const int T = n_threads, R = 256;
+    const unsigned shift = 2 * k >= 8 ? 2 * k - 8 : 0;
+    std::vector<std::vector<std::vector<uint64_t>>> filed(T, std::vector<std::vector<uint64_t>>(R));
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                auto& mine = filed[t];
+                for (uint64_t r = n * t / T; r < n * (t + 1) / T; ++r) {
+                    const uint8_t* seq = bases + off[r]; const size_t len = (size_t)(off[r + 1] - off[r]);
+                    if (len < k) continue;
+                    for (size_t i = 0; i + k <= len; ++i) {
+                        uint64_t v;
+                        if (!seq_to_u64(seq + i, k, k, &v)) continue;
+                        const uint64_t c = canonical_u64(v, k);
+                        mine[(size_t)((c >> shift) & 255u)].push_back(c);
+                    }
+                }
+            });
+        for (auto& t : th) t.join();
+    }
+    std::vector<std::vector<std::pair<uint64_t, uint64_t>>> parts(R);
+    {
+        std::atomic<int> next{0};
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&] {
+                for (;;) {
+                    const int r = next.fetch_add(1);
+                    if (r >= R) break;
+                    size_t tot = 0;
+                    for (int s = 0; s < T; ++s) tot += filed[s][r].size();
+                    size_t cap = 1 << 12; while (cap < tot / 2 + 16) cap <<= 1;
+                    CountMap m(cap);
+                    for (int s = 0; s < T; ++s) {
+                        for (uint64_t c : filed[s][r]) m.add(c, 1);
+                        std::vector<uint64_t>().swap(filed[s][r]);
+                    }
+                    auto& out = parts[r]; out.reserve(m.n);
+                    for (size_t i = 0; i <= m.mask; ++i)
+                        if (m.used[i] && m.vals[i] >= min_count) out.emplace_back(m.keys[i], m.vals[i]);
+                    std::sort(out.begin(), out.end());
+                }
+            });
+        for (auto& t : th) t.join();
+    }
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    *n_out = total;
+    *keys = (uint64_t*)malloc(sizeof(uint64_t) * (total + 1));
+    *counts = (uint64_t*)malloc(sizeof(uint64_t) * (total + 1));
+    size_t o = 0;
+    for (auto& p : parts) {
+        for (auto& e : p) { (*keys)[o] = e.first; (*counts)[o] = e.second; ++o; }
+        std::vector<std::pair<uint64_t, uint64_t>>().swap(p);
+    }
+}
+
 }  // extern "C"

@@ -95,6 +95,10 @@ ABI = {
     "ok_shard_sample_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
     "ok_shard_scatter_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, vp]),
     "ok_shard_count_device": (C.c_int, [vp, vp]),
+    "ok_xchg_geometry": (C.c_int, [vp, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), u64p]),
+    "ok_xchg_sample_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
+    "ok_xchg_scatter_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
+    "ok_xchg_count_device": (C.c_int, [vp]),
     "ok_counter_finish": (C.c_int, [vp, C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]),
     "ok_counter_finish_device": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp), u64p]),
     "ok_counter_set_path": (C.c_int, [vp, C.c_int]),
@@ -462,6 +466,22 @@ class KmerCounter:
 
     def shard_count_device(self, d_cursors_all_ptr):
         _check(lib().ok_shard_count_device(self._h, d_cursors_all_ptr))
+
+    # ---- chunked exchange over the copy engines (the default multi-GPU form); collectives stay with the caller ----
+    def xchg_geometry(self, n_bases_max):
+        sb, lb, nc, cap = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+        _check(lib().ok_xchg_geometry(self._h, n_bases_max, C.byref(sb), C.byref(lb), C.byref(nc), C.byref(cap)))
+        return sb.value, lb.value, nc.value, cap.value
+
+    def xchg_sample_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_fine_ptr, d_hist_l1c_ptr):
+        _check(lib().ok_xchg_sample_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_fine_ptr, d_hist_l1c_ptr))
+
+    def xchg_scatter_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_mine_ptr, h_l1c_all):
+        h = np.ascontiguousarray(h_l1c_all, dtype=np.uint32)
+        _check(lib().ok_xchg_scatter_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_mine_ptr, _ptr(h)))
+
+    def xchg_count_device(self):
+        _check(lib().ok_xchg_count_device(self._h))
 
     def add_kmers_device(self, d_kmers_ptr, n):
         _check(lib().ok_counter_add_kmers_device(self._h, d_kmers_ptr, n))

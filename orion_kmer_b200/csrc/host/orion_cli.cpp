@@ -288,8 +288,9 @@ void run_build(const Parsed& p) {
     Db db; db.h = okh_db_new((uint8_t)k);
     for (auto& path : genomes) {
         Batch b;
-        load_fastx(path, true, true, "Failed to open input file for buffered reading: " + quoted(path),
-                   "Failed to create FASTA/Q reader for file: " + path, b);
+        // anyhow prints the OUTERMOST context (main.rs:10-13 logs "{}"): build.rs:39,43 with the lossy path, unquoted
+        load_fastx(path, true, true, "Failed to get buffered file reader for file: " + path,
+                   "Failed to parse FASTA/Q content from: " + path, b);
         Set s;
         gpu(ok_set_create((uint8_t)k, OK_NORM_NORMALIZED, 0, &s.s));
         gpu(ok_set_add_batch(s.s, okh_batch_bases(b.h), okh_batch_offsets(b.h), b.n_records()));
@@ -395,8 +396,9 @@ void run_classify(const Parsed& p) {
     }
     // input k-mer counts, filtered by min_kmer_frequency (classify.rs:135-201)
     Batch b;
-    load_fastx(in_path, true, true, "Failed to open input file for buffered reading: " + quoted(in_path),
-               "Failed to create FASTA/Q reader for input file: " + in_path, b);
+    // classify.rs:143-155: outermost contexts, path formatted with {:?}
+    load_fastx(in_path, true, true, "Failed to get buffered file reader for file: " + quoted(in_path),
+               "Failed to parse FASTA/Q content from: " + quoted(in_path), b);
     ok_counter* c = nullptr;
     gpu(ok_counter_create((uint8_t)k, OK_NORM_NORMALIZED, 0, &c));
     gpu(ok_counter_add_batch(c, okh_batch_bases(b.h), okh_batch_offsets(b.h), b.n_records()));

@@ -146,6 +146,15 @@ struct ShardState {
     OkShardBlocks* h_blk = nullptr;          // page-locked mirror
     unsigned *reg_beg = nullptr, *reg_end = nullptr, *reg_fill = nullptr, *send_cur = nullptr, *send_end = nullptr;
     unsigned long long* d_received = nullptr;
+    // chunked exchange over the copy engines (ok_xchg_*)
+    unsigned n_chunks = 0;                   // chunks per batch, agreed by all ranks
+    unsigned long long* d_send = nullptr; uint64_t cap_send = 0;   // sub-blocks for the other owners, built locally
+    unsigned* d_xchg = nullptr;              // cur | end | beg (sender side), rbeg | rend | rfill (receiver side): n_chunks x 1024 each; then hdr_send | hdr_recv: n_chunks x 8
+    cudaStream_t s_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool xchg_pending = false;               // a batch has been scattered and exchanged, not yet counted
+    unsigned xchg_chunks_used = 0;
+    float ms_copy_tail = 0;                  // what the peer copies took beyond the last scatter kernel
 };
 
 struct PartHost {                            // page-locked mirror of the batch's scalars
@@ -505,10 +514,10 @@ void part_launch_items(ok_counter* c, PartPlan& pl) {
 // the sub-partitions per level-1 bin).  Sorted runs land in place (keys in d_buf2, counts in
 // d_buf1); pl.scan[p] = output offset of sub-partition p; host_total (page-locked, optional)
 // receives the running total of distinct k-mers after this range.
-int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, bool whole, unsigned long long* host_total) {
+int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, bool whole, unsigned long long* host_total, bool level2 = true) {
     const OkPartSpill ps{c->spill, c->d_stats};
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
-    if (pl.cfg.b2 > 0) {
+    if (pl.cfg.b2 > 0 && level2) {
         auto k_l2 = OK_BY_K(c->k, k_part_scatter_keys, 2, true);
         TRY(set_smem(k_l2, sizeof(OkScatterKeysSmem)));
         if (whole)
@@ -550,9 +559,10 @@ int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, boo
 // level 2 + count + scan, shared by the two entry points.  The keys are already scattered into
 // level-1 bins in d_buf1 (b2 > 0) or straight into sub-partitions in d_buf2 (b2 == 0).  Leaves
 // the result as sorted sub-partition runs (RUN_SPARSE); compaction happens when it is asked for.
-int part_finish(ok_counter* c, PartPlan& pl) {
-    part_launch_items(c, pl);
-    TRY(part_launch_range(c, pl, 0, pl.n_sub, true, nullptr));
+int part_finish(ok_counter* c, PartPlan& pl, bool level2 = true) {
+    // level2 == false: the caller has already run the level-2 scatter (chunk by chunk: ok_xchg_count_device)
+    if (level2) part_launch_items(c, pl);
+    TRY(part_launch_range(c, pl, 0, pl.n_sub, true, nullptr, level2));
     CU(cudaEventRecord(c->ev_p[5], c->s_main));
     // the one host round trip of the batch: totals, slice boundaries of the result, statistics
     const unsigned step = std::max<unsigned>(1, pl.n_sub / RESULT_SLICES);
@@ -1088,6 +1098,9 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
     cudaFree(c->d_out_keys); cudaFree(c->d_out_counts);
     cudaFree(c->d_run_keys); cudaFree(c->d_run_counts); if (!c->buf1_external) cudaFree(c->d_buf1); cudaFree(c->d_buf2); cudaFree(c->d_cnt);
     cudaFree(c->shard.d_state); cudaFree(c->shard.d_received); cudaFree(c->shard.d_snap); cudaFreeHost(c->shard.h_blk);
+    cudaFree(c->shard.d_send); cudaFree(c->shard.d_xchg);
+    for (auto st : c->shard.s_peer) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto e : c->shard.ev_chunk) if (e) cudaEventDestroy(e);
     cudaFree(c->d_meta); cudaFreeHost(c->h_part);
     for (auto e : c->ev_p) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_chunks) cudaEventDestroy(e);
@@ -1585,6 +1598,246 @@ OK_EXPORT int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all
     return r == PART_RETRY ? set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list") : r;
 }
 
+// ---- multi-GPU exchange, third form: chunked scatter + one copy-engine peer copy per (peer, chunk) ----
+// Per batch and rank:  ok_xchg_sample_device -> [reduce-scatter of the fine histogram, all-gather of the per-chunk
+// level-1 histograms] -> ok_xchg_scatter_device (host plan; per chunk: extraction + multisplit by (owner, level-1
+// bin) into the chunk's sub-blocks, then one plain async peer copy per owner on that owner's copy stream, under the
+// next chunk's extraction; returns once every copy of this sender has landed) -> [any collective = the barrier]
+// -> ok_xchg_count_device (per chunk: fills from the sub-block headers, level-2 scatter; then the count).
+namespace {
+unsigned host_part_capacity(unsigned sampled, unsigned stride, uint64_t limit) {      // == ok_part_capacity (partition.cuh)
+    const unsigned long long est = (unsigned long long)sampled * stride;
+    unsigned long long cap = est;
+    if (stride > 1) cap += (unsigned long long)(6.0f * sqrtf((float)est * (float)stride)) + 128ull;
+    if (cap > limit) cap = limit;
+    return (unsigned)((cap + 1ull) & ~1ull);
+}
+constexpr unsigned XCHG_STRIDE = 1024;   // entries per chunk row of the d_xchg arrays
+}  // namespace
+
+OK_EXPORT int ok_xchg_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* sub_bits, uint32_t* l1_bits, uint32_t* n_chunks,
+                               uint64_t* buffer_keys) {
+    if (!n_chunks) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_geometry: NULL argument");
+    TRY(ok_shard_geometry(c, n_bases_max, sub_bits, l1_bits, buffer_keys));
+    ShardState& sh = c->shard;
+    unsigned nc = 8;
+    if (const char* ev = getenv("ORION_XCHG_CHUNKS")) nc = (unsigned)std::min(8, std::max(1, atoi(ev)));
+    const uint64_t n_tiles = (n_bases_max + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    if (n_tiles < 64ull * nc) nc = 1;             // small batches: the per-chunk regions would be mostly slack
+    sh.n_chunks = nc;
+    // a sub-block carries a header and every region its own 6-sigma slack: n_chunks x senders x bins regions per owner
+    const uint64_t regions = (uint64_t)nc << (sh.g + sh.b1);
+    sh.cap_keys += regions * 200 + (uint64_t)(6.0 * std::sqrt((double)sh.stride) * std::sqrt((double)regions * (double)(n_bases_max + n_bases_max / 4)));
+    if (sh.cap_keys >= (1ull << 32)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_geometry: batch too large for 32-bit offsets");
+    if (!sh.d_xchg) CU(cudaMalloc((void**)&sh.d_xchg, (6 * 8 * XCHG_STRIDE + 2 * 8 * 8) * sizeof(unsigned)));
+    for (int r = 0; r < c->n_shards; ++r) if (!sh.s_peer[r] && r != c->shard_rank) CU(cudaStreamCreateWithFlags(&sh.s_peer[r], cudaStreamNonBlocking));
+    for (auto& e : sh.ev_chunk) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *n_chunks = nc; *buffer_keys = sh.cap_keys;
+    return OK_SUCCESS;
+}
+
+// d_hist_fine[n_ranks << sub_bits] (owner, sub-partition); d_hist_l1c[n_chunks][n_ranks << l1_bits] (chunk, owner, level-1 bin)
+OK_EXPORT int ok_xchg_sample_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                                    uint64_t n_records, uint32_t* d_hist_fine, uint32_t* d_hist_l1c) {
+    TRY(shard_check(c, "ok_xchg_sample_device", n_bases));
+    if (!d_hist_fine || !d_hist_l1c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_sample_device: NULL histogram");
+    if (n_bases && ((uintptr_t)d_bases & 15u)) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
+    ShardState& sh = c->shard;
+    if (!sh.n_chunks) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_sample_device: ok_xchg_geometry first");
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    const unsigned n_regs = (unsigned)c->n_shards << sh.b1;
+    CU(cudaEventRecord(c->ev_a, c->s_main));
+    CU(cudaMemsetAsync(d_hist_fine, 0, ((size_t)c->n_shards << sh.sub_bits) * sizeof(unsigned), c->s_main));
+    CU(cudaMemsetAsync(d_hist_l1c, 0, (size_t)sh.n_chunks * n_regs * sizeof(unsigned), c->s_main));
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    if (n_tiles && n_records) {
+        const uint64_t sampled = (n_tiles + sh.stride - 1) / sh.stride;
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((sampled + 7) / 8, (uint64_t)grid_sm * 4));
+        auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_xchg_sample<true> : k_xchg_sample<false>;
+        const size_t smem = (size_t)sh.n_chunks * n_regs * sizeof(unsigned);
+        TRY(set_smem(kern, smem));
+        const uint64_t per_chunk = (n_tiles + sh.n_chunks - 1) / sh.n_chunks;
+        LAUNCH(kern, blocks, 256, smem, c->s_main, d_bases, n_bases, d_rec_offsets, n_records, n_tiles, (uint64_t)sh.stride, c->k,
+               shard_global_cfg(c, sh.sub_bits), d_hist_fine, 32u - (sh.g + sh.b1), n_regs, per_chunk, sh.n_chunks, d_hist_l1c);
+    }
+    CU(cudaEventRecord(c->ev_b, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&c->ms_route, c->ev_a, c->ev_b);
+    return OK_SUCCESS;
+}
+
+// d_hist_mine[1 << sub_bits]: the fine histogram summed over the ranks, this rank's slice (device);
+// h_l1c_all[n_ranks][n_chunks][n_ranks << l1_bits]: every rank's per-chunk level-1 histogram (HOST memory).
+OK_EXPORT int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                                     uint64_t n_records, const uint32_t* d_hist_mine, const uint32_t* h_l1c_all) {
+    TRY(shard_check(c, "ok_xchg_scatter_device", n_bases));
+    if (!d_hist_mine || !h_l1c_all) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_scatter_device: NULL argument");
+    ShardState& sh = c->shard;
+    if (!sh.n_chunks) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_scatter_device: ok_xchg_geometry first");
+    const unsigned W = (unsigned)c->n_shards, me = (unsigned)c->shard_rank, NC = sh.n_chunks, n_bin1 = 1u << sh.b1, n_regs = W << sh.b1;
+    PartPlan& pl = c->pl; pl = PartPlan{};
+    pl.cfg.key_shift = 64 - 2 * c->k; pl.cfg.shard_log2 = sh.g; pl.cfg.b1 = sh.b1; pl.cfg.b2 = sh.b2;
+    pl.n_sub = 1u << sh.sub_bits; pl.n_bin1 = n_bin1; pl.stride = sh.stride; pl.sharded = true;
+    const uint64_t n_units = sh.n_bases_max + sh.n_bases_max / 4;
+    pl.hinted = sh.hinted;
+    pl.big_count = sh.hinted ? std::min<uint64_t>(c->user_hint, sh.n_bases_max) / pl.n_sub > 4600 : sh.n_bases_max / pl.n_sub > 5800;
+    if (const char* ev = getenv("ORION_BIG_COUNT")) pl.big_count = atoi(ev) != 0;
+    TRY(part_layout(c, n_units, OK_TILE_BASES, 0, pl));
+    TRY(dev_reserve(&sh.d_send, &sh.cap_send, sh.cap_keys));
+    // ---- the layout, identical on every rank: owner o's buffer = for every sender, for every chunk, one sub-block
+    const unsigned hdr_keys = std::max(2u, (n_bin1 / 2u + 1u) & ~1u);
+    const uint64_t limit = std::min<uint64_t>(c->cap_buf1, 0xFFFFFFF0ull) & ~1ull;
+    std::vector<unsigned> cur((size_t)NC * XCHG_STRIDE, 0), end((size_t)NC * XCHG_STRIDE, 0), rbeg((size_t)NC * XCHG_STRIDE, 0),
+                          rend((size_t)NC * XCHG_STRIDE, 0), hdr_send(NC * 8, 0), hdr_recv(NC * 8, 0);
+    struct Copy { uint64_t src, dst, len; unsigned peer, chunk; };
+    std::vector<Copy> copies;
+    uint64_t local_run = 0;
+    bool clipped = false;
+    for (unsigned o = 0; o < W; ++o) {
+        uint64_t run = 0;
+        for (unsigned s2 = 0; s2 < W; ++s2)
+            for (unsigned ch = 0; ch < NC; ++ch) {
+                const uint32_t* h = h_l1c_all + ((size_t)s2 * NC + ch) * n_regs + (size_t)o * n_bin1;
+                const uint64_t sub_start = std::min(run, limit);
+                run += hdr_keys;
+                const uint64_t local_base = local_run;                  // only meaningful for s2 == me, o != me
+                for (unsigned b = 0; b < n_bin1; ++b) {
+                    const unsigned cap = host_part_capacity(h[b], sh.stride, limit);
+                    const uint64_t lo = std::min(run, limit), hi = std::min(run + cap, limit);
+                    if (hi - lo < cap) clipped = true;
+                    if (s2 == me) {
+                        const uint64_t shift = o == me ? 0 : local_base - sub_start;      // remote -> local coordinates (mod 2^64)
+                        cur[(size_t)ch * XCHG_STRIDE + o * n_bin1 + b] = (unsigned)(lo + shift);
+                        end[(size_t)ch * XCHG_STRIDE + o * n_bin1 + b] = (unsigned)(hi + shift);
+                    }
+                    if (o == me) { rbeg[(size_t)ch * XCHG_STRIDE + s2 * n_bin1 + b] = (unsigned)lo; rend[(size_t)ch * XCHG_STRIDE + s2 * n_bin1 + b] = (unsigned)hi; }
+                    run += cap;
+                }
+                const uint64_t sub_len = std::min(run, limit) - sub_start;
+                if (o == me) hdr_recv[ch * 8 + s2] = (unsigned)sub_start;
+                if (s2 == me) {
+                    hdr_send[ch * 8 + o] = (unsigned)(o == me ? sub_start : local_base);
+                    if (o != me) { copies.push_back({local_base, sub_start, sub_len, o, ch}); local_run += sub_len; }
+                }
+            }
+    }
+    if (local_run > sh.cap_send) return set_err(OK_ERR_INTERNAL, "chunked exchange: the send buffer is too small (%llu > %llu keys); count this batch through the two-pass route instead",
+                                                (unsigned long long)local_run, (unsigned long long)sh.cap_send);
+    (void)clipped;    // a clipped region simply spills below and the batch falls back to the exact route
+    unsigned* dx = sh.d_xchg;
+    unsigned *d_cur = dx, *d_end = dx + 8 * XCHG_STRIDE, *d_beg = dx + 16 * XCHG_STRIDE, *d_rbeg = dx + 24 * XCHG_STRIDE, *d_rend = dx + 32 * XCHG_STRIDE;
+    unsigned *d_hs = dx + 48 * XCHG_STRIDE, *d_hr = d_hs + 64;
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    CU(cudaEventRecord(c->ev_p[0], c->s_main));
+    CU(cudaMemcpyAsync(d_cur, cur.data(), cur.size() * 4, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(d_beg, cur.data(), cur.size() * 4, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(d_end, end.data(), end.size() * 4, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(d_rbeg, rbeg.data(), rbeg.size() * 4, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(d_rend, rend.data(), rend.size() * 4, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(d_hs, hdr_send.data(), hdr_send.size() * 4, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaMemcpyAsync(d_hr, hdr_recv.data(), hdr_recv.size() * 4, cudaMemcpyHostToDevice, c->s_main));
+    // my sub-partitions (as the receiver) from the summed sample
+    CU(cudaMemcpyAsync(pl.hist, d_hist_mine, pl.n_sub * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->s_main));
+    LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)sh.cap_keys, pl.chunk_sum);
+    LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)sh.cap_keys, pl.cfg.b2,
+           pl.chunk_sum, (unsigned)pl.cap_bound, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
+    CU(cudaEventRecord(c->ev_p[1], c->s_main));
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    const uint64_t per_chunk = (n_tiles + NC - 1) / NC;
+    OkPeerOut po{}; po.shift = sh.b1;
+    for (unsigned r = 0; r < W; ++r) po.p[r] = r == me ? c->d_buf1 : sh.d_send;
+    auto kern = c->norm_mode == OK_NORM_NORMALIZED ? OK_BY_K(c->k, k_part_scatter_bases, true, true) : OK_BY_K(c->k, k_part_scatter_bases, false, true);
+    TRY(set_smem(kern, sizeof(OkScatterSmem)));
+    const OkPartCfg cfg = shard_global_cfg(c, sh.b1);      // level-1 bin id = (owner, bin)
+    size_t next_copy = 0;
+    std::sort(copies.begin(), copies.end(), [](const Copy& a, const Copy& b) { return a.chunk != b.chunk ? a.chunk < b.chunk : a.peer < b.peer; });
+    for (unsigned ch = 0; ch < NC; ++ch) {
+        const uint64_t t0 = ch * per_chunk, t1 = std::min<uint64_t>(n_tiles, t0 + per_chunk);
+        if (t1 > t0 && n_records) {
+            const uint64_t max_warps = (uint64_t)grid_sm * (OK_SB_KPT == 16 ? 3 : 2) * OK_SB_WARPS;
+            const uint64_t tpw = std::max<uint64_t>(1, (t1 - t0 + max_warps - 1) / max_warps);
+            const unsigned blocks = (unsigned)((t1 - t0 + OK_SB_WARPS * tpw - 1) / (OK_SB_WARPS * tpw));
+            LAUNCH(kern, blocks, OK_SB_THREADS, sizeof(OkScatterSmem), c->s_main, d_bases, n_bases, d_rec_offsets, n_records, t0, t1, tpw, c->k,
+                   cfg, d_cur + (size_t)ch * XCHG_STRIDE, (const unsigned*)(d_end + (size_t)ch * XCHG_STRIDE), (unsigned long long*)nullptr,
+                   (OkPartSpill{c->spill, c->d_stats}), c->d_stats->route_counts, po, OkPushDesc{});
+        }
+        LAUNCH(k_xchg_headers, 1, 1024, 0, c->s_main, d_cur + (size_t)ch * XCHG_STRIDE, d_end + (size_t)ch * XCHG_STRIDE, d_beg + (size_t)ch * XCHG_STRIDE,
+               n_regs, sh.b1, me, d_hs + ch * 8, c->d_buf1, sh.d_send);
+        CU(cudaEventRecord(sh.ev_chunk[ch], c->s_main));
+        // one plain asynchronous peer copy per (owner, chunk), each owner on its own stream: they run on the copy
+        // engines under the extraction of the next chunk
+        for (; next_copy < copies.size() && copies[next_copy].chunk == ch; ++next_copy) {
+            const Copy& cp = copies[next_copy];
+            CU(cudaStreamWaitEvent(sh.s_peer[cp.peer], sh.ev_chunk[ch], 0));
+            if (cp.len) CU(cudaMemcpyAsync(sh.peer[cp.peer] + cp.dst, sh.d_send + cp.src, cp.len * 8, cudaMemcpyDeviceToDevice, sh.s_peer[cp.peer]));
+        }
+    }
+    CU(cudaEventRecord(c->ev_p[2], c->s_main));
+    for (unsigned r = 0; r < W; ++r)
+        if (r != me) { CU(cudaEventRecord(sh.ev_chunk[0], sh.s_peer[r])); CU(cudaStreamWaitEvent(c->s_main, sh.ev_chunk[0], 0)); }
+    CU(cudaEventRecord(c->ev_b, c->s_main));
+    TRY(read_stats(c));          // drains the compute stream, which has waited for every peer copy
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&c->ms_scatter1, c->ev_p[1], c->ev_p[2]);
+    cudaEventElapsedTime(&c->ms_push, c->ev_p[2], c->ev_b);
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_p[0], c->ev_b); c->ms_route += ms;
+    sh.xchg_chunks_used = NC;
+    if (c->h_stats->spill_n) {
+        // a region overflowed: the spilled k-mers belong to OTHER ranks, this rank cannot count them
+        CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        c->h_stats->spill_n = 0;
+        return set_err(OK_ERR_INTERNAL, "chunked exchange overflowed a sampled region; count this batch through the two-pass route instead");
+    }
+    sh.xchg_pending = true;
+    return OK_SUCCESS;
+}
+
+// every rank has returned from ok_xchg_scatter_device (the caller's collective in between is the barrier)
+OK_EXPORT int ok_xchg_count_device(ok_counter* c) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_count_device: NULL handle");
+    ShardState& sh = c->shard;
+    if (!c->pl.sharded || !sh.xchg_pending || c->run_state != RUN_NONE) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_count_device: no exchanged batch pending");
+    sh.xchg_pending = false;
+    PartPlan& pl = c->pl;
+    if (pl.cfg.b2 == 0) return set_err(OK_ERR_INTERNAL, "sharded path needs two scatter levels");
+    const uint64_t windows_before = c->windows;
+    const unsigned W = (unsigned)c->n_shards, n_regs = W << sh.b1, NC = sh.xchg_chunks_used;
+    unsigned* dx = sh.d_xchg;
+    unsigned *d_rbeg = dx + 24 * XCHG_STRIDE, *d_rend = dx + 32 * XCHG_STRIDE, *d_rfill = dx + 40 * XCHG_STRIDE, *d_hr = dx + 48 * XCHG_STRIDE + 64;
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    const OkPartSpill ps{c->spill, c->d_stats};
+    auto k_l2 = OK_BY_K(c->k, k_part_scatter_keys, 2, true);
+    TRY(set_smem(k_l2, sizeof(OkScatterKeysSmem)));
+    const float ms_scatter1 = c->ms_scatter1;
+    CU(cudaEventRecord(c->ev_p[2], c->s_main));      // part_finish times the level-2 scatter from here
+    CU(cudaMemsetAsync(sh.d_received, 0, 8, c->s_main));
+    for (unsigned ch = 0; ch < NC; ++ch) {
+        LAUNCH(k_xchg_fills, 1, 1024, 0, c->s_main, c->d_buf1, d_hr + ch * 8, n_regs, sh.b1, d_rbeg + (size_t)ch * XCHG_STRIDE,
+               d_rend + (size_t)ch * XCHG_STRIDE, d_rfill + (size_t)ch * XCHG_STRIDE, sh.d_received);
+        LAUNCH(k_part_items, 32, 1024, 0, c->s_main, d_rbeg + (size_t)ch * XCHG_STRIDE, d_rfill + (size_t)ch * XCHG_STRIDE, d_rend + (size_t)ch * XCHG_STRIDE,
+               n_regs, pl.n_bin1 - 1u, pl.item_off, pl.item_n, pl.item_bin, pl.scal, (unsigned*)nullptr);
+        LAUNCH(k_l2, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
+               pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps, (const unsigned*)nullptr, 0u, 0u);
+    }
+    CU(cudaMemcpyAsync(&c->h_part->received, sh.d_received, 8, cudaMemcpyDeviceToHost, c->s_main));
+    TRY(part_finish(c, pl, /*level2=*/false));
+    c->ms_scatter1 = ms_scatter1;                     // measured by ok_xchg_scatter_device (part_finish re-read moved events)
+    c->ms_insert = c->ms_sample + c->ms_scatter1 + c->ms_push + c->ms_scatter2 + c->ms_count;
+    c->windows = windows_before + c->h_part->received;
+    CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    if (part_hint_misled(c, pl)) {
+        TRY(part_discard(c, windows_before));
+        c->distrust_hint = true; sh.ready = false;
+        return set_err(OK_ERR_INTERNAL, "capacity hint too low for the sharded count (%llu sub-partitions outgrew their tables); "
+                                        "recount the batch: the hint is ignored from now on", (unsigned long long)c->h_part->scal.n_deferred);
+    }
+    const int r = part_absorb_spills(c, windows_before);
+    return r == PART_RETRY ? set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list") : r;
+}
+
 OK_EXPORT int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t** d_kmers,
                                        const uint64_t** d_counts, uint64_t* n) {
     if (!c || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_finish_device: NULL argument");
@@ -1698,6 +1951,11 @@ int take_builder(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_counter** 
         if (!g_spare_builders.empty() && k >= 1 && k <= 32 && (norm_mode == OK_NORM_NORMALIZED || norm_mode == OK_NORM_RAW)) {
             ok_counter* c = g_spare_builders.back();
             g_spare_builders.pop_back();
+            if (c->tv.slots && c->tv.key_shift != 64u - 2u * k) {
+                // the pooled table was laid out for another k: its home slots (key << key_shift) would no longer be
+                // monotone in the new keys and every sorted consumer of the set would be handed an unsorted array
+                cudaFree(c->tv.slots); c->tv = OkTableView{}; c->grows = 0; c->occupied = 0;
+            }
             c->k = k; c->norm_mode = norm_mode; c->hint = capacity_hint; c->user_hint = capacity_hint;
             c->distrust_hint = false; c->path_mode = 0;
             *out = c;
@@ -1742,8 +2000,12 @@ int set_seal(ok_set* s) {
         const uint64_t total = n + (s->has_max ? 1 : 0);
         if (total) {
             CU(cudaMalloc((void**)&s->d_keys, total * 8));
-            if (n) CU(cudaMemcpy(s->d_keys, dk, n * 8, cudaMemcpyDeviceToDevice));
-            if (s->has_max) { unsigned long long m = OK_EMPTY_KEY; CU(cudaMemcpy(s->d_keys + n, &m, 8, cudaMemcpyHostToDevice)); }
+            // on the set's own stream and drained here: every consumer runs on non-blocking streams, which the legacy
+            // default stream does not order against, and the builder's buffer (dk) goes back to the pool right below
+            if (n) CU(cudaMemcpyAsync(s->d_keys, dk, n * 8, cudaMemcpyDeviceToDevice, s->st));
+            const unsigned long long m = OK_EMPTY_KEY;
+            if (s->has_max) CU(cudaMemcpyAsync(s->d_keys + n, &m, 8, cudaMemcpyHostToDevice, s->st));
+            CU(cudaStreamSynchronize(s->st));
         }
         n = total;
         give_builder(s->builder);
@@ -1803,7 +2065,8 @@ OK_EXPORT int ok_set_from_sorted(uint8_t k, const uint64_t* kmers, uint64_t n, o
     s->has_max = (n && kmers[n - 1] == OK_EMPTY_KEY) ? 1 : 0;
     cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
     if (e == cudaSuccess && n) e = cudaMalloc((void**)&s->d_keys, n * 8);
-    if (e == cudaSuccess && n) e = cudaMemcpy(s->d_keys, kmers, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(s->d_keys, kmers, n * 8, cudaMemcpyHostToDevice, s->st);
+    if (e == cudaSuccess && n) e = cudaStreamSynchronize(s->st);     // pageable source: the DMA has landed before anyone reads the set
     if (e != cudaSuccess) { ok_set_destroy(s); return set_err(OK_ERR_CUDA, "CUDA error %s in ok_set_from_sorted", cudaGetErrorName(e)); }
     *out = s;
     return OK_SUCCESS;
@@ -1826,7 +2089,7 @@ OK_EXPORT int ok_set_export(ok_set* s, uint64_t** kmers, uint64_t* n) {
     TRY(set_seal(s));
     void* h = nullptr;
     TRY(pool_alloc(&h, s->n * 8));
-    if (s->n) CU(cudaMemcpy(h, s->d_keys, s->n * 8, cudaMemcpyDeviceToHost));
+    if (s->n) { CU(cudaMemcpyAsync(h, s->d_keys, s->n * 8, cudaMemcpyDeviceToHost, s->st)); CU(cudaStreamSynchronize(s->st)); }
     *kmers = (uint64_t*)h; *n = s->n;
     return OK_SUCCESS;
 }

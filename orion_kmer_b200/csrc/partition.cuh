@@ -362,6 +362,77 @@ k_shard_fills(const unsigned* __restrict__ cur_all, unsigned g_log2, unsigned me
     if (threadIdx.x == 0) *n_received = got;
 }
 
+// ------------------------------------------ chunked exchange over the copy engines (ok_xchg_*) --
+// Third form of the multi-GPU exchange.  The batch is scattered in a few CHUNKS; chunk c of sender s writes
+// what it extracts for owner o into its own SUB-BLOCK (s -> o, c): a header (the fills of its level-1
+// regions) followed by one region per level-1 bin, sized from the sender's per-chunk sample.  A sub-block
+// is contiguous and laid out identically in the sender's send buffer and in the owner's level-1 buffer, so
+// ONE plain asynchronous peer copy per (peer, chunk) moves it -- issued on a per-peer copy stream as soon
+// as the chunk's scatter kernel has finished, i.e. under the extraction of the next chunk.  The SMs never
+// touch NVLink (measured: SM-issued remote stores saturate near 400 GB/s per GPU in an 8-way all-to-all,
+// a copy-engine peer copy reaches 720-770).  The layout is computed on the host from the all-gathered
+// per-chunk level-1 histograms, identically on every rank.
+template <bool MAP_U>
+__global__ void __launch_bounds__(256)
+k_xchg_sample(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
+              uint64_t n_rec, uint64_t n_tiles, uint64_t stride, unsigned k, OkPartCfg cfg /* global: b1 = g + sub_bits */,
+              unsigned* __restrict__ hist_fine, unsigned l1_shift /* 32 - (g + level-1 bits) */, unsigned n_regs,
+              uint64_t tiles_per_chunk, unsigned n_chunks, unsigned* __restrict__ hist_l1c /* [n_chunks][n_regs] */) {
+    extern __shared__ unsigned sh_l1c[];      // the (chunk, owner, level-1 bin) histogram of this CTA
+    for (unsigned i = threadIdx.x; i < n_chunks * n_regs; i += blockDim.x) sh_l1c[i] = 0;
+    __syncthreads();
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t t = warp * stride; t < n_tiles; t += warps * stride) {
+        const unsigned chunk = (unsigned)min((uint64_t)(n_chunks - 1u), t / tiles_per_chunk);
+        unsigned* l1 = sh_l1c + chunk * n_regs;
+        ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t, t + 1, t + 1, k, lane,
+            [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {
+                ok_lane_windows(pc, cc, okmask, k, [&](int, uint64_t key) {
+                    const uint32_t phi = ok_part_phi(key, cfg);
+                    atomicAdd(&hist_fine[ok_phi_sub(phi, cfg)], 1u);
+                    atomicAdd(&l1[phi >> l1_shift], 1u);
+                });
+            }, true);
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < n_chunks * n_regs; i += blockDim.x) { const unsigned v = sh_l1c[i]; if (v) atomicAdd(&hist_l1c[i], v); }
+}
+
+// after a chunk's scatter: the fills of this sender's regions go into the header of every sub-block, so they
+// travel with the data (no second collective).  hdr[o] = key offset of the header of sub-block (me -> o, chunk)
+// in the buffer the scatter wrote it to (own level-1 buffer for o == me, the send buffer otherwise).
+__global__ void __launch_bounds__(1024)
+k_xchg_headers(const unsigned* __restrict__ cur, const unsigned* __restrict__ end, const unsigned* __restrict__ beg,
+               unsigned n_regs, unsigned b1, unsigned me, const unsigned* __restrict__ hdr,
+               unsigned long long* __restrict__ own, unsigned long long* __restrict__ send) {
+    const unsigned i = threadIdx.x;
+    if (i >= n_regs) return;
+    const unsigned o = i >> b1, b = i & ((1u << b1) - 1u);
+    const unsigned e = min(cur[i], end[i]);
+    reinterpret_cast<unsigned*>((o == me ? own : send) + hdr[o])[b] = e > beg[i] ? e - beg[i] : 0u;
+}
+
+// receiver: headers of the sub-blocks (s -> me, chunk) -> fill cursor of each of my regions of that chunk
+__global__ void __launch_bounds__(1024)
+k_xchg_fills(const unsigned long long* __restrict__ own, const unsigned* __restrict__ hdr /* [senders] */, unsigned n_regs, unsigned b1,
+             const unsigned* __restrict__ reg_beg, const unsigned* __restrict__ reg_end, unsigned* __restrict__ reg_fill,
+             unsigned long long* __restrict__ n_received /* += */) {
+    __shared__ unsigned long long wsum[33];
+    const unsigned r = threadIdx.x, s = r >> b1, b = r & ((1u << b1) - 1u);
+    unsigned long long got = 0;
+    if (r < n_regs) {
+        const unsigned fill = reinterpret_cast<const unsigned*>(own + hdr[s])[b];
+        const unsigned cap = reg_end[r] - reg_beg[r];
+        const unsigned f = min(fill, cap);
+        reg_fill[r] = reg_beg[r] + f;
+        got = f;
+    }
+    got = ok_block_sum_1024(got, wsum);
+    if (threadIdx.x == 0 && got) atomicAdd(n_received, got);
+}
+
 // ------------------------------------------------------------- shared multisplit machinery --
 // Slotted staging: the 8192 staging slots are split evenly among the bins of the level, a key's
 // rank inside its bin (one shared-memory atomicAdd) is its slot, so one pass stages the round.

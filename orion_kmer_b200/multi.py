@@ -15,10 +15,59 @@ import time
 import numpy as np
 
 
+class Coll:
+    """The handful of small collectives of the exchange.  Under NCCL they run on device tensors; under any other
+    backend (gloo: the CPU tests, and the two-processes-on-ONE-GPU test that the single-GPU test tier can run) device
+    tensors are staged through host memory.  Results are identical; only the plumbing differs."""
+
+    def __init__(self, dist, torch, group=None):
+        self.dist, self.torch, self.group = dist, torch, group
+        self.native = dist.get_backend(group) == "nccl"
+
+    def all_reduce(self, t, op=None):
+        op = op if op is not None else self.dist.ReduceOp.SUM
+        if self.native or not t.is_cuda:
+            self.dist.all_reduce(t, op=op, group=self.group)
+        else:
+            h = t.cpu()
+            self.dist.all_reduce(h, op=op, group=self.group)
+            t.copy_(h)
+        return t
+
+    def all_gather(self, out, inp):
+        """out: world * len(inp) elements, rank-major"""
+        if self.native:
+            self.dist.all_gather_into_tensor(out, inp, group=self.group)
+            return out
+        h = inp.cpu().contiguous()
+        parts = [self.torch.empty_like(h) for _ in range(self.dist.get_world_size(self.group))]
+        self.dist.all_gather(parts, h, group=self.group)
+        out.copy_(self.torch.cat(parts))
+        return out
+
+    def reduce_scatter(self, out, inp):
+        """out = this rank's slice of the element-wise sum of every rank's inp"""
+        if self.native:
+            self.dist.reduce_scatter_tensor(out, inp, group=self.group)
+            return out
+        h = inp.cpu()
+        self.dist.all_reduce(h, group=self.group)
+        r, n = self.dist.get_rank(self.group), out.numel()
+        out.copy_(h[r * n:(r + 1) * n])
+        return out
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
 def exchange(dist, torch, send, send_counts, group=None):
     """send: 1-D int64 tensor holding the k-mers for rank 0, then rank 1, ... (send_counts each).
     -> (recv tensor, recv_counts list)."""
     world = dist.get_world_size(group)
+    staged = send.is_cuda and dist.get_backend(group) != "nccl"
+    dev = send.device
+    if staged:
+        send = send.cpu()
     sc = torch.as_tensor(np.asarray(send_counts, dtype=np.int64), device=send.device)
     rc = torch.empty(world, dtype=torch.int64, device=send.device)
     dist.all_to_all_single(rc, sc, group=group)
@@ -26,7 +75,7 @@ def exchange(dist, torch, send, send_counts, group=None):
     recv = torch.empty(sum(recv_counts), dtype=torch.int64, device=send.device)
     dist.all_to_all_single(recv, send[:int(sum(send_counts))], output_split_sizes=recv_counts,
                            input_split_sizes=[int(x) for x in send_counts], group=group)
-    return recv, recv_counts
+    return (recv.to(dev) if staged else recv), recv_counts
 
 
 class ShardedCounter:
@@ -36,17 +85,20 @@ class ShardedCounter:
     receive buffer (CUDA-IPC peer memory over NVLink); the only collectives left are a world x world
     count matrix and a barrier.  fused=False: bucket locally, NCCL all_to_all_single, then count."""
 
-    def __init__(self, ok, torch, dist, k, norm_mode=0, fused=2, capacity_hint=0):
+    def __init__(self, ok, torch, dist, k, norm_mode=0, fused=3, capacity_hint=0):
         self.ok, self.torch, self.dist = ok, torch, dist
+        self.coll = Coll(dist, torch)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         # capacity_hint = expected distinct k-mers of THIS rank's shard (0: none): sizes the sub-partitions for their
         # distinct keys (fewer bins per scatter level); a hint that proves too low costs one recount, then it is ignored
         self.counter = ok.KmerCounter(k, norm_mode, capacity_hint)
         self.hinted = capacity_hint > 0
         self.counter.set_shard(self.rank, self.world)
-        # 2: sharded scatter (sample, then ONE extraction pass that writes level-1 partitioned k-mers into
-        #    the owners' buffers); 1: two-pass fused route (count, then scatter by owner); 0: NCCL all-to-all
+        # 3: chunked exchange (sample, then the extraction scatters chunk by chunk into per-chunk sub-blocks that plain
+        #    copy-engine peer copies move under the next chunk's extraction); 2: sharded scatter (a copy warp in the
+        #    extraction kernel pushes with SM stores); 1: two-pass fused route; 0: NCCL all-to-all
         self.fused = int(fused)
+        self.fallbacks = 0
         self.d_send = None
         self.recv, self.recv_cap, self.peer_ptrs = None, 0, None
         self.geom = None
@@ -55,9 +107,8 @@ class ShardedCounter:
     # ---- receive buffer shared with the peers (collective) ----
     def _ensure_recv(self, need_keys):
         torch, dist = self.torch, self.dist
-        need = torch.tensor([need_keys], device="cuda", dtype=torch.int64)
-        dist.all_reduce(need, op=dist.ReduceOp.MAX)
-        need = int(need.item())
+        need = torch.tensor([need_keys], dtype=torch.int64)
+        need = int(self.coll.all_reduce(need.cuda() if self.coll.native else need, dist.ReduceOp.MAX).item())
         if need <= self.recv_cap:
             return
         self._release_recv()
@@ -73,35 +124,101 @@ class ShardedCounter:
         if self.recv is None:
             return
         self.torch.cuda.synchronize()
-        self.dist.barrier()
+        self.coll.barrier()
         for r, p in enumerate(self.peer_ptrs):
             if r != self.rank:
                 self.ok.PeerBuffer.close_peer(p)
-        self.dist.barrier()
+        self.coll.barrier()
         self.recv.destroy()
         self.recv, self.recv_cap, self.peer_ptrs = None, 0, None
 
+    def _agree(self, ok_flag):
+        """MIN over the ranks of a success flag: every rank takes the same branch (also a barrier)"""
+        t = self.torch.tensor([int(ok_flag)], dtype=self.torch.int32)
+        return bool(int(self.coll.all_reduce(t.cuda() if self.coll.native else t, self.dist.ReduceOp.MIN).item()))
+
+    def _max(self, v):
+        t = self.torch.tensor([int(v)], dtype=self.torch.int64)
+        return int(self.coll.all_reduce(t.cuda() if self.coll.native else t, self.dist.ReduceOp.MAX).item())
+
     def count_batch_device(self, d_bases, n_bases, d_off, n_reads):
+        if self.fused == 3:
+            return self._count_xchg(d_bases, n_bases, d_off, n_reads)
         if self.fused == 2:
             return self._count_sharded(d_bases, n_bases, d_off, n_reads)
         if self.fused == 1:
             return self._count_fused(d_bases, n_bases, d_off, n_reads)
         return self._count_unfused(d_bases, n_bases, d_off, n_reads)
 
+    def _count_xchg(self, d_bases, n_bases, d_off, n_reads):
+        """sample -> [reduce-scatter of the fine histogram + all-gather of the per-chunk level-1 histograms] -> chunked
+        scatter, one copy-engine peer copy per (owner, chunk) under the next chunk's extraction -> [agreement
+        all-reduce: also the barrier] -> fills from the sub-block headers, level 2 chunk by chunk, count."""
+        torch, W = self.torch, self.world
+        t0 = time.perf_counter()
+        nmax = self._max(n_bases)
+        if self.geom is None or self.geom.get("mode") != 3 or nmax > self.geom["nmax"]:
+            sub_bits, l1_bits, n_chunks, cap = self.counter.xchg_geometry(nmax)
+            self._ensure_recv(cap)
+            self.counter.shard_set_buffers(self.peer_ptrs, self.recv_cap)
+            i32 = dict(dtype=torch.int32, device="cuda")
+            self.geom = {"mode": 3, "nmax": nmax, "sub_bits": sub_bits, "l1_bits": l1_bits, "n_chunks": n_chunks,
+                         "hist_fine": torch.empty(W << sub_bits, **i32), "hist_mine": torch.empty(1 << sub_bits, **i32),
+                         "hist_l1c": torch.empty(n_chunks * (W << l1_bits), **i32),
+                         "l1c_all": torch.empty(W * n_chunks * (W << l1_bits), **i32)}
+        g = self.geom
+        self.counter.xchg_sample_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
+                                        g["hist_fine"].data_ptr(), g["hist_l1c"].data_ptr())
+        self.coll.reduce_scatter(g["hist_mine"], g["hist_fine"])
+        self.coll.all_gather(g["l1c_all"], g["hist_l1c"])
+        h_l1c_all = g["l1c_all"].cpu().numpy().view(np.uint32)       # the layout is planned on the host, identically on every rank
+        t1 = time.perf_counter()
+        ok_flag = 1
+        try:
+            self.counter.xchg_scatter_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
+                                             g["hist_mine"].data_ptr(), h_l1c_all)
+        except self.ok.OrionError as e:
+            ok_flag = 0
+            if os.environ.get("ORION_VERBOSE"):
+                print(f"[rank {self.rank}] chunked exchange failed, falling back: {e}", flush=True)
+        t2 = time.perf_counter()
+        all_ok = self._agree(ok_flag)       # every sender's copies have landed in my buffer
+        t3 = time.perf_counter()
+        if not all_ok:                      # a sampled region overflowed somewhere: every rank recounts through the exact route
+            self.fallbacks += 1
+            self.counter.clear()
+            return self._count_unfused(d_bases, n_bases, d_off, n_reads)
+        count_ok = 1
+        try:
+            self.counter.xchg_count_device()
+        except self.ok.OrionError as e:
+            count_ok = 0
+            if os.environ.get("ORION_VERBOSE"):
+                print(f"[rank {self.rank}] sharded count failed, recounting: {e}", flush=True)
+        if not self._agree(count_ok):       # e.g. a capacity hint that is too low only shows once the shared-memory tables overflow
+            self.fallbacks += 1
+            self.counter.clear()
+            self.counter.set_capacity_hint(0)      # every rank drops the hint: the geometry must stay collective
+            self.hinted, self.geom = False, None
+            return self._count_unfused(d_bases, n_bases, d_off, n_reads)
+        t4 = time.perf_counter()
+        st = self.counter.stats()
+        self.t = {"route_ms": (t2 - t0) * 1e3, "route_count_ms": (t1 - t0) * 1e3, "route_scatter_ms": (t2 - t1) * 1e3,
+                  "exchange_ms": (t3 - t2) * 1e3, "count_ms": (t4 - t3) * 1e3,
+                  "sent_kmers": float("nan"), "sent_off_rank": float("nan"), "recv_kmers": int(st["n_windows"])}
+
     def _count_sharded(self, d_bases, n_bases, d_off, n_reads):
         """sample -> [reduce-scatter + all-gather of the histograms] -> scatter into the owners' level-1
         regions over NVLink -> [all-gather of the cursors: also the barrier] -> level 2 + count."""
         torch, dist, W = self.torch, self.dist, self.world
         t0 = time.perf_counter()
-        nmax = torch.tensor([n_bases], device="cuda", dtype=torch.int64)
-        dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
-        nmax = int(nmax.item())
-        if self.geom is None or nmax > self.geom["nmax"]:
+        nmax = self._max(n_bases)
+        if self.geom is None or self.geom.get("mode") != 2 or nmax > self.geom["nmax"]:
             sub_bits, l1_bits, cap = self.counter.shard_geometry(nmax)
             self._ensure_recv(cap)
             self.counter.shard_set_buffers(self.peer_ptrs, self.recv_cap)
             i32 = dict(dtype=torch.int32, device="cuda")
-            self.geom = {"nmax": nmax, "sub_bits": sub_bits, "l1_bits": l1_bits,
+            self.geom = {"mode": 2, "nmax": nmax, "sub_bits": sub_bits, "l1_bits": l1_bits,
                          "hist_fine": torch.empty(W << sub_bits, **i32), "hist_l1": torch.empty(W << l1_bits, **i32),
                          "hist_mine": torch.empty(1 << sub_bits, **i32), "l1_all": torch.empty(W * (W << l1_bits), **i32),
                          "cursors": torch.empty(W << l1_bits, **i32), "cur_all": torch.empty(W * (W << l1_bits), **i32),
@@ -109,8 +226,8 @@ class ShardedCounter:
         g = self.geom
         self.counter.shard_sample_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
                                          g["hist_fine"].data_ptr(), g["hist_l1"].data_ptr())
-        dist.reduce_scatter_tensor(g["hist_mine"], g["hist_fine"])
-        dist.all_gather_into_tensor(g["l1_all"], g["hist_l1"])
+        self.coll.reduce_scatter(g["hist_mine"], g["hist_fine"])
+        self.coll.all_gather(g["l1_all"], g["hist_l1"])
         torch.cuda.current_stream().synchronize()
         t1 = time.perf_counter()
         ok_flag = 1
@@ -119,34 +236,30 @@ class ShardedCounter:
                                               g["hist_mine"].data_ptr(), g["l1_all"].data_ptr(), g["cursors"].data_ptr())
         except self.ok.OrionError as e:
             ok_flag = 0
-            self.fallbacks = getattr(self, "fallbacks", 0) + 1
             if os.environ.get("ORION_VERBOSE"):
                 print(f"[rank {self.rank}] sharded scatter failed, falling back: {e}", flush=True)
         t2 = time.perf_counter()
-        g["flag"].fill_(ok_flag)
-        dist.all_reduce(g["flag"], op=dist.ReduceOp.MIN)
-        dist.all_gather_into_tensor(g["cur_all"], g["cursors"])      # every sender has finished writing into my buffer
-        all_ok = int(g["flag"].item())
+        all_ok = self._agree(ok_flag)
+        self.coll.all_gather(g["cur_all"], g["cursors"])      # every sender has finished writing into my buffer
         t3 = time.perf_counter()
         if not all_ok:          # a sampled region overflowed somewhere: every rank recounts through the exact route
+            self.fallbacks += 1
             self.counter.clear()
             return self._count_unfused(d_bases, n_bases, d_off, n_reads)
         count_ok = 1
         try:
             self.counter.shard_count_device(g["cur_all"].data_ptr())
-        except self.ok.OrionError:
-            if not self.hinted:
-                raise
+        except self.ok.OrionError as e:
             count_ok = 0
-        if self.hinted:         # a capacity hint that is too low only shows once the shared-memory tables overflow
-            g["flag"].fill_(count_ok)
-            dist.all_reduce(g["flag"], op=dist.ReduceOp.MIN)
-            if not int(g["flag"].item()):
-                self.fallbacks = getattr(self, "fallbacks", 0) + 1
-                self.counter.clear()
-                self.counter.set_capacity_hint(0)      # every rank drops the hint: the geometry must stay collective
-                self.hinted, self.geom = False, None
-                return self._count_unfused(d_bases, n_bases, d_off, n_reads)
+            if os.environ.get("ORION_VERBOSE"):
+                print(f"[rank {self.rank}] sharded count failed, recounting: {e}", flush=True)
+        # ALWAYS agreed (hint or not): a rank that raised alone would leave the others waiting in the next collective
+        if not self._agree(count_ok):
+            self.fallbacks += 1
+            self.counter.clear()
+            self.counter.set_capacity_hint(0)      # every rank drops the hint: the geometry must stay collective
+            self.hinted, self.geom = False, None
+            return self._count_unfused(d_bases, n_bases, d_off, n_reads)
         t4 = time.perf_counter()
         st = self.counter.stats()
         self.t = {"route_ms": (t2 - t0) * 1e3, "route_count_ms": (t1 - t0) * 1e3, "route_scatter_ms": (t2 - t1) * 1e3,
@@ -178,7 +291,7 @@ class ShardedCounter:
         # world x world matrix M[src][dst]
         mine = torch.from_numpy(counts.astype(np.int64)).cuda()
         M = torch.empty(self.world * self.world, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(M, mine)
+        self.coll.all_gather(M, mine)
         M = M.cpu().numpy().reshape(self.world, self.world)
         recv_total = M.sum(axis=0)
         self._ensure_recv(int(recv_total[self.rank]))
@@ -188,7 +301,7 @@ class ShardedCounter:
         dst = [self.peer_ptrs[d] + 8 * int(offs[d]) for d in range(self.world)]
         self.counter.route_scatter_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads, dst, counts)
         t2 = time.perf_counter()
-        dist.barrier()                       # every sender has finished writing into my buffer
+        self.coll.barrier()                  # every sender has finished writing into my buffer
         t3 = time.perf_counter()
         self.counter.add_kmers_device(self.recv.ptr, int(recv_total[self.rank]))
         t4 = time.perf_counter()
@@ -219,8 +332,59 @@ def all_vs_all(ok, torch, dist, sets, device=None):
     return sizes, ok.finish_all_vs_all(sizes, m.cpu().numpy().view(np.uint64))
 
 
+def verify_sharded_table(ok, dist, sc, K, bases, off, n_windows, slice_checker=None):
+    """Parity of the sharded result, every rank: keys strictly ascending, rank boundaries in order (so the ranks'
+    outputs concatenate to the sorted global table), sum of counts == windows received; and -- slice_checker given --
+    one narrow key slice straddling the boundary between two ranks against an independent CPU pass over ALL ranks'
+    reads (each rank checks its own reads, the partial tables are summed on rank 0).  -> dict on rank 0, None elsewhere.
+    slice_checker(k, bases, offsets, lo, hi) -> (keys, counts) restricted to lo <= key <= hi: bench.py passes the
+    oracle's; this package itself never loads the oracle."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pk, pc, n = sc.counter.finish_raw(1)
+    keys = np.ctypeslib.as_array(pk, shape=(max(n, 1),))[:n]
+    counts = np.ctypeslib.as_array(pc, shape=(max(n, 1),))[:n]
+    local = {"rank": rank, "n": int(n), "ascending": bool(n < 2 or np.all(keys[1:] > keys[:-1])),
+             "first": int(keys[0]) if n else None, "last": int(keys[-1]) if n else None,
+             "sum_counts": int(counts.sum(dtype=np.uint64)), "windows": int(n_windows)}
+    infos = [None] * world
+    dist.all_gather_object(infos, local)
+    # slice: 1/4096 of the key space around the first key of the middle rank
+    span = (1 << (2 * K)) >> 12
+    mid = infos[world // 2]["first"] or 0
+    lo, hi = max(0, mid - span // 2), mid + span // 2
+    a, b = np.searchsorted(keys, np.uint64(lo), "left"), np.searchsorted(keys, np.uint64(hi), "right")
+    part = {"gpu": (keys[a:b].copy(), counts[a:b].copy())}
+    if slice_checker is not None:
+        t0 = time.perf_counter()
+        part["cpu"] = slice_checker(K, bases, off, lo, hi)
+        part["cpu_s"] = time.perf_counter() - t0
+    sc.counter.free_result(pk, pc)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(part, parts, dst=0)
+    if rank != 0:
+        return None
+    out = {"ascending_all_ranks": all(i["ascending"] for i in infos),
+           "rank_boundaries_in_order": all(infos[r]["last"] < infos[r + 1]["first"] for r in range(world - 1)
+                                           if infos[r]["n"] and infos[r + 1]["n"]),
+           "sum_counts_eq_windows": all(i["sum_counts"] == i["windows"] for i in infos),
+           "distinct_total": sum(i["n"] for i in infos), "windows_total": sum(i["windows"] for i in infos)}
+    if slice_checker is not None:
+        gk = np.concatenate([p["gpu"][0] for p in parts])
+        gc = np.concatenate([p["gpu"][1] for p in parts])
+        ck = np.concatenate([p["cpu"][0] for p in parts])
+        cc = np.concatenate([p["cpu"][1] for p in parts])
+        uk, inv = np.unique(ck, return_inverse=True)
+        uc = np.zeros(len(uk), dtype=np.uint64)
+        np.add.at(uc, inv, cc)
+        out["parity_slice_ok"] = bool(np.array_equal(gk, uk) and np.array_equal(gc, uc))
+        out["slice"] = {"key_lo": int(lo), "key_hi": int(hi), "distinct": int(len(uk)), "windows": int(uc.sum()),
+                        "straddles_ranks": [world // 2 - 1, world // 2] if world > 1 else [0],
+                        "cpu_seconds_max": max(p["cpu_s"] for p in parts)}
+    return out
+
+
 def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config, ClockSampler, measured_peak,
-          metric, numa_node=None):
+          metric, numa_node=None, slice_checker=None):
     import torch.distributed as dist
     K = 31
     n_reads = args.reads
@@ -232,7 +396,7 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
     d_bases = h_bases.cuda()
     d_off = h_off.cuda()
     hint = args.hint or int(n_bases * 0.17)       # expected distinct k-mers per rank (30x coverage, 0.5 % errors)
-    sc = ShardedCounter(ok, torch, dist, K, fused=int(os.environ.get("ORION_FUSED", "2")), capacity_hint=hint)
+    sc = ShardedCounter(ok, torch, dist, K, fused=int(os.environ.get("ORION_FUSED", "3")), capacity_hint=hint)
 
     def step_device():
         sc.clear()
@@ -275,6 +439,28 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
     dt_e2e, _ = timed(step_host, args.steps, max(1, args.warmup))
     n_out = sc.counter.finish_device(1)[2]
 
+    # ---- parity of what was just timed (same counter, same geometry, same hint) -------------------------
+    # The CPU slice pass costs ~0.2 us per base and thread; when the whole batch would take too long on this
+    # host's cores the step is repeated on a prefix of every rank's reads (same buffers and geometry) and THAT
+    # table is checked -- the line says which.
+    parity = None
+    if not getattr(args, "no_parity", False):
+        threads = max(1, (os.cpu_count() or 1) // world)
+        budget_s = float(getattr(args, "parity_seconds", 60.0))
+        est_s = n_bases * 0.2e-6 / threads
+        v_reads = n_reads if est_s <= budget_s else max(10_000, int(n_reads * budget_s / est_s))
+        v_bases = v_reads * 150
+        if v_reads != n_reads:
+            sc.clear()
+            sc.count_batch_device(d_bases, v_bases, d_off, v_reads)
+        vb, vo = bases[:v_bases], off[:v_reads + 1]
+        checker = (lambda k, b, o, lo, hi: slice_checker(k, b, o, lo, hi, threads)) if slice_checker else None
+        parity = verify_sharded_table(ok, dist, sc, K, vb, vo, sc.counter.stats()["n_windows"], checker)
+        if rank == 0:
+            parity["reads_per_rank_checked"] = int(v_reads)
+            parity["full_batch"] = bool(v_reads == n_reads)
+            parity["cpu_threads_per_rank"] = threads
+
     # whole-job totals
     tot = torch.tensor([st["n_windows"], st["n_distinct"], n_bases], device="cuda", dtype=torch.float64)
     dist.all_reduce(tot)
@@ -306,13 +492,16 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
                                     "transfer_ms": mean.get("route_scatter_ms", mean["exchange_ms"]),
                                     "achieved_GBs_per_rank": nvlink_bytes / (mean.get("route_scatter_ms", mean["exchange_ms"]) / 1e3) / 1e9,
                                     "peak_GBs": 770.0, "peak_source": "B200_PROFILING.md peer copy per direction",
-                                    "mode": {2: "sharded scatter: k_part_scatter_bases<PEER> writes level-1 partitioned k-mers into the owners' buffers",
+                                    "mode": {3: "chunked exchange: k_part_scatter_bases builds per-chunk sub-blocks, one copy-engine peer copy per (owner, chunk) under the next chunk's extraction",
+                                             2: "sharded scatter: k_part_scatter_bases<PEER> writes level-1 partitioned k-mers into the owners' buffers",
                                              1: "two-pass route fused into k_part_scatter_bases<PEER> (writes into peer memory)",
                                              0: "NCCL all_to_all_single"}[sc.fused]}},
             "phases_ms": mean,
             "table": {"windows": int(windows), "distinct": int(distinct), "rank0_distinct": int(n_out),
                       "spilled": int(st["n_spilled"]), "rank0_fallbacks_to_nccl_all_to_all": int(getattr(sc, "fallbacks", 0))},
             "cpu_baseline": None,
+            "parity": parity,
+            "parity_slice_ok": None if parity is None else parity.get("parity_slice_ok"),
         }
         print(json.dumps(line))
     sc.close()

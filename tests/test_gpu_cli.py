@@ -120,7 +120,7 @@ def test_build_sniffs_gzip_and_xz_but_not_zstd(exe, golden, tmp_path):
     assert all(set(v.tolist()) == want for v in refs.values())
     # build reads RAW bytes and lets needletail sniff; needletail 0.5.1 has no zstd -> not a FASTA/Q start byte
     r = run(exe, "build", "-k", 7, "-g", os.path.join(FIX, "test_input1.fasta.zst"), "-o", tmp_path / "z.db", ok_exit=False)
-    assert r.returncode == 1 and "Failed to create FASTA/Q reader" in r.stderr
+    assert r.returncode == 1 and "Failed to parse FASTA/Q content from" in r.stderr
 
 
 # ----------------------------------------------------------------------------------- compare --

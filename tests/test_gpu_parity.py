@@ -210,6 +210,96 @@ def test_count_config2_sample_exact(oracle):
     c.close()
 
 
+def _available_host_memory():
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    for f in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(f).read().strip()
+            if v.isdigit():
+                lim = int(v)
+                try:
+                    lim -= int(open(f.replace("memory.max", "memory.current").replace("limit_in_bytes", "usage_in_bytes")).read())
+                except (OSError, ValueError):
+                    pass
+                avail = lim if avail is None else min(avail, lim)
+        except OSError:
+            pass
+    return avail
+
+
+def test_count_config2_full_batch_with_bench_hint_exact(oracle):
+    """BASELINE.json configs[1] AT FULL SIZE, counted exactly the way bench.py times it -- device-resident batch of
+    10 M x 150 bp reads, capacity hint 0.17 x bases (hint-sized sub-partitions, k_part_count with packed 16-bit counts
+    and its early-out) -- and compared, whole table, with the oracle (count.rs:23-38,106-119).  Also through the
+    host-buffer entry (sliced result pipeline) and without the hint.  The oracle pass needs ~20 GB of host memory;
+    on a smaller host four key slices (1/64 of the key space each) are compared instead."""
+    import json
+    import os
+    import time
+    import torch
+    n_reads, k = 10_000_000, 31
+    g = synth.genome(3, 5 * n_reads)
+    bases = synth.reads(g, 3, n_reads)
+    off = synth.read_offsets(n_reads)
+    n_bases = len(bases)
+    hint = int(n_bases * 0.17)
+    nt = min(os.cpu_count() or 1, 64)
+    t0 = time.time()
+    mem = _available_host_memory()
+    full = mem is None or mem > 28 * 2 ** 30
+    if full:
+        wk, wc = oracle.count_batch_ranged_mt(k, bases, off, nt)
+        slices = [(0, 2 ** 64 - 1)]
+    else:
+        span = (1 << 62) >> 6
+        slices = [(a, a + span - 1) for a in (0, (1 << 62) // 3, (1 << 62) // 2 + 12345, (1 << 62) - span)]
+        parts = [oracle.count_batch_slice_mt(k, bases, off, lo, hi, nt) for lo, hi in slices]
+        wk, wc = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    t_oracle = time.time() - t0
+
+    def check(keys, counts, what):
+        if not full:
+            sel = np.zeros(len(keys), bool)
+            for lo, hi in slices:
+                sel[np.searchsorted(keys, np.uint64(lo), "left"):np.searchsorted(keys, np.uint64(hi), "right")] = True
+            assert np.all(keys[1:] > keys[:-1]), what
+            keys, counts = keys[sel], counts[sel]
+        assert len(keys) == len(wk), (what, len(keys), len(wk))
+        assert np.array_equal(keys, wk), what
+        assert np.array_equal(counts, wc), what
+
+    d_b = torch.from_numpy(bases).cuda()
+    d_o = torch.from_numpy(off.view(np.int64)).cuda()
+    record = {"reads": n_reads, "k": k, "hint": hint, "oracle": "count_batch_ranged_mt" if full else "4 key slices of 1/64",
+              "oracle_threads": nt, "oracle_seconds": round(t_oracle, 1), "oracle_distinct": int(len(wk)),
+              "oracle_windows": int(wc.sum()), "checked": []}
+    for what, h, host in (("device batch, bench hint", hint, False), ("host batch (sliced result pipeline), bench hint", hint, True),
+                          ("device batch, no hint", 0, False)):
+        c = ok.KmerCounter(k, ok.NORMALIZED, h)
+        if host:
+            c.add_batch(bases, off)
+        else:
+            c.add_batch_device(d_b.data_ptr(), n_bases, d_o.data_ptr(), n_reads)
+        keys, counts = c.finish(1)
+        st = c.stats()
+        c.close()
+        assert st["partitioned"] == 1, what
+        check(keys, counts, what)
+        record["checked"].append({"what": what, "distinct": int(len(keys)), "windows": int(st["n_windows"]),
+                                  "n_deferred": int(st["n_deferred"]), "n_spilled": int(st["n_spilled"]), "equal": True})
+        del keys, counts
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_config2_full.json"), "w") as f:
+            json.dump(record, f, indent=1)
+
+
 def test_count_large_properties():
     """size-independent properties at a size the oracle is not run on: total = number of
     countable windows, strictly ascending keys, and both-strand invariance."""
@@ -316,6 +406,24 @@ def test_sets_random_against_oracle(oracle):
     w = ok.KmerSet.from_sorted(32, weird)
     assert w.probe_counts(np.array([2 ** 64 - 1, 5, 6], np.uint64), np.array([7, 1, 1], np.uint64)) == (2, 8)
     assert list(ok.KmerSet.union([w, ok.KmerSet.from_sorted(32, np.array([5, 9], np.uint64))]).to_array()) == [0, 5, 9, 2 ** 64 - 1]
+
+
+def test_pooled_set_builder_reused_for_another_k(oracle):
+    """A sealed set hands its builder (table included) back to the pool; the next set may have another k.  The pooled
+    table's home slots were laid out for the old k: reused as is, the readout of a small k=21 / k=31 set after a k=5
+    one is no longer sorted.  Small genomes: they stay on the table path, where the bug lived."""
+    rng = np.random.default_rng(5)
+    for ks in ([5, 21, 31], [31, 21, 5, 32, 3]):
+        for i, k in enumerate(ks):
+            g = synth.genome(900 + 10 * k + i, 10_000 + 1000 * i)
+            s = ok.KmerSet.from_fastx(k, synth.fasta_text(b"g", g))
+            want = oracle.kmer_set_batch(k, g, np.array([0, len(g)], np.uint64))
+            got = s.to_array()
+            assert np.array_equal(got, want), (ks, k)
+            other = oracle.kmer_set_batch(k, g[: len(g) // 2], np.array([0, len(g) // 2], np.uint64))
+            t = ok.KmerSet.from_sorted(k, other)
+            assert s.intersection_size(t) == len(np.intersect1d(want, other)), (ks, k)
+            s.close(); t.close()
 
 
 def test_intersection_tiled_kernel_shapes():
@@ -674,6 +782,68 @@ def test_sharded_scatter_matches_oracle(oracle, n_ranks, hint):
     wk, wc = oracle.count_batch(k, all_bases, all_off)
     assert np.array_equal(gk, wk)
     assert np.array_equal(gc, wc)
+
+
+def _xchg_dance(counters, batches, n):
+    """one step of the chunked exchange (ok_xchg_*) for every emulated rank; torch ops stand in for the collectives"""
+    import torch
+    n_ranks = len(counters)
+    dev = [(torch.from_numpy(b).cuda(), torch.from_numpy(o.view(np.int64)).cuda()) for b, o in batches]
+    nmax = max(len(b) for b, _ in batches)
+    geoms = [c.xchg_geometry(nmax) for c in counters]
+    assert len(set(geoms)) == 1
+    sub_bits, l1_bits, n_chunks, cap = geoms[0]
+    bufs = [ok.PeerBuffer(cap * 8) for _ in range(n_ranks)]
+    try:
+        for c in counters:
+            c.shard_set_buffers([b.ptr for b in bufs], cap)
+        i32 = dict(dtype=torch.int32, device="cuda")
+        hist_fine = [torch.empty(n_ranks << sub_bits, **i32) for _ in range(n_ranks)]
+        hist_l1c = [torch.empty(n_chunks * (n_ranks << l1_bits), **i32) for _ in range(n_ranks)]
+        for r, c in enumerate(counters):
+            c.xchg_sample_device(dev[r][0].data_ptr(), len(batches[r][0]), dev[r][1].data_ptr(), n,
+                                 hist_fine[r].data_ptr(), hist_l1c[r].data_ptr())
+        hist_sum = torch.stack(hist_fine).sum(0, dtype=torch.int32)
+        l1c_all = torch.cat(hist_l1c).cpu().numpy().view(np.uint32)
+        for r, c in enumerate(counters):
+            mine = hist_sum[r << sub_bits:(r + 1) << sub_bits].contiguous()
+            c.xchg_scatter_device(dev[r][0].data_ptr(), len(batches[r][0]), dev[r][1].data_ptr(), n, mine.data_ptr(), l1c_all)
+        keys, counts = [], []
+        for r, c in enumerate(counters):
+            c.xchg_count_device()
+            gk, gc = c.finish()
+            assert c.stats()["n_spilled"] == 0
+            keys.append(gk); counts.append(gc)
+        return np.concatenate(keys), np.concatenate(counts), n_chunks
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            b.destroy()
+
+
+@pytest.mark.parametrize("n_ranks", [2, 4, 8])
+@pytest.mark.parametrize("hint", [0, 600_000])
+@pytest.mark.parametrize("chunks", [8, 1, 3])
+def test_chunked_exchange_matches_oracle(oracle, monkeypatch, n_ranks, hint, chunks):
+    """ok_xchg_*: per-chunk sub-blocks moved by plain peer copies, fills carried in the sub-block headers.  Ranks of
+    unequal batch size (the last one is short), twice through the same buffers."""
+    monkeypatch.setenv("ORION_XCHG_CHUNKS", str(chunks))
+    k = 31
+    g = synth.genome(85, 400_000)
+    n = 12_000
+    batches = [(synth.reads(g, 86, n, first_read=r * n), synth.read_offsets(n)) for r in range(n_ranks)]
+    counters = [ok.KmerCounter(k, capacity_hint=hint) for _ in range(n_ranks)]
+    for r, c in enumerate(counters):
+        c.set_shard(r, n_ranks)
+    wk, wc = oracle.count_batch(k, np.concatenate([b for b, _ in batches]), synth.read_offsets(n * n_ranks))
+    for rep in range(2):
+        for c in counters:
+            c.clear()
+        gk, gc, used = _xchg_dance(counters, batches, n)
+        assert used == chunks
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc), rep
+    for c in counters:
+        c.close()
 
 
 def test_sharded_count_with_a_hint_far_too_low_asks_for_a_recount(oracle):

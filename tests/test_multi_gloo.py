@@ -131,3 +131,26 @@ def test_two_rank_all_vs_all_matches_single_process():
         assert sizes[i] == len(sets[i]) == full[i, i]
         for j in range(n):
             assert full[i, j] == len(np.intersect1d(sets[i], sets[j], assume_unique=True)), (i, j)
+
+
+def _coll_worker(rank, world, port):
+    from orion_kmer_b200 import multi
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    try:
+        c = multi.Coll(dist, torch)
+        t = torch.tensor([rank + 1], dtype=torch.int32)
+        assert c.all_reduce(t, dist.ReduceOp.MIN).item() == 1
+        inp = torch.arange(4, dtype=torch.int32) + 10 * rank
+        out = torch.empty(8, dtype=torch.int32)
+        assert c.all_gather(out, inp).tolist() == [0, 1, 2, 3, 10, 11, 12, 13]
+        mine = torch.empty(2, dtype=torch.int32)
+        assert c.reduce_scatter(mine, inp.clone()).tolist() == ([10, 12] if rank == 0 else [14, 16])
+        c.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_collective_helper_without_nccl():
+    """multi.Coll stages the exchange's small collectives through host memory on a backend without device support
+    (gloo: what the two-processes-on-one-GPU test uses); same results as the NCCL forms."""
+    mp.spawn(_coll_worker, args=(2, _free_port()), nprocs=2, join=True)
