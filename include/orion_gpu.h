@@ -85,7 +85,11 @@ int ok_canonical_u64(uint64_t kmer, uint8_t k, uint64_t* out);
 int ok_counter_create(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_counter** out);
 /* replace the capacity hint (0 = none); for a sharded counter: expected distinct k-mers of its shard */
 int ok_counter_set_capacity_hint(ok_counter* c, uint64_t capacity_hint);
-/* process_sequence_chunk over every record of the batch; host buffers (pinned or pageable).
+/* ONE table across all batches (count.rs:48,52-79): batches add up whatever their sizes.  A large batch into a
+ * counter that already holds the sorted result of earlier large batches is counted on its own by the same
+ * one-shot path and the two sorted runs are merged on the device (counts of equal k-mers summed); batches of more
+ * than ~1.8 G bases are cut into sub-batches internally.
+ * process_sequence_chunk over every record of the batch; host buffers (pinned or pageable).
  * The buffers are free again when the call returns.  For a large batch into an empty counter
  * the call returns once the batch has landed and been scattered by key range; the rest of the
  * count runs inside ok_counter_finish, slice by slice under the device-to-host copy of the
@@ -184,6 +188,9 @@ int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t**
  * shared-memory path, everything else through the device-wide table), 1 = table only,
  * 2 = partitioned whenever the counter is still empty.  Results are identical. */
 int ok_counter_set_path(ok_counter* c, int mode);
+/* multi-GPU: drop what this rank holds of the batch whose exchange just failed on some rank (every rank then
+ * recounts it through another route); the result of earlier batches is kept */
+int ok_counter_abort_batch(ok_counter* c);
 /* forget all counts, keep the allocation (bench loops) */
 int ok_counter_clear(ok_counter* c);
 int ok_counter_destroy(ok_counter* c);
@@ -205,6 +212,8 @@ typedef struct ok_counter_stats {
     int partitioned;         /* 1 when the current result is a sorted run     */
     float ms_push;           /* sharded scatter: bulk copies into the peers' buffers (NVLink) */
     uint64_t n_deferred;     /* sub-partitions the fast count kernel left to the generic one  */
+    float ms_merge;          /* device time spent merging batch runs since the last clear     */
+    uint64_t n_merges;       /* merges of a batch's run into the accumulated run              */
 } ok_counter_stats;
 int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out);
 

@@ -57,7 +57,8 @@ class CounterStats(C.Structure):
                 ("n_grows", C.c_uint64), ("ms_insert", C.c_float), ("ms_readout", C.c_float),
                 ("ms_fill", C.c_float), ("ms_route", C.c_float), ("ms_sample", C.c_float),
                 ("ms_scatter1", C.c_float), ("ms_scatter2", C.c_float), ("ms_count", C.c_float),
-                ("ms_compact", C.c_float), ("partitioned", C.c_int), ("ms_push", C.c_float), ("n_deferred", C.c_uint64)]
+                ("ms_compact", C.c_float), ("partitioned", C.c_int), ("ms_push", C.c_float), ("n_deferred", C.c_uint64),
+                ("ms_merge", C.c_float), ("n_merges", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -103,6 +104,7 @@ ABI = {
     "ok_counter_finish_device": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp), u64p]),
     "ok_counter_set_path": (C.c_int, [vp, C.c_int]),
     "ok_counter_set_capacity_hint": (C.c_int, [vp, C.c_uint64]),
+    "ok_counter_abort_batch": (C.c_int, [vp]),
     "ok_counter_clear": (C.c_int, [vp]),
     "ok_counter_destroy": (C.c_int, [vp]),
     "ok_counter_get_stats": (C.c_int, [vp, C.POINTER(CounterStats)]),
@@ -518,6 +520,9 @@ class KmerCounter:
     def set_path(self, mode):
         """0 automatic, 1 table only, 2 partitioned whenever the counter is empty"""
         _check(lib().ok_counter_set_path(self._h, mode))
+
+    def abort_batch(self):
+        _check(lib().ok_counter_abort_batch(self._h))
 
     def clear(self):
         _check(lib().ok_counter_clear(self._h))

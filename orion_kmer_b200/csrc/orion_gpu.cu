@@ -15,6 +15,7 @@
 #include "orion_gpu.h"
 #include "kernels.cuh"
 #include "partition.cuh"
+#include "merge.cuh"
 
 #define OK_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -202,6 +203,14 @@ struct ok_counter {
     unsigned long long* d_run_keys = nullptr; uint64_t cap_run_keys = 0;
     unsigned long long* d_run_counts = nullptr; uint64_t cap_run_counts = 0;
     uint64_t n_run = 0, n_deferred = 0;
+    // earlier batches' result, set aside while the next large batch is counted on its own; merged afterwards (merge.cuh)
+    unsigned long long* d_acc_keys = nullptr; uint64_t cap_acc_keys = 0;
+    unsigned long long* d_acc_counts = nullptr; uint64_t cap_acc_counts = 0;
+    uint64_t n_acc = 0;
+    unsigned long long* d_mrg_keys = nullptr; uint64_t cap_mrg_keys = 0;      // merge output (swapped with the run afterwards)
+    unsigned long long* d_mrg_counts = nullptr; uint64_t cap_mrg_counts = 0;
+    ulonglong2* d_split = nullptr; uint64_t cap_split = 0;
+    float ms_merge = 0; uint64_t n_merges = 0;
     unsigned long long* d_buf1 = nullptr; uint64_t cap_buf1 = 0;
     unsigned long long* d_buf2 = nullptr; uint64_t cap_buf2 = 0;
     unsigned long long* d_cnt = nullptr; uint64_t cap_cnt = 0;       // counts of the runs when d_buf1 is peer-mapped memory (measured: 25 % slower to write)
@@ -401,10 +410,13 @@ constexpr unsigned PART_WINDOWS_MAX = 24576;      // ... and windows per sub-par
 constexpr unsigned PART_MAX_BITS = 18;            // up to 9 bits at level 1 + up to 10 at level 2
 unsigned RESULT_SLICES = 16;            // the result pipeline compacts and ships the table in slices
 
+// A counter that already holds a sorted RUN stays on the one-shot path: the run is set aside, the batch counted on
+// its own and the two runs merged (run_stash / run_unstash).  Only a live device-wide TABLE rules the path out.
+// Batches beyond PART_MAX_UNITS are cut into sub-batches by the callers (32-bit offsets inside a batch).
+constexpr uint64_t PART_MAX_UNITS = 1792ull << 20;
 bool part_eligible(const ok_counter* c, uint64_t n_units) {
     if (c->path_mode == 1) return false;
-    if (c->run_state != RUN_NONE || c->occupied) return false;
-    if (n_units >= (1ull << 31)) return false;   // buffers are indexed with 32-bit offsets
+    if (c->run_state == RUN_NONE && c->occupied) return false;
     return c->path_mode == 2 || n_units >= PART_MIN_BASES;
 }
 
@@ -460,7 +472,7 @@ template <class K> int set_smem(K kern, size_t bytes) {
 uint64_t part_cap_bound(uint64_t n_units, unsigned n_sub, unsigned stride, uint64_t unit_chunk) {
     const double S = (double)n_units + (double)unit_chunk * (stride + 1.0);
     double b = S;
-    if (stride > 1) b += 6.0 * std::sqrt((double)stride) * std::sqrt((double)n_sub * S) + 129.0 * n_sub;
+    if (stride > 1) b += 6.0 * std::sqrt((double)stride) * std::sqrt((double)n_sub * (S + (double)n_sub * stride)) + (129.0 + 10.0 * stride) * n_sub;
     return (uint64_t)b + 2ull * n_sub + 64;
 }
 
@@ -629,28 +641,33 @@ struct PieceSchedule { uint64_t n_pieces, piece_bytes; const cudaEvent_t* ev; };
 // defer: stop after the level-1 scatter when the plan can be finished slice by slice (RUN_LEVEL1);
 // part_settle or the sliced ok_counter_finish does the rest.
 bool part_sliceable(const PartPlan& pl);
+// tile_begin / tile_end: count the windows ending in tiles [tile_begin, tile_end) only -- a sub-batch of a batch too
+// large for one pass (the walk takes its k-1 base halo from the tile before, so sub-batches lose no window)
 int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec,
-                     const uint8_t* sample_src, const PieceSchedule* pieces, bool defer = false) {
+                     const uint8_t* sample_src, const PieceSchedule* pieces, bool defer = false,
+                     uint64_t tile_begin = 0, uint64_t tile_end = ~0ull) {
     PartPlan& pl = c->pl; pl = PartPlan{};
     const uint64_t windows_before = c->windows;
-    part_choose_bits(c, n_bases, pl, /*use_hint=*/true);
-    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    const uint64_t n_tiles = std::min<uint64_t>(tile_end, (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES);      // first tile NOT counted
+    const uint64_t n_units = std::min<uint64_t>(n_tiles * OK_TILE_BASES, n_bases) - tile_begin * OK_TILE_BASES;   // window ends in range
+    const bool whole = tile_begin == 0 && n_tiles * OK_TILE_BASES >= n_bases;
+    part_choose_bits(c, n_units, pl, /*use_hint=*/true);
     // every `stride`-th tile is sampled; large sub-partitions (sized from a capacity hint) still see > 500 samples each at 1/32
-    pl.stride = n_tiles > 4096 ? (n_bases / pl.n_sub >= 12288 ? 32 : 16) : 1;
+    pl.stride = n_tiles - tile_begin > 4096 ? (n_units / pl.n_sub >= 12288 ? 32 : 16) : 1;
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
-    TRY(part_layout(c, n_bases, OK_TILE_BASES, 0, pl));
+    TRY(part_layout(c, n_units, OK_TILE_BASES, 0, pl));
     CU(cudaEventRecord(c->ev_p[0], c->s_main));
     CU(cudaMemsetAsync(pl.hist, 0, pl.n_sub * sizeof(unsigned), c->s_main));
     {
-        const uint64_t sampled = (n_tiles + pl.stride - 1) / pl.stride;
+        const uint64_t sampled = (n_tiles - tile_begin + pl.stride - 1) / pl.stride;
         const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((sampled + 7) / 8, (uint64_t)grid_sm * 8));
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_sample<true> : k_part_sample<false>;
         LAUNCH(kern, blocks, 256, 0, c->s_main, sample_src, n_bases, d_off, n_rec, n_tiles, (uint64_t)pl.stride, c->k, pl.cfg, pl.hist,
-               /*halo=*/sample_src == d_bases);
+               /*halo=*/sample_src == d_bases, tile_begin);
         CU(cudaEventRecord(c->ev_b, c->s_main));   // the last reader of sample_src (possibly the caller's own buffer, zero-copy)
     }
-    LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.chunk_sum);
-    LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_bases, pl.cfg.b2,
+    LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_units, pl.chunk_sum);
+    LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n_units, pl.cfg.b2,
            pl.chunk_sum, (unsigned)pl.cap_bound, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     {
@@ -663,7 +680,7 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
         const uint64_t max_warps = (uint64_t)grid_sm * (OK_SB_KPT == 16 ? 3 : 2) * OK_SB_WARPS;   // resident warps (72 KB smem per CTA)
         const uint64_t n_launch = pieces ? pieces->n_pieces : 1;
         for (uint64_t p = 0; p < n_launch; ++p) {
-            uint64_t t0 = 0, t1 = n_tiles, visible = n_bases;
+            uint64_t t0 = tile_begin, t1 = n_tiles, visible = n_bases;
             if (pieces) {
                 CU(cudaStreamWaitEvent(c->s_main, pieces->ev[p], 0));
                 t0 = p * (pieces->piece_bytes / OK_TILE_BASES);
@@ -678,7 +695,7 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
         }
     }
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
-    if (defer && part_sliceable(pl)) {
+    if (defer && whole && part_sliceable(pl)) {
         c->run_state = RUN_LEVEL1;
         c->pend_bases = n_bases; c->pend_rec = n_rec; c->pend_windows_before = windows_before;
         return OK_SUCCESS;
@@ -687,7 +704,7 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
     if (part_hint_misled(c, pl)) {
         TRY(part_discard(c, windows_before));
         c->distrust_hint = true;
-        return part_count_bases(c, d_bases, n_bases, d_off, n_rec, d_bases, pieces, false);
+        return part_count_bases(c, d_bases, n_bases, d_off, n_rec, d_bases, pieces, false, tile_begin, tile_end);
     }
     return part_absorb_spills(c, windows_before);
 }
@@ -780,6 +797,7 @@ int run_to_table(ok_counter* c) {
     if (c->h_stats->spill_n) TRY(table_rebuild(c, 2 * c->tv.n_home));   // also re-adds what the one-shot path spilled
     return OK_SUCCESS;
 }
+int acc_to_table(ok_counter* c);
 
 // min_count filter of the run into the d_out arrays
 int run_filter(ok_counter* c, uint64_t min_count, uint64_t* n_out) {
@@ -803,6 +821,117 @@ int run_filter(ok_counter* c, uint64_t min_count, uint64_t* n_out) {
         CU(cudaGetLastError());
     }
     *n_out = total;
+    return OK_SUCCESS;
+}
+
+// ---- more than one large batch: runs are merged, not folded into a table (count.rs:48: ONE table across all files) ----
+int run_unstash(ok_counter* c);
+
+// set the counter's sorted run aside so that the next batch can take the one-shot path on its own
+int run_stash(ok_counter* c) {
+    if (c->n_acc) TRY(run_unstash(c));              // (never in the normal flow: every batch ends with run_unstash)
+    if (c->run_state == RUN_NONE) return OK_SUCCESS;
+    TRY(run_make_dense(c));
+    if (c->n_run) {
+        std::swap(c->d_run_keys, c->d_acc_keys); std::swap(c->cap_run_keys, c->cap_acc_keys);
+        std::swap(c->d_run_counts, c->d_acc_counts); std::swap(c->cap_run_counts, c->cap_acc_counts);
+        c->n_acc = c->n_run;
+    }
+    c->n_run = 0; c->run_state = RUN_NONE; c->occupied = 0;
+    return OK_SUCCESS;
+}
+
+// the set-aside run goes into the device-wide table (the batch that followed it ended there)
+int acc_to_table(ok_counter* c) {
+    const uint64_t n = c->n_acc;
+    c->n_acc = 0;
+    uint64_t done = 0;
+    c->hint = std::max<uint64_t>(c->hint, c->occupied + n + n / 4);
+    while (done < n) {
+        uint64_t allowed = 0;
+        TRY(ensure_headroom(c, n - done, &allowed));
+        const uint64_t m = std::min<uint64_t>(n - done, allowed);
+        LAUNCH(k_add_kmers, grid_for(m), 256, 0, c->s_main, c->tv, c->d_stats, c->spill, c->d_acc_keys + done, c->d_acc_counts + done, m, 0);
+        TRY(read_stats(c));
+        CU(cudaGetLastError());
+        if (c->h_stats->spill_n) {
+            if (c->h_stats->spill_n > c->spill.cap) return set_err(OK_ERR_INTERNAL, "spill list overflow while folding a run");
+            TRY(table_rebuild(c, 2 * c->tv.n_home));
+        }
+        done += m;
+    }
+    return OK_SUCCESS;
+}
+
+// after a batch: merge the set-aside run with the batch's run (merge.cuh); the result is the counter's run again
+int run_unstash(ok_counter* c) {
+    if (c->n_acc == 0) return OK_SUCCESS;
+    if (c->run_state == RUN_NONE) {
+        if (c->occupied || (c->tv.slots && c->h_stats->spill_n)) return acc_to_table(c);     // the batch went to the table
+        // the batch held no countable window: the set-aside run is the result
+        std::swap(c->d_run_keys, c->d_acc_keys); std::swap(c->cap_run_keys, c->cap_acc_keys);
+        std::swap(c->d_run_counts, c->d_acc_counts); std::swap(c->cap_run_counts, c->cap_acc_counts);
+        c->n_run = c->n_acc; c->n_acc = 0; c->occupied = c->n_run; c->run_state = RUN_DENSE;
+        return OK_SUCCESS;
+    }
+    TRY(run_make_dense(c));
+    const uint64_t na = c->n_acc, nb = c->n_run;
+    const uint64_t n_tiles = (na + nb + OK_MG_TILE - 1) / OK_MG_TILE;
+    TRY(dev_reserve(&c->d_split, &c->cap_split, n_tiles + 1));
+    TRY(dev_reserve(&c->d_tiles, &c->cap_tiles, n_tiles + 1));
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    TRY(set_smem(k_merge_count, sizeof(OkMergeSmem)));
+    TRY(set_smem(k_merge_write, sizeof(OkMergeSmem)));
+    CU(cudaEventRecord(c->ev_a, c->s_main));
+    LAUNCH(k_merge_partition, grid_for(n_tiles + 1), 256, 0, c->s_main, c->d_acc_keys, na, c->d_run_keys, nb, n_tiles, c->d_split);
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)grid_sm * 4));
+    LAUNCH(k_merge_count, blocks, OK_MG_THREADS, sizeof(OkMergeSmem), c->s_main, c->d_acc_keys, c->d_run_keys, c->d_split, n_tiles, c->d_tiles);
+    LAUNCH(k_scan_tiles, 1, 1024, 0, c->s_main, c->d_tiles, n_tiles, c->d_tiles + n_tiles);
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, c->d_tiles + n_tiles, 8, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    if (c->cap_mrg_keys < total || c->cap_mrg_counts < total) {       // later batches add ever fewer new k-mers: some headroom saves reallocations
+        TRY(dev_reserve(&c->d_mrg_keys, &c->cap_mrg_keys, total + total / 8));
+        TRY(dev_reserve(&c->d_mrg_counts, &c->cap_mrg_counts, total + total / 8));
+    }
+    LAUNCH(k_merge_write, blocks, OK_MG_THREADS, sizeof(OkMergeSmem), c->s_main, c->d_acc_keys, c->d_acc_counts, c->d_run_keys, c->d_run_counts,
+           c->d_split, n_tiles, c->d_tiles, c->d_mrg_keys, c->d_mrg_counts);
+    CU(cudaEventRecord(c->ev_b, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->ms_merge += ms; ++c->n_merges;
+    std::swap(c->d_run_keys, c->d_mrg_keys); std::swap(c->cap_run_keys, c->cap_mrg_keys);
+    std::swap(c->d_run_counts, c->d_mrg_counts); std::swap(c->cap_run_counts, c->cap_mrg_counts);
+    c->n_run = total; c->occupied = total; c->n_acc = 0; c->run_state = RUN_DENSE;
+    return OK_SUCCESS;
+}
+
+// a device-resident batch of any size through the one-shot path, whatever sorted run the counter already holds:
+// cut into sub-batches of <= PART_MAX_UNITS bases, each counted on its own and merged into the run.
+// PART_RETRY: nothing of the batch was counted (the caller goes through the table).
+int part_add_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec) {
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    uint64_t max_units = PART_MAX_UNITS;
+    if (const char* ev = getenv("ORION_MAX_BATCH_BASES")) { const long long v = atoll(ev); if (v >= (1 << 16)) max_units = std::min<uint64_t>((uint64_t)v, PART_MAX_UNITS); }   // test hook: sub-batches on small inputs
+    const uint64_t n_sub = (n_bases + max_units - 1) / max_units;
+    const uint64_t per = (n_tiles + n_sub - 1) / n_sub;
+    for (uint64_t t0 = 0; t0 < n_tiles; t0 += per) {
+        const uint64_t t1 = std::min(n_tiles, t0 + per);
+        TRY(run_stash(c));
+        int r = part_count_bases(c, d_bases, n_bases, d_off, n_rec, d_bases, nullptr, false, t0, t1);
+        if (r == PART_RETRY) {
+            // the one-shot path gave up on this sub-batch (nothing of it is kept): everything so far goes into the
+            // table and the rest of the batch is counted there
+            if (t0 == 0 && c->n_acc == 0) return PART_RETRY;
+            TRY(run_to_table(c));
+            TRY(acc_to_table(c));
+            return counter_process_tiles(c, d_bases, n_bases, d_off, n_rec, t0, n_tiles);
+        }
+        if (r != OK_SUCCESS) return r;
+        TRY(run_unstash(c));
+        if (c->run_state == RUN_NONE && c->occupied && t1 < n_tiles)      // ended up in the table (spills): stay there
+            return counter_process_tiles(c, d_bases, n_bases, d_off, n_rec, t1, n_tiles);
+    }
     return OK_SUCCESS;
 }
 
@@ -1102,6 +1231,7 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
     for (auto st : c->shard.s_peer) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto e : c->shard.ev_chunk) if (e) cudaEventDestroy(e);
     cudaFree(c->d_meta); cudaFreeHost(c->h_part);
+    cudaFree(c->d_acc_keys); cudaFree(c->d_acc_counts); cudaFree(c->d_mrg_keys); cudaFree(c->d_mrg_counts); cudaFree(c->d_split);
     for (auto e : c->ev_p) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_chunks) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -1117,11 +1247,12 @@ OK_EXPORT int ok_counter_clear(ok_counter* c) {
     if (c->run_state == RUN_LEVEL1) { CU(cudaStreamSynchronize(c->s_main)); c->run_state = RUN_NONE; }   // a deferred batch is simply dropped
     if (c->tv.slots && c->occupied && c->run_state == RUN_NONE)
         LAUNCH(k_fill_slots, grid_for(c->tv.n_total, 256, 16), 256, 0, c->s_main, c->tv.slots, c->tv.n_total);
-    c->run_state = RUN_NONE; c->n_run = 0;
+    c->run_state = RUN_NONE; c->n_run = 0; c->n_acc = 0;
     CU(cudaMemsetAsync(c->d_stats, 0, sizeof(OkDevStats), c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
     c->occupied = c->windows = c->bases_seen = c->max_disp = c->spilled_total = 0;
     c->ms_insert = c->ms_readout = c->ms_fill = 0;
+    c->ms_merge = 0; c->n_merges = 0;
     return OK_SUCCESS;
 }
 
@@ -1134,10 +1265,11 @@ OK_EXPORT int ok_counter_add_batch_device(ok_counter* c, const uint8_t* d_bases,
     TRY(part_settle(c));
     c->ms_insert = 0; c->ms_fill = 0;
     if (part_eligible(c, n_bases)) {
-        const int r = part_count_bases(c, d_bases, n_bases, d_rec_offsets, n_records, d_bases, nullptr);
+        const int r = part_add_device(c, d_bases, n_bases, d_rec_offsets, n_records);
         if (r != PART_RETRY) { if (r == OK_SUCCESS) c->bases_seen += n_bases; return r; }
     }
     TRY(run_to_table(c));
+    TRY(acc_to_table(c));
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
     TRY(counter_process_tiles(c, d_bases, n_bases, d_rec_offsets, n_records, 0, n_tiles));
     c->bases_seen += n_bases;
@@ -1170,7 +1302,13 @@ OK_EXPORT int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const ui
         CU(cudaEventRecord(c->ev_chunks[p], c->s_copy));
     }
     CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces], 0));
-    if (part_eligible(c, n_bases)) {
+    if (part_eligible(c, n_bases) && (c->run_state != RUN_NONE || n_bases > PART_MAX_UNITS || getenv("ORION_MAX_BATCH_BASES"))) {
+        // a later batch of a multi-batch job, or one too large for a single pass: land it, then sub-batches + merge
+        CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[n_pieces - 1], 0));
+        const int r = part_add_device(c, c->d_bases, n_bases, c->d_off, n_records);
+        CU(cudaStreamSynchronize(c->s_copy));
+        if (r != PART_RETRY) { if (r == OK_SUCCESS) c->bases_seen += n_bases; return r; }
+    } else if (part_eligible(c, n_bases)) {
         // The level-1 scatter follows the pieces as they land.  The plan needs a sample of the WHOLE
         // batch first: a page-locked caller buffer is sampled in place (zero-copy reads over PCIe,
         // 1/16 of the tiles); a pageable one only after the last piece has landed.
@@ -1192,6 +1330,7 @@ OK_EXPORT int ok_counter_add_batch(ok_counter* c, const uint8_t* bases, const ui
         if (r != PART_RETRY) { if (r == OK_SUCCESS) c->bases_seen += n_bases; return r; }
     }
     TRY(run_to_table(c));
+    TRY(acc_to_table(c));
     const uint64_t tiles_per_piece = COPY_CHUNK / OK_TILE_BASES;
     for (uint64_t p = 0; p < n_pieces; ++p) {
         CU(cudaStreamWaitEvent(c->s_main, c->ev_chunks[p], 0));
@@ -1212,8 +1351,14 @@ OK_EXPORT int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers
     if (!d_kmers) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL d_kmers");
     TRY(part_settle(c));
     c->ms_insert = 0; c->ms_fill = 0;
-    if (part_eligible(c, n)) { const int r = part_count_keys(c, d_kmers, n); if (r != PART_RETRY) return r; }
+    if (part_eligible(c, n) && n < (1ull << 31)) {
+        TRY(run_stash(c));
+        const int r = part_count_keys(c, d_kmers, n);
+        if (r == OK_SUCCESS) return run_unstash(c);
+        if (r != PART_RETRY) return r;
+    }
     TRY(run_to_table(c));
+    TRY(acc_to_table(c));
     uint64_t done = 0;
     while (done < n) {
         uint64_t allowed = 0;
@@ -1364,7 +1509,7 @@ OK_EXPORT int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_ba
         if (counts[r] >= (1ull << 32)) return set_err(OK_ERR_INVALID_ARGUMENT, "more than 2^32 k-mers for one rank in one batch");
         po.p[r] = (unsigned long long*)d_dst[r]; ends[r] = (unsigned)counts[r];
     }
-    if (c->run_state != RUN_NONE) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_route_scatter_device: the counter holds a result; clear it first");
+    TRY(part_settle(c)); TRY(run_stash(c));
     TRY(dev_reserve(&c->d_meta, &c->cap_meta, 64));
     unsigned *d_cur = c->d_meta, *d_end = c->d_meta + 8;
     CU(cudaEventRecord(c->ev_a, c->s_main));
@@ -1459,6 +1604,7 @@ OkPartCfg shard_global_cfg(const ok_counter* c, unsigned bits) {   // bins over 
 // d_hist_fine[n_ranks << sub_bits] += sampled k-mers per (owner, sub-partition); d_hist_l1[n_ranks << l1_bits] = per (owner, level-1 bin)
 OK_EXPORT int ok_shard_sample_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
                                      uint64_t n_records, uint32_t* d_hist_fine, uint32_t* d_hist_l1) {
+    if (c) { TRY(part_settle(c)); TRY(run_stash(c)); }      // an earlier batch's run is set aside and merged after the count
     TRY(shard_check(c, "ok_shard_sample_device", n_bases));
     if (!d_hist_fine || !d_hist_l1) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_sample_device: NULL histogram");
     if (n_bases && ((uintptr_t)d_bases & 15u)) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
@@ -1472,7 +1618,7 @@ OK_EXPORT int ok_shard_sample_device(ok_counter* c, const uint8_t* d_bases, uint
         const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((sampled + 7) / 8, (uint64_t)grid_sm * 8));
         auto kern = c->norm_mode == OK_NORM_NORMALIZED ? k_part_sample<true> : k_part_sample<false>;
         LAUNCH(kern, blocks, 256, 0, c->s_main, d_bases, n_bases, d_rec_offsets, n_records, n_tiles, (uint64_t)sh.stride, c->k,
-               shard_global_cfg(c, sh.sub_bits), d_hist_fine, /*halo=*/true);
+               shard_global_cfg(c, sh.sub_bits), d_hist_fine, /*halo=*/true, (uint64_t)0);
     }
     LAUNCH(k_shard_l1_hist, (unsigned)(c->n_shards << sh.b1), 128, 0, c->s_main, d_hist_fine, sh.b2, d_hist_l1);
     CU(cudaEventRecord(c->ev_b, c->s_main));
@@ -1595,7 +1741,8 @@ OK_EXPORT int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all
                                         "recount the batch: the hint is ignored from now on", (unsigned long long)c->h_part->scal.n_deferred);
     }
     const int r = part_absorb_spills(c, windows_before);
-    return r == PART_RETRY ? set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list") : r;
+    if (r == PART_RETRY) return set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list");
+    return r == OK_SUCCESS ? run_unstash(c) : r;
 }
 
 // ---- multi-GPU exchange, third form: chunked scatter + one copy-engine peer copy per (peer, chunk) ----
@@ -1605,13 +1752,6 @@ OK_EXPORT int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all
 // next chunk's extraction; returns once every copy of this sender has landed) -> [any collective = the barrier]
 // -> ok_xchg_count_device (per chunk: fills from the sub-block headers, level-2 scatter; then the count).
 namespace {
-unsigned host_part_capacity(unsigned sampled, unsigned stride, uint64_t limit) {      // == ok_part_capacity (partition.cuh)
-    const unsigned long long est = (unsigned long long)sampled * stride;
-    unsigned long long cap = est;
-    if (stride > 1) cap += (unsigned long long)(6.0f * sqrtf((float)est * (float)stride)) + 128ull;
-    if (cap > limit) cap = limit;
-    return (unsigned)((cap + 1ull) & ~1ull);
-}
 constexpr unsigned XCHG_STRIDE = 1024;   // entries per chunk row of the d_xchg arrays
 }  // namespace
 
@@ -1627,7 +1767,8 @@ OK_EXPORT int ok_xchg_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* su
     sh.n_chunks = nc;
     // a sub-block carries a header and every region its own 6-sigma slack: n_chunks x senders x bins regions per owner
     const uint64_t regions = (uint64_t)nc << (sh.g + sh.b1);
-    sh.cap_keys += regions * 200 + (uint64_t)(6.0 * std::sqrt((double)sh.stride) * std::sqrt((double)regions * (double)(n_bases_max + n_bases_max / 4)));
+    sh.cap_keys += regions * (200ull + 10ull * sh.stride) +
+                   (uint64_t)(6.0 * std::sqrt((double)sh.stride) * std::sqrt((double)regions * ((double)(n_bases_max + n_bases_max / 4) + (double)regions * sh.stride)));
     if (sh.cap_keys >= (1ull << 32)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_geometry: batch too large for 32-bit offsets");
     if (!sh.d_xchg) CU(cudaMalloc((void**)&sh.d_xchg, (6 * 8 * XCHG_STRIDE + 2 * 8 * 8) * sizeof(unsigned)));
     for (int r = 0; r < c->n_shards; ++r) if (!sh.s_peer[r] && r != c->shard_rank) CU(cudaStreamCreateWithFlags(&sh.s_peer[r], cudaStreamNonBlocking));
@@ -1639,6 +1780,7 @@ OK_EXPORT int ok_xchg_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* su
 // d_hist_fine[n_ranks << sub_bits] (owner, sub-partition); d_hist_l1c[n_chunks][n_ranks << l1_bits] (chunk, owner, level-1 bin)
 OK_EXPORT int ok_xchg_sample_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
                                     uint64_t n_records, uint32_t* d_hist_fine, uint32_t* d_hist_l1c) {
+    if (c) { TRY(part_settle(c)); TRY(run_stash(c)); }      // an earlier batch's run is set aside and merged after the count
     TRY(shard_check(c, "ok_xchg_sample_device", n_bases));
     if (!d_hist_fine || !d_hist_l1c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_sample_device: NULL histogram");
     if (n_bases && ((uintptr_t)d_bases & 15u)) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
@@ -1693,7 +1835,6 @@ OK_EXPORT int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint
     struct Copy { uint64_t src, dst, len; unsigned peer, chunk; };
     std::vector<Copy> copies;
     uint64_t local_run = 0;
-    bool clipped = false;
     for (unsigned o = 0; o < W; ++o) {
         uint64_t run = 0;
         for (unsigned s2 = 0; s2 < W; ++s2)
@@ -1703,9 +1844,8 @@ OK_EXPORT int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint
                 run += hdr_keys;
                 const uint64_t local_base = local_run;                  // only meaningful for s2 == me, o != me
                 for (unsigned b = 0; b < n_bin1; ++b) {
-                    const unsigned cap = host_part_capacity(h[b], sh.stride, limit);
+                    const unsigned cap = ok_part_capacity(h[b], sh.stride, limit);
                     const uint64_t lo = std::min(run, limit), hi = std::min(run + cap, limit);
-                    if (hi - lo < cap) clipped = true;
                     if (s2 == me) {
                         const uint64_t shift = o == me ? 0 : local_base - sub_start;      // remote -> local coordinates (mod 2^64)
                         cur[(size_t)ch * XCHG_STRIDE + o * n_bin1 + b] = (unsigned)(lo + shift);
@@ -1724,7 +1864,7 @@ OK_EXPORT int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint
     }
     if (local_run > sh.cap_send) return set_err(OK_ERR_INTERNAL, "chunked exchange: the send buffer is too small (%llu > %llu keys); count this batch through the two-pass route instead",
                                                 (unsigned long long)local_run, (unsigned long long)sh.cap_send);
-    (void)clipped;    // a clipped region simply spills below and the batch falls back to the exact route
+    // (a region clipped by `limit` simply spills below and the batch falls back to the exact route)
     unsigned* dx = sh.d_xchg;
     unsigned *d_cur = dx, *d_end = dx + 8 * XCHG_STRIDE, *d_beg = dx + 16 * XCHG_STRIDE, *d_rbeg = dx + 24 * XCHG_STRIDE, *d_rend = dx + 32 * XCHG_STRIDE;
     unsigned *d_hs = dx + 48 * XCHG_STRIDE, *d_hr = d_hs + 64;
@@ -1835,7 +1975,8 @@ OK_EXPORT int ok_xchg_count_device(ok_counter* c) {
                                         "recount the batch: the hint is ignored from now on", (unsigned long long)c->h_part->scal.n_deferred);
     }
     const int r = part_absorb_spills(c, windows_before);
-    return r == PART_RETRY ? set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list") : r;
+    if (r == PART_RETRY) return set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list");
+    return r == OK_SUCCESS ? run_unstash(c) : r;
 }
 
 OK_EXPORT int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t** d_kmers,
@@ -1912,6 +2053,21 @@ OK_EXPORT int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** km
     return OK_SUCCESS;
 }
 
+// multi-GPU: the exchange of the batch in progress failed on some rank (a sampled region overflowed, a hint proved
+// too low) and every rank recounts it through another route.  Drops what this rank holds of THAT batch only;
+// the result of earlier batches (set aside while the batch was being counted) stays.
+OK_EXPORT int ok_counter_abort_batch(ok_counter* c) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_abort_batch: NULL handle");
+    c->shard.xchg_pending = false;
+    c->pl.sharded = false;
+    if (c->run_state == RUN_LEVEL1) { CU(cudaStreamSynchronize(c->s_main)); c->run_state = RUN_NONE; }
+    if (c->run_state != RUN_NONE && c->n_acc) { c->run_state = RUN_NONE; c->n_run = 0; c->occupied = 0; }
+    CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    c->h_stats->spill_n = 0;
+    return OK_SUCCESS;
+}
+
 OK_EXPORT int ok_counter_set_capacity_hint(ok_counter* c, uint64_t capacity_hint) {
     if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_set_capacity_hint: NULL handle");
     c->user_hint = capacity_hint; c->distrust_hint = false;
@@ -1935,6 +2091,7 @@ OK_EXPORT int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out) {
     out->ms_sample = c->ms_sample; out->ms_scatter1 = c->ms_scatter1; out->ms_scatter2 = c->ms_scatter2;
     out->ms_count = c->ms_count; out->ms_compact = c->ms_compact; out->partitioned = c->run_state != RUN_NONE ? 1 : 0;
     out->ms_push = c->ms_push; out->n_deferred = c->n_deferred;
+    out->ms_merge = c->ms_merge; out->n_merges = c->n_merges;
     return OK_SUCCESS;
 }
 

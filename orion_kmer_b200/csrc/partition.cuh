@@ -83,14 +83,14 @@ template <bool MAP_U>
 __global__ void __launch_bounds__(256)
 k_part_sample(const uint8_t* __restrict__ bases, uint64_t n_bases, const uint64_t* __restrict__ rec_off,
               uint64_t n_rec, uint64_t n_tiles, uint64_t stride, unsigned k, OkPartCfg cfg,
-              unsigned* __restrict__ hist, bool halo) {
+              unsigned* __restrict__ hist, bool halo, uint64_t tile_begin = 0) {
     // halo = false: a sampled tile stands alone (no read of the tile before it: half the PCIe traffic when
     // the source is the caller's host buffer); the k-1 windows reaching back are not seen, a ~3 % low
     // bias that only the generously padded single-GPU plan tolerates.  Exact counts need the halo.
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
-    for (uint64_t t = warp * stride; t < n_tiles; t += warps * stride)
+    for (uint64_t t = tile_begin + warp * stride; t < n_tiles; t += warps * stride)      // tiles [tile_begin, n_tiles): a sub-batch
         ok_walk_tiles<MAP_U>(bases, n_bases, rec_off, n_rec, t, t + 1, t + 1, k, lane,
             [&](uint64_t, uint64_t pc, uint64_t cc, uint32_t okmask) {
                 ok_lane_windows(pc, cc, okmask, k, [&](int, uint64_t key) {
@@ -133,11 +133,14 @@ __device__ __forceinline__ unsigned ok_block_excl_scan_1024(unsigned v, unsigned
 }
 
 // capacity of a sub-partition from its sampled count: estimate + 6 sigma of the sampling error
-// (+ slack), even so that every region starts 16-byte aligned (TMA bulk loads)
-__device__ __forceinline__ unsigned ok_part_capacity(unsigned sampled, unsigned stride, unsigned n_units) {
+// (+ slack), even so that every region starts 16-byte aligned (TMA bulk loads).  The sigma is taken from
+// sampled + 1 and ten more samples' worth of room is added: a SMALL region whose sample happens to be empty
+// (probability e^-mean: the chunked multi-GPU exchange lays out ~10^5 regions of a few hundred keys in the
+// tests) would otherwise get a capacity below its true size.  Host twin: host_part_capacity (orion_gpu.cu).
+__host__ __device__ __forceinline__ unsigned ok_part_capacity(unsigned sampled, unsigned stride, unsigned long long n_units) {
     const unsigned long long est = (unsigned long long)sampled * stride;
     unsigned long long cap = est;
-    if (stride > 1) cap += (unsigned long long)(6.0f * sqrtf((float)est * (float)stride)) + 128ull;
+    if (stride > 1) cap += (unsigned long long)(6.0f * sqrtf((float)(est + stride) * (float)stride)) + 10ull * stride + 128ull;
     if (cap > n_units) cap = n_units;
     return (unsigned)((cap + 1ull) & ~1ull);
 }

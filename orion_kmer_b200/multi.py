@@ -186,7 +186,7 @@ class ShardedCounter:
         t3 = time.perf_counter()
         if not all_ok:                      # a sampled region overflowed somewhere: every rank recounts through the exact route
             self.fallbacks += 1
-            self.counter.clear()
+            self.counter.abort_batch()
             return self._count_unfused(d_bases, n_bases, d_off, n_reads)
         count_ok = 1
         try:
@@ -197,7 +197,7 @@ class ShardedCounter:
                 print(f"[rank {self.rank}] sharded count failed, recounting: {e}", flush=True)
         if not self._agree(count_ok):       # e.g. a capacity hint that is too low only shows once the shared-memory tables overflow
             self.fallbacks += 1
-            self.counter.clear()
+            self.counter.abort_batch()
             self.counter.set_capacity_hint(0)      # every rank drops the hint: the geometry must stay collective
             self.hinted, self.geom = False, None
             return self._count_unfused(d_bases, n_bases, d_off, n_reads)
@@ -244,7 +244,7 @@ class ShardedCounter:
         t3 = time.perf_counter()
         if not all_ok:          # a sampled region overflowed somewhere: every rank recounts through the exact route
             self.fallbacks += 1
-            self.counter.clear()
+            self.counter.abort_batch()
             return self._count_unfused(d_bases, n_bases, d_off, n_reads)
         count_ok = 1
         try:
@@ -256,7 +256,7 @@ class ShardedCounter:
         # ALWAYS agreed (hint or not): a rank that raised alone would leave the others waiting in the next collective
         if not self._agree(count_ok):
             self.fallbacks += 1
-            self.counter.clear()
+            self.counter.abort_batch()
             self.counter.set_capacity_hint(0)      # every rank drops the hint: the geometry must stay collective
             self.hinted, self.geom = False, None
             return self._count_unfused(d_bases, n_bases, d_off, n_reads)

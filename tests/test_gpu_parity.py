@@ -524,8 +524,79 @@ def test_partitioned_path_matches_oracle(oracle, k):
             c.close()
 
 
+def test_partitioned_two_batches_merge(oracle):
+    """count.rs:48,52-79: ONE table across all input files.  A second (third, ...) large batch is counted on its own
+    by the one-shot path and its sorted run merged into the accumulated one (merge.cuh) -- no fold into the
+    device-wide table.  Host and device entries, several k, min_count filters, a batch that adds nothing new,
+    a batch without a single countable window, and a small batch at the end (that one does go through the table)."""
+    import torch
+    for k in (31, 21, 32, 11):
+        g = synth.genome(61 + k, 800_000)
+        n = 40_000
+        batches = [synth.reads(g, 62, n), synth.reads(g, 63, n), synth.reads(synth.genome(99, 300_000), 64, n)]
+        batches.append(batches[0])                                  # nothing new: every key is a pair in the merge
+        batches.append(np.full(n * 150, ord("N"), np.uint8))        # no countable window at all
+        off = synth.read_offsets(n)
+        c = ok.KmerCounter(k)
+        o = oracle.Counter(k)
+        for i, b in enumerate(batches):
+            if i % 2:
+                d_b, d_o = torch.from_numpy(b).cuda(), torch.from_numpy(off.view(np.int64)).cuda()
+                c.add_batch_device(d_b.data_ptr(), len(b), d_o.data_ptr(), n)
+            else:
+                c.add_batch(b, off)
+            o.add_batch(b, off)
+            st = c.stats()
+            assert st["partitioned"] == 1 and st["n_merges"] == i and st["n_slots"] == 0, (k, i, st)
+            if i in (1, 3, 4):
+                for mc in (1, 2, 5):
+                    gk, gc = c.finish(mc)
+                    wk, wc = o.finish(mc)
+                    assert np.array_equal(gk, wk) and np.array_equal(gc, wc), (k, i, mc)
+        assert c.stats()["n_windows"] == int(o.finish(1)[1].sum())
+        small = synth.reads(g, 65, 500)                             # below the one-shot threshold: run -> table
+        off_s = synth.read_offsets(500)
+        c.add_batch(small, off_s)
+        o.add_batch(small, off_s)
+        assert c.stats()["partitioned"] == 0
+        gk, gc = c.finish(1)
+        wk, wc = o.finish(1)
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc), k
+        c.close(); o.close()
+
+
+def test_large_batch_is_cut_into_sub_batches(oracle, monkeypatch):
+    """batches beyond ~1.8 G bases are cut into sub-batches by tile range (32-bit offsets inside a pass), each counted
+    on its own and merged.  ORION_MAX_BATCH_BASES shrinks the limit so that the oracle can check it: reads, and one
+    long multi-megabase record whose windows straddle every cut (the walk takes its halo from the tile before)."""
+    import torch
+    monkeypatch.setenv("ORION_MAX_BATCH_BASES", "700000")
+    k = 31
+    g = synth.genome(66, 3_000_000)
+    g[1_000_000:1_000_100] = ord("N")
+    n = 30_000
+    reads, off = synth.reads(g, 67, n), synth.read_offsets(n)
+    cases = [(reads, off), (g, np.array([0, len(g)], np.uint64)),
+             (np.concatenate([g[:1_500_000], reads]), np.concatenate([[0], 1_500_000 + off]).astype(np.uint64))]
+    for i, (b, o) in enumerate(cases):
+        wk, wc = oracle.count_batch(k, b, o)
+        for host in (True, False):
+            c = ok.KmerCounter(k, capacity_hint=0 if i else 1_000_000)
+            if host:
+                c.add_batch(b, o)
+            else:
+                d_b, d_o = torch.from_numpy(b).cuda(), torch.from_numpy(o.view(np.int64)).cuda()
+                c.add_batch_device(d_b.data_ptr(), len(b), d_o.data_ptr(), len(o) - 1)
+            st = c.stats()
+            gk, gc = c.finish(1)
+            c.close()
+            assert st["partitioned"] == 1 and st["n_merges"] >= 4, st
+            assert np.array_equal(gk, wk) and np.array_equal(gc, wc), (i, host)
+
+
 def test_partitioned_run_then_more_batches(oracle):
-    """a second batch folds the sorted run into the table; results stay exact"""
+    """a second batch on the forced one-shot path is merged into the run; a later batch through the table path
+    (set_path(1)) folds the run into the table; results stay exact"""
     g = synth.genome(61, 800_000)
     n = 40_000
     b1, b2 = synth.reads(g, 62, n), synth.reads(g, 63, n)
@@ -534,7 +605,10 @@ def test_partitioned_run_then_more_batches(oracle):
     c.set_path(2)
     c.add_batch(b1, off)
     assert c.stats()["partitioned"] == 1
-    c.add_batch(b2, off)
+    c.add_batch(b2[:n * 75], off[:n // 2 + 1])
+    assert c.stats()["partitioned"] == 1 and c.stats()["n_merges"] == 1
+    c.set_path(1)
+    c.add_batch(b2[n * 75:], off[:n // 2 + 1])
     assert c.stats()["partitioned"] == 0
     o = oracle.Counter(31)
     o.add_batch(b1, off)
@@ -543,6 +617,7 @@ def test_partitioned_run_then_more_batches(oracle):
         gk, gc = c.finish(mc)
         wk, wc = o.finish(mc)
         assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+    c.set_path(2)
     c.clear()
     c.add_batch(b2, off)
     gk, gc = c.finish()
@@ -842,6 +917,24 @@ def test_chunked_exchange_matches_oracle(oracle, monkeypatch, n_ranks, hint, chu
         gk, gc, used = _xchg_dance(counters, batches, n)
         assert used == chunks
         assert np.array_equal(gk, wk) and np.array_equal(gc, wc), rep
+    for c in counters:
+        c.close()
+
+
+def test_chunked_exchange_second_batch_merges_into_the_shards(oracle):
+    """config 3 at 2 / 4 GPUs is several batches per rank: the second sharded batch is merged into every rank's shard"""
+    k, n_ranks, n = 31, 4, 12_000
+    g = synth.genome(87, 400_000)
+    rounds = [[(synth.reads(g, 88 + i, n, first_read=r * n), synth.read_offsets(n)) for r in range(n_ranks)] for i in range(3)]
+    counters = [ok.KmerCounter(k) for _ in range(n_ranks)]
+    for r, c in enumerate(counters):
+        c.set_shard(r, n_ranks)
+    for i, batches in enumerate(rounds):
+        gk, gc, _ = _xchg_dance(counters, batches, n)
+        assert all(c.stats()["n_merges"] == i for c in counters)
+        all_bases = np.concatenate([b for rd in rounds[:i + 1] for b, _ in rd])
+        wk, wc = oracle.count_batch(k, all_bases, synth.read_offsets(n * n_ranks * (i + 1)))
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc), i
     for c in counters:
         c.close()
 
