@@ -221,8 +221,23 @@ int ok_counter_get_stats(ok_counter* c, ok_counter_stats* out);
 int ok_set_create(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_set** out);
 int ok_set_add_batch(ok_set* s, const uint8_t* bases, const uint64_t* rec_offsets,
                      uint64_t n_records);                  /* DashSet::insert build.rs:55 */
+/* same, batch already resident in device memory */
+int ok_set_add_batch_device(ok_set* s, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                            uint64_t n_records);
 /* a set from an existing sorted, duplicate-free host array (a reference loaded from a .db) */
 int ok_set_from_sorted(uint8_t k, const uint64_t* kmers, uint64_t n, ok_set** out);
+/* ... or device array (checked on the device; a key-range slice received from a peer in multi-GPU set algebra) */
+int ok_set_from_sorted_device(uint8_t k, const uint64_t* d_kmers, uint64_t n, ok_set** out);
+/* the sealed set's sorted keys in device memory, valid until the set is destroyed */
+int ok_set_keys_device(ok_set* s, const uint64_t** d_kmers, uint64_t* n);
+/* keys[first .. first + n) of the sealed set into a caller's device buffer (the send buffer of the key exchange) */
+int ok_set_copy_keys_device(ok_set* s, uint64_t first, uint64_t n, uint64_t* d_out);
+/* multi-GPU set algebra (compare.rs:51-66, query.rs:77-109, classify.rs:224-277 over key-range shards): where
+ * the key ranges of n_ranks owners begin inside this sorted set -- the ownership rule of the sharded count (equal
+ * shares of the canonical k-mer position, monotone in the key).  bounds[n_ranks + 1]; rank r owns
+ * keys[bounds[r] .. bounds[r+1]).  Intersection sizes, hit counts and (matched, depth) sums over the shards add up
+ * to the whole: one all-reduce(sum) of integers completes them. */
+int ok_set_shard_bounds(ok_set* s, int n_ranks, uint64_t* bounds);
 int ok_set_size(ok_set* s, uint64_t* n);                   /* HashSet::len                */
 int ok_set_k(ok_set* s, uint8_t* k);
 /* sorted ascending copy on the host (build_tests.rs compares decoded set contents) */
@@ -247,6 +262,9 @@ int ok_sets_all_vs_all_part(ok_set* const* sets, uint64_t n, uint64_t part, uint
 /* hits_per_read[r] = number of windows of read r whose canonical k-mer is in the set */
 int ok_probe_reads(ok_set* s, int norm_mode, const uint8_t* bases, const uint64_t* rec_offsets,
                    uint64_t n_records, uint32_t* hits_per_read);
+/* same, reads and result resident in device memory */
+int ok_probe_reads_device(ok_set* s, int norm_mode, const uint8_t* d_bases, uint64_t n_bases,
+                          const uint64_t* d_rec_offsets, uint64_t n_records, uint32_t* d_hits_per_read);
 /* matched = |{i : kmers[i] in ref}| , depth_sum = sum of counts[i] over those */
 int ok_probe_counts(ok_set* ref, const uint64_t* kmers, const uint64_t* counts, uint64_t n,
                     uint64_t* matched, uint64_t* depth_sum);

@@ -110,7 +110,13 @@ ABI = {
     "ok_counter_get_stats": (C.c_int, [vp, C.POINTER(CounterStats)]),
     "ok_set_create": (C.c_int, [C.c_uint8, C.c_int, C.c_uint64, C.POINTER(vp)]),
     "ok_set_add_batch": (C.c_int, [vp, vp, vp, C.c_uint64]),
+    "ok_set_add_batch_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64]),
     "ok_set_from_sorted": (C.c_int, [C.c_uint8, vp, C.c_uint64, C.POINTER(vp)]),
+    "ok_set_from_sorted_device": (C.c_int, [C.c_uint8, vp, C.c_uint64, C.POINTER(vp)]),
+    "ok_set_keys_device": (C.c_int, [vp, C.POINTER(vp), u64p]),
+    "ok_set_shard_bounds": (C.c_int, [vp, C.c_int, vp]),
+    "ok_set_copy_keys_device": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp]),
+    "ok_probe_reads_device": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, C.c_uint64, vp]),
     "ok_set_size": (C.c_int, [vp, u64p]),
     "ok_set_k": (C.c_int, [vp, u8p]),
     "ok_set_export": (C.c_int, [vp, C.POINTER(u64p), u64p]),
@@ -588,10 +594,37 @@ class KmerSet:
         _check(lib().ok_set_from_sorted(k, _ptr(kmers), len(kmers), C.byref(h)))
         return cls(h, k)
 
+    @classmethod
+    def from_sorted_device(cls, k, d_kmers_ptr, n):
+        h = vp()
+        _check(lib().ok_set_from_sorted_device(k, d_kmers_ptr, n, C.byref(h)))
+        return cls(h, k)
+
     def add_batch(self, bases, offsets):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         _check(lib().ok_set_add_batch(self._h, _ptr(bases), _ptr(offsets), len(offsets) - 1))
+
+    def add_batch_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records):
+        _check(lib().ok_set_add_batch_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records))
+
+    def keys_device(self):
+        """-> (device pointer, n): the sorted keys, valid while the set lives"""
+        p, n = vp(), C.c_uint64()
+        _check(lib().ok_set_keys_device(self._h, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def copy_keys_device(self, first, n, d_out_ptr):
+        _check(lib().ok_set_copy_keys_device(self._h, first, n, d_out_ptr))
+
+    def shard_bounds(self, n_ranks):
+        """multi-GPU: index where each owner's key range begins (n_ranks + 1 entries)"""
+        b = np.zeros(n_ranks + 1, dtype=np.uint64)
+        _check(lib().ok_set_shard_bounds(self._h, n_ranks, _ptr(b)))
+        return b
+
+    def probe_reads_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hits_ptr, norm_mode=RAW):
+        _check(lib().ok_probe_reads_device(self._h, norm_mode, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hits_ptr))
 
     def __len__(self):
         n = C.c_uint64()

@@ -2143,6 +2143,10 @@ struct ok_set {
     unsigned long long* d_table = nullptr;    // hashed membership table, built on first probe
     uint64_t n_table = 0;
     cudaStream_t st = nullptr;
+    // staging of ok_probe_reads, kept across calls (three cudaMalloc / cudaFree per call cost more than a small probe)
+    uint8_t* d_pb = nullptr; uint64_t cap_pb = 0;
+    uint64_t* d_po = nullptr; uint64_t cap_po = 0;
+    unsigned* d_ph = nullptr; uint64_t cap_ph = 0;
 };
 
 namespace {
@@ -2209,6 +2213,12 @@ OK_EXPORT int ok_set_add_batch(ok_set* s, const uint8_t* bases, const uint64_t* 
     return ok_counter_add_batch(s->builder, bases, rec_offsets, n_records);
 }
 
+OK_EXPORT int ok_set_add_batch_device(ok_set* s, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets, uint64_t n_records) {
+    if (!s) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_add_batch_device: NULL handle");
+    if (s->sealed || !s->builder) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_add_batch_device: the set is already sealed");
+    return ok_counter_add_batch_device(s->builder, d_bases, n_bases, d_rec_offsets, n_records);
+}
+
 OK_EXPORT int ok_set_from_sorted(uint8_t k, const uint64_t* kmers, uint64_t n, ok_set** out) {
     if (!out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_from_sorted: out is NULL");
     *out = nullptr;
@@ -2226,6 +2236,66 @@ OK_EXPORT int ok_set_from_sorted(uint8_t k, const uint64_t* kmers, uint64_t n, o
     if (e == cudaSuccess && n) e = cudaStreamSynchronize(s->st);     // pageable source: the DMA has landed before anyone reads the set
     if (e != cudaSuccess) { ok_set_destroy(s); return set_err(OK_ERR_CUDA, "CUDA error %s in ok_set_from_sorted", cudaGetErrorName(e)); }
     *out = s;
+    return OK_SUCCESS;
+}
+
+// a set from a sorted, duplicate-free DEVICE array (a key-range slice received from a peer, multi-GPU set algebra)
+OK_EXPORT int ok_set_from_sorted_device(uint8_t k, const uint64_t* d_kmers, uint64_t n, ok_set** out) {
+    if (!out) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_from_sorted_device: out is NULL");
+    *out = nullptr;
+    if (k == 0 || k > 32) return invalid_k(k);
+    if (n && !d_kmers) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL d_kmers");
+    TRY(ensure_init());
+    ok_set* s = new ok_set();
+    s->k = k; s->n = n; s->sealed = true;
+    unsigned* d_bad = nullptr; unsigned bad = 0; unsigned long long last = 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, 4, s->st);
+    if (e == cudaSuccess && n) e = cudaMalloc((void**)&s->d_keys, n * 8);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(s->d_keys, d_kmers, n * 8, cudaMemcpyDeviceToDevice, s->st);
+    if (e == cudaSuccess && n > 1) LAUNCH(k_check_ascending, grid_for(n), 256, 0, s->st, s->d_keys, n, d_bad);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(&last, s->d_keys + n - 1, 8, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) { ok_set_destroy(s); return set_err(OK_ERR_CUDA, "CUDA error %s in ok_set_from_sorted_device", cudaGetErrorName(e)); }
+    if (bad) { ok_set_destroy(s); return set_err(OK_ERR_INVALID_ARGUMENT, "kmers must be strictly ascending"); }
+    s->has_max = (n && last == OK_EMPTY_KEY) ? 1 : 0;
+    *out = s;
+    return OK_SUCCESS;
+}
+
+// the sealed set's sorted keys in device memory (valid until the set is destroyed)
+OK_EXPORT int ok_set_keys_device(ok_set* s, const uint64_t** d_kmers, uint64_t* n) {
+    if (!s || !d_kmers || !n) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_keys_device: NULL argument");
+    TRY(set_seal(s));
+    *d_kmers = (const uint64_t*)s->d_keys; *n = s->n;
+    return OK_SUCCESS;
+}
+
+OK_EXPORT int ok_set_copy_keys_device(ok_set* s, uint64_t first, uint64_t n, uint64_t* d_out) {
+    if (!s || (n && !d_out)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_copy_keys_device: NULL argument");
+    TRY(set_seal(s));
+    if (first > s->n || n > s->n - first) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_copy_keys_device: range outside the set");
+    if (n) { CU(cudaMemcpyAsync(d_out, s->d_keys + first, n * 8, cudaMemcpyDeviceToDevice, s->st)); CU(cudaStreamSynchronize(s->st)); }
+    return OK_SUCCESS;
+}
+
+// multi-GPU set algebra: where the key ranges of n_ranks owners begin inside this set (the same ownership rule as
+// the sharded count: equal shares of the canonical k-mer position).  bounds[r] .. bounds[r+1] = the keys rank r owns.
+OK_EXPORT int ok_set_shard_bounds(ok_set* s, int n_ranks, uint64_t* bounds) {
+    if (!s || !bounds) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_shard_bounds: NULL argument");
+    if (n_ranks < 1 || n_ranks > 1024) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_shard_bounds: n_ranks out of range");
+    TRY(set_seal(s));
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc((void**)&d, (n_ranks + 1) * 8));
+    LAUNCH(k_set_shard_bounds, 1, 1024, 0, s->st, s->d_keys, s->n - (s->has_max ? 1 : 0), 64u - 2u * s->k, (unsigned)n_ranks, d);
+    cudaError_t e = cudaMemcpyAsync(bounds, d, (n_ranks + 1) * 8, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_err(OK_ERR_CUDA, "CUDA error %s in ok_set_shard_bounds", cudaGetErrorName(e));
+    bounds[n_ranks] = s->n;          // a foreign u64::MAX key (k = 32) belongs to the last owner
     return OK_SUCCESS;
 }
 
@@ -2300,7 +2370,7 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
 OK_EXPORT int ok_set_destroy(ok_set* s) {
     if (!s) return OK_SUCCESS;
     if (s->builder) give_builder(s->builder);
-    cudaFree(s->d_keys); cudaFree(s->d_table);
+    cudaFree(s->d_keys); cudaFree(s->d_table); cudaFree(s->d_pb); cudaFree(s->d_po); cudaFree(s->d_ph);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return OK_SUCCESS;
@@ -2357,26 +2427,61 @@ OK_EXPORT int ok_sets_all_vs_all_part(ok_set* const* sets, uint64_t n, uint64_t 
         TRY(set_seal(sets[i]));
         sizes[i] = sets[i]->n;
     }
-    unsigned long long* d = nullptr;
-    uint64_t n_lo = 2;
-    for (uint64_t i = 0; i < n; ++i) n_lo = std::max<uint64_t>(n_lo, sets[i]->n / OK_IS_TILE + 2);
-    CU(cudaMalloc((void**)&d, (n * n + n_lo) * 8));
-    unsigned long long* d_lo = d + n * n;                 // tile bounds of the pair in flight (the pairs run in stream order)
+    // Row by row: set i against every later set of this part in TWO launches (k_intersect_row_*), set i resident in
+    // L2 for the whole row.  (Per pair -- two launches each, 65,280 for 256 sets -- it took 2.0 s at 256 x 5 M keys.)
+    static const bool pairwise = getenv("ORION_AVA_PAIRWISE") != nullptr;      // A/B knob: the per-pair launches
     cudaStream_t st = sets[0]->st;
-    CU(cudaMemsetAsync(d, 0, n * n * 8, st));
+    unsigned long long *d = nullptr, *d_lo = nullptr;
+    const unsigned long long** d_ptrs = nullptr; unsigned long long* d_ns = nullptr; unsigned* d_cols = nullptr;
+    auto release = [&] { cudaFree(d); cudaFree(d_lo); cudaFree((void*)d_ptrs); cudaFree(d_ns); cudaFree(d_cols); };
+#define CUR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return set_err(e_ == cudaErrorMemoryAllocation ? OK_ERR_OUT_OF_MEMORY : OK_ERR_CUDA, "CUDA error %s in ok_sets_all_vs_all", cudaGetErrorName(e_)); } } while (0)
+    uint64_t max_tiles = 1;
+    for (uint64_t i = 0; i < n; ++i) max_tiles = std::max<uint64_t>(max_tiles, (sets[i]->n + OK_IS_TILE - 1) / OK_IS_TILE);
+    CUR(cudaMalloc((void**)&d, n * n * 8));
+    CUR(cudaMalloc((void**)&d_lo, (max_tiles + 1) * n * 8));
+    CUR(cudaMalloc((void**)&d_ptrs, n * sizeof(void*)));
+    CUR(cudaMalloc((void**)&d_ns, n * 8));
+    std::vector<const unsigned long long*> h_ptrs(n);
+    std::vector<unsigned long long> h_ns(n);
+    for (uint64_t i = 0; i < n; ++i) { h_ptrs[i] = sets[i]->d_keys; h_ns[i] = sets[i]->n; }
+    CUR(cudaMemcpyAsync((void*)d_ptrs, h_ptrs.data(), n * sizeof(void*), cudaMemcpyHostToDevice, st));
+    CUR(cudaMemcpyAsync(d_ns, h_ns.data(), n * 8, cudaMemcpyHostToDevice, st));
+    CUR(cudaMemsetAsync(d, 0, n * n * 8, st));
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    // the columns of every row of this part, uploaded once
+    std::vector<unsigned> cols; std::vector<uint64_t> row_first(n + 1, 0);
     uint64_t p = 0;
-    for (uint64_t i = 0; i < n; ++i)
+    for (uint64_t i = 0; i < n; ++i) {
+        row_first[i] = cols.size();
         for (uint64_t j = i + 1; j < n; ++j, ++p) {
             if (p % n_parts != part) continue;
-            ok_set *a = sets[i], *b = sets[j];
-            if (a->n > b->n) std::swap(a, b);
-            if (a->n == 0) continue;
-            launch_intersection(a, b, d_lo, d + i * n + j, st);
+            if (sets[i]->n == 0 || sets[j]->n == 0) continue;
+            if (pairwise) {
+                ok_set *a = sets[i], *b = sets[j];
+                if (a->n > b->n) std::swap(a, b);
+                launch_intersection(a, b, d_lo, d + i * n + j, st);
+            } else {
+                cols.push_back((unsigned)j);
+            }
         }
-    CU(cudaMemcpyAsync(inter, d, n * n * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
-    cudaFree(d);
+    }
+    row_first[n] = cols.size();
+    CUR(cudaMalloc((void**)&d_cols, std::max<size_t>(cols.size(), 1) * sizeof(unsigned)));
+    if (!cols.empty()) CUR(cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    for (uint64_t i = 0; i < n; ++i) {
+        const unsigned n_cols = (unsigned)(row_first[i + 1] - row_first[i]);
+        if (!n_cols) continue;
+        const OkRowSets rs{d_ptrs, d_ns, d_cols + row_first[i]};
+        const uint64_t n_tiles = (sets[i]->n + OK_IS_TILE - 1) / OK_IS_TILE;
+        LAUNCH(k_intersect_row_bounds, grid_for((n_tiles + 1) * n_cols), 256, 0, st, sets[i]->d_keys, sets[i]->n, rs, n_cols, d_lo);
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles * n_cols, (uint64_t)grid_sm * 8));
+        LAUNCH(k_intersect_row_tiled, blocks, 256, 0, st, sets[i]->d_keys, sets[i]->n, rs, n_cols, d_lo, d + i * n, (uint64_t)1);
+    }
+    CUR(cudaMemcpyAsync(inter, d, n * n * 8, cudaMemcpyDeviceToHost, st));
+    CUR(cudaStreamSynchronize(st));
+    CUR(cudaGetLastError());
+#undef CUR
+    release();
     return OK_SUCCESS;
 }
 
@@ -2400,10 +2505,10 @@ OK_EXPORT int ok_probe_reads(ok_set* s, int norm_mode, const uint8_t* bases, con
     const uint64_t n_bases = rec_offsets[n_records];
     memset(hits_per_read, 0, n_records * sizeof(uint32_t));
     if (n_bases == 0) return OK_SUCCESS;
-    uint8_t* d_b = nullptr; uint64_t* d_o = nullptr; unsigned* d_h = nullptr;
-    CU(cudaMalloc((void**)&d_b, n_bases + 64));
-    CU(cudaMalloc((void**)&d_o, (n_records + 1) * 8));
-    CU(cudaMalloc((void**)&d_h, n_records * 4));
+    TRY(dev_reserve(&s->d_pb, &s->cap_pb, n_bases + 64));
+    TRY(dev_reserve(&s->d_po, &s->cap_po, n_records + 1));
+    TRY(dev_reserve(&s->d_ph, &s->cap_ph, n_records));
+    uint8_t* d_b = s->d_pb; uint64_t* d_o = s->d_po; unsigned* d_h = s->d_ph;
     CU(cudaMemcpyAsync(d_b, bases, n_bases, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(d_o, rec_offsets, (n_records + 1) * 8, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemsetAsync(d_h, 0, n_records * 4, s->st));
@@ -2415,7 +2520,26 @@ OK_EXPORT int ok_probe_reads(ok_set* s, int norm_mode, const uint8_t* bases, con
     CU(cudaMemcpyAsync(hits_per_read, d_h, n_records * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
     CU(cudaGetLastError());
-    cudaFree(d_b); cudaFree(d_o); cudaFree(d_h);
+    return OK_SUCCESS;
+}
+
+// the same probe with the reads and the result resident in device memory (bench `value` leg, multi-GPU probes)
+OK_EXPORT int ok_probe_reads_device(ok_set* s, int norm_mode, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                                    uint64_t n_records, uint32_t* d_hits_per_read) {
+    if (!s || (n_records && (!d_rec_offsets || !d_hits_per_read))) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_probe_reads_device: NULL argument");
+    if (n_records == 0) return OK_SUCCESS;
+    if (n_bases && ((uintptr_t)d_bases & 15u)) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
+    TRY(set_table(s));
+    CU(cudaMemsetAsync(d_hits_per_read, 0, n_records * 4, s->st));
+    if (n_bases) {
+        SinkProbeReads sink{};
+        sink.t = OkKeyTableView{s->d_table, s->n_table, s->has_max};
+        sink.rec_off = d_rec_offsets; sink.n_rec = n_records; sink.hits = d_hits_per_read;
+        const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+        launch_extract(nullptr, d_bases, n_bases, d_rec_offsets, n_records, 0, n_tiles, s->st, sink, norm_mode, s->k);
+    }
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaGetLastError());
     return OK_SUCCESS;
 }
 

@@ -332,6 +332,107 @@ def all_vs_all(ok, torch, dist, sets, device=None):
     return sizes, ok.finish_all_vs_all(sizes, m.cpu().numpy().view(np.uint64))
 
 
+# ------------------------------------------------------------------ multi-GPU set algebra --
+# build (e-2): genome i is built on rank i % world -- independent units, no exchange (build.rs:93-116).
+# compare / query / classify (e-3, e-4): every set is cut at the SAME owner boundaries (key ranges of the canonical
+# k-mer position, the rule of the sharded count) and slice r of every set travels to rank r in one all-to-all.
+# A key lives in exactly one shard, so |A n B|, per-read hits and (matched, depth) are plain sums over the ranks:
+# one all-reduce(sum) of integers completes each of them (compare.rs:51-66, query.rs:77-109, classify.rs:224-277).
+
+def build_sets(ok, dist, k, genomes, make_batch):
+    """genome-per-GPU build: -> {global index: KmerSet} of the genomes this rank owns.  make_batch(i) -> (bases, offsets)
+    of genome i (host arrays, already normalised)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = {}
+    for i in range(rank, genomes, world):
+        bases, off = make_batch(i)
+        s = ok.KmerSet.build(k)
+        s.add_batch(bases, off)
+        len(s)                                   # seals the set (its builder goes back to the pool)
+        mine[i] = s
+    return mine
+
+
+def reshard_sets(ok, torch, dist, k, mine, n_sets):
+    """mine: {global index: KmerSet} whole sets held by this rank (every index on exactly one rank).
+    -> (shards, sizes): n_sets KmerSets holding THIS rank's key range of every set (global index order), and the
+    full sizes of all sets (np.uint64[n_sets]).  One all-to-all of the keys is the only exchange."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    coll = Coll(dist, torch)
+    dev = "cuda" if coll.native else "cpu"
+    idx = sorted(mine)
+    owners = [None] * world
+    dist.all_gather_object(owners, idx)
+    owner_of = {i: q for q, lst in enumerate(owners) for i in lst}
+    assert sorted(owner_of) == list(range(n_sets)), "every set must live on exactly one rank"
+    part = np.zeros((n_sets, world), dtype=np.int64)          # part[i][r] = keys of set i owned by rank r
+    bounds = {}
+    for i in idx:
+        bnd = mine[i].shard_bounds(world).astype(np.int64)
+        bounds[i] = bnd
+        part[i] = bnd[1:] - bnd[:-1]
+    t = torch.from_numpy(part).to(dev)
+    coll.all_reduce(t)
+    part = t.cpu().numpy()
+    # send buffer: for every destination rank, its slice of each of my sets (ascending set index)
+    send_counts = [int(sum(part[i][r] for i in idx)) for r in range(world)]
+    send = torch.empty(max(1, sum(send_counts)), dtype=torch.int64, device="cuda")
+    at = 0
+    for r in range(world):
+        for i in idx:
+            n = int(part[i][r])
+            if n:
+                mine[i].copy_keys_device(int(bounds[i][r]), n, send.data_ptr() + 8 * at)
+            at += n
+    recv, recv_counts = exchange(dist, torch, send, send_counts)
+    seg = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)      # where source rank q's keys start
+    shards, used = [], [0] * world
+    for i in range(n_sets):
+        q, n = owner_of[i], int(part[i][rank])
+        shards.append(ok.KmerSet.from_sorted_device(k, recv.data_ptr() + 8 * int(seg[q] + used[q]), n))
+        used[q] += n
+    assert all(used[q] == recv_counts[q] for q in range(world))
+    return shards, part.sum(axis=1).astype(np.uint64)
+
+
+def all_vs_all_sharded(ok, torch, dist, k, mine, n_sets):
+    """compare.rs:51-60 for every pair of n_sets sets spread over the ranks: identical key-range sharding of every
+    set, every rank computes the whole n x n matrix over ITS key range, one all-reduce(sum) adds the ranges up.
+    -> (sizes, full symmetric intersection matrix), on every rank."""
+    coll = Coll(dist, torch)
+    shards, sizes = reshard_sets(ok, torch, dist, k, mine, n_sets)
+    _, upper = ok.all_vs_all_part(shards, 0, 1)
+    m = torch.from_numpy(upper.view(np.int64).copy()).to("cuda" if coll.native else "cpu")
+    coll.all_reduce(m)
+    for s in shards:
+        s.close()
+    return sizes, ok.finish_all_vs_all(sizes, m.cpu().numpy().view(np.uint64))
+
+
+def query_sharded(ok, torch, dist, shard_union, bases, off, norm_mode=1):
+    """query.rs:77-109 with the database sharded by key range and the reads replicated: every rank counts the windows
+    whose k-mer lies in ITS shard, one all-reduce(sum) of the per-read hits completes them."""
+    coll = Coll(dist, torch)
+    hits = shard_union.probe_reads(bases, off, norm_mode).astype(np.int64)
+    t = torch.from_numpy(hits).to("cuda" if coll.native else "cpu")
+    coll.all_reduce(t)
+    return t.cpu().numpy().astype(np.uint32)
+
+
+def classify_sharded(ok, torch, dist, shards, kmers, counts):
+    """classify.rs:224-277 numerators and denominators with every reference sharded by key range: matched / depth per
+    reference and |R| are sums over the ranks (the input count map is replicated).
+    -> (matched[n_refs], depth[n_refs], ref_sizes[n_refs]) on every rank."""
+    coll = Coll(dist, torch)
+    m, d = ok.probe_counts_many(shards, kmers, counts)
+    sizes = np.array([len(s) for s in shards], dtype=np.int64)
+    t = torch.from_numpy(np.concatenate([m.astype(np.int64), d.astype(np.int64), sizes])).to("cuda" if coll.native else "cpu")
+    coll.all_reduce(t)
+    out = t.cpu().numpy().astype(np.uint64)
+    n = len(shards)
+    return out[:n], out[n:2 * n], out[2 * n:]
+
+
 def verify_sharded_table(ok, dist, sc, K, bases, off, n_windows, slice_checker=None):
     """Parity of the sharded result, every rank: keys strictly ascending, rank boundaries in order (so the ranks'
     outputs concatenate to the sorted global table), sum of counts == windows received; and -- slice_checker given --

@@ -426,6 +426,52 @@ def test_pooled_set_builder_reused_for_another_k(oracle):
             s.close(); t.close()
 
 
+def test_key_range_shards_add_up_to_the_whole(oracle):
+    """multi-GPU set algebra on one GPU: every set cut at the same owner boundaries (ok_set_shard_bounds); intersection
+    sizes, per-read hits and (matched, depth) summed over the shards equal the unsharded results and the oracle's."""
+    k = 21
+    base = synth.genome(41, 400_000)
+    gens = [base, synth.mutate(base, 1, 30_000), synth.genome(42, 250_000), base[:5000], synth.mutate(base, 2, 200_000)]
+    sets = [ok.KmerSet.from_fastx(k, synth.fasta_text(b"g%d" % i, g)) for i, g in enumerate(gens)]
+    osets = [oracle.kmer_set_batch(k, g, np.array([0, len(g)], np.uint64)) for g in gens]
+    sizes, inter = ok.all_vs_all(sets)
+    n_reads = 5000
+    reads = np.concatenate([synth.reads(base, 43, n_reads), synth.reads(gens[2], 44, n_reads)])
+    off = synth.read_offsets(2 * n_reads)
+    union = ok.KmerSet.union(sets)
+    hits = union.probe_reads(reads, off, ok.RAW)
+    assert np.array_equal(hits.astype(np.uint64), oracle.query_hits(oracle.set_union(osets), k, reads, off, 8))
+    pk, pc = oracle.count_batch(k, reads, off)
+    m_all, d_all = ok.probe_counts_many(sets, pk, pc)
+    for world in (2, 8):
+        owners = np.zeros(len(osets[0]), np.int32)
+        ok._check(ok.lib().okx_owner_of(ok._ptr(osets[0]), len(osets[0]), k, world, ok._ptr(owners)))
+        acc_inter, acc_hits = np.zeros_like(inter), np.zeros(len(hits), np.uint64)
+        acc_m, acc_d = np.zeros(len(sets), np.uint64), np.zeros(len(sets), np.uint64)
+        for r in range(world):
+            shards = []
+            for s, o in zip(sets, osets):
+                b = s.shard_bounds(world)
+                assert b[0] == 0 and b[-1] == len(o) and np.all(b[1:] >= b[:-1])
+                ptr, n = s.keys_device()
+                shards.append(ok.KmerSet.from_sorted_device(k, ptr + 8 * int(b[r]), int(b[r + 1] - b[r])))
+            assert np.array_equal(shards[0].to_array(), osets[0][owners == r])      # the ownership rule of the sharded count
+            sz, up = ok.all_vs_all_part(shards, 0, 1)
+            acc_inter += ok.finish_all_vs_all(sz, up)
+            su = ok.KmerSet.union(shards)
+            acc_hits += su.probe_reads(reads, off, ok.RAW)
+            m, d = ok.probe_counts_many(shards, pk, pc)
+            acc_m += m; acc_d += d
+            for sh in shards + [su]:
+                sh.close()
+        assert np.array_equal(acc_inter, inter) and np.array_equal(acc_hits, hits.astype(np.uint64))
+        assert np.array_equal(acc_m, m_all) and np.array_equal(acc_d, d_all)
+    with pytest.raises(ok.OrionError, match="strictly ascending"):
+        import torch
+        bad = torch.tensor([5, 9, 9, 12], dtype=torch.int64, device="cuda")
+        ok.KmerSet.from_sorted_device(k, bad.data_ptr(), 4)
+
+
 def test_intersection_tiled_kernel_shapes():
     """k_intersect_bounds + k_intersect_tiled against numpy on shapes that stress the tiling: equal sets, disjoint
     ranges, a small set inside a large one (one tile of A against hundreds of chunks of B), interleaved keys, tile
