@@ -178,6 +178,21 @@ int ok_xchg_sample_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_base
 int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
                            uint64_t n_records, const uint32_t* d_hist_mine, const uint32_t* h_l1c_all);
 int ok_xchg_count_device(ok_counter* c);
+/* ok_xchg_scatter_device in steps, so that the owner's level-2 scatter overlaps the exchange of the later chunks:
+ *   ok_xchg_scatter_begin   plan, enqueue every chunk's scatter and its peer copies; returns at once
+ *   for chunk = 0 .. n_chunks-1:
+ *       ok_xchg_chunk_sent  (host) wait until THIS sender's copies of the chunk have landed in every owner's buffer
+ *       caller: a host-side barrier among the ranks (after it, every sender's sub-block of the chunk is complete)
+ *       ok_xchg_chunk_recv  enqueue the receive work of the chunk (fills from the headers, level-2 scatter) on the
+ *                           library's receive stream
+ *   ok_xchg_scatter_end     drain the sender side; reports an overflowed region like ok_xchg_scatter_device
+ * then the agreement collective and ok_xchg_count_device as above.  The device never waits on another rank: all
+ * cross-rank synchronisation is the caller's host code. */
+int ok_xchg_scatter_begin(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                          uint64_t n_records, const uint32_t* d_hist_mine, const uint32_t* h_l1c_all);
+int ok_xchg_chunk_sent(ok_counter* c, uint32_t chunk);
+int ok_xchg_chunk_recv(ok_counter* c, uint32_t chunk);
+int ok_xchg_scatter_end(ok_counter* c);
 /* count.rs:106-119: entries with count >= min_count, ascending by k-mer value. */
 int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** kmers, uint64_t** counts,
                       uint64_t* n);

@@ -100,6 +100,10 @@ ABI = {
     "ok_xchg_sample_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
     "ok_xchg_scatter_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
     "ok_xchg_count_device": (C.c_int, [vp]),
+    "ok_xchg_scatter_begin": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
+    "ok_xchg_chunk_sent": (C.c_int, [vp, C.c_uint32]),
+    "ok_xchg_chunk_recv": (C.c_int, [vp, C.c_uint32]),
+    "ok_xchg_scatter_end": (C.c_int, [vp]),
     "ok_counter_finish": (C.c_int, [vp, C.c_uint64, C.POINTER(u64p), C.POINTER(u64p), u64p]),
     "ok_counter_finish_device": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp), u64p]),
     "ok_counter_set_path": (C.c_int, [vp, C.c_int]),
@@ -487,6 +491,19 @@ class KmerCounter:
     def xchg_scatter_device(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_mine_ptr, h_l1c_all):
         h = np.ascontiguousarray(h_l1c_all, dtype=np.uint32)
         _check(lib().ok_xchg_scatter_device(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_mine_ptr, _ptr(h)))
+
+    def xchg_scatter_begin(self, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_mine_ptr, h_l1c_all):
+        h = np.ascontiguousarray(h_l1c_all, dtype=np.uint32)
+        _check(lib().ok_xchg_scatter_begin(self._h, d_bases_ptr, n_bases, d_offsets_ptr, n_records, d_hist_mine_ptr, _ptr(h)))
+
+    def xchg_chunk_sent(self, chunk):
+        _check(lib().ok_xchg_chunk_sent(self._h, chunk))
+
+    def xchg_chunk_recv(self, chunk):
+        _check(lib().ok_xchg_chunk_recv(self._h, chunk))
+
+    def xchg_scatter_end(self):
+        _check(lib().ok_xchg_scatter_end(self._h))
 
     def xchg_count_device(self):
         _check(lib().ok_xchg_count_device(self._h))

@@ -151,7 +151,16 @@ struct ShardState {
     unsigned n_chunks = 0;                   // chunks per batch, agreed by all ranks
     unsigned long long* d_send = nullptr; uint64_t cap_send = 0;   // sub-blocks for the other owners, built locally
     unsigned* d_xchg = nullptr;              // cur | end | beg (sender side), rbeg | rend | rfill (receiver side): n_chunks x 1024 each; then hdr_send | hdr_recv: n_chunks x 8
-    cudaStream_t s_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t s_peer[8][4] = {};          // copy streams: up to 4 per peer (one stream's copies reach ~500 GB/s, NVLink takes more)
+    cudaEvent_t ev_piece[8][4] = {};         // end of a (peer, stream) piece of the chunk in flight
+    unsigned streams_per_peer = 1;
+    cudaStream_t s_join = nullptr;           // joins the copy streams of a chunk: ev_sent[chunk] = "this sender's chunk has landed everywhere"
+    cudaEvent_t ev_sent[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // the owner's receive pipeline (fills + level-2 scatter per chunk) on its own stream, under the exchange of later chunks
+    cudaStream_t s_recv = nullptr;
+    cudaEvent_t ev_recv[3] = {nullptr, nullptr, nullptr};     // start / end of the receive pipeline
+    unsigned recv_chunks = 0;                // chunks whose receive work has been issued (ok_xchg_chunk_recv)
+    bool begun = false;                      // ok_xchg_scatter_begin without its _end yet
     cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool xchg_pending = false;               // a batch has been scattered and exchanged, not yet counted
     unsigned xchg_chunks_used = 0;
@@ -1228,7 +1237,11 @@ OK_EXPORT int ok_counter_destroy(ok_counter* c) {
     cudaFree(c->d_run_keys); cudaFree(c->d_run_counts); if (!c->buf1_external) cudaFree(c->d_buf1); cudaFree(c->d_buf2); cudaFree(c->d_cnt);
     cudaFree(c->shard.d_state); cudaFree(c->shard.d_received); cudaFree(c->shard.d_snap); cudaFreeHost(c->shard.h_blk);
     cudaFree(c->shard.d_send); cudaFree(c->shard.d_xchg);
-    for (auto st : c->shard.s_peer) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto& row : c->shard.s_peer) for (auto st : row) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto& row : c->shard.ev_piece) for (auto e : row) if (e) cudaEventDestroy(e);
+    for (auto st : {c->shard.s_join, c->shard.s_recv}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto e : c->shard.ev_sent) if (e) cudaEventDestroy(e);
+    for (auto e : c->shard.ev_recv) if (e) cudaEventDestroy(e);
     for (auto e : c->shard.ev_chunk) if (e) cudaEventDestroy(e);
     cudaFree(c->d_meta); cudaFreeHost(c->h_part);
     cudaFree(c->d_acc_keys); cudaFree(c->d_acc_counts); cudaFree(c->d_mrg_keys); cudaFree(c->d_mrg_counts); cudaFree(c->d_split);
@@ -1771,8 +1784,23 @@ OK_EXPORT int ok_xchg_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* su
                    (uint64_t)(6.0 * std::sqrt((double)sh.stride) * std::sqrt((double)regions * ((double)(n_bases_max + n_bases_max / 4) + (double)regions * sh.stride)));
     if (sh.cap_keys >= (1ull << 32)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_geometry: batch too large for 32-bit offsets");
     if (!sh.d_xchg) CU(cudaMalloc((void**)&sh.d_xchg, (6 * 8 * XCHG_STRIDE + 2 * 8 * 8) * sizeof(unsigned)));
-    for (int r = 0; r < c->n_shards; ++r) if (!sh.s_peer[r] && r != c->shard_rank) CU(cudaStreamCreateWithFlags(&sh.s_peer[r], cudaStreamNonBlocking));
+    // with few peers one copy per (peer, chunk) leaves copy engines idle (measured at 2 GPUs: 500 GB/s on one stream):
+    // the sub-block is cut into pieces on several streams
+    sh.streams_per_peer = std::max(1u, std::min(4u, 8u / (unsigned)c->n_shards));
+    if (const char* ev = getenv("ORION_XCHG_STREAMS")) sh.streams_per_peer = (unsigned)std::min(4, std::max(1, atoi(ev)));
+    for (int r = 0; r < c->n_shards; ++r)
+        for (unsigned q = 0; q < sh.streams_per_peer; ++q)
+            if (!sh.s_peer[r][q] && r != c->shard_rank) {
+                CU(cudaStreamCreateWithFlags(&sh.s_peer[r][q], cudaStreamNonBlocking));
+                CU(cudaEventCreateWithFlags(&sh.ev_piece[r][q], cudaEventDisableTiming));
+            }
     for (auto& e : sh.ev_chunk) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : sh.ev_sent) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!sh.s_recv) {
+        CU(cudaStreamCreateWithFlags(&sh.s_recv, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&sh.s_join, cudaStreamNonBlocking));
+        for (auto& e : sh.ev_recv) CU(cudaEventCreate(&e));
+    }
     *n_chunks = nc; *buffer_keys = sh.cap_keys;
     return OK_SUCCESS;
 }
@@ -1811,8 +1839,9 @@ OK_EXPORT int ok_xchg_sample_device(ok_counter* c, const uint8_t* d_bases, uint6
 
 // d_hist_mine[1 << sub_bits]: the fine histogram summed over the ranks, this rank's slice (device);
 // h_l1c_all[n_ranks][n_chunks][n_ranks << l1_bits]: every rank's per-chunk level-1 histogram (HOST memory).
-OK_EXPORT int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
-                                     uint64_t n_records, const uint32_t* d_hist_mine, const uint32_t* h_l1c_all) {
+namespace {
+int xchg_begin(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+               uint64_t n_records, const uint32_t* d_hist_mine, const uint32_t* h_l1c_all) {
     TRY(shard_check(c, "ok_xchg_scatter_device", n_bases));
     if (!d_hist_mine || !h_l1c_all) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_scatter_device: NULL argument");
     ShardState& sh = c->shard;
@@ -1882,6 +1911,7 @@ OK_EXPORT int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint
     LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)sh.cap_keys, pl.chunk_sum);
     LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)sh.cap_keys, pl.cfg.b2,
            pl.chunk_sum, (unsigned)pl.cap_bound, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
+    CU(cudaMemsetAsync(sh.d_received, 0, 8, c->s_main));
     CU(cudaEventRecord(c->ev_p[1], c->s_main));
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
     const uint64_t per_chunk = (n_tiles + NC - 1) / NC;
@@ -1909,22 +1939,37 @@ OK_EXPORT int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint
         // engines under the extraction of the next chunk
         for (; next_copy < copies.size() && copies[next_copy].chunk == ch; ++next_copy) {
             const Copy& cp = copies[next_copy];
-            CU(cudaStreamWaitEvent(sh.s_peer[cp.peer], sh.ev_chunk[ch], 0));
-            if (cp.len) CU(cudaMemcpyAsync(sh.peer[cp.peer] + cp.dst, sh.d_send + cp.src, cp.len * 8, cudaMemcpyDeviceToDevice, sh.s_peer[cp.peer]));
+            const uint64_t piece = ((cp.len + sh.streams_per_peer - 1) / sh.streams_per_peer + 1) & ~1ull;      // even: 16-byte aligned cuts
+            for (unsigned q = 0; q < sh.streams_per_peer; ++q) {
+                const uint64_t a = std::min<uint64_t>(cp.len, q * piece), b2 = std::min<uint64_t>(cp.len, (q + 1) * piece);
+                CU(cudaStreamWaitEvent(sh.s_peer[cp.peer][q], sh.ev_chunk[ch], 0));
+                if (b2 > a) CU(cudaMemcpyAsync(sh.peer[cp.peer] + cp.dst + a, sh.d_send + cp.src + a, (b2 - a) * 8, cudaMemcpyDeviceToDevice, sh.s_peer[cp.peer][q]));
+                CU(cudaEventRecord(sh.ev_piece[cp.peer][q], sh.s_peer[cp.peer][q]));
+                CU(cudaStreamWaitEvent(sh.s_join, sh.ev_piece[cp.peer][q], 0));
+            }
         }
+        CU(cudaStreamWaitEvent(sh.s_join, sh.ev_chunk[ch], 0));
+        CU(cudaEventRecord(sh.ev_sent[ch], sh.s_join));       // chunk ch of this sender has landed in every owner's buffer
     }
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
-    for (unsigned r = 0; r < W; ++r)
-        if (r != me) { CU(cudaEventRecord(sh.ev_chunk[0], sh.s_peer[r])); CU(cudaStreamWaitEvent(c->s_main, sh.ev_chunk[0], 0)); }
+    sh.xchg_chunks_used = NC; sh.recv_chunks = 0; sh.begun = true;
+    return OK_SUCCESS;
+}
+
+int xchg_end(ok_counter* c) {
+    ShardState& sh = c->shard;
+    if (!sh.begun) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_scatter_end: no chunked scatter in progress");
+    sh.begun = false;
+    CU(cudaStreamWaitEvent(c->s_main, sh.ev_sent[sh.xchg_chunks_used - 1], 0));     // s_join is in order: the last chunk's event covers them all
     CU(cudaEventRecord(c->ev_b, c->s_main));
     TRY(read_stats(c));          // drains the compute stream, which has waited for every peer copy
     CU(cudaGetLastError());
     cudaEventElapsedTime(&c->ms_scatter1, c->ev_p[1], c->ev_p[2]);
     cudaEventElapsedTime(&c->ms_push, c->ev_p[2], c->ev_b);
     float ms = 0; cudaEventElapsedTime(&ms, c->ev_p[0], c->ev_b); c->ms_route += ms;
-    sh.xchg_chunks_used = NC;
     if (c->h_stats->spill_n) {
         // a region overflowed: the spilled k-mers belong to OTHER ranks, this rank cannot count them
+        CU(cudaStreamSynchronize(sh.s_recv));
         CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
         CU(cudaStreamSynchronize(c->s_main));
         c->h_stats->spill_n = 0;
@@ -1932,6 +1977,66 @@ OK_EXPORT int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint
     }
     sh.xchg_pending = true;
     return OK_SUCCESS;
+}
+
+// receive work of one chunk on the receive stream: fills from the sub-block headers, work items, level-2 scatter
+int xchg_recv_chunk(ok_counter* c, unsigned ch, cudaStream_t st) {
+    ShardState& sh = c->shard;
+    PartPlan& pl = c->pl;
+    const unsigned W = (unsigned)c->n_shards, n_regs = W << sh.b1;
+    unsigned* dx = sh.d_xchg;
+    unsigned *d_rbeg = dx + 24 * XCHG_STRIDE, *d_rend = dx + 32 * XCHG_STRIDE, *d_rfill = dx + 40 * XCHG_STRIDE, *d_hr = dx + 48 * XCHG_STRIDE + 64;
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    auto k_l2 = OK_BY_K(c->k, k_part_scatter_keys, 2, true);
+    TRY(set_smem(k_l2, sizeof(OkScatterKeysSmem)));
+    LAUNCH(k_xchg_fills, 1, 1024, 0, st, c->d_buf1, d_hr + ch * 8, n_regs, sh.b1, d_rbeg + (size_t)ch * XCHG_STRIDE,
+           d_rend + (size_t)ch * XCHG_STRIDE, d_rfill + (size_t)ch * XCHG_STRIDE, sh.d_received);
+    LAUNCH(k_part_items, 32, 1024, 0, st, d_rbeg + (size_t)ch * XCHG_STRIDE, d_rfill + (size_t)ch * XCHG_STRIDE, d_rend + (size_t)ch * XCHG_STRIDE,
+           n_regs, pl.n_bin1 - 1u, pl.item_off, pl.item_n, pl.item_bin, pl.scal, (unsigned*)nullptr);
+    LAUNCH(k_l2, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), st, c->d_buf1, pl.item_off, pl.item_n,
+           pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, (OkPartSpill{c->spill, c->d_stats}), (const unsigned*)nullptr, 0u, 0u);
+    return OK_SUCCESS;
+}
+}  // namespace
+
+OK_EXPORT int ok_xchg_scatter_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                                     uint64_t n_records, const uint32_t* d_hist_mine, const uint32_t* h_l1c_all) {
+    TRY(xchg_begin(c, d_bases, n_bases, d_rec_offsets, n_records, d_hist_mine, h_l1c_all));
+    return xchg_end(c);
+}
+
+// The same in steps, so that the owner's level-2 work overlaps the exchange: _begin enqueues the whole chunked scatter
+// and its peer copies and returns at once; for every chunk the caller (1) waits with ok_xchg_chunk_sent until THIS
+// sender's copies of the chunk have landed, (2) synchronises with the other ranks on the host (any barrier), then
+// (3) calls ok_xchg_chunk_recv, which enqueues the receive work of that chunk -- every sender's sub-block of it is
+// complete -- on a stream of its own; _end drains the sender side and reports overflowed regions.
+// No device-side waiting on remote state: all cross-rank synchronisation stays with the caller's host code.
+OK_EXPORT int ok_xchg_scatter_begin(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
+                                    uint64_t n_records, const uint32_t* d_hist_mine, const uint32_t* h_l1c_all) {
+    return xchg_begin(c, d_bases, n_bases, d_rec_offsets, n_records, d_hist_mine, h_l1c_all);
+}
+OK_EXPORT int ok_xchg_chunk_sent(ok_counter* c, uint32_t chunk) {
+    if (!c || !c->shard.begun || chunk >= c->shard.xchg_chunks_used) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_chunk_sent: no such chunk in flight");
+    CU(cudaEventSynchronize(c->shard.ev_sent[chunk]));
+    return OK_SUCCESS;
+}
+OK_EXPORT int ok_xchg_chunk_recv(ok_counter* c, uint32_t chunk) {
+    if (!c || !c->shard.begun || chunk != c->shard.recv_chunks || chunk >= c->shard.xchg_chunks_used)
+        return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_chunk_recv: chunks are received in order, after ok_xchg_scatter_begin");
+    ShardState& sh = c->shard;
+    if (chunk == 0) {
+        CU(cudaStreamWaitEvent(sh.s_recv, c->ev_p[1], 0));      // the plan (cursors of my sub-partitions) exists
+        CU(cudaEventRecord(sh.ev_recv[0], sh.s_recv));
+    }
+    CU(cudaStreamWaitEvent(sh.s_recv, sh.ev_chunk[chunk], 0));  // my own sub-block of the chunk (written directly) and its header
+    TRY(xchg_recv_chunk(c, chunk, sh.s_recv));
+    ++sh.recv_chunks;
+    if (sh.recv_chunks == sh.xchg_chunks_used) { CU(cudaEventRecord(sh.ev_recv[1], sh.s_recv)); CU(cudaEventRecord(sh.ev_recv[2], sh.s_recv)); }
+    return OK_SUCCESS;
+}
+OK_EXPORT int ok_xchg_scatter_end(ok_counter* c) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_scatter_end: NULL handle");
+    return xchg_end(c);
 }
 
 // every rank has returned from ok_xchg_scatter_device (the caller's collective in between is the barrier)
@@ -1943,27 +2048,18 @@ OK_EXPORT int ok_xchg_count_device(ok_counter* c) {
     PartPlan& pl = c->pl;
     if (pl.cfg.b2 == 0) return set_err(OK_ERR_INTERNAL, "sharded path needs two scatter levels");
     const uint64_t windows_before = c->windows;
-    const unsigned W = (unsigned)c->n_shards, n_regs = W << sh.b1, NC = sh.xchg_chunks_used;
-    unsigned* dx = sh.d_xchg;
-    unsigned *d_rbeg = dx + 24 * XCHG_STRIDE, *d_rend = dx + 32 * XCHG_STRIDE, *d_rfill = dx + 40 * XCHG_STRIDE, *d_hr = dx + 48 * XCHG_STRIDE + 64;
-    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
-    const OkPartSpill ps{c->spill, c->d_stats};
-    auto k_l2 = OK_BY_K(c->k, k_part_scatter_keys, 2, true);
-    TRY(set_smem(k_l2, sizeof(OkScatterKeysSmem)));
+    const unsigned NC = sh.xchg_chunks_used;
     const float ms_scatter1 = c->ms_scatter1;
+    const bool overlapped = sh.recv_chunks == NC;
+    if (sh.recv_chunks) CU(cudaStreamWaitEvent(c->s_main, overlapped ? sh.ev_recv[2] : sh.ev_chunk[0], 0));
+    if (sh.recv_chunks && !overlapped) CU(cudaStreamSynchronize(sh.s_recv));      // (a caller that stopped half-way)
     CU(cudaEventRecord(c->ev_p[2], c->s_main));      // part_finish times the level-2 scatter from here
-    CU(cudaMemsetAsync(sh.d_received, 0, 8, c->s_main));
-    for (unsigned ch = 0; ch < NC; ++ch) {
-        LAUNCH(k_xchg_fills, 1, 1024, 0, c->s_main, c->d_buf1, d_hr + ch * 8, n_regs, sh.b1, d_rbeg + (size_t)ch * XCHG_STRIDE,
-               d_rend + (size_t)ch * XCHG_STRIDE, d_rfill + (size_t)ch * XCHG_STRIDE, sh.d_received);
-        LAUNCH(k_part_items, 32, 1024, 0, c->s_main, d_rbeg + (size_t)ch * XCHG_STRIDE, d_rfill + (size_t)ch * XCHG_STRIDE, d_rend + (size_t)ch * XCHG_STRIDE,
-               n_regs, pl.n_bin1 - 1u, pl.item_off, pl.item_n, pl.item_bin, pl.scal, (unsigned*)nullptr);
-        LAUNCH(k_l2, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, c->d_buf1, pl.item_off, pl.item_n,
-               pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, ps, (const unsigned*)nullptr, 0u, 0u);
-    }
+    for (unsigned ch = sh.recv_chunks; ch < NC; ++ch) TRY(xchg_recv_chunk(c, ch, c->s_main));     // not overlapped: everything after the barrier
     CU(cudaMemcpyAsync(&c->h_part->received, sh.d_received, 8, cudaMemcpyDeviceToHost, c->s_main));
     TRY(part_finish(c, pl, /*level2=*/false));
     c->ms_scatter1 = ms_scatter1;                     // measured by ok_xchg_scatter_device (part_finish re-read moved events)
+    if (overlapped) cudaEventElapsedTime(&c->ms_scatter2, sh.ev_recv[0], sh.ev_recv[1]);     // ran under the exchange (includes its waits)
+    sh.recv_chunks = 0;
     c->ms_insert = c->ms_sample + c->ms_scatter1 + c->ms_push + c->ms_scatter2 + c->ms_count;
     c->windows = windows_before + c->h_part->received;
     CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
@@ -2060,6 +2156,9 @@ OK_EXPORT int ok_counter_abort_batch(ok_counter* c) {
     if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_abort_batch: NULL handle");
     c->shard.xchg_pending = false;
     c->pl.sharded = false;
+    if (c->shard.begun) { cudaStreamSynchronize(c->s_main); cudaStreamSynchronize(c->shard.s_join); c->shard.begun = false; }
+    if (c->shard.s_recv) CU(cudaStreamSynchronize(c->shard.s_recv));
+    c->shard.recv_chunks = 0;
     if (c->run_state == RUN_LEVEL1) { CU(cudaStreamSynchronize(c->s_main)); c->run_state = RUN_NONE; }
     if (c->run_state != RUN_NONE && c->n_acc) { c->run_state = RUN_NONE; c->n_run = 0; c->occupied = 0; }
     CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));

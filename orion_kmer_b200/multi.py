@@ -60,6 +60,58 @@ class Coll:
         self.dist.barrier(group=self.group)
 
 
+class HostFlags:
+    """Host-side barrier of the ranks of one node in shared memory (a few microseconds; a collective through sockets
+    or through the GPU costs 0.1-1 ms and, on the GPU, an SM slot).  Rank r bumps slot r; a barrier is over once every
+    slot has reached the caller's tick.  Falls back to the process group's barrier when shared memory is unavailable."""
+
+    def __init__(self, dist, coll):
+        self.dist, self.coll = dist, coll
+        self.rank, self.world, self.tick = dist.get_rank(), dist.get_world_size(), 0
+        self.shm, self.slots = None, None
+        try:
+            from multiprocessing import shared_memory
+            name = [None]
+            if self.rank == 0:
+                self.shm = shared_memory.SharedMemory(create=True, size=64 * self.world)
+                self.shm.buf[:64 * self.world] = bytes(64 * self.world)
+                name[0] = self.shm.name
+            dist.broadcast_object_list(name, src=0)
+            if self.rank != 0 and name[0]:
+                self.shm = shared_memory.SharedMemory(name=name[0])
+            ok = self.shm is not None
+        except Exception:
+            ok = False
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok)
+        if all(flags):
+            self.slots = np.ndarray((self.world, 8), dtype=np.int64, buffer=self.shm.buf)[:, 0]     # one cache line per rank
+        coll.barrier()
+
+    def barrier(self, timeout=60.0):
+        self.tick += 1
+        if self.slots is None:
+            return self.coll.barrier()
+        self.slots[self.rank] = self.tick
+        t0, spins = time.perf_counter(), 0
+        while int(self.slots.min()) < self.tick:
+            spins += 1
+            if spins % 4096 == 0 and time.perf_counter() - t0 > timeout:
+                raise RuntimeError(f"rank {self.rank}: host barrier timed out (a peer rank is gone?)")
+
+    def close(self):
+        if self.shm is not None:
+            self.slots = None
+            try:
+                self.coll.barrier()
+                self.shm.close()
+                if self.rank == 0:
+                    self.shm.unlink()
+            except Exception:
+                pass
+            self.shm = None
+
+
 def exchange(dist, torch, send, send_counts, group=None):
     """send: 1-D int64 tensor holding the k-mers for rank 0, then rank 1, ... (send_counts each).
     -> (recv tensor, recv_counts list)."""
@@ -99,6 +151,9 @@ class ShardedCounter:
         #    extraction kernel pushes with SM stores); 1: two-pass fused route; 0: NCCL all-to-all
         self.fused = int(fused)
         self.fallbacks = 0
+        # overlap the owner's level-2 scatter with the exchange of the later chunks (chunk-wise host barrier)
+        self.overlap = not os.environ.get("ORION_XCHG_NO_OVERLAP")
+        self.flags = HostFlags(dist, self.coll) if self.fused == 3 and self.overlap else None
         self.d_send = None
         self.recv, self.recv_cap, self.peer_ptrs = None, 0, None
         self.geom = None
@@ -175,8 +230,25 @@ class ShardedCounter:
         t1 = time.perf_counter()
         ok_flag = 1
         try:
-            self.counter.xchg_scatter_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
-                                             g["hist_mine"].data_ptr(), h_l1c_all)
+            if self.flags is None:
+                self.counter.xchg_scatter_device(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
+                                                 g["hist_mine"].data_ptr(), h_l1c_all)
+            else:
+                began = True
+                try:
+                    self.counter.xchg_scatter_begin(d_bases.data_ptr(), n_bases, d_off.data_ptr(), n_reads,
+                                                    g["hist_mine"].data_ptr(), h_l1c_all)
+                except self.ok.OrionError:
+                    began = False                   # (still walks the barriers below: the others are waiting in them)
+                    raise
+                finally:
+                    for ch in range(g["n_chunks"]):
+                        if began:
+                            self.counter.xchg_chunk_sent(ch)     # my copies of chunk ch have landed
+                        self.flags.barrier()                     # ... and everybody else's
+                        if began:
+                            self.counter.xchg_chunk_recv(ch)     # level 2 of chunk ch, under the exchange of the later chunks
+                self.counter.xchg_scatter_end()
         except self.ok.OrionError as e:
             ok_flag = 0
             if os.environ.get("ORION_VERBOSE"):
@@ -315,6 +387,9 @@ class ShardedCounter:
 
     def close(self):
         self._release_recv()
+        if self.flags is not None:
+            self.flags.close()
+            self.flags = None
         self.counter.close()
 
 

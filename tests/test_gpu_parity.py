@@ -905,7 +905,7 @@ def test_sharded_scatter_matches_oracle(oracle, n_ranks, hint):
     assert np.array_equal(gc, wc)
 
 
-def _xchg_dance(counters, batches, n):
+def _xchg_dance(counters, batches, n, stepwise=False):
     """one step of the chunked exchange (ok_xchg_*) for every emulated rank; torch ops stand in for the collectives"""
     import torch
     n_ranks = len(counters)
@@ -926,9 +926,20 @@ def _xchg_dance(counters, batches, n):
                                  hist_fine[r].data_ptr(), hist_l1c[r].data_ptr())
         hist_sum = torch.stack(hist_fine).sum(0, dtype=torch.int32)
         l1c_all = torch.cat(hist_l1c).cpu().numpy().view(np.uint32)
-        for r, c in enumerate(counters):
-            mine = hist_sum[r << sub_bits:(r + 1) << sub_bits].contiguous()
-            c.xchg_scatter_device(dev[r][0].data_ptr(), len(batches[r][0]), dev[r][1].data_ptr(), n, mine.data_ptr(), l1c_all)
+        mine = [hist_sum[r << sub_bits:(r + 1) << sub_bits].contiguous() for r in range(n_ranks)]
+        if stepwise:        # the receive pipeline of every chunk as soon as all ranks have sent it (a loop stands in for the host barrier)
+            for r, c in enumerate(counters):
+                c.xchg_scatter_begin(dev[r][0].data_ptr(), len(batches[r][0]), dev[r][1].data_ptr(), n, mine[r].data_ptr(), l1c_all)
+            for ch in range(n_chunks):
+                for c in counters:
+                    c.xchg_chunk_sent(ch)
+                for c in counters:
+                    c.xchg_chunk_recv(ch)
+            for c in counters:
+                c.xchg_scatter_end()
+        else:
+            for r, c in enumerate(counters):
+                c.xchg_scatter_device(dev[r][0].data_ptr(), len(batches[r][0]), dev[r][1].data_ptr(), n, mine[r].data_ptr(), l1c_all)
         keys, counts = [], []
         for r, c in enumerate(counters):
             c.xchg_count_device()
@@ -960,7 +971,7 @@ def test_chunked_exchange_matches_oracle(oracle, monkeypatch, n_ranks, hint, chu
     for rep in range(2):
         for c in counters:
             c.clear()
-        gk, gc, used = _xchg_dance(counters, batches, n)
+        gk, gc, used = _xchg_dance(counters, batches, n, stepwise=rep == 1)
         assert used == chunks
         assert np.array_equal(gk, wk) and np.array_equal(gc, wc), rep
     for c in counters:
@@ -976,7 +987,7 @@ def test_chunked_exchange_second_batch_merges_into_the_shards(oracle):
     for r, c in enumerate(counters):
         c.set_shard(r, n_ranks)
     for i, batches in enumerate(rounds):
-        gk, gc, _ = _xchg_dance(counters, batches, n)
+        gk, gc, _ = _xchg_dance(counters, batches, n, stepwise=i == 1)
         assert all(c.stats()["n_merges"] == i for c in counters)
         all_bases = np.concatenate([b for rd in rounds[:i + 1] for b, _ in rd])
         wk, wc = oracle.count_batch(k, all_bases, synth.read_offsets(n * n_ranks * (i + 1)))

@@ -154,3 +154,37 @@ def test_collective_helper_without_nccl():
     """multi.Coll stages the exchange's small collectives through host memory on a backend without device support
     (gloo: what the two-processes-on-one-GPU test uses); same results as the NCCL forms."""
     mp.spawn(_coll_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _flags_worker(rank, world, port, ret):
+    from orion_kmer_b200 import multi
+    import time
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    try:
+        f = multi.HostFlags(dist, multi.Coll(dist, torch))
+        assert f.slots is not None, "shared memory unavailable"
+        order = []
+        for i in range(50):
+            if rank == i % world:
+                time.sleep(0.002)               # the late rank: the others must wait for it
+            order.append(time.perf_counter())
+            f.barrier()
+        t_after = time.perf_counter()
+        out = [None] * world
+        dist.all_gather_object(out, (order, t_after))
+        # nobody left barrier i before everybody had entered it
+        for i in range(49):
+            assert max(o[0][i] for o in out) <= min(o[0][i + 1] for o in out) + 1e-3
+        f.close()
+        if rank == 0:
+            ret["ok"] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_host_flags_barrier():
+    """the shared-memory barrier the chunked exchange paces its receive pipeline with"""
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_flags_worker, args=(3, _free_port(), ret), nprocs=3, join=True)
+        assert ret.get("ok")
