@@ -206,6 +206,9 @@ int ok_counter_set_path(ok_counter* c, int mode);
 /* multi-GPU: drop what this rank holds of the batch whose exchange just failed on some rank (every rank then
  * recounts it through another route); the result of earlier batches is kept */
 int ok_counter_abort_batch(ok_counter* c);
+/* multi-GPU: every rank has counted its share of the batch (ok_shard_count_device / ok_xchg_count_device succeeded
+ * everywhere): merge it into the result of the earlier batches.  A no-op for the first batch. */
+int ok_counter_commit_batch(ok_counter* c);
 /* forget all counts, keep the allocation (bench loops) */
 int ok_counter_clear(ok_counter* c);
 int ok_counter_destroy(ok_counter* c);

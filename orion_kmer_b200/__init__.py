@@ -109,6 +109,7 @@ ABI = {
     "ok_counter_set_path": (C.c_int, [vp, C.c_int]),
     "ok_counter_set_capacity_hint": (C.c_int, [vp, C.c_uint64]),
     "ok_counter_abort_batch": (C.c_int, [vp]),
+    "ok_counter_commit_batch": (C.c_int, [vp]),
     "ok_counter_clear": (C.c_int, [vp]),
     "ok_counter_destroy": (C.c_int, [vp]),
     "ok_counter_get_stats": (C.c_int, [vp, C.POINTER(CounterStats)]),
@@ -543,6 +544,9 @@ class KmerCounter:
     def set_path(self, mode):
         """0 automatic, 1 table only, 2 partitioned whenever the counter is empty"""
         _check(lib().ok_counter_set_path(self._h, mode))
+
+    def commit_batch(self):
+        _check(lib().ok_counter_commit_batch(self._h))
 
     def abort_batch(self):
         _check(lib().ok_counter_abort_batch(self._h))

@@ -149,6 +149,12 @@ struct ShardState {
     unsigned long long* d_received = nullptr;
     // chunked exchange over the copy engines (ok_xchg_*)
     unsigned n_chunks = 0;                   // chunks per batch, agreed by all ranks
+    // three-level form (>= 4 ranks): the sender splits by OWNER only (long contiguous runs: friendly to DRAM and to the
+    // copy engines), the owner runs BOTH scatter levels of the one-GPU path on what arrives (level 1 per chunk, under
+    // the exchange).  rb1 / rb2: the owner's level bits; b1 (sender-side level-1 bits) is 0 then.
+    bool three = false;
+    unsigned rb1 = 0, rb2 = 0;
+    uint64_t recv_cap = 0;                   // keys every peer-mapped buffer holds
     unsigned long long* d_send = nullptr; uint64_t cap_send = 0;   // sub-blocks for the other owners, built locally
     unsigned* d_xchg = nullptr;              // cur | end | beg (sender side), rbeg | rend | rfill (receiver side): n_chunks x 1024 each; then hdr_send | hdr_recv: n_chunks x 8
     cudaStream_t s_peer[8][4] = {};          // copy streams: up to 4 per peer (one stream's copies reach ~500 GB/s, NVLink takes more)
@@ -212,6 +218,7 @@ struct ok_counter {
     unsigned long long* d_run_keys = nullptr; uint64_t cap_run_keys = 0;
     unsigned long long* d_run_counts = nullptr; uint64_t cap_run_counts = 0;
     uint64_t n_run = 0, n_deferred = 0;
+    uint64_t batch_windows = 0;         // windows the sharded batch in progress added (taken back by ok_counter_abort_batch)
     // earlier batches' result, set aside while the next large batch is counted on its own; merged afterwards (merge.cuh)
     unsigned long long* d_acc_keys = nullptr; uint64_t cap_acc_keys = 0;
     unsigned long long* d_acc_counts = nullptr; uint64_t cap_acc_counts = 0;
@@ -1594,8 +1601,14 @@ OK_EXPORT int ok_shard_set_buffers(ok_counter* c, void* const* d_peer_buffers, u
         if (!d_peer_buffers[r] || ((uintptr_t)d_peer_buffers[r] & 15u)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_set_buffers: bad buffer of rank %d", r);
         sh.peer[r] = (unsigned long long*)d_peer_buffers[r];
     }
-    if (!c->buf1_external && c->d_buf1) { cudaFree(c->d_buf1); }
-    c->d_buf1 = sh.peer[c->shard_rank]; c->cap_buf1 = cap_keys; c->buf1_external = true;
+    sh.recv_cap = cap_keys;
+    if (sh.three) {
+        // the peer-mapped buffer only RECEIVES (raw keys per sender and chunk); the level-1 buffer is the counter's own
+        if (c->buf1_external) { c->d_buf1 = nullptr; c->cap_buf1 = 0; c->buf1_external = false; }
+    } else {
+        if (!c->buf1_external && c->d_buf1) { cudaFree(c->d_buf1); }
+        c->d_buf1 = sh.peer[c->shard_rank]; c->cap_buf1 = cap_keys; c->buf1_external = true;
+    }
     sh.buffers = true;
     return OK_SUCCESS;
 }
@@ -1743,6 +1756,7 @@ OK_EXPORT int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all
     if (pl.cfg.b2 == 0) return set_err(OK_ERR_INTERNAL, "sharded path needs two scatter levels");
     TRY(part_finish(c, pl));
     c->windows = windows_before + c->h_part->received;
+    c->batch_windows = c->h_part->received;
     CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
     if (part_hint_misled(c, pl)) {
@@ -1755,7 +1769,7 @@ OK_EXPORT int ok_shard_count_device(ok_counter* c, const uint32_t* d_cursors_all
     }
     const int r = part_absorb_spills(c, windows_before);
     if (r == PART_RETRY) return set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list");
-    return r == OK_SUCCESS ? run_unstash(c) : r;
+    return r;       // an earlier batch's run stays set aside until ok_counter_commit_batch (the ranks agree first)
 }
 
 // ---- multi-GPU exchange, third form: chunked scatter + one copy-engine peer copy per (peer, chunk) ----
@@ -1773,6 +1787,20 @@ OK_EXPORT int ok_xchg_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* su
     if (!n_chunks) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_geometry: NULL argument");
     TRY(ok_shard_geometry(c, n_bases_max, sub_bits, l1_bits, buffer_keys));
     ShardState& sh = c->shard;
+    sh.three = c->n_shards >= 4;
+    if (const char* ev = getenv("ORION_XCHG_LEVELS")) sh.three = atoi(ev) == 3;
+    sh.rb1 = sh.b1; sh.rb2 = sh.b2;
+    if (sh.three) {
+        // 2^g owners x 2^sub_bits sub-partitions are g + sub_bits bits of position: in two passes that is 512-1024 bins
+        // per pass at 8 GPUs -- 64-byte runs, one DRAM page activation each, which starves the copy engines (measured:
+        // 300 GB/s per GPU against 640 with idle SMs).  Three passes of <= 256 bins keep the runs at 256 bytes and more.
+        PartPlan pl;
+        part_choose_bits(c, n_bases_max, pl, /*use_hint=*/true);
+        sh.hinted = pl.hinted;
+        sh.rb1 = pl.cfg.b1; sh.rb2 = pl.cfg.b2; sh.sub_bits = pl.cfg.b1 + pl.cfg.b2; sh.b1 = 0; sh.b2 = sh.sub_bits;
+        sh.cap_keys = n_bases_max + n_bases_max / 4 + 4096;        // raw keys; the per-region slack is added below
+        *sub_bits = sh.sub_bits; *l1_bits = 0;
+    }
     unsigned nc = 8;
     if (const char* ev = getenv("ORION_XCHG_CHUNKS")) nc = (unsigned)std::min(8, std::max(1, atoi(ev)));
     const uint64_t n_tiles = (n_bases_max + OK_TILE_BASES - 1) / OK_TILE_BASES;
@@ -1847,9 +1875,10 @@ int xchg_begin(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const ui
     ShardState& sh = c->shard;
     if (!sh.n_chunks) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_scatter_device: ok_xchg_geometry first");
     const unsigned W = (unsigned)c->n_shards, me = (unsigned)c->shard_rank, NC = sh.n_chunks, n_bin1 = 1u << sh.b1, n_regs = W << sh.b1;
+    unsigned long long* const own = sh.peer[me];          // my peer-mapped buffer (== the level-1 buffer in the two-level form)
     PartPlan& pl = c->pl; pl = PartPlan{};
-    pl.cfg.key_shift = 64 - 2 * c->k; pl.cfg.shard_log2 = sh.g; pl.cfg.b1 = sh.b1; pl.cfg.b2 = sh.b2;
-    pl.n_sub = 1u << sh.sub_bits; pl.n_bin1 = n_bin1; pl.stride = sh.stride; pl.sharded = true;
+    pl.cfg.key_shift = 64 - 2 * c->k; pl.cfg.shard_log2 = sh.g; pl.cfg.b1 = sh.rb1; pl.cfg.b2 = sh.rb2;
+    pl.n_sub = 1u << sh.sub_bits; pl.n_bin1 = 1u << sh.rb1; pl.stride = sh.stride; pl.sharded = !sh.three;
     const uint64_t n_units = sh.n_bases_max + sh.n_bases_max / 4;
     pl.hinted = sh.hinted;
     pl.big_count = sh.hinted ? std::min<uint64_t>(c->user_hint, sh.n_bases_max) / pl.n_sub > 4600 : sh.n_bases_max / pl.n_sub > 5800;
@@ -1858,7 +1887,7 @@ int xchg_begin(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const ui
     TRY(dev_reserve(&sh.d_send, &sh.cap_send, sh.cap_keys));
     // ---- the layout, identical on every rank: owner o's buffer = for every sender, for every chunk, one sub-block
     const unsigned hdr_keys = std::max(2u, (n_bin1 / 2u + 1u) & ~1u);
-    const uint64_t limit = std::min<uint64_t>(c->cap_buf1, 0xFFFFFFF0ull) & ~1ull;
+    const uint64_t limit = std::min<uint64_t>(sh.recv_cap, 0xFFFFFFF0ull) & ~1ull;
     std::vector<unsigned> cur((size_t)NC * XCHG_STRIDE, 0), end((size_t)NC * XCHG_STRIDE, 0), rbeg((size_t)NC * XCHG_STRIDE, 0),
                           rend((size_t)NC * XCHG_STRIDE, 0), hdr_send(NC * 8, 0), hdr_recv(NC * 8, 0);
     struct Copy { uint64_t src, dst, len; unsigned peer, chunk; };
@@ -1916,10 +1945,12 @@ int xchg_begin(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const ui
     const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
     const uint64_t per_chunk = (n_tiles + NC - 1) / NC;
     OkPeerOut po{}; po.shift = sh.b1;
-    for (unsigned r = 0; r < W; ++r) po.p[r] = r == me ? c->d_buf1 : sh.d_send;
+    for (unsigned r = 0; r < W; ++r) po.p[r] = r == me ? own : sh.d_send;
     auto kern = c->norm_mode == OK_NORM_NORMALIZED ? OK_BY_K(c->k, k_part_scatter_bases, true, true) : OK_BY_K(c->k, k_part_scatter_bases, false, true);
+    if (n_regs <= 256 && g_scatter_p3)      // >= 32 staging slots per bin: three fuller rounds per warp-tile
+        kern = c->norm_mode == OK_NORM_NORMALIZED ? OK_BY_K3(c->k, k_part_scatter_bases, true, true) : OK_BY_K3(c->k, k_part_scatter_bases, false, true);
     TRY(set_smem(kern, sizeof(OkScatterSmem)));
-    const OkPartCfg cfg = shard_global_cfg(c, sh.b1);      // level-1 bin id = (owner, bin)
+    const OkPartCfg cfg = shard_global_cfg(c, sh.b1);      // scatter bin id = (owner, sender-side level-1 bin)
     size_t next_copy = 0;
     std::sort(copies.begin(), copies.end(), [](const Copy& a, const Copy& b) { return a.chunk != b.chunk ? a.chunk < b.chunk : a.peer < b.peer; });
     for (unsigned ch = 0; ch < NC; ++ch) {
@@ -1933,7 +1964,7 @@ int xchg_begin(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const ui
                    (OkPartSpill{c->spill, c->d_stats}), c->d_stats->route_counts, po, OkPushDesc{});
         }
         LAUNCH(k_xchg_headers, 1, 1024, 0, c->s_main, d_cur + (size_t)ch * XCHG_STRIDE, d_end + (size_t)ch * XCHG_STRIDE, d_beg + (size_t)ch * XCHG_STRIDE,
-               n_regs, sh.b1, me, d_hs + ch * 8, c->d_buf1, sh.d_send);
+               n_regs, sh.b1, me, d_hs + ch * 8, own, sh.d_send);
         CU(cudaEventRecord(sh.ev_chunk[ch], c->s_main));
         // one plain asynchronous peer copy per (owner, chunk), each owner on its own stream: they run on the copy
         // engines under the extraction of the next chunk
@@ -1989,11 +2020,24 @@ int xchg_recv_chunk(ok_counter* c, unsigned ch, cudaStream_t st) {
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
     auto k_l2 = OK_BY_K(c->k, k_part_scatter_keys, 2, true);
     TRY(set_smem(k_l2, sizeof(OkScatterKeysSmem)));
-    LAUNCH(k_xchg_fills, 1, 1024, 0, st, c->d_buf1, d_hr + ch * 8, n_regs, sh.b1, d_rbeg + (size_t)ch * XCHG_STRIDE,
+    unsigned long long* const own = sh.peer[c->shard_rank];
+    LAUNCH(k_xchg_fills, 1, 1024, 0, st, own, d_hr + ch * 8, n_regs, sh.b1, d_rbeg + (size_t)ch * XCHG_STRIDE,
            d_rend + (size_t)ch * XCHG_STRIDE, d_rfill + (size_t)ch * XCHG_STRIDE, sh.d_received);
+    if (sh.three) {
+        // what arrived is raw keys per sender: LEVEL 1 of the owner's own two levels, straight from the receive buffer
+        const bool two = pl.cfg.b2 > 0;
+        auto k_l1 = OK_BY_K(c->k, k_part_scatter_keys, 1, true);
+        TRY(set_smem(k_l1, sizeof(OkScatterKeysSmem)));
+        LAUNCH(k_part_items, 32, 1024, 0, st, d_rbeg + (size_t)ch * XCHG_STRIDE, d_rfill + (size_t)ch * XCHG_STRIDE, d_rend + (size_t)ch * XCHG_STRIDE,
+               n_regs, 0xFFFFFFFFu, pl.item_off, pl.item_n, pl.item_bin, pl.scal, (unsigned*)nullptr);
+        LAUNCH(k_l1, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), st, own, pl.item_off, pl.item_n,
+               pl.item_bin, pl.scal, pl.cfg, two ? pl.cursor1 : pl.cursor, (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2,
+               (OkPartSpill{c->spill, c->d_stats}), (const unsigned*)nullptr, 0u, 0u);
+        return OK_SUCCESS;
+    }
     LAUNCH(k_part_items, 32, 1024, 0, st, d_rbeg + (size_t)ch * XCHG_STRIDE, d_rfill + (size_t)ch * XCHG_STRIDE, d_rend + (size_t)ch * XCHG_STRIDE,
            n_regs, pl.n_bin1 - 1u, pl.item_off, pl.item_n, pl.item_bin, pl.scal, (unsigned*)nullptr);
-    LAUNCH(k_l2, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), st, c->d_buf1, pl.item_off, pl.item_n,
+    LAUNCH(k_l2, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), st, own, pl.item_off, pl.item_n,
            pl.item_bin, pl.scal, pl.cfg, pl.cursor, pl.cap_end, c->d_buf2, (OkPartSpill{c->spill, c->d_stats}), (const unsigned*)nullptr, 0u, 0u);
     return OK_SUCCESS;
 }
@@ -2043,10 +2087,10 @@ OK_EXPORT int ok_xchg_scatter_end(ok_counter* c) {
 OK_EXPORT int ok_xchg_count_device(ok_counter* c) {
     if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_count_device: NULL handle");
     ShardState& sh = c->shard;
-    if (!c->pl.sharded || !sh.xchg_pending || c->run_state != RUN_NONE) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_count_device: no exchanged batch pending");
+    if (!sh.xchg_pending || c->run_state != RUN_NONE) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_count_device: no exchanged batch pending");
     sh.xchg_pending = false;
     PartPlan& pl = c->pl;
-    if (pl.cfg.b2 == 0) return set_err(OK_ERR_INTERNAL, "sharded path needs two scatter levels");
+    if (pl.cfg.b2 == 0 && !sh.three) return set_err(OK_ERR_INTERNAL, "sharded path needs two scatter levels");
     const uint64_t windows_before = c->windows;
     const unsigned NC = sh.xchg_chunks_used;
     const float ms_scatter1 = c->ms_scatter1;
@@ -2056,12 +2100,13 @@ OK_EXPORT int ok_xchg_count_device(ok_counter* c) {
     CU(cudaEventRecord(c->ev_p[2], c->s_main));      // part_finish times the level-2 scatter from here
     for (unsigned ch = sh.recv_chunks; ch < NC; ++ch) TRY(xchg_recv_chunk(c, ch, c->s_main));     // not overlapped: everything after the barrier
     CU(cudaMemcpyAsync(&c->h_part->received, sh.d_received, 8, cudaMemcpyDeviceToHost, c->s_main));
-    TRY(part_finish(c, pl, /*level2=*/false));
+    TRY(part_finish(c, pl, /*level2=*/sh.three));   // three-level form: the receive work was level 1, level 2 follows now
     c->ms_scatter1 = ms_scatter1;                     // measured by ok_xchg_scatter_device (part_finish re-read moved events)
-    if (overlapped) cudaEventElapsedTime(&c->ms_scatter2, sh.ev_recv[0], sh.ev_recv[1]);     // ran under the exchange (includes its waits)
+    if (overlapped && !sh.three) cudaEventElapsedTime(&c->ms_scatter2, sh.ev_recv[0], sh.ev_recv[1]);     // ran under the exchange (includes its waits)
     sh.recv_chunks = 0;
     c->ms_insert = c->ms_sample + c->ms_scatter1 + c->ms_push + c->ms_scatter2 + c->ms_count;
     c->windows = windows_before + c->h_part->received;
+    c->batch_windows = c->h_part->received;
     CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
     if (part_hint_misled(c, pl)) {
@@ -2072,7 +2117,7 @@ OK_EXPORT int ok_xchg_count_device(ok_counter* c) {
     }
     const int r = part_absorb_spills(c, windows_before);
     if (r == PART_RETRY) return set_err(OK_ERR_INTERNAL, "sharded count spilled beyond the spill list");
-    return r == OK_SUCCESS ? run_unstash(c) : r;
+    return r;       // an earlier batch's run stays set aside until ok_counter_commit_batch (the ranks agree first)
 }
 
 OK_EXPORT int ok_counter_finish_device(ok_counter* c, uint64_t min_count, const uint64_t** d_kmers,
@@ -2152,6 +2197,12 @@ OK_EXPORT int ok_counter_finish(ok_counter* c, uint64_t min_count, uint64_t** km
 // multi-GPU: the exchange of the batch in progress failed on some rank (a sampled region overflowed, a hint proved
 // too low) and every rank recounts it through another route.  Drops what this rank holds of THAT batch only;
 // the result of earlier batches (set aside while the batch was being counted) stays.
+OK_EXPORT int ok_counter_commit_batch(ok_counter* c) {
+    if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_commit_batch: NULL handle");
+    TRY(part_settle(c));
+    return run_unstash(c);
+}
+
 OK_EXPORT int ok_counter_abort_batch(ok_counter* c) {
     if (!c) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_counter_abort_batch: NULL handle");
     c->shard.xchg_pending = false;
@@ -2159,12 +2210,20 @@ OK_EXPORT int ok_counter_abort_batch(ok_counter* c) {
     if (c->shard.begun) { cudaStreamSynchronize(c->s_main); cudaStreamSynchronize(c->shard.s_join); c->shard.begun = false; }
     if (c->shard.s_recv) CU(cudaStreamSynchronize(c->shard.s_recv));
     c->shard.recv_chunks = 0;
-    if (c->run_state == RUN_LEVEL1) { CU(cudaStreamSynchronize(c->s_main)); c->run_state = RUN_NONE; }
-    if (c->run_state != RUN_NONE && c->n_acc) { c->run_state = RUN_NONE; c->n_run = 0; c->occupied = 0; }
+    // Whatever run the counter holds now belongs to the aborted batch (the result of earlier batches was set aside
+    // when the batch began and is only merged by ok_counter_commit_batch); its windows are taken back as well.
+    CU(cudaStreamSynchronize(c->s_main));
+    if (c->run_state != RUN_NONE) {
+        uint64_t w = 0;
+        if (c->run_state == RUN_SPARSE || c->run_state == RUN_DENSE) w = c->batch_windows;
+        c->windows = c->windows >= w ? c->windows - w : 0;
+        CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
+        c->run_state = RUN_NONE; c->n_run = 0; c->occupied = 0;
+    }
     CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
     c->h_stats->spill_n = 0;
-    return OK_SUCCESS;
+    return run_unstash(c);       // the set-aside run (if any) is the counter's result again
 }
 
 OK_EXPORT int ok_counter_set_capacity_hint(ok_counter* c, uint64_t capacity_hint) {

@@ -273,6 +273,7 @@ class ShardedCounter:
             self.counter.set_capacity_hint(0)      # every rank drops the hint: the geometry must stay collective
             self.hinted, self.geom = False, None
             return self._count_unfused(d_bases, n_bases, d_off, n_reads)
+        self.counter.commit_batch()         # every rank counted its share: merge into the result of earlier batches (if any)
         t4 = time.perf_counter()
         st = self.counter.stats()
         self.t = {"route_ms": (t2 - t0) * 1e3, "route_count_ms": (t1 - t0) * 1e3, "route_scatter_ms": (t2 - t1) * 1e3,
@@ -332,6 +333,7 @@ class ShardedCounter:
             self.counter.set_capacity_hint(0)      # every rank drops the hint: the geometry must stay collective
             self.hinted, self.geom = False, None
             return self._count_unfused(d_bases, n_bases, d_off, n_reads)
+        self.counter.commit_batch()         # every rank counted its share: merge into the result of earlier batches (if any)
         t4 = time.perf_counter()
         st = self.counter.stats()
         self.t = {"route_ms": (t2 - t0) * 1e3, "route_count_ms": (t1 - t0) * 1e3, "route_scatter_ms": (t2 - t1) * 1e3,

@@ -872,6 +872,7 @@ def _sharded_dance(counters, batches, n):
         keys, counts = [], []
         for r, c in enumerate(counters):
             c.shard_count_device(cur_all.data_ptr())
+            c.commit_batch()
             gk, gc = c.finish()
             assert c.stats()["n_spilled"] == 0
             keys.append(gk); counts.append(gc)
@@ -905,7 +906,7 @@ def test_sharded_scatter_matches_oracle(oracle, n_ranks, hint):
     assert np.array_equal(gc, wc)
 
 
-def _xchg_dance(counters, batches, n, stepwise=False):
+def _xchg_dance(counters, batches, n, stepwise=False, abort=False):
     """one step of the chunked exchange (ok_xchg_*) for every emulated rank; torch ops stand in for the collectives"""
     import torch
     n_ranks = len(counters)
@@ -943,6 +944,11 @@ def _xchg_dance(counters, batches, n, stepwise=False):
         keys, counts = [], []
         for r, c in enumerate(counters):
             c.xchg_count_device()
+        for r, c in enumerate(counters):
+            if abort:       # some rank failed (here: pretend): every rank drops its share of THIS batch, earlier batches stay
+                c.abort_batch()
+            else:
+                c.commit_batch()
             gk, gc = c.finish()
             assert c.stats()["n_spilled"] == 0
             keys.append(gk); counts.append(gc)
@@ -956,10 +962,13 @@ def _xchg_dance(counters, batches, n, stepwise=False):
 @pytest.mark.parametrize("n_ranks", [2, 4, 8])
 @pytest.mark.parametrize("hint", [0, 600_000])
 @pytest.mark.parametrize("chunks", [8, 1, 3])
-def test_chunked_exchange_matches_oracle(oracle, monkeypatch, n_ranks, hint, chunks):
-    """ok_xchg_*: per-chunk sub-blocks moved by plain peer copies, fills carried in the sub-block headers.  Ranks of
-    unequal batch size (the last one is short), twice through the same buffers."""
+@pytest.mark.parametrize("levels", [2, 3])
+def test_chunked_exchange_matches_oracle(oracle, monkeypatch, n_ranks, hint, chunks, levels):
+    """ok_xchg_*: per-chunk sub-blocks moved by plain peer copies, fills carried in the sub-block headers; once in one
+    call, once chunk by chunk with the receive work issued as the chunks land.  levels = 2: the sender splits by (owner,
+    level-1 bin), the owner runs level 2; levels = 3: the sender splits by owner only, the owner runs both levels."""
     monkeypatch.setenv("ORION_XCHG_CHUNKS", str(chunks))
+    monkeypatch.setenv("ORION_XCHG_LEVELS", str(levels))
     k = 31
     g = synth.genome(85, 400_000)
     n = 12_000
@@ -987,6 +996,11 @@ def test_chunked_exchange_second_batch_merges_into_the_shards(oracle):
     for r, c in enumerate(counters):
         c.set_shard(r, n_ranks)
     for i, batches in enumerate(rounds):
+        if i == 1:          # a batch that is counted and then aborted leaves the table of the earlier batches
+            gk, gc, _ = _xchg_dance(counters, rounds[2], n, abort=True)
+            wk, wc = oracle.count_batch(k, np.concatenate([b for b, _ in rounds[0]]), synth.read_offsets(n * n_ranks))
+            assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+            assert sum(c.stats()["n_windows"] for c in counters) == int(wc.sum())
         gk, gc, _ = _xchg_dance(counters, batches, n, stepwise=i == 1)
         assert all(c.stats()["n_merges"] == i for c in counters)
         all_bases = np.concatenate([b for rd in rounds[:i + 1] for b, _ in rd])
