@@ -1,7 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- bases/sec counted (canonical k=31), BASELINE.json's metric.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R] [--config 1..5]
+
+  --config 2 (default)   BASELINE.json configs[1]: 10 M x 150 bp reads per GPU, k = 31 (N > 1: weak scaling, sharded)
+  --config 1             configs[0]: one 5 Mbp genome, k = 21 (the reference's own CPU-runnable case)
+  --config 3             configs[2]: --total-reads (default 100 M) x 150 bp split over the N GPUs (strong), N >= 2
+  --config 4             configs[3]: build a database from --genomes genomes, query --query-reads reads (bench_sets.py)
+  --config 5             configs[4]: all-vs-all compare of --sets genome k-mer sets, k = 21 (bench_sets.py)
 
 A step = one whole count job over one batch of synthetic reads (BASELINE.json configs[1]:
 10M x 150 bp reads, k = 31): empty table -> extract + count every window -> sorted
@@ -249,6 +255,12 @@ def run_ours(args):
     numa_node = bind_to_gpu_numa_node(local)
     ok.init(local)
 
+    if args.config == 1:
+        return run_config1(args, ok, synth, torch, local)
+    if args.config in (4, 5):
+        return run_sets_config(args, torch, ok, synth, world, rank, local)
+    if args.config == 3 and world == 1:
+        raise SystemExit("--config 3 is the sharded job of BASELINE.json configs[2]: run it under torchrun with --gpus 2, 4 or 8")
     n_reads = args.reads
     genome_len = args.genome or n_reads * 5
     if world > 1:
@@ -415,6 +427,206 @@ def run_ours(args):
     counter.close()
 
 
+# ------------------------------------------------------------------------------ configs[0] --
+def run_config1(args, ok, synth, torch, local):
+    """one 5 Mbp genome record (10 runs of 100 N, 1 % lower case), k = 21: the whole table against the oracle"""
+    import oracle
+    oracle.build()
+    k = 21
+    g = synth.config1_genome()
+    off = np.array([0, len(g)], np.uint64)
+    bases, _ = pinned_array(ok, len(g), np.uint8)
+    bases[:] = g
+    d_b = torch.from_numpy(bases).cuda()
+    d_o = torch.from_numpy(off.view(np.int64)).cuda()
+    counter = ok.KmerCounter(k, ok.NORMALIZED, 0)
+
+    def step_device():
+        counter.clear()
+        counter.add_batch_device(d_b.data_ptr(), len(g), d_o.data_ptr(), 1)
+        return counter.finish_device(1)
+
+    def step_host():
+        counter.clear()
+        counter.add_batch_ptr(bases.ctypes.data, off.ctypes.data, 1)
+        pk, pc, n = counter.finish_raw(1)
+        counter.free_result(pk, pc)
+        return n
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ok.launch_count()
+    steps = max(args.steps, 20)                       # a step is ~1 ms: a few more for a stable clock sample
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_device()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    launches = (ok.launch_count() - launches0) // steps
+    clocks = sampler.stop()
+    st = counter.stats()
+    for _ in range(2):
+        step_host()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        n_out = step_host()
+    dt_e2e = (time.perf_counter() - t0) / steps
+    keys, counts = counter.finish(1)
+    t0 = time.perf_counter()
+    wk, wc = oracle.count_batch(k, g, off)
+    t_cpu = time.perf_counter() - t0
+    parity = bool(np.array_equal(keys, wk) and np.array_equal(counts, wc))
+    text_ok = ok.format_counts(keys[:1000], counts[:1000], k) == oracle.format_counts(wk[:1000], wc[:1000], k)
+    peak, peak_src = measured_peak()
+    alg = len(g) * 1.5 + st["n_windows"] * 16.0 + st["n_distinct"] * 32.0
+    line = {"metric": "bases/sec counted (canonical k=21)", "value": len(g) / dt, "unit": "bases/s", "n_gpus": 1, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "count canonical 21-mers in a single synthetic 5 Mbp genome record (BASELINE.json configs[0])",
+                       "k": k, "bases": int(len(g)), "n_runs": 10, "lower_case": "1 %", "seed": 1, "min_count": 1,
+                       "l2": "80 MB of keys against a 126 MB L2: partly L2-resident; the step is launch-latency bound (~15 launches)"},
+            "e2e": {"value": len(g) / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3, "h2d_bytes_per_step": int(len(g) + 16),
+                    "d2h_bytes_per_step": int(16 * n_out)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole step (a 5 Mbp genome is ~1 ms of launches; no kernel dominates)",
+                         "achieved": alg / dt / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / dt / 1e9 / peak, "peak_source": peak_src,
+                         "traffic": None, "algorithmic_bytes_per_launch": alg},
+            "phases_ms": {p[3:]: float(st[p]) for p in ("ms_sample", "ms_scatter1", "ms_scatter2", "ms_count", "ms_compact", "ms_insert", "ms_readout")},
+            "path": "partitioned" if st["partitioned"] else "table",
+            "table": {"windows": int(st["n_windows"]), "distinct": int(st["n_distinct"])},
+            "cpu_baseline": {"value": len(g) / t_cpu, "unit": "bases/s", "cores": 1, "kind": "port",
+                             "sample": f"the whole genome ({len(g)} bases), {t_cpu:.2f} s", "host_cores_available": os.cpu_count()},
+            "parity_full_table_ok": parity, "parity_tsv_text_ok": bool(text_ok)}
+    print(json.dumps(line))
+    counter.close()
+
+
+# ----------------------------------------------------- checkers of the set configurations (oracle) --
+def oracle_compare_sample(k, n_sets, length, sizes, inter, n_pairs):
+    """a few pairs of the all-vs-all against the oracle's compare (compare.rs:51-66); also the timed CPU baseline
+    (1 thread: the reference compares two databases per process, single-threaded)"""
+    import oracle
+    import bench_sets
+    from orion_kmer_b200 import synth
+    oracle.build()
+    cand = [(0, 1), (0, min(49, n_sets - 1)), (0, min(50, n_sets - 1)), (n_sets // 3, n_sets - 1), (n_sets // 2, n_sets // 2 + 1)]
+    pairs = [p for p in dict.fromkeys(cand) if p[0] != p[1]][:max(1, n_pairs)]
+    need = sorted({i for p in pairs for i in p})
+    osets = {i: oracle.kmer_set_batch(k, bench_sets.genome(synth, i, length), np.array([0, length], np.uint64)) for i in need}
+    ok_all, t = True, 0.0
+    for i, j in pairs:
+        t0 = time.perf_counter()
+        r = oracle.compare(osets[i], osets[j])
+        t += time.perf_counter() - t0
+        ok_all &= (r["db1"], r["db2"], r["intersection_size"]) == (int(sizes[i]), int(sizes[j]), int(inter[i, j]))
+        ok_all &= int(inter[j, i]) == int(inter[i, j]) and int(inter[i, i]) == int(sizes[i])
+    return {"ok": bool(ok_all), "pairs": [list(p) for p in pairs],
+            "cpu_baseline": {"value": len(pairs) / t, "unit": "pairs/s", "cores": 1, "kind": "port",
+                             "sample": f"{len(pairs)} pairs of {length}-base genome sets (hash one set, probe with the other), {t:.2f} s; "
+                                       "set construction not included", "host_cores_available": os.cpu_count()}}
+
+
+def oracle_query_sample(k, n_genomes, length, reads, roff, hits, n_reads, cpu_genomes):
+    """Parity of the build + union + query path at a size the CPU can check: the SAME library calls on a subset of
+    cpu_genomes genomes and n_reads reads against the oracle (build.rs:46-58, db_types.rs:43-48, query.rs:83-107);
+    properties of the full-size result; the timed CPU baseline (build: 1 thread; query: all cores, query.rs:78)."""
+    import oracle
+    import bench_sets
+    import orion_kmer_b200 as ok
+    from orion_kmer_b200 import synth
+    oracle.build()
+    subset = sorted({int(x) for x in np.linspace(0, n_genomes - 1, min(cpu_genomes, n_genomes))})
+    one = np.array([0, length], np.uint64)
+    t0 = time.perf_counter()
+    first = oracle.kmer_set_batch(k, bench_sets.genome(synth, subset[0], length), one)          # faithful single thread
+    t_build1 = time.perf_counter() - t0
+    nt = min(os.cpu_count() or 1, 64)
+    osets = [first] + [oracle.count_batch_ranged_mt(k, bench_sets.genome(synth, i, length), one, nt)[0] for i in subset[1:]]
+    ounion = np.unique(np.concatenate(osets))
+    r_n = min(n_reads, len(roff) - 1)
+    rb, ro = reads[:r_n * 150], roff[:r_n + 1]
+    t0 = time.perf_counter()
+    want = oracle.query_hits(ounion, k, rb, ro, nt)
+    t_query = time.perf_counter() - t0
+    gsets = []
+    for i in subset:
+        s = ok.KmerSet.build(k)
+        s.add_batch(bench_sets.genome(synth, i, length), one)
+        gsets.append(s)
+    gunion = ok.KmerSet.union(gsets)
+    got = gunion.probe_reads(rb, ro, ok.RAW)
+    same = bool(len(gunion) == len(ounion) and np.array_equal(got.astype(np.uint64), want)
+                and all(len(s) == len(o) for s, o in zip(gsets, osets)))
+    for s in gsets + [gunion]:
+        s.close()
+    # full-size properties: no read has more hits than windows; adding genomes can only add hits
+    props = bool(int(hits.max()) <= 150 - k + 1 and np.all(hits[:r_n].astype(np.uint64) >= want))
+    return {"ok": bool(same and props), "reads": int(r_n), "subset_genomes": len(subset),
+            "cpu_baseline": {"value": length / t_build1, "unit": "bases/s", "cores": 1, "kind": "port",
+                             "sample": f"build of 1 genome ({length} bases, 1 thread, {t_build1:.2f} s); query of {r_n} reads against the union of "
+                                       f"{len(subset)} genomes on {nt} threads: {r_n / t_query:.0f} reads/s",
+                             "query_reads_per_s": r_n / t_query, "query_cores": nt, "host_cores_available": os.cpu_count()}}
+
+
+def run_sets_config(args, torch, ok, synth, world, rank, local):
+    import bench_sets
+    ctx = {"ok": ok, "synth": synth, "torch": torch, "world": world, "rank": rank, "local": local, "ClockSampler": ClockSampler,
+           "measured_peak": measured_peak, "oracle_compare_sample": oracle_compare_sample, "oracle_query_sample": oracle_query_sample,
+           "pinned": lambda n: pinned_array(ok, n, np.uint8)[0]}
+    line = bench_sets.run_compare(args, ctx) if args.config == 5 else bench_sets.run_build_query(args, ctx)
+    bench_sets.emit(line)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference_sets(args):
+    """--impl reference for configs 4 / 5: the oracle port on a bounded sample, all the host threads the reference
+    itself would use (query.rs:78 is its only parallel loop)"""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n = args.sets if args.config == 5 else args.genomes
+    vals = []
+    for _ in range(args.warmup + args.steps):
+        if args.config == 5:
+            sizes = {}
+            chk = None
+            import oracle
+            import bench_sets
+            from orion_kmer_b200 import synth
+            oracle.build()
+            a = oracle.kmer_set_batch(21, bench_sets.genome(synth, 0, args.genome_len), np.array([0, args.genome_len], np.uint64))
+            b = oracle.kmer_set_batch(21, bench_sets.genome(synth, 1, args.genome_len), np.array([0, args.genome_len], np.uint64))
+            t0 = time.perf_counter()
+            for _ in range(3):
+                oracle.compare(a, b)
+            base = {"value": 3 / (time.perf_counter() - t0), "unit": "pairs/s", "cores": 1, "kind": "port",
+                    "sample": "3 compares of one pair of 5 Mbp genome sets"}
+        else:
+            import oracle
+            import bench_sets
+            from orion_kmer_b200 import synth
+            oracle.build()
+            g = bench_sets.genome(synth, 0, args.genome_len)
+            t0 = time.perf_counter()
+            oracle.kmer_set_batch(31, g, np.array([0, len(g)], np.uint64))
+            base = {"value": len(g) / (time.perf_counter() - t0), "unit": "bases/s", "cores": 1, "kind": "port",
+                    "sample": "build of 1 genome, single thread (build.rs:93-116 is sequential)"}
+        vals.append(base["value"])
+    v = float(np.mean(vals[args.warmup:]))
+    base["value"] = v
+    metric = ("set pairs compared per second (k=21 all-vs-all: |A|, |B|, |A n B| per pair; Jaccard on the host)" if args.config == 5
+              else "bases/sec through build + union + query (k=31)")
+    print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": base["unit"], "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                      "config": {"workload": f"BASELINE.json configs[{args.config - 1}] ({n} sets)"}, "cpu_baseline": base,
+                      "e2e": {"value": v, "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -426,11 +638,28 @@ def main():
     ap.add_argument("--hint", type=int, default=0, help="expected distinct k-mers per GPU")
     ap.add_argument("--sample-reads", type=int, default=250_000,
                     help="reads in the CPU baseline sample (250k = 37.5 M bases: ~10-20 s of single-thread CPU work)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs[config-1]")
+    ap.add_argument("--total-reads", type=int, default=0, help="config 3: reads of the whole job, split over the GPUs (default 100 M)")
+    ap.add_argument("--sets", type=int, default=256, help="config 5: genome sets")
+    ap.add_argument("--genomes", type=int, default=1000, help="config 4: genomes in the database")
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--query-reads", type=int, default=1_000_000, help="config 4: reads in the query sample")
+    ap.add_argument("--parity-pairs", type=int, default=5)
+    ap.add_argument("--parity-reads", type=int, default=20_000)
+    ap.add_argument("--cpu-genomes", type=int, default=12, help="config 4: genomes in the CPU-checked subset")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the parity check of the sharded table")
     ap.add_argument("--parity-seconds", type=float, default=60.0, help="N > 1: CPU budget of the key-slice check")
     args = ap.parse_args()
+    if args.config == 3:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        args.total_reads = args.total_reads or 100_000_000
+        args.reads = args.total_reads // max(1, world)
+        args.genome = args.genome or args.total_reads * 5 // max(1, world)      # multi.bench multiplies by world: 30x coverage of the whole job
     if args.impl == "reference":
-        run_reference(args)
+        if args.config in (4, 5):
+            run_reference_sets(args)
+        else:
+            run_reference(args)
     else:
         run_ours(args)
 

@@ -75,6 +75,8 @@ k_merge_count(const unsigned long long* __restrict__ a, const unsigned long long
     }
 }
 
+// COUNTS = false: keys only (union of two k-mer sets, db_types.rs:43-48): ac, bc and out_counts are not touched
+template <bool COUNTS>
 __global__ void __launch_bounds__(OK_MG_THREADS)
 k_merge_write(const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ ac,
               const unsigned long long* __restrict__ b, const unsigned long long* __restrict__ bc,
@@ -95,13 +97,13 @@ k_merge_write(const unsigned long long* __restrict__ a, const unsigned long long
         for (unsigned i = threadIdx.x; i < ca; i += OK_MG_THREADS) {
             const unsigned long long v = sm.sa[i];
             const unsigned r = i + ok_mg_lower(sm.sb, cb, v);
-            sm.mk[r] = v; sm.mc[r] = ac[s0.x + i];
+            sm.mk[r] = v; if (COUNTS) sm.mc[r] = ac[s0.x + i];
         }
         for (unsigned i = threadIdx.x; i < cb; i += OK_MG_THREADS) {
             const unsigned long long v = sm.sb[i];
             unsigned p = ok_mg_lower(sm.sa, ca, v);
             p += (p < ca && sm.sa[p] == v) ? 1u : 0u;            // #A elements <= v
-            sm.mk[i + p] = v; sm.mc[i + p] = bc[s0.y + i];
+            sm.mk[i + p] = v; if (COUNTS) sm.mc[i + p] = bc[s0.y + i];
         }
         __syncthreads();
         // an element equal to its predecessor is the B copy of a pair: its count goes to the predecessor
@@ -112,7 +114,7 @@ k_merge_write(const unsigned long long* __restrict__ a, const unsigned long long
             if (r < n) {
                 key = sm.mk[r];
                 keep = r == 0 || sm.mk[r - 1] != key;
-                cnt = sm.mc[r] + ((r + 1 < n && sm.mk[r + 1] == key) ? sm.mc[r + 1] : 0ull);
+                if (COUNTS) cnt = sm.mc[r] + ((r + 1 < n && sm.mk[r + 1] == key) ? sm.mc[r + 1] : 0ull);
             }
             const unsigned bal = __ballot_sync(OK_FULL, keep);
             if (lane == 0) sm.wsum[wid] = __popc(bal);
@@ -122,7 +124,7 @@ k_merge_write(const unsigned long long* __restrict__ a, const unsigned long long
             for (int w = 0; w < 8; ++w) { const unsigned x = sm.wsum[w]; woff += w < wid ? x : 0u; tot += x; }
             if (keep) {
                 const unsigned long long idx = sm.running + woff + __popc(bal & ((1u << lane) - 1u));
-                out_keys[idx] = key; out_counts[idx] = cnt;
+                out_keys[idx] = key; if (COUNTS) out_counts[idx] = cnt;
             }
             __syncthreads();
             if (threadIdx.x == 0) sm.running += tot;

@@ -897,7 +897,7 @@ int run_unstash(ok_counter* c) {
     TRY(dev_reserve(&c->d_tiles, &c->cap_tiles, n_tiles + 1));
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
     TRY(set_smem(k_merge_count, sizeof(OkMergeSmem)));
-    TRY(set_smem(k_merge_write, sizeof(OkMergeSmem)));
+    TRY(set_smem(k_merge_write<true>, sizeof(OkMergeSmem)));
     CU(cudaEventRecord(c->ev_a, c->s_main));
     LAUNCH(k_merge_partition, grid_for(n_tiles + 1), 256, 0, c->s_main, c->d_acc_keys, na, c->d_run_keys, nb, n_tiles, c->d_split);
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)grid_sm * 4));
@@ -910,7 +910,7 @@ int run_unstash(ok_counter* c) {
         TRY(dev_reserve(&c->d_mrg_keys, &c->cap_mrg_keys, total + total / 8));
         TRY(dev_reserve(&c->d_mrg_counts, &c->cap_mrg_counts, total + total / 8));
     }
-    LAUNCH(k_merge_write, blocks, OK_MG_THREADS, sizeof(OkMergeSmem), c->s_main, c->d_acc_keys, c->d_acc_counts, c->d_run_keys, c->d_run_counts,
+    LAUNCH(k_merge_write<true>, blocks, OK_MG_THREADS, sizeof(OkMergeSmem), c->s_main, c->d_acc_keys, c->d_acc_counts, c->d_run_keys, c->d_run_counts,
            c->d_split, n_tiles, c->d_tiles, c->d_mrg_keys, c->d_mrg_counts);
     CU(cudaEventRecord(c->ev_b, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
@@ -2282,7 +2282,8 @@ int take_builder(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_counter** 
 
 void give_builder(ok_counter* c) {
     if (!c) return;
-    if (c->n_shards == 1 && !c->buf1_external && ok_counter_clear(c) == OK_SUCCESS) {
+    const uint64_t footprint = (c->cap_buf1 + c->cap_buf2 + c->cap_run_keys + c->cap_run_counts + c->cap_acc_keys + c->cap_mrg_keys) * 8 + c->cap_bases;
+    if (c->n_shards == 1 && !c->buf1_external && footprint < (4ull << 30) && ok_counter_clear(c) == OK_SUCCESS) {      // multi-GB scratch goes back to the device
         std::lock_guard<std::mutex> lk(g_mu);
         if (g_spare_builders.size() < MAX_SPARE_BUILDERS) { g_spare_builders.push_back(c); return; }
     }
@@ -2479,6 +2480,42 @@ OK_EXPORT int ok_set_export(ok_set* s, uint64_t** kmers, uint64_t* n) {
     return OK_SUCCESS;
 }
 
+namespace {
+// union of two sealed sets by the keys-only merge (merge.cuh); -> a new sealed set
+int set_merge_keys(const ok_set* a, const ok_set* b, ok_set** out) {
+    *out = nullptr;
+    ok_set* u = new ok_set();
+    u->k = a->k; u->norm_mode = a->norm_mode; u->sealed = true; u->has_max = a->has_max | b->has_max;
+    ulonglong2* d_split = nullptr; unsigned long long* d_tiles = nullptr;
+    auto fail = [&](int code) { cudaFree(d_split); cudaFree(d_tiles); ok_set_destroy(u); return code; };
+#define CUM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(set_err(e_ == cudaErrorMemoryAllocation ? OK_ERR_OUT_OF_MEMORY : OK_ERR_CUDA, "CUDA error %s while merging two sets", cudaGetErrorName(e_))); } while (0)
+    CUM(cudaStreamCreateWithFlags(&u->st, cudaStreamNonBlocking));
+    const uint64_t na = a->n, nb = b->n, n_tiles = (na + nb + OK_MG_TILE - 1) / OK_MG_TILE;
+    CUM(cudaMalloc((void**)&d_split, (n_tiles + 1) * sizeof(ulonglong2)));
+    CUM(cudaMalloc((void**)&d_tiles, (n_tiles + 1) * 8));
+    if (set_smem(k_merge_count, sizeof(OkMergeSmem)) != OK_SUCCESS || set_smem(k_merge_write<false>, sizeof(OkMergeSmem)) != OK_SUCCESS) return fail(OK_ERR_CUDA);
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)grid_sm * 4));
+    LAUNCH(k_merge_partition, grid_for(n_tiles + 1), 256, 0, u->st, a->d_keys, na, b->d_keys, nb, n_tiles, d_split);
+    LAUNCH(k_merge_count, blocks, OK_MG_THREADS, sizeof(OkMergeSmem), u->st, a->d_keys, b->d_keys, d_split, n_tiles, d_tiles);
+    LAUNCH(k_scan_tiles, 1, 1024, 0, u->st, d_tiles, n_tiles, d_tiles + n_tiles);
+    unsigned long long total = 0;
+    CUM(cudaMemcpyAsync(&total, d_tiles + n_tiles, 8, cudaMemcpyDeviceToHost, u->st));
+    CUM(cudaStreamSynchronize(u->st));
+    if (total) CUM(cudaMalloc((void**)&u->d_keys, total * 8));
+    LAUNCH(k_merge_write<false>, blocks, OK_MG_THREADS, sizeof(OkMergeSmem), u->st, a->d_keys, (const unsigned long long*)nullptr, b->d_keys,
+           (const unsigned long long*)nullptr, d_split, n_tiles, d_tiles, u->d_keys, (unsigned long long*)nullptr);
+    CUM(cudaStreamSynchronize(u->st));
+    CUM(cudaGetLastError());
+#undef CUM
+    cudaFree(d_split); cudaFree(d_tiles);
+    u->n = total;
+    *out = u;
+    return OK_SUCCESS;
+}
+constexpr uint64_t UNION_GROUP_KEYS = 1200ull << 20;      // keys one pass of the partitioned path takes (32-bit offsets)
+}  // namespace
+
 OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
     if (!out || (n_sets && !sets)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_union: NULL argument");
     *out = nullptr;
@@ -2489,6 +2526,39 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
         if (sets[i]->k != sets[0]->k) return kmer_size_mismatch(sets[0]->k, sets[i]->k);
         TRY(set_seal(sets[i]));
         sum += sets[i]->n; has_max |= sets[i]->has_max;
+    }
+    uint64_t group_keys = UNION_GROUP_KEYS;
+    if (const char* ev = getenv("ORION_UNION_GROUP_KEYS")) { const long long v = atoll(ev); if (v > 0) group_keys = (uint64_t)v; }     // test hook
+    if (sum > group_keys && n_sets > 1) {
+        // more keys than one pass takes (1,000 genomes are 5e9): groups of sets, each group one pass, and the group
+        // results folded together with the keys-only merge -- every key is read and written once per fold step
+        ok_set* acc = nullptr;
+        uint64_t i = 0;
+        while (i < n_sets) {
+            uint64_t j = i, keys = 0;
+            while (j < n_sets && (j == i || keys + sets[j]->n <= group_keys)) keys += sets[j++]->n;
+            ok_set* g = nullptr;
+            int r;
+            if (j - i == 1) {      // one (large) set: it is its own union
+                r = ok_set_from_sorted_device((uint8_t)sets[i]->k, (const uint64_t*)sets[i]->d_keys, sets[i]->n, &g);
+                if (r == OK_SUCCESS) g->norm_mode = sets[i]->norm_mode;
+            } else {
+                r = ok_set_union(sets + i, j - i, &g);
+                if (r == OK_SUCCESS) r = set_seal(g);
+            }
+            if (r != OK_SUCCESS) { ok_set_destroy(g); ok_set_destroy(acc); return r; }
+            if (!acc) acc = g;
+            else {
+                ok_set* m = nullptr;
+                r = set_merge_keys(acc, g, &m);
+                ok_set_destroy(acc); ok_set_destroy(g);
+                if (r != OK_SUCCESS) return r;
+                acc = m;
+            }
+            i = j;
+        }
+        *out = acc;
+        return OK_SUCCESS;
     }
     ok_set* u = nullptr;
     TRY(ok_set_create((uint8_t)sets[0]->k, sets[0]->norm_mode, std::max<uint64_t>(sum, 1), &u));

@@ -576,9 +576,21 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
     hint = args.hint or int(n_bases * 0.17)       # expected distinct k-mers per rank (30x coverage, 0.5 % errors)
     sc = ShardedCounter(ok, torch, dist, K, fused=int(os.environ.get("ORION_FUSED", "3")), capacity_hint=hint)
 
+    # a rank's share may be more than one pass can take (32-bit offsets inside a batch): sub-batches of <= 11 M reads,
+    # each exchanged and counted on its own and merged into the rank's shard (reads are 150 bases: cuts at multiples
+    # of 8 reads keep the 16-byte alignment)
+    MAXR = 11_000_000
+    n_sub = (n_reads + MAXR - 1) // MAXR
+    per = ((n_reads + n_sub - 1) // n_sub + 7) // 8 * 8
+    cuts = [(a, min(n_reads, a + per)) for a in range(0, n_reads, per)]
+
+    def count_all():
+        for a, b in cuts:
+            sc.count_batch_device(d_bases[a * 150:b * 150], (b - a) * 150, d_off, b - a)
+
     def step_device():
         sc.clear()
-        sc.count_batch_device(d_bases, n_bases, d_off, n_reads)
+        count_all()
         return sc.counter.finish_device(1)
 
     def step_host():
@@ -586,7 +598,7 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
         d_bases.copy_(h_bases, non_blocking=True)
         d_off.copy_(h_off, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        sc.count_batch_device(d_bases, n_bases, d_off, n_reads)
+        count_all()
         pk, pc, n = sc.counter.finish_raw(1)
         sc.counter.free_result(pk, pc)
         return n
@@ -629,6 +641,8 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
         v_reads = n_reads if est_s <= budget_s else max(10_000, int(n_reads * budget_s / est_s))
         v_bases = v_reads * 150
         if v_reads != n_reads:
+            v_reads = min(v_reads, cuts[0][1])
+            v_bases = v_reads * 150
             sc.clear()
             sc.count_batch_device(d_bases, v_bases, d_off, v_reads)
         vb, vo = bases[:v_bases], off[:v_reads + 1]
@@ -655,9 +669,13 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
         nvlink_bytes = off_rank * 8.0
         line = {
             "metric": metric, "value": total_bases / dt, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong" if getattr(args, "config", 2) == 3 else "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(n_reads, genome_len, world),
+            "config": dict(workload_config(n_reads, genome_len, world), sub_batches_per_rank=len(cuts),
+                           **({"workload": f"count canonical 31-mers from {n_reads * world}x150bp synthetic reads key-range-sharded over "
+                                           f"{world} GPUs (BASELINE.json configs[2])", "total_reads": n_reads * world}
+                              if getattr(args, "config", 2) == 3 else {})),
             "e2e": {"value": total_bases / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3,
                     "h2d_bytes_per_step": int((n_bases + (n_reads + 1) * 8) * world),
                     "d2h_bytes_per_step": int(16 * distinct), "rank0_numa_node": numa_node},
