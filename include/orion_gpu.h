@@ -149,6 +149,11 @@ int ok_counter_route_scatter_device(ok_counter* c, const uint8_t* d_bases, uint6
 int ok_shard_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* sub_bits, uint32_t* l1_bits,
                       uint64_t* buffer_keys);
 int ok_shard_set_buffers(ok_counter* c, void* const* d_peer_buffers, uint64_t cap_keys);
+/* how many k-mers a rank may receive, as a multiple of the largest batch (default 1.25).  Owners are equal shares of
+ * the canonical-k-mer position, balanced for uniform base composition; the summed sample shows the real shares
+ * before anything is sent, and a skewed input (35 % GC: 1.6 x on one of 8 owners) needs a larger margin.  Take the
+ * geometry again afterwards. */
+int ok_shard_set_margin(ok_counter* c, double margin);
 int ok_shard_sample_device(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases,
                            const uint64_t* d_rec_offsets, uint64_t n_records, uint32_t* d_hist_fine,
                            uint32_t* d_hist_l1);

@@ -93,6 +93,7 @@ ABI = {
     "ok_counter_route_scatter_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp]),
     "ok_shard_geometry": (C.c_int, [vp, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), u64p]),
     "ok_shard_set_buffers": (C.c_int, [vp, vp, C.c_uint64]),
+    "ok_shard_set_margin": (C.c_int, [vp, C.c_double]),
     "ok_shard_sample_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
     "ok_shard_scatter_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, vp]),
     "ok_shard_count_device": (C.c_int, [vp, vp]),
@@ -465,6 +466,9 @@ class KmerCounter:
         sb, lb, cap = C.c_uint32(), C.c_uint32(), C.c_uint64()
         _check(lib().ok_shard_geometry(self._h, n_bases_max, C.byref(sb), C.byref(lb), C.byref(cap)))
         return sb.value, lb.value, cap.value
+
+    def shard_set_margin(self, margin):
+        _check(lib().ok_shard_set_margin(self._h, margin))
 
     def shard_set_buffers(self, peer_ptrs, cap_keys):
         arr = (vp * len(peer_ptrs))(*[int(p) for p in peer_ptrs])

@@ -154,6 +154,7 @@ struct ShardState {
     // the exchange).  rb1 / rb2: the owner's level bits; b1 (sender-side level-1 bits) is 0 then.
     bool three = false;
     unsigned rb1 = 0, rb2 = 0;
+    double margin = 1.25;                    // what a rank may receive, as a multiple of the largest batch (ok_shard_set_margin)
     uint64_t recv_cap = 0;                   // keys every peer-mapped buffer holds
     unsigned long long* d_send = nullptr; uint64_t cap_send = 0;   // sub-blocks for the other owners, built locally
     unsigned* d_xchg = nullptr;              // cur | end | beg (sender side), rbeg | rend | rfill (receiver side): n_chunks x 1024 each; then hdr_send | hdr_recv: n_chunks x 8
@@ -1564,7 +1565,7 @@ OK_EXPORT int ok_shard_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* s
     ShardState& sh = c->shard;
     sh.g = 0; for (int g = c->n_shards; g > 1; g >>= 1) ++sh.g;
     // what a rank receives is balanced by the canonical prior: plan for 1.25 x the largest batch
-    const uint64_t n_units = n_bases_max + n_bases_max / 4;
+    const uint64_t n_units = (uint64_t)((double)n_bases_max * c->shard.margin);
     PartPlan pl;
     part_choose_bits(c, n_bases_max, pl, /*use_hint=*/true);
     sh.hinted = pl.hinted;
@@ -1587,6 +1588,16 @@ OK_EXPORT int ok_shard_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* s
     }
     sh.ready = true; sh.buffers = false;
     *sub_bits = sh.sub_bits; *l1_bits = sh.b1; *buffer_keys = sh.cap_keys;
+    return OK_SUCCESS;
+}
+
+// What a rank receives is balanced by the canonical-k-mer prior: exactly for uniform base composition, within a few
+// per cent for repeats and microsatellites, but a 35 %-GC genome puts 1.6 x the mean on one of 8 owners
+// (tools/skew.py).  The caller learns the real shares from the summed sample (before anything is sent) and can
+// raise the margin; the geometry must be taken again afterwards.
+OK_EXPORT int ok_shard_set_margin(ok_counter* c, double margin) {
+    if (!c || !(margin >= 1.0 && margin <= 8.0)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_shard_set_margin: margin must be in [1, 8]");
+    c->shard.margin = margin; c->shard.ready = false;
     return OK_SUCCESS;
 }
 
@@ -1666,7 +1677,7 @@ OK_EXPORT int ok_shard_scatter_device(ok_counter* c, const uint8_t* d_bases, uin
     PartPlan& pl = c->pl; pl = PartPlan{};
     pl.cfg.key_shift = 64 - 2 * c->k; pl.cfg.shard_log2 = sh.g; pl.cfg.b1 = sh.b1; pl.cfg.b2 = sh.b2;
     pl.n_sub = 1u << sh.sub_bits; pl.n_bin1 = 1u << sh.b1; pl.stride = sh.stride; pl.sharded = true;
-    const uint64_t n_units = sh.n_bases_max + sh.n_bases_max / 4;
+    const uint64_t n_units = (uint64_t)((double)sh.n_bases_max * sh.margin);
     pl.hinted = sh.hinted;
     pl.big_count = sh.hinted ? std::min<uint64_t>(c->user_hint, sh.n_bases_max) / pl.n_sub > 4600     // expected distinct keys per sub-partition
                              : sh.n_bases_max / pl.n_sub > 5800;     // what arrives is balanced: about one batch worth of k-mers
@@ -1798,7 +1809,7 @@ OK_EXPORT int ok_xchg_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* su
         part_choose_bits(c, n_bases_max, pl, /*use_hint=*/true);
         sh.hinted = pl.hinted;
         sh.rb1 = pl.cfg.b1; sh.rb2 = pl.cfg.b2; sh.sub_bits = pl.cfg.b1 + pl.cfg.b2; sh.b1 = 0; sh.b2 = sh.sub_bits;
-        sh.cap_keys = n_bases_max + n_bases_max / 4 + 4096;        // raw keys; the per-region slack is added below
+        sh.cap_keys = (uint64_t)((double)n_bases_max * sh.margin) + 4096;        // raw keys; the per-region slack is added below
         *sub_bits = sh.sub_bits; *l1_bits = 0;
     }
     unsigned nc = 8;
@@ -1809,7 +1820,7 @@ OK_EXPORT int ok_xchg_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* su
     // a sub-block carries a header and every region its own 6-sigma slack: n_chunks x senders x bins regions per owner
     const uint64_t regions = (uint64_t)nc << (sh.g + sh.b1);
     sh.cap_keys += regions * (200ull + 10ull * sh.stride) +
-                   (uint64_t)(6.0 * std::sqrt((double)sh.stride) * std::sqrt((double)regions * ((double)(n_bases_max + n_bases_max / 4) + (double)regions * sh.stride)));
+                   (uint64_t)(6.0 * std::sqrt((double)sh.stride) * std::sqrt((double)regions * (((double)n_bases_max * sh.margin) + (double)regions * sh.stride)));
     if (sh.cap_keys >= (1ull << 32)) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_geometry: batch too large for 32-bit offsets");
     if (!sh.d_xchg) CU(cudaMalloc((void**)&sh.d_xchg, (6 * 8 * XCHG_STRIDE + 2 * 8 * 8) * sizeof(unsigned)));
     // with few peers one copy per (peer, chunk) leaves copy engines idle (measured at 2 GPUs: 500 GB/s on one stream):
@@ -1879,7 +1890,7 @@ int xchg_begin(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const ui
     PartPlan& pl = c->pl; pl = PartPlan{};
     pl.cfg.key_shift = 64 - 2 * c->k; pl.cfg.shard_log2 = sh.g; pl.cfg.b1 = sh.rb1; pl.cfg.b2 = sh.rb2;
     pl.n_sub = 1u << sh.sub_bits; pl.n_bin1 = 1u << sh.rb1; pl.stride = sh.stride; pl.sharded = !sh.three;
-    const uint64_t n_units = sh.n_bases_max + sh.n_bases_max / 4;
+    const uint64_t n_units = (uint64_t)((double)sh.n_bases_max * sh.margin);
     pl.hinted = sh.hinted;
     pl.big_count = sh.hinted ? std::min<uint64_t>(c->user_hint, sh.n_bases_max) / pl.n_sub > 4600 : sh.n_bases_max / pl.n_sub > 5800;
     if (const char* ev = getenv("ORION_BIG_COUNT")) pl.big_count = atoi(ev) != 0;
@@ -1952,7 +1963,12 @@ int xchg_begin(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, const ui
     TRY(set_smem(kern, sizeof(OkScatterSmem)));
     const OkPartCfg cfg = shard_global_cfg(c, sh.b1);      // scatter bin id = (owner, sender-side level-1 bin)
     size_t next_copy = 0;
-    std::sort(copies.begin(), copies.end(), [](const Copy& a, const Copy& b) { return a.chunk != b.chunk ? a.chunk < b.chunk : a.peer < b.peer; });
+    // Issue order matters: the copy engines take the copies roughly in the order they were enqueued, whatever their
+    // streams.  With every sender starting at owner 0 all ranks hit the same destination at once and its ingress caps
+    // the whole exchange (measured: 320 GB/s per GPU; staggered, tools/nvlink_a2a_mp reaches 700).  Sender s starts at
+    // owner s+1: at any moment the copies in flight form a permutation.
+    std::sort(copies.begin(), copies.end(), [&](const Copy& a, const Copy& b) {
+        return a.chunk != b.chunk ? a.chunk < b.chunk : (a.peer + W - me) % W < (b.peer + W - me) % W; });
     for (unsigned ch = 0; ch < NC; ++ch) {
         const uint64_t t0 = ch * per_chunk, t1 = std::min<uint64_t>(n_tiles, t0 + per_chunk);
         if (t1 > t0 && n_records) {

@@ -151,6 +151,7 @@ class ShardedCounter:
         #    extraction kernel pushes with SM stores); 1: two-pass fused route; 0: NCCL all-to-all
         self.fused = int(fused)
         self.fallbacks = 0
+        self.margin = 1.25      # what a rank may receive, as a multiple of the largest batch (raised when the sample says so)
         # overlap the owner's level-2 scatter with the exchange of the later chunks (chunk-wise host barrier)
         self.overlap = not os.environ.get("ORION_XCHG_NO_OVERLAP")
         self.flags = HostFlags(dist, self.coll) if self.fused == 3 and self.overlap else None
@@ -227,6 +228,15 @@ class ShardedCounter:
         self.coll.reduce_scatter(g["hist_mine"], g["hist_fine"])
         self.coll.all_gather(g["l1c_all"], g["hist_l1c"])
         h_l1c_all = g["l1c_all"].cpu().numpy().view(np.uint32)       # the layout is planned on the host, identically on every rank
+        # what every owner will receive is known now (sampled): a skewed input (35 % GC: 1.6 x the mean on one of 8
+        # owners) needs more room than the default margin -- agree on a larger one and take the geometry again
+        recv_est = h_l1c_all.reshape(W, g["n_chunks"], W, -1).sum(axis=(0, 1, 3)).astype(np.float64) * 16.0
+        need = float(recv_est.max()) * 1.08 / max(1, nmax)
+        if need > self.margin:
+            self.margin = min(8.0, need * 1.1)
+            self.counter.shard_set_margin(self.margin)
+            self.geom = None
+            return self._count_xchg(d_bases, n_bases, d_off, n_reads)
         t1 = time.perf_counter()
         ok_flag = 1
         try:

@@ -472,6 +472,30 @@ def test_key_range_shards_add_up_to_the_whole(oracle):
         ok.KmerSet.from_sorted_device(k, bad.data_ptr(), 4)
 
 
+def test_union_in_groups_matches_oracle(oracle, monkeypatch):
+    """db_types.rs:43-48 for more keys than one pass of the partitioned path takes (1,000 genomes are 5e9 keys): groups
+    of sets are unified one pass each and the group results folded with the keys-only merge.  The group size is
+    shrunk so that the oracle can check it."""
+    k = 31
+    base = synth.genome(45, 300_000)
+    gens = [base, synth.mutate(base, 3, 40_000), synth.genome(46, 50_000), base[:50_000], synth.genome(47, 5_000), base[100_000:250_000]]
+    sets = [ok.KmerSet.from_fastx(k, synth.fasta_text(b"g%d" % i, g)) for i, g in enumerate(gens)]
+    osets = [oracle.kmer_set_batch(k, g, np.array([0, len(g)], np.uint64)) for g in gens]
+    want = oracle.set_union(osets)
+    for group in (400_000, 120_000, 10_000_000):
+        monkeypatch.setenv("ORION_UNION_GROUP_KEYS", str(group))
+        u = ok.KmerSet.union(sets)
+        assert np.array_equal(u.to_array(), want), group
+        assert u.probe_counts(want[::7], np.ones(len(want[::7]), np.uint64)) == (len(want[::7]), len(want[::7]))
+        u.close()
+    # foreign k = 32 sets holding u64::MAX, folded
+    monkeypatch.setenv("ORION_UNION_GROUP_KEYS", "3")
+    a = ok.KmerSet.from_sorted(32, np.array([1, 5, 2 ** 64 - 1], np.uint64))
+    b = ok.KmerSet.from_sorted(32, np.array([5, 9], np.uint64))
+    c = ok.KmerSet.from_sorted(32, np.array([0, 9, 2 ** 64 - 1], np.uint64))
+    assert list(ok.KmerSet.union([a, b, c]).to_array()) == [0, 1, 5, 9, 2 ** 64 - 1]
+
+
 def test_intersection_tiled_kernel_shapes():
     """k_intersect_bounds + k_intersect_tiled against numpy on shapes that stress the tiling: equal sets, disjoint
     ranges, a small set inside a large one (one tile of A against hundreds of chunks of B), interleaved keys, tile
