@@ -131,6 +131,9 @@ struct PartPlan {
     unsigned long long* chunk_sum = nullptr; // per-1024-chunk totals of the two-launch scans
     OkPartScalars* scal = nullptr;
     unsigned* bin_first = nullptr;           // first level-2 work item of every level-1 bin (+ the total)
+    unsigned long long* lb = nullptr;        // look-back words of the dense count (one per sub-partition)
+    unsigned* ticket = nullptr;              // sub-partition ticket of the dense count kernel
+    uint64_t dense_cap = 0;                  // entries d_run_keys / d_run_counts hold for the dense attempt (0: sparse only)
     unsigned n_slices = 0, slice_step = 0;   // result slices: sub-partitions [i*step, (i+1)*step)
 };
 
@@ -181,6 +184,7 @@ struct PartHost {                            // page-locked mirror of the batch'
     unsigned long long received;             // sharded path: k-mers the peers wrote into this rank's buffer
     unsigned long long slice0_windows;       // sliced result pipeline: windows held by the first slice
     unsigned long long windows_now;          //   ... and by the whole batch
+    unsigned dense_failed;                   // the dense count met a sub-partition it could not finish (zero-copy store)
 };
 
 struct ok_counter {
@@ -504,13 +508,15 @@ int part_layout(ok_counter* c, uint64_t n_units, uint64_t unit_chunk, uint64_t f
     const uint64_t o_scan = take(2 * (n_sub + 2)), o_chunk = take(2 * (n_sub / 1024 + 2)), o_scal = take(sizeof(OkPartScalars) / 4), o_hist = take(n_sub), o_beg = take(n_sub),
                    o_cur = take(n_sub), o_end = take(n_sub), o_def = take(n_sub), o_b1 = take(OK_PART_MAXBINS),
                    o_c1 = take(OK_PART_MAXBINS), o_e1 = take(OK_PART_MAXBINS), o_io = take(pl.max_items),
-                   o_in = take(pl.max_items), o_ib = take(pl.max_items), o_bf = take(OK_PART_MAXBINS + 1);
+                   o_in = take(pl.max_items), o_ib = take(pl.max_items), o_bf = take(OK_PART_MAXBINS + 1),
+                   o_lb = take(2 * (n_sub + 2)), o_tk = take(4);
     TRY(dev_reserve(&c->d_meta, &c->cap_meta, words));
     unsigned* m = c->d_meta;
     pl.scan = (unsigned long long*)(m + o_scan); pl.chunk_sum = (unsigned long long*)(m + o_chunk); pl.scal = (OkPartScalars*)(m + o_scal);
     pl.hist = m + o_hist; pl.beg = m + o_beg; pl.cursor = m + o_cur; pl.cap_end = m + o_end; pl.deferred = m + o_def;
     pl.beg1 = m + o_b1; pl.cursor1 = m + o_c1; pl.end1 = m + o_e1;
     pl.item_off = m + o_io; pl.item_n = m + o_in; pl.item_bin = m + o_ib; pl.bin_first = m + o_bf;
+    pl.lb = (unsigned long long*)(m + o_lb); pl.ticket = m + o_tk;
     TRY(dev_reserve(&c->d_buf2, &c->cap_buf2, pl.cap_bound + 16));
     if (c->buf1_external) {
         if (c->cap_buf1 < pl.cap_bound + 16) return set_err(OK_ERR_INVALID_ARGUMENT, "the peer buffer is too small for this batch (%llu < %llu keys)",
@@ -543,7 +549,8 @@ void part_launch_items(ok_counter* c, PartPlan& pl) {
 // the sub-partitions per level-1 bin).  Sorted runs land in place (keys in d_buf2, counts in
 // d_buf1); pl.scan[p] = output offset of sub-partition p; host_total (page-locked, optional)
 // receives the running total of distinct k-mers after this range.
-int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, bool whole, unsigned long long* host_total, bool level2 = true) {
+int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, bool whole, unsigned long long* host_total, bool level2 = true,
+                      bool dense = false) {
     const OkPartSpill ps{c->spill, c->d_stats};
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
     if (pl.cfg.b2 > 0 && level2) {
@@ -561,23 +568,31 @@ int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, boo
     // count every sub-partition in shared memory; sorted runs land in place, counts in d_buf1
     unsigned* d_nd = pl.hist;   // the sample histogram is no longer needed (k_part_plan zeroed it)
     unsigned* cnt_out = reinterpret_cast<unsigned*>(c->buf1_external ? c->d_cnt : c->d_buf1);   // 32-bit counts, same indices as the keys
+    OkDenseOut dn{};
+    if (dense) {
+        dn.lb = pl.lb; dn.keys = c->d_run_keys; dn.counts = c->d_run_counts; dn.cap = pl.dense_cap; dn.ticket = pl.ticket;
+        dn.failed = &c->h_part_dev->dense_failed;
+        CU(cudaMemsetAsync(pl.ticket, 0, sizeof(unsigned), c->s_main));
+    }
     if (pl.big_count) {
         auto k_cnt = OK_BY_K(c->k, k_part_count, 14);
         TRY(set_smem(k_cnt, sizeof(OkCount2Smem<14>)));
         LAUNCH(k_cnt, std::min<unsigned>(p1 - p0, grid_sm), OkCount2Cfg<14>::THREADS, sizeof(OkCount2Smem<14>), c->s_main,
                c->d_buf2, pl.beg, pl.cursor, pl.cap_end, p0, p1, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal,
-               (g_count_seed & 1) ? OkCount2Cfg<14>::THREADS : 0u, (g_count_seed & 2) != 0);
+               (g_count_seed & 1) ? OkCount2Cfg<14>::THREADS : 0u, (g_count_seed & 2) != 0, dn);
     } else {
         auto k_cnt = OK_BY_K(c->k, k_part_count, 13);
         TRY(set_smem(k_cnt, sizeof(OkCount2Smem<13>)));
         LAUNCH(k_cnt, std::min<unsigned>(p1 - p0, grid_sm * 2), OkCount2Cfg<13>::THREADS, sizeof(OkCount2Smem<13>), c->s_main,
                c->d_buf2, pl.beg, pl.cursor, pl.cap_end, p0, p1, pl.cfg, cnt_out, d_nd, pl.deferred, pl.scal,
-               (g_count_seed & 1) ? OkCount2Cfg<13>::THREADS : 0u, (g_count_seed & 2) != 0);
+               (g_count_seed & 1) ? OkCount2Cfg<13>::THREADS : 0u, (g_count_seed & 2) != 0, dn);
     }
-    const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
-    TRY(set_smem(k_part_count_generic, ct_smem));
-    LAUNCH(k_part_count_generic, grid_sm, OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg, pl.cursor, pl.cap_end,
-           pl.deferred, pl.scal, pl.cfg, cnt_out, d_nd, ps);
+    if (!dense) {        // (a dense attempt with a deferred sub-partition has failed as a whole: the range is recounted sparse)
+        const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
+        TRY(set_smem(k_part_count_generic, ct_smem));
+        LAUNCH(k_part_count_generic, grid_sm, OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg, pl.cursor, pl.cap_end,
+               pl.deferred, pl.scal, pl.cfg, cnt_out, d_nd, ps);
+    }
     if (whole) CU(cudaEventRecord(c->ev_p[4], c->s_main));
     const unsigned chunk0 = p0 / 1024u, n_chunks = (p1 - p0 + 1023u) / 1024u;
     LAUNCH(k_part_scan_sums, n_chunks, 1024, 0, c->s_main, d_nd, pl.n_sub, pl.chunk_sum, chunk0);
@@ -588,10 +603,42 @@ int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, boo
 // level 2 + count + scan, shared by the two entry points.  The keys are already scattered into
 // level-1 bins in d_buf1 (b2 > 0) or straight into sub-partitions in d_buf2 (b2 == 0).  Leaves
 // the result as sorted sub-partition runs (RUN_SPARSE); compaction happens when it is asked for.
+// The count kernel writes the dense result itself (OkDenseOut): reserve the outputs and clear the look-back words.
+// Capacity: every window could be a distinct k-mer, so without a capacity hint the outputs are sized for the
+// windows; with one, for the hint + 25 % -- a result that outgrows them fails the attempt (recounted sparse).
+int part_dense_prepare(ok_counter* c, PartPlan& pl) {
+    static const bool off = getenv("ORION_NO_DENSE") != nullptr;      // A/B knob: sorted runs in place + compaction pass
+    pl.dense_cap = 0;
+    if (off) return OK_SUCCESS;
+    uint64_t cap = pl.cap_bound;
+    if (c->user_hint && !c->distrust_hint) cap = std::min<uint64_t>(cap, c->user_hint + c->user_hint / 4 + (1ull << 20));
+    TRY(dev_reserve(&c->d_run_keys, &c->cap_run_keys, cap));
+    TRY(dev_reserve(&c->d_run_counts, &c->cap_run_counts, cap));
+    CU(cudaMemsetAsync(pl.lb, 0, (size_t)pl.n_sub * 8, c->s_main));
+    c->h_part->dense_failed = 0;
+    pl.dense_cap = cap;
+    return OK_SUCCESS;
+}
+
+// a dense attempt failed (a sub-partition was deferred, or the result outgrew the outputs): count [0, n_sub) again in
+// the sparse form.  The dense pass left the sub-partitions (d_buf2) untouched.
+int part_recount_sparse(ok_counter* c, PartPlan& pl) {
+    CU(cudaMemsetAsync(&pl.scal->n_deferred, 0, sizeof(unsigned), c->s_main));
+    CU(cudaMemsetAsync(&pl.scal->def_done, 0, sizeof(unsigned), c->s_main));
+    pl.dense_cap = 0;
+    return part_launch_range(c, pl, 0, pl.n_sub, true, nullptr, /*level2=*/false, /*dense=*/false);
+}
+
 int part_finish(ok_counter* c, PartPlan& pl, bool level2 = true) {
     // level2 == false: the caller has already run the level-2 scatter (chunk by chunk: ok_xchg_count_device)
     if (level2) part_launch_items(c, pl);
-    TRY(part_launch_range(c, pl, 0, pl.n_sub, true, nullptr, level2));
+    TRY(part_dense_prepare(c, pl));
+    bool dense = pl.dense_cap != 0;
+    TRY(part_launch_range(c, pl, 0, pl.n_sub, true, nullptr, level2, dense));
+    if (dense) {
+        CU(cudaStreamSynchronize(c->s_main));
+        if (c->h_part->dense_failed) { dense = false; TRY(part_recount_sparse(c, pl)); }
+    }
     CU(cudaEventRecord(c->ev_p[5], c->s_main));
     // the one host round trip of the batch: totals, slice boundaries of the result, statistics
     const unsigned step = std::max<unsigned>(1, pl.n_sub / RESULT_SLICES);
@@ -612,7 +659,7 @@ int part_finish(ok_counter* c, PartPlan& pl, bool level2 = true) {
     c->ms_compact = 0;
     c->ms_insert = c->ms_sample + c->ms_scatter1 + c->ms_scatter2 + c->ms_count;
     c->ms_readout = 0;
-    c->n_run = c->h_part->total; c->run_state = RUN_SPARSE;
+    c->n_run = c->h_part->total; c->run_state = dense ? RUN_DENSE : RUN_SPARSE;
     c->n_deferred = c->h_part->scal.n_deferred;
     c->occupied = c->n_run;
     return OK_SUCCESS;
@@ -1012,9 +1059,11 @@ int part_finish_sliced(ok_counter* c, uint64_t** kmers, uint64_t** counts, uint6
     cudaEvent_t* ev_scan = c->ev_chunks.data();
     cudaEvent_t* ev_comp = c->ev_chunks.data() + n_slices;
     part_launch_items(c, pl);
+    TRY(part_dense_prepare(c, pl));
+    const bool dense = pl.dense_cap != 0;      // the count kernel writes the dense result: a slice ships as soon as it is counted
     auto issue = [&](unsigned i) -> int {
         const unsigned p0 = i * step, p1 = p0 + step;
-        TRY(part_launch_range(c, pl, p0, p1, false, &hd->slice_base[i + 1]));
+        TRY(part_launch_range(c, pl, p0, p1, false, &hd->slice_base[i + 1], true, dense));
         if (i == 0) LAUNCH(k_part_slice_fill, 1, 1024, 0, c->s_main, pl.beg, pl.cursor, pl.cap_end, 0u, p1, &hd->slice0_windows);
         CU(cudaEventRecord(ev_scan[i], c->s_main));
         return OK_SUCCESS;
@@ -1044,23 +1093,34 @@ int part_finish_sliced(ok_counter* c, uint64_t** kmers, uint64_t** counts, uint6
             if (w0 > 0) est = std::max(est, d0 * (w_all / w0));
             est = std::min(est * 1.04 + 262144.0, std::max(w_all, d0) + 16.0);   // distinct <= windows
             cap = (uint64_t)est;
+            if (dense) cap = std::min<uint64_t>(cap, pl.dense_cap);
             TRY(pool_alloc(&hk, cap * 8));
             TRY(pool_alloc(&hc, cap * 8));
-            TRY(dev_reserve(&c->d_run_keys, &c->cap_run_keys, cap));
-            TRY(dev_reserve(&c->d_run_counts, &c->cap_run_counts, cap));
+            if (!dense) {
+                TRY(dev_reserve(&c->d_run_keys, &c->cap_run_keys, cap));
+                TRY(dev_reserve(&c->d_run_counts, &c->cap_run_counts, cap));
+            }
         }
-        if (shipping && o1 > cap) shipping = false;
+        if (shipping && (o1 > cap || (dense && *(volatile unsigned*)&h->dense_failed))) shipping = false;
         if (shipping && o1 > o0) {
-            CU(cudaStreamWaitEvent(c->s_aux, ev_scan[i], 0));
-            launch_compact(c, i * step, (i + 1) * step, c->d_run_keys, c->d_run_counts, c->s_aux);
-            CU(cudaEventRecord(ev_comp[i], c->s_aux));
-            CU(cudaStreamWaitEvent(c->s_copy, ev_comp[i], 0));
+            if (dense) {
+                CU(cudaStreamWaitEvent(c->s_copy, ev_scan[i], 0));
+            } else {
+                CU(cudaStreamWaitEvent(c->s_aux, ev_scan[i], 0));
+                launch_compact(c, i * step, (i + 1) * step, c->d_run_keys, c->d_run_counts, c->s_aux);
+                CU(cudaEventRecord(ev_comp[i], c->s_aux));
+                CU(cudaStreamWaitEvent(c->s_copy, ev_comp[i], 0));
+            }
             CU(cudaMemcpyAsync((uint64_t*)hk + o0, c->d_run_keys + o0, (o1 - o0) * 8, cudaMemcpyDeviceToHost, c->s_copy));
             CU(cudaMemcpyAsync((uint64_t*)hc + o0, c->d_run_counts + o0, (o1 - o0) * 8, cudaMemcpyDeviceToHost, c->s_copy));
         }
         if (i + 2 < n_slices) TRY(issue(i + 2));
     }
+    CU(cudaStreamSynchronize(c->s_main));
+    const bool dense_ok = dense && !h->dense_failed;
+    if (dense && !dense_ok) { shipping = false; TRY(part_recount_sparse(c, pl)); }      // a deferred sub-partition: everything again, sparse
     CU(cudaMemcpyAsync(&h->scal, pl.scal, sizeof(OkPartScalars), cudaMemcpyDeviceToHost, c->s_main));
+    if (dense && !dense_ok) CU(cudaMemcpyAsync(&h->slice_base[n_slices], pl.scan + pl.n_sub, 8, cudaMemcpyDeviceToHost, c->s_main));
     TRY(read_stats(c));   // synchronises the compute stream
     CU(cudaStreamSynchronize(c->s_aux));
     CU(cudaStreamSynchronize(c->s_copy));
@@ -1071,7 +1131,7 @@ int part_finish_sliced(ok_counter* c, uint64_t** kmers, uint64_t** counts, uint6
     c->ms_insert = c->ms_readout = 0;
     c->n_run = total; c->occupied = total;
     c->n_deferred = h->scal.n_deferred;
-    c->run_state = RUN_SPARSE;
+    c->run_state = dense_ok ? RUN_DENSE : RUN_SPARSE;
     const bool spilled = c->h_stats->spill_n != 0;
     if (part_hint_misled(c, pl)) {       // see part_hint_misled: count the batch again, sized from its windows
         TRY(part_discard(c, c->pend_windows_before));
@@ -1798,7 +1858,9 @@ OK_EXPORT int ok_xchg_geometry(ok_counter* c, uint64_t n_bases_max, uint32_t* su
     if (!n_chunks) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_xchg_geometry: NULL argument");
     TRY(ok_shard_geometry(c, n_bases_max, sub_bits, l1_bits, buffer_keys));
     ShardState& sh = c->shard;
-    sh.three = c->n_shards >= 4;
+    // measured at 8 GPUs (profiles/r2_*): two levels 33.0 ms per step, three levels 35.8 -- the extra pass over the
+    // received keys costs more than the friendlier runs save; the three-level form stays selectable (ORION_XCHG_LEVELS=3)
+    sh.three = false;
     if (const char* ev = getenv("ORION_XCHG_LEVELS")) sh.three = atoi(ev) == 3;
     sh.rb1 = sh.b1; sh.rb2 = sh.b2;
     if (sh.three) {

@@ -868,7 +868,7 @@ template <int LOG2> struct OkCount2Smem {
     unsigned short newl[C::MAXKEYS];               // table slots of the distinct keys, in claim order
     unsigned short sidx[C::MAXKEYS];               // the same, grouped by bucket
     unsigned boff[C::BUCKETS];                     // bucket histogram -> bucket end offsets
-    unsigned wsum[34];
+    unsigned wsum[36];                             // [0..31] warp sums, [32..33] the CTA's dense base (u64), [34] its ticket
     unsigned n_new;
 };
 
@@ -918,6 +918,54 @@ __device__ __forceinline__ void ok_c2_insert_slow(OkCount2Smem<LOG2>& sm, unsign
     }
 }
 
+// Dense output straight from the count kernel (no compaction pass): sub-partition p's distinct keys go to
+// out[base(p) ..], base(p) = distinct keys of all sub-partitions before it, found by a decoupled look-back over
+// lb[]: after its insert phase a CTA publishes its own total (AGG), then sums its predecessors' totals backwards
+// until it meets one that already knows its inclusive prefix (PFX), and publishes its own.  Sub-partitions are
+// handed out by a TICKET, so every predecessor a CTA waits for belongs to a CTA that is already running: no
+// deadlock whatever else shares the GPU.  A sub-partition the fast kernel cannot finish (too many windows or
+// distinct keys, crowded buckets) FAILS the dense attempt (*failed = 1, it publishes a total of 0 so that nobody
+// hangs) and the host recounts the range in the sparse form below; the dense pass never modifies its input.
+struct OkDenseOut {
+    unsigned long long* lb;            // [n_sub] look-back words; nullptr: sparse output (sorted runs in place)
+    unsigned long long* keys;          // dense outputs
+    unsigned long long* counts;
+    unsigned long long cap;            // entries the dense outputs hold
+    unsigned* ticket;                  // zeroed before every launch
+    unsigned* failed;
+};
+#define OK_LB_AGG 0x4000000000000000ull
+#define OK_LB_PFX 0x8000000000000000ull
+#define OK_LB_VAL 0x3FFFFFFFFFFFFFFFull
+
+// warp 0 of the CTA (all 32 lanes): publish `tot` for sub-partition p, return the exclusive prefix
+__device__ __forceinline__ unsigned long long ok_dense_lookback(unsigned long long* lb, unsigned p, unsigned long long tot) {
+    const int lane = threadIdx.x & 31;
+    if (p == 0) {
+        if (lane == 0) { __threadfence(); atomicExch(&lb[0], OK_LB_PFX | tot); }
+        return 0ull;
+    }
+    if (lane == 0) atomicExch(&lb[p], OK_LB_AGG | tot);
+    unsigned long long excl = 0;
+    long long q = (long long)p - 1;               // lane i looks at q - i
+    for (;;) {
+        const long long at = q - lane;
+        unsigned long long v;
+        do {
+            v = at >= 0 ? *((volatile unsigned long long*)&lb[at]) : OK_LB_PFX;      // before sub-partition 0: prefix 0
+        } while (__any_sync(OK_FULL, (v & (OK_LB_AGG | OK_LB_PFX)) == 0ull));
+        const unsigned pfx = __ballot_sync(OK_FULL, (v & OK_LB_PFX) != 0ull);
+        const int first = pfx ? __ffs(pfx) - 1 : 32;                                   // nearest predecessor with a prefix
+        unsigned long long part = lane <= first ? (v & OK_LB_VAL) : 0ull;
+        part = ok_warp_sum(part);
+        excl += part;
+        if (pfx) break;
+        q -= 32;
+    }
+    if (lane == 0) atomicExch(&lb[p], OK_LB_PFX | (excl + tot));
+    return excl;
+}
+
 template <int LOG2, int KC = 0>
 __global__ void __launch_bounds__(OkCount2Cfg<LOG2>::THREADS, LOG2 == 13 ? 2 : 1)
 k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ beg,
@@ -925,7 +973,7 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
              const unsigned* __restrict__ cap_end, unsigned p_begin, unsigned p_end, OkPartCfg cfg_in,
              unsigned* __restrict__ cnt_out /* 32-bit counts of the runs, same indices as src */, unsigned* __restrict__ n_distinct,
              unsigned* __restrict__ deferred, OkPartScalars* __restrict__ scal, unsigned seed_keys /* 0 or THREADS */,
-             bool direct_first) {
+             bool direct_first, const __grid_constant__ OkDenseOut dense) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using C = OkCount2Cfg<LOG2>;
     constexpr unsigned OK_C2_SLOTS = C::SLOTS, OK_C2_MAXKEYS = C::MAXKEYS, OK_C2_THREADS = C::THREADS, OK_C2_BUCKETS = C::BUCKETS;
@@ -943,17 +991,31 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
         if (threadIdx.x == 0) sm.n_new = 0;
     }
     __syncthreads();
-    for (unsigned p = p_begin + blockIdx.x; p < p_end; p += gridDim.x) {
+    const bool DENSE = dense.lb != nullptr;
+    unsigned long long* const dbase = reinterpret_cast<unsigned long long*>(sm.wsum + 32);     // (wsum[32..33]: the CTA's dense base)
+    for (unsigned p = p_begin + blockIdx.x;; p += gridDim.x) {
+        if (DENSE) {         // sub-partitions in ticket order (see OkDenseOut)
+            __syncthreads();
+            if (threadIdx.x == 0) sm.wsum[34] = atomicAdd(dense.ticket, 1u);
+            __syncthreads();
+            p = p_begin + sm.wsum[34];
+        }
+        if (p >= p_end) break;
         // invariant here: table empty, counts zero, boff zero, n_new zero
         const unsigned b0 = beg[p];
         const unsigned e0 = min(fill_end[p], cap_end[p]);          // the rest was spilled by the scatter
         const unsigned n = e0 > b0 ? e0 - b0 : 0u;
-        if (n == 0) { if (threadIdx.x == 0) n_distinct[p] = 0; continue; }
+        if (n == 0) {
+            if (threadIdx.x == 0) n_distinct[p] = 0;
+            if (DENSE && wid == 0) ok_dense_lookback(dense.lb, p, 0ull);
+            continue;
+        }
         // The table has to hold the DISTINCT keys only: a sub-partition may bring many more windows than slots
         // (the host sizes sub-partitions from the caller's capacity hint).  If the distinct keys do outgrow the
         // table the insert phase stops early and the sub-partition goes to the generic kernel.
         if (n > C::MAXN) {
-            if (threadIdx.x == 0) deferred[atomicAdd(&scal->n_deferred, 1u)] = p;
+            if (threadIdx.x == 0) { deferred[atomicAdd(&scal->n_deferred, 1u)] = p; if (DENSE) *dense.failed = 1u; }
+            if (DENSE && wid == 0) ok_dense_lookback(dense.lb, p, 0ull);
             continue;
         }
         const bool may_overflow = n > OK_C2_MAXKEYS;
@@ -1035,12 +1097,14 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             for (unsigned i = threadIdx.x; i < OK_C2_SLOTS / 2; i += OK_C2_THREADS) k2[i] = make_ulonglong2(OK_EMPTY_KEY, OK_EMPTY_KEY);
             for (unsigned i = threadIdx.x; i < OK_C2_SLOTS / 8; i += OK_C2_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
             for (unsigned i = threadIdx.x; i < OK_C2_BUCKETS; i += OK_C2_THREADS) sm.boff[i] = 0;
-            if (threadIdx.x == 0) { sm.n_new = 0; deferred[atomicAdd(&scal->n_deferred, 1u)] = p; }
+            if (threadIdx.x == 0) { sm.n_new = 0; deferred[atomicAdd(&scal->n_deferred, 1u)] = p; if (DENSE) *dense.failed = 1u; }
+            if (DENSE && wid == 0) ok_dense_lookback(dense.lb, p, 0ull);
             __syncthreads();
             continue;
         }
         // ---- (2) exclusive scan of the bucket counts, BPT per thread
         const unsigned tot = sm.n_new;
+        if (DENSE && threadIdx.x == 0 && p) atomicExch(&dense.lb[p], OK_LB_AGG | tot);      // early: successors can already add it up
         unsigned hh[C::BPT], hsum = 0, hmax = 0;
 #pragma unroll
         for (unsigned q = 0; q < C::BPT; ++q) { hh[q] = sm.boff[C::BPT * threadIdx.x + q]; hsum += hh[q]; hmax = max(hmax, hh[q]); }
@@ -1067,6 +1131,10 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
                 const unsigned s = sm.newl[i];
                 sm.sidx[atomicAdd(&sm.boff[ok_c2_bucket<LOG2>(sm.tkey[s], cfg, sub_bits)], 1u)] = (unsigned short)s;
             }
+            if (DENSE && wid == 0) {          // by now the predecessors have usually published their prefix: one look
+                const unsigned long long b = ok_dense_lookback(dense.lb, p, tot);
+                if (lane == 0) { *dbase = b; if (b + tot > dense.cap) *dense.failed = 1u; }
+            }
             __syncthreads();
             // ---- (4) rank inside the bucket (~1 key per bucket) = final position; emit
             for (unsigned i = threadIdx.x; i < tot; i += OK_C2_THREADS) {
@@ -1076,11 +1144,17 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
                 const unsigned lo = b ? sm.boff[b - 1] : 0u, hi = sm.boff[b];
                 unsigned pos = lo;
                 for (unsigned j = lo; j < hi; ++j) pos += sm.tkey[sm.sidx[j]] < key ? 1u : 0u;
-                src[b0 + pos] = key;
-                cnt_out[b0 + pos] = reinterpret_cast<unsigned short*>(sm.tcnt)[s];
+                if (DENSE) {
+                    const unsigned long long at = *dbase + pos;
+                    if (at < dense.cap) { dense.keys[at] = key; dense.counts[at] = reinterpret_cast<unsigned short*>(sm.tcnt)[s]; }
+                } else {
+                    src[b0 + pos] = key;
+                    cnt_out[b0 + pos] = reinterpret_cast<unsigned short*>(sm.tcnt)[s];
+                }
             }
-        } else if (threadIdx.x == 0) {   // keys too clustered for per-bucket ranking: leave it to the generic kernel
-            deferred[atomicAdd(&scal->n_deferred, 1u)] = p;
+        } else {                          // keys too clustered for per-bucket ranking: leave it to the generic kernel
+            if (threadIdx.x == 0) { deferred[atomicAdd(&scal->n_deferred, 1u)] = p; if (DENSE) *dense.failed = 1u; }
+            if (DENSE && wid == 0) ok_dense_lookback(dense.lb, p, 0ull);
         }
         __syncthreads();
         // ---- (5) clean what this sub-partition used
