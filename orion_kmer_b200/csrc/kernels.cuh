@@ -562,6 +562,36 @@ k_probe_counts(OkKeyTableView t, const unsigned long long* __restrict__ keys,
 // of B is read from global memory once (the per-key search of k_intersect_sorted makes ~23 dependent global
 // loads per key of A: measured 13 s for the 32,640 pairs of config 5).
 #define OK_IS_TILE 2048u
+// A thread holds OK_IS_TILE / 256 CONSECUTIVE keys of A (ascending): one binary search places the first in the chunk of
+// B, the others walk on from there -- on average one step per key for sets of similar size -- and fall back to a
+// binary search of the rest when a gap is long.  (One binary search per key: 11 dependent shared-memory loads each;
+// measured 61 us per pair of 5 M-key sets against 49 us with the rows batched and ... with the walk.)
+__device__ __forceinline__ unsigned ok_is_match_run(const unsigned long long* __restrict__ sb, unsigned cn,
+                                                    const unsigned long long (&ka)[OK_IS_TILE / 256], unsigned n_valid) {
+    unsigned m = 0;
+    if (n_valid == 0 || ka[n_valid - 1] < sb[0] || ka[0] > sb[cn - 1]) return 0u;
+    unsigned l = 0, h = cn;
+    { const unsigned long long key = ka[0]; while (l < h) { const unsigned mid = (l + h) >> 1; if (sb[mid] < key) l = mid + 1; else h = mid; } }
+#pragma unroll
+    for (unsigned q = 0; q < OK_IS_TILE / 256; ++q) {
+        if (q >= n_valid) break;
+        const unsigned long long key = ka[q];
+        unsigned steps = 0;
+        while (l < cn && sb[l] < key) {
+            ++l;
+            if (++steps == 8u) {        // a long gap: binary search of what is left
+                unsigned lo = l, hi = cn;
+                while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (sb[mid] < key) lo = mid + 1; else hi = mid; }
+                l = lo;
+                break;
+            }
+        }
+        if (l >= cn) break;
+        m += sb[l] == key ? 1u : 0u;
+    }
+    return m;
+}
+
 __global__ void __launch_bounds__(256)
 k_intersect_bounds(const unsigned long long* __restrict__ a, uint64_t na, const unsigned long long* __restrict__ b,
                    uint64_t nb, unsigned long long* __restrict__ lo_out /* n_tiles + 1 */) {
@@ -582,27 +612,19 @@ k_intersect_tiled(const unsigned long long* __restrict__ a, uint64_t na, const u
     unsigned long long m = 0;
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const uint64_t i0 = t * OK_IS_TILE;
-        unsigned long long ka[OK_IS_TILE / 256];
+        constexpr unsigned KPT = OK_IS_TILE / 256;
+        unsigned long long ka[KPT];
+        const uint64_t i1 = i0 + (uint64_t)threadIdx.x * KPT;          // this thread's consecutive keys
+        const unsigned n_valid = i1 >= na ? 0u : (unsigned)(na - i1 < KPT ? na - i1 : KPT);
 #pragma unroll
-        for (unsigned q = 0; q < OK_IS_TILE / 256; ++q) {
-            const uint64_t i = i0 + q * 256u + threadIdx.x;
-            ka[q] = i < na ? a[i] : OK_EMPTY_KEY;          // the sentinel is handled below: it may be a real key of a k = 32 set
-        }
+        for (unsigned q = 0; q < KPT; ++q) ka[q] = q < n_valid ? a[i1 + q] : OK_EMPTY_KEY;
         const uint64_t lo = tile_lo[t], hi = tile_lo[t + 1];
         for (uint64_t c = lo; c < hi; c += OK_IS_TILE) {
             const unsigned cn = (unsigned)(hi - c < OK_IS_TILE ? hi - c : OK_IS_TILE);
             __syncthreads();                               // the previous chunk is no longer being searched
             for (unsigned j = threadIdx.x; j < cn; j += 256u) sb[j] = b[c + j];
             __syncthreads();
-            const unsigned long long first = sb[0], last = sb[cn - 1];
-#pragma unroll
-            for (unsigned q = 0; q < OK_IS_TILE / 256; ++q) {
-                const unsigned long long key = ka[q];
-                if (i0 + q * 256u + threadIdx.x >= na || key < first || key > last) continue;
-                unsigned l = 0, h = cn;
-                while (l < h) { const unsigned mid = (l + h) >> 1; if (sb[mid] < key) l = mid + 1; else h = mid; }
-                m += (l < cn && sb[l] == key) ? 1u : 0u;
-            }
+            m += ok_is_match_run(sb, cn, ka, n_valid);
         }
     }
     m = ok_warp_sum(m);
@@ -665,27 +687,19 @@ k_intersect_row_tiled(const unsigned long long* __restrict__ a, uint64_t na, OkR
         if (jj != cur_jj) { if (cur_jj != 0xFFFFFFFFu) flush(); cur_jj = jj; }
         const unsigned long long* __restrict__ b = sets.keys[sets.col[jj]];
         const uint64_t i0 = t * OK_IS_TILE;
-        unsigned long long ka[OK_IS_TILE / 256];
+        constexpr unsigned KPT = OK_IS_TILE / 256;
+        unsigned long long ka[KPT];
+        const uint64_t i1 = i0 + (uint64_t)threadIdx.x * KPT;          // this thread's consecutive keys
+        const unsigned n_valid = i1 >= na ? 0u : (unsigned)(na - i1 < KPT ? na - i1 : KPT);
 #pragma unroll
-        for (unsigned q = 0; q < OK_IS_TILE / 256; ++q) {
-            const uint64_t i = i0 + q * 256u + threadIdx.x;
-            ka[q] = i < na ? a[i] : OK_EMPTY_KEY;
-        }
+        for (unsigned q = 0; q < KPT; ++q) ka[q] = q < n_valid ? a[i1 + q] : OK_EMPTY_KEY;
         const uint64_t lo = lo_all[(uint64_t)jj * per + t], hi = lo_all[(uint64_t)jj * per + t + 1];
         for (uint64_t c = lo; c < hi; c += OK_IS_TILE) {
             const unsigned cn = (unsigned)(hi - c < OK_IS_TILE ? hi - c : OK_IS_TILE);
             __syncthreads();
             for (unsigned j = threadIdx.x; j < cn; j += 256u) sb[j] = b[c + j];
             __syncthreads();
-            const unsigned long long first = sb[0], last = sb[cn - 1];
-#pragma unroll
-            for (unsigned q = 0; q < OK_IS_TILE / 256; ++q) {
-                const unsigned long long key = ka[q];
-                if (i0 + q * 256u + threadIdx.x >= na || key < first || key > last) continue;
-                unsigned l = 0, h = cn;
-                while (l < h) { const unsigned mid = (l + h) >> 1; if (sb[mid] < key) l = mid + 1; else h = mid; }
-                m += (l < cn && sb[l] == key) ? 1u : 0u;
-            }
+            m += ok_is_match_run(sb, cn, ka, n_valid);
         }
     }
     if (cur_jj != 0xFFFFFFFFu) flush();
