@@ -588,7 +588,7 @@ int part_launch_range(ok_counter* c, PartPlan& pl, unsigned p0, unsigned p1, boo
                (g_count_seed & 1) ? OkCount2Cfg<13>::THREADS : 0u, (g_count_seed & 2) != 0, dn);
     }
     if (!dense) {        // (a dense attempt with a deferred sub-partition has failed as a whole: the range is recounted sparse)
-        const size_t ct_smem = (size_t)(OK_CT_SLOTS + OK_CT_PAD) * 12;
+        const size_t ct_smem = (size_t)OK_CT_SLOTS * 12;
         TRY(set_smem(k_part_count_generic, ct_smem));
         LAUNCH(k_part_count_generic, grid_sm, OK_CT_THREADS, ct_smem, c->s_main, c->d_buf2, pl.beg, pl.cursor, pl.cap_end,
                pl.deferred, pl.scal, pl.cfg, cnt_out, d_nd, ps);

@@ -28,9 +28,8 @@
 #define OK_PART_TILE 4096u        // keys per CTA round of a scatter (256 threads x 16)
 #define OK_PART_MAXBINS 1024u     // bins per scatter level
 #define OK_STAGE_SLOTS 8192u      // staging slots of a scatter round
-// generic (fallback) count kernel: monotone shared-memory table
+// generic (fallback) count kernel: hashed shared-memory table, sorted afterwards
 #define OK_CT_SLOTS 8192u
-#define OK_CT_PAD 512u            // tail padding = displacement bound of the monotone table
 #define OK_CT_THREADS 512u
 // fast count kernel: hashed shared-memory table + position buckets (sizes: OkCount2Cfg)
 #define OK_C2_BUCKET_MAX 32u      // a fuller bucket defers the sub-partition to the generic kernel
@@ -1170,28 +1169,24 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
     }
 }
 
-// Generic kernel for the sub-partitions the fast kernel deferred: MONOTONE shared-memory table
-// (home slot = position inside the sub-partition, linear probing, displacement bound OK_CT_PAD
-// with an exact spill), ordered sweep + local rank fix.  Any sub-partition size.
-__device__ __forceinline__ unsigned ok_ct_home(uint64_t key, const OkPartCfg& cfg, unsigned sub_bits) {
-    const uint64_t f = ok_part_pos(key, cfg) << sub_bits;     // position inside the sub-partition
-    return (unsigned)(((f >> 32) * (uint64_t)OK_CT_SLOTS) >> 32);
-}
-
+// Generic kernel for the sub-partitions the fast kernel deferred (any number of windows; keys as clustered as they
+// come): HASHED shared-memory table with 32-bit counts, then a bitonic sort of the table itself -- empty slots hold
+// the sentinel u64::MAX and sort to the end, so the first n_distinct slots are the sorted run.  Round 1 used a
+// MONOTONE table here (home slot = position inside the sub-partition): microsatellite reads put thousands of
+// distinct k-mers on one 16-base prefix, i.e. on ONE home slot, the displacement bound spilled every window of
+// them and the spill list overflowed (tools/skew.py, 2 % microsatellites).  Hashing does not care where keys sit.
+// Only a sub-partition with more than OK_CT_MAXKEYS distinct keys spills (exact, slow path).
+#define OK_CT_MAXKEYS 6144u
 __global__ void __launch_bounds__(OK_CT_THREADS, 2)
 k_part_count_generic(unsigned long long* __restrict__ src, const unsigned* __restrict__ beg,
                      const unsigned* __restrict__ fill_end, const unsigned* __restrict__ cap_end,
                      const unsigned* __restrict__ deferred, const OkPartScalars* __restrict__ scal, OkPartCfg cfg,
                      unsigned* __restrict__ cnt_out, unsigned* __restrict__ n_distinct, OkPartSpill ps) {
-    constexpr unsigned NT = OK_CT_SLOTS + OK_CT_PAD;            // 8704
-    constexpr unsigned ROUNDS = NT / OK_CT_THREADS;             // 17 strided rounds in the sweep
-    constexpr unsigned NW = OK_CT_THREADS / 32;                 // 16 warps
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem_raw);   // [NT]
-    unsigned* tcnt = reinterpret_cast<unsigned*>(tkey + NT);                      // [NT]
-    __shared__ unsigned seg[ROUNDS * NW + 1];       // occupied slots per (round, warp), then exclusive scan
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned sub_bits = cfg.b1 + cfg.b2;
+    unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem_raw);   // [OK_CT_SLOTS]
+    unsigned* tcnt = reinterpret_cast<unsigned*>(tkey + OK_CT_SLOTS);             // [OK_CT_SLOTS]
+    __shared__ unsigned n_keys;
+    (void)cfg;
     const unsigned n_def = scal->n_deferred;
     for (unsigned d = scal->def_done + blockIdx.x; d < n_def; d += gridDim.x) {
         const unsigned p = deferred[d];
@@ -1199,90 +1194,47 @@ k_part_count_generic(unsigned long long* __restrict__ src, const unsigned* __res
         const unsigned e0 = min(fill_end[p], cap_end[p]);
         const unsigned n = e0 > b0 ? e0 - b0 : 0u;
         if (n == 0) { if (threadIdx.x == 0) n_distinct[p] = 0; continue; }
-        {   // 128-bit stores: two keys / four counts at a time
-            ulonglong2* k2 = reinterpret_cast<ulonglong2*>(tkey);
-            uint4* c4 = reinterpret_cast<uint4*>(tcnt);
-            for (unsigned i = threadIdx.x; i < NT / 2; i += OK_CT_THREADS) k2[i] = make_ulonglong2(OK_EMPTY_KEY, OK_EMPTY_KEY);
-            for (unsigned i = threadIdx.x; i < NT / 4; i += OK_CT_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < OK_CT_SLOTS; i += OK_CT_THREADS) { tkey[i] = OK_EMPTY_KEY; tcnt[i] = 0u; }
+        if (threadIdx.x == 0) n_keys = 0;
+        __syncthreads();
+        // ---- insert: CAS claim + add; a key that finds the table full of other keys is spilled
+        for (unsigned i = threadIdx.x; i < n; i += OK_CT_THREADS) {
+            const unsigned long long key = __ldcs(src + b0 + i);
+            if (key == OK_EMPTY_KEY) continue;          // canonical k-mers never equal the sentinel
+            unsigned s = ok_c2_hash<13>(key);
+            bool placed = false;
+            for (unsigned probes = 0; probes < OK_CT_SLOTS; ++probes) {
+                unsigned long long cur = tkey[s];
+                if (cur == OK_EMPTY_KEY) {
+                    if (*(volatile unsigned*)&n_keys >= OK_CT_MAXKEYS) break;      // full enough: the rest of the new keys spill
+                    cur = atomicCAS(&tkey[s], OK_EMPTY_KEY, key);
+                    if (cur == OK_EMPTY_KEY) { atomicAdd(&n_keys, 1u); cur = key; }
+                }
+                if (cur == key) { atomicAdd(&tcnt[s], 1u); placed = true; break; }
+                s = (s + 1u) & (OK_CT_SLOTS - 1u);
+            }
+            if (!placed) ok_spill(ps.sp, ps.st, key, 1);
         }
         __syncthreads();
-        // ---- insert: CAS claim + add, 4 keys in flight per thread
-        for (unsigned base = 0; base < n; base += 4 * OK_CT_THREADS) {
-            unsigned long long kk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned i = base + q * OK_CT_THREADS + threadIdx.x;
-                kk[q] = i < n ? __ldcs(src + b0 + i) : OK_EMPTY_KEY;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned long long key = kk[q];
-                if (key == OK_EMPTY_KEY) continue;      // canonical k-mers never equal the sentinel
-                const unsigned h = ok_ct_home(key, cfg, sub_bits);
-                bool placed = false;
-                for (unsigned s = h; s < h + OK_CT_PAD; ++s) {
-                    unsigned long long cur = tkey[s];
-                    if (cur == OK_EMPTY_KEY) {
-                        cur = atomicCAS(&tkey[s], OK_EMPTY_KEY, key);
-                        if (cur == OK_EMPTY_KEY) cur = key;
+        // ---- bitonic sort of the whole table by key (8192 slots, 16 per thread and stage)
+        for (unsigned k2 = 2; k2 <= OK_CT_SLOTS; k2 <<= 1)
+            for (unsigned j = k2 >> 1; j > 0; j >>= 1) {
+                for (unsigned t = threadIdx.x; t < OK_CT_SLOTS / 2; t += OK_CT_THREADS) {
+                    const unsigned i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));       // the lower index of pair t
+                    const unsigned l = i | j;
+                    const bool up = (i & k2) == 0u;
+                    const unsigned long long a = tkey[i], bkey = tkey[l];
+                    if ((a > bkey) == up) {
+                        tkey[i] = bkey; tkey[l] = a;
+                        const unsigned ca = tcnt[i]; tcnt[i] = tcnt[l]; tcnt[l] = ca;
                     }
-                    if (cur == key) { atomicAdd(&tcnt[s], 1u); placed = true; break; }
                 }
-                if (!placed) ok_spill(ps.sp, ps.st, key, 1);
+                __syncthreads();
             }
-        }
-        __syncthreads();
-        // ---- ordered sweep, round r covers slots [r*512, (r+1)*512), one per thread
-        unsigned occ = 0;                               // bit r: my slot of round r is occupied
-        unsigned long long pre_lo = 0, pre_hi = 0;      // 5 bits per round: occupied slots of my warp segment before mine
-#pragma unroll
-        for (unsigned r = 0; r < ROUNDS; ++r) {
-            const bool o = tkey[r * OK_CT_THREADS + threadIdx.x] != OK_EMPTY_KEY;
-            const unsigned bal = __ballot_sync(OK_FULL, o);
-            occ |= (o ? 1u : 0u) << r;
-            const unsigned long long before = __popc(bal & ((1u << lane) - 1u));
-            if (r < 12) pre_lo |= before << (5 * r); else pre_hi |= before << (5 * (r - 12));
-            if (lane == 0) seg[r * NW + wid] = __popc(bal);
-        }
-        __syncthreads();
-        if (wid == 0) {                                 // exclusive scan of the 272 segment counts
-            unsigned carry = 0;
-            for (unsigned i0 = 0; i0 < ROUNDS * NW; i0 += 32) {
-                const unsigned i = i0 + lane;
-                const unsigned v = i < ROUNDS * NW ? seg[i] : 0u;
-                unsigned inc = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
-                if (i < ROUNDS * NW) seg[i] = carry + inc - v;
-                carry += __shfl_sync(OK_FULL, inc, 31);
-            }
-            if (lane == 0) seg[ROUNDS * NW] = carry;
-        }
-        __syncthreads();
-        const unsigned tot = seg[ROUNDS * NW];
-        // second pass over MY occupied slots only (lanes pack their work, sparse tables cost little)
-        while (occ) {
-            const unsigned r = __ffs(occ) - 1; occ &= occ - 1;
-            const unsigned s = r * OK_CT_THREADS + threadIdx.x;
-            const unsigned long long key = tkey[s];
-            const unsigned before = (unsigned)((r < 12 ? pre_lo >> (5 * r) : pre_hi >> (5 * (r - 12))) & 31u);
-            int adj = 0;
-            const bool lone = (s == 0 || tkey[s - 1] == OK_EMPTY_KEY) && (s + 1 >= NT || tkey[s + 1] == OK_EMPTY_KEY);
-            if (!lone) {
-                const unsigned h = ok_ct_home(key, cfg, sub_bits);
-                for (unsigned t = h; t < s; ++t) adj -= tkey[t] > key ? 1 : 0;          // parked before us, larger
-                for (unsigned t = s + 1; t < h + OK_CT_PAD; ++t) {                       // pushed past us, smaller
-                    const unsigned long long kt = tkey[t];
-                    if (kt == OK_EMPTY_KEY) break;
-                    adj += kt < key ? 1 : 0;
-                }
-            }
-            const unsigned idx = seg[r * NW + wid] + before + adj;
-            src[b0 + idx] = key;                       // idx < tot <= n: stays inside the region
-            cnt_out[b0 + idx] = tcnt[s];
-        }
+        const unsigned tot = n_keys;                   // (a spilled key may also sit in the table: the spill list is exact either way)
+        for (unsigned i = threadIdx.x; i < tot; i += OK_CT_THREADS) { src[b0 + i] = tkey[i]; cnt_out[b0 + i] = tcnt[i]; }
         if (threadIdx.x == 0) n_distinct[p] = tot;
-        __syncthreads();
     }
 }
 

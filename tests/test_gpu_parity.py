@@ -713,6 +713,35 @@ def test_partitioned_heavy_duplicates_and_low_complexity(oracle):
         c.close()
 
 
+def test_microsatellite_reads_with_errors_stay_exact(oracle):
+    """2 % of a genome in microsatellites ((A)n, (AC)n, (AAT)n ... runs of 200-2000 bases) and 0.5 % substitution
+    errors: a handful of sub-partitions receive hundreds of thousands of windows whose distinct k-mers share their
+    first 16 bases.  They are deferred to the generic count kernel (hashed table + bitonic sort); round 1's monotone
+    table spilled every one of those windows and the spill list overflowed."""
+    rng = np.random.default_rng(8)
+    g = synth.genome(8, 4_000_000)
+    motifs = [b"A", b"AC", b"AAT", b"AG", b"T"]
+    done = 0
+    while done < len(g) * 0.02:
+        ln = int(rng.integers(200, 2000))
+        p = int(rng.integers(0, len(g) - ln))
+        m = motifs[int(rng.integers(0, len(motifs)))]
+        g[p:p + ln] = np.frombuffer((m * (ln // len(m) + 1))[:ln], np.uint8)
+        done += ln
+    n = 800_000
+    bases, off = synth.reads(g, 9, n), synth.read_offsets(n)
+    wk, wc = oracle.count_batch_mt(31, bases, off, 8)
+    for hint in (int(len(bases) * 0.17), 0):
+        c = ok.KmerCounter(31, capacity_hint=hint)
+        c.add_batch(bases, off)
+        st = c.stats()
+        gk, gc = c.finish()
+        c.close()
+        assert st["partitioned"] == 1 and st["n_spilled"] == 0, st
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc), hint
+    assert int(wc.max()) > 10_000           # the hot k-mers are there
+
+
 def test_capacity_hint_sizes_sub_partitions_and_a_wrong_hint_stays_exact(oracle):
     """With a capacity hint the sub-partitions are sized for their expected DISTINCT keys (several windows per
     table slot).  A hint far below the truth makes every shared-memory table overflow: the sub-partitions are

@@ -33,6 +33,7 @@ for _ in range(a.steps):
         c.add_batch_device(d_b.data_ptr(), len(bases), d_o.data_ptr(), a.reads)
     _, _, n = c.finish_device(1)
 print("distinct", n, c.stats())
+c.close()
 if a.sets:
     import bench_sets
     sets = []
@@ -43,3 +44,5 @@ if a.sets:
         sets.append(s)
     sizes, inter = ok.all_vs_all(sets)
     print("all-vs-all", sizes[:3], inter[0, :3])
+    for s_ in sets:
+        s_.close()
