@@ -685,14 +685,45 @@ bool part_hint_misled(const ok_counter* c, const PartPlan& pl) {
     return pl.hinted && c->n_deferred > pl.n_sub / 256u + 4u;
 }
 
-int part_absorb_spills(ok_counter* c, uint64_t windows_before) {
+int part_count_keys_absorb(ok_counter* c, const uint64_t* d_keys, uint64_t n, int depth);
+int run_stash(ok_counter* c);
+int run_unstash(ok_counter* c);
+
+// What the one-shot path spilled (keys past a sampled capacity or past a sub-partition's table) is exact but
+// unsorted.  The spilled keys are counted as a small batch of their own by the same path and that run is MERGED
+// into the batch's run (a few rounds at most: every round takes another table-full of distinct keys out of a hot
+// sub-partition).  Folding everything into the device-wide ordered table -- round 1's way -- fails exactly when
+// spills happen: thousands of distinct k-mers on one 16-base prefix (microsatellites) share one home slot there.
+// If even the spill list overflowed, nothing of this batch is kept and the caller re-counts it through the table path.
+int part_absorb_spills(ok_counter* c, uint64_t windows_before, int depth = 0) {
     if (c->h_stats->spill_n == 0) return OK_SUCCESS;
     if (c->h_stats->spill_n > c->spill.cap) {
         TRY(part_discard(c, windows_before));
         return PART_RETRY;
     }
-    c->spilled_total += c->h_stats->spill_n;
-    return run_to_table(c);
+    const uint64_t n = c->h_stats->spill_n;
+    c->spilled_total += n;
+    if (depth >= 6 || c->n_acc) return run_to_table(c);          // (a set-aside run of earlier batches: keep the old way)
+    unsigned long long* d_tmp = nullptr;
+    CU(cudaMalloc((void**)&d_tmp, n * 8));
+    CU(cudaMemcpyAsync(d_tmp, c->spill.keys, n * 8, cudaMemcpyDeviceToDevice, c->s_main));
+    CU(cudaMemsetAsync(&c->d_stats->spill_n, 0, 8, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    c->h_stats->spill_n = 0;
+    const uint64_t windows = c->windows;                        // the spilled windows are already in it
+    const int saved_mode = c->path_mode;
+    int r = run_stash(c);
+    if (r == OK_SUCCESS) {
+        c->path_mode = 2;
+        r = part_count_keys_absorb(c, (const uint64_t*)d_tmp, n, depth + 1);     // (plans afresh: c->pl now describes the spill batch)
+    }
+    c->path_mode = saved_mode;
+    cudaFree(d_tmp);
+    if (r != OK_SUCCESS) return r == PART_RETRY ? set_err(OK_ERR_INTERNAL, "the spill list overflowed while its own keys were being counted") : r;
+    c->windows = windows;
+    CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    return run_unstash(c);
 }
 
 // pieces of a batch that is still landing in device memory: piece i covers bases
@@ -773,7 +804,9 @@ int part_count_bases(ok_counter* c, const uint8_t* d_bases, uint64_t n_bases, co
     return part_absorb_spills(c, windows_before);
 }
 
-int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
+int part_count_keys_absorb(ok_counter* c, const uint64_t* d_keys, uint64_t n, int depth);
+int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) { return part_count_keys_absorb(c, d_keys, n, 0); }
+int part_count_keys_absorb(ok_counter* c, const uint64_t* d_keys, uint64_t n, int depth) {
     PartPlan& pl = c->pl; pl = PartPlan{};
     const uint64_t windows_before = c->windows;
     part_choose_bits(c, n, pl);
@@ -804,7 +837,7 @@ int part_count_keys(ok_counter* c, const uint64_t* d_keys, uint64_t n) {
     }
     CU(cudaEventRecord(c->ev_p[2], c->s_main));
     TRY(part_finish(c, pl));
-    return part_absorb_spills(c, windows_before);
+    return part_absorb_spills(c, windows_before, depth);
 }
 
 // compact sub-partitions [p0, p1) of the sparse run into the dense arrays

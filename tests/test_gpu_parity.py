@@ -740,6 +740,20 @@ def test_microsatellite_reads_with_errors_stay_exact(oracle):
         assert st["partitioned"] == 1 and st["n_spilled"] == 0, st
         assert np.array_equal(gk, wk) and np.array_equal(gc, wc), hint
     assert int(wc.max()) > 10_000           # the hot k-mers are there
+    # deeper coverage: the poly-A sub-partition now holds more distinct error variants than one shared-memory table
+    # takes (6144): the excess is spilled, counted as a batch of its own and MERGED into the run (round 1 folded the
+    # run into the device-wide ordered table, which cannot hold thousands of keys on one home slot, and failed)
+    import os
+    n = 2_400_000
+    bases, off = synth.reads(g, 10, n), synth.read_offsets(n)
+    wk, wc = oracle.count_batch_ranged_mt(31, bases, off, min(os.cpu_count() or 1, 16))
+    c = ok.KmerCounter(31, capacity_hint=int(len(bases) * 0.17))
+    c.add_batch(bases, off)
+    st = c.stats()
+    gk, gc = c.finish()
+    c.close()
+    assert st["partitioned"] == 1, st
+    assert np.array_equal(gk, wk) and np.array_equal(gc, wc), st
 
 
 def test_capacity_hint_sizes_sub_partitions_and_a_wrong_hint_stays_exact(oracle):
