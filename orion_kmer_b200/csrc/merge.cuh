@@ -46,6 +46,16 @@ __device__ __forceinline__ unsigned ok_mg_lower(const unsigned long long* s, uns
     while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (s[mid] < v) lo = mid + 1; else hi = mid; }
     return lo;
 }
+// the same for a thread that asks for ascending v's one after the other: walk on from the previous answer (both sides are
+// sorted, so a step or two on average), binary search of the rest after 8 steps.  *at: previous answer, updated.
+__device__ __forceinline__ unsigned ok_mg_lower_from(const unsigned long long* s, unsigned n, unsigned long long v, unsigned at) {
+    unsigned steps = 0;
+    while (at < n && s[at] < v) {
+        ++at;
+        if (++steps == 8u) return at + ok_mg_lower(s + at, n - at, v);
+    }
+    return at;
+}
 
 __global__ void __launch_bounds__(OK_MG_THREADS)
 k_merge_count(const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b,
@@ -59,10 +69,14 @@ k_merge_count(const unsigned long long* __restrict__ a, const unsigned long long
         for (unsigned i = threadIdx.x; i < ca; i += OK_MG_THREADS) sm.sa[i] = a[s0.x + i];
         __syncthreads();
         unsigned pairs = 0;
-        for (unsigned i = threadIdx.x; i < cb; i += OK_MG_THREADS) {
-            const unsigned long long v = b[s0.y + i];
-            const unsigned p = ok_mg_lower(sm.sa, ca, v);
-            pairs += (p < ca && sm.sa[p] == v) ? 1u : 0u;
+        {   // every thread takes consecutive elements of B: one binary search, then a walk
+            const unsigned per = (cb + OK_MG_THREADS - 1) / OK_MG_THREADS, i0 = threadIdx.x * per, i1 = min(cb, i0 + per);
+            unsigned p = i0 < i1 ? ok_mg_lower(sm.sa, ca, b[s0.y + i0]) : 0u;
+            for (unsigned i = i0; i < i1; ++i) {
+                const unsigned long long v = b[s0.y + i];
+                p = ok_mg_lower_from(sm.sa, ca, v, p);
+                pairs += (p < ca && sm.sa[p] == v) ? 1u : 0u;
+            }
         }
         pairs = (unsigned)ok_warp_sum(pairs);
         if ((threadIdx.x & 31) == 0) sm.wsum[threadIdx.x >> 5] = pairs;
@@ -94,16 +108,25 @@ k_merge_write(const unsigned long long* __restrict__ a, const unsigned long long
         if (threadIdx.x == 0) sm.running = tile_base[t];
         __syncthreads();
         // merged rank of every element: its own index + the elements of the other side before it (ties: A first)
-        for (unsigned i = threadIdx.x; i < ca; i += OK_MG_THREADS) {
-            const unsigned long long v = sm.sa[i];
-            const unsigned r = i + ok_mg_lower(sm.sb, cb, v);
-            sm.mk[r] = v; if (COUNTS) sm.mc[r] = ac[s0.x + i];
+        // (every thread takes consecutive elements of a side: one binary search in the other side, then a walk)
+        {
+            const unsigned per = (ca + OK_MG_THREADS - 1) / OK_MG_THREADS, i0 = threadIdx.x * per, i1 = min(ca, i0 + per);
+            unsigned p = i0 < i1 ? ok_mg_lower(sm.sb, cb, sm.sa[i0]) : 0u;
+            for (unsigned i = i0; i < i1; ++i) {
+                const unsigned long long v = sm.sa[i];
+                p = ok_mg_lower_from(sm.sb, cb, v, p);              // #B elements < v
+                sm.mk[i + p] = v; if (COUNTS) sm.mc[i + p] = ac[s0.x + i];
+            }
         }
-        for (unsigned i = threadIdx.x; i < cb; i += OK_MG_THREADS) {
-            const unsigned long long v = sm.sb[i];
-            unsigned p = ok_mg_lower(sm.sa, ca, v);
-            p += (p < ca && sm.sa[p] == v) ? 1u : 0u;            // #A elements <= v
-            sm.mk[i + p] = v; if (COUNTS) sm.mc[i + p] = bc[s0.y + i];
+        {
+            const unsigned per = (cb + OK_MG_THREADS - 1) / OK_MG_THREADS, i0 = threadIdx.x * per, i1 = min(cb, i0 + per);
+            unsigned p = i0 < i1 ? ok_mg_lower(sm.sa, ca, sm.sb[i0]) : 0u;
+            for (unsigned i = i0; i < i1; ++i) {
+                const unsigned long long v = sm.sb[i];
+                p = ok_mg_lower_from(sm.sa, ca, v, p);              // #A elements < v
+                const unsigned le = p + ((p < ca && sm.sa[p] == v) ? 1u : 0u);    // #A elements <= v
+                sm.mk[i + le] = v; if (COUNTS) sm.mc[i + le] = bc[s0.y + i];
+            }
         }
         __syncthreads();
         // an element equal to its predecessor is the B copy of a pair: its count goes to the predecessor
