@@ -472,6 +472,7 @@ def reshard_sets(ok, torch, dist, k, mine, n_sets):
                 mine[i].copy_keys_device(int(bounds[i][r]), n, send.data_ptr() + 8 * at)
             at += n
     recv, recv_counts = exchange(dist, torch, send, send_counts)
+    torch.cuda.synchronize()      # the library reads `recv` on its own streams: the collective must have landed first
     seg = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)      # where source rank q's keys start
     shards, used = [], [0] * world
     for i in range(n_sets):
