@@ -176,3 +176,30 @@ def test_mt_variant_equals_faithful(oracle):
     a = oracle.count_batch(11, bases, off)
     b = oracle.count_batch_mt(11, bases, off, 4)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_large_input_checkers_equal_the_plain_restatement(oracle):
+    """orc_count_batch_ranged_mt (whole table of a batch too large for per-thread maps) and orc_count_batch_slice_mt (one
+    key slice) only reorganise the work: every window still goes through seq_to_u64 + canonical_u64 and an exact map.
+    Both must reproduce the single-threaded restatement of count.rs:23-38,106-119."""
+    import numpy as np
+    rng = np.random.default_rng(12)
+    alphabet = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    for k in (1, 3, 4, 5, 11, 21, 31, 32):
+        bases = alphabet[rng.integers(0, len(alphabet), 60_000)]
+        cuts = np.unique(rng.integers(0, len(bases), 400))
+        off = np.concatenate([[0], cuts, [len(bases)]]).astype(np.uint64)
+        wk, wc = oracle.count_batch(k, bases, off, 1, False)
+        for nt in (1, 3, 8):
+            gk, gc = oracle.count_batch_ranged_mt(k, bases, off, nt)
+            assert np.array_equal(gk, wk) and np.array_equal(gc, wc), (k, nt)
+            for mc in (2, 3):
+                fk, fc = oracle.count_batch_ranged_mt(k, bases, off, nt, mc)
+                assert np.array_equal(fk, wk[wc >= mc]) and np.array_equal(fc, wc[wc >= mc])
+        if len(wk) > 10:
+            lo, hi = int(wk[len(wk) // 4]), int(wk[3 * len(wk) // 4])
+            sk, sc = oracle.count_batch_slice_mt(k, bases, off, lo, hi, 4)
+            sel = (wk >= lo) & (wk <= hi)
+            assert np.array_equal(sk, wk[sel]) and np.array_equal(sc, wc[sel]), k
+        ek, ec = oracle.count_batch_slice_mt(k, bases, off, 0, 2 ** 64 - 1, 2)
+        assert np.array_equal(ek, wk) and np.array_equal(ec, wc)
