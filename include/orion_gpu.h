@@ -247,6 +247,18 @@ int ok_set_add_batch(ok_set* s, const uint8_t* bases, const uint64_t* rec_offset
 /* same, batch already resident in device memory */
 int ok_set_add_batch_device(ok_set* s, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets,
                             uint64_t n_records);
+/* build.rs:93-116 for MANY files at once: file i = the device-resident batch (d_bases[i], n_bases[i],
+ * d_rec_offsets[i], n_records[i]); out[i] = its sealed set.  The files are independent units: a few host threads
+ * (ORION_BUILD_THREADS, default 4) each drive their own pooled builder and streams, so one file's host round trips,
+ * allocations and launch gaps are covered by the kernels of the others.  Same sets as n calls of ok_set_create +
+ * ok_set_add_batch_device.  On error nothing is returned (all out[i] NULL). */
+int ok_sets_build_many_device(uint8_t k, int norm_mode, uint64_t n_files, const uint8_t* const* d_bases,
+                              const uint64_t* n_bases, const uint64_t* const* d_rec_offsets, const uint64_t* n_records,
+                              ok_set** out);
+/* the same with host batches (bases[i], rec_offsets[i], n_records[i]; rec_offsets[i][0] == 0): every worker copies
+ * its own file in, under the kernels of the others */
+int ok_sets_build_many(uint8_t k, int norm_mode, uint64_t n_files, const uint8_t* const* bases,
+                       const uint64_t* const* rec_offsets, const uint64_t* n_records, ok_set** out);
 /* a set from an existing sorted, duplicate-free host array (a reference loaded from a .db) */
 int ok_set_from_sorted(uint8_t k, const uint64_t* kmers, uint64_t n, ok_set** out);
 /* ... or device array (checked on the device; a key-range slice received from a peer in multi-GPU set algebra) */

@@ -117,6 +117,8 @@ ABI = {
     "ok_set_create": (C.c_int, [C.c_uint8, C.c_int, C.c_uint64, C.POINTER(vp)]),
     "ok_set_add_batch": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "ok_set_add_batch_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64]),
+    "ok_sets_build_many_device": (C.c_int, [C.c_uint8, C.c_int, C.c_uint64, vp, vp, vp, vp, C.POINTER(vp)]),
+    "ok_sets_build_many": (C.c_int, [C.c_uint8, C.c_int, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
     "ok_set_from_sorted": (C.c_int, [C.c_uint8, vp, C.c_uint64, C.POINTER(vp)]),
     "ok_set_from_sorted_device": (C.c_int, [C.c_uint8, vp, C.c_uint64, C.POINTER(vp)]),
     "ok_set_keys_device": (C.c_int, [vp, C.POINTER(vp), u64p]),
@@ -143,6 +145,9 @@ _HOOKS = {
     "okx_device_extract": (C.c_int, [vp, vp, C.c_uint64, C.c_uint, C.c_int, vp, C.c_uint64, u64p]),
     "okx_owner_of": (C.c_int, [vp, C.c_uint64, C.c_uint, C.c_int, vp]),
     "okx_plan_bits": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint, vp]),
+    "okx_strided_order": (C.c_int, [C.c_uint64, vp, C.c_uint64, u64p]),
+    "okx_ava_geometry": (C.c_int, [C.c_uint, vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp]),
+    "okx_ava_block": (C.c_int, [C.c_uint, C.c_uint, vp]),
 }
 
 _gpu = None
@@ -624,6 +629,32 @@ class KmerSet:
         h = vp()
         _check(lib().ok_set_from_sorted_device(k, d_kmers_ptr, n, C.byref(h)))
         return cls(h, k)
+
+    @classmethod
+    def build_many_device(cls, k, d_bases_ptrs, n_bases, d_offsets_ptrs, n_records, norm_mode=NORMALIZED):
+        """build.rs:93-116 for many files at once (ok_sets_build_many_device): file i is the device-resident batch
+        (d_bases_ptrs[i], n_bases[i], d_offsets_ptrs[i], n_records[i]) -> list of sealed sets"""
+        n = len(d_bases_ptrs)
+        pb = np.ascontiguousarray(d_bases_ptrs, dtype=np.uint64)
+        po = np.ascontiguousarray(d_offsets_ptrs, dtype=np.uint64)
+        nb = np.ascontiguousarray(n_bases, dtype=np.uint64)
+        nr = np.ascontiguousarray(n_records, dtype=np.uint64)
+        assert len(po) == len(nb) == len(nr) == n
+        out = (vp * n)()
+        _check(lib().ok_sets_build_many_device(k, norm_mode, n, _ptr(pb), _ptr(nb), _ptr(po), _ptr(nr), out))
+        return [cls(vp(h), k) for h in out]
+
+    @classmethod
+    def build_many(cls, k, batches, norm_mode=NORMALIZED):
+        """build.rs:93-116 for many files at once (ok_sets_build_many): batches = [(bases, offsets), ...] host arrays"""
+        keep = [(np.ascontiguousarray(b, dtype=np.uint8), np.ascontiguousarray(o, dtype=np.uint64)) for b, o in batches]
+        n = len(keep)
+        pb = np.array([b.ctypes.data for b, _ in keep], dtype=np.uint64)
+        po = np.array([o.ctypes.data for _, o in keep], dtype=np.uint64)
+        nr = np.array([len(o) - 1 for _, o in keep], dtype=np.uint64)
+        out = (vp * n)()
+        _check(lib().ok_sets_build_many(k, norm_mode, n, _ptr(pb), _ptr(po), _ptr(nr), out))
+        return [cls(vp(h), k) for h in out]
 
     def add_batch(self, bases, offsets):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)

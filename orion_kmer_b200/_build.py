@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.environ.get("ORION_GPU_LIB") or os.path.join(HERE, "liborion_gpu.so")   # ORION_GPU_LIB: A/B builds of the kernels (tuning runs)
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("orion_gpu.cu", "kernels.cuh", "kmer_math.cuh", "partition.cuh")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("orion_gpu.cu", "kernels.cuh", "kmer_math.cuh", "partition.cuh", "merge.cuh", "setops.cuh")]
 HEADER = os.path.join(ROOT, "include", "orion_gpu.h")
 
 NVCC_FLAGS = [

@@ -631,6 +631,77 @@ k_intersect_tiled(const unsigned long long* __restrict__ a, uint64_t na, const u
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, m);
 }
 
+// ---- membership by merge (query.rs:87-94 for a large database) ----
+// Which keys of the sorted duplicate-free array A occur in the sorted duplicate-free array B?  Same tiling as
+// k_intersect_tiled (A tile in registers, its range of B streamed through shared memory, every key of A and B read
+// once); the matching keys are appended to `out` in no particular order, *n_out counts them.  ok_probe_reads uses it
+// with A = the distinct k-mers of a read batch and B = a set of billions of keys: B is read front to back once
+// instead of being probed at random (a 40 GB hashed table answered 0.5 G probes/s: TLB and DRAM-page misses).
+__device__ __forceinline__ unsigned ok_is_match_mask(const unsigned long long* __restrict__ sb, unsigned cn,
+                                                     const unsigned long long (&ka)[OK_IS_TILE / 256], unsigned n_valid) {
+    unsigned hit = 0;
+    if (n_valid == 0 || ka[n_valid - 1] < sb[0] || ka[0] > sb[cn - 1]) return 0u;
+    unsigned l = 0, h = cn;
+    { const unsigned long long key = ka[0]; while (l < h) { const unsigned mid = (l + h) >> 1; if (sb[mid] < key) l = mid + 1; else h = mid; } }
+#pragma unroll
+    for (unsigned q = 0; q < OK_IS_TILE / 256; ++q) {
+        if (q >= n_valid) break;
+        const unsigned long long key = ka[q];
+        unsigned steps = 0;
+        while (l < cn && sb[l] < key) {
+            ++l;
+            if (++steps == 8u) {        // a long gap: binary search of what is left
+                unsigned lo = l, hi = cn;
+                while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (sb[mid] < key) lo = mid + 1; else hi = mid; }
+                l = lo;
+                break;
+            }
+        }
+        if (l >= cn) break;
+        if (sb[l] == key) hit |= 1u << q;
+    }
+    return hit;
+}
+__global__ void __launch_bounds__(256)
+k_member_tiled(const unsigned long long* __restrict__ a, uint64_t na, const unsigned long long* __restrict__ b,
+               const unsigned long long* __restrict__ tile_lo, unsigned long long* __restrict__ out,
+               unsigned long long* __restrict__ n_out) {
+    __shared__ unsigned long long sb[OK_IS_TILE];
+    const uint64_t n_tiles = (na + OK_IS_TILE - 1) / OK_IS_TILE;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint64_t i0 = t * OK_IS_TILE;
+        constexpr unsigned KPT = OK_IS_TILE / 256;
+        unsigned long long ka[KPT];
+        const uint64_t i1 = i0 + (uint64_t)threadIdx.x * KPT;          // this thread's consecutive keys
+        const unsigned n_valid = i1 >= na ? 0u : (unsigned)(na - i1 < KPT ? na - i1 : KPT);
+#pragma unroll
+        for (unsigned q = 0; q < KPT; ++q) ka[q] = q < n_valid ? a[i1 + q] : OK_EMPTY_KEY;
+        const uint64_t lo = tile_lo[t], hi = tile_lo[t + 1];
+        unsigned hit = 0;                                              // B is duplicate-free: a key matches in one chunk at most
+        for (uint64_t c = lo; c < hi; c += OK_IS_TILE) {
+            const unsigned cn = (unsigned)(hi - c < OK_IS_TILE ? hi - c : OK_IS_TILE);
+            __syncthreads();                               // the previous chunk is no longer being searched
+            for (unsigned j = threadIdx.x; j < cn; j += 256u) sb[j] = b[c + j];
+            __syncthreads();
+            hit |= ok_is_match_mask(sb, cn, ka, n_valid);
+        }
+        // one reservation per warp: inclusive scan of the lanes' match counts
+        const unsigned cnt = __popc(hit);
+        unsigned inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(OK_FULL, inc, o); if (lane >= o) inc += y; }
+        const unsigned total = __shfl_sync(OK_FULL, inc, 31);
+        unsigned long long base = 0;
+        if (lane == 31 && total) base = atomicAdd(n_out, (unsigned long long)total);
+        base = __shfl_sync(OK_FULL, base, 31);
+        unsigned long long pos = base + inc - cnt;
+#pragma unroll
+        for (unsigned q = 0; q < KPT; ++q)
+            if (hit >> q & 1u) out[pos++] = ka[q];
+    }
+}
+
 // ---- one ROW of an all-vs-all (compare.rs:51-60 for every pair): set A against many sets B_j in two launches ----
 // Per pair the tiled form above costs two launches; the 32,640 pairs of BASELINE.json configs[4] are 65,280 launches
 // of ~40 us each on one stream, and every pair re-reads A from DRAM.  Here the work items of a row are

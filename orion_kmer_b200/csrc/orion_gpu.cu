@@ -10,12 +10,14 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "orion_gpu.h"
 #include "kernels.cuh"
 #include "partition.cuh"
 #include "merge.cuh"
+#include "setops.cuh"
 
 #define OK_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -220,6 +222,7 @@ struct ok_counter {
     uint64_t pend_bases = 0, pend_rec = 0, pend_windows_before = 0;   // RUN_LEVEL1: the batch still sitting in d_bases / d_off
     ShardState shard;
     bool buf1_external = false;        // d_buf1 is the caller's peer-mapped buffer (never reallocated or freed here)
+    bool keys_sorted_runs = false;     // ok_set_union: the next key batch is a concatenation of sorted runs (strided level-1 gather)
     unsigned long long* d_run_keys = nullptr; uint64_t cap_run_keys = 0;
     unsigned long long* d_run_counts = nullptr; uint64_t cap_run_counts = 0;
     uint64_t n_run = 0, n_deferred = 0;
@@ -813,11 +816,18 @@ int part_count_keys_absorb(ok_counter* c, const uint64_t* d_keys, uint64_t n, in
     const uint64_t n_chunks = (n + 255) / 256;
     pl.stride = n_chunks > 16384 ? 16 : 1;
     const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    // a concatenation of sorted runs (ok_set_union): single-key sample + strided level-1 gather (partition.cuh)
+    const bool no_stride = getenv("ORION_UNION_NO_STRIDE") != nullptr;       // A/B knob: contiguous items as for any key array
+    const bool strided = c->keys_sorted_runs && depth == 0 && !((uintptr_t)d_keys & 15u) && !no_stride;
     TRY(part_layout(c, n, 256, n, pl));
     CU(cudaEventRecord(c->ev_p[0], c->s_main));
     CU(cudaMemsetAsync(pl.hist, 0, pl.n_sub * sizeof(unsigned), c->s_main));
-    LAUNCH(k_part_sample_keys, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + pl.stride - 1) / pl.stride, (uint64_t)grid_sm * 16)),
-           256, 0, c->s_main, (const unsigned long long*)d_keys, n, (uint64_t)pl.stride, pl.cfg, pl.hist);
+    if (strided)
+        LAUNCH(k_part_sample_keys_single, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n / pl.stride + 255) / 256, (uint64_t)grid_sm * 16)),
+               256, 0, c->s_main, (const unsigned long long*)d_keys, n, (uint64_t)pl.stride, pl.cfg, pl.hist);
+    else
+        LAUNCH(k_part_sample_keys, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + pl.stride - 1) / pl.stride, (uint64_t)grid_sm * 16)),
+               256, 0, c->s_main, (const unsigned long long*)d_keys, n, (uint64_t)pl.stride, pl.cfg, pl.hist);
     LAUNCH(k_part_plan_sums, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n, pl.chunk_sum);
     LAUNCH(k_part_plan, (pl.n_sub + 1023) / 1024, 1024, 0, c->s_main, pl.hist, pl.n_sub, pl.stride, (unsigned)n, pl.cfg.b2,
            pl.chunk_sum, (unsigned)pl.cap_bound, pl.beg, pl.cursor, pl.cap_end, pl.beg1, pl.cursor1, pl.end1, pl.scal);
@@ -825,13 +835,23 @@ int part_count_keys_absorb(ok_counter* c, const uint64_t* d_keys, uint64_t n, in
     {
         // one level-1 scatter over the whole key array, in items of 4096 keys
         const bool two = pl.cfg.b2 > 0;
-        LAUNCH(k_part_flat_items, 64, 1024, 0, c->s_main, (unsigned)n, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
-        auto kern = ((uintptr_t)d_keys & 15u) ? k_part_scatter_keys<1, false> : k_part_scatter_keys<1, true>;
-        TRY(set_smem(kern, sizeof(OkScatterKeysSmem)));
-        LAUNCH(kern, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, (const unsigned long long*)d_keys,
-               pl.item_off, pl.item_n, pl.item_bin, pl.scal, pl.cfg, two ? pl.cursor1 : pl.cursor,
-               (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2, (OkPartSpill{c->spill, c->d_stats}),
-               (const unsigned*)nullptr, 0u, 0u);
+        if (strided) {
+            LAUNCH(k_part_set_items, 1, 1, 0, c->s_main, pl.scal, (unsigned)ok_strided_items(n));
+            auto kern = k_part_scatter_keys<1, false, 0, true>;
+            TRY(set_smem(kern, sizeof(OkScatterKeysSmem)));
+            LAUNCH(kern, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, (const unsigned long long*)d_keys,
+                   pl.item_off, pl.item_n, pl.item_bin, pl.scal, pl.cfg, two ? pl.cursor1 : pl.cursor,
+                   (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2, (OkPartSpill{c->spill, c->d_stats}),
+                   (const unsigned*)nullptr, (unsigned)(n & 0xFFFFFFFFu), (unsigned)(n >> 32));
+        } else {
+            LAUNCH(k_part_flat_items, 64, 1024, 0, c->s_main, (unsigned)n, pl.item_off, pl.item_n, pl.item_bin, pl.scal);
+            auto kern = ((uintptr_t)d_keys & 15u) ? k_part_scatter_keys<1, false> : k_part_scatter_keys<1, true>;
+            TRY(set_smem(kern, sizeof(OkScatterKeysSmem)));
+            LAUNCH(kern, grid_sm * 2, OK_SK_THREADS, sizeof(OkScatterKeysSmem), c->s_main, (const unsigned long long*)d_keys,
+                   pl.item_off, pl.item_n, pl.item_bin, pl.scal, pl.cfg, two ? pl.cursor1 : pl.cursor,
+                   (const unsigned*)(two ? pl.end1 : pl.cap_end), two ? c->d_buf1 : c->d_buf2, (OkPartSpill{c->spill, c->d_stats}),
+                   (const unsigned*)nullptr, 0u, 0u);
+        }
         c->windows += n;
         CU(cudaMemcpyAsync(&c->d_stats->windows, &c->windows, 8, cudaMemcpyHostToDevice, c->s_main));
     }
@@ -2417,6 +2437,10 @@ struct ok_set {
     uint8_t* d_pb = nullptr; uint64_t cap_pb = 0;
     uint64_t* d_po = nullptr; uint64_t cap_po = 0;
     unsigned* d_ph = nullptr; uint64_t cap_ph = 0;
+    // scratch of the probe by merge (probe_reads_merge), kept across calls as well
+    unsigned long long* d_mlo = nullptr; uint64_t cap_mlo = 0;        // tile bounds in the set + the match counter
+    unsigned long long* d_mkeys = nullptr; uint64_t cap_mkeys = 0;    // the batch's distinct k-mers found in the set
+    unsigned long long* d_mtab = nullptr; uint64_t cap_mtab = 0;      // hashed table of those
 };
 
 namespace {
@@ -2487,6 +2511,74 @@ OK_EXPORT int ok_set_add_batch_device(ok_set* s, const uint8_t* d_bases, uint64_
     if (!s) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_add_batch_device: NULL handle");
     if (s->sealed || !s->builder) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_add_batch_device: the set is already sealed");
     return ok_counter_add_batch_device(s->builder, d_bases, n_bases, d_rec_offsets, n_records);
+}
+
+// build.rs:93-116 over many files: independent units, a few host threads each with its own builder (see the header).
+// n_bases == nullptr: host batches (every worker copies its own file in, under the kernels of the others).
+namespace {
+int sets_build_many(uint8_t k, int norm_mode, uint64_t n_files, const uint8_t* const* d_bases, const uint64_t* n_bases,
+                    const uint64_t* const* d_rec_offsets, const uint64_t* n_records, ok_set** out) {
+    const bool on_device = n_bases != nullptr;
+    if (n_files && (!d_bases || !d_rec_offsets || !n_records || !out))
+        return set_err(OK_ERR_INVALID_ARGUMENT, "ok_sets_build_many: NULL argument");
+    for (uint64_t i = 0; i < n_files; ++i) out[i] = nullptr;
+    if (k == 0 || k > 32) return invalid_k(k);          // build.rs:83-85
+    if (norm_mode != OK_NORM_NORMALIZED && norm_mode != OK_NORM_RAW) return set_err(OK_ERR_INVALID_ARGUMENT, "unknown norm_mode %d", norm_mode);
+    if (n_files == 0) return OK_SUCCESS;
+    TRY(ensure_init());
+    unsigned n_threads = 4;
+    if (const char* ev = getenv("ORION_BUILD_THREADS")) n_threads = (unsigned)std::min(16, std::max(1, atoi(ev)));
+    n_threads = (unsigned)std::min<uint64_t>(n_threads, n_files);
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> first_error{OK_SUCCESS};
+    std::mutex err_mu;
+    std::string err_text;
+    auto worker = [&] {
+        cudaSetDevice(g_device);                         // the current device is per-thread state
+        for (;;) {
+            const uint64_t i = next.fetch_add(1);
+            if (i >= n_files || first_error.load() != OK_SUCCESS) return;
+            ok_set* s = nullptr;
+            int r = ok_set_create(k, norm_mode, 0, &s);
+            if (r == OK_SUCCESS && n_records[i]) {
+                if (on_device) { if (n_bases[i]) r = ok_set_add_batch_device(s, d_bases[i], n_bases[i], d_rec_offsets[i], n_records[i]); }
+                else r = ok_set_add_batch(s, d_bases[i], d_rec_offsets[i], n_records[i]);
+            }
+            if (r == OK_SUCCESS) r = set_seal(s);
+            if (r != OK_SUCCESS) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (first_error.load() == OK_SUCCESS) { first_error.store(r); err_text = g_err; }      // g_err is this thread's own
+                ok_set_destroy(s);
+                return;
+            }
+            out[i] = s;
+        }
+    };
+    if (n_threads <= 1) worker();
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+        for (auto& th : pool) th.join();
+    }
+    if (first_error.load() != OK_SUCCESS) {
+        for (uint64_t i = 0; i < n_files; ++i) { ok_set_destroy(out[i]); out[i] = nullptr; }
+        g_err = err_text;
+        return first_error.load();
+    }
+    return OK_SUCCESS;
+}
+}  // namespace
+
+OK_EXPORT int ok_sets_build_many_device(uint8_t k, int norm_mode, uint64_t n_files, const uint8_t* const* d_bases,
+                                        const uint64_t* n_bases, const uint64_t* const* d_rec_offsets, const uint64_t* n_records,
+                                        ok_set** out) {
+    if (n_files && !n_bases) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_sets_build_many_device: NULL n_bases");
+    static const uint64_t none = 0;
+    return sets_build_many(k, norm_mode, n_files, d_bases, n_files ? n_bases : &none, d_rec_offsets, n_records, out);
+}
+OK_EXPORT int ok_sets_build_many(uint8_t k, int norm_mode, uint64_t n_files, const uint8_t* const* bases,
+                                 const uint64_t* const* rec_offsets, const uint64_t* n_records, ok_set** out) {
+    return sets_build_many(k, norm_mode, n_files, bases, nullptr, rec_offsets, n_records, out);
 }
 
 OK_EXPORT int ok_set_from_sorted(uint8_t k, const uint64_t* kmers, uint64_t n, ok_set** out) {
@@ -2690,7 +2782,9 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
             at += m;
         }
         if (e != cudaSuccess) { cudaFree(d_all); ok_set_destroy(u); return set_err(OK_ERR_CUDA, "CUDA error %s in ok_set_union", cudaGetErrorName(e)); }
+        u->builder->keys_sorted_runs = true;
         const int r = ok_counter_add_kmers_device(u->builder, (const uint64_t*)d_all, total);   // returns with the stream drained
+        u->builder->keys_sorted_runs = false;
         cudaStreamSynchronize(st);
         cudaFree(d_all);
         if (r != OK_SUCCESS) { ok_set_destroy(u); return r; }
@@ -2710,6 +2804,7 @@ OK_EXPORT int ok_set_destroy(ok_set* s) {
     if (!s) return OK_SUCCESS;
     if (s->builder) give_builder(s->builder);
     cudaFree(s->d_keys); cudaFree(s->d_table); cudaFree(s->d_pb); cudaFree(s->d_po); cudaFree(s->d_ph);
+    cudaFree(s->d_mlo); cudaFree(s->d_mkeys); cudaFree(s->d_mtab);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return OK_SUCCESS;
@@ -2751,6 +2846,91 @@ OK_EXPORT int ok_set_intersection_size(ok_set* a, ok_set* b, uint64_t* out) {
     return OK_SUCCESS;
 }
 
+namespace {
+// Tile geometry of the keyed all-vs-all (setops.cuh) from the first and last key of every non-empty set and the total
+// number of keys.  Host logic only (okx_ava_geometry replays it for the CPU tests).
+OkAvaGeo ava_geometry(unsigned k, const unsigned long long* ends /* 2 per set */, const uint64_t* ns, uint64_t n_sets, uint64_t total) {
+    OkAvaGeo g{};
+    g.key_shift = 64u - 2u * k;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (uint64_t s = 0; s < n_sets; ++s) {
+        if (!ns[s]) continue;
+        lo = std::min(lo, ok_phi32(ends[2 * s], g.key_shift));
+        hi = std::max(hi, ok_phi32(ends[2 * s + 1], g.key_shift));
+    }
+    if (lo > hi) { lo = 0; hi = 0; }                     // no keys at all
+    const uint64_t span = (uint64_t)hi - lo + 1u;
+    uint64_t tiles = std::max<uint64_t>(1, total / OK_AVA_TARGET);
+    tiles = std::min<uint64_t>(tiles, std::min<uint64_t>(span, 1ull << 22));
+    g.phi_lo = lo;
+    g.n_tiles = (unsigned)tiles;
+    g.scale = (tiles << 32) / span;                      // <= 2^32: (span - 1) * scale < tiles * 2^32
+    return g;
+}
+
+// 0: row by row (kernels.cuh); 1: key by key (setops.cuh).  ORION_AVA_KEYED=1 forces the keyed form onto any input
+// it can take (test hook), =0 switches it off (A/B knob).
+bool ava_keyed_wanted(ok_set* const* sets, uint64_t n, uint64_t n_parts) {
+    if (n_parts != 1 || n < 2 || n > OK_AVA_MAX_SETS) return false;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (sets[i]->has_max || sets[i]->n >= 0xFFFFFFFFull) return false;
+        total += sets[i]->n;
+    }
+    if (const char* ev = getenv("ORION_AVA_KEYED")) return atoi(ev) != 0;
+    return n >= 8 && total >= (1ull << 20);
+}
+
+// inter[i * n + j] (i < j) = |set i n set j| for all pairs at once; *done = false: a tile did not fit (clustered keys),
+// nothing was written and the caller takes the row form
+int ava_keyed(ok_set* const* sets, uint64_t n, uint64_t* inter, bool* done) {
+    *done = false;
+    cudaStream_t st = sets[0]->st;
+    const unsigned long long** d_ptrs = nullptr; unsigned long long *d_ns = nullptr, *d_ends = nullptr, *d_out = nullptr;
+    unsigned *d_bounds = nullptr, *d_failed = nullptr;
+    auto release = [&] { cudaFree((void*)d_ptrs); cudaFree(d_ns); cudaFree(d_ends); cudaFree(d_out); cudaFree(d_bounds); cudaFree(d_failed); };
+#define CUR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return set_err(e_ == cudaErrorMemoryAllocation ? OK_ERR_OUT_OF_MEMORY : OK_ERR_CUDA, "CUDA error %s in the keyed all-vs-all", cudaGetErrorName(e_)); } } while (0)
+    std::vector<const unsigned long long*> h_ptrs(n);
+    std::vector<unsigned long long> h_ns(n), h_ends(2 * n, 0ull);
+    uint64_t total = 0, max_n = 0;
+    for (uint64_t i = 0; i < n; ++i) { h_ptrs[i] = sets[i]->d_keys; h_ns[i] = sets[i]->n; total += sets[i]->n; max_n = std::max<uint64_t>(max_n, sets[i]->n); }
+    CUR(cudaMalloc((void**)&d_ptrs, n * sizeof(void*)));
+    CUR(cudaMalloc((void**)&d_ns, n * 8));
+    CUR(cudaMalloc((void**)&d_ends, 2 * n * 8));
+    CUR(cudaMalloc((void**)&d_out, n * n * 8));
+    CUR(cudaMalloc((void**)&d_failed, 4));
+    CUR(cudaMemcpyAsync((void*)d_ptrs, h_ptrs.data(), n * sizeof(void*), cudaMemcpyHostToDevice, st));
+    CUR(cudaMemcpyAsync(d_ns, h_ns.data(), n * 8, cudaMemcpyHostToDevice, st));
+    CUR(cudaMemsetAsync(d_ends, 0, 2 * n * 8, st));
+    CUR(cudaMemsetAsync(d_out, 0, n * n * 8, st));
+    CUR(cudaMemsetAsync(d_failed, 0, 4, st));
+    LAUNCH(k_ava_ends, (unsigned)((n + 255) / 256), 256, 0, st, d_ptrs, (const unsigned long long*)d_ns, (unsigned)n, d_ends);
+    CUR(cudaMemcpyAsync(h_ends.data(), d_ends, 2 * n * 8, cudaMemcpyDeviceToHost, st));
+    CUR(cudaStreamSynchronize(st));
+    if (total == 0) { release(); memset(inter, 0, n * n * 8); *done = true; return OK_SUCCESS; }
+    const OkAvaGeo g = ava_geometry(sets[0]->k, h_ends.data(), (const uint64_t*)h_ns.data(), n, total);
+    CUR(cudaMalloc((void**)&d_bounds, n * ((size_t)g.n_tiles + 1) * sizeof(unsigned)));
+    const unsigned grid_sm = (unsigned)(g_sms > 0 ? g_sms : 148);
+    const dim3 grid_b((unsigned)std::max<uint64_t>(1, std::min<uint64_t>((max_n + 255) / 256, 64)), (unsigned)n);
+    LAUNCH(k_ava_bounds, grid_b, 256, 0, st, d_ptrs, (const unsigned long long*)d_ns, g, d_bounds);
+    if (set_smem(k_ava_tiles, sizeof(OkAvaSmem)) != OK_SUCCESS) { release(); return OK_ERR_CUDA; }
+    LAUNCH(k_ava_tiles, std::min<unsigned>(g.n_tiles, grid_sm), OK_AVA_THREADS, sizeof(OkAvaSmem), st, d_ptrs, (unsigned)n, g,
+           (const unsigned*)d_bounds, d_out, d_failed);
+    unsigned failed = 0;
+    CUR(cudaMemcpyAsync(&failed, d_failed, 4, cudaMemcpyDeviceToHost, st));
+    CUR(cudaStreamSynchronize(st));
+    CUR(cudaGetLastError());
+    if (!failed) {
+        CUR(cudaMemcpyAsync(inter, d_out, n * n * 8, cudaMemcpyDeviceToHost, st));
+        CUR(cudaStreamSynchronize(st));
+        *done = true;
+    }
+#undef CUR
+    release();
+    return OK_SUCCESS;
+}
+}  // namespace
+
 // pairs (i < j) in row-major order, pair p belongs to part p % n_parts: sizes[n] and the upper-triangle entries of
 // this part's pairs (everything else in inter[n*n] is zero).  Multi-GPU: every rank holds all sets, takes one
 // part, and one all-reduce(sum) of the matrix completes it.
@@ -2765,6 +2945,12 @@ OK_EXPORT int ok_sets_all_vs_all_part(ok_set* const* sets, uint64_t n, uint64_t 
         if (sets[i]->k != sets[0]->k) return kmer_size_mismatch(sets[0]->k, sets[i]->k);
         TRY(set_seal(sets[i]));
         sizes[i] = sets[i]->n;
+    }
+    // Key by key (setops.cuh): every key of every set is read once and the whole matrix accumulated in one pass.
+    if (ava_keyed_wanted(sets, n, n_parts)) {
+        bool done = false;
+        TRY(ava_keyed(sets, n, inter, &done));
+        if (done) return OK_SUCCESS;
     }
     // Row by row: set i against every later set of this part in TWO launches (k_intersect_row_*), set i resident in
     // L2 for the whole row.  (Per pair -- two launches each, 65,280 for 256 sets -- it took 2.0 s at 256 x 5 M keys.)
@@ -2834,13 +3020,91 @@ OK_EXPORT int ok_sets_all_vs_all(ok_set* const* sets, uint64_t n, uint64_t* size
 }
 
 // ================================================================================= probes ==
+namespace {
+// query.rs:83-107 on a device-resident batch: d_hits[r] = windows of read r whose canonical k-mer is in the set.
+//
+// Small sets: a hashed table of the whole set (built once, on the first probe), one random probe per window.
+// Large sets (PROBE_MERGE_MIN_KEYS and up) are never hashed -- 2.5 G keys made a 40 GB table that answered
+// 0.5 G probes/s (TLB and DRAM-page misses on every probe) after a 40 GB build.  Instead, by merge:
+//   1. the batch's DISTINCT canonical k-mers, sorted           (the count path, a pooled builder)
+//   2. which of them are in the set                             (k_member_tiled: the set is streamed once, in order)
+//   3. a hashed table of just those (<= the batch's distinct k-mers, typically L2- or TLB-friendly)
+//   4. the per-read probe of the windows against that table     (the same k_extract<SinkProbeReads> as for small sets)
+// A window's k-mer is in the set iff it is in (batch k-mers n set), so the hits are the same integers.
+constexpr uint64_t PROBE_MERGE_MIN_KEYS = 1ull << 26;
+
+int probe_use_merge(const ok_set* s, uint64_t n_bases) {
+    if (const char* ev = getenv("ORION_PROBE_MERGE")) return atoi(ev) != 0;       // A/B knob and test hook: 1 always, 0 never
+    return s->n >= PROBE_MERGE_MIN_KEYS && n_bases >= PART_MIN_BASES && !s->d_table;
+}
+
+int probe_reads_merge(ok_set* s, int norm_mode, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec,
+                      unsigned* d_hits) {
+    ok_counter* c = nullptr;
+    TRY(take_builder((uint8_t)s->k, norm_mode, 0, &c));
+    struct Giveback { ok_counter* c; ~Giveback() { give_builder(c); } } gb{c};
+    TRY(ok_counter_add_batch_device(c, d_bases, n_bases, d_off, n_rec));
+    const uint64_t *dq = nullptr, *dqc = nullptr; uint64_t nq = 0;
+    TRY(ok_counter_finish_device(c, 1, &dq, &dqc, &nq));           // returns with the builder's stream drained
+    const uint64_t nb = s->n - (s->has_max ? 1 : 0);               // (u64::MAX is never a canonical k-mer of a read)
+    if (nq == 0 || nb == 0) return OK_SUCCESS;                     // d_hits is already zero
+    const uint64_t n_tiles = (nq + OK_IS_TILE - 1) / OK_IS_TILE;
+    TRY(dev_reserve(&s->d_mlo, &s->cap_mlo, n_tiles + 2));
+    TRY(dev_reserve(&s->d_mkeys, &s->cap_mkeys, nq));
+    unsigned long long* d_nm = s->d_mlo + n_tiles + 1;
+    CU(cudaMemsetAsync(d_nm, 0, 8, s->st));
+    LAUNCH(k_intersect_bounds, grid_for(n_tiles + 1), 256, 0, s->st, (const unsigned long long*)dq, nq, s->d_keys, nb, s->d_mlo);
+    LAUNCH(k_member_tiled, (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)(g_sms > 0 ? g_sms : 148) * 8), 256, 0, s->st,
+           (const unsigned long long*)dq, nq, s->d_keys, (const unsigned long long*)s->d_mlo, s->d_mkeys, d_nm);
+    unsigned long long nm = 0;
+    CU(cudaMemcpyAsync(&nm, d_nm, 8, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaGetLastError());
+    if (nm == 0) return OK_SUCCESS;
+    const uint64_t n_tab = std::max<uint64_t>(1024, 2 * (uint64_t)nm);
+    TRY(dev_reserve(&s->d_mtab, &s->cap_mtab, n_tab));
+    LAUNCH(k_fill_u64, grid_for(n_tab), 256, 0, s->st, s->d_mtab, n_tab, OK_EMPTY_KEY);
+    LAUNCH(k_keytable_build, grid_for(nm), 256, 0, s->st, s->d_mtab, n_tab, (const unsigned long long*)s->d_mkeys, (uint64_t)nm);
+    SinkProbeReads sink{};
+    sink.t = OkKeyTableView{s->d_mtab, n_tab, s->has_max};
+    sink.rec_off = d_off; sink.n_rec = n_rec; sink.hits = d_hits;
+    const uint64_t n_ex = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    launch_extract(nullptr, d_bases, n_bases, d_off, n_rec, 0, n_ex, s->st, sink, norm_mode, s->k);
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaGetLastError());
+    return OK_SUCCESS;
+}
+
+// d_hits zeroed on the set's stream, then one of the two forms; returns with the stream drained
+int probe_reads_device(ok_set* s, int norm_mode, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_off, uint64_t n_rec,
+                       unsigned* d_hits) {
+    TRY(set_seal(s));
+    CU(cudaMemsetAsync(d_hits, 0, n_rec * 4, s->st));
+    if (n_bases == 0) { CU(cudaStreamSynchronize(s->st)); return OK_SUCCESS; }
+    if (probe_use_merge(s, n_bases)) {
+        CU(cudaStreamSynchronize(s->st));            // the builder works on its own stream: the reads and the zeroed hits are in place
+        return probe_reads_merge(s, norm_mode, d_bases, n_bases, d_off, n_rec, d_hits);
+    }
+    TRY(set_table(s));
+    SinkProbeReads sink{};
+    sink.t = OkKeyTableView{s->d_table, s->n_table, s->has_max};
+    sink.rec_off = d_off; sink.n_rec = n_rec; sink.hits = d_hits;
+    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
+    launch_extract(nullptr, d_bases, n_bases, d_off, n_rec, 0, n_tiles, s->st, sink, norm_mode, s->k);
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaGetLastError());
+    return OK_SUCCESS;
+}
+}  // namespace
+
 OK_EXPORT int ok_probe_reads(ok_set* s, int norm_mode, const uint8_t* bases, const uint64_t* rec_offsets,
                              uint64_t n_records, uint32_t* hits_per_read) {
     if (!s || (n_records && (!rec_offsets || !hits_per_read)))
         return set_err(OK_ERR_INVALID_ARGUMENT, "ok_probe_reads: NULL argument");
     if (n_records == 0) return OK_SUCCESS;
     if (rec_offsets[0] != 0) return set_err(OK_ERR_INVALID_ARGUMENT, "rec_offsets[0] must be 0");
-    TRY(set_table(s));
+    if (norm_mode != OK_NORM_NORMALIZED && norm_mode != OK_NORM_RAW) return set_err(OK_ERR_INVALID_ARGUMENT, "unknown norm_mode %d", norm_mode);
+    TRY(set_seal(s));
     const uint64_t n_bases = rec_offsets[n_records];
     memset(hits_per_read, 0, n_records * sizeof(uint32_t));
     if (n_bases == 0) return OK_SUCCESS;
@@ -2850,12 +3114,7 @@ OK_EXPORT int ok_probe_reads(ok_set* s, int norm_mode, const uint8_t* bases, con
     uint8_t* d_b = s->d_pb; uint64_t* d_o = s->d_po; unsigned* d_h = s->d_ph;
     CU(cudaMemcpyAsync(d_b, bases, n_bases, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(d_o, rec_offsets, (n_records + 1) * 8, cudaMemcpyHostToDevice, s->st));
-    CU(cudaMemsetAsync(d_h, 0, n_records * 4, s->st));
-    SinkProbeReads sink{};
-    sink.t = OkKeyTableView{s->d_table, s->n_table, s->has_max};
-    sink.rec_off = d_o; sink.n_rec = n_records; sink.hits = d_h;
-    const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
-    launch_extract(nullptr, d_b, n_bases, d_o, n_records, 0, n_tiles, s->st, sink, norm_mode, s->k);
+    TRY(probe_reads_device(s, norm_mode, d_b, n_bases, d_o, n_records, d_h));
     CU(cudaMemcpyAsync(hits_per_read, d_h, n_records * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
     CU(cudaGetLastError());
@@ -2868,18 +3127,8 @@ OK_EXPORT int ok_probe_reads_device(ok_set* s, int norm_mode, const uint8_t* d_b
     if (!s || (n_records && (!d_rec_offsets || !d_hits_per_read))) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_probe_reads_device: NULL argument");
     if (n_records == 0) return OK_SUCCESS;
     if (n_bases && ((uintptr_t)d_bases & 15u)) return set_err(OK_ERR_INVALID_ARGUMENT, "d_bases must be 16-byte aligned");
-    TRY(set_table(s));
-    CU(cudaMemsetAsync(d_hits_per_read, 0, n_records * 4, s->st));
-    if (n_bases) {
-        SinkProbeReads sink{};
-        sink.t = OkKeyTableView{s->d_table, s->n_table, s->has_max};
-        sink.rec_off = d_rec_offsets; sink.n_rec = n_records; sink.hits = d_hits_per_read;
-        const uint64_t n_tiles = (n_bases + OK_TILE_BASES - 1) / OK_TILE_BASES;
-        launch_extract(nullptr, d_bases, n_bases, d_rec_offsets, n_records, 0, n_tiles, s->st, sink, norm_mode, s->k);
-    }
-    CU(cudaStreamSynchronize(s->st));
-    CU(cudaGetLastError());
-    return OK_SUCCESS;
+    if (norm_mode != OK_NORM_NORMALIZED && norm_mode != OK_NORM_RAW) return set_err(OK_ERR_INVALID_ARGUMENT, "unknown norm_mode %d", norm_mode);
+    return probe_reads_device(s, norm_mode, d_bases, n_bases, d_rec_offsets, n_records, d_hits_per_read);
 }
 
 // classify.rs:224-277 probes the SAME input count map against every reference: the input is uploaded once and
@@ -3056,5 +3305,44 @@ OK_EXPORT int okx_plan_bits(uint64_t n_units, uint64_t capacity_hint, unsigned k
     part_choose_bits(&c, n_units, pl, /*use_hint=*/true);
     out[0] = pl.cfg.b1 + pl.cfg.b2; out[1] = pl.cfg.b1; out[2] = pl.cfg.b2; out[3] = pl.hinted ? 1u : 0u; out[4] = pl.big_count ? 1u : 0u;
     out[5] = part_sliceable(pl) ? pl.n_sub / part_slice_step(pl) : 0u;
+    return OK_SUCCESS;
+}
+
+// the strided level-1 gather of a union (partition.cuh, k_part_scatter_keys<1, false, 0, true>) replayed on the host:
+// out[w * 4096 + t * 8 + q] = index of the key thread t of item w holds in register q (u64::MAX: none).  Host logic
+// only; the CPU tests check that every key of the array is read exactly once.
+OK_EXPORT int okx_strided_order(uint64_t n_keys, uint64_t* out, uint64_t cap, uint64_t* n_items) {
+    if (!out || !n_items) return set_err(OK_ERR_INVALID_ARGUMENT, "okx_strided_order: NULL argument");
+    const uint64_t rl = ok_strided_rows_len(n_keys), items = ok_strided_items(n_keys);
+    *n_items = items;
+    if (cap < items * OK_PART_TILE) return set_err(OK_ERR_INVALID_ARGUMENT, "okx_strided_order: out holds %llu entries, %llu needed",
+                                                   (unsigned long long)cap, (unsigned long long)(items * OK_PART_TILE));
+    for (uint64_t w = 0; w < items; ++w)
+        for (unsigned t = 0; t < OK_SK_THREADS; ++t)
+            for (unsigned q = 0; q < OK_SK_KPT; q += 2) {
+                const uint64_t i = ok_strided_index((uint64_t)(q / 2) * OK_SK_THREADS + t, w, rl);
+                uint64_t* o = out + w * OK_PART_TILE + (uint64_t)t * OK_SK_KPT + q;
+                o[0] = i < n_keys ? i : ~0ull;
+                o[1] = i + 1 < n_keys ? i + 1 : ~0ull;
+            }
+    return OK_SUCCESS;
+}
+
+
+// tile geometry of the keyed all-vs-all as ava_geometry derives it, and the tile of every key (host logic only):
+// geo[0] = n_tiles, [1] = phi_lo, [2] = scale; tiles[i] = ok_ava_tile(keys[i])
+OK_EXPORT int okx_ava_geometry(unsigned k, const uint64_t* ends, const uint64_t* ns, uint64_t n_sets, uint64_t total,
+                               const uint64_t* keys, uint64_t n_keys, uint64_t* geo, uint32_t* tiles) {
+    if (k == 0 || k > 32) return invalid_k(k);
+    if (!ends || !ns || !geo) return set_err(OK_ERR_INVALID_ARGUMENT, "okx_ava_geometry: NULL argument");
+    const OkAvaGeo g = ava_geometry(k, (const unsigned long long*)ends, ns, n_sets, total);
+    geo[0] = g.n_tiles; geo[1] = g.phi_lo; geo[2] = g.scale;
+    for (uint64_t i = 0; i < n_keys; ++i) tiles[i] = ok_ava_tile(keys[i], g);
+    return OK_SUCCESS;
+}
+// block (bi, bj) of thread b in k_ava_tiles: out[0] = owns a block (0/1), out[1] = bi, out[2] = bj
+OK_EXPORT int okx_ava_block(unsigned b, unsigned n_sets, uint32_t* out) {
+    unsigned bi, bj;
+    out[0] = ok_ava_block(b, (n_sets + 7u) / 8u, bi, bj) ? 1u : 0u; out[1] = bi; out[2] = bj;
     return OK_SUCCESS;
 }

@@ -107,6 +107,15 @@ k_part_sample_keys(const unsigned long long* __restrict__ keys, uint64_t n, uint
         if (i < n) atomicAdd(&hist[ok_phi_sub(ok_part_phi(keys[i], cfg), cfg)], 1u);
     }
 }
+// keys = a concatenation of SORTED runs (the union of sealed sets, db_types.rs:43-48): a 256-key chunk of a run covers a
+// handful of sub-partitions only and a sample of whole chunks says nothing about the others.  Here every `stride`-th
+// KEY is sampled (one 32-byte sector per sample, n / stride of them), which is the Poisson sample the plan assumes.
+__global__ void __launch_bounds__(256)
+k_part_sample_keys_single(const unsigned long long* __restrict__ keys, uint64_t n, uint64_t stride, OkPartCfg cfg,
+                          unsigned* __restrict__ hist) {
+    for (uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * stride; i < n; i += (uint64_t)gridDim.x * blockDim.x * stride)
+        atomicAdd(&hist[ok_phi_sub(ok_part_phi(__ldg(keys + i), cfg), cfg)], 1u);
+}
 
 // ------------------------------------------------------------------------------ planning --
 // block-wide exclusive scan helper (1024 threads): returns the exclusive prefix of v, total in *tot
@@ -760,13 +769,36 @@ struct OkScatterKeysSmem {
 // and the global cursor bumps of a round (the kernel is latency-, not issue-bound).
 #define OK_SK_KPT 8
 #define OK_SK_THREADS (OK_PART_TILE / OK_SK_KPT)
-template <int LEVEL, bool TMA = true, int KC = 0>  // LEVEL 1: bin by bin1 (keys arriving from peers); LEVEL 2: bin by bin2 inside a bin1
+// STRIDED (LEVEL 1, plain loads): src is a concatenation of SORTED runs (the union of sealed sets).  4096 consecutive
+// keys of a run fall into one or two bins: every rank comes from the same shared-memory counter and all but `cap` keys
+// of the round leave through the per-key overflow path (measured: 2.5 G keys/s against 70 G for shuffled keys).  So an
+// item is gathered from OK_SK_PLACES places spread evenly over the whole array, one 16-byte pair of keys from each
+// (ok_strided_index): the places of an item belong to different runs and key ranges, the bins fill evenly again, and
+// the eight items that share a 128-byte line run side by side (consecutive CTAs), so DRAM still sees whole lines.
+#define OK_SK_PLACES (OK_PART_TILE / 2u)
+// rows of the strided view: the array is cut into OK_SK_PLACES rows of `rl` 128-byte lines (16 keys)
+__host__ __device__ __forceinline__ uint64_t ok_strided_rows_len(uint64_t n_keys) {
+    const uint64_t n_lines = (n_keys + 15u) / 16u;
+    return (n_lines + OK_SK_PLACES - 1u) / OK_SK_PLACES;
+}
+__host__ __device__ __forceinline__ uint64_t ok_strided_items(uint64_t n_keys) { return 8u * ok_strided_rows_len(n_keys); }
+// first key index of pair `place` (0 .. OK_SK_PLACES) of item w: a bijection (place, w, 0/1) <-> [0, 16 rl OK_SK_PLACES)
+__host__ __device__ __forceinline__ uint64_t ok_strided_index(uint64_t place, uint64_t w, uint64_t rl) {
+    return (place * rl + (w >> 3)) * 16u + (w & 7u) * 2u;
+}
+__global__ void k_part_set_items(OkPartScalars* __restrict__ sc, unsigned n_items) { sc->n_items = n_items; }
+
+template <int LEVEL, bool TMA = true, int KC = 0, bool STRIDED = false>  // LEVEL 1: bin by bin1 (keys arriving from peers); LEVEL 2: bin by bin2 inside a bin1
 __global__ void __launch_bounds__(OK_SK_THREADS, 2)
 k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* __restrict__ item_off,
                     const unsigned* __restrict__ item_n, const unsigned* __restrict__ item_bin,
                     const OkPartScalars* __restrict__ scal, OkPartCfg cfg_in, unsigned* __restrict__ cursors,
                     const unsigned* __restrict__ bin_end, unsigned long long* __restrict__ out, OkPartSpill ps,
                     const unsigned* __restrict__ bin_first = nullptr, unsigned bin_lo = 0, unsigned bin_hi = 0) {
+    static_assert(!STRIDED || (LEVEL == 1 && !TMA), "the strided gather is a level-1 scatter with plain loads");
+    // STRIDED: there is no sliced run of a flat key array; (bin_lo, bin_hi) carry the number of keys in src instead
+    const uint64_t flat_n = STRIDED ? ((uint64_t)bin_hi << 32 | bin_lo) : 0;
+    if (STRIDED) { bin_first = nullptr; }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     OkScatterKeysSmem& sm = *reinterpret_cast<OkScatterKeysSmem*>(smem_raw);
     OkPartCfg cfg = cfg_in;
@@ -786,7 +818,8 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* 
     };
     // the descriptors of a round are fetched one round ahead (two dependent L2 round trips per round otherwise)
     unsigned n = 0, bin = 0;
-    if (w_begin + blockIdx.x < n_items) { n = item_n[w_begin + blockIdx.x]; if (LEVEL == 2) bin = item_bin[w_begin + blockIdx.x]; }
+    if (!STRIDED && w_begin + blockIdx.x < n_items) { n = item_n[w_begin + blockIdx.x]; if (LEVEL == 2) bin = item_bin[w_begin + blockIdx.x]; }
+    const uint64_t strided_rl = STRIDED ? ok_strided_rows_len(flat_n) : 0;
     if (TMA && threadIdx.x == 0) {
         ok_mbar_init(&sm.bar, 1);
         if (w_begin + blockIdx.x < n_items) load_item(w_begin + blockIdx.x, n);
@@ -796,7 +829,7 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* 
     for (unsigned w = w_begin + blockIdx.x; w < n_items; w += gridDim.x) {
         const unsigned wn = w + gridDim.x;
         unsigned n_next = 0, bin_next = 0;
-        if (wn < n_items) { n_next = item_n[wn]; if (LEVEL == 2) bin_next = item_bin[wn]; }
+        if (!STRIDED && wn < n_items) { n_next = item_n[wn]; if (LEVEL == 2) bin_next = item_bin[wn]; }
         const unsigned bin_base = LEVEL == 1 ? 0u : bin << cfg.b2;
         uint64_t key[OK_SK_KPT]; unsigned vm = 0;
         if (TMA) {
@@ -807,6 +840,18 @@ k_part_scatter_keys(const unsigned long long* __restrict__ src, const unsigned* 
                 key[q] = sm.in[i];
                 if (LEVEL == 1 && i + 1 == n && (n & 1u)) key[q] = src[item_off[w] + i];
                 if (i < n) vm |= 1u << q;
+            }
+        } else if (STRIDED) {
+#pragma unroll
+            for (int q = 0; q < OK_SK_KPT; q += 2) {
+                const uint64_t i = ok_strided_index((uint64_t)(q / 2) * OK_SK_THREADS + threadIdx.x, w, strided_rl);
+                key[q] = 0; key[q + 1] = 0;
+                if (i + 1 < flat_n) {        // (normal L2 policy: the neighbouring items read the rest of the line)
+                    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(src + i));
+                    key[q] = v.x; key[q + 1] = v.y; vm |= 3u << q;
+                } else if (i < flat_n) {
+                    key[q] = __ldg(src + i); vm |= 1u << q;
+                }
             }
         } else {
             const unsigned long long* __restrict__ keys = src + item_off[w];

@@ -496,6 +496,193 @@ def test_union_in_groups_matches_oracle(oracle, monkeypatch):
     assert list(ok.KmerSet.union([a, b, c]).to_array()) == [0, 1, 5, 9, 2 ** 64 - 1]
 
 
+@pytest.mark.parametrize("base_len", [500_000, 760_000])
+def test_union_of_sorted_sets_strided_gather(oracle, monkeypatch, base_len):
+    """db_types.rs:43-48 through ONE partitioned pass over the concatenated (sorted) sets.  The level-1 scatter gathers
+    its items from 2048 places of the array (k_part_scatter_keys<1, false, 0, true>) and the plan samples single keys;
+    the contiguous form (ORION_UNION_NO_STRIDE) and the oracle must give the same set.  The two sizes sit either side
+    of the sampling threshold (every key / every 16th key); the totals are odd (a last pair with one key)."""
+    k = 31
+    base = synth.genome(61, base_len)
+    gens = [base] + [synth.mutate(base, 10 + i, 3_000 * (i + 1)) for i in range(5)] + [synth.genome(62, 333_333), base[:77_777]]
+    sets = [ok.KmerSet.from_fastx(k, synth.fasta_text(b"g%d" % i, g)) for i, g in enumerate(gens)]
+    osets = [oracle.kmer_set_batch(k, g, np.array([0, len(g)], np.uint64)) for g in gens]
+    total = sum(len(o) for o in osets)
+    assert total > (1 << 20) and (total > 16384 * 256) == (base_len > 600_000)
+    want = oracle.set_union(osets)
+    for no_stride in (False, True):
+        if no_stride:
+            monkeypatch.setenv("ORION_UNION_NO_STRIDE", "1")
+        else:
+            monkeypatch.delenv("ORION_UNION_NO_STRIDE", raising=False)
+        u = ok.KmerSet.union(sets)
+        assert len(u) == len(want) and np.array_equal(u.to_array(), want), no_stride
+        u.close()
+    monkeypatch.delenv("ORION_UNION_NO_STRIDE", raising=False)
+    # an odd number of keys, and the sets in another order
+    three = len(osets[3]) + len(osets[7]) + len(osets[0])
+    last = osets[6][:len(osets[6]) - (three + len(osets[6]) + 1) % 2]          # makes the total odd
+    odd = [sets[3], sets[7], sets[0], ok.KmerSet.from_sorted(k, last)]
+    assert sum(len(x) for x in odd) % 2 == 1
+    u = ok.KmerSet.union(odd)
+    assert np.array_equal(u.to_array(), oracle.set_union([osets[3], osets[7], osets[0], last]))
+    for x in sets + [u, odd[3]]:
+        x.close()
+
+
+@pytest.mark.parametrize("mode", ["1", "0"])
+def test_query_by_merge_matches_hashed_probe_and_oracle(oracle, monkeypatch, mode):
+    """query.rs:83-107 in its two forms: ORION_PROBE_MERGE=1 forces the probe by merge that sets of >= 2^26 keys take
+    (distinct k-mers of the batch -> k_member_tiled against the sorted set -> hashed table of the matches -> per-read
+    probe), 0 the hashed table of the whole set.  Same integers either way, and the oracle's."""
+    import torch
+    monkeypatch.setenv("ORION_PROBE_MERGE", mode)
+    k = 31
+    g = synth.genome(50, 500_000)
+    other = synth.genome(51, 500_000)
+    kset = ok.KmerSet.from_fastx(k, synth.fasta_text(b"g", g))
+    oset = oracle.kmer_set_batch(k, g, np.array([0, len(g)], np.uint64))
+    n = 20_000
+    bases = np.concatenate([synth.reads(g, 52, n), synth.reads(other, 53, n)])      # 6 M bases: the one-shot count path
+    off = synth.read_offsets(2 * n)
+    want = oracle.query_hits(oset, k, bases, off, 8)
+    assert np.array_equal(kset.probe_reads(bases, off, ok.RAW).astype(np.uint64), want)
+    # the device-resident entry (bench `value` leg, sharded query)
+    d_b = torch.from_numpy(bases).cuda()
+    d_o = torch.from_numpy(off.view(np.int64)).cuda()
+    d_h = torch.full((2 * n,), 77, dtype=torch.int32, device="cuda")
+    kset.probe_reads_device(d_b.data_ptr(), len(bases), d_o.data_ptr(), 2 * n, d_h.data_ptr(), ok.RAW)
+    assert np.array_equal(d_h.cpu().numpy().astype(np.uint64), want)
+    # a small batch (table path of the counter), ragged reads incl. shorter than k and empty ones, lower case and U
+    rng = np.random.default_rng(4)
+    b2, o2 = random_batch(rng, 200_000, 40)
+    b2[:100_000] = g[:100_000]
+    b2[5000:5100] = np.frombuffer(bytes(g[5000:5100]).lower(), np.uint8)
+    b2[np.flatnonzero(b2[:100_000] == ord("T"))[::50]] = ord("U")              # RAW: not a base; NORMALIZED: T
+    assert np.array_equal(kset.probe_reads(b2, o2, ok.RAW).astype(np.uint64), oracle.query_hits(oset, k, b2, o2, 4))
+    b2t = np.where((b2 == ord("U")) | (b2 == ord("u")), np.uint8(ord("T")), b2)
+    assert np.array_equal(kset.probe_reads(b2, o2, ok.NORMALIZED).astype(np.uint64), oracle.query_hits(oset, k, b2t, o2, 4))
+    # an empty set / reads shorter than k only
+    empty = ok.KmerSet.from_sorted(k, np.zeros(0, np.uint64))
+    assert not empty.probe_reads(bases[:15000], off[:101], ok.RAW).any()
+    short = np.frombuffer(b"ACGTACGTAC" * 10, np.uint8)
+    assert not kset.probe_reads(short, np.arange(0, 101, 10, dtype=np.uint64), ok.RAW).any()
+    # a foreign k = 32 set holding u64::MAX: poly-A reads hit key 0 only
+    w = ok.KmerSet.from_sorted(32, np.array([0, 5, 2 ** 64 - 1], np.uint64))
+    polya = np.frombuffer(b"A" * 40 + b"T" * 40 + b"ACGT" * 10, np.uint8)
+    assert list(w.probe_reads(polya, np.array([0, 40, 80, 120], np.uint64), ok.RAW)) == [9, 9, 0]
+    for x in (kset, empty, w):
+        x.close()
+
+
+@pytest.mark.parametrize("threads", ["4", "1"])
+def test_build_many_matches_one_by_one_and_oracle(oracle, monkeypatch, threads):
+    """build.rs:93-116 over many files at once: several host threads, each with its own pooled builder, must give the
+    sets the one-file-at-a-time calls give (and the oracle's).  Files of very different sizes (one-shot path, table
+    path, empty, shorter than k), multi-record files, host and device entry."""
+    import torch
+    monkeypatch.setenv("ORION_BUILD_THREADS", threads)
+    k = 31
+    rng = np.random.default_rng(12)
+    files = []
+    for i in range(14):
+        n = int([2_000_000, 40_000, 1_300_000, 0, 20, 700_000, 5000][i % 7] * (1 + 0.1 * (i // 7)))
+        g = synth.genome(300 + i, max(n, 1))[:n]
+        cuts = np.unique(rng.integers(0, n + 1, size=3)) if n else np.zeros(0, np.int64)
+        off = np.concatenate([[0], cuts, [n]]).astype(np.uint64)
+        files.append((np.ascontiguousarray(g, dtype=np.uint8), off))
+    want = [oracle.kmer_set_batch(k, b, o) for b, o in files]
+    host = ok.KmerSet.build_many(k, files)
+    for s, w in zip(host, want):
+        assert len(s) == len(w) and np.array_equal(s.to_array(), w)
+    # device entry: every file padded to a 16-byte boundary inside one buffer
+    starts, at = [], 0
+    for b, _ in files:
+        starts.append(at)
+        at += (len(b) + 15) // 16 * 16
+    buf = np.zeros(max(at, 16), np.uint8)
+    for (b, _), st in zip(files, starts):
+        buf[st:st + len(b)] = b
+    d_buf = torch.from_numpy(buf).cuda()
+    d_offs = [torch.from_numpy(o.view(np.int64).copy()).cuda() for _, o in files]
+    dev = ok.KmerSet.build_many_device(k, [d_buf.data_ptr() + st for st in starts], [len(b) for b, _ in files],
+                                       [t.data_ptr() for t in d_offs], [len(o) - 1 for _, o in files])
+    for s, w in zip(dev, want):
+        assert np.array_equal(s.to_array(), w)
+    one = ok.KmerSet.build(k)
+    one.add_batch(*files[2])
+    assert np.array_equal(one.to_array(), want[2])
+    with pytest.raises(ok.OrionError, match="Invalid K-mer size"):
+        ok.KmerSet.build_many(33, files[:2])
+    for x in host + dev + [one]:
+        x.close()
+
+
+@pytest.mark.parametrize("keyed", ["1", "0"])
+def test_all_vs_all_keyed_matches_rows_and_numpy(oracle, monkeypatch, keyed):
+    """compare.rs:51-60 for every pair, in its two forms: ORION_AVA_KEYED=1 forces the one-pass keyed form (setops.cuh:
+    tiles of the key space, a hashed shared-memory table per tile, bit rows + popcount per pair block), 0 the row-by-row
+    merges.  Families of related genomes (keys shared by many sets), an identical copy, a tiny set, an empty set, an
+    unrelated genome; 13 sets (not a multiple of the 8 x 8 pair blocks), then key-range slices (a multi-GPU shard:
+    a narrow slice of the position space), then 2 sets."""
+    monkeypatch.setenv("ORION_AVA_KEYED", keyed)
+    k = 21
+    b1, b2 = synth.genome(71, 300_000), synth.genome(72, 200_000)
+    gens = [b1, synth.mutate(b1, 1, 300), synth.mutate(b1, 2, 3_000), synth.mutate(b1, 3, 15_000), b2, synth.mutate(b2, 4, 2_000),
+            synth.mutate(b2, 5, 10_000), b1, b1[:1000], synth.genome(73, 150_000), b2[50_000:120_000], synth.mutate(b1, 6, 100)]
+    sets = [ok.KmerSet.from_fastx(k, synth.fasta_text(b"g%d" % i, g)) for i, g in enumerate(gens)]
+    sets.insert(6, ok.KmerSet.from_sorted(k, np.zeros(0, np.uint64)))
+    arrs = [s.to_array() for s in sets]
+    assert np.array_equal(arrs[0], oracle.kmer_set_batch(k, b1, np.array([0, len(b1)], np.uint64)))
+    n = len(sets)
+    assert n == 13
+
+    def check(handles, arrays):
+        sizes, inter = ok.all_vs_all(handles)
+        for i in range(len(handles)):
+            assert sizes[i] == len(arrays[i]) == inter[i, i]
+            for j in range(i + 1, len(handles)):
+                want = len(np.intersect1d(arrays[i], arrays[j], assume_unique=True))
+                assert inter[i, j] == want == inter[j, i], (keyed, i, j)
+    check(sets, arrs)
+    # key-range slices: rank 5 of 8 owners, every set cut at the same boundaries
+    shards = []
+    for s in sets:
+        b = s.shard_bounds(8)
+        ptr, _ = s.keys_device()
+        shards.append(ok.KmerSet.from_sorted_device(k, ptr + 8 * int(b[5]), int(b[6] - b[5])))
+    check(shards, [a[int(s.shard_bounds(8)[5]):int(s.shard_bounds(8)[6])] for s, a in zip(sets, arrs)])
+    check([sets[0], sets[3]], [arrs[0], arrs[3]])
+    # the part form a sharded job uses (one part = everything): upper triangle only, the rest zero
+    sz, up = ok.all_vs_all_part(sets, 0, 1)
+    assert np.array_equal(ok.finish_all_vs_all(sz, up), ok.all_vs_all(sets)[1]) and not np.tril(up).any()
+    for x in sets + shards:
+        x.close()
+
+
+def test_all_vs_all_keyed_falls_back_on_clustered_keys(monkeypatch):
+    """keys sharing their first 16 bases share one position: the tile holding them outgrows the shared-memory table,
+    the keyed pass reports it and the matrix is computed row by row -- same integers."""
+    monkeypatch.setenv("ORION_AVA_KEYED", "1")
+    rng = np.random.default_rng(9)
+    k = 31
+    prefix = np.uint64(0x1234567) << np.uint64(30 + 2)           # the top 32 of the 62 key bits fixed
+    pool = np.unique(rng.integers(0, 1 << 30, size=30_000, dtype=np.uint64)) | prefix
+    spread = np.unique(np.minimum(rng.integers(0, 1 << 62, size=40_000, dtype=np.uint64), rng.integers(0, 1 << 62, size=40_000, dtype=np.uint64)))
+    arrs = []
+    for i in range(10):
+        pick = pool[rng.random(len(pool)) < 0.5]
+        arrs.append(np.unique(np.concatenate([pick, spread[rng.random(len(spread)) < 0.3]])))
+    sets = [ok.KmerSet.from_sorted(k, a) for a in arrs]
+    sizes, inter = ok.all_vs_all(sets)
+    for i in range(10):
+        assert sizes[i] == len(arrs[i])
+        for j in range(i + 1, 10):
+            assert inter[i, j] == len(np.intersect1d(arrs[i], arrs[j], assume_unique=True))
+    for x in sets:
+        x.close()
+
+
 def test_intersection_tiled_kernel_shapes():
     """k_intersect_bounds + k_intersect_tiled against numpy on shapes that stress the tiling: equal sets, disjoint
     ranges, a small set inside a large one (one tile of A against hundreds of chunks of B), interleaved keys, tile

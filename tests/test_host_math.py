@@ -209,3 +209,88 @@ def test_format_counts_threaded_chunks_match_the_oracle_byte_for_byte(oracle):
         assert text == oracle.format_counts(keys, counts, k), k
         assert text.count(b"\n") == len(keys)
     assert ok.format_counts(np.zeros(0, np.uint64), np.zeros(0, np.uint64), 31) == b""
+
+
+# ------------------------------- the strided level-1 gather of a union (host replay of the kernel's index map) --
+@pytest.mark.parametrize("n", [1, 2, 3, 15, 16, 17, 4095, 4096, 4097, 32767, 32768, 32769, 100_001, 1_234_567])
+def test_strided_gather_reads_every_key_once(n):
+    """k_part_scatter_keys<1, false, 0, true> gathers an item from 2048 places of the key array (ok_strided_index).
+    Every key index below n must be read by exactly one (item, thread, register), pairs must be 16-byte aligned, and
+    the places of one item must be spread over the whole array (that is the point: a sorted run no longer lands in
+    one bin)."""
+    import ctypes as C
+    n_items = C.c_uint64()
+    cap = (n // 32768 + 2) * 8 * 4096
+    out = np.full(cap, np.iinfo(np.uint64).max, dtype=np.uint64)
+    assert ok.lib().okx_strided_order(n, ok._ptr(out), cap, C.byref(n_items)) == 0
+    items = n_items.value
+    assert items % 8 == 0 and items * 4096 >= n and items * 4096 <= cap
+    got = out[:items * 4096]
+    valid = got[got != np.iinfo(np.uint64).max]
+    assert len(valid) == n and np.array_equal(np.sort(valid), np.arange(n, dtype=np.uint64))
+    pairs = got.reshape(-1, 2)
+    both = (pairs[:, 0] != np.iinfo(np.uint64).max) & (pairs[:, 1] != np.iinfo(np.uint64).max)
+    assert np.all(pairs[both, 0] % 2 == 0) and np.all(pairs[both, 1] == pairs[both, 0] + 1)
+    assert not np.any((pairs[:, 0] == np.iinfo(np.uint64).max) & (pairs[:, 1] != np.iinfo(np.uint64).max))
+    if n >= 1_000_000:
+        first = got[:4096].reshape(-1, 2)[:, 0]
+        first = np.sort(first[first != np.iinfo(np.uint64).max])
+        assert len(first) > 2000 and np.min(np.diff(first)) >= 16 * (n // 16 // 2048)      # one pair per row of the view
+
+
+# ------------------------------------------- keyed all-vs-all (setops.cuh): tile geometry and block ownership --
+def _phi32(key, k):
+    u = (int(key) << (64 - 2 * k)) & (2 ** 64 - 1)
+    w = ((~u) & (2 ** 64 - 1)) >> 32
+    return ((~(w * w)) & (2 ** 64 - 1)) >> 32
+
+
+@pytest.mark.parametrize("k,n_keys,target_sets", [(21, 200_000, 5), (31, 50_000, 3), (5, 600, 2), (32, 100_000, 4), (21, 4000, 1)])
+def test_ava_tiles_are_monotone_and_in_range(k, n_keys, target_sets):
+    """tile(key) = ((phi32(key) - phi_lo) * scale) >> 32 must be monotone in the key (the bounds kernel writes a bound
+    where the tile id changes between neighbours), below n_tiles for every key of every set, and the geometry must
+    follow from the sets' end keys alone.  A narrow key range (a multi-GPU shard) still spreads over all tiles."""
+    rng = np.random.default_rng(k * 1000 + n_keys)
+    hi = 2 ** (2 * k) if k < 32 else 2 ** 64
+    for lo_frac, hi_frac in ((0.0, 1.0), (0.25, 0.375)):
+        sets = []
+        for _ in range(target_sets):
+            a, b = (rng.integers(int(hi * lo_frac), max(int(hi * lo_frac) + 1, int(hi * hi_frac) - 1), size=n_keys, dtype=np.uint64, endpoint=True)
+                    for _ in range(2))
+            ks = np.unique(np.minimum(a, b) if lo_frac == 0.0 else a)      # canonical k-mers: the smaller of x and rc(x), density 2 (1 - u)
+            sets.append(ks)
+        sets.append(np.zeros(0, np.uint64))                  # an empty set takes no part in the geometry
+        ns = np.array([len(s) for s in sets], np.uint64)
+        ends = np.zeros(2 * len(sets), np.uint64)
+        for i, s in enumerate(sets):
+            if len(s):
+                ends[2 * i], ends[2 * i + 1] = s[0], s[-1]
+        allk = np.unique(np.concatenate(sets))
+        total = int(ns.sum())
+        geo = np.zeros(3, np.uint64)
+        tiles = np.zeros(len(allk), np.uint32)
+        assert ok.lib().okx_ava_geometry(k, ok._ptr(ends), ok._ptr(ns), len(sets), total, ok._ptr(allk), len(allk), ok._ptr(geo), ok._ptr(tiles)) == 0
+        n_tiles, phi_lo, scale = int(geo[0]), int(geo[1]), int(geo[2])
+        assert 1 <= n_tiles <= max(1, total // 3072) and n_tiles <= 1 << 22
+        assert np.all(np.diff(tiles.astype(np.int64)) >= 0) and int(tiles.max()) < n_tiles and int(tiles.min()) == 0
+        for i in rng.integers(0, len(allk), size=200):
+            assert int(tiles[i]) == ((_phi32(allk[i], k) - phi_lo) * scale) >> 32
+        if n_tiles >= 8:
+            assert int(tiles.max()) >= n_tiles - 2         # the last tiles are used: the range was rescaled, not clipped
+            fill = np.bincount(tiles, minlength=n_tiles)
+            assert fill.max() <= 6144                       # uniform keys: no tile near the table's limit
+
+
+@pytest.mark.parametrize("n_sets", [2, 7, 8, 9, 64, 200, 255, 256])
+def test_ava_blocks_cover_the_upper_triangle_once(n_sets):
+    nb = (n_sets + 7) // 8
+    seen = set()
+    out = np.zeros(3, np.uint32)
+    for b in range(576):
+        assert ok.lib().okx_ava_block(b, n_sets, ok._ptr(out)) == 0
+        if b < nb * (nb + 1) // 2:
+            assert out[0] == 1 and out[1] <= out[2] < nb
+            seen.add((int(out[1]), int(out[2])))
+        else:
+            assert out[0] == 0
+    assert seen == {(i, j) for i in range(nb) for j in range(i, nb)}
