@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <time.h>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -55,6 +56,24 @@ std::vector<ok_counter*> g_spare_builders;   // cleared set builders waiting for
         kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
         g_launches.fetch_add(1, std::memory_order_relaxed);          \
     } while (0)
+
+// ORION_TRACE=1: wall-clock laps of the host-side steps of the set operations on stderr (every lap drains the device
+// first, so a traced run is slower than a plain one; the laps say where the time goes)
+const bool g_trace = getenv("ORION_TRACE") != nullptr;
+struct TraceClock {
+    double t0 = 0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    TraceClock() { if (g_trace) { cudaDeviceSynchronize(); t0 = now(); } }
+    void lap(const char* fmt, ...) {
+        if (!g_trace) return;
+        cudaDeviceSynchronize();
+        const double t1 = now();
+        char buf[256];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        fprintf(stderr, "[orion trace] %-60s %9.3f ms\n", buf, t1 - t0);
+        t0 = now();
+    }
+};
 
 int ensure_init() {
     if (g_device >= 0) return OK_SUCCESS;
@@ -1486,8 +1505,12 @@ OK_EXPORT int ok_counter_add_kmers_device(ok_counter* c, const uint64_t* d_kmers
     TRY(part_settle(c));
     c->ms_insert = 0; c->ms_fill = 0;
     if (part_eligible(c, n) && n < (1ull << 31)) {
+        TraceClock tc;
         TRY(run_stash(c));
         const int r = part_count_keys(c, d_kmers, n);
+        tc.lap("add_kmers %llu keys: r=%d run=%llu deferred=%llu spilled=%llu sample %.2f l1 %.2f l2 %.2f count %.2f", (unsigned long long)n, r,
+               (unsigned long long)c->n_run, (unsigned long long)c->n_deferred, (unsigned long long)c->spilled_total, c->ms_sample, c->ms_scatter1,
+               c->ms_scatter2, c->ms_count);
         if (r == OK_SUCCESS) return run_unstash(c);
         if (r != PART_RETRY) return r;
     }
@@ -2418,7 +2441,9 @@ void give_builder(ok_counter* c) {
         std::lock_guard<std::mutex> lk(g_mu);
         if (g_spare_builders.size() < MAX_SPARE_BUILDERS) { g_spare_builders.push_back(c); return; }
     }
+    TraceClock tc;
     ok_counter_destroy(c);
+    tc.lap("give_builder: destroy (%.1f GB)", footprint * 1e-9);
 }
 }  // namespace
 
@@ -2450,8 +2475,10 @@ int set_seal(ok_set* s) {
     if (!s->st) CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     uint64_t n = 0;
     if (s->builder) {
+        TraceClock tc;
         const uint64_t *dk = nullptr, *dc = nullptr;
         TRY(ok_counter_finish_device(s->builder, 1, &dk, &dc, &n));
+        tc.lap("seal: finish_device %llu keys", (unsigned long long)n);
         const uint64_t total = n + (s->has_max ? 1 : 0);
         if (total) {
             CU(cudaMalloc((void**)&s->d_keys, total * 8));
@@ -2463,8 +2490,10 @@ int set_seal(ok_set* s) {
             CU(cudaStreamSynchronize(s->st));
         }
         n = total;
+        tc.lap("seal: malloc + copy");
         give_builder(s->builder);
         s->builder = nullptr;
+        tc.lap("seal: give_builder");
     }
     s->n = n;
     s->sealed = true;
@@ -2510,7 +2539,11 @@ OK_EXPORT int ok_set_add_batch(ok_set* s, const uint8_t* bases, const uint64_t* 
 OK_EXPORT int ok_set_add_batch_device(ok_set* s, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_rec_offsets, uint64_t n_records) {
     if (!s) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_add_batch_device: NULL handle");
     if (s->sealed || !s->builder) return set_err(OK_ERR_INVALID_ARGUMENT, "ok_set_add_batch_device: the set is already sealed");
-    return ok_counter_add_batch_device(s->builder, d_bases, n_bases, d_rec_offsets, n_records);
+    TraceClock tc;
+    const int r = ok_counter_add_batch_device(s->builder, d_bases, n_bases, d_rec_offsets, n_records);
+    tc.lap("set add_batch_device %llu bases: sample %.3f l1 %.3f l2 %.3f count %.3f (device ms)", (unsigned long long)n_bases, s->builder->ms_sample,
+           s->builder->ms_scatter1, s->builder->ms_scatter2, s->builder->ms_count);
+    return r;
 }
 
 // build.rs:93-116 over many files: independent units, a few host threads each with its own builder (see the header).
@@ -2554,12 +2587,14 @@ int sets_build_many(uint8_t k, int norm_mode, uint64_t n_files, const uint8_t* c
             out[i] = s;
         }
     };
+    TraceClock tc;
     if (n_threads <= 1) worker();
     else {
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < n_threads; ++t) pool.emplace_back(worker);
         for (auto& th : pool) th.join();
     }
+    tc.lap("build_many: %llu files, %u threads", (unsigned long long)n_files, n_threads);
     if (first_error.load() != OK_SUCCESS) {
         for (uint64_t i = 0; i < n_files; ++i) { ok_set_destroy(out[i]); out[i] = nullptr; }
         g_err = err_text;
@@ -2742,6 +2777,7 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
             while (j < n_sets && (j == i || keys + sets[j]->n <= group_keys)) keys += sets[j++]->n;
             ok_set* g = nullptr;
             int r;
+            TraceClock tc;
             if (j - i == 1) {      // one (large) set: it is its own union
                 r = ok_set_from_sorted_device((uint8_t)sets[i]->k, (const uint64_t*)sets[i]->d_keys, sets[i]->n, &g);
                 if (r == OK_SUCCESS) g->norm_mode = sets[i]->norm_mode;
@@ -2750,11 +2786,14 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
                 if (r == OK_SUCCESS) r = set_seal(g);
             }
             if (r != OK_SUCCESS) { ok_set_destroy(g); ok_set_destroy(acc); return r; }
+            tc.lap("union: group of %llu sets, %llu keys -> %llu", (unsigned long long)(j - i), (unsigned long long)keys, (unsigned long long)g->n);
             if (!acc) acc = g;
             else {
                 ok_set* m = nullptr;
                 r = set_merge_keys(acc, g, &m);
+                tc.lap("union: merge %llu + %llu", (unsigned long long)acc->n, (unsigned long long)g->n);
                 ok_set_destroy(acc); ok_set_destroy(g);
+                tc.lap("union: destroy merged inputs");
                 if (r != OK_SUCCESS) return r;
                 acc = m;
             }
@@ -2772,9 +2811,11 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
     uint64_t total = 0;
     for (uint64_t i = 0; i < n_sets; ++i) total += sets[i]->n - (sets[i]->has_max ? 1 : 0);
     if (n_sets > 1 && total >= PART_MIN_BASES && total < (1ull << 31) && !getenv("ORION_UNION_SETWISE")) {
+        TraceClock tc;
         unsigned long long* d_all = nullptr;
         cudaStream_t st = u->builder->s_main;
         cudaError_t e = cudaMalloc((void**)&d_all, total * 8);
+        tc.lap("union: malloc d_all %.1f GB", total * 8e-9);
         uint64_t at = 0;
         for (uint64_t i = 0; i < n_sets && e == cudaSuccess; ++i) {
             const uint64_t m = sets[i]->n - (sets[i]->has_max ? 1 : 0);
@@ -2782,11 +2823,14 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
             at += m;
         }
         if (e != cudaSuccess) { cudaFree(d_all); ok_set_destroy(u); return set_err(OK_ERR_CUDA, "CUDA error %s in ok_set_union", cudaGetErrorName(e)); }
+        tc.lap("union: concatenate");
         u->builder->keys_sorted_runs = true;
         const int r = ok_counter_add_kmers_device(u->builder, (const uint64_t*)d_all, total);   // returns with the stream drained
         u->builder->keys_sorted_runs = false;
         cudaStreamSynchronize(st);
+        tc.lap("union: add_kmers_device (incl. its buffers)");
         cudaFree(d_all);
+        tc.lap("union: free d_all");
         if (r != OK_SUCCESS) { ok_set_destroy(u); return r; }
         *out = u;
         return OK_SUCCESS;

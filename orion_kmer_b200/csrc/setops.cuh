@@ -11,9 +11,10 @@
 //                  x(key) of kmer_math.cuh; bounds[s][t] = first index of set s inside tile t (one streaming pass:
 //                  a thread writes a bound wherever the tile id changes between neighbouring keys)
 //   k_ava_tiles    one CTA per tile, persistent: (A) the tile's range of every set goes into a hashed shared-memory
-//                  table, key -> number of sets holding it; (B) keys held by >= 2 sets get dense ids (block scan);
-//                  (C) the ranges are streamed again (L1 / L2) and bit `id` of row s is set for every shared key of set
-//                  s; (D) thread (bi, bj) owns an 8 x 8 block of the pair matrix and adds popc(row_i & row_j) word by
+//                  table, key -> number of sets holding it (the ranges of all sets are one flat list of entries, four
+//                  loads per thread in flight); (B) keys held by >= 2 sets get dense ids (block scan); (C) bit `id` of
+//                  row s is set for every shared key of set s (from the entries' table slots, kept in shared memory);
+//                  (D) thread (bi, bj) owns an 8 x 8 block of the pair matrix and adds popc(row_i & row_j) word by
 //                  word into 64 registers, kept across all tiles of the CTA and flushed once at the end.
 //
 // Integer work throughout (AND + POPC on bit rows, shared-memory atomics): nothing for the tensor cores.  A tile
@@ -85,12 +86,15 @@ struct OkAvaSmem {
     unsigned long long key[OK_AVA_SLOTS];            // 64 KB
     unsigned cnt[OK_AVA_SLOTS];                      // 32 KB: sets holding the key; after (B): id + 1 of a shared key, 0 otherwise
     unsigned col[(OK_AVA_ROUND_IDS / 32u) * OK_AVA_MAX_SETS];   // 32 KB: word w of row s at [w * 256 + s]
-    unsigned lo[OK_AVA_MAX_SETS], len[OK_AVA_MAX_SETS];          // this tile's range of every set
+    unsigned ent[OK_AVA_MAX_ENTRIES];                // 24 KB: entry e of the tile = table slot | set << 13
+    const unsigned long long* ptr[OK_AVA_MAX_SETS];  // first key of this tile's range of every set
+    unsigned off[OK_AVA_MAX_SETS + 1u];              // entries of the sets before s (exclusive prefix of the range lengths)
     unsigned wsum[32];
-    unsigned n_entries, n_shared;
+    unsigned n_shared;
 };
 
-__global__ void __launch_bounds__(OK_AVA_THREADS, 1)
+// 576 threads x 112 registers = 63 K of the SM's 64 K (with __launch_bounds__(576, 1) ptxas stops at 96 and spills)
+__global__ void __maxnreg__(112)
 k_ava_tiles(const unsigned long long* const* __restrict__ keys, unsigned n_sets, OkAvaGeo g, const unsigned* __restrict__ bounds,
             unsigned long long* __restrict__ out /* n_sets x n_sets, entries i < j */, unsigned* __restrict__ failed) {
     extern __shared__ __align__(128) unsigned char ava_smem_raw[];
@@ -106,35 +110,57 @@ k_ava_tiles(const unsigned long long* const* __restrict__ keys, unsigned n_sets,
     const size_t brow = (size_t)g.n_tiles + 1u;
 
     for (unsigned t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
-        // ---- the tile's range of every set; an empty table
+        // ---- the tile's range of every set (thread s: set s), their exclusive prefix; an empty table
+        unsigned len = 0u, inc = 0u;
         if (tid < OK_AVA_MAX_SETS) {
-            unsigned lo = 0u, len = 0u;
-            if (tid < n_sets) { lo = bounds[tid * brow + t]; len = bounds[tid * brow + t + 1u] - lo; }
-            sm.lo[tid] = lo; sm.len[tid] = len;
+            const unsigned long long* p = nullptr;
+            if (tid < n_sets) { const unsigned lo = bounds[tid * brow + t]; len = bounds[tid * brow + t + 1u] - lo; p = keys[tid] + lo; }
+            sm.ptr[tid] = p;
+            inc = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(OK_FULL, inc, o); if ((int)lane >= o) inc += y; }
+            if (lane == 31u) sm.wsum[wid] = inc;
         }
         for (unsigned i = tid; i < OK_AVA_SLOTS; i += OK_AVA_THREADS) { sm.key[i] = OK_EMPTY_KEY; sm.cnt[i] = 0u; }
-        if (tid == 0) sm.n_entries = 0u;
         __syncthreads();
         if (tid < OK_AVA_MAX_SETS) {
-            const unsigned v = (unsigned)ok_warp_sum(sm.len[tid]);
-            if (lane == 0 && v) atomicAdd(&sm.n_entries, v);
+            unsigned before = 0u;
+            for (unsigned w = 0; w < wid; ++w) before += sm.wsum[w];
+            sm.off[tid] = before + inc - len;
+            if (tid == OK_AVA_MAX_SETS - 1u) sm.off[OK_AVA_MAX_SETS] = before + inc;
         }
         __syncthreads();
-        const unsigned n_entries = sm.n_entries;
-        __syncthreads();                                   // everybody has read it before the next tile resets it
+        const unsigned n_entries = sm.off[OK_AVA_MAX_SETS];     // (rewritten after the next tile's first barrier only)
         if (n_entries == 0u) continue;
         if (n_entries > OK_AVA_MAX_ENTRIES) { if (tid == 0) *failed = 1u; continue; }
-        // ---- (A) key -> number of sets holding it (a set holds a key once)
-        for (unsigned s = wid; s < n_sets; s += NW) {
-            const unsigned len = sm.len[s];
-            const unsigned long long* __restrict__ a = keys[s] + sm.lo[s];
-            for (unsigned j = lane; j < len; j += 32u) {
-                const unsigned long long key = __ldg(a + j);
-                unsigned h = ok_ava_hash(key);
-                for (;;) {
-                    const unsigned long long cur = atomicCAS(&sm.key[h], OK_EMPTY_KEY, key);
-                    if (cur == OK_EMPTY_KEY || cur == key) { atomicAdd(&sm.cnt[h], 1u); break; }
-                    h = (h + 1u) & (OK_AVA_SLOTS - 1u);
+        // ---- (A) key -> number of sets holding it (a set holds a key once).  Entry e of the tile belongs to the last
+        // set whose prefix is <= e; four loads per thread are in flight before the first insert.
+        for (unsigned e0 = tid; e0 < n_entries; e0 += OK_AVA_THREADS * 4u) {
+            unsigned long long kk[4];
+            unsigned ss[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned e = e0 + (unsigned)u * OK_AVA_THREADS;
+                kk[u] = OK_EMPTY_KEY; ss[u] = 0u;
+                if (e < n_entries) {
+                    unsigned lo = 0u, hi = OK_AVA_MAX_SETS - 1u;
+                    while (lo < hi) { const unsigned mid = (lo + hi + 1u) >> 1; if (sm.off[mid] <= e) lo = mid; else hi = mid - 1u; }
+                    ss[u] = lo;
+                    kk[u] = __ldg(sm.ptr[lo] + (e - sm.off[lo]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned e = e0 + (unsigned)u * OK_AVA_THREADS;
+                if (e < n_entries) {
+                    const unsigned long long key = kk[u];
+                    unsigned h = ok_ava_hash(key);
+                    for (;;) {
+                        const unsigned long long cur = atomicCAS(&sm.key[h], OK_EMPTY_KEY, key);
+                        if (cur == OK_EMPTY_KEY || cur == key) { atomicAdd(&sm.cnt[h], 1u); break; }
+                        h = (h + 1u) & (OK_AVA_SLOTS - 1u);
+                    }
+                    sm.ent[e] = h | (ss[u] << 13);
                 }
             }
         }
@@ -143,7 +169,7 @@ k_ava_tiles(const unsigned long long* const* __restrict__ keys, unsigned n_sets,
         const unsigned s0 = tid * SPT;
         unsigned mine = 0u;
         for (unsigned i = 0; i < SPT; ++i) { const unsigned q = s0 + i; if (q < OK_AVA_SLOTS && sm.cnt[q] >= 2u) ++mine; }
-        unsigned inc = mine;
+        inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(OK_FULL, inc, o); if ((int)lane >= o) inc += y; }
         if (lane == 31u) sm.wsum[wid] = inc;
@@ -172,19 +198,12 @@ k_ava_tiles(const unsigned long long* const* __restrict__ keys, unsigned n_sets,
             const unsigned n_words = (ids + 31u) / 32u;
             for (unsigned i = tid; i < n_words * OK_AVA_MAX_SETS; i += OK_AVA_THREADS) sm.col[i] = 0u;
             __syncthreads();
-            for (unsigned s = wid; s < n_sets; s += NW) {
-                const unsigned len = sm.len[s];
-                const unsigned long long* __restrict__ a = keys[s] + sm.lo[s];
-                for (unsigned j = lane; j < len; j += 32u) {
-                    const unsigned long long key = __ldg(a + j);
-                    unsigned h = ok_ava_hash(key);
-                    unsigned long long cur;                                             // it is there: (A) put it
-                    while ((cur = sm.key[h]) != key && cur != OK_EMPTY_KEY) h = (h + 1u) & (OK_AVA_SLOTS - 1u);
-                    const unsigned id1 = cur == key ? sm.cnt[h] : 0u;
-                    if (id1) {
-                        const unsigned r = id1 - 1u - base;                             // (wraps for ids of other rounds)
-                        if (r < ids) atomicOr(&sm.col[(r >> 5) * OK_AVA_MAX_SETS + s], 1u << (r & 31u));
-                    }
+            for (unsigned e = tid; e < n_entries; e += OK_AVA_THREADS) {
+                const unsigned v = sm.ent[e];
+                const unsigned id1 = sm.cnt[v & (OK_AVA_SLOTS - 1u)];
+                if (id1) {
+                    const unsigned r = id1 - 1u - base;                                 // (wraps for ids of other rounds)
+                    if (r < ids) atomicOr(&sm.col[(r >> 5) * OK_AVA_MAX_SETS + (v >> 13)], 1u << (r & 31u));
                 }
             }
             __syncthreads();
