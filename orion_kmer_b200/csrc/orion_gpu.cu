@@ -51,6 +51,57 @@ std::atomic<uint64_t> g_launches{0};
 std::mutex g_mu;
 std::vector<ok_counter*> g_spare_builders;   // cleared set builders waiting for the next ok_set_create (guarded by g_mu)
 
+// Streams of the sets: a small shared pool, handed out round-robin and never destroyed.  A stream per set -- 1,000
+// of them for the 1,000 genomes of BASELINE.json configs[3] -- made every device-wide synchronisation (cudaFree's
+// implicit one, first of all) walk a thousand streams: closing the sets took 0.4 - 8 ms each, the union's large frees
+// up to 270 ms.  Every set operation drains its stream before it returns, so sets can share them.
+// Key arrays of the sets: carved out of 1 GiB slabs.  A cudaMalloc costs ~0.35 ms whatever its size (measured: 0.37 ms
+// for 0.1 GB, 0.77 ms for 10 GB) -- 40 % of the time a 5 Mbp genome's set took to build -- and a cudaFree drains the
+// device.  A slab goes back to the device when the last set inside it is destroyed; arrays above a quarter of a slab
+// get an allocation of their own.
+struct KeySlab { unsigned long long* base; uint64_t cap, used; uint64_t live; };
+constexpr uint64_t KEY_SLAB_KEYS = 1ull << 27;          // 1 GiB
+KeySlab* g_cur_slab = nullptr;                          // guarded by g_mu
+cudaError_t keys_alloc(uint64_t n_keys, unsigned long long** out, KeySlab** owner) {
+    *owner = nullptr;
+    if (n_keys > KEY_SLAB_KEYS / 4) return cudaMalloc((void**)out, n_keys * 8);
+    const uint64_t need = (std::max<uint64_t>(n_keys, 1) + 31u) & ~31ull;       // 256-byte granules: 16-byte loads, TMA sources
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_cur_slab && g_cur_slab->live == 0) g_cur_slab->used = 0;              // nobody inside: start over
+    if (!g_cur_slab || g_cur_slab->used + need > g_cur_slab->cap) {
+        KeySlab* sl = new KeySlab{nullptr, KEY_SLAB_KEYS, 0, 0};
+        const cudaError_t e = cudaMalloc((void**)&sl->base, KEY_SLAB_KEYS * 8);
+        if (e != cudaSuccess) { delete sl; cudaGetLastError(); return cudaMalloc((void**)out, n_keys * 8); }     // (a device almost full: exact size)
+        if (g_cur_slab && g_cur_slab->live == 0) { cudaFree(g_cur_slab->base); delete g_cur_slab; }
+        g_cur_slab = sl;
+    }
+    *out = g_cur_slab->base + g_cur_slab->used;
+    g_cur_slab->used += need;
+    ++g_cur_slab->live;
+    *owner = g_cur_slab;
+    return cudaSuccess;
+}
+void keys_free(unsigned long long* p, KeySlab* owner) {
+    if (!owner) { cudaFree(p); return; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (--owner->live == 0 && owner != g_cur_slab) { cudaFree(owner->base); delete owner; }
+}
+
+constexpr int N_SET_STREAMS = 8;
+cudaStream_t g_set_streams[N_SET_STREAMS] = {};
+std::atomic<unsigned> g_set_stream_next{0};
+cudaError_t set_stream(cudaStream_t* out) {
+    const unsigned i = g_set_stream_next.fetch_add(1) % N_SET_STREAMS;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_set_streams[i]) {
+        const cudaError_t e = cudaStreamCreateWithFlags(&g_set_streams[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+    }
+    *out = g_set_streams[i];
+    return cudaSuccess;
+}
+
+
 #define LAUNCH(kern, grid, block, smem, stream, ...)                 \
     do {                                                             \
         kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
@@ -1282,6 +1333,8 @@ OK_EXPORT int ok_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& b : g_pool) cudaFreeHost(b.p);
     g_pool.clear();
+    for (auto& st : g_set_streams) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
+    if (g_cur_slab && g_cur_slab->live == 0) { cudaFree(g_cur_slab->base); delete g_cur_slab; g_cur_slab = nullptr; }
     g_device = -1;
     return OK_SUCCESS;
 }
@@ -2434,17 +2487,41 @@ int take_builder(uint8_t k, int norm_mode, uint64_t capacity_hint, ok_counter** 
     return ok_counter_create(k, norm_mode, capacity_hint, out);   // build.rs:83-85 validates k the same way
 }
 
+uint64_t builder_footprint(const ok_counter* c) {
+    return (c->cap_buf1 + c->cap_buf2 + c->cap_run_keys + c->cap_run_counts + c->cap_acc_keys + c->cap_mrg_keys) * 8 + c->cap_bases;
+}
+constexpr uint64_t BIG_BUILDER = 4ull << 30;
+std::atomic<int> g_keep_big_builders{0};       // > 0 while a union in groups is running: its multi-GB builder serves every group
+
 void give_builder(ok_counter* c) {
     if (!c) return;
-    const uint64_t footprint = (c->cap_buf1 + c->cap_buf2 + c->cap_run_keys + c->cap_run_counts + c->cap_acc_keys + c->cap_mrg_keys) * 8 + c->cap_bases;
-    if (c->n_shards == 1 && !c->buf1_external && footprint < (4ull << 30) && ok_counter_clear(c) == OK_SUCCESS) {      // multi-GB scratch goes back to the device
+    const uint64_t footprint = builder_footprint(c);
+    if (c->n_shards == 1 && !c->buf1_external && (footprint < BIG_BUILDER || g_keep_big_builders.load() > 0) && ok_counter_clear(c) == OK_SUCCESS) {      // multi-GB scratch goes back to the device
         std::lock_guard<std::mutex> lk(g_mu);
-        if (g_spare_builders.size() < MAX_SPARE_BUILDERS) { g_spare_builders.push_back(c); return; }
+        if (g_spare_builders.size() < MAX_SPARE_BUILDERS || footprint >= BIG_BUILDER) { g_spare_builders.push_back(c); return; }
     }
     TraceClock tc;
     ok_counter_destroy(c);
     tc.lap("give_builder: destroy (%.1f GB)", footprint * 1e-9);
 }
+
+// a union in groups (ok_set_union): the builder that counted one group, tens of GB of scratch, is kept for the next
+// one (destroying and regrowing it cost 30 - 270 ms per group); whatever multi-GB builder is pooled when the union
+// ends goes back to the device
+struct KeepBigBuilders {
+    KeepBigBuilders() { g_keep_big_builders.fetch_add(1); }
+    ~KeepBigBuilders() {
+        if (g_keep_big_builders.fetch_sub(1) != 1) return;
+        std::vector<ok_counter*> big;
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            for (size_t i = 0; i < g_spare_builders.size();)
+                if (builder_footprint(g_spare_builders[i]) >= BIG_BUILDER) { big.push_back(g_spare_builders[i]); g_spare_builders.erase(g_spare_builders.begin() + i); }
+                else ++i;
+        }
+        for (ok_counter* c : big) ok_counter_destroy(c);
+    }
+};
 }  // namespace
 
 struct ok_set {
@@ -2452,6 +2529,7 @@ struct ok_set {
     int norm_mode = 0;
     ok_counter* builder = nullptr;            // while batches are still being added
     unsigned long long* d_keys = nullptr;     // sorted, duplicate-free, once sealed
+    KeySlab* slab = nullptr;                  // the slab d_keys lives in (nullptr: an allocation of its own)
     uint64_t n = 0;
     bool sealed = false;
     int has_max = 0;                          // contains 0xFFFF...F (only possible for foreign k=32 sets)
@@ -2472,7 +2550,7 @@ namespace {
 
 int set_seal(ok_set* s) {
     if (s->sealed) return OK_SUCCESS;
-    if (!s->st) CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    if (!s->st) CU(set_stream(&s->st));
     uint64_t n = 0;
     if (s->builder) {
         TraceClock tc;
@@ -2481,7 +2559,7 @@ int set_seal(ok_set* s) {
         tc.lap("seal: finish_device %llu keys", (unsigned long long)n);
         const uint64_t total = n + (s->has_max ? 1 : 0);
         if (total) {
-            CU(cudaMalloc((void**)&s->d_keys, total * 8));
+            CU(keys_alloc(total, &s->d_keys, &s->slab));
             // on the set's own stream and drained here: every consumer runs on non-blocking streams, which the legacy
             // default stream does not order against, and the builder's buffer (dk) goes back to the pool right below
             if (n) CU(cudaMemcpyAsync(s->d_keys, dk, n * 8, cudaMemcpyDeviceToDevice, s->st));
@@ -2621,17 +2699,31 @@ OK_EXPORT int ok_set_from_sorted(uint8_t k, const uint64_t* kmers, uint64_t n, o
     *out = nullptr;
     if (k == 0 || k > 32) return invalid_k(k);
     if (n && !kmers) return set_err(OK_ERR_INVALID_ARGUMENT, "NULL kmers");
-    for (uint64_t i = 1; i < n; ++i)
-        if (kmers[i] <= kmers[i - 1]) return set_err(OK_ERR_INVALID_ARGUMENT, "kmers must be strictly ascending (index %llu)", (unsigned long long)i);
     TRY(ensure_init());
+    // (the order is checked on the device, after the upload: a host loop over the 1.28 G keys of 256 genome sets took
+    // longer than their transfer)
     ok_set* s = new ok_set();
     s->k = k; s->n = n; s->sealed = true;
     s->has_max = (n && kmers[n - 1] == OK_EMPTY_KEY) ? 1 : 0;
-    cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
-    if (e == cudaSuccess && n) e = cudaMalloc((void**)&s->d_keys, n * 8);
+    unsigned* d_bad = nullptr; unsigned bad = 0;
+    cudaError_t e = set_stream(&s->st);
+    if (e == cudaSuccess && n > 1) e = cudaMalloc((void**)&d_bad, 4);
+    if (e == cudaSuccess && n > 1) e = cudaMemsetAsync(d_bad, 0, 4, s->st);
+    if (e == cudaSuccess && n) e = keys_alloc(n, &s->d_keys, &s->slab);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(s->d_keys, kmers, n * 8, cudaMemcpyHostToDevice, s->st);
-    if (e == cudaSuccess && n) e = cudaStreamSynchronize(s->st);     // pageable source: the DMA has landed before anyone reads the set
+    if (e == cudaSuccess && n > 1) {
+        LAUNCH(k_check_ascending, grid_for(n), 256, 0, s->st, s->d_keys, n, d_bad);
+        e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s->st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);          // pageable source: the DMA has landed before anyone reads the set
+    cudaFree(d_bad);
     if (e != cudaSuccess) { ok_set_destroy(s); return set_err(OK_ERR_CUDA, "CUDA error %s in ok_set_from_sorted", cudaGetErrorName(e)); }
+    if (bad) {
+        ok_set_destroy(s);
+        uint64_t i = 1;
+        while (i < n && kmers[i] > kmers[i - 1]) ++i;
+        return set_err(OK_ERR_INVALID_ARGUMENT, "kmers must be strictly ascending (index %llu)", (unsigned long long)i);
+    }
     *out = s;
     return OK_SUCCESS;
 }
@@ -2646,10 +2738,10 @@ OK_EXPORT int ok_set_from_sorted_device(uint8_t k, const uint64_t* d_kmers, uint
     ok_set* s = new ok_set();
     s->k = k; s->n = n; s->sealed = true;
     unsigned* d_bad = nullptr; unsigned bad = 0; unsigned long long last = 0;
-    cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    cudaError_t e = set_stream(&s->st);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, 4, s->st);
-    if (e == cudaSuccess && n) e = cudaMalloc((void**)&s->d_keys, n * 8);
+    if (e == cudaSuccess && n) e = keys_alloc(n, &s->d_keys, &s->slab);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(s->d_keys, d_kmers, n * 8, cudaMemcpyDeviceToDevice, s->st);
     if (e == cudaSuccess && n > 1) LAUNCH(k_check_ascending, grid_for(n), 256, 0, s->st, s->d_keys, n, d_bad);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s->st);
@@ -2727,7 +2819,7 @@ int set_merge_keys(const ok_set* a, const ok_set* b, ok_set** out) {
     ulonglong2* d_split = nullptr; unsigned long long* d_tiles = nullptr;
     auto fail = [&](int code) { cudaFree(d_split); cudaFree(d_tiles); ok_set_destroy(u); return code; };
 #define CUM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(set_err(e_ == cudaErrorMemoryAllocation ? OK_ERR_OUT_OF_MEMORY : OK_ERR_CUDA, "CUDA error %s while merging two sets", cudaGetErrorName(e_))); } while (0)
-    CUM(cudaStreamCreateWithFlags(&u->st, cudaStreamNonBlocking));
+    CUM(set_stream(&u->st));
     const uint64_t na = a->n, nb = b->n, n_tiles = (na + nb + OK_MG_TILE - 1) / OK_MG_TILE;
     CUM(cudaMalloc((void**)&d_split, (n_tiles + 1) * sizeof(ulonglong2)));
     CUM(cudaMalloc((void**)&d_tiles, (n_tiles + 1) * 8));
@@ -2770,6 +2862,7 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
     if (sum > group_keys && n_sets > 1) {
         // more keys than one pass takes (1,000 genomes are 5e9): groups of sets, each group one pass, and the group
         // results folded together with the keys-only merge -- every key is read and written once per fold step
+        KeepBigBuilders keep;
         ok_set* acc = nullptr;
         uint64_t i = 0;
         while (i < n_sets) {
@@ -2847,9 +2940,9 @@ OK_EXPORT int ok_set_union(ok_set* const* sets, uint64_t n_sets, ok_set** out) {
 OK_EXPORT int ok_set_destroy(ok_set* s) {
     if (!s) return OK_SUCCESS;
     if (s->builder) give_builder(s->builder);
-    cudaFree(s->d_keys); cudaFree(s->d_table); cudaFree(s->d_pb); cudaFree(s->d_po); cudaFree(s->d_ph);
+    if (s->d_keys) keys_free(s->d_keys, s->slab);
+    cudaFree(s->d_table); cudaFree(s->d_pb); cudaFree(s->d_po); cudaFree(s->d_ph);
     cudaFree(s->d_mlo); cudaFree(s->d_mkeys); cudaFree(s->d_mtab);
-    if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return OK_SUCCESS;
 }
@@ -3087,9 +3180,11 @@ int probe_reads_merge(ok_set* s, int norm_mode, const uint8_t* d_bases, uint64_t
     ok_counter* c = nullptr;
     TRY(take_builder((uint8_t)s->k, norm_mode, 0, &c));
     struct Giveback { ok_counter* c; ~Giveback() { give_builder(c); } } gb{c};
+    TraceClock tc;
     TRY(ok_counter_add_batch_device(c, d_bases, n_bases, d_off, n_rec));
     const uint64_t *dq = nullptr, *dqc = nullptr; uint64_t nq = 0;
     TRY(ok_counter_finish_device(c, 1, &dq, &dqc, &nq));           // returns with the builder's stream drained
+    tc.lap("probe by merge: %llu bases -> %llu distinct k-mers", (unsigned long long)n_bases, (unsigned long long)nq);
     const uint64_t nb = s->n - (s->has_max ? 1 : 0);               // (u64::MAX is never a canonical k-mer of a read)
     if (nq == 0 || nb == 0) return OK_SUCCESS;                     // d_hits is already zero
     const uint64_t n_tiles = (nq + OK_IS_TILE - 1) / OK_IS_TILE;
@@ -3104,6 +3199,7 @@ int probe_reads_merge(ok_set* s, int norm_mode, const uint8_t* d_bases, uint64_t
     CU(cudaMemcpyAsync(&nm, d_nm, 8, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
     CU(cudaGetLastError());
+    tc.lap("probe by merge: %llu of them in the set of %llu keys", nm, (unsigned long long)nb);
     if (nm == 0) return OK_SUCCESS;
     const uint64_t n_tab = std::max<uint64_t>(1024, 2 * (uint64_t)nm);
     TRY(dev_reserve(&s->d_mtab, &s->cap_mtab, n_tab));
@@ -3116,6 +3212,7 @@ int probe_reads_merge(ok_set* s, int norm_mode, const uint8_t* d_bases, uint64_t
     launch_extract(nullptr, d_bases, n_bases, d_off, n_rec, 0, n_ex, s->st, sink, norm_mode, s->k);
     CU(cudaStreamSynchronize(s->st));
     CU(cudaGetLastError());
+    tc.lap("probe by merge: table of the matches + per-read probe");
     return OK_SUCCESS;
 }
 

@@ -93,8 +93,11 @@ struct OkAvaSmem {
     unsigned n_shared;
 };
 
-// 576 threads x 112 registers = 63 K of the SM's 64 K (with __launch_bounds__(576, 1) ptxas stops at 96 and spills)
-__global__ void __maxnreg__(112)
+// (registers are handed out to 4 warps at a time: 18 warps count as 20, which leaves 96 registers per thread)
+#ifndef OK_AVA_MLP
+#define OK_AVA_MLP 4               // loads a thread has in flight in (A)
+#endif
+__global__ void __launch_bounds__(OK_AVA_THREADS, 1)
 k_ava_tiles(const unsigned long long* const* __restrict__ keys, unsigned n_sets, OkAvaGeo g, const unsigned* __restrict__ bounds,
             unsigned long long* __restrict__ out /* n_sets x n_sets, entries i < j */, unsigned* __restrict__ failed) {
     extern __shared__ __align__(128) unsigned char ava_smem_raw[];
@@ -135,11 +138,11 @@ k_ava_tiles(const unsigned long long* const* __restrict__ keys, unsigned n_sets,
         if (n_entries > OK_AVA_MAX_ENTRIES) { if (tid == 0) *failed = 1u; continue; }
         // ---- (A) key -> number of sets holding it (a set holds a key once).  Entry e of the tile belongs to the last
         // set whose prefix is <= e; four loads per thread are in flight before the first insert.
-        for (unsigned e0 = tid; e0 < n_entries; e0 += OK_AVA_THREADS * 4u) {
-            unsigned long long kk[4];
-            unsigned ss[4];
+        for (unsigned e0 = tid; e0 < n_entries; e0 += OK_AVA_THREADS * OK_AVA_MLP) {
+            unsigned long long kk[OK_AVA_MLP];
+            unsigned ss[OK_AVA_MLP];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < OK_AVA_MLP; ++u) {
                 const unsigned e = e0 + (unsigned)u * OK_AVA_THREADS;
                 kk[u] = OK_EMPTY_KEY; ss[u] = 0u;
                 if (e < n_entries) {
@@ -150,7 +153,7 @@ k_ava_tiles(const unsigned long long* const* __restrict__ keys, unsigned n_sets,
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < OK_AVA_MLP; ++u) {
                 const unsigned e = e0 + (unsigned)u * OK_AVA_THREADS;
                 if (e < n_entries) {
                     const unsigned long long key = kk[u];

@@ -470,6 +470,12 @@ def test_key_range_shards_add_up_to_the_whole(oracle):
         import torch
         bad = torch.tensor([5, 9, 9, 12], dtype=torch.int64, device="cuda")
         ok.KmerSet.from_sorted_device(k, bad.data_ptr(), 4)
+    # the host entry checks the order on the device as well (after the upload) and still names the offending index
+    with pytest.raises(ok.OrionError, match=r"strictly ascending \(index 3\)"):
+        ok.KmerSet.from_sorted(k, np.array([1, 5, 9, 9, 12], np.uint64))
+    with pytest.raises(ok.OrionError, match=r"strictly ascending \(index 1\)"):
+        ok.KmerSet.from_sorted(k, np.array([7, 3], np.uint64))
+    assert list(ok.KmerSet.from_sorted(k, np.array([7], np.uint64)).to_array()) == [7]
 
 
 def test_union_in_groups_matches_oracle(oracle, monkeypatch):
