@@ -249,7 +249,7 @@ int ok_set_add_batch_device(ok_set* s, const uint8_t* d_bases, uint64_t n_bases,
                             uint64_t n_records);
 /* build.rs:93-116 for MANY files at once: file i = the device-resident batch (d_bases[i], n_bases[i],
  * d_rec_offsets[i], n_records[i]); out[i] = its sealed set.  The files are independent units: a few host threads
- * (ORION_BUILD_THREADS, default 4) each drive their own pooled builder and streams, so one file's host round trips,
+ * (ORION_BUILD_THREADS, default 2) each drive their own pooled builder and streams, so one file's host round trips,
  * allocations and launch gaps are covered by the kernels of the others.  Same sets as n calls of ok_set_create +
  * ok_set_add_batch_device.  On error nothing is returned (all out[i] NULL). */
 int ok_sets_build_many_device(uint8_t k, int norm_mode, uint64_t n_files, const uint8_t* const* d_bases,
