@@ -439,10 +439,12 @@ def build_sets(ok, dist, k, genomes, make_batch):
     return mine
 
 
-def reshard_sets(ok, torch, dist, k, mine, n_sets):
+def reshard_sets(ok, torch, dist, k, mine, n_sets, key_device="cuda"):
     """mine: {global index: KmerSet} whole sets held by this rank (every index on exactly one rank).
     -> (shards, sizes): n_sets KmerSets holding THIS rank's key range of every set (global index order), and the
-    full sizes of all sets (np.uint64[n_sets]).  One all-to-all of the keys is the only exchange."""
+    full sizes of all sets (np.uint64[n_sets]).  One all-to-all of the keys is the only exchange.
+    key_device: where the send / receive buffers of the keys live -- always "cuda" with the library; the CPU tests of
+    this bookkeeping (gloo, a numpy stand-in for the sets) pass "cpu"."""
     rank, world = dist.get_rank(), dist.get_world_size()
     coll = Coll(dist, torch)
     dev = "cuda" if coll.native else "cpu"
@@ -462,7 +464,7 @@ def reshard_sets(ok, torch, dist, k, mine, n_sets):
     part = t.cpu().numpy()
     # send buffer: for every destination rank, its slice of each of my sets (ascending set index)
     send_counts = [int(sum(part[i][r] for i in idx)) for r in range(world)]
-    send = torch.empty(max(1, sum(send_counts)), dtype=torch.int64, device="cuda")
+    send = torch.empty(max(1, sum(send_counts)), dtype=torch.int64, device=key_device)
     at = 0
     for r in range(world):
         for i in idx:
@@ -471,7 +473,8 @@ def reshard_sets(ok, torch, dist, k, mine, n_sets):
                 mine[i].copy_keys_device(int(bounds[i][r]), n, send.data_ptr() + 8 * at)
             at += n
     recv, recv_counts = exchange(dist, torch, send, send_counts)
-    torch.cuda.synchronize()      # the library reads `recv` on its own streams: the collective must have landed first
+    if key_device == "cuda":
+        torch.cuda.synchronize()  # the library reads `recv` on its own streams: the collective must have landed first
     seg = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)      # where source rank q's keys start
     shards, used = [], [0] * world
     for i in range(n_sets):
@@ -482,12 +485,12 @@ def reshard_sets(ok, torch, dist, k, mine, n_sets):
     return shards, part.sum(axis=1).astype(np.uint64)
 
 
-def all_vs_all_sharded(ok, torch, dist, k, mine, n_sets):
+def all_vs_all_sharded(ok, torch, dist, k, mine, n_sets, key_device="cuda"):
     """compare.rs:51-60 for every pair of n_sets sets spread over the ranks: identical key-range sharding of every
     set, every rank computes the whole n x n matrix over ITS key range, one all-reduce(sum) adds the ranges up.
     -> (sizes, full symmetric intersection matrix), on every rank."""
     coll = Coll(dist, torch)
-    shards, sizes = reshard_sets(ok, torch, dist, k, mine, n_sets)
+    shards, sizes = reshard_sets(ok, torch, dist, k, mine, n_sets, key_device)
     _, upper = ok.all_vs_all_part(shards, 0, 1)
     m = torch.from_numpy(upper.view(np.int64).copy()).to("cuda" if coll.native else "cpu")
     coll.all_reduce(m)
