@@ -205,11 +205,15 @@ def oracle_slice_checker():
 
 
 def run_reference(args):
+    """--impl reference, configs 2 and 3: the oracle port (the Rust crate cannot be built here) on a bounded sample of
+    OUR arm's workload -- same genome, same reads, same `config` object -- with the threads the reference itself uses
+    for this path: one (count.rs:68-79 is a sequential loop over the records)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(1, args.gpus)
     n_reads = args.reads
-    genome_len = args.genome or n_reads * 5
+    genome_len = (args.genome or n_reads * 5) * (world if world > 1 else 1)      # as multi.bench: coverage stays 30x
     sample = args.sample_reads
     vals = []
     base = None
@@ -220,13 +224,48 @@ def run_reference(args):
     v = float(np.mean(vals))
     sample_bases = min(sample, n_reads) * READ_LEN
     base["value"] = v
+    if world > 1:
+        from orion_kmer_b200 import multi
+        config = multi.bench_config(workload_config, args.config, n_reads, genome_len, world)
+    else:
+        config = workload_config(n_reads, genome_len, 1)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "bases/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample_bases / v,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "config": workload_config(n_reads, genome_len, args.gpus),
+            "higher_is_better": True, "scaling": "strong" if args.config == 3 else "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": config,
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+CONFIG1 = {"workload": "count canonical 21-mers in a single synthetic 5 Mbp genome record (BASELINE.json configs[0])",
+           "k": 21, "n_runs": 10, "lower_case": "1 %", "seed": 1, "min_count": 1,
+           "l2": "80 MB of keys against a 126 MB L2: partly L2-resident; the step is launch-latency bound (~15 launches)"}
+
+
+def run_reference_config1(args):
+    """--impl reference --config 1: the oracle port over the whole 5 Mbp genome record (k = 21), one thread"""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle
+    from orion_kmer_b200 import synth
+    oracle.build()
+    g = synth.config1_genome()
+    off = np.array([0, len(g)], np.uint64)
+    ts = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        keys, _ = oracle.count_batch(21, g, off)
+        if i >= args.warmup:
+            ts.append(time.perf_counter() - t0)
+    dt = float(np.mean(ts))
+    v = len(g) / dt
+    base = {"value": v, "unit": "bases/s", "cores": 1, "kind": "port",
+            "sample": f"the whole genome ({len(g)} bases), {dt:.2f} s, {len(keys)} distinct", "host_cores_available": os.cpu_count()}
+    print(json.dumps({"impl": "reference", "metric": "bases/sec counted (canonical k=21)", "value": v, "unit": "bases/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": dict(CONFIG1, bases=int(len(g))),
+                      "cpu_baseline": base, "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def workload_config(n_reads, genome_len, n_gpus):
@@ -501,9 +540,7 @@ def run_config1(args, ok, synth, torch, local):
     line = {"metric": "bases/sec counted (canonical k=21)", "value": len(g) / dt, "unit": "bases/s", "n_gpus": 1, "steps": steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "count canonical 21-mers in a single synthetic 5 Mbp genome record (BASELINE.json configs[0])",
-                       "k": k, "bases": int(len(g)), "n_runs": 10, "lower_case": "1 %", "seed": 1, "min_count": 1,
-                       "l2": "80 MB of keys against a 126 MB L2: partly L2-resident; the step is launch-latency bound (~15 launches)"},
+            "config": dict(CONFIG1, bases=int(len(g))),
             "e2e": {"value": len(g) / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3, "h2d_bytes_per_step": int(len(g) + 16),
                     "d2h_bytes_per_step": int(16 * n_out)},
             "gpu_launches": int(launches), "clocks": clocks,
@@ -674,6 +711,8 @@ def main():
     if args.impl == "reference":
         if args.config in (4, 5):
             run_reference_sets(args)
+        elif args.config == 1:
+            run_reference_config1(args)
         else:
             run_reference(args)
     else:

@@ -574,6 +574,26 @@ def verify_sharded_table(ok, dist, sc, K, bases, off, n_windows, slice_checker=N
     return out
 
 
+def sub_batches(n_reads):
+    """A rank's share may be more than one pass can take (32-bit offsets inside a batch): sub-batches of <= 11 M reads,
+    each exchanged and counted on its own and merged into the rank's shard (reads are 150 bases: cuts at multiples
+    of 8 reads keep the 16-byte alignment).  -> [(first read, end read), ...]"""
+    MAXR = 11_000_000
+    n_sub = (n_reads + MAXR - 1) // MAXR
+    per = ((n_reads + n_sub - 1) // n_sub + 7) // 8 * 8
+    return [(a, min(n_reads, a + per)) for a in range(0, n_reads, per)]
+
+
+def bench_config(workload_config, config, n_reads, genome_len, world):
+    """the `config` object of a sharded bench line (n_reads per rank, genome_len of the whole job): bench.py's reference
+    arm prints the same one"""
+    extra = {}
+    if config == 3:
+        extra = {"workload": f"count canonical 31-mers from {n_reads * world}x150bp synthetic reads key-range-sharded over "
+                             f"{world} GPUs (BASELINE.json configs[2])", "total_reads": n_reads * world}
+    return dict(workload_config(n_reads, genome_len, world), sub_batches_per_rank=len(sub_batches(n_reads)), **extra)
+
+
 def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config, ClockSampler, measured_peak,
           metric, numa_node=None, slice_checker=None):
     import torch.distributed as dist
@@ -589,13 +609,7 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
     hint = args.hint or int(n_bases * 0.17)       # expected distinct k-mers per rank (30x coverage, 0.5 % errors)
     sc = ShardedCounter(ok, torch, dist, K, fused=int(os.environ.get("ORION_FUSED", "3")), capacity_hint=hint)
 
-    # a rank's share may be more than one pass can take (32-bit offsets inside a batch): sub-batches of <= 11 M reads,
-    # each exchanged and counted on its own and merged into the rank's shard (reads are 150 bases: cuts at multiples
-    # of 8 reads keep the 16-byte alignment)
-    MAXR = 11_000_000
-    n_sub = (n_reads + MAXR - 1) // MAXR
-    per = ((n_reads + n_sub - 1) // n_sub + 7) // 8 * 8
-    cuts = [(a, min(n_reads, a + per)) for a in range(0, n_reads, per)]
+    cuts = sub_batches(n_reads)
 
     def count_all():
         for a, b in cuts:
@@ -685,10 +699,7 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong" if getattr(args, "config", 2) == 3 else "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": dict(workload_config(n_reads, genome_len, world), sub_batches_per_rank=len(cuts),
-                           **({"workload": f"count canonical 31-mers from {n_reads * world}x150bp synthetic reads key-range-sharded over "
-                                           f"{world} GPUs (BASELINE.json configs[2])", "total_reads": n_reads * world}
-                              if getattr(args, "config", 2) == 3 else {})),
+            "config": bench_config(workload_config, getattr(args, "config", 2), n_reads, genome_len, world),
             "e2e": {"value": total_bases / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3,
                     "h2d_bytes_per_step": int((n_bases + (n_reads + 1) * 8) * world),
                     "d2h_bytes_per_step": int(16 * distinct), "rank0_numa_node": numa_node},
