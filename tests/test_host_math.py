@@ -294,3 +294,44 @@ def test_ava_blocks_cover_the_upper_triangle_once(n_sets):
         else:
             assert out[0] == 0
     assert seen == {(i, j) for i in range(nb) for j in range(i, nb)}
+
+
+def test_ava_keyed_algorithm_replayed_on_the_host_matches_pairwise_intersections():
+    """The keyed all-vs-all (setops.cuh) replayed in numpy over the library's own tile geometry: cut every set at the
+    tile bounds, per tile count the holders of each key, give the keys with >= 2 holders a bit each, and add
+    popcount(row_i & row_j) to the pair matrix.  The sum over tiles must be |A n B| for every pair (compare.rs:58) --
+    the claim the CUDA kernel rests on -- and no tile may exceed the shared-memory table (6144 entries)."""
+    rng = np.random.default_rng(5)
+    k = 21
+    pool = np.unique(np.minimum(rng.integers(0, 1 << 42, 60_000, dtype=np.uint64), rng.integers(0, 1 << 42, 60_000, dtype=np.uint64)))
+    sets = [pool[rng.random(len(pool)) < f] for f in (0.6, 0.5, 0.9, 0.0, 0.2, 1.0, 0.05, 0.5, 0.7)]
+    sets[7] = np.unique(np.concatenate([sets[7], rng.integers(0, 1 << 42, 5000, dtype=np.uint64)]))     # keys nobody else holds
+    n = len(sets)
+    ns = np.array([len(s) for s in sets], np.uint64)
+    ends = np.zeros(2 * n, np.uint64)
+    for i, s in enumerate(sets):
+        if len(s):
+            ends[2 * i], ends[2 * i + 1] = s[0], s[-1]
+    geo = np.zeros(3, np.uint64)
+    inter = np.zeros((n, n), np.int64)
+    per_set_tiles = []
+    for s in sets:
+        tiles = np.zeros(len(s), np.uint32)
+        assert ok.lib().okx_ava_geometry(k, ok._ptr(ends), ok._ptr(ns), n, int(ns.sum()), ok._ptr(s), len(s), ok._ptr(geo), ok._ptr(tiles)) == 0
+        assert np.all(np.diff(tiles.astype(np.int64)) >= 0)         # monotone: a tile is one contiguous range of the sorted set
+        per_set_tiles.append(tiles)
+    n_tiles = int(geo[0])
+    assert n_tiles == int(ns.sum()) // 3072
+    for t in range(n_tiles):
+        ranges = [s[tl == t] for s, tl in zip(sets, per_set_tiles)]
+        entries = np.concatenate(ranges)
+        assert len(entries) <= 6144
+        keys, holders = np.unique(entries, return_counts=True)
+        shared = keys[holders >= 2]                                 # dense ids = positions in `shared`
+        rows = np.zeros((n, len(shared)), bool)
+        for i, r in enumerate(ranges):
+            rows[i, np.searchsorted(shared, r[np.isin(r, shared, assume_unique=True)])] = True
+        inter += rows.astype(np.int64) @ rows.astype(np.int64).T    # popcount(row_i & row_j) for every pair
+    for i in range(n):
+        for j in range(i + 1, n):
+            assert inter[i, j] == len(np.intersect1d(sets[i], sets[j], assume_unique=True)), (i, j)
