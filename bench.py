@@ -184,7 +184,9 @@ def cpu_baseline(n_reads_total, genome_len, sample_reads, all_cores=True):
     out = {"value": len(bases) / dt, "unit": "bases/s", "cores": 1, "kind": "port",
            "sample": f"first {sample_reads} reads ({len(bases)} bases) of the workload, {dt:.2f} s, "
                      f"{len(keys)} distinct",
-           "host_cores_available": os.cpu_count()}
+           "host_cores_available": os.cpu_count(),
+           "note": "a bounded sample, not BASELINE.md's full run: its table is several times smaller than the full job's and "
+                   "friendlier to the CPU caches, so the CPU figure is if anything flattering (the speed-up is conservative)"}
     if all_cores:
         nt = min(os.cpu_count() or 1, 64)
         t0 = time.perf_counter()
