@@ -122,9 +122,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
+NUMA_NOTE = {"why": "not attempted"}
+
+
 def bind_to_gpu_numa_node(gpu):
     """Run this rank (and first-touch its page-locked buffers) on the CPUs next to its GPU: with 8 ranks
-    on a two-socket host, buffers on the wrong node cross the socket link on every H2D / D2H copy."""
+    on a two-socket host, buffers on the wrong node cross the socket link on every H2D / D2H copy.
+    -> the node, or None (NUMA_NOTE["why"] then says what was found)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -135,6 +139,7 @@ def bind_to_gpu_numa_node(gpu):
         dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
         node = int(open(dev + "/numa_node").read())
         if node < 0:
+            NUMA_NOTE["why"] = f"{dev}/numa_node reads {node}: the host exposes no NUMA node for this GPU"
             return None
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
@@ -143,8 +148,10 @@ def bind_to_gpu_numa_node(gpu):
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
+        NUMA_NOTE["why"] = f"bound to node {node} ({len(cpus)} CPUs)" if cpus else f"node {node} has no CPU this process may run on"
         return node
-    except Exception:
+    except Exception as e:
+        NUMA_NOTE["why"] = f"{type(e).__name__}: {e}"
         return None
 
 
@@ -307,7 +314,8 @@ def run_ours(args):
     if world > 1:
         from orion_kmer_b200 import multi
         return multi.bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config,
-                           ClockSampler, measured_peak, METRIC, numa_node, slice_checker=oracle_slice_checker())
+                           ClockSampler, measured_peak, METRIC, numa_node, slice_checker=oracle_slice_checker(),
+                           numa_note=NUMA_NOTE["why"])
 
     g, bases, off = make_workload(ok, synth, n_reads, genome_len)
     n_bases = len(bases)
@@ -459,7 +467,7 @@ def run_ours(args):
         "e2e": {"value": n_bases / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3,
                 "h2d_bytes_per_step": int(n_bases + (n_reads + 1) * 8), "d2h_bytes_per_step": int(16 * n_out),
                 "add_batch_ms": float(np.mean(e2e_t["add_batch_ms"])), "finish_ms": float(np.mean(e2e_t["finish_ms"])),
-                "numa_node": numa_node,
+                "numa_node": numa_node, "numa_note": NUMA_NOTE["why"],
                 "two_jobs_in_flight": None if dt_pipe is None else {
                     "value": n_bases / dt_pipe, "unit": "bases/s", "ms_per_job": dt_pipe * 1e3,
                     "note": "informational: two counters, two host threads, job i+1's H2D under job i's D2H"},

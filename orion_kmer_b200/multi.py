@@ -595,7 +595,7 @@ def bench_config(workload_config, config, n_reads, genome_len, world):
 
 
 def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_config, ClockSampler, measured_peak,
-          metric, numa_node=None, slice_checker=None):
+          metric, numa_node=None, slice_checker=None, numa_note=None):
     import torch.distributed as dist
     K = 31
     n_reads = args.reads
@@ -702,7 +702,7 @@ def bench(args, ok, synth, torch, world, rank, local, make_workload, workload_co
             "config": bench_config(workload_config, getattr(args, "config", 2), n_reads, genome_len, world),
             "e2e": {"value": total_bases / dt_e2e, "unit": "bases/s", "ms_per_step": dt_e2e * 1e3,
                     "h2d_bytes_per_step": int((n_bases + (n_reads + 1) * 8) * world),
-                    "d2h_bytes_per_step": int(16 * distinct), "rank0_numa_node": numa_node},
+                    "d2h_bytes_per_step": int(16 * distinct), "rank0_numa_node": numa_node, "rank0_numa_note": numa_note},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole step (route + all-to-all + sharded count), rank 0 phases below",
                          "achieved": alg_step / dt / 1e9, "peak": peak * world, "unit": "GB/s",
