@@ -248,10 +248,12 @@ class IoError(OSError):
     pass
 
 
-def read_file(path, by_magic=False):
-    """utils.rs:125-152 (codec by extension) or, by_magic, the raw read + needletail sniff of build/classify"""
+def read_file(path, by_magic=False, fastx=False):
+    """utils.rs:125-152 (codec by extension: the .db files); by_magic: the raw read + needletail's magic sniff
+    (gzip / bzip2 / xz) of build and classify; fastx: the extension codec and THEN the sniff, the way count and query
+    read their FASTA/FASTQ inputs (count.rs:59-63)"""
     H = host_lib()
-    h = H.okh_read_file(os.fsencode(path), 1 if by_magic else 0)
+    h = H.okh_read_file(os.fsencode(path), 1 if by_magic else (2 if fastx else 0))
     if not h:
         raise IoError(H.okh_io_last_error().decode())
     try:

@@ -35,7 +35,7 @@ void okh_batch_free(void* h);
 uint64_t okh_format_counts(const uint64_t* kmers, const uint64_t* counts, uint64_t n, unsigned k, char* out);
 uint64_t okh_format_counts_size(const uint64_t* counts, uint64_t n, unsigned k);
 const char* okh_io_last_error();
-void* okh_read_file(const char* path, int by_magic);
+void* okh_read_file(const char* path, int mode);
 const uint8_t* okh_file_data(void* h);
 uint64_t okh_file_size(void* h);
 void okh_file_free(void* h);
@@ -142,13 +142,18 @@ struct Batch {
     uint64_t n_records() const { return okh_batch_n_records(h); }
 };
 
-// count.rs:56-66 / query.rs:45-52 (codec by extension) and build.rs:38-43 / classify.rs:143-151 (raw
-// bytes, needletail sniffs): read, decode, frame.  strip_ws: normalize(false) removes whitespace;
+// count.rs:56-66 / query.rs:45-52 (codec by extension, then needletail's sniff of what comes out) and
+// build.rs:38-43 / classify.rs:143-151 (raw bytes, needletail sniffs): read, decode, frame.  strip_ws: normalize(false) removes whitespace;
 // query keeps record.sequence() as it is.
 void load_fastx(const std::string& path, bool by_magic, bool strip_ws, const std::string& open_ctx,
                 const std::string& parse_ctx, Batch& out) {
-    void* f = okh_read_file(path.c_str(), by_magic ? 1 : 0);
-    if (!f) fail(open_ctx);
+    void* f = okh_read_file(path.c_str(), by_magic ? 1 : 2);
+    if (!f) {
+        // File::open fails inside get_decompressed_input_reader / get_buffered_file_reader (the "open" context); a corrupt
+        // compressed stream only shows when parse_fastx_reader reads its first bytes (the "parse" context)
+        const std::string why = okh_io_last_error();
+        fail(why.rfind("Failed to open", 0) == 0 ? open_ctx : parse_ctx);
+    }
     int st = 0;
     out.h = okh_fastx_parse(okh_file_data(f), okh_file_size(f), strip_ws ? 1 : 0, &st);
     okh_file_free(f);

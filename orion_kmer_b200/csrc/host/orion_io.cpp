@@ -1,10 +1,14 @@
 // orion_io.cpp -- file codecs and the .db format: the host-side rows f1/f2 of SURVEY.md section 8.
 // Part of liborion_host.so (g++, no CUDA).
 //
-//   okh_read_file     utils.rs:125-152 get_decompressed_input_reader (codec chosen by EXTENSION:
-//                     gz / xz / zst / zstd / plain)  and, with by_magic != 0, the way build.rs:38 and
-//                     classify.rs:143 read: raw bytes handed to needletail, which sniffs gzip / xz
-//                     magic itself (needletail 0.5.1 is locked without zstd)
+//   okh_read_file     mode 0: utils.rs:125-152 get_decompressed_input_reader (codec chosen by EXTENSION:
+//                     gz / xz / zst / zstd / plain) -- the .db files;
+//                     mode 1: the way build.rs:38 and classify.rs:143 read: raw bytes handed to needletail's
+//                     parse_fastx_reader, which sniffs gzip / bzip2 / xz magic itself (needletail 0.5.1 is
+//                     locked with bzip2, flate2 and xz2, Cargo.lock:584-591, and without zstd);
+//                     mode 2: count.rs:59-63 and query.rs:45-51: the extension codec FIRST, and what comes
+//                     out goes through the same parse_fastx_reader sniff (so reads.fastq.bz2, or a gzip
+//                     file without the .gz extension, are decoded there as well)
 //   okh_write_file    utils.rs:167-199 get_output_writer (gz level 6, xz preset 6, zstd level 3)
 //   okh_db_*          db_types.rs:8-14 KmerDbV2 { k: u8, references: HashMap<String, HashSet<u64>> } as
 //                     bincode 1.3.3 default options write it (build.rs:141, utils.rs:44): little-endian,
@@ -13,7 +17,7 @@
 //                     Entry and key order are arbitrary in the reference (hash iteration order); this
 //                     writer emits references in insertion order and keys ascending.
 //
-// zlib is linked.  liblzma / libzstd ship in this image as runtime libraries only (no headers), so
+// zlib is linked.  liblzma / libzstd / libbz2 ship in this image as runtime libraries only (no headers), so
 // they are loaded with dlopen and the few entry points used are declared here; a missing library
 // turns into the error "xz/zstd support unavailable".
 #include <dlfcn.h>
@@ -224,29 +228,97 @@ bool zstd_compress(const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
     return true;
 }
 
+// ---- bzip2 via libbz2.so.1.0 (bzlib.h's streaming decoder), input only: needletail sniffs it ----
+// Every stream of a multi-stream file (pbzip2 writes those) is decoded.  needletail 0.5.1 hands the reader to the
+// bzip2 crate; whether that stops after the first stream is not pinned by any reference test (parity unpinned).
+struct bz_stream_abi {
+    char* next_in; unsigned avail_in; unsigned total_in_lo32; unsigned total_in_hi32;
+    char* next_out; unsigned avail_out; unsigned total_out_lo32; unsigned total_out_hi32;
+    void* state;
+    void* (*bzalloc)(void*, int, int); void (*bzfree)(void*, void*); void* opaque;
+};
+enum { BZ_OK_ = 0, BZ_STREAM_END_ = 4 };
+struct Bz2Api {
+    int (*init)(bz_stream_abi*, int, int) = nullptr;
+    int (*run)(bz_stream_abi*) = nullptr;
+    int (*end)(bz_stream_abi*) = nullptr;
+    bool ok = false;
+};
+Bz2Api& bz2() {
+    static Bz2Api a = [] {
+        Bz2Api x;
+        void* h = dlopen("libbz2.so.1.0", RTLD_NOW);
+        if (!h) h = dlopen("libbz2.so.1", RTLD_NOW);
+        if (!h) h = dlopen("libbz2.so", RTLD_NOW);
+        if (h) {
+            x.init = (int (*)(bz_stream_abi*, int, int))dlsym(h, "BZ2_bzDecompressInit");
+            x.run = (int (*)(bz_stream_abi*))dlsym(h, "BZ2_bzDecompress");
+            x.end = (int (*)(bz_stream_abi*))dlsym(h, "BZ2_bzDecompressEnd");
+            x.ok = x.init && x.run && x.end;
+        }
+        return x;
+    }();
+    return a;
+}
+bool unbz2(const std::vector<uint8_t>& in, std::vector<uint8_t>& out) {
+    if (!bz2().ok) { io_fail("bzip2 support unavailable: libbz2.so.1.0 not found"); return false; }
+    std::vector<uint8_t> buf(1 << 20);
+    size_t in_pos = 0;
+    while (in_pos < in.size()) {                        // one decoder per stream
+        if (in_pos && (in.size() - in_pos < 3 || memcmp(in.data() + in_pos, "BZh", 3))) break;     // trailing bytes that are no stream: ignored, as bzip2 does
+        bz_stream_abi s{};
+        if (bz2().init(&s, 0, 0) != BZ_OK_) { io_fail("libbz2: decoder init failed"); return false; }
+        for (;;) {
+            if (s.avail_in == 0 && in_pos < in.size()) {
+                const size_t take = std::min<size_t>(in.size() - in_pos, 1u << 30);
+                s.next_in = (char*)const_cast<uint8_t*>(in.data() + in_pos); s.avail_in = (unsigned)take; in_pos += take;
+            }
+            s.next_out = (char*)buf.data(); s.avail_out = (unsigned)buf.size();
+            const int r = bz2().run(&s);
+            out.insert(out.end(), buf.data(), buf.data() + (buf.size() - s.avail_out));
+            if (r == BZ_STREAM_END_) { in_pos -= s.avail_in; break; }        // what follows is the next stream
+            if (r != BZ_OK_) { bz2().end(&s); io_fail("corrupt bzip2 stream"); return false; }
+            if (s.avail_in == 0 && in_pos >= in.size() && s.avail_out != 0) { bz2().end(&s); io_fail("truncated bzip2 stream"); return false; }
+        }
+        bz2().end(&s);
+    }
+    return true;
+}
+
+// needletail's parse_fastx_reader on a byte stream: gzip (1f 8b), bzip2 ("BZ") or xz (fd 37 7a 58 5a 00) magic
+// selects a decoder, anything else is taken as it is
+bool sniff_decode(std::vector<uint8_t>& raw, std::vector<uint8_t>& out) {
+    if (raw.size() >= 2 && raw[0] == 0x1f && raw[1] == 0x8b) return gunzip(raw, out);
+    if (raw.size() >= 2 && raw[0] == 'B' && raw[1] == 'Z') return unbz2(raw, out);
+    if (raw.size() >= 6 && !memcmp(raw.data(), "\xfd" "7zXZ\0", 6)) return unxz(raw, out);
+    out.swap(raw);
+    return true;
+}
+
 struct FileData { std::vector<uint8_t> bytes; };
 
 }  // namespace
 
 OKH_EXPORT const char* okh_io_last_error() { return g_io_err.c_str(); }
 
-// by_magic == 0: codec from the extension (count / query / load_kmer_db_v2).
-// by_magic != 0: plain read, then gzip / xz magic bytes decide (build / classify inputs through needletail).
-OKH_EXPORT void* okh_read_file(const char* path, int by_magic) {
+// mode 0: codec from the extension (load_kmer_db_v2).  mode 1: plain read, then needletail's magic sniff (build /
+// classify inputs).  mode 2: codec from the extension, then the sniff (count / query inputs).
+OKH_EXPORT void* okh_read_file(const char* path, int mode) {
     std::vector<uint8_t> raw;
-    if (!slurp(path, raw, by_magic ? "input file for buffered reading" : "input file")) return nullptr;
+    if (!slurp(path, raw, mode == 1 ? "input file for buffered reading" : "input file")) return nullptr;
     FileData* fd = new FileData();
     bool ok = true;
-    if (by_magic) {
-        if (raw.size() >= 2 && raw[0] == 0x1f && raw[1] == 0x8b) ok = gunzip(raw, fd->bytes);
-        else if (raw.size() >= 6 && !memcmp(raw.data(), "\xfd" "7zXZ\0", 6)) ok = unxz(raw, fd->bytes);
-        else fd->bytes.swap(raw);
+    if (mode == 1) {
+        ok = sniff_decode(raw, fd->bytes);
     } else {
         const std::string e = ext_of(path);
-        if (e == "gz") ok = gunzip(raw, fd->bytes);
-        else if (e == "xz") ok = unxz(raw, fd->bytes);
-        else if (e == "zst" || e == "zstd") ok = unzstd(raw, fd->bytes);
-        else fd->bytes.swap(raw);
+        std::vector<uint8_t> dec;
+        if (e == "gz") ok = gunzip(raw, dec);
+        else if (e == "xz") ok = unxz(raw, dec);
+        else if (e == "zst" || e == "zstd") ok = unzstd(raw, dec);
+        else dec.swap(raw);
+        if (ok && mode == 2) ok = sniff_decode(dec, fd->bytes);
+        else fd->bytes.swap(dec);
     }
     if (!ok) { delete fd; return nullptr; }
     return fd;

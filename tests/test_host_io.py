@@ -109,3 +109,37 @@ def test_db_same_name_overwrites_and_truncation_is_detected(tmp_path):
     open(p, "wb").write(struct.pack("<BQ", 4, 1) + struct.pack("<Q", 1 << 60))   # absurd length must not allocate
     with pytest.raises(ok.IoError, match="Failed to deserialize KmerDbV2"):
         ok.read_kmer_db(p)
+
+
+def test_bzip2_and_the_sniff_after_the_extension_codec(tmp_path):
+    """needletail 0.5.1 (Cargo.lock:580-591: bzip2, flate2, xz2) sniffs the magic bytes of whatever reader it is given.
+    build / classify give it the raw file; count / query give it the output of the extension codec (count.rs:59-63), so
+    a .bz2 input, or a gzip file under another name, is decoded for them as well.  .db files are never sniffed."""
+    import bz2
+    p = str(tmp_path / "genome.fa.bz2")
+    open(p, "wb").write(bz2.compress(INPUT1))
+    assert ok.read_file(p, by_magic=True) == INPUT1                 # build / classify
+    assert ok.read_file(p, fastx=True) == INPUT1                    # count / query: no codec for ".bz2", then the sniff
+    assert ok.read_file(p) == open(p, "rb").read()                  # a .db path: extension only
+    multi = str(tmp_path / "two_streams.bz2")                       # pbzip2 writes one stream per block
+    open(multi, "wb").write(bz2.compress(b">a\nACGT\n") + bz2.compress(b">b\nTTTT\n") + b"\0\0\0")
+    assert ok.read_file(multi, by_magic=True) == b">a\nACGT\n>b\nTTTT\n"
+    big = bytes(np.random.default_rng(3).integers(65, 70, 3_000_000, dtype=np.uint8))      # several 900 kB blocks, > one output buffer
+    open(p, "wb").write(bz2.compress(big))
+    assert ok.read_file(p, by_magic=True) == big
+    q = str(tmp_path / "reads.fastq")                               # gzip content, no .gz in the name
+    open(q, "wb").write(gzip.compress(INPUT1))
+    assert ok.read_file(q, fastx=True) == INPUT1 and ok.read_file(q) != INPUT1
+    twice = str(tmp_path / "twice.fa.gz")                           # the extension codec, then the sniff finds xz
+    open(twice, "wb").write(gzip.compress(lzma.compress(INPUT1)))
+    assert ok.read_file(twice, fastx=True) == INPUT1 and ok.read_file(twice) == lzma.compress(INPUT1)
+    for name in ("test_input1.fasta.gz", "test_input1.fasta.xz", "test_input1.fasta.zst"):       # the reference's fixtures: unchanged
+        assert ok.read_file(os.path.join(FIX, name), fastx=True) == INPUT1
+    bad = str(tmp_path / "bad.fa")
+    open(bad, "wb").write(b"BZh9 this is not bzip2 at all")
+    with pytest.raises(ok.IoError, match="bzip2"):
+        ok.read_file(bad, by_magic=True)
+    cut = str(tmp_path / "cut.bz2")
+    open(cut, "wb").write(bz2.compress(big)[:100_000])
+    with pytest.raises(ok.IoError, match="bzip2"):
+        ok.read_file(cut, fastx=True)
