@@ -130,3 +130,37 @@ def test_parallel_framing_equals_the_sequential_parser():
     for t in (1, 4):
         with pytest.raises(ok.FastxError):
             ok.parse_fastx(bad, threads=t)
+
+
+def test_framing_fuzz_against_the_oracle(oracle):
+    """4,000 random texts glued from the tokens that matter to the framing rules (record markers, '+' lines, LF / CRLF /
+    bare CR, blank lines, whitespace inside sequences, markers at odd places): the product's parser and the oracle's
+    needletail restatement must accept the same texts and frame the same records, sequentially and in pieces."""
+    import random
+    rnd = random.Random(20261019)
+    toks = [b">", b"@", b"+", b"\n", b"\n", b"\n", b"\r\n", b"ACGT", b"acgtn", b" ", b"\t", b"id1", b"GATTACA", b"!!!!", b"IIIIIII",
+            b"N", b"U", b"\n+\n", b"\n>", b"\n@", b"", b"\r"]
+    strip = bytes.maketrans(b"", b"")
+
+    def records(b):
+        return [(i, bytes(b.bases[int(b.offsets[j]):int(b.offsets[j + 1])])) for j, i in enumerate(b.ids)]
+
+    accepted = 0
+    for _ in range(4000):
+        text = rnd.choice([b">", b"@", b">", b"@", b""]) + b"".join(rnd.choice(toks) for _ in range(rnd.randint(0, 14)))
+        try:
+            want = oracle.parse_fastx(text)
+        except oracle.FastxError:
+            want = None
+        for threads in (1, 3):
+            try:
+                got = records(ok.parse_fastx(text, ok.RAW, threads=threads))
+                norm = records(ok.parse_fastx(text, ok.NORMALIZED, threads=threads))
+            except ok.FastxError:
+                got = norm = None
+            assert (got is None) == (want is None), (text, threads)
+            if want is not None:
+                assert got == want, (text, threads)
+                assert norm == [(i, s.translate(strip, b" \t\r\n")) for i, s in want], (text, threads)
+        accepted += want is not None
+    assert 400 < accepted < 3600          # both outcomes are exercised
