@@ -47,3 +47,23 @@ def test_no_cpu_fallback():
         ok.KmerCounter(21)
     assert e.value.code == ok.OK_ERR_NO_DEVICE
     assert "no CPU fallback" in str(e.value)
+
+
+def test_integration_md_binds_only_what_the_header_declares_with_the_same_arity():
+    """the Rust `extern "C"` block of INTEGRATION.md (what a maintainer of the reference crate would paste into
+    src/gpu.rs) must name functions of include/orion_gpu.h and give each the number of arguments the header gives it"""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index('extern "C" {'):doc.index("pub const OK_NORM_NORMALIZED")]
+    block = re.sub(r"//[^\n]*", "", block)
+    rust = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (ok_[a-z0-9_]+)\s*\((.*?)\)\s*->", block, flags=re.S)}
+    assert len(rust) >= 20
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "orion_gpu.h")).read(), flags=re.S)
+    c = {m.group(1): m.group(2) for m in re.finditer(r"\b(ok_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)}
+
+    def arity(args):
+        args = args.strip()
+        return 0 if args in ("", "void") else args.count(",") + 1
+
+    for name, args in rust.items():
+        assert name in c, f"{name} is bound in INTEGRATION.md but not declared in the header"
+        assert arity(args) == arity(c[name]), (name, args, c[name])
