@@ -53,6 +53,8 @@ typedef struct ok_set ok_set;         /* replaces HashSet<u64> of one reference,
 
 /* ---- lifecycle (commands/mod.rs:10-33 dispatch_command) ------------------------------- */
 int ok_init(const int* device_ids, int n_devices); /* n_devices must be 1; NULL -> device 0 */
+/* releases what the library keeps between calls (pooled set builders, page-locked result blocks, the sets' stream
+ * pool, an empty key slab).  Destroy every counter and set first: handles do not survive a shutdown. */
 int ok_shutdown(void);
 const char* ok_last_error(void);
 const char* ok_version(void);
