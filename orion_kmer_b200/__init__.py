@@ -195,6 +195,7 @@ def host_lib():
         L.okh_format_counts.restype = C.c_uint64
         L.okh_format_counts.argtypes = [vp, vp, C.c_uint64, C.c_uint, vp]
         L.okh_synth_genome.argtypes = [C.c_uint64, C.c_uint64, vp]
+        L.okh_json_f64.restype = C.c_int; L.okh_json_f64.argtypes = [C.c_double, C.c_char_p]
         L.okh_synth_reads.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                       C.c_uint32, C.c_uint32, vp, C.c_int]
         L.okh_synth_mutate.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, vp]
@@ -261,6 +262,13 @@ def read_file(path, by_magic=False, fastx=False):
         return C.string_at(H.okh_file_data(h), n) if n else b""
     finally:
         H.okh_file_free(h)
+
+
+def json_f64(v):
+    """serde_json's text of an f64 (the ratios in the compare / classify reports): ryu's shortest round-trip digits"""
+    b = C.create_string_buffer(48)
+    n = host_lib().okh_json_f64(float(v), b)
+    return b.raw[:n].decode()
 
 
 def write_file(path, data, by_extension=True):

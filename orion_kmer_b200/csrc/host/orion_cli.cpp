@@ -34,6 +34,7 @@ const uint64_t* okh_batch_id_offsets(void* h);
 void okh_batch_free(void* h);
 uint64_t okh_format_counts(const uint64_t* kmers, const uint64_t* counts, uint64_t n, unsigned k, char* out);
 uint64_t okh_format_counts_size(const uint64_t* counts, uint64_t n, unsigned k);
+int okh_json_f64(double v, char* out);
 const char* okh_io_last_error();
 void* okh_read_file(const char* path, int mode);
 const uint8_t* okh_file_data(void* h);
@@ -216,21 +217,10 @@ std::string json_str(const std::string& s) {
     }
     return o + "\"";
 }
-std::string json_f64(double v) {      // shortest representation that round-trips, always with a fraction or exponent (ryu)
-    if (!std::isfinite(v)) return "null";
-    char b[40];
-    for (int prec = 1; prec <= 17; ++prec) { snprintf(b, sizeof b, "%.*g", prec, v); if (strtod(b, nullptr) == v) break; }
-    std::string s = b;
-    const size_t e = s.find('e');
-    if (e != std::string::npos) {        // 1e-07 -> 1e-7
-        std::string mant = s.substr(0, e), ex = s.substr(e + 1);
-        const bool neg = !ex.empty() && ex[0] == '-';
-        if (!ex.empty() && (ex[0] == '-' || ex[0] == '+')) ex = ex.substr(1);
-        while (ex.size() > 1 && ex[0] == '0') ex = ex.substr(1);
-        return mant + "e" + (neg ? "-" : "") + ex;
-    }
-    if (s.find('.') == std::string::npos) s += ".0";
-    return s;
+std::string json_f64(double v) {      // serde_json's text of an f64 (ryu's shortest digits and layout): liborion_host.so
+    char b[48];
+    const int n = okh_json_f64(v, b);
+    return std::string(b, (size_t)n);
 }
 struct Json {                           // objects and arrays only need what the two reports use
     std::string out; int depth = 0; std::vector<bool> first;

@@ -6,12 +6,15 @@
 //                         normalize(false)  (count.rs:63-72, build.rs:42-48, query.rs:51-66)
 //                         -> the C-ABI batch layout (bases + offsets) and the record ids
 //   okh_format_counts     count.rs:127-135  "KMER\tcount\n"
+//   okh_json_f64          serde_json's (ryu) text of an f64: the ratios of the compare / classify reports
 //   okh_synth_*           seeded synthetic workloads of SURVEY.md section 8(d) (SplitMix64)
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -310,6 +313,44 @@ OKH_EXPORT uint64_t okh_format_counts(const uint64_t* kmers, const uint64_t* cou
         });
     for (auto& x : th) x.join();
     return start[nt];
+}
+
+
+// ---- serde_json's f64 text (compare.rs:16-25, classify.rs:22-52 reports) ----------------------------------------
+// serde_json prints a finite f64 through the ryu crate: the SHORTEST decimal digits that round-trip, laid out by
+// ryu's pretty printer -- digits D (length L), value = D x 10^k, kk = L + k:
+//   k >= 0 and kk <= 16   ->  D followed by k zeros and ".0"           100.0   1000000000000000.0
+//   0 < kk <= 16          ->  D with a point after kk digits            12.34   0.5 is the next case
+//   -5 < kk <= 0          ->  "0." then -kk zeros then D                0.5     0.00001234
+//   otherwise             ->  d[.ddd]e<kk-1>                            1e16    1.234e-7   1e-6
+// Non-finite values print as null.  The digits come from the smallest precision of "%.*e" that reads back to the
+// same double (the correctly rounded shortest form; ryu picks the same digits outside rare tie cases).
+// out: at least 32 bytes.  Returns the length written (no terminator counted).
+OKH_EXPORT int okh_json_f64(double v, char* out) {
+    if (!std::isfinite(v)) { memcpy(out, "null", 5); return 4; }
+    char b[48];
+    int prec = 1;
+    for (; prec <= 17; ++prec) { snprintf(b, sizeof b, "%.*e", prec - 1, v); if (strtod(b, nullptr) == v) break; }
+    // b = [-]d[.ddd]e[+-]XX
+    const char* p = b;
+    std::string s;
+    if (*p == '-') { s += '-'; ++p; }
+    std::string digits;
+    for (; *p && *p != 'e'; ++p) if (*p != '.') digits += *p;
+    const int x = atoi(p + 1);                                    // decimal exponent of the first digit
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    if (digits == "0") { s += "0.0"; memcpy(out, s.c_str(), s.size() + 1); return (int)s.size(); }
+    const int L = (int)digits.size(), kk = x + 1, k = kk - L;
+    if (k >= 0 && kk <= 16) { s += digits; s.append((size_t)k, '0'); s += ".0"; }
+    else if (kk > 0 && kk <= 16) { s += digits.substr(0, (size_t)kk); s += '.'; s += digits.substr((size_t)kk); }
+    else if (kk > -5 && kk <= 0) { s += "0."; s.append((size_t)(-kk), '0'); s += digits; }
+    else {
+        s += digits[0];
+        if (L > 1) { s += '.'; s += digits.substr(1); }
+        s += 'e'; s += std::to_string(kk - 1);
+    }
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
 }
 
 // ---- synthetic workloads: SplitMix64, 2-bit fields low bits first -> ACGT ----

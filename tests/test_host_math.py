@@ -335,3 +335,35 @@ def test_ava_keyed_algorithm_replayed_on_the_host_matches_pairwise_intersections
     for i in range(n):
         for j in range(i + 1, n):
             assert inter[i, j] == len(np.intersect1d(sets[i], sets[j], assume_unique=True)), (i, j)
+
+
+# ------------------------------------------------------------- serde_json's f64 text in the compare / classify reports --
+def test_json_f64_follows_ryu_layout_and_round_trips():
+    """compare.rs:16-25 / classify.rs:22-52 serialise their ratios with serde_json, which prints an f64 through ryu: the
+    shortest digits that round-trip, in ryu's layout (plain decimals for 1e-5 <= |v| < 1e16, d.ddde<exp> outside, always
+    a fraction or an exponent).  Known layouts, then 20,000 random doubles: the text reads back to the same double and
+    carries the digits of the shortest representation (Python's repr)."""
+    import random
+    import struct
+    want = {1.0: "1.0", 0.0: "0.0", -0.0: "-0.0", 0.5: "0.5", 10.0: "10.0", 20.0: "20.0", 100.0: "100.0", 12.5: "12.5",
+            1 / 3: "0.3333333333333333", 2 / 3: "0.6666666666666666", 0.1: "0.1", 0.30000000000000004: "0.30000000000000004",
+            1e15: "1000000000000000.0", 1e16: "1e16", 1.2345678901234568e17: "1.2345678901234568e17", 123456789.125: "123456789.125",
+            0.0001: "0.0001", 1e-5: "0.00001", 1.234e-5: "0.00001234", 1e-6: "1e-6", 1.234e-7: "1.234e-7", 5e-324: "5e-324",
+            1.7976931348623157e308: "1.7976931348623157e308", -2.5: "-2.5", -1e-7: "-1e-7",
+            float("nan"): "null", float("inf"): "null", float("-inf"): "null"}
+    for v, text in want.items():
+        assert ok.json_f64(v) == text, (v, ok.json_f64(v), text)
+
+    def digits(s):
+        return s.lstrip("-").split("e")[0].replace(".", "").lstrip("0").rstrip("0") or "0"
+    rnd = random.Random(11)
+    for i in range(20_000):
+        v = (rnd.random(), rnd.randint(0, 10 ** 7) / rnd.randint(1, 10 ** 7), rnd.random() * 10.0 ** rnd.randint(-30, 30),
+             struct.unpack("<d", struct.pack("<Q", rnd.getrandbits(64)))[0])[i % 4]
+        if v != v or abs(v) == float("inf"):
+            continue
+        t = ok.json_f64(v)
+        assert float(t) == v and digits(t) == digits(repr(v)), (v, t)
+        assert ("." in t or "e" in t) and not t.endswith(".")
+        if 1e-5 <= abs(v) < 1e16:
+            assert "e" not in t, (v, t)
