@@ -345,13 +345,13 @@ def test_json_f64_follows_ryu_layout_and_round_trips():
     carries the digits of the shortest representation (Python's repr)."""
     import random
     import struct
-    want = {1.0: "1.0", 0.0: "0.0", -0.0: "-0.0", 0.5: "0.5", 10.0: "10.0", 20.0: "20.0", 100.0: "100.0", 12.5: "12.5",
-            1 / 3: "0.3333333333333333", 2 / 3: "0.6666666666666666", 0.1: "0.1", 0.30000000000000004: "0.30000000000000004",
-            1e15: "1000000000000000.0", 1e16: "1e16", 1.2345678901234568e17: "1.2345678901234568e17", 123456789.125: "123456789.125",
-            0.0001: "0.0001", 1e-5: "0.00001", 1.234e-5: "0.00001234", 1e-6: "1e-6", 1.234e-7: "1.234e-7", 5e-324: "5e-324",
-            1.7976931348623157e308: "1.7976931348623157e308", -2.5: "-2.5", -1e-7: "-1e-7",
-            float("nan"): "null", float("inf"): "null", float("-inf"): "null"}
-    for v, text in want.items():
+    want = [(1.0, "1.0"), (0.0, "0.0"), (-0.0, "-0.0"), (0.5, "0.5"), (10.0, "10.0"), (20.0, "20.0"), (100.0, "100.0"), (12.5, "12.5"),
+            (1 / 3, "0.3333333333333333"), (2 / 3, "0.6666666666666666"), (0.1, "0.1"), (0.30000000000000004, "0.30000000000000004"),
+            (1e15, "1000000000000000.0"), (1e16, "1e16"), (1.2345678901234568e17, "1.2345678901234568e17"),
+            (123456789.125, "123456789.125"), (0.0001, "0.0001"), (1e-5, "0.00001"), (1.234e-5, "0.00001234"), (1e-6, "1e-6"),
+            (1.234e-7, "1.234e-7"), (5e-324, "5e-324"), (1.7976931348623157e308, "1.7976931348623157e308"), (-2.5, "-2.5"),
+            (-1e-7, "-1e-7"), (float("nan"), "null"), (float("inf"), "null"), (float("-inf"), "null")]
+    for v, text in want:
         assert ok.json_f64(v) == text, (v, ok.json_f64(v), text)
 
     def digits(s):
