@@ -1102,7 +1102,9 @@ k_part_count(unsigned long long* __restrict__ src, const unsigned* __restrict__ 
             __syncthreads();
         }
         for (unsigned base = seed_keys; base < n; base += 4 * OK_C2_THREADS) {
-            if (may_overflow && *(volatile unsigned*)&sm.n_new > C::LIMIT) break;   // warp-uniform (one shared word)
+            // (a vote, not a bare read of the shared word: other warps bump n_new meanwhile, and the full-mask ballots below
+            // need every lane of the warp to take the same way out whether or not the lanes read it in the same instant)
+            if (may_overflow && __any_sync(OK_FULL, *(volatile unsigned*)&sm.n_new > C::LIMIT)) break;
             unsigned long long kk[4], cur[4]; unsigned hs[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {

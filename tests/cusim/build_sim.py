@@ -54,7 +54,7 @@ def build_library(dst, opt="-O1"):
     rewrite_headers(dst)
     text = open(os.path.join(CSRC, "orion_gpu.cu")).read()
     text = _sub(r"kern<<<\(grid\), \(block\), \(smem\), \(stream\)>>>\(__VA_ARGS__\);",
-                "cusim::launch((grid), (block), [&] { kern(__VA_ARGS__); });", text, "LAUNCH macro")
+                "cusim::launch((grid), (block), [&] { kern(__VA_ARGS__); }, #kern);", text, "LAUNCH macro")
     assert "<<<" not in text
     text = _sub(r'#include "setops.cuh"\n', '#include "setops.cuh"\n#include "sim_globals.h"\n', text, "include list", count=1)
     src = os.path.join(dst, "orion_gpu_sim.cpp")

@@ -15,7 +15,10 @@
 #pragma once
 #include <pthread.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <math.h>
 
@@ -61,6 +64,9 @@ static inline unsigned long min(unsigned long a, unsigned b) { return a < b ? a 
 static inline unsigned long long min(unsigned a, unsigned long long b) { return a < b ? a : b; }
 static inline unsigned long long min(unsigned long long a, unsigned b) { return a < b ? a : b; }
 
+inline thread_local uint3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
 namespace cusim {
 // __syncthreads() is a pthread barrier of ALL the block's threads.  On the device a thread that has returned from the
 // kernel counts as arrived at every later barrier; here such a thread stays behind as a ghost that keeps arriving until
@@ -77,15 +83,25 @@ struct Block {
     pthread_mutex_t named_mu = PTHREAD_MUTEX_INITIALIZER;
 };
 inline thread_local long bar_gen = 0;
+// where every thread of the running block is waiting (for the watchdog's report of a deadlock)
+inline void* wait_site[1024];
+inline int wait_kind[1024];                     // 0 running, 1 __syncthreads, 2 warp-level sync, 3 returned (ghost), 4 named barrier
+inline unsigned long progress = 0;              // bumped at every barrier passed (atomic)
+struct Waiting {
+    unsigned t;
+    Waiting(int kind, void* site) : t(threadIdx.x) { wait_site[t] = site; __atomic_store_n(&wait_kind[t], kind, __ATOMIC_SEQ_CST); }
+    ~Waiting() { __atomic_store_n(&wait_kind[t], 0, __ATOMIC_SEQ_CST); __atomic_fetch_add(&progress, 1ul, __ATOMIC_RELAXED); }
+};
 inline Block*& cur() { static Block* b = nullptr; return b; }
 alignas(128) inline unsigned char dyn_smem[232448];
 }  // namespace cusim
 
-inline thread_local uint3 threadIdx, blockIdx;
-inline dim3 blockDim, gridDim;
 
-static inline void __syncthreads() { pthread_barrier_wait(&cusim::cur()->bar); ++cusim::bar_gen; }
-static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { pthread_barrier_wait(&cusim::cur()->warp_bar[threadIdx.x >> 5]); }
+static inline __attribute__((always_inline)) void __syncthreads() {
+    cusim::Waiting w(1, __builtin_extract_return_addr(__builtin_return_address(0)));
+    pthread_barrier_wait(&cusim::cur()->bar); ++cusim::bar_gen;
+}
+static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { cusim::Waiting w(2, __builtin_return_address(0)); pthread_barrier_wait(&cusim::cur()->warp_bar[threadIdx.x >> 5]); }
 
 namespace cusim {
 inline void named_barrier(unsigned n) {
@@ -99,6 +115,7 @@ inline void named_barrier(unsigned n) {
 inline unsigned long long exchange(unsigned long long v, unsigned src) {
     Block* b = cur();
     const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    Waiting wt(2, __builtin_return_address(0));
     b->slots[w * 32 + lane] = v;
     pthread_barrier_wait(&b->warp_bar[w]);
     const unsigned long long r = b->slots[w * 32 + (src & 31u)];
@@ -122,6 +139,7 @@ static inline unsigned __ballot_sync(unsigned m, int pred) {
     unsigned r = 0;
     cusim::Block* b = cusim::cur();
     const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    cusim::Waiting wt(2, __builtin_return_address(0));
     b->slots[w * 32 + lane] = pred ? 1ull : 0ull;
     pthread_barrier_wait(&b->warp_bar[w]);
     for (unsigned i = 0; i < 32; ++i) r |= (unsigned)b->slots[w * 32 + i] << i;
@@ -183,8 +201,10 @@ namespace cusim {
 // kern<<<grid, block, smem>>>(args...): blocks one after the other, the threads of a block side by side
 inline pthread_mutex_t launch_mu = PTHREAD_MUTEX_INITIALIZER;
 struct LaunchLock { LaunchLock() { pthread_mutex_lock(&launch_mu); } ~LaunchLock() { pthread_mutex_unlock(&launch_mu); } };
-template <class F> void launch(dim3 grid, unsigned block, F body) {
-    LaunchLock one_at_a_time;                  // (host threads of the library may launch side by side: ok_sets_build_many)
+template <class F> void launch(dim3 grid, unsigned block, F body, const char* name = "kernel") {
+    LaunchLock one_at_a_time;
+    static const bool trace = getenv("CUSIM_TRACE") != nullptr;        // CUSIM_TRACE=1: every launch on stderr (which kernel hangs?)
+    if (trace) fprintf(stderr, "[cusim] %s <<<(%u,%u), %u>>>\n", name, grid.x, grid.y, block);                  // (host threads of the library may launch side by side: ok_sets_build_many)
     gridDim = grid; blockDim = dim3(block);
     // one set of `block` OS threads per launch; they run the blocks of the grid one after the other, together
     Block b;
@@ -197,6 +217,8 @@ template <class F> void launch(dim3 grid, unsigned block, F body) {
     pthread_barrier_t rearm;
     pthread_barrier_init(&rearm, nullptr, block);
     cur() = &b;
+    int launch_over = 0;
+    for (unsigned t = 0; t < block; ++t) wait_kind[t] = 0;
     std::vector<std::thread> th;
     th.reserve(block);
     for (unsigned t = 0; t < block; ++t)
@@ -207,6 +229,7 @@ template <class F> void launch(dim3 grid, unsigned block, F body) {
                     bar_gen = 0;
                     body();
                     if (__atomic_add_fetch(&b.finished, 1u, __ATOMIC_SEQ_CST) == block) __atomic_store_n(&b.done_at, bar_gen + 1, __ATOMIC_SEQ_CST);
+                    __atomic_store_n(&wait_kind[t], 3, __ATOMIC_SEQ_CST);
                     for (;;) {                                  // ghost: arrive at the barriers the others still run into
                         pthread_barrier_wait(&b.bar); ++bar_gen;
                         if (__atomic_load_n(&b.done_at, __ATOMIC_SEQ_CST) == bar_gen) break;
@@ -219,7 +242,30 @@ template <class F> void launch(dim3 grid, unsigned block, F body) {
                     pthread_barrier_wait(&rearm);
                 }
         });
+    // watchdog: no barrier passed and no thread finished for a while = a deadlock; say where the threads wait
+    std::thread watchdog([&] {
+        unsigned long last = ~0ul; int still = 0;
+        const char* ev = getenv("CUSIM_WATCHDOG_S");
+        const int limit = ev ? atoi(ev) : 120;
+        while (!__atomic_load_n(&launch_over, __ATOMIC_SEQ_CST)) {
+            timespec ts{1, 0}; nanosleep(&ts, nullptr);
+            const unsigned long now = __atomic_load_n(&progress, __ATOMIC_RELAXED);
+            bool running = false;
+            for (unsigned t = 0; t < block; ++t) running |= __atomic_load_n(&wait_kind[t], __ATOMIC_SEQ_CST) == 0;
+            if (now != last || running) { last = now; still = 0; continue; }
+            if (++still < limit) continue;
+            fprintf(stderr, "[cusim] DEADLOCK in %s <<<(%u,%u), %u>>>: every thread has been waiting for %d s\n", name, grid.x, grid.y, block, limit);
+            for (unsigned t = 0; t < block; ++t)
+                fprintf(stderr, "  thread %4u  %s  called from %p\n", t,
+                        wait_kind[t] == 1 ? "__syncthreads" : wait_kind[t] == 2 ? "warp-level sync" : wait_kind[t] == 3 ? "returned (ghost)" : "named barrier",
+                        wait_site[t]);
+            fflush(stderr);
+            abort();
+        }
+    });
     for (auto& x : th) x.join();
+    __atomic_store_n(&launch_over, 1, __ATOMIC_SEQ_CST);
+    watchdog.join();
     pthread_barrier_destroy(&b.bar);
     pthread_barrier_destroy(&rearm);
     for (auto& wb : b.warp_bar) pthread_barrier_destroy(&wb);
