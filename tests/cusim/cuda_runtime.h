@@ -84,13 +84,12 @@ struct Block {
 };
 inline thread_local long bar_gen = 0;
 // where every thread of the running block is waiting (for the watchdog's report of a deadlock)
-inline void* wait_site[1024];
-inline int wait_kind[1024];                     // 0 running, 1 __syncthreads, 2 warp-level sync, 3 returned (ghost), 4 named barrier
-inline unsigned long progress = 0;              // bumped at every barrier passed (atomic)
+struct alignas(64) WaitSlot { void* site; int kind; unsigned long passed; };     // one cache line per thread
+inline WaitSlot wait_slot[1024];                // kind: 0 running, 1 __syncthreads, 2 warp-level sync, 3 returned (ghost)
 struct Waiting {
-    unsigned t;
-    Waiting(int kind, void* site) : t(threadIdx.x) { wait_site[t] = site; __atomic_store_n(&wait_kind[t], kind, __ATOMIC_SEQ_CST); }
-    ~Waiting() { __atomic_store_n(&wait_kind[t], 0, __ATOMIC_SEQ_CST); __atomic_fetch_add(&progress, 1ul, __ATOMIC_RELAXED); }
+    WaitSlot& s;
+    Waiting(int kind, void* site) : s(wait_slot[threadIdx.x]) { s.site = site; __atomic_store_n(&s.kind, kind, __ATOMIC_RELAXED); }
+    ~Waiting() { __atomic_store_n(&s.kind, 0, __ATOMIC_RELAXED); __atomic_store_n(&s.passed, s.passed + 1, __ATOMIC_RELAXED); }
 };
 inline Block*& cur() { static Block* b = nullptr; return b; }
 alignas(128) inline unsigned char dyn_smem[232448];
@@ -218,7 +217,7 @@ template <class F> void launch(dim3 grid, unsigned block, F body, const char* na
     pthread_barrier_init(&rearm, nullptr, block);
     cur() = &b;
     int launch_over = 0;
-    for (unsigned t = 0; t < block; ++t) wait_kind[t] = 0;
+    for (unsigned t = 0; t < block; ++t) { wait_slot[t].kind = 0; wait_slot[t].passed = 0; }
     std::vector<std::thread> th;
     th.reserve(block);
     for (unsigned t = 0; t < block; ++t)
@@ -229,7 +228,7 @@ template <class F> void launch(dim3 grid, unsigned block, F body, const char* na
                     bar_gen = 0;
                     body();
                     if (__atomic_add_fetch(&b.finished, 1u, __ATOMIC_SEQ_CST) == block) __atomic_store_n(&b.done_at, bar_gen + 1, __ATOMIC_SEQ_CST);
-                    __atomic_store_n(&wait_kind[t], 3, __ATOMIC_SEQ_CST);
+                    __atomic_store_n(&wait_slot[t].kind, 3, __ATOMIC_RELAXED);
                     for (;;) {                                  // ghost: arrive at the barriers the others still run into
                         pthread_barrier_wait(&b.bar); ++bar_gen;
                         if (__atomic_load_n(&b.done_at, __ATOMIC_SEQ_CST) == bar_gen) break;
@@ -242,23 +241,24 @@ template <class F> void launch(dim3 grid, unsigned block, F body, const char* na
                     pthread_barrier_wait(&rearm);
                 }
         });
-    // watchdog: no barrier passed and no thread finished for a while = a deadlock; say where the threads wait
+    // watchdog: no barrier passed and no thread running for a while = a deadlock; say where the threads wait
     std::thread watchdog([&] {
         unsigned long last = ~0ul; int still = 0;
         const char* ev = getenv("CUSIM_WATCHDOG_S");
-        const int limit = ev ? atoi(ev) : 120;
+        const int limit = (ev ? atoi(ev) : 120) * 50;                    // in ticks of 20 ms
         while (!__atomic_load_n(&launch_over, __ATOMIC_SEQ_CST)) {
-            timespec ts{1, 0}; nanosleep(&ts, nullptr);
-            const unsigned long now = __atomic_load_n(&progress, __ATOMIC_RELAXED);
-            bool running = false;
-            for (unsigned t = 0; t < block; ++t) running |= __atomic_load_n(&wait_kind[t], __ATOMIC_SEQ_CST) == 0;
+            timespec ts{0, 20000000}; nanosleep(&ts, nullptr);
+            unsigned long now = 0; bool running = false;
+            for (unsigned t = 0; t < block; ++t) {
+                now += __atomic_load_n(&wait_slot[t].passed, __ATOMIC_RELAXED);
+                running |= __atomic_load_n(&wait_slot[t].kind, __ATOMIC_RELAXED) == 0;
+            }
             if (now != last || running) { last = now; still = 0; continue; }
             if (++still < limit) continue;
-            fprintf(stderr, "[cusim] DEADLOCK in %s <<<(%u,%u), %u>>>: every thread has been waiting for %d s\n", name, grid.x, grid.y, block, limit);
+            fprintf(stderr, "[cusim] DEADLOCK in %s <<<(%u,%u), %u>>>: every thread has been waiting for %d s\n", name, grid.x, grid.y, block, limit / 50);
             for (unsigned t = 0; t < block; ++t)
-                fprintf(stderr, "  thread %4u  %s  called from %p\n", t,
-                        wait_kind[t] == 1 ? "__syncthreads" : wait_kind[t] == 2 ? "warp-level sync" : wait_kind[t] == 3 ? "returned (ghost)" : "named barrier",
-                        wait_site[t]);
+                fprintf(stderr, "  thread %4u  %s\n", t,
+                        wait_slot[t].kind == 1 ? "__syncthreads" : wait_slot[t].kind == 2 ? "warp-level sync (shuffle / vote / __syncwarp)" : "returned from the kernel (ghost)");
             fflush(stderr);
             abort();
         }
