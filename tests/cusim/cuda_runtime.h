@@ -9,6 +9,10 @@
 //                                hang or corrupt on the device)
 //   atomicCAS / atomicAdd / atomicOr / atomicExch            GCC __atomic builtins (sequentially consistent)
 //   __shared__                   `static`: one block runs at a time; dynamic shared memory is one global buffer
+// A thread that returns from the kernel stays behind as a ghost that keeps arriving at the block's barriers (exited threads
+// count as arrived on the device).  CUSIM_TRACE=1 prints every launch; a watchdog (CUSIM_WATCHDOG_S, default 120 s) aborts
+// a launch in which every thread has been waiting that long and says where each one waits (a split warp: some lanes at a
+// full-mask vote, the others at __syncthreads -- how k_part_count's bare read of a shared counter was found).
 // Not modelled: the memory model beyond sequential consistency, warp-synchronous execution outside the *_sync calls,
 // bank conflicts, occupancy.  What it does check: indexing, barrier placement, the arithmetic -- and, built with
 // -fsanitize=thread or address, data races between barriers and out-of-bounds accesses in the kernels' own source.
